@@ -1,0 +1,297 @@
+/*
+ * ra_engine.h -- C ABI of the B200 batched multi-Raft engine.
+ *
+ * Drop-in boundary: the call from ra_server_proc into the pure Raft core,
+ *   ra_server:handle_leader(Msg, State)            src/ra_server_proc.erl:1354
+ *   ra_server:RaftState(Msg, State)                src/ra_server_proc.erl:1383
+ * both returning {NextRaftState, NewState, Effects} (src/ra_server.erl:520-521).
+ * The reference has no FFI for this path (it is 100 % Erlang); the entry points
+ * below are what a dirty-NIF shim binds.  Every struct is
+ * plain-old-data, little endian, no pointers inside, no torch types.
+ *
+ * Vocabulary follows the reference: member, peer, term, index, commit_index,
+ * last_applied, last_written, append_entries_rpc (AER), pre_vote, ...
+ *
+ * A "row" is one Raft member (one ra_server_state()).  Members of group g are
+ * rows  slot * n_groups + g  for slot in [0, n_members): slot-major, so that
+ * the same slot of consecutive groups is contiguous in every HBM column.
+ */
+#ifndef RA_ENGINE_H
+#define RA_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RA_MAX_MEMBERS   8      /* members per group (slots 0..7)                    */
+#define RA_MAX_RUNS      8      /* term runs kept per member log view                */
+#define RA_NO_SLOT       0xFFu  /* 'undefined' for leader_id / voted_for             */
+#define RA_UNDEF_TERM    UINT64_MAX /* fetch_term -> undefined                         */
+#define RA_MBOX_DEPTH    4      /* per (src,dst) messages per step in routed mode    */
+#define RA_LOCAL_CAP     4      /* host ("local") events per row per step            */
+#define RA_MSG_CAP       16     /* outgoing RPC records per row per step             */
+#define RA_NOTE_CAP      8      /* host notes per row per step                       */
+
+/* ra_state(), src/ra_server.erl:116-119 (the five states on the hot path) */
+enum ra_role {
+    RA_FOLLOWER        = 0,
+    RA_CANDIDATE       = 1,
+    RA_PRE_VOTE        = 2,
+    RA_LEADER          = 3,
+    RA_AWAIT_CONDITION = 4
+};
+
+/* ra_membership(), src/ra.hrl:58 */
+enum ra_membership {
+    RA_VOTER      = 0,
+    RA_PROMOTABLE = 1,
+    RA_NON_VOTER  = 2,
+    RA_UNKNOWN    = 3
+};
+
+/* ra_peer_status(), src/ra.hrl:52-56 (pids/attempt counts stay on the host) */
+enum ra_peer_status {
+    RA_PEER_NORMAL           = 0,
+    RA_PEER_SENDING_SNAPSHOT = 1,
+    RA_PEER_SNAPSHOT_BACKOFF = 2,
+    RA_PEER_SUSPENDED        = 3,
+    RA_PEER_DISCONNECTED     = 4
+};
+
+/* ra_msg(), src/ra_server.erl:144-164 -- the subset evaluated on the GPU */
+enum ra_event_type {
+    RA_EV_NONE              = 0,
+    RA_EV_AER               = 1,  /* #append_entries_rpc{}      src/ra.hrl:122-128 */
+    RA_EV_AER_REPLY         = 2,  /* {Peer,#append_entries_reply{}}      :130-141 */
+    RA_EV_REQUEST_VOTE      = 3,  /* #request_vote_rpc{}                  :144-148 */
+    RA_EV_REQUEST_VOTE_RES  = 4,  /* #request_vote_result{}               :151-153 */
+    RA_EV_PRE_VOTE          = 5,  /* #pre_vote_rpc{}                      :156-164 */
+    RA_EV_PRE_VOTE_RES      = 6,  /* #pre_vote_result{}                   :166-169 */
+    RA_EV_WRITTEN           = 7,  /* {ra_log_event,{written,Term,Seq}}  ra_log.erl:73 */
+    RA_EV_COMMAND           = 8,  /* {command,_} / {commands,_} ra_server.erl:644-729 */
+    RA_EV_ELECTION_TIMEOUT  = 9,  /* election_timeout                              */
+    RA_EV_AWAIT_COND_TIMEOUT= 10, /* await_condition_timeout                       */
+    RA_EV_PIPELINE_RPCS     = 11, /* pipeline_rpcs            ra_server.erl:784-792 */
+    RA_EV_TICK              = 12  /* leader tick -> make_rpcs ra_server_proc.erl:610 */
+};
+
+/* ra_event.flags */
+#define RA_EVF_NOOP        0x01u /* COMMAND: entry is {noop,_,_} (forces pipelining, :674-679) */
+#define RA_EVF_NEXT_EVENT  0x02u /* out only, pure mode: {next_event, Msg} addressed to self   */
+#define RA_EVF_INFO        0x08u /* next_event type was `info` (pipeline_rpcs)                 */
+
+/*
+ * One 64-byte wire record.  Used for (a) events fed to the engine and (b) RPC
+ * records the engine emits (they are already addressed: `row` = destination).
+ *
+ *  type            from_slot   term      a               b              c              d            e
+ *  AER             leader      rpc term  prev_log_index  prev_log_term  leader_commit  entry term   term of the entries after the
+ *                                                                                                    first n1 (used when n1 != 0)
+ *                  n = number of entries (prev+1 .. prev+n); n1 = 0: all have term d, else the first
+ *                  n1 have term d and the other n-n1 have term e (an AER spans <= 2 term runs)
+ *  AER_REPLY       replier     term      next_index      last_index     last_term      success(0/1)
+ *  REQUEST_VOTE    candidate   term      last_log_index  last_log_term
+ *  REQUEST_VOTE_RES voter      term      -               -              -              granted(0/1)
+ *  PRE_VOTE        candidate   term      last_log_index  last_log_term  token          version | machine_version<<32
+ *  PRE_VOTE_RES    voter       term      -               -              token          granted(0/1)
+ *  WRITTEN         -           term      from            to                                        (Seq = [{from,to}])
+ *  COMMAND         -           -         -               -              -              -            n = number of commands
+ */
+typedef struct ra_event {
+    uint32_t row;        /* destination member row                                  */
+    uint8_t  type;       /* enum ra_event_type                                      */
+    uint8_t  from_slot;  /* sender's slot in the group, RA_NO_SLOT for host events  */
+    uint8_t  flags;      /* RA_EVF_*                                                */
+    uint8_t  _pad;
+    uint16_t n;          /* entry / command count                                   */
+    uint16_t n1;         /* AER: entries in the first term run (0 = all)            */
+    uint32_t seq;        /* out records: k-th record of its row in this step        */
+    uint64_t term;
+    uint64_t a, b, c, d;
+    uint64_t e;
+} ra_event;
+
+/* Host notes: what ra_server_proc must do that the engine cannot (32 bytes). */
+enum ra_note_type {
+    RA_NOTE_NONE       = 0,
+    RA_NOTE_WAL_APPEND = 1, /* a=from b=to c=term of `to`: entries now in the log view;
+                               host writes payloads (ra_log:append / ra_log:write)        */
+    RA_NOTE_TRUNCATE   = 2, /* a=new last index b=its term   (ra_log:set_last_index)      */
+    RA_NOTE_COMMIT     = 3, /* a=old commit_index b=new      ({aux,eval}, :3611-3614)     */
+    RA_NOTE_APPLY      = 4, /* a=first b=last index to run through ra_machine:apply/3     */
+    RA_NOTE_STATUS     = 5, /* end-of-step summary: aux=flags, a=term, b=voted_for|leader<<8|
+                               role_old<<16|role_new<<24, c=detail                         */
+    RA_NOTE_SEND_SNAPSHOT = 6, /* a=peer slot b=snapshot index  ({send_snapshot,..} :2395) */
+    RA_NOTE_NOT_LEADER = 7  /* COMMAND reached a non-leader: a=n commands b=leader slot   */
+};
+
+/* RA_NOTE_STATUS aux flags */
+#define RA_ST_TERM_VOTE_CHANGED   0x0001u /* update_term_and_voted_for persisted (:3014-3031)    */
+#define RA_ST_ROLE_CHANGED        0x0002u
+#define RA_ST_LEADER_MSG          0x0004u /* {record_leader_msg,_} (:1280)                        */
+#define RA_ST_START_ELECTION_TMO  0x0008u /* start_election_timeout effect (:2934,2942)           */
+#define RA_ST_MSG_DROPPED         0x0010u /* an outgoing record did not fit (transport full)      */
+#define RA_ST_PIPELINE_PENDING    0x0020u /* pipeline_rpcs continues next step                    */
+#define RA_ST_FATAL               0x0040u /* c = enum ra_fatal; the reference would exit/crash    */
+#define RA_ST_CMD_POSTPONED       0x0080u /* COMMAND while in await_condition (proc postpones)    */
+#define RA_ST_BECAME_LEADER       0x0100u
+#define RA_ST_NOTE_OVERFLOW       0x0200u
+
+enum ra_fatal {
+    RA_FATAL_NONE = 0,
+    RA_FATAL_LEADER_SAW_AER_SAME_TERM = 1, /* exit(leader_saw_append_entries_rpc_in_same_term) :840 */
+    RA_FATAL_WRITE_INTEGRITY = 2,          /* ra_log:write/2 {error,{integrity_error,_}}  :1369    */
+    RA_FATAL_SET_LAST_INDEX_NOT_FOUND = 3, /* {ok,L} = ra_log:set_last_index(..) badmatch :1301    */
+    RA_FATAL_ASSERT = 4,                   /* a ?assert / ?assertNot in the reference failed       */
+    RA_FATAL_NO_SNAPSHOT = 5               /* make_rpc_effect: prev entry and snapshot both absent :2378 */
+};
+
+typedef struct ra_note {
+    uint32_t row;
+    uint8_t  type;     /* enum ra_note_type */
+    uint8_t  slot;
+    uint16_t aux;
+    uint64_t a, b, c;
+} ra_note;
+
+/* One peer entry of ra_cluster() / ra_peer_state(), src/ra.hrl:63-75 */
+typedef struct ra_peer_init {
+    uint64_t next_index;          /* new_peer/0: 1   src/ra_server.erl:2963-2968 */
+    uint64_t match_index;         /* 0 */
+    uint64_t commit_index_sent;   /* 0 */
+    uint8_t  status;              /* enum ra_peer_status */
+    uint8_t  voter;               /* 1 unless voter_status.membership =/= voter */
+    uint8_t  _pad[6];
+} ra_peer_init;
+
+/*
+ * Everything ra_server:init/1 (src/ra_server.erl:434-457) + the log facade hold
+ * for one member, as far as the hot path reads it.  Used to load rows and to
+ * read them back for a parity diff.
+ */
+typedef struct ra_row_state {
+    uint32_t row;
+    uint8_t  role;                /* enum ra_role */
+    uint8_t  self_slot;
+    uint8_t  n_members;
+    uint8_t  leader_slot;         /* RA_NO_SLOT = undefined */
+    uint8_t  voted_for;           /* RA_NO_SLOT = undefined */
+    uint8_t  membership;          /* enum ra_membership of this member */
+    uint8_t  condition;           /* 0 none, 1 catch-up(missing), 2 catch-up(term_mismatch) */
+    uint8_t  has_snapshot;
+    uint32_t votes;
+    uint32_t machine_version;             /* #cfg.machine_version            */
+    uint32_t effective_machine_version;   /* #cfg.effective_machine_version  */
+    uint32_t n_runs;
+    uint32_t flags;               /* bit0: pipeline_rpcs pending, bit1: cond reply valid */
+    uint64_t current_term;
+    uint64_t commit_index;
+    uint64_t last_applied;
+    uint64_t pre_vote_token;
+    uint64_t token_counter;
+    /* log view (ra_log facade): range [first_index,last_index] */
+    uint64_t first_index;
+    uint64_t last_index;
+    uint64_t last_term;
+    uint64_t last_written_index;
+    uint64_t last_written_term;
+    uint64_t snapshot_index;
+    uint64_t snapshot_term;
+    /* index->term knowledge as runs: entries run_start[i] .. (run_start[i+1]-1 | last_index)
+       have term run_term[i]; runs are ascending in start index.                        */
+    uint64_t run_start[RA_MAX_RUNS];
+    uint64_t run_term[RA_MAX_RUNS];
+    /* await_condition timeout effect: the reply to repeat (src/ra_server.erl:1383-1386) */
+    uint64_t cond_reply_term, cond_reply_next_index, cond_reply_last_index, cond_reply_last_term;
+    ra_peer_init peers[RA_MAX_MEMBERS];   /* indexed by slot; entry self_slot mirrors the
+                                             reference keeping itself in the cluster map  */
+} ra_row_state;
+
+typedef struct ra_engine_cfg {
+    uint32_t n_groups;            /* rows = n_groups * n_members                          */
+    uint32_t n_members;           /* 1..RA_MAX_MEMBERS                                    */
+    uint32_t max_pipeline_count;  /* ?DEFAULT_MAX_PIPELINE_COUNT 4096  src/ra_server.hrl:8 */
+    uint32_t max_aer_batch;       /* ?AER_CHUNK_SIZE 128               src/ra_server.hrl:7 */
+    int32_t  device;              /* CUDA device ordinal                                  */
+    uint32_t route_on_device;     /* 1: RPC records for rows of this engine are delivered
+                                     through HBM mailboxes (benchmark transport), never
+                                     shown to the host.  0: every RPC record is returned. */
+    uint32_t pure;                /* 1: do not chase {next_event,_}; return it as a record
+                                     (the shape ra_server_SUITE asserts on)               */
+    uint32_t _reserved;
+} ra_engine_cfg;
+
+typedef struct ra_engine ra_engine;
+
+typedef struct ra_counters {
+    uint64_t events;              /* events evaluated                                     */
+    uint64_t commits;             /* sum of commit_index advances on leaders (the metric) */
+    uint64_t applied;             /* sum of last_applied advances                         */
+    uint64_t msgs_out;            /* RPC records emitted                                  */
+    uint64_t msgs_dropped;        /* RPC records that found the transport full            */
+    uint64_t elections_won;
+    uint64_t fatal_rows;
+    uint64_t steps;
+} ra_counters;
+
+enum ra_status {
+    RA_OK = 0,
+    RA_E_INVAL = -1,      /* bad argument                                   */
+    RA_E_NOMEM = -2,
+    RA_E_CUDA = -3,       /* CUDA runtime error, see ra_engine_strerror     */
+    RA_E_UNGROUPED = -4,  /* events of one row are not adjacent in the batch */
+    RA_E_CAPACITY = -5,   /* more than RA_LOCAL_CAP events for one row, or out buffers too small */
+    RA_E_NODEVICE = -6
+};
+
+/* Lifecycle.  The engine owns the HBM Struct-of-Arrays; callers own all host buffers and
+   the engine never keeps a host pointer past a call.  One engine per GPU; calls on one
+   engine must be serialised (as gen_statem serialises one member's mailbox).          */
+int  ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out);
+void ra_engine_destroy(ra_engine* e);
+
+/* = ra_server:init/1 values (src/ra_server.erl:434-457) + log tail, per row. */
+int  ra_engine_load_rows(ra_engine* e, const ra_row_state* rows, size_t n);
+/* Convenience: every row := ra_server_SUITE:empty_state/2 (:4022-4032), current_term 0. */
+int  ra_engine_reset_empty(ra_engine* e);
+/* For the parity diff. `rows[i].row` selects the row; the rest is filled in. */
+int  ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n);
+
+/*
+ * Evaluate one batch.  ev[0..n_ev): events for one row must be adjacent and are applied
+ * in array order (= mailbox order); at most RA_LOCAL_CAP per row per call.  In
+ * route_on_device mode mailbox records delivered by the previous step are evaluated first
+ * (by sender slot, then send order), then ev[].  Outputs: RPC records (already addressed)
+ * and host notes, each ordered by (row, seq).  Returns RA_OK or a negative ra_status.
+ */
+int  ra_engine_step(ra_engine* e,
+                    const ra_event* ev, size_t n_ev,
+                    ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                    ra_note*  notes, size_t notes_cap, size_t* n_notes);
+
+/*
+ * Benchmark transport + synthetic host, all on the device (no host copies):
+ * one step = [deliver mailboxes] + raft_step + [host model: every WAL_APPEND note becomes
+ * the matching WRITTEN event of the next step; every leader gets COMMAND(n=cmds_per_step)].
+ * election_permille: per step, that fraction (x/1000) of groups get election_timeout on a
+ * follower chosen by hash(seed, step, group).  Returns after the work is enqueued on the
+ * engine's stream; ra_engine_sync() waits for it.
+ */
+int  ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per_step,
+                     uint32_t election_permille, uint64_t seed);
+int  ra_engine_sync(ra_engine* e);
+int  ra_engine_counters(ra_engine* e, ra_counters* out);     /* syncs */
+/* elapsed device time (ms) of the raft_step kernel over the last flood call, CUDA events
+   on the engine's stream, and its launch count */
+int  ra_engine_last_kernel_ms(ra_engine* e, float* ms, uint32_t* launches);
+
+const char* ra_engine_strerror(int status);
+const char* ra_engine_last_cuda_error(ra_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RA_ENGINE_H */
