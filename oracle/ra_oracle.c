@@ -335,6 +335,7 @@ static void emit_msg(ctx_t *c, u32 to_slot, msg_t *e)
 {
     ra_oracle *o = c->o;
     member_t *m = c->m;
+    if (to_slot >= m->n_members) return;                 /* unknown peer: nothing to send to */
     e->row = row_of(o, group_of(o, m->row), to_slot);
     if (!(e->flags & RA_EVF_NEXT_EVENT)) e->from_slot = m->self_slot;
     e->_pad = 0;
@@ -1445,6 +1446,8 @@ int ra_oracle_step(ra_oracle *o, const ra_event *ev, size_t n_ev,
                    ra_note *notes, size_t notes_cap, size_t *n_notes)
 {
     if (!o || (!ev && n_ev)) return RA_E_INVAL;
+    /* contract: a step() discards locals queued by the flood host model */
+    if (o->loc_n) memset(o->loc_n, 0, o->n_rows);
     u8 *seen = (u8 *)calloc(o->n_rows, 1);
     /* validate grouping + capacity */
     for (size_t i = 0; i < n_ev;) {

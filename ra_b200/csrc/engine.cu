@@ -1,0 +1,583 @@
+// engine.cu -- C ABI (include/ra_engine.h) of the B200 batched multi-Raft engine.
+//
+// Host side: owns the HBM Struct-of-Arrays, stages host buffers, launches
+//   raft_step_kernel  -- the hot path (raft_step.cuh), one thread per member row
+//   ingest / gather   -- flat host batch <-> per-row slots (plumbing for ra_engine_step)
+// There is no CPU fallback: without a CUDA device ra_engine_create fails with
+// RA_E_NODEVICE and nothing else works.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "raft_step.cuh"
+
+#define THREADS 128
+
+// ------------------------------------------------------------------------------------------
+// the hot kernel
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 warp_sum32(u32 v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ u64 warp_sum64(u64 v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(THREADS)
+raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F)
+{
+    const u32 r = blockIdx.x * THREADS + threadIdx.x;
+    u64 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
+    if (r < C.rows) {
+        ulonglong2 ap = C.ap[r];
+        const u32 slot = r / C.groups, group = r - slot * C.groups;
+        const u32 nloc = C.loc_n[r];
+        u32 mail = 0;
+        if (C.routed)
+            for (u32 s = 0; s < C.members; s++) mail |= C.mbox_n[cur][(size_t)s * C.rows + r];
+        const bool fatal0 = MT_FATAL(ap.y) != 0;
+        const bool pending = MT_PIPE_PEND(ap.y) != 0;
+        if (F.on || nloc || mail || pending) {
+            Member m;
+            m.C = &C; m.row = r; m.slot = slot; m.group = group;
+            const ulonglong2 tc = C.tc[r], lg = C.lg[r], lw = C.lw[r], sn = C.sn[r], tk = C.tk[r], fm = C.fm[r];
+            m.term = tc.x; m.commit = tc.y; m.last_idx = lg.x; m.last_term = lg.y;
+            m.lw_idx = lw.x; m.lw_term = lw.y; m.applied = ap.x; m.meta = ap.y;
+            m.snap_idx = sn.x; m.snap_term = sn.y; m.token = tk.x; m.token_ctr = tk.y;
+            m.first_idx = fm.x; m.macver = fm.y;
+            m.n_msgs = 0; m.n_notes = 0; m.status = 0; m.fatal_code = 0; m.role0 = MT_ROLE(ap.y);
+            m.sent_to = 0; m.pn_type = RA_NOTE_NONE; m.pn_slot = 0; m.pn_a = m.pn_b = m.pn_c = 0;
+            m.w_n = 0; m.w0a = m.w0b = m.w0c = m.w1a = m.w1b = m.w1c = 0;
+            m.c_events = m.c_msgs = m.c_dropped = m.c_elections = 0; m.c_commits = m.c_applied = 0;
+            m.nb = cur ^ 1;
+            if (!fatal0) {
+                if (pending) {
+                    MT_SET(m.meta, 24, 1, 0);
+                    process_event(m, mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+                }
+                if (C.routed) {
+                    for (u32 s = 0; s < C.members; s++) {
+                        u8* cp = &C.mbox_n[cur][(size_t)s * C.rows + r];
+                        const u32 cnt = *cp;
+                        for (u32 k = 0; k < cnt; k++)
+                            process_event(m, ld_rec(&C.mbox[cur][((size_t)s * RA_MBOX_DEPTH + k) * C.rows + r]));
+                        if (cnt) *cp = 0;
+                    }
+                }
+                for (u32 k = 0; k < nloc; k++) process_event(m, ld_rec(&C.loc[(size_t)k * C.rows + r]));
+            }
+            if (nloc) C.loc_n[r] = 0;
+            if (C.routed) {
+                for (u32 s = 0; s < C.members; s++)
+                    if (s != slot)
+                        C.mbox_n[cur ^ 1][(size_t)slot * C.rows + (size_t)s * C.groups + group] = (u8)((m.sent_to >> (4 * s)) & 15u);
+            }
+            // end of the row's step: STATUS note
+            note_flush(m);
+            if (m.status) {
+                u64 ld = MT_LEADER(m.meta), vf = MT_VOTED(m.meta);
+                u64 b = (vf == SLOT_NONE ? 0xFFull : vf) | ((ld == SLOT_NONE ? 0xFFull : ld) << 8) |
+                        ((u64)m.role0 << 16) | ((u64)MT_ROLE(m.meta) << 24);
+                note_store(m, m.n_notes, RA_NOTE_STATUS, slot, m.status, m.term, b, m.fatal_code);
+                m.n_notes++;
+                if (m.status & RA_ST_FATAL) k_fatal = 1;
+            }
+            C.out_n[r] = m.n_msgs | (m.n_notes << 16);
+            // flood: synthetic host (DESIGN.md "flood host model")
+            if (F.on && !MT_FATAL(m.meta)) {
+                u32 k = 0;
+                if (m.w_n == 2) {
+                    st_rec(&C.loc[(size_t)k * C.rows + r], mk_rec(r, RA_EV_WRITTEN, RA_NO_SLOT, 0, 0, 0, 0, m.w0c, m.w0a, m.w0b, 0, 0, 0)); k++;
+                }
+                if (m.w_n >= 1) {
+                    st_rec(&C.loc[(size_t)k * C.rows + r], mk_rec(r, RA_EV_WRITTEN, RA_NO_SLOT, 0, 0, 0, 0, m.w1c, m.w1a, m.w1b, 0, 0, 0)); k++;
+                }
+                const u32 role = MT_ROLE(m.meta);
+                if (role == RA_LEADER && F.cmds) {
+                    st_rec(&C.loc[(size_t)k * C.rows + r], mk_rec(r, RA_EV_COMMAND, RA_NO_SLOT, 0, F.cmds, 0, 0, 0, 0, 0, 0, 0, 0)); k++;
+                }
+                u32 idle = MT_IDLE(m.meta);
+                if (role == RA_LEADER || (m.status & RA_ST_LEADER_MSG)) idle = 0;
+                else if (idle < 15) idle++;
+                bool fire = false;
+                if (role != RA_LEADER) {
+                    u64 h = mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ ((u64)group * 0xD1B54A32D192ED03ull));
+                    if (F.permille && (h % 1000) < F.permille && ((h / 1000) % C.members) == slot) fire = true;
+                    u64 h2 = mix64(F.seed ^ ((u64)r * 0xA24BAED4963EE407ull) ^ F.step);
+                    if (idle >= 8 + (u32)(h2 % 8)) fire = true;
+                }
+                if (fire) {
+                    st_rec(&C.loc[(size_t)k * C.rows + r], mk_rec(r, RA_EV_ELECTION_TIMEOUT, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)); k++;
+                    idle = 0;
+                }
+                MT_SET(m.meta, 28, 4, idle);
+                C.loc_n[r] = k;
+            }
+            // write back what changed
+            if (m.term != tc.x || m.commit != tc.y) st2(&C.tc[r], m.term, m.commit);
+            if (m.last_idx != lg.x || m.last_term != lg.y) st2(&C.lg[r], m.last_idx, m.last_term);
+            if (m.lw_idx != lw.x || m.lw_term != lw.y) st2(&C.lw[r], m.lw_idx, m.lw_term);
+            if (m.applied != ap.x || m.meta != ap.y) st2(&C.ap[r], m.applied, m.meta);
+            if (m.token != tk.x || m.token_ctr != tk.y) st2(&C.tk[r], m.token, m.token_ctr);
+            if (m.first_idx != fm.x) st2(&C.fm[r], m.first_idx, m.macver);
+            k_events = m.c_events; k_commits = m.c_commits; k_applied = m.c_applied;
+            k_msgs = m.c_msgs; k_dropped = m.c_dropped; k_elect = m.c_elections;
+        }
+    }
+    // per-launch device counters: warp reduce, one atomic per warp and counter that moved
+    const u32 any = __ballot_sync(0xffffffffu, (k_events | k_fatal) != 0);
+    if (any) {
+        k_events = warp_sum64(k_events); k_commits = warp_sum64(k_commits); k_applied = warp_sum64(k_applied);
+        k_msgs = warp_sum64(k_msgs); k_dropped = warp_sum64(k_dropped); k_elect = warp_sum64(k_elect);
+        k_fatal = warp_sum64(k_fatal);
+        if ((threadIdx.x & 31) == 0) {
+            if (k_events)  atomicAdd(&C.counters[0], k_events);
+            if (k_commits) atomicAdd(&C.counters[1], k_commits);
+            if (k_applied) atomicAdd(&C.counters[2], k_applied);
+            if (k_msgs)    atomicAdd(&C.counters[3], k_msgs);
+            if (k_dropped) atomicAdd(&C.counters[4], k_dropped);
+            if (k_elect)   atomicAdd(&C.counters[5], k_elect);
+            if (k_fatal)   atomicAdd(&C.counters[6], k_fatal);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// plumbing kernels
+// ------------------------------------------------------------------------------------------
+__global__ void reset_empty_kernel(const Cols C)
+{
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= C.rows) return;
+    // ra_server_SUITE:empty_state/2: term 0, log {0 => 0}, peers next=1 match=0, all voters
+    u64 meta = 0;
+    MT_SET(meta, 0, 3, RA_FOLLOWER); MT_SET(meta, 3, 4, SLOT_NONE); MT_SET(meta, 7, 4, SLOT_NONE);
+    MT_SET(meta, 19, 4, 1); MT_SET(meta, 27, 1, 1);
+    MT_SET(meta, 56, 8, (1u << C.members) - 1u);
+    st2(&C.tc[r], 0, 0); st2(&C.lg[r], 0, 0); st2(&C.lw[r], 0, 0); st2(&C.ap[r], 0, meta);
+    st2(&C.sn[r], 0, 0); st2(&C.tk[r], 0, 0); st2(&C.fm[r], 0, 0);
+    st2(&C.cd[r], 0, 0); st2(&C.cd[(size_t)C.rows + r], 0, 0);
+    for (u32 s = 0; s < C.members; s++) { st2(&C.pnm[(size_t)s * C.rows + r], 1, 0); C.pcs[(size_t)s * C.rows + r] = 0; }
+    for (u32 k = 0; k < RA_MAX_RUNS; k++) st2(&C.run[(size_t)k * C.rows + r], 0, 0);
+    C.loc_n[r] = 0; C.out_n[r] = 0;
+    if (C.routed)
+        for (int b = 0; b < 2; b++)
+            for (u32 s = 0; s < C.members; s++) C.mbox_n[b][(size_t)s * C.rows + r] = 0;
+}
+
+__global__ void load_rows_kernel(const Cols C, const ra_row_state* in, u32 n)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ra_row_state& s = in[i];
+    const u32 r = s.row;
+    u64 meta = 0;
+    MT_SET(meta, 0, 3, s.role);
+    MT_SET(meta, 3, 4, s.leader_slot == RA_NO_SLOT ? SLOT_NONE : s.leader_slot);
+    MT_SET(meta, 7, 4, s.voted_for == RA_NO_SLOT ? SLOT_NONE : s.voted_for);
+    MT_SET(meta, 11, 2, s.membership); MT_SET(meta, 13, 2, s.condition);
+    MT_SET(meta, 15, 4, s.votes); MT_SET(meta, 19, 4, s.n_runs);
+    MT_SET(meta, 23, 1, s.has_snapshot ? 1 : 0);
+    MT_SET(meta, 24, 1, (s.flags & 1) ? 1 : 0); MT_SET(meta, 25, 1, (s.flags & 2) ? 1 : 0);
+    MT_SET(meta, 26, 1, (s.flags & 4) ? 1 : 0);
+    MT_SET(meta, 27, 1, s.machine_version >= s.effective_machine_version ? 1 : 0);
+    u32 voters = 0;
+    for (u32 p = 0; p < RA_MAX_MEMBERS; p++) {
+        MT_SET(meta, 32 + 3 * p, 3, s.peers[p].status);
+        if (s.peers[p].voter) voters |= 1u << p;
+    }
+    MT_SET(meta, 56, 8, voters);
+    st2(&C.tc[r], s.current_term, s.commit_index);
+    st2(&C.lg[r], s.last_index, s.last_term);
+    st2(&C.lw[r], s.last_written_index, s.last_written_term);
+    st2(&C.ap[r], s.last_applied, meta);
+    st2(&C.sn[r], s.snapshot_index, s.snapshot_term);
+    st2(&C.tk[r], s.pre_vote_token, s.token_counter);
+    st2(&C.fm[r], s.first_index, (u64)s.machine_version | ((u64)s.effective_machine_version << 32));
+    st2(&C.cd[r], s.cond_reply_term, s.cond_reply_next_index);
+    st2(&C.cd[(size_t)C.rows + r], s.cond_reply_last_index, s.cond_reply_last_term);
+    for (u32 p = 0; p < C.members; p++) {
+        st2(&C.pnm[(size_t)p * C.rows + r], s.peers[p].next_index, s.peers[p].match_index);
+        C.pcs[(size_t)p * C.rows + r] = s.peers[p].commit_index_sent;
+    }
+    for (u32 k = 0; k < RA_MAX_RUNS; k++)
+        st2(&C.run[(size_t)k * C.rows + r], k < s.n_runs ? s.run_start[k] : 0, k < s.n_runs ? s.run_term[k] : 0);
+    C.loc_n[r] = 0;
+}
+
+__global__ void read_rows_kernel(const Cols C, ra_row_state* out, u32 n)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ra_row_state& s = out[i];
+    const u32 r = s.row;
+    const ulonglong2 tc = C.tc[r], lg = C.lg[r], lw = C.lw[r], ap = C.ap[r], sn = C.sn[r], tk = C.tk[r], fm = C.fm[r];
+    const u64 meta = ap.y;
+    s.role = MT_ROLE(meta); s.self_slot = r / C.groups; s.n_members = C.members;
+    u32 l = MT_LEADER(meta), v = MT_VOTED(meta);
+    s.leader_slot = l == SLOT_NONE ? RA_NO_SLOT : l; s.voted_for = v == SLOT_NONE ? RA_NO_SLOT : v;
+    s.membership = MT_MEMBERSHIP(meta); s.condition = MT_COND(meta); s.has_snapshot = MT_HAS_SNAP(meta);
+    s.votes = MT_VOTES(meta); s.machine_version = (u32)fm.y; s.effective_machine_version = (u32)(fm.y >> 32);
+    s.n_runs = MT_NRUNS(meta);
+    s.flags = MT_PIPE_PEND(meta) | (MT_COND_VALID(meta) << 1) | (MT_FATAL(meta) << 2);
+    s.current_term = tc.x; s.commit_index = tc.y; s.last_applied = ap.x;
+    s.pre_vote_token = tk.x; s.token_counter = tk.y;
+    s.first_index = fm.x; s.last_index = lg.x; s.last_term = lg.y;
+    s.last_written_index = lw.x; s.last_written_term = lw.y;
+    s.snapshot_index = sn.x; s.snapshot_term = sn.y;
+    for (u32 k = 0; k < RA_MAX_RUNS; k++) {
+        ulonglong2 rr = C.run[(size_t)k * C.rows + r];
+        s.run_start[k] = k < s.n_runs ? rr.x : 0; s.run_term[k] = k < s.n_runs ? rr.y : 0;
+    }
+    ulonglong2 c0 = C.cd[r], c1 = C.cd[(size_t)C.rows + r];
+    s.cond_reply_term = c0.x; s.cond_reply_next_index = c0.y; s.cond_reply_last_index = c1.x; s.cond_reply_last_term = c1.y;
+    for (u32 p = 0; p < RA_MAX_MEMBERS; p++) {
+        ra_peer_init& pi = s.peers[p];
+        if (p < C.members) {
+            ulonglong2 nm = C.pnm[(size_t)p * C.rows + r];
+            pi.next_index = nm.x; pi.match_index = nm.y; pi.commit_index_sent = C.pcs[(size_t)p * C.rows + r];
+            pi.status = MT_PSTATUS(meta, p); pi.voter = MT_VOTER(meta, p);
+        } else { pi.next_index = pi.match_index = pi.commit_index_sent = 0; pi.status = 0; pi.voter = 0; }
+        for (int q = 0; q < 6; q++) pi._pad[q] = 0;
+    }
+}
+
+// flat host batch -> per-row local slots.  err[0]: 1 = ungrouped, 2 = too many for a row, 3 = bad row
+__global__ void ingest_kernel(const Cols C, const ra_event* ev, u32 n, u32* err)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 row = ev[i].row;
+    if (row >= C.rows) { atomicMax(err, 3u); return; }
+    if (i > 0 && ev[i - 1].row == row) return;                 // not the head of its run
+    u32 len = 1;
+    while (i + len < n && ev[i + len].row == row && len <= RA_LOCAL_CAP) len++;
+    if (len > RA_LOCAL_CAP) { atomicMax(err, 2u); return; }
+    if (atomicCAS(&C.loc_n[row], 0u, len) != 0u) { atomicMax(err, 1u); return; }
+    for (u32 k = 0; k < len; k++) st_rec(&C.loc[(size_t)k * C.rows + row], ld_rec(&ev[i + k]));
+}
+
+__global__ void clear_loc_kernel(const Cols C)
+{
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < C.rows) C.loc_n[r] = 0;
+}
+
+// per-row slots -> flat (row, seq)-ordered arrays; offs = exclusive scan of out_n packed as
+// msgs | notes << 32
+__global__ void pack_counts_kernel(const Cols C, u64* packed)
+{
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= C.rows) return;
+    const u32 v = C.out_n[r];
+    packed[r] = (u64)(v & 0xffffu) | ((u64)(v >> 16) << 32);
+}
+__global__ void gather_kernel(const Cols C, const u64* offs, ra_event* msgs, u64 msgs_cap, ra_note* notes, u64 notes_cap)
+{
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= C.rows) return;
+    const u32 v = C.out_n[r];
+    if (!v) return;
+    C.out_n[r] = 0;
+    const u32 nm = v & 0xffffu, nn = v >> 16;
+    const u64 om = offs[r] & 0xffffffffull, on = offs[r] >> 32;
+    for (u32 k = 0; k < nm; k++)
+        if (om + k < msgs_cap) st_rec(&msgs[om + k], ld_rec(&C.omsg[(size_t)k * C.rows + r]));
+    for (u32 k = 0; k < nn; k++)
+        if (on + k < notes_cap) {
+            const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&C.onote[(size_t)k * C.rows + r]);
+            ulonglong2* d = reinterpret_cast<ulonglong2*>(&notes[on + k]);
+            d[0] = q[0]; d[1] = q[1];
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+struct ra_engine {
+    ra_engine_cfg cfg;
+    Cols C;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    int cur;
+    u64 step_no, steps;
+    void* allocs[64]; int n_allocs;
+    // staging
+    ra_event* d_ev; size_t d_ev_cap;
+    ra_event* d_msgs; size_t d_msgs_cap;
+    ra_note* d_notes; size_t d_notes_cap;
+    u64 *d_packed, *d_offs; void* d_scan_tmp; size_t scan_tmp_bytes;
+    u32* d_err;
+    ra_row_state* d_rows; size_t d_rows_cap;
+    float last_ms; u32 last_launches;
+    char err[256];
+};
+
+static int fail(ra_engine* e, cudaError_t ce, const char* what)
+{
+    if (e) snprintf(e->err, sizeof e->err, "%s: %s", what, cudaGetErrorString(ce));
+    return RA_E_CUDA;
+}
+#define CK(call) do { cudaError_t ce_ = (call); if (ce_ != cudaSuccess) return fail(e, ce_, #call); } while (0)
+
+template <typename T>
+static int dalloc(ra_engine* e, T** p, size_t count)
+{
+    void* q = nullptr;
+    cudaError_t ce = cudaMalloc(&q, count * sizeof(T) ? count * sizeof(T) : 16);
+    if (ce != cudaSuccess) return fail(e, ce, "cudaMalloc");
+    cudaMemsetAsync(q, 0, count * sizeof(T) ? count * sizeof(T) : 16, e->stream);
+    e->allocs[e->n_allocs++] = q;
+    *p = (T*)q;
+    return RA_OK;
+}
+
+static inline u32 nblocks(u64 n, u32 t) { return (u32)((n + t - 1) / t); }
+
+extern "C" const char* ra_engine_strerror(int st)
+{
+    switch (st) {
+    case RA_OK: return "ok";
+    case RA_E_INVAL: return "invalid argument";
+    case RA_E_NOMEM: return "out of memory";
+    case RA_E_CUDA: return "CUDA error (see ra_engine_last_cuda_error)";
+    case RA_E_UNGROUPED: return "events of one row are not adjacent in the batch";
+    case RA_E_CAPACITY: return "capacity exceeded (RA_LOCAL_CAP per row, or output buffers too small)";
+    case RA_E_NODEVICE: return "no CUDA device: the engine has no CPU fallback";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char* ra_engine_last_cuda_error(ra_engine* e) { return e ? e->err : ""; }
+
+extern "C" void ra_engine_destroy(ra_engine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaStreamSynchronize(e->stream);
+    for (int i = 0; i < e->n_allocs; i++) cudaFree(e->allocs[i]);
+    cudaFree(e->d_ev); cudaFree(e->d_msgs); cudaFree(e->d_notes); cudaFree(e->d_rows); cudaFree(e->d_scan_tmp);
+    cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+    cudaStreamDestroy(e->stream);
+    free(e);
+}
+
+extern "C" int ra_engine_reset_empty(ra_engine* e)
+{
+    if (!e) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    reset_empty_kernel<<<nblocks(e->C.rows, 256), 256, 0, e->stream>>>(e->C);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(e->C.counters, 0, 8 * sizeof(u64), e->stream));
+    e->cur = 0; e->step_no = 0; e->steps = 0;
+    CK(cudaStreamSynchronize(e->stream));
+    return RA_OK;
+}
+
+extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
+{
+    if (!cfg || !out || cfg->n_members < 1 || cfg->n_members > RA_MAX_MEMBERS || cfg->n_groups == 0) return RA_E_INVAL;
+    if ((u64)cfg->n_groups * cfg->n_members > 0x7fffffffull) return RA_E_INVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev) return RA_E_NODEVICE;
+    ra_engine* e = (ra_engine*)calloc(1, sizeof(ra_engine));
+    if (!e) return RA_E_NOMEM;
+    e->cfg = *cfg;
+    if (e->cfg.max_pipeline_count == 0) e->cfg.max_pipeline_count = 4096;
+    if (e->cfg.max_aer_batch == 0) e->cfg.max_aer_batch = 128;
+    int rc = RA_OK;
+    cudaError_t ce;
+    if ((ce = cudaSetDevice(cfg->device)) != cudaSuccess) { rc = fail(e, ce, "cudaSetDevice"); goto bad; }
+    if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail(e, ce, "cudaStreamCreate"); goto bad; }
+    cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
+    {
+        Cols& C = e->C;
+        const size_t R = (size_t)cfg->n_groups * cfg->n_members, M = cfg->n_members;
+        C.rows = (u32)R; C.groups = cfg->n_groups; C.members = cfg->n_members;
+        C.max_pipeline = e->cfg.max_pipeline_count; C.max_batch = e->cfg.max_aer_batch;
+        C.routed = cfg->route_on_device ? 1 : 0; C.pure = cfg->pure ? 1 : 0;
+#define DA(p, n) if ((rc = dalloc(e, &(p), (n))) != RA_OK) goto bad
+        DA(C.tc, R); DA(C.lg, R); DA(C.lw, R); DA(C.ap, R); DA(C.sn, R); DA(C.tk, R); DA(C.fm, R);
+        DA(C.cd, 2 * R); DA(C.pnm, M * R); DA(C.pcs, M * R); DA(C.run, RA_MAX_RUNS * R);
+        DA(C.loc, (size_t)RA_LOCAL_CAP * R); DA(C.loc_n, R);
+        DA(C.onote, (size_t)RA_NOTE_CAP * R); DA(C.out_n, R); DA(C.counters, 8);
+        if (C.routed) {
+            for (int b = 0; b < 2; b++) { DA(C.mbox[b], M * RA_MBOX_DEPTH * R); DA(C.mbox_n[b], M * R); }
+            DA(C.omsg, (size_t)RA_MSG_CAP * (C.pure ? R : 1));
+        } else {
+            C.mbox[0] = C.mbox[1] = nullptr; C.mbox_n[0] = C.mbox_n[1] = nullptr;
+            DA(C.omsg, (size_t)RA_MSG_CAP * R);
+        }
+        DA(e->d_packed, R + 1); DA(e->d_offs, R + 1); DA(e->d_err, 4);
+#undef DA
+        e->scan_tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp_bytes, e->d_packed, e->d_offs, (int)(R + 1), e->stream);
+        if ((ce = cudaMalloc(&e->d_scan_tmp, e->scan_tmp_bytes ? e->scan_tmp_bytes : 16)) != cudaSuccess) { rc = fail(e, ce, "cudaMalloc scan"); goto bad; }
+    }
+    if ((rc = ra_engine_reset_empty(e)) != RA_OK) goto bad;
+    *out = e;
+    return RA_OK;
+bad:
+    ra_engine_destroy(e);
+    return rc;
+}
+
+template <typename T>
+static int ensure(ra_engine* e, T** p, size_t* cap, size_t need)
+{
+    if (*cap >= need && *p) return RA_OK;
+    if (*p) cudaFree(*p);
+    size_t nc = need < 1024 ? 1024 : need + need / 4;
+    void* q = nullptr;
+    cudaError_t ce = cudaMalloc(&q, nc * sizeof(T));
+    if (ce != cudaSuccess) { *p = nullptr; *cap = 0; return fail(e, ce, "cudaMalloc staging"); }
+    *p = (T*)q; *cap = nc;
+    return RA_OK;
+}
+
+extern "C" int ra_engine_load_rows(ra_engine* e, const ra_row_state* rows, size_t n)
+{
+    if (!e || (!rows && n)) return RA_E_INVAL;
+    if (n == 0) return RA_OK;
+    for (size_t i = 0; i < n; i++)
+        if (rows[i].row >= e->C.rows || rows[i].n_runs > RA_MAX_RUNS || rows[i].n_members != e->C.members) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    int rc = ensure(e, &e->d_rows, &e->d_rows_cap, n); if (rc) return rc;
+    CK(cudaMemcpyAsync(e->d_rows, rows, n * sizeof(ra_row_state), cudaMemcpyHostToDevice, e->stream));
+    load_rows_kernel<<<nblocks(n, 128), 128, 0, e->stream>>>(e->C, e->d_rows, (u32)n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    return RA_OK;
+}
+
+extern "C" int ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n)
+{
+    if (!e || (!rows && n)) return RA_E_INVAL;
+    if (n == 0) return RA_OK;
+    for (size_t i = 0; i < n; i++) if (rows[i].row >= e->C.rows) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    int rc = ensure(e, &e->d_rows, &e->d_rows_cap, n); if (rc) return rc;
+    CK(cudaMemcpyAsync(e->d_rows, rows, n * sizeof(ra_row_state), cudaMemcpyHostToDevice, e->stream));
+    read_rows_kernel<<<nblocks(n, 128), 128, 0, e->stream>>>(e->C, e->d_rows, (u32)n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rows, e->d_rows, n * sizeof(ra_row_state), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return RA_OK;
+}
+
+static int launch_step(ra_engine* e, const FloodArgs& F)
+{
+    raft_step_kernel<<<nblocks(e->C.rows, THREADS), THREADS, 0, e->stream>>>(e->C, e->cur, F);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return fail(e, ce, "raft_step_kernel");
+    if (e->C.routed) e->cur ^= 1;
+    e->steps++;
+    return RA_OK;
+}
+
+extern "C" int ra_engine_step(ra_engine* e, const ra_event* ev, size_t n_ev,
+                              ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                              ra_note* notes, size_t notes_cap, size_t* n_notes)
+{
+    if (!e || (!ev && n_ev) || n_ev > 0x7fffffffull) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    const u32 R = e->C.rows;
+    int rc;
+    // a step() after flood() must not see the flood host model's queued locals
+    if (n_ev) {
+        if ((rc = ensure(e, &e->d_ev, &e->d_ev_cap, n_ev))) return rc;
+        CK(cudaMemcpyAsync(e->d_ev, ev, n_ev * sizeof(ra_event), cudaMemcpyHostToDevice, e->stream));
+    }
+    u32 h_err = 0;
+    clear_loc_kernel<<<nblocks(R, 256), 256, 0, e->stream>>>(e->C);
+    CK(cudaMemsetAsync(e->d_err, 0, sizeof(u32), e->stream));
+    if (n_ev) {
+        ingest_kernel<<<nblocks(n_ev, 256), 256, 0, e->stream>>>(e->C, e->d_ev, (u32)n_ev, e->d_err);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h_err, e->d_err, sizeof(u32), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (h_err) {
+            clear_loc_kernel<<<nblocks(R, 256), 256, 0, e->stream>>>(e->C);
+            CK(cudaStreamSynchronize(e->stream));
+            return h_err == 1 ? RA_E_UNGROUPED : (h_err == 2 ? RA_E_CAPACITY : RA_E_INVAL);
+        }
+    }
+    FloodArgs F; memset(&F, 0, sizeof F);
+    if ((rc = launch_step(e, F))) return rc;
+    // per-row slots -> flat arrays ordered by (row, seq)
+    pack_counts_kernel<<<nblocks(R, 256), 256, 0, e->stream>>>(e->C, e->d_packed);
+    CK(cudaMemsetAsync(e->d_packed + R, 0, sizeof(u64), e->stream));
+    CK(cub::DeviceScan::ExclusiveSum(e->d_scan_tmp, e->scan_tmp_bytes, e->d_packed, e->d_offs, (int)(R + 1), e->stream));
+    u64 total = 0;
+    CK(cudaMemcpyAsync(&total, e->d_offs + R, sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    const size_t tm = (size_t)(total & 0xffffffffull), tn = (size_t)(total >> 32);
+    if ((rc = ensure(e, &e->d_msgs, &e->d_msgs_cap, tm ? tm : 1))) return rc;
+    if ((rc = ensure(e, &e->d_notes, &e->d_notes_cap, tn ? tn : 1))) return rc;
+    gather_kernel<<<nblocks(R, 256), 256, 0, e->stream>>>(e->C, e->d_offs, e->d_msgs, tm, e->d_notes, tn);
+    CK(cudaGetLastError());
+    if (tm > msgs_cap || tn > notes_cap) { CK(cudaStreamSynchronize(e->stream)); return RA_E_CAPACITY; }
+    if (tm) CK(cudaMemcpyAsync(msgs, e->d_msgs, tm * sizeof(ra_event), cudaMemcpyDeviceToHost, e->stream));
+    if (tn) CK(cudaMemcpyAsync(notes, e->d_notes, tn * sizeof(ra_note), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (n_msgs) *n_msgs = tm;
+    if (n_notes) *n_notes = tn;
+    return RA_OK;
+}
+
+extern "C" int ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per_step,
+                               uint32_t election_permille, uint64_t seed)
+{
+    if (!e || !e->C.routed) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    for (u32 t = 0; t < n_steps; t++) {
+        FloodArgs F; F.on = 1; F.cmds = cmds_per_step; F.permille = election_permille; F._p = 0;
+        F.seed = seed; F.step = e->step_no + t;
+        int rc = launch_step(e, F);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(e->ev1, e->stream));
+    e->step_no += n_steps;
+    e->last_launches = n_steps;
+    return RA_OK;
+}
+
+extern "C" int ra_engine_sync(ra_engine* e)
+{
+    if (!e) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    return RA_OK;
+}
+
+extern "C" int ra_engine_last_kernel_ms(ra_engine* e, float* ms, uint32_t* launches)
+{
+    if (!e) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaEventSynchronize(e->ev1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, e->ev0, e->ev1));
+    if (ms) *ms = t;
+    if (launches) *launches = e->last_launches;
+    return RA_OK;
+}
+
+extern "C" int ra_engine_counters(ra_engine* e, ra_counters* out)
+{
+    if (!e || !out) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    u64 h[8];
+    CK(cudaMemcpyAsync(h, e->C.counters, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    out->events = h[0]; out->commits = h[1]; out->applied = h[2]; out->msgs_out = h[3];
+    out->msgs_dropped = h[4]; out->elections_won = h[5]; out->fatal_rows = h[6]; out->steps = e->steps;
+    return RA_OK;
+}

@@ -1,0 +1,1078 @@
+// raft_step.cuh -- device side of the batched multi-Raft engine (sm_100a).
+//
+// One thread owns one member row for the whole launch ("owner computes"): every HBM column
+// is indexed by row, rows are slot-major (row = slot * n_groups + group), so the 32 lanes
+// of a warp touch 32 consecutive 16-byte cells of each column -> one fully coalesced
+// 512-byte request per column pair (LDG.E.128 / STG.E.128).  The Raft decision logic is
+// integer compare/min/max/select; no tensor cores.
+//
+// What is evaluated (reference: rabbitmq/ra v3.1.6 src/ra_server.erl):
+//   handle_leader/2    :520-1023   AER-reply (success / failure back-off / higher term),
+//                                  command(s), written event, pipeline_rpcs, AER, votes
+//   handle_follower/2  :1264-1641  AER (log match, truncate, write), written event, votes
+//   handle_candidate/2 :1026-1171, handle_pre_vote/2 :1173-1261,
+//   handle_await_condition/2 :1900-1941 + follower_catchup_cond/3 :2184-2213
+//   evaluate_quorum/2 :3606-3619, agreed_commit/1 :3657-3661 (rank select, no sort),
+//   make_pipelined_rpc_effects/3 :2268-2329, make_rpc_effect/5 :2365-2399,
+//   call_for_election/3 :2853-2897, process_pre_vote/3 :2899-2956
+// plus the slice of ra_server_proc that feeds back into it inside one mailbox turn
+// ({next_event,_} chasing :1574-1577, become/3 via handle_state_enter, tick on election win).
+//
+// The log facade (src/ra_log.erl fetch_term/exists/write/set_last_index/handle_event
+// {written}) is a run-length index->term view: at most RA_MAX_RUNS (start, term) runs per
+// member, so no per-entry storage lives on the GPU.
+#pragma once
+#include <stdint.h>
+#include "../../include/ra_engine.h"
+
+typedef unsigned long long u64;
+typedef long long i64;
+typedef unsigned int u32;
+typedef unsigned char u8;
+
+#define RA_UNDEF 0xFFFFFFFFFFFFFFFFull
+
+// ---- meta word (second half of the `ap` pair) -------------------------------------
+//  [0:3) role  [3:7) leader  [7:11) voted_for  [11:13) membership  [13:15) condition
+//  [15:19) votes  [19:23) n_runs  23 has_snapshot  24 pipeline_pending  25 cond_reply_valid
+//  26 fatal  27 mv_ok  [28:32) idle  [32:56) peer status 3b x 8  [56:64) voter mask
+#define MT_ROLE(m)        ((u32)((m) & 7ull))
+#define MT_LEADER(m)      ((u32)(((m) >> 3) & 15ull))
+#define MT_VOTED(m)       ((u32)(((m) >> 7) & 15ull))
+#define MT_MEMBERSHIP(m)  ((u32)(((m) >> 11) & 3ull))
+#define MT_COND(m)        ((u32)(((m) >> 13) & 3ull))
+#define MT_VOTES(m)       ((u32)(((m) >> 15) & 15ull))
+#define MT_NRUNS(m)       ((u32)(((m) >> 19) & 15ull))
+#define MT_HAS_SNAP(m)    ((u32)(((m) >> 23) & 1ull))
+#define MT_PIPE_PEND(m)   ((u32)(((m) >> 24) & 1ull))
+#define MT_COND_VALID(m)  ((u32)(((m) >> 25) & 1ull))
+#define MT_FATAL(m)       ((u32)(((m) >> 26) & 1ull))
+#define MT_MV_OK(m)       ((u32)(((m) >> 27) & 1ull))
+#define MT_IDLE(m)        ((u32)(((m) >> 28) & 15ull))
+#define MT_PSTATUS(m, s)  ((u32)(((m) >> (32 + 3 * (s))) & 7ull))
+#define MT_VOTER(m, s)    ((u32)(((m) >> (56 + (s))) & 1ull))
+#define MT_SET(m, sh, w, v) ((m) = ((m) & ~((((u64)1 << (w)) - 1) << (sh))) | (((u64)(v) & (((u64)1 << (w)) - 1)) << (sh)))
+#define SLOT_NONE 15u
+
+struct Cols {
+    // scalar pairs, one cell per row
+    ulonglong2* tc;     // {current_term, commit_index}
+    ulonglong2* lg;     // {last_index, last_term}
+    ulonglong2* lw;     // {last_written_index, last_written_term}
+    ulonglong2* ap;     // {last_applied, meta}
+    ulonglong2* sn;     // {snapshot_index, snapshot_term}
+    ulonglong2* tk;     // {pre_vote_token, token_counter}
+    ulonglong2* fm;     // {first_index, machine_version | effective_machine_version << 32}
+    ulonglong2* cd;     // [2][rows] await_condition reply {term,next},{last_index,last_term}
+    // per peer slot s: [s][rows]
+    ulonglong2* pnm;    // {next_index, match_index}
+    u64*        pcs;    // commit_index_sent
+    // log view: [k][rows] {run_start, run_term}
+    ulonglong2* run;
+    // transport / io, all [slot-or-k][rows]
+    ra_event* mbox[2];  // [(src*DEPTH + k)][rows]
+    u8*       mbox_n[2];// [src][rows]
+    ra_event* loc;      // [k][rows] host ("local") events
+    u32*      loc_n;    // [rows]
+    ra_event* omsg;     // [k][rows] outgoing RPC records (non-routed)
+    ra_note*  onote;    // [k][rows]
+    u32*      out_n;    // [rows] msgs | notes << 16
+    u64*      counters; // ra_counters as 8 x u64
+    u32 rows, groups, members;
+    u32 max_pipeline, max_batch;
+    u32 routed, pure;
+};
+
+struct FloodArgs { u32 on; u32 cmds; u32 permille; u32 _p; u64 seed; u64 step; };
+
+__device__ __forceinline__ ulonglong2 ld2(const ulonglong2* p) { return *p; }
+__device__ __forceinline__ void st2(ulonglong2* p, u64 x, u64 y) { *p = make_ulonglong2(x, y); }
+
+__device__ __forceinline__ u64 mix64(u64 x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// 64-byte record as four 16-byte words
+struct Rec { ulonglong2 w0, w1, w2, w3; };
+__device__ __forceinline__ Rec ld_rec(const ra_event* p)
+{
+    const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
+    Rec r; r.w0 = q[0]; r.w1 = q[1]; r.w2 = q[2]; r.w3 = q[3];
+    return r;
+}
+__device__ __forceinline__ void st_rec(ra_event* p, const Rec& r)
+{
+    ulonglong2* q = reinterpret_cast<ulonglong2*>(p);
+    q[0] = r.w0; q[1] = r.w1; q[2] = r.w2; q[3] = r.w3;
+}
+// header word: row | type<<32 | from<<40 | flags<<48 | pad<<56 ; second: n | n1<<16 | seq<<32
+__device__ __forceinline__ u32 R_row(const Rec& r)   { return (u32)r.w0.x; }
+__device__ __forceinline__ u32 R_type(const Rec& r)  { return (u32)(r.w0.x >> 32) & 0xff; }
+__device__ __forceinline__ u32 R_from(const Rec& r)  { return (u32)(r.w0.x >> 40) & 0xff; }
+__device__ __forceinline__ u32 R_flags(const Rec& r) { return (u32)(r.w0.x >> 48) & 0xff; }
+__device__ __forceinline__ u32 R_n(const Rec& r)     { return (u32)r.w0.y & 0xffff; }
+__device__ __forceinline__ u32 R_n1(const Rec& r)    { return (u32)(r.w0.y >> 16) & 0xffff; }
+__device__ __forceinline__ u64 R_term(const Rec& r)  { return r.w1.x; }
+__device__ __forceinline__ u64 R_a(const Rec& r)     { return r.w1.y; }
+__device__ __forceinline__ u64 R_b(const Rec& r)     { return r.w2.x; }
+__device__ __forceinline__ u64 R_c(const Rec& r)     { return r.w2.y; }
+__device__ __forceinline__ u64 R_d(const Rec& r)     { return r.w3.x; }
+__device__ __forceinline__ u64 R_e(const Rec& r)     { return r.w3.y; }
+
+__device__ __forceinline__ Rec mk_rec(u32 row, u32 type, u32 from, u32 flags, u32 n, u32 n1, u32 seq,
+                                      u64 term, u64 a, u64 b, u64 c, u64 d, u64 e)
+{
+    Rec r;
+    r.w0.x = (u64)row | ((u64)(type & 0xff) << 32) | ((u64)(from & 0xff) << 40) | ((u64)(flags & 0xff) << 48);
+    r.w0.y = (u64)(n & 0xffff) | ((u64)(n1 & 0xffff) << 16) | ((u64)seq << 32);
+    r.w1.x = term; r.w1.y = a; r.w2.x = b; r.w2.y = c; r.w3.x = d; r.w3.y = e;
+    return r;
+}
+__device__ __forceinline__ void R_set_row_seq(Rec& r, u32 row, u32 seq)
+{
+    r.w0.x = (r.w0.x & 0xFFFFFFFF00000000ull) | row;
+    r.w0.y = (r.w0.y & 0x00000000FFFFFFFFull) | ((u64)seq << 32);
+}
+__device__ __forceinline__ void R_set_from(Rec& r, u32 from)
+{
+    r.w0.x = (r.w0.x & ~(0xffull << 40)) | ((u64)(from & 0xff) << 40);
+}
+__device__ __forceinline__ void R_or_flags(Rec& r, u32 f)
+{
+    r.w0.x |= ((u64)(f & 0xff) << 48);
+}
+__device__ __forceinline__ void R_clear_pad(Rec& r) { r.w0.x &= ~(0xffull << 56); }
+
+// ------------------------------------------------------------------------------------
+// per-thread view of one member
+// ------------------------------------------------------------------------------------
+struct Member {
+    const Cols* C;
+    u32 row, slot, group;
+    // scalars (registers)
+    u64 term, commit, last_idx, last_term, lw_idx, lw_term, applied, meta;
+    u64 snap_idx, snap_term, token, token_ctr, first_idx, macver;
+    // outputs
+    u32 n_msgs, n_notes, status, fatal_code, role0;
+    u32 sent_to;                // 4 bits per peer slot: records put in (me -> slot) this step
+    // one note kept back so that a continuing WAL_APPEND / APPLY can merge into it
+    u32 pn_type, pn_slot; u64 pn_a, pn_b, pn_c;
+    // flood host model: the last two finalised WAL_APPEND notes
+    u32 w_n; u64 w0a, w0b, w0c, w1a, w1b, w1c;
+    // counters
+    u32 c_events, c_msgs, c_dropped, c_elections;
+    u64 c_commits, c_applied;
+    int nb;                     // mailbox buffer written this step
+};
+
+__device__ __forceinline__ u32 m_role(const Member& m) { return MT_ROLE(m.meta); }
+__device__ __forceinline__ u32 m_nruns(const Member& m) { return MT_NRUNS(m.meta); }
+__device__ __forceinline__ bool log_nonempty(const Member& m) { return m.first_idx <= m.last_idx; }
+
+__device__ __forceinline__ ulonglong2 run_get(const Member& m, u32 k)
+{ return m.C->run[(size_t)k * m.C->rows + m.row]; }
+__device__ __forceinline__ void run_set(const Member& m, u32 k, u64 start, u64 term)
+{ st2(&m.C->run[(size_t)k * m.C->rows + m.row], start, term); }
+
+__device__ __forceinline__ ulonglong2 peer_nm(const Member& m, u32 s)
+{ return m.C->pnm[(size_t)s * m.C->rows + m.row]; }
+__device__ __forceinline__ void peer_nm_set(const Member& m, u32 s, u64 next, u64 match)
+{ st2(&m.C->pnm[(size_t)s * m.C->rows + m.row], next, match); }
+__device__ __forceinline__ u64 peer_cs(const Member& m, u32 s)
+{ return m.C->pcs[(size_t)s * m.C->rows + m.row]; }
+__device__ __forceinline__ void peer_cs_set(const Member& m, u32 s, u64 v)
+{ m.C->pcs[(size_t)s * m.C->rows + m.row] = v; }
+
+// ---- log view -----------------------------------------------------------------------
+
+// run that holds idx (idx must be in range); returns k, fills start/term/end
+__device__ __forceinline__ u32 run_find(const Member& m, u64 idx, u64& start, u64& term, u64& end)
+{
+    u32 nr = m_nruns(m);
+    u64 e = m.last_idx;
+    for (u32 k = nr; k-- > 0;) {
+        ulonglong2 r = run_get(m, k);
+        if (r.x <= idx || k == 0) { start = r.x; term = r.y; end = e; return k; }
+        e = r.x - 1;
+    }
+    start = m.first_idx; term = m.last_term; end = m.last_idx;
+    return 0;
+}
+
+// ra_log:fetch_term/2 (ra_log.erl:1140-1152)
+__device__ __forceinline__ u64 log_fetch_term(const Member& m, i64 idx)
+{
+    if (idx < 0) return RA_UNDEF;
+    u64 i = (u64)idx;
+    if (!log_nonempty(m) || i < m.first_idx || i > m.last_idx) return RA_UNDEF;
+    if (i == m.last_idx) return m.last_term;
+    u64 s, t, e; run_find(m, i, s, t, e);
+    return t;
+}
+
+// ra_server:fetch_term/2 (:3158-3169): falls back on the snapshot
+__device__ __forceinline__ u64 srv_fetch_term(const Member& m, i64 idx)
+{
+    u64 t = log_fetch_term(m, idx);
+    if (t != RA_UNDEF) return t;
+    if (idx >= 0 && MT_HAS_SNAP(m.meta) && m.snap_idx == (u64)idx) return m.snap_term;
+    return RA_UNDEF;
+}
+
+// append n entries of one term at last_index+1 .. (ra_log:append/2, tail of write/2)
+__device__ __forceinline__ void log_append(Member& m, u64 n, u64 term)
+{
+    if (n == 0) return;
+    u32 nr = m_nruns(m);
+    u64 idx = m.last_idx + 1;
+    bool empty = !log_nonempty(m);
+    if (empty) { m.first_idx = idx; nr = 0; }
+    if (empty || nr == 0 || term != m.last_term) {
+        if (nr == RA_MAX_RUNS) {
+            // contract: forget the oldest run (horizon of RA_MAX_RUNS term runs)
+            for (u32 k = 0; k + 1 < RA_MAX_RUNS; k++) { ulonglong2 r = run_get(m, k + 1); run_set(m, k, r.x, r.y); }
+            nr = RA_MAX_RUNS - 1;
+            m.first_idx = run_get(m, 0).x;
+        }
+        run_set(m, nr, idx, term);
+        nr++;
+    }
+    MT_SET(m.meta, 19, 4, nr);
+    m.last_idx = idx + n - 1;
+    m.last_term = term;
+}
+
+// drop everything above idx; `fallback_term` is used when idx is no longer inside the log
+__device__ __forceinline__ void log_truncate(Member& m, u64 idx, u64 fallback_term)
+{
+    u32 nr = m_nruns(m);
+    while (nr > 0 && run_get(m, nr - 1).x > idx) nr--;
+    if (!log_nonempty(m) || idx < m.first_idx) {
+        nr = 0;
+        m.first_idx = idx + 1;
+        m.last_term = fallback_term;
+    } else {
+        m.last_term = run_get(m, nr - 1).y;
+    }
+    m.last_idx = idx;
+    MT_SET(m.meta, 19, 4, nr);
+}
+
+// ra_log:set_last_index/2 (ra_log.erl:800-845); false = {not_found,_}
+__device__ __forceinline__ bool log_set_last_index(Member& m, u64 idx)
+{
+    u64 t = log_fetch_term(m, (i64)idx);
+    bool has = MT_HAS_SNAP(m.meta) != 0;
+    bool at_snap = has && m.snap_idx == idx;
+    if (t == RA_UNDEF && !at_snap) return false;
+    if (at_snap) {
+        log_truncate(m, idx, m.snap_term);
+        m.last_term = m.snap_term;
+        m.lw_idx = m.snap_idx; m.lw_term = m.snap_term;
+        return true;
+    }
+    u64 lwidx = idx < m.lw_idx ? idx : m.lw_idx;
+    u64 lwterm = (has && m.snap_idx == lwidx) ? m.snap_term : log_fetch_term(m, (i64)lwidx);
+    log_truncate(m, idx, t);
+    m.last_term = t;
+    m.lw_idx = lwidx; m.lw_term = lwterm;
+    return true;
+}
+
+// ra_log:handle_event({written,Term,[{From,To}]}) (ra_log.erl:849-896): the reference walks
+// the range down one index at a time; with runs the same answer is found run by run.
+__device__ __forceinline__ void log_handle_written(Member& m, u64 term, u64 from, u64 to)
+{
+    u64 cur = to;
+    bool has = MT_HAS_SNAP(m.meta) != 0;
+    for (int guard = 0; guard < 2 * RA_MAX_RUNS + 4; guard++) {
+        bool in = log_nonempty(m) && cur >= m.first_idx && cur <= m.last_idx;
+        if (in) {
+            u64 s, t, e; run_find(m, cur, s, t, e);
+            if (t == term) { m.lw_idx = cur; m.lw_term = term; return; }
+            u64 lo = s > m.first_idx ? s : m.first_idx;      // every index in [lo,cur] mismatches
+            if (from > lo) return;                            // the walk ends inside the run
+            if (lo == 0 || lo - 1 < from) return;
+            cur = lo - 1;
+            continue;
+        }
+        if (has && cur <= m.snap_idx) return;                 // :871-881
+        if (cur > m.last_idx) {
+            // undefined above the log: the walk either meets the snapshot clause first ...
+            u64 stop = cur < m.snap_idx ? cur : m.snap_idx;
+            if (has && m.snap_idx > m.last_idx && stop >= from) return;
+            // ... or reaches last_index
+            if (m.last_idx < from) return;
+            cur = m.last_idx;
+            if (!(log_nonempty(m))) return;                   // below/outside: nothing can match
+            continue;
+        }
+        return;                                               // below the log: no effect either way
+    }
+}
+
+// ---- outputs ---------------------------------------------------------------------------
+
+__device__ __forceinline__ void set_fatal(Member& m, u32 code)
+{
+    if (!(m.status & RA_ST_FATAL)) { m.status |= RA_ST_FATAL; m.fatal_code = code; }
+    MT_SET(m.meta, 26, 1, 1);
+}
+
+__device__ __forceinline__ void note_store(Member& m, u32 k, u32 type, u32 slot, u32 aux, u64 a, u64 b, u64 c)
+{
+    ulonglong2* q = reinterpret_cast<ulonglong2*>(&m.C->onote[(size_t)k * m.C->rows + m.row]);
+    q[0] = make_ulonglong2((u64)m.row | ((u64)(type & 0xff) << 32) | ((u64)(slot & 0xff) << 40) | ((u64)(aux & 0xffff) << 48), a);
+    q[1] = make_ulonglong2(b, c);
+}
+
+__device__ __forceinline__ void note_flush(Member& m)
+{
+    if (m.pn_type == RA_NOTE_NONE) return;
+    note_store(m, m.n_notes - 1, m.pn_type, m.pn_slot, 0, m.pn_a, m.pn_b, m.pn_c);
+    if (m.pn_type == RA_NOTE_WAL_APPEND) {
+        m.w0a = m.w1a; m.w0b = m.w1b; m.w0c = m.w1c;
+        m.w1a = m.pn_a; m.w1b = m.pn_b; m.w1c = m.pn_c;
+        if (m.w_n < 2) m.w_n++;
+    }
+    m.pn_type = RA_NOTE_NONE;
+}
+
+__device__ __forceinline__ void note(Member& m, u32 type, u32 slot, u64 a, u64 b, u64 c)
+{
+    if (m.pn_type == type && type == RA_NOTE_WAL_APPEND && m.pn_c == c && m.pn_b + 1 == a) { m.pn_b = b; return; }
+    if (m.pn_type == type && type == RA_NOTE_APPLY && m.pn_b + 1 == a) { m.pn_b = b; return; }
+    if (m.n_notes >= RA_NOTE_CAP - 1) { m.status |= RA_ST_NOTE_OVERFLOW; return; }
+    note_flush(m);
+    m.n_notes++;
+    m.pn_type = type; m.pn_slot = slot; m.pn_a = a; m.pn_b = b; m.pn_c = c;
+}
+
+// send one RPC record to the member in `to` of my group
+__device__ __forceinline__ void emit_msg(Member& m, u32 to, Rec r)
+{
+    const Cols& C = *m.C;
+    if (to >= C.members) return;                        // unknown peer: nothing to send to
+    u32 dst = to * C.groups + m.group;
+    bool is_next = (R_flags(r) & RA_EVF_NEXT_EVENT) != 0;
+    if (!is_next) R_set_from(r, m.slot);
+    R_clear_pad(r);
+    if (C.routed && !is_next) {
+        u32 k = (m.sent_to >> (4 * to)) & 15u;
+        if (k >= RA_MBOX_DEPTH) { m.status |= RA_ST_MSG_DROPPED; m.c_dropped++; return; }
+        R_set_row_seq(r, dst, k);
+        st_rec(&C.mbox[m.nb][((size_t)m.slot * RA_MBOX_DEPTH + k) * C.rows + dst], r);
+        m.sent_to += 1u << (4 * to);
+        m.c_msgs++;
+        return;
+    }
+    if (m.n_msgs >= RA_MSG_CAP) { m.status |= RA_ST_MSG_DROPPED; m.c_dropped++; return; }
+    R_set_row_seq(r, dst, m.n_msgs);
+    st_rec(&C.omsg[(size_t)m.n_msgs * C.rows + m.row], r);
+    m.n_msgs++;
+    m.c_msgs++;
+}
+
+// ---- next-event queue (gen_statem semantics: new next_events go to the front) ----------
+struct NextQ { Rec q[4]; u32 n; };
+__device__ __forceinline__ void nq_push(NextQ& q, const Rec& r) { if (q.n < 4) q.q[q.n++] = r; }
+
+// ---- term / vote --------------------------------------------------------------------
+
+// update_term_and_voted_for/3 :3014-3031
+__device__ __forceinline__ void update_term_and_voted_for(Member& m, u64 term, u32 voted)
+{
+    if (term == m.term && voted == MT_VOTED(m.meta)) return;
+    m.term = term;
+    MT_SET(m.meta, 7, 4, voted);
+    m.status |= RA_ST_TERM_VOTE_CHANGED;
+}
+// update_term/2 :3033-3037
+__device__ __forceinline__ void update_term(Member& m, u64 term)
+{
+    if (term > m.term) update_term_and_voted_for(m, term, SLOT_NONE);
+}
+// is_candidate_log_up_to_date/3 :3132-3139
+__device__ __forceinline__ bool log_up_to_date(u64 idx, u64 term, u64 last_idx, u64 last_term)
+{
+    return term > last_term || (term == last_term && idx >= last_idx);
+}
+// required_quorum/1 :3969-3972
+__device__ __forceinline__ u32 required_quorum(const Member& m)
+{
+    u32 mask = (u32)(m.meta >> 56) & ((1u << m.C->members) - 1u);
+    return (u32)__popc(mask) / 2 + 1;
+}
+
+// append_entries_reply/3 :3597-3604
+__device__ __forceinline__ Rec aer_reply(const Member& m, u64 term, bool success)
+{
+    return mk_rec(0, RA_EV_AER_REPLY, 0, 0, 0, 0, 0, term, m.last_idx + 1, m.lw_idx, m.lw_term, success ? 1 : 0, 0);
+}
+__device__ __forceinline__ void reply_vote(Member& m, u32 to, u32 type, u64 term, u64 token, bool granted)
+{
+    emit_msg(m, to, mk_rec(0, type, 0, 0, 0, 0, 0, term, 0, 0, token, granted ? 1 : 0, 0));
+}
+
+// ---- apply / quorum -----------------------------------------------------------------
+
+// apply_to/3 :3217-3255 for '$usr' / same-version noop entries
+__device__ __forceinline__ void apply_to(Member& m, u64 upto)
+{
+    if (!(upto > m.applied)) return;
+    if (!MT_MV_OK(m.meta)) return;
+    u64 from = m.applied + 1;
+    u64 to = m.last_idx < upto ? m.last_idx : upto;
+    if (to < from) return;
+    note(m, RA_NOTE_APPLY, 0, from, to, 0);
+    m.c_applied += to - from + 1;
+    m.applied = to;
+}
+
+// evaluate_quorum/2 :3606-3619 with match_indexes/1 :3644-3655 and agreed_commit/1
+// :3657-3661.  The reference sorts [LastWritten | voter match indexes] descending and takes
+// element trunc(N/2)+1; the same element is the smallest value v of the list with
+// #{x >= v} >= trunc(N/2)+1 ... found by rank counting over <= 8 values, no sort.
+__device__ __forceinline__ void evaluate_quorum(Member& m)
+{
+    const u32 M = m.C->members;
+    u64 v[RA_MAX_MEMBERS + 1];
+    u32 n = 0;
+    v[n++] = m.lw_idx;
+#pragma unroll
+    for (u32 s = 0; s < RA_MAX_MEMBERS; s++) {
+        if (s < M && s != m.slot && MT_VOTER(m.meta, s)) v[n++] = peer_nm(m, s).y;
+    }
+    u32 nth = n / 2 + 1;
+    u64 best = 0; bool found = false;
+    for (u32 i = 0; i < n; i++) {
+        u32 ge = 0;
+        for (u32 j = 0; j < n; j++) ge += (v[j] >= v[i]) ? 1u : 0u;
+        if (ge >= nth && (!found || v[i] > best)) { best = v[i]; found = true; }
+    }
+    u64 ci0 = m.commit;
+    if (srv_fetch_term(m, (i64)best) == m.term) m.commit = best;        // §5.4.2 gate :3625-3629
+    if (m.commit > ci0) {
+        note(m, RA_NOTE_COMMIT, 0, ci0, m.commit, 0);
+        m.c_commits += m.commit - ci0;
+    }
+    apply_to(m, m.commit);
+}
+
+// evaluate_commit_index_follower/2 :2229-2263
+__device__ __forceinline__ void evaluate_commit_index_follower(Member& m)
+{
+    if (MT_LEADER(m.meta) == SLOT_NONE) return;
+    apply_to(m, m.last_idx < m.commit ? m.last_idx : m.commit);
+}
+
+// ---- leader RPC generation --------------------------------------------------------------
+
+// make_append_entries_rpc/6 :2401-2418 -> new next index
+__device__ __forceinline__ u64 make_aer(Member& m, u32 peer, i64 prev_idx, u64 prev_term, u64 num)
+{
+    u64 last = m.last_idx;
+    u64 from = (u64)(prev_idx + 1);
+    u64 to = (u64)prev_idx + num; if (last < to) to = last;
+    u32 n = 0, n1 = 0; u64 d = 0, e = 0;
+    if (to >= from && log_nonempty(m) && from >= m.first_idx && from <= m.last_idx) {
+        u64 s, t, end; u32 k = run_find(m, from, s, t, end);
+        d = t;
+        if (end < to) {                                   // second run; contract: cut after it
+            n1 = (u32)(end - from + 1);
+            ulonglong2 r2 = run_get(m, k + 1);
+            e = r2.y;
+            u64 end2 = (k + 2 < m_nruns(m)) ? run_get(m, k + 2).x - 1 : m.last_idx;
+            if (end2 < to) to = end2;
+        }
+        n = (u32)(to - from + 1);
+    } else {
+        to = from - 1; if (last < to) to = last;
+    }
+    emit_msg(m, peer, mk_rec(0, RA_EV_AER, 0, 0, n, n1, 0, m.term, (u64)prev_idx, prev_term, m.commit, d, e));
+    return to + 1;
+}
+
+// make_rpc_effect/5 :2365-2399
+__device__ __forceinline__ u64 make_rpc_effect(Member& m, u32 peer, u64 next, u64 max_batch, bool& snapshot)
+{
+    i64 prev = (i64)next - 1;
+    snapshot = false;
+    u64 pt = log_fetch_term(m, prev);
+    if (pt != RA_UNDEF) return make_aer(m, peer, prev, pt, max_batch);
+    if (!MT_HAS_SNAP(m.meta)) { set_fatal(m, RA_FATAL_NO_SNAPSHOT); return next; }
+    if (prev >= 0 && m.snap_idx == (u64)prev) return make_aer(m, peer, prev, m.snap_term, max_batch);
+    if (!(prev < (i64)m.snap_idx)) { set_fatal(m, RA_FATAL_ASSERT); return next; }
+    snapshot = true;
+    note(m, RA_NOTE_SEND_SNAPSHOT, peer, peer, m.snap_idx, 0);
+    return m.snap_idx;
+}
+
+// make_pipelined_rpc_effects/3 :2268-2329 -> More
+__device__ __forceinline__ bool make_pipelined_rpcs(Member& m, bool force)
+{
+    const Cols& C = *m.C;
+    u64 next_log_idx = m.last_idx + 1;
+    i64 max_pipe = C.max_pipeline, max_batch = C.max_batch;
+    bool more = false;
+    for (u32 s = 0; s < C.members; s++) {
+        if (s == m.slot) continue;
+        if (MT_PSTATUS(m.meta, s) != RA_PEER_NORMAL) continue;
+        ulonglong2 nm = peer_nm(m, s);
+        u64 cs = peer_cs(m, s);
+        if (!(nm.x < next_log_idx || cs < m.commit)) continue;
+        i64 in_flight = (i64)nm.x - (i64)nm.y - 1;
+        if (!(in_flight < max_pipe || force)) continue;
+        i64 bs = max_pipe - in_flight; if (max_batch < bs) bs = max_batch; if (bs < 1) bs = 1;
+        bool snap;
+        u64 nn = make_rpc_effect(m, s, nm.x, (u64)bs, snap);
+        if (MT_FATAL(m.meta)) return false;
+        if (!(nn >= nm.x)) { set_fatal(m, RA_FATAL_ASSERT); return false; }
+        peer_nm_set(m, s, nn, nm.y);
+        peer_cs_set(m, s, m.commit);
+        if (snap && !C.pure) MT_SET(m.meta, 32 + 3 * s, 3, RA_PEER_SENDING_SNAPSHOT);
+        i64 nif = (i64)nn - (i64)nm.y - 1;
+        if (nn < next_log_idx && nif < max_pipe) more = true;
+    }
+    return more;
+}
+
+// make_rpcs_for/2 over stale_peers/1 (:2985-3003) or all normal peers (make_all_rpcs/1)
+__device__ __forceinline__ void make_rpcs(Member& m, bool all)
+{
+    const Cols& C = *m.C;
+    for (u32 s = 0; s < C.members; s++) {
+        if (s == m.slot) continue;
+        if (MT_PSTATUS(m.meta, s) != RA_PEER_NORMAL) continue;
+        ulonglong2 nm = peer_nm(m, s);
+        if (!all) {
+            bool stale = ((i64)nm.y < (i64)nm.x - 1) || (peer_cs(m, s) < m.commit);
+            if (!stale) continue;
+        }
+        bool snap;
+        (void)make_rpc_effect(m, s, nm.x, 1, snap);
+        if (MT_FATAL(m.meta)) return;
+    }
+}
+
+// initialise_peers/1 :3207-3215
+__device__ __forceinline__ void initialise_peers(Member& m)
+{
+    u64 next = m.last_idx + 1;
+    for (u32 s = 0; s < m.C->members; s++) {
+        peer_nm_set(m, s, next, 0);
+        peer_cs_set(m, s, 0);
+        MT_SET(m.meta, 32 + 3 * s, 3, RA_PEER_NORMAL);
+    }
+}
+
+// ---- elections --------------------------------------------------------------------------
+
+// call_for_election/3 :2853-2897
+__device__ __forceinline__ u32 call_for_election(Member& m, u32 target, NextQ& nq)
+{
+    Rec self, req;
+    if (target == RA_CANDIDATE) {
+        u64 nt = m.term + 1;
+        req = mk_rec(0, RA_EV_REQUEST_VOTE, 0, 0, 0, 0, 0, nt, m.last_idx, m.last_term, 0, 0, 0);
+        self = mk_rec(m.row, RA_EV_REQUEST_VOTE_RES, m.slot, 0, 0, 0, 0, nt, 0, 0, 0, 1, 0);
+        update_term_and_voted_for(m, nt, m.slot);
+    } else {
+        u64 token = ++m.token_ctr;                                  // make_ref()
+        u64 mv = m.macver & 0xffffffffull;
+        req = mk_rec(0, RA_EV_PRE_VOTE, 0, 0, 0, 0, 0, m.term, m.last_idx, m.last_term, token, 1ull | (mv << 32), 0);
+        self = mk_rec(m.row, RA_EV_PRE_VOTE_RES, m.slot, 0, 0, 0, 0, m.term, 0, 0, token, 1, 0);
+        update_term_and_voted_for(m, m.term, m.slot);
+        m.token = token;
+    }
+    MT_SET(m.meta, 3, 4, SLOT_NONE);       // leader_id => undefined
+    MT_SET(m.meta, 15, 4, 0);              // votes => 0
+    nq_push(nq, self);                     // {next_event, cast, VoteForSelf}
+    for (u32 s = 0; s < m.C->members; s++)
+        if (s != m.slot) emit_msg(m, s, req);
+    return target;
+}
+
+// process_pre_vote/3 :2899-2956
+__device__ __forceinline__ u32 process_pre_vote(Member& m, u32 fsm, const Rec& e)
+{
+    u64 term = R_term(e), token = R_c(e);
+    u32 version = (u32)(R_d(e) & 0xffffffffull), their = (u32)(R_d(e) >> 32);
+    u32 macver = (u32)(m.macver & 0xffffffffull), eff = (u32)(m.macver >> 32);
+    u32 cand = R_from(e);
+    if (term >= m.term) {
+        update_term(m, term);
+        if (log_up_to_date(R_a(e), R_b(e), m.last_idx, m.last_term)) {
+            if (version > 1) reply_vote(m, cand, RA_EV_PRE_VOTE_RES, term, token, false);
+            else if (their == eff || (their >= eff && their <= macver))
+                reply_vote(m, cand, RA_EV_PRE_VOTE_RES, term, token, true);
+            else { reply_vote(m, cand, RA_EV_PRE_VOTE_RES, term, token, false); m.status |= RA_ST_START_ELECTION_TMO; }
+        } else if (fsm == RA_FOLLOWER) {
+            m.status |= RA_ST_START_ELECTION_TMO;
+        } else {
+            reply_vote(m, cand, RA_EV_PRE_VOTE_RES, term, token, false);
+        }
+    } else {
+        reply_vote(m, cand, RA_EV_PRE_VOTE_RES, m.term, token, false);
+    }
+    return fsm;
+}
+
+// has_log_entry_or_snapshot/3 :3141-3156  (0 ok, 1 missing, 2 term_mismatch)
+__device__ __forceinline__ u32 has_entry(const Member& m, u64 idx, u64 term)
+{
+    u64 t = log_fetch_term(m, (i64)idx);
+    if (t == RA_UNDEF) {
+        if (MT_HAS_SNAP(m.meta) && m.snap_idx == idx) return m.snap_term == term ? 0u : 2u;
+        return 1u;
+    }
+    return t == term ? 0u : 2u;
+}
+
+__device__ __forceinline__ void remember_cond_reply(Member& m, u32 reason, const Rec& rp)
+{
+    const Cols& C = *m.C;
+    MT_SET(m.meta, 13, 2, reason);
+    MT_SET(m.meta, 25, 1, 1);
+    st2(&C.cd[m.row], R_term(rp), R_a(rp));
+    st2(&C.cd[(size_t)C.rows + m.row], R_b(rp), R_c(rp));
+}
+
+// ---- handle_follower/2 :1264-1641 -----------------------------------------------------------
+__device__ __noinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& nq)
+{
+    const u32 type = R_type(e);
+    if (type == RA_EV_AER) {
+        u64 term = R_term(e), cur = m.term;
+        u32 leader = R_from(e);
+        if (term >= cur) {
+            u64 pl_idx = R_a(e), pl_term = R_b(e), leader_commit = R_c(e);
+            u32 n0 = R_n(e), n1 = R_n1(e);
+            m.status |= RA_ST_LEADER_MSG;
+            MT_SET(m.meta, 3, 4, leader);
+            update_term(m, term);
+            u32 r = has_entry(m, pl_idx, pl_term);
+            if (r == 0) {
+                // drop_existing/3 :3673-3681, run by run instead of entry by entry
+                u64 idx = pl_idx + 1, stop = pl_idx + n0;
+                while (idx <= stop) {
+                    if (!log_nonempty(m) || idx < m.first_idx || idx > m.last_idx) break;
+                    u64 s, t, end; run_find(m, idx, s, t, end);
+                    bool first_piece = (n1 != 0) && (idx - (pl_idx + 1) < n1);
+                    u64 et = (n1 == 0 || first_piece) ? R_d(e) : R_e(e);
+                    u64 pe = first_piece ? pl_idx + n1 : stop;
+                    if (t != et) break;
+                    u64 seg = end < pe ? end : pe;
+                    idx = seg + 1;
+                }
+                u64 k = idx - (pl_idx + 1);
+                u64 last_valid = idx - 1;
+                if (k == n0) {                                             // Entries == [] :1288
+                    u64 local_last = m.last_idx;
+                    bool validated;
+                    if (n0 == 0 && local_last > pl_idx) {                  // :1294-1303
+                        if (pl_idx < m.applied) { set_fatal(m, RA_FATAL_ASSERT); return RA_FOLLOWER; }
+                        if (!log_set_last_index(m, pl_idx)) { set_fatal(m, RA_FATAL_SET_LAST_INDEX_NOT_FOUND); return RA_FOLLOWER; }
+                        note(m, RA_NOTE_TRUNCATE, 0, m.last_idx, m.last_term, 0);
+                        validated = true;
+                    } else validated = local_last <= last_valid;
+                    if (validated) {                                       // :1313-1326
+                        m.commit = leader_commit;
+                        evaluate_commit_index_follower(m);
+                        emit_msg(m, leader, aer_reply(m, term, true));
+                    } else {                                               // :1327-1346
+                        u64 lvi = m.applied > last_valid ? m.applied : last_valid;
+                        emit_msg(m, leader, mk_rec(0, RA_EV_AER_REPLY, 0, 0, 0, 0, 0, cur, lvi + 1, lvi,
+                                                   srv_fetch_term(m, (i64)lvi), 1, 0));
+                    }
+                    return RA_FOLLOWER;
+                }
+                // [{FstIdx,_,_}|_] :1348-1371
+                u64 fst = pl_idx + 1 + k;
+                if (fst < m.applied) { set_fatal(m, RA_FATAL_ASSERT); return RA_FOLLOWER; }
+                if (!(fst <= m.last_idx + 1) || (!log_nonempty(m) && fst != m.last_idx + 1)) {
+                    set_fatal(m, RA_FATAL_WRITE_INTEGRITY); return RA_FOLLOWER;
+                }
+                m.commit = leader_commit;
+                if (fst <= m.last_idx) {
+                    u64 pt = log_fetch_term(m, (i64)fst - 1);
+                    log_truncate(m, fst - 1, pt != RA_UNDEF ? pt : m.snap_term);
+                }
+                // remaining entries fst..stop: at most two term pieces
+                u64 split = (n1 != 0) ? pl_idx + n1 : stop;       // last index of the first piece
+                if (n1 != 0 && fst <= split) {
+                    u64 c1 = split - fst + 1;
+                    log_append(m, c1, R_d(e));
+                    note(m, RA_NOTE_WAL_APPEND, 0, fst, split, R_d(e));
+                    if (stop > split) {
+                        if (R_e(e) == R_d(e)) { log_append(m, stop - split, R_e(e)); note(m, RA_NOTE_WAL_APPEND, 0, split + 1, stop, R_e(e)); }
+                        else { log_append(m, stop - split, R_e(e)); note(m, RA_NOTE_WAL_APPEND, 0, split + 1, stop, R_e(e)); }
+                    }
+                } else {
+                    u64 t = (n1 == 0) ? R_d(e) : R_e(e);
+                    log_append(m, stop - fst + 1, t);
+                    note(m, RA_NOTE_WAL_APPEND, 0, fst, stop, t);
+                }
+                evaluate_commit_index_follower(m);
+                return RA_FOLLOWER;
+            }
+            if (r == 1) {                                                  // missing :1373-1387
+                Rec rp = aer_reply(m, term, false);
+                remember_cond_reply(m, 1, rp);
+                emit_msg(m, leader, rp);
+                return RA_AWAIT_CONDITION;
+            }
+            // term_mismatch :1388-1413 -> mismatch_append_entries_reply/3 :3587-3595
+            u64 la = m.applied, lat = srv_fetch_term(m, (i64)la);
+            if (lat == RA_UNDEF) { set_fatal(m, RA_FATAL_ASSERT); return RA_FOLLOWER; }
+            Rec rp = mk_rec(0, RA_EV_AER_REPLY, 0, 0, 0, 0, 0, term, la + 1, la, lat, 0, 0);
+            remember_cond_reply(m, 2, rp);
+            emit_msg(m, leader, rp);
+            return RA_AWAIT_CONDITION;
+        }
+        emit_msg(m, leader, aer_reply(m, cur, false));                     // :1415-1424
+        return RA_FOLLOWER;
+    }
+    if (type == RA_EV_WRITTEN) {                                           // :1441-1458
+        u64 a = m.lw_idx, b = m.lw_term;
+        log_handle_written(m, R_term(e), R_a(e), R_b(e));
+        u32 leader = MT_LEADER(m.meta);
+        if ((a != m.lw_idx || b != m.lw_term) && leader != SLOT_NONE)
+            emit_msg(m, leader, aer_reply(m, m.term, true));
+        return RA_FOLLOWER;
+    }
+    if (type == RA_EV_PRE_VOTE) {                                          // :1459-1466
+        if (MT_MEMBERSHIP(m.meta) != RA_VOTER) return RA_FOLLOWER;
+        return process_pre_vote(m, RA_FOLLOWER, e);
+    }
+    if (type == RA_EV_REQUEST_VOTE) {                                      // :1467-1513
+        if (MT_MEMBERSHIP(m.meta) != RA_VOTER) return RA_FOLLOWER;
+        u64 term = R_term(e), cur = m.term;
+        u32 cand = R_from(e), voted = MT_VOTED(m.meta);
+        if (term == cur && voted != SLOT_NONE && voted != (cand & 15u)) {
+            reply_vote(m, cand, RA_EV_REQUEST_VOTE_RES, term, 0, false);
+        } else if (term >= cur) {
+            update_term(m, term);
+            if (log_up_to_date(R_a(e), R_b(e), m.last_idx, m.last_term)) {
+                reply_vote(m, cand, RA_EV_REQUEST_VOTE_RES, term, 0, true);
+                update_term_and_voted_for(m, term, cand & 15u);
+            } else reply_vote(m, cand, RA_EV_REQUEST_VOTE_RES, term, 0, false);
+        } else reply_vote(m, cand, RA_EV_REQUEST_VOTE_RES, cur, 0, false);
+        return RA_FOLLOWER;
+    }
+    if (type == RA_EV_AER_REPLY) {                                         // :1514-1517
+        update_term(m, R_term(e) > m.term ? R_term(e) : m.term);
+        return RA_FOLLOWER;
+    }
+    if (type == RA_EV_ELECTION_TIMEOUT) {                                  // :1603-1610
+        if (MT_MEMBERSHIP(m.meta) != RA_VOTER) return RA_FOLLOWER;
+        return call_for_election(m, RA_PRE_VOTE, nq);
+    }
+    if (type == RA_EV_COMMAND) {
+        u32 l = MT_LEADER(m.meta);
+        note(m, RA_NOTE_NOT_LEADER, 0, R_n(e), l == SLOT_NONE ? RA_NO_SLOT : l, 0);
+    }
+    return RA_FOLLOWER;
+}
+
+// ---- handle_leader/2 :520-1023 --------------------------------------------------------------
+__device__ __forceinline__ Rec pipeline_event(const Member& m)
+{
+    return mk_rec(m.row, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, RA_EVF_INFO, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+}
+__device__ __forceinline__ u32 step_down(Member& m, u64 term)
+{
+    MT_SET(m.meta, 3, 4, SLOT_NONE);
+    update_term(m, term);
+    return RA_FOLLOWER;
+}
+
+__device__ __noinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
+{
+    const Cols& C = *m.C;
+    const u32 type = R_type(e);
+    if (type == RA_EV_AER_REPLY) {
+        u64 term = R_term(e);
+        u32 from = R_from(e);
+        bool success = R_d(e) != 0;
+        bool known = from < C.members;
+        if (success && term == m.term) {                                   // :522-561
+            if (!known) return RA_LEADER;
+            ulonglong2 nm = peer_nm(m, from);
+            u64 nn = R_a(e) > nm.x ? R_a(e) : nm.x;
+            u64 mm = R_b(e) > nm.y ? R_b(e) : nm.y;
+            peer_nm_set(m, from, nn, mm);
+            evaluate_quorum(m);
+            nq_push(nq, pipeline_event(m));
+            return RA_LEADER;
+        }
+        if (term > m.term) {                                               // :562-576
+            if (!known) return RA_LEADER;
+            return step_down(m, term);
+        }
+        if (!success) {                                                    // :577-643
+            if (!known) return RA_LEADER;
+            ulonglong2 nm = peer_nm(m, from);
+            u64 pnext = R_a(e), plast = R_b(e), plast_term = R_c(e);
+            u64 t = log_fetch_term(m, (i64)plast);
+            u64 nn = nm.x, mm = nm.y;
+            if (t == RA_UNDEF) nn = pnext;
+            else if (t == plast_term && plast >= nm.y) { mm = plast; nn = pnext; }
+            else if (plast < nm.y) { mm = plast; nn = plast + 1; }
+            else {
+                i64 a = (i64)nm.x - 1, b = (i64)pnext;
+                i64 x = a < b ? a : b;
+                nn = x > (i64)nm.y ? (u64)x : nm.y;
+            }
+            peer_nm_set(m, from, nn, mm);
+            (void)make_pipelined_rpcs(m, false);
+        }
+        return RA_LEADER;
+    }
+    if (type == RA_EV_COMMAND) {                                           // :644-729
+        u64 n = R_n(e);
+        if (n == 0) return RA_LEADER;
+        u64 from = m.last_idx + 1;
+        log_append(m, n, m.term);                                          // append_log_leader/3
+        note(m, RA_NOTE_WAL_APPEND, 0, from, from + n - 1, m.term);
+        (void)make_pipelined_rpcs(m, (R_flags(e) & RA_EVF_NOOP) != 0);
+        return RA_LEADER;
+    }
+    if (type == RA_EV_WRITTEN) {                                           // :730-735
+        log_handle_written(m, R_term(e), R_a(e), R_b(e));
+        evaluate_quorum(m);
+        nq_push(nq, pipeline_event(m));
+        return RA_LEADER;
+    }
+    if (type == RA_EV_PIPELINE_RPCS) {                                     // :784-792
+        if (make_pipelined_rpcs(m, false)) nq_push(nq, pipeline_event(m));
+        return RA_LEADER;
+    }
+    if (type == RA_EV_AER) {
+        if (R_term(e) > m.term) { u32 r = step_down(m, R_term(e)); nq_push(nq, e); return r; }   // :826-835
+        if (R_term(e) == m.term) { set_fatal(m, RA_FATAL_LEADER_SAW_AER_SAME_TERM); return RA_LEADER; } // :836-840
+        emit_msg(m, R_from(e), aer_reply(m, m.term, false));               // :841-845
+        return RA_LEADER;
+    }
+    if (type == RA_EV_REQUEST_VOTE) {
+        if (R_term(e) > m.term) {                                          // :919-933
+            if (R_from(e) >= C.members) return RA_LEADER;
+            u32 r = step_down(m, R_term(e)); nq_push(nq, e); return r;
+        }
+        reply_vote(m, R_from(e), RA_EV_REQUEST_VOTE_RES, m.term, 0, false);     // :934-936
+        return RA_LEADER;
+    }
+    if (type == RA_EV_PRE_VOTE) {
+        if (R_term(e) > m.term) {                                          // :937-951
+            if (R_from(e) >= C.members) return RA_LEADER;
+            u32 r = step_down(m, R_term(e)); nq_push(nq, e); return r;
+        }
+        make_rpcs(m, true);                                                // :952-957
+        return RA_LEADER;
+    }
+    if (type == RA_EV_TICK) make_rpcs(m, false);                           // ra_server_proc.erl:610-613
+    return RA_LEADER;
+}
+
+// ---- handle_candidate/2 :1026-1171 ----------------------------------------------------------
+__device__ __noinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& nq)
+{
+    const u32 type = R_type(e);
+    if (type == RA_EV_REQUEST_VOTE_RES) {
+        if (R_d(e) && R_term(e) == m.term) {                               // :1028-1044
+            u32 nv = MT_VOTES(m.meta) + 1;
+            if (nv == required_quorum(m)) {
+                MT_SET(m.meta, 3, 4, m.slot);
+                initialise_peers(m);
+                MT_SET(m.meta, 15, 4, 0);
+                nq_push(nq, mk_rec(m.row, RA_EV_COMMAND, RA_NO_SLOT, RA_EVF_NOOP, 1, 0, 0, 0, 0, 0, 0, 0, 0));
+                m.c_elections++;
+                return RA_LEADER;
+            }
+            MT_SET(m.meta, 15, 4, nv);
+            return RA_CANDIDATE;
+        }
+        if (R_term(e) > m.term) { update_term_and_voted_for(m, R_term(e), SLOT_NONE); return RA_FOLLOWER; }  // :1045-1052
+        return RA_CANDIDATE;
+    }
+    if (type == RA_EV_AER) {
+        if (R_term(e) >= m.term) {                                         // :1055-1058
+            update_term_and_voted_for(m, R_term(e), SLOT_NONE);
+            nq_push(nq, e);
+            return RA_FOLLOWER;
+        }
+        emit_msg(m, R_from(e), aer_reply(m, m.term, false));               // :1059-1063
+        return RA_CANDIDATE;
+    }
+    if (type == RA_EV_AER_REPLY) {
+        if (R_term(e) > m.term) { update_term_and_voted_for(m, R_term(e), SLOT_NONE); return RA_FOLLOWER; }  // :1082-1090
+        return RA_CANDIDATE;
+    }
+    if (type == RA_EV_REQUEST_VOTE) {
+        if (R_term(e) > m.term) {                                          // :1091-1098
+            update_term_and_voted_for(m, R_term(e), SLOT_NONE);
+            nq_push(nq, e);
+            return RA_FOLLOWER;
+        }
+        reply_vote(m, R_from(e), RA_EV_REQUEST_VOTE_RES, m.term, 0, false);     // :1107-1109
+        return RA_CANDIDATE;
+    }
+    if (type == RA_EV_PRE_VOTE) {
+        if (R_term(e) > m.term) {                                          // :1099-1106
+            update_term_and_voted_for(m, R_term(e), SLOT_NONE);
+            nq_push(nq, e);
+            return RA_FOLLOWER;
+        }
+        return process_pre_vote(m, RA_CANDIDATE, e);                       // :1110-1114
+    }
+    if (type == RA_EV_WRITTEN) { log_handle_written(m, R_term(e), R_a(e), R_b(e)); return RA_CANDIDATE; }
+    if (type == RA_EV_ELECTION_TIMEOUT) return call_for_election(m, RA_CANDIDATE, nq);
+    if (type == RA_EV_COMMAND) {
+        u32 l = MT_LEADER(m.meta);
+        note(m, RA_NOTE_NOT_LEADER, 0, R_n(e), l == SLOT_NONE ? RA_NO_SLOT : l, 0);
+    }
+    return RA_CANDIDATE;
+}
+
+// ---- handle_pre_vote/2 :1173-1261 -----------------------------------------------------------
+__device__ __noinline__ u32 handle_pre_vote(Member& m, const Rec& e, NextQ& nq)
+{
+    const u32 type = R_type(e);
+    if (type == RA_EV_AER) {
+        if (R_term(e) >= m.term) {                                         // :1175-1180
+            update_term(m, R_term(e));
+            MT_SET(m.meta, 15, 4, 0);
+            nq_push(nq, e);
+            return RA_FOLLOWER;
+        }
+        return RA_PRE_VOTE;
+    }
+    if (type == RA_EV_REQUEST_VOTE) {
+        if (R_term(e) > m.term) {                                          // :1196-1201
+            update_term(m, R_term(e));
+            MT_SET(m.meta, 15, 4, 0);
+            nq_push(nq, e);
+            return RA_FOLLOWER;
+        }
+        return RA_PRE_VOTE;
+    }
+    if (type == RA_EV_PRE_VOTE_RES) {
+        if (R_term(e) > m.term) {                                          // :1202-1207
+            update_term(m, R_term(e));
+            MT_SET(m.meta, 15, 4, 0);
+            return RA_FOLLOWER;
+        }
+        if (R_d(e) && R_term(e) == m.term && R_c(e) == m.token && MT_MEMBERSHIP(m.meta) == RA_VOTER) {  // :1212-1229
+            u32 nv = MT_VOTES(m.meta) + 1;
+            if (nv == required_quorum(m)) return call_for_election(m, RA_CANDIDATE, nq);
+            MT_SET(m.meta, 15, 4, nv);
+        }
+        return RA_PRE_VOTE;
+    }
+    if (type == RA_EV_PRE_VOTE) return process_pre_vote(m, RA_PRE_VOTE, e);
+    if (type == RA_EV_ELECTION_TIMEOUT) return call_for_election(m, RA_PRE_VOTE, nq);
+    if (type == RA_EV_WRITTEN) { log_handle_written(m, R_term(e), R_a(e), R_b(e)); return RA_PRE_VOTE; }
+    if (type == RA_EV_COMMAND) {
+        u32 l = MT_LEADER(m.meta);
+        note(m, RA_NOTE_NOT_LEADER, 0, R_n(e), l == SLOT_NONE ? RA_NO_SLOT : l, 0);
+    }
+    return RA_PRE_VOTE;
+}
+
+// ---- handle_await_condition/2 :1900-1941 ------------------------------------------------------
+__device__ __noinline__ u32 handle_await_condition(Member& m, const Rec& e, NextQ& nq)
+{
+    const Cols& C = *m.C;
+    const u32 type = R_type(e);
+    if (type == RA_EV_REQUEST_VOTE) { nq_push(nq, e); return RA_FOLLOWER; }           // :1902-1903
+    if (type == RA_EV_PRE_VOTE) return process_pre_vote(m, RA_AWAIT_CONDITION, e);    // :1904-1905
+    if (type == RA_EV_ELECTION_TIMEOUT) {                                             // :1906-1913
+        if (MT_MEMBERSHIP(m.meta) != RA_VOTER) return RA_AWAIT_CONDITION;
+        return call_for_election(m, RA_PRE_VOTE, nq);
+    }
+    if (type == RA_EV_AWAIT_COND_TIMEOUT) {                                           // :1914-1927
+        u32 leader = MT_LEADER(m.meta);
+        if (MT_COND_VALID(m.meta) && leader != SLOT_NONE) {
+            ulonglong2 c0 = C.cd[m.row], c1 = C.cd[(size_t)C.rows + m.row];
+            emit_msg(m, leader, mk_rec(0, RA_EV_AER_REPLY, 0, 0, 0, 0, 0, c0.x, c0.y, c1.x, c1.y, 0, 0));
+            m.status |= RA_ST_LEADER_MSG;
+        }
+        MT_SET(m.meta, 13, 2, 0); MT_SET(m.meta, 25, 1, 0);
+        return RA_FOLLOWER;
+    }
+    if (type == RA_EV_WRITTEN) { log_handle_written(m, R_term(e), R_a(e), R_b(e)); return RA_AWAIT_CONDITION; }
+    if (type == RA_EV_AER) {                                                          // :1932-1941
+        bool ok = false;
+        if (R_term(e) >= m.term) {                                                    // :2184-2202
+            u32 r = has_entry(m, R_a(e), R_b(e));
+            ok = (r == 0) || (r == 2 && MT_COND(m.meta) == 1);
+        }
+        if (ok) {
+            MT_SET(m.meta, 13, 2, 0); MT_SET(m.meta, 25, 1, 0);
+            nq_push(nq, e);
+            return RA_FOLLOWER;
+        }
+        return RA_AWAIT_CONDITION;
+    }
+    if (type == RA_EV_COMMAND) m.status |= RA_ST_CMD_POSTPONED;
+    return RA_AWAIT_CONDITION;
+}
+
+// ---- the ra_server_proc shim ------------------------------------------------------------------
+__device__ __forceinline__ void process_event(Member& m, const Rec& in)
+{
+    const Cols& C = *m.C;
+    Rec pend[8]; u32 np = 0;
+    pend[np++] = in;
+    bool chased = false;
+    m.c_events++;
+    while (np > 0) {
+        if (MT_FATAL(m.meta)) return;
+        Rec e = pend[0];
+        np--;
+        for (u32 i = 0; i < np; i++) pend[i] = pend[i + 1];
+        if (R_type(e) == RA_EV_PIPELINE_RPCS && (R_flags(e) & RA_EVF_INFO)) {
+            // contract: one chased pipeline pass per input event; the rest runs next step
+            if (chased) { MT_SET(m.meta, 24, 1, 1); m.status |= RA_ST_PIPELINE_PENDING; continue; }
+            chased = true;
+        }
+        NextQ nq; nq.n = 0;
+        u32 old = m_role(m), nr;
+        switch (old) {
+        case RA_LEADER:          nr = handle_leader(m, e, nq); break;
+        case RA_FOLLOWER:        nr = handle_follower(m, e, nq); break;
+        case RA_CANDIDATE:       nr = handle_candidate(m, e, nq); break;
+        case RA_PRE_VOTE:        nr = handle_pre_vote(m, e, nq); break;
+        case RA_AWAIT_CONDITION: nr = handle_await_condition(m, e, nq); break;
+        default:                 nr = old; break;
+        }
+        if (MT_FATAL(m.meta)) return;
+        if (nr != old) {
+            MT_SET(m.meta, 0, 3, nr);
+            m.status |= RA_ST_ROLE_CHANGED;
+            if (!C.pure && nr == RA_FOLLOWER)                      // become/3 :2166-2175
+                m.meta &= ~(0xFFFFFFull << 32);
+            if (nr == RA_LEADER) m.status |= RA_ST_BECAME_LEADER;
+        }
+        if (C.pure) {
+            for (u32 i = 0; i < nq.n; i++) { Rec r = nq.q[i]; R_or_flags(r, RA_EVF_NEXT_EVENT); emit_msg(m, m.slot, r); }
+            continue;
+        }
+        // candidate -> leader: tick_timeout goes ahead of the effects' next events
+        // (ra_server_proc.erl:728-730)
+        Rec front[5]; u32 nf = 0;
+        if (nr == RA_LEADER && old == RA_CANDIDATE)
+            front[nf++] = mk_rec(m.row, RA_EV_TICK, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+        for (u32 i = 0; i < nq.n; i++) front[nf++] = nq.q[i];
+        if (nf) {
+            if (np + nf > 8) nf = 8 - np;
+            for (u32 i = np; i-- > 0;) pend[i + nf] = pend[i];
+            for (u32 i = 0; i < nf; i++) pend[i] = front[i];
+            np += nf;
+        }
+    }
+}

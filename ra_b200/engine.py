@@ -1,0 +1,83 @@
+"""Host binding of the CUDA engine (ra_b200/csrc/libra_engine.so) through its C ABI.
+
+There is deliberately no fallback: if the shared library is missing, or no CUDA device is
+present, construction raises -- the product path never routes through a CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "csrc", "libra_engine.so")
+_lib = None
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise EngineUnavailable(
+                "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). The engine has no CPU fallback." % _SO)
+        _lib = C.CDLL(_SO)
+        _lib.ra_engine_flood.restype = C.c_int
+        _lib.ra_engine_flood.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
+        _lib.ra_engine_sync.restype = C.c_int
+        _lib.ra_engine_sync.argtypes = [C.c_void_p]
+        _lib.ra_engine_last_kernel_ms.restype = C.c_int
+        _lib.ra_engine_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+        _lib.ra_engine_strerror.restype = C.c_char_p
+        _lib.ra_engine_strerror.argtypes = [C.c_int]
+        _lib.ra_engine_last_cuda_error.restype = C.c_char_p
+        _lib.ra_engine_last_cuda_error.argtypes = [C.c_void_p]
+    return _lib
+
+
+EXPORTS = ["ra_engine_create", "ra_engine_destroy", "ra_engine_load_rows", "ra_engine_reset_empty",
+           "ra_engine_read_rows", "ra_engine_step", "ra_engine_flood", "ra_engine_sync",
+           "ra_engine_counters", "ra_engine_last_kernel_ms", "ra_engine_strerror",
+           "ra_engine_last_cuda_error"]
+
+
+class Engine(abi.Backend):
+    """One engine = the Raft members resident on one GPU."""
+    name = "engine"
+
+    def __init__(self, n_groups: int, n_members: int, **kw):
+        try:
+            super().__init__(lib(), "ra_engine", n_groups, n_members, **kw)
+        except abi.RaError as e:
+            if e.status == abi.RA_E_NODEVICE:
+                raise EngineUnavailable("no CUDA device: the engine has no CPU fallback") from e
+            raise
+
+    def _check(self, st: int, what: str) -> None:
+        if st != abi.RA_OK:
+            msg = lib().ra_engine_strerror(st).decode()
+            if st == abi.RA_E_CUDA and self._h:
+                msg += ": " + lib().ra_engine_last_cuda_error(self._h).decode()
+            err = abi.RaError(st, "ra_engine_%s" % what)
+            err.args = ("%s (%s)" % (err.args[0], msg),)
+            raise err
+
+    def flood(self, n_steps: int, cmds_per_step: int = 1, election_permille: int = 0, seed: int = 1,
+              sync: bool = True) -> None:
+        self._check(lib().ra_engine_flood(self._h, n_steps, cmds_per_step, election_permille, seed), "flood")
+        if sync:
+            self.sync()
+
+    def sync(self) -> None:
+        self._check(lib().ra_engine_sync(self._h), "sync")
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0)
+        n = C.c_uint32(0)
+        self._check(lib().ra_engine_last_kernel_ms(self._h, C.byref(ms), C.byref(n)), "last_kernel_ms")
+        return float(ms.value), int(n.value)

@@ -1,0 +1,41 @@
+"""`-m "not gpu"`: the C-ABI library loads and exports every symbol include/ra_engine.h declares
+(no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "ra_engine.h")).read()
+    return sorted(set(re.findall(r"\b(ra_engine_[a-z_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    so = os.path.join(ROOT, "ra_b200", "csrc", "libra_engine.so")
+    assert os.path.exists(so), "build the engine first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(so)
+    names = _declared()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), n
+    from ra_b200 import engine
+    assert sorted(engine.EXPORTS) == names
+
+
+def test_record_sizes_match_header():
+    from ra_b200 import abi
+    assert ctypes.sizeof(abi.RaEvent) == 64 and ctypes.sizeof(abi.RaNote) == 32
+
+
+def test_no_device_fails_loudly():
+    """Without a GPU the product refuses to run instead of falling back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ra_b200.engine import Engine, EngineUnavailable
+    with pytest.raises(EngineUnavailable):
+        Engine(1, 3)
