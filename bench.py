@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- committed entries/sec across N Raft groups; HBM GB/s vs roofline.
+
+One "step" = one pass of the hot path (one raft_step launch) over every member row of the
+workload: all RPC records sent in the previous step are evaluated, every leader appends
+`cmds` client commands, every follower handles its AppendEntries / written events, quorum
+is evaluated, replies and new AppendEntries are emitted for the next step.
+
+ value      committed entries/s (sum of commit_index advances on leaders / device time), inputs
+            (mailboxes, log views, SoA) resident in HBM: ra_engine_flood, CUDA events on the
+            engine's stream, max over ranks.
+ e2e        the same flood driven through the public C ABI (ra_engine_step with pinned HOST
+            buffers; H2D of the step's events and D2H of its notes inside every step).
+ roofline   algorithmic bytes (B_commit(5) = 2884 B, B_commit(7) = 4282 B per
+            committed entry) / duration of the raft_step launches / measured HBM peak.
+ cpu_baseline  the CPU restatement of ra_server (oracle/, kind "port": the reference is Erlang
+            and no OTP toolchain exists on the box) on a bounded sample of the same workload.
+
+ --impl reference times that CPU port with all host threads (see DESIGN.md "reference arm").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_COMMIT = {3: 40 + 104 * 3 + 2 * (169 + 185) + (128 + 8 * 3) + 2 * (145 + 8 * 3),
+            5: 2884, 7: 4282}
+METRIC = "committed entries/sec across N Raft groups; HBM GB/s vs roofline"
+
+
+def b_commit(m: int) -> int:
+    return (40 + 104 * m) + (m - 1) * (169 + 185) + (128 + 8 * m) + (m - 1) * (145 + 8 * m)
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_init(n_gpus: int):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier_sync(world: int, local: int):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize(local)
+
+
+def reduce_max_sum(world: int, local: int, ms: float, commits: float, events: float):
+    if world == 1:
+        return ms, commits, events
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % local)
+    s = torch.tensor([commits, events], dtype=torch.float64, device="cuda:%d" % local)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    return float(t.item()), float(s[0].item()), float(s[1].item())
+
+
+def run_engine(args):
+    from ra_b200 import abi
+    from ra_b200.engine import Engine, HostFlood
+    import torch
+
+    rank, world, local = dist_init(args.gpus)
+    G, M = args.groups, args.members
+    dev = local
+    eng = Engine(G, M, device=dev, route_on_device=True)
+    eng.reset_empty()
+    eng.step([abi.ev_simple(eng.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(G)])
+    eng.flood(args.settle, args.cmds, args.permille, seed=args.seed + rank)       # elect leaders, fill the pipeline
+    eng.flood(args.warmup, args.cmds, args.permille, seed=args.seed + rank)       # W untimed warm-up steps
+    c0 = eng.counters()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    barrier_sync(world, local)
+    eng.flood(args.steps, args.cmds, args.permille, seed=args.seed + rank, sync=False)
+    eng.sync()
+    barrier_sync(world, local)
+    ms, launches = eng.last_kernel_ms()                       # CUDA events on the engine's stream
+    clocks = sampler.stop()
+    c1 = eng.counters()
+    commits = c1["commits"] - c0["commits"]
+    events = c1["events"] - c0["events"]
+    ms_max, commits_all, events_all = reduce_max_sum(world, local, ms, commits, events)
+    value = commits_all / (ms_max * 1e-3)
+
+    # e2e: the same flood through ra_engine_step with pinned host buffers (rank-local engine)
+    e2e = None
+    if not args.no_e2e:
+        eng2 = Engine(G, M, device=dev, route_on_device=True)
+        eng2.reset_empty()
+        hf = HostFlood(eng2)
+        hf.run(args.settle, args.cmds, args.permille, seed=args.seed + rank, bootstrap=True)
+        hf.run(min(args.warmup, 10), args.cmds, args.permille, seed=args.seed + rank)
+        d0 = eng2.counters()
+        barrier_sync(world, local)
+        st = hf.run(args.e2e_steps, args.cmds, args.permille, seed=args.seed + rank)
+        barrier_sync(world, local)
+        d1 = eng2.counters()
+        sec, ec, _ = reduce_max_sum(world, local, st["seconds"], d1["commits"] - d0["commits"], 0)
+        e2e = {"value": ec / sec, "unit": "commits/s",
+               "h2d_bytes_per_step": st["h2d_bytes"] // args.e2e_steps,
+               "d2h_bytes_per_step": st["d2h_bytes"] // args.e2e_steps,
+               "steps": args.e2e_steps, "ms_per_step": sec * 1e3 / args.e2e_steps,
+               "gpu_launches_per_step": 6}
+        hf.close()
+        eng2.close()
+
+    if rank != 0:
+        return
+    peak, peak_src = hbm_peak()
+    bc = b_commit(M)
+    achieved = (commits / (ms * 1e-3)) * bc / 1e9               # this rank's kernel, GB/s
+    out = {
+        "metric": METRIC, "value": value, "unit": "commits/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "%d groups x %d members per GPU, steady-state AppendEntries flood, %d command(s) per "
+                               "leader per step, %.1f%% election timeouts per step (BASELINE.json configs[2] shape)"
+                               % (G, M, args.cmds, args.permille / 10.0),
+                   "groups_per_gpu": G, "members": M, "cmds_per_step": args.cmds,
+                   "election_permille": args.permille, "parallelism": "groups sharded by rank, no data-path collective",
+                   "l2": "working set (SoA %.0f MB + mailboxes) exceeds the 126 MB L2; no explicit flush"
+                         % (G * M * 392 / 1e6),
+                   "events_per_step": events / args.steps, "commits_per_step": commits / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_commit": bc, "kernel": "raft_step_kernel"},
+    }
+    if e2e:
+        out["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(args, sample_groups=min(G, args.cpu_groups), steps=args.cpu_steps)
+    print(json.dumps(out))
+
+
+def cpu_baseline(args, sample_groups: int, steps: int, threads: int | None = None) -> dict:
+    """The oracle (CPU port of ra_server's hot path) on a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+    from ra_b200 import abi
+    cores = threads or os.cpu_count() or 1
+    o = Oracle(sample_groups, args.members, route_on_device=True)
+    o.reset_empty()
+    o.step([abi.ev_simple(o.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(sample_groups)])
+    o.flood(args.settle, args.cmds, args.permille, seed=args.seed, threads=cores)
+    c0 = o.counters()
+    t0 = time.perf_counter()
+    o.flood(steps, args.cmds, args.permille, seed=args.seed, threads=cores)
+    dt = time.perf_counter() - t0
+    c1 = o.counters()
+    o.close()
+    return {"value": (c1["commits"] - c0["commits"]) / dt, "unit": "commits/s", "cores": cores, "kind": "port",
+            "sample": "%d groups x %d members, %d steps of the same flood (%.1f s); C restatement of "
+                      "ra_server.erl, not BEAM" % (sample_groups, args.members, steps, dt),
+            "seconds": dt, "ms_per_step": dt * 1e3 / steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    G, M = args.groups, args.members
+    # every step is a bounded sample of the workload: cpu_groups groups instead of G
+    sg = min(G, args.cpu_groups)
+    cb = cpu_baseline(args, sample_groups=sg, steps=args.steps)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "commits/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": "%d groups x %d members per GPU, steady-state AppendEntries flood, %d command(s) per "
+                                  "leader per step, %.1f%% election timeouts per step (BASELINE.json configs[2] shape)"
+                                  % (G, M, args.cmds, args.permille / 10.0),
+                      "sample_groups": sg, "members": M, "cmds_per_step": args.cmds,
+                      "election_permille": args.permille},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "commits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--groups", type=int, default=100_000, help="groups per GPU")
+    ap.add_argument("--members", type=int, default=5)
+    ap.add_argument("--cmds", type=int, default=1)
+    ap.add_argument("--permille", type=int, default=10, help="election timeouts per step per 1000 groups")
+    ap.add_argument("--settle", type=int, default=40, help="untimed steps to elect leaders and fill the pipeline")
+    ap.add_argument("--seed", type=int, default=0xA00)
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--cpu-groups", type=int, default=20_000)
+    ap.add_argument("--cpu-steps", type=int, default=100)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -252,6 +252,7 @@ enum ra_status {
    engine must be serialised (as gen_statem serialises one member's mailbox).          */
 int  ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out);
 void ra_engine_destroy(ra_engine* e);
+int  ra_engine_get_cfg(ra_engine* e, ra_engine_cfg* out);
 
 /* = ra_server:init/1 values (src/ra_server.erl:434-457) + log tail, per row. */
 int  ra_engine_load_rows(ra_engine* e, const ra_row_state* rows, size_t n);
@@ -287,6 +288,27 @@ int  ra_engine_counters(ra_engine* e, ra_counters* out);     /* syncs */
 /* elapsed device time (ms) of the raft_step kernel over the last flood call, CUDA events
    on the engine's stream, and its launch count */
 int  ra_engine_last_kernel_ms(ra_engine* e, float* ms, uint32_t* launches);
+
+/*
+ * The same flood driven from the HOST through ra_engine_step (host buffers, H2D of the
+ * step's events and D2H of its notes inside every step): what an Erlang batching process
+ * in front of many ra_server_procs would do.  The host model (WAL completion, clients,
+ * election timers) is the one ra_engine_flood runs on the device, so both paths leave
+ * identical rows.  The engine must be route_on_device and freshly reset.
+ */
+typedef struct ra_hostsim ra_hostsim;
+int  ra_hostsim_create(ra_engine* e, ra_hostsim** out);
+void ra_hostsim_destroy(ra_hostsim* s);
+/* bootstrap != 0: first send election_timeout to slot 0 of every group (ra:trigger_election) */
+int  ra_hostsim_run(ra_hostsim* s, uint32_t n_steps, uint32_t cmds_per_step,
+                    uint32_t election_permille, uint64_t seed, int bootstrap);
+/* bytes moved over PCIe by the last ra_hostsim_run and its wall time in seconds */
+int  ra_hostsim_stats(ra_hostsim* s, uint64_t* h2d_bytes, uint64_t* d2h_bytes, double* seconds,
+                      uint64_t* engine_calls);
+
+/* pinned host memory for callers that want zero-copy staging of their batches */
+void* ra_engine_alloc_host(size_t bytes);
+void  ra_engine_free_host(void* p);
 
 const char* ra_engine_strerror(int status);
 const char* ra_engine_last_cuda_error(ra_engine* e);

@@ -335,8 +335,9 @@ static void emit_msg(ctx_t *c, u32 to_slot, msg_t *e)
 {
     ra_oracle *o = c->o;
     member_t *m = c->m;
-    if (to_slot >= m->n_members) return;                 /* unknown peer: nothing to send to */
     e->row = row_of(o, group_of(o, m->row), to_slot);
+    if (c->routed_out && !(e->flags & RA_EVF_NEXT_EVENT) && to_slot >= m->n_members)
+        return;                                          /* no mailbox for an unknown peer */
     if (!(e->flags & RA_EVF_NEXT_EVENT)) e->from_slot = m->self_slot;
     e->_pad = 0;
     if (c->routed_out && !(e->flags & RA_EVF_NEXT_EVENT)) {

@@ -550,6 +550,13 @@ extern "C" int ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per
     return RA_OK;
 }
 
+extern "C" int ra_engine_get_cfg(ra_engine* e, ra_engine_cfg* out)
+{
+    if (!e || !out) return RA_E_INVAL;
+    *out = e->cfg;
+    return RA_OK;
+}
+
 extern "C" int ra_engine_sync(ra_engine* e)
 {
     if (!e) return RA_E_INVAL;

@@ -1,0 +1,150 @@
+// host_flood.cu -- a HOST-side caller of the public C ABI (ra_engine_step with host buffers).
+//
+// It plays the part of the Erlang side in the benchmark: per step it hands the engine the
+// events only the host can produce -- {ra_log_event,{written,..}} for every WAL_APPEND note of
+// the previous step (ra_log_wal.erl:784-808), one {commands,_} per leader (the ra_bench-style
+// client flood, src/ra_bench.erl:89-136) and election_timeout when a member heard no leader
+// for a while (ra_server_proc.erl:1927-1946) -- and reads the notes back.  Everything goes
+// through ra_engine_step: H2D of the events, D2H of the notes, every step.
+#include <chrono>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/ra_engine.h"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+static inline u64 mix64(u64 x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+struct ra_hostsim {
+    ra_engine* e;
+    u32 groups, members, rows;
+    std::vector<unsigned char> role, idle;
+    ra_event* ev;  size_t ev_cap;     // pinned
+    ra_event* msgs; size_t msgs_cap;  // pinned
+    ra_note* notes; size_t notes_cap; // pinned
+    size_t n_ev;
+    u64 step;
+    u64 h2d, d2h, calls; double seconds;
+};
+
+extern "C" void* ra_engine_alloc_host(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void ra_engine_free_host(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int ra_hostsim_create(ra_engine* e, ra_hostsim** out)
+{
+    ra_engine_cfg cfg;
+    if (!e || !out || ra_engine_get_cfg(e, &cfg) != RA_OK) return RA_E_INVAL;
+    if (!cfg.route_on_device) return RA_E_INVAL;
+    const u32 groups = cfg.n_groups, members = cfg.n_members;
+    ra_hostsim* s = new ra_hostsim();
+    s->e = e; s->groups = groups; s->members = members; s->rows = groups * members;
+    s->role.assign(s->rows, RA_FOLLOWER); s->idle.assign(s->rows, 0);
+    s->ev_cap = (size_t)s->rows * RA_LOCAL_CAP; s->msgs_cap = 1024; s->notes_cap = (size_t)s->rows * RA_NOTE_CAP;
+    s->ev = (ra_event*)ra_engine_alloc_host(s->ev_cap * sizeof(ra_event));
+    s->msgs = (ra_event*)ra_engine_alloc_host(s->msgs_cap * sizeof(ra_event));
+    s->notes = (ra_note*)ra_engine_alloc_host(s->notes_cap * sizeof(ra_note));
+    if (!s->ev || !s->msgs || !s->notes) { delete s; return RA_E_NOMEM; }
+    s->n_ev = 0; s->step = 0; s->h2d = s->d2h = s->calls = 0; s->seconds = 0;
+    *out = s;
+    return RA_OK;
+}
+
+extern "C" void ra_hostsim_destroy(ra_hostsim* s)
+{
+    if (!s) return;
+    ra_engine_free_host(s->ev); ra_engine_free_host(s->msgs); ra_engine_free_host(s->notes);
+    delete s;
+}
+
+static inline void put(ra_event* e, u32 row, u32 type, u32 n, u64 term, u64 a, u64 b)
+{
+    memset(e, 0, sizeof *e);
+    e->row = row; e->type = (uint8_t)type; e->from_slot = RA_NO_SLOT; e->n = (uint16_t)n;
+    e->term = term; e->a = a; e->b = b;
+}
+
+// notes of one step -> events of the next (the flood host model)
+static void model(ra_hostsim* s, size_t n_notes, u32 cmds, u32 permille, u64 seed, bool run_model)
+{
+    size_t ne = 0, i = 0;
+    for (u32 row = 0; row < s->rows; row++) {
+        const ra_note* w0 = nullptr; const ra_note* w1 = nullptr;
+        u32 status = 0; bool fatal = false;
+        for (; i < n_notes && s->notes[i].row == row; i++) {
+            const ra_note& n = s->notes[i];
+            if (n.type == RA_NOTE_WAL_APPEND) { w0 = w1; w1 = &n; }
+            else if (n.type == RA_NOTE_STATUS) {
+                status = n.aux;
+                s->role[row] = (unsigned char)((n.b >> 24) & 0xff);
+                if (n.aux & RA_ST_FATAL) fatal = true;
+            }
+        }
+        if (!run_model || fatal) continue;
+        if (w0) put(&s->ev[ne++], row, RA_EV_WRITTEN, 0, w0->c, w0->a, w0->b);
+        if (w1) put(&s->ev[ne++], row, RA_EV_WRITTEN, 0, w1->c, w1->a, w1->b);
+        const u32 role = s->role[row];
+        if (role == RA_LEADER && cmds) put(&s->ev[ne++], row, RA_EV_COMMAND, cmds, 0, 0, 0);
+        u32 idle = s->idle[row];
+        if (role == RA_LEADER || (status & RA_ST_LEADER_MSG)) idle = 0;
+        else if (idle < 15) idle++;
+        bool fire = false;
+        if (role != RA_LEADER) {
+            const u32 group = row % s->groups, slot = row / s->groups;
+            u64 h = mix64(seed ^ (s->step * 0x9E3779B97F4A7C15ull) ^ ((u64)group * 0xD1B54A32D192ED03ull));
+            if (permille && (h % 1000) < permille && ((h / 1000) % s->members) == slot) fire = true;
+            u64 h2 = mix64(seed ^ ((u64)row * 0xA24BAED4963EE407ull) ^ s->step);
+            if (idle >= 8 + (u32)(h2 % 8)) fire = true;
+        }
+        if (fire) { put(&s->ev[ne++], row, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0); idle = 0; }
+        s->idle[row] = (unsigned char)idle;
+    }
+    s->n_ev = ne;
+}
+
+extern "C" int ra_hostsim_run(ra_hostsim* s, uint32_t n_steps, uint32_t cmds, uint32_t permille,
+                              uint64_t seed, int bootstrap)
+{
+    if (!s) return RA_E_INVAL;
+    auto t0 = std::chrono::steady_clock::now();
+    s->h2d = s->d2h = s->calls = 0;
+    size_t nm = 0, nn = 0;
+    int rc;
+    if (bootstrap) {
+        for (u32 g = 0; g < s->groups; g++) put(&s->ev[g], g, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0);
+        rc = ra_engine_step(s->e, s->ev, s->groups, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
+        if (rc) return rc;
+        s->h2d += (u64)s->groups * sizeof(ra_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
+        model(s, nn, cmds, permille, seed, false);         // roles only; no model run for this step
+        s->n_ev = 0;
+    }
+    for (u32 t = 0; t < n_steps; t++) {
+        rc = ra_engine_step(s->e, s->ev, s->n_ev, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
+        if (rc) return rc;
+        s->h2d += (u64)s->n_ev * sizeof(ra_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
+        model(s, nn, cmds, permille, seed, true);
+        s->step++;
+    }
+    s->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return RA_OK;
+}
+
+extern "C" int ra_hostsim_stats(ra_hostsim* s, uint64_t* h2d, uint64_t* d2h, double* seconds, uint64_t* calls)
+{
+    if (!s) return RA_E_INVAL;
+    if (h2d) *h2d = s->h2d; if (d2h) *d2h = s->d2h; if (seconds) *seconds = s->seconds; if (calls) *calls = s->calls;
+    return RA_OK;
+}

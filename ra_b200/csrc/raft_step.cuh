@@ -356,9 +356,9 @@ __device__ __forceinline__ void note(Member& m, u32 type, u32 slot, u64 a, u64 b
 __device__ __forceinline__ void emit_msg(Member& m, u32 to, Rec r)
 {
     const Cols& C = *m.C;
-    if (to >= C.members) return;                        // unknown peer: nothing to send to
-    u32 dst = to * C.groups + m.group;
+    u32 dst = to * C.groups + m.group;                  // (an id outside the group is the host's business)
     bool is_next = (R_flags(r) & RA_EVF_NEXT_EVENT) != 0;
+    if (C.routed && !is_next && to >= C.members) return;  // no mailbox for an unknown peer
     if (!is_next) R_set_from(r, m.slot);
     R_clear_pad(r);
     if (C.routed && !is_next) {

@@ -37,13 +37,24 @@ def lib() -> C.CDLL:
         _lib.ra_engine_strerror.argtypes = [C.c_int]
         _lib.ra_engine_last_cuda_error.restype = C.c_char_p
         _lib.ra_engine_last_cuda_error.argtypes = [C.c_void_p]
+        _lib.ra_hostsim_create.restype = C.c_int
+        _lib.ra_hostsim_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        _lib.ra_hostsim_destroy.restype = None
+        _lib.ra_hostsim_destroy.argtypes = [C.c_void_p]
+        _lib.ra_hostsim_run.restype = C.c_int
+        _lib.ra_hostsim_run.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int]
+        _lib.ra_hostsim_stats.restype = C.c_int
+        _lib.ra_hostsim_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                          C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     return _lib
 
 
 EXPORTS = ["ra_engine_create", "ra_engine_destroy", "ra_engine_load_rows", "ra_engine_reset_empty",
            "ra_engine_read_rows", "ra_engine_step", "ra_engine_flood", "ra_engine_sync",
            "ra_engine_counters", "ra_engine_last_kernel_ms", "ra_engine_strerror",
-           "ra_engine_last_cuda_error"]
+           "ra_engine_last_cuda_error", "ra_engine_get_cfg", "ra_engine_alloc_host",
+           "ra_engine_free_host"]
+HOSTSIM_EXPORTS = ["ra_hostsim_create", "ra_hostsim_destroy", "ra_hostsim_run", "ra_hostsim_stats"]
 
 
 class Engine(abi.Backend):
@@ -81,3 +92,33 @@ class Engine(abi.Backend):
         n = C.c_uint32(0)
         self._check(lib().ra_engine_last_kernel_ms(self._h, C.byref(ms), C.byref(n)), "last_kernel_ms")
         return float(ms.value), int(n.value)
+
+
+class HostFlood:
+    """The flood driven from the host through ra_engine_step (host buffers every step)."""
+
+    def __init__(self, engine: Engine):
+        self.e = engine
+        self._h = C.c_void_p()
+        engine._check(lib().ra_hostsim_create(engine._h, C.byref(self._h)), "hostsim_create")
+
+    def run(self, n_steps: int, cmds_per_step: int = 1, election_permille: int = 0, seed: int = 1,
+            bootstrap: bool = False) -> dict:
+        self.e._check(lib().ra_hostsim_run(self._h, n_steps, cmds_per_step, election_permille, seed,
+                                           1 if bootstrap else 0), "hostsim_run")
+        h2d, d2h, calls = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        sec = C.c_double(0)
+        lib().ra_hostsim_stats(self._h, C.byref(h2d), C.byref(d2h), C.byref(sec), C.byref(calls))
+        return dict(h2d_bytes=int(h2d.value), d2h_bytes=int(d2h.value), seconds=float(sec.value),
+                    engine_calls=int(calls.value))
+
+    def close(self) -> None:
+        if self._h:
+            lib().ra_hostsim_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass

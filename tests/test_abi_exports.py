@@ -24,6 +24,11 @@ def test_header_symbols_exported():
         assert hasattr(lib, n), n
     from ra_b200 import engine
     assert sorted(engine.EXPORTS) == names
+    src = open(os.path.join(ROOT, "include", "ra_engine.h")).read()
+    sim = sorted(set(re.findall(r"\b(ra_hostsim_[a-z_]+)\s*\(", src)))
+    assert sim == sorted(engine.HOSTSIM_EXPORTS)
+    for n in sim:
+        assert hasattr(lib, n), n
 
 
 def test_record_sizes_match_header():

@@ -161,3 +161,27 @@ def test_step_input_validation():
     msgs, notes = e.step([])
     assert msgs == [] and notes == []
     assert e.counters()["events"] == 0
+
+
+def test_host_driven_flood_equals_device_flood():
+    """ra_hostsim_run (every step through ra_engine_step with host buffers) leaves exactly the rows
+    ra_engine_flood (device transport + device host model) leaves, and both equal the oracle."""
+    from ra_b200.engine import HostFlood
+    g, m, steps = 2000, 5, 70
+    a = _engine(g, m, route_on_device=True)
+    b = _engine(g, m, route_on_device=True)
+    o = Oracle(g, m, route_on_device=True)
+    _bootstrap(a)
+    a.flood(steps, 1, 10, seed=5)
+    _bootstrap(o)
+    o.flood(steps, 1, 10, seed=5, threads=8)
+    b.reset_empty()
+    hf = HostFlood(b)
+    st = hf.run(steps, 1, 10, seed=5, bootstrap=True)
+    assert st["h2d_bytes"] > 0 and st["d2h_bytes"] > 0 and st["engine_calls"] == steps + 1
+    ca, cb, co = a.counters(), b.counters(), o.counters()
+    assert ca == co
+    for k in ("events", "commits", "applied", "msgs_out", "elections_won"):
+        assert cb[k] == ca[k]
+    ra, rb = _rows_bytes(a, a.n_rows), _rows_bytes(b, b.n_rows)
+    assert rb == ra, "first differing row: %d" % _first_diff(ra, rb)
