@@ -122,13 +122,15 @@ def barrier_sync(world: int, local: int):
     torch.cuda.synchronize(local)
 
 
-def reduce_max_sum(world: int, local: int, ms: float, commits: float, events: float):
+def reduce_max_sum(world: int, local, ms: float, commits: float, events: float):
+    """MAX of the per-rank time, SUM of the per-rank work (local=None: CPU tensors, gloo)."""
     if world == 1:
         return ms, commits, events
     import torch
     import torch.distributed as dist
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % local)
-    s = torch.tensor([commits, events], dtype=torch.float64, device="cuda:%d" % local)
+    dev = "cpu" if local is None else "cuda:%d" % local
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    s = torch.tensor([commits, events], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(s, op=dist.ReduceOp.SUM)
     return float(t.item()), float(s[0].item()), float(s[1].item())
