@@ -378,8 +378,12 @@ __device__ __forceinline__ void emit_msg(Member& m, u32 to, Rec r)
 }
 
 // ---- next-event queue (gen_statem semantics: new next_events go to the front) ----------
-struct NextQ { Rec q[4]; u32 n; };
-__device__ __forceinline__ void nq_push(NextQ& q, const Rec& r) { if (q.n < 4) q.q[q.n++] = r; }
+// A {next_event,_} is never an arbitrary message on this path: it is the event being handled
+// (re-dispatched under the new role) or one of four synthetic ones, so the queue holds 4-bit
+// codes, not 64-byte records, and lives in one register.
+enum { NX_REDISPATCH = 1, NX_PIPELINE = 2, NX_SELF_PRE_VOTE = 3, NX_SELF_VOTE = 4, NX_NOOP = 5, NX_TICK = 6 };
+struct NextQ { u32 codes; u32 n; };
+__device__ __forceinline__ void nq_push(NextQ& q, u32 code) { q.codes |= code << (4 * q.n); q.n++; }
 
 // ---- term / vote --------------------------------------------------------------------
 
@@ -575,23 +579,21 @@ __device__ __forceinline__ void initialise_peers(Member& m)
 // call_for_election/3 :2853-2897
 __device__ __forceinline__ u32 call_for_election(Member& m, u32 target, NextQ& nq)
 {
-    Rec self, req;
+    Rec req;
     if (target == RA_CANDIDATE) {
         u64 nt = m.term + 1;
         req = mk_rec(0, RA_EV_REQUEST_VOTE, 0, 0, 0, 0, 0, nt, m.last_idx, m.last_term, 0, 0, 0);
-        self = mk_rec(m.row, RA_EV_REQUEST_VOTE_RES, m.slot, 0, 0, 0, 0, nt, 0, 0, 0, 1, 0);
         update_term_and_voted_for(m, nt, m.slot);
     } else {
         u64 token = ++m.token_ctr;                                  // make_ref()
         u64 mv = m.macver & 0xffffffffull;
         req = mk_rec(0, RA_EV_PRE_VOTE, 0, 0, 0, 0, 0, m.term, m.last_idx, m.last_term, token, 1ull | (mv << 32), 0);
-        self = mk_rec(m.row, RA_EV_PRE_VOTE_RES, m.slot, 0, 0, 0, 0, m.term, 0, 0, token, 1, 0);
         update_term_and_voted_for(m, m.term, m.slot);
         m.token = token;
     }
     MT_SET(m.meta, 3, 4, SLOT_NONE);       // leader_id => undefined
     MT_SET(m.meta, 15, 4, 0);              // votes => 0
-    nq_push(nq, self);                     // {next_event, cast, VoteForSelf}
+    nq_push(nq, target == RA_CANDIDATE ? NX_SELF_VOTE : NX_SELF_PRE_VOTE);   // {next_event, cast, VoteForSelf}
     for (u32 s = 0; s < m.C->members; s++)
         if (s != m.slot) emit_msg(m, s, req);
     return target;
@@ -643,7 +645,7 @@ __device__ __forceinline__ void remember_cond_reply(Member& m, u32 reason, const
 }
 
 // ---- handle_follower/2 :1264-1641 -----------------------------------------------------------
-__device__ __noinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& nq)
+__device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& nq)
 {
     const u32 type = R_type(e);
     if (type == RA_EV_AER) {
@@ -791,7 +793,7 @@ __device__ __forceinline__ u32 step_down(Member& m, u64 term)
     return RA_FOLLOWER;
 }
 
-__device__ __noinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
+__device__ __forceinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
 {
     const Cols& C = *m.C;
     const u32 type = R_type(e);
@@ -807,7 +809,7 @@ __device__ __noinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
             u64 mm = R_b(e) > nm.y ? R_b(e) : nm.y;
             peer_nm_set(m, from, nn, mm);
             evaluate_quorum(m);
-            nq_push(nq, pipeline_event(m));
+            nq_push(nq, NX_PIPELINE);
             return RA_LEADER;
         }
         if (term > m.term) {                                               // :562-576
@@ -845,15 +847,15 @@ __device__ __noinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
     if (type == RA_EV_WRITTEN) {                                           // :730-735
         log_handle_written(m, R_term(e), R_a(e), R_b(e));
         evaluate_quorum(m);
-        nq_push(nq, pipeline_event(m));
+        nq_push(nq, NX_PIPELINE);
         return RA_LEADER;
     }
     if (type == RA_EV_PIPELINE_RPCS) {                                     // :784-792
-        if (make_pipelined_rpcs(m, false)) nq_push(nq, pipeline_event(m));
+        if (make_pipelined_rpcs(m, false)) nq_push(nq, NX_PIPELINE);
         return RA_LEADER;
     }
     if (type == RA_EV_AER) {
-        if (R_term(e) > m.term) { u32 r = step_down(m, R_term(e)); nq_push(nq, e); return r; }   // :826-835
+        if (R_term(e) > m.term) { u32 r = step_down(m, R_term(e)); nq_push(nq, NX_REDISPATCH); return r; }   // :826-835
         if (R_term(e) == m.term) { set_fatal(m, RA_FATAL_LEADER_SAW_AER_SAME_TERM); return RA_LEADER; } // :836-840
         emit_msg(m, R_from(e), aer_reply(m, m.term, false));               // :841-845
         return RA_LEADER;
@@ -861,7 +863,7 @@ __device__ __noinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
     if (type == RA_EV_REQUEST_VOTE) {
         if (R_term(e) > m.term) {                                          // :919-933
             if (R_from(e) >= C.members) return RA_LEADER;
-            u32 r = step_down(m, R_term(e)); nq_push(nq, e); return r;
+            u32 r = step_down(m, R_term(e)); nq_push(nq, NX_REDISPATCH); return r;
         }
         reply_vote(m, R_from(e), RA_EV_REQUEST_VOTE_RES, m.term, 0, false);     // :934-936
         return RA_LEADER;
@@ -869,7 +871,7 @@ __device__ __noinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
     if (type == RA_EV_PRE_VOTE) {
         if (R_term(e) > m.term) {                                          // :937-951
             if (R_from(e) >= C.members) return RA_LEADER;
-            u32 r = step_down(m, R_term(e)); nq_push(nq, e); return r;
+            u32 r = step_down(m, R_term(e)); nq_push(nq, NX_REDISPATCH); return r;
         }
         make_rpcs(m, true);                                                // :952-957
         return RA_LEADER;
@@ -879,7 +881,7 @@ __device__ __noinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
 }
 
 // ---- handle_candidate/2 :1026-1171 ----------------------------------------------------------
-__device__ __noinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& nq)
+__device__ __forceinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& nq)
 {
     const u32 type = R_type(e);
     if (type == RA_EV_REQUEST_VOTE_RES) {
@@ -889,7 +891,7 @@ __device__ __noinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& nq)
                 MT_SET(m.meta, 3, 4, m.slot);
                 initialise_peers(m);
                 MT_SET(m.meta, 15, 4, 0);
-                nq_push(nq, mk_rec(m.row, RA_EV_COMMAND, RA_NO_SLOT, RA_EVF_NOOP, 1, 0, 0, 0, 0, 0, 0, 0, 0));
+                nq_push(nq, NX_NOOP);
                 m.c_elections++;
                 return RA_LEADER;
             }
@@ -902,7 +904,7 @@ __device__ __noinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& nq)
     if (type == RA_EV_AER) {
         if (R_term(e) >= m.term) {                                         // :1055-1058
             update_term_and_voted_for(m, R_term(e), SLOT_NONE);
-            nq_push(nq, e);
+            nq_push(nq, NX_REDISPATCH);
             return RA_FOLLOWER;
         }
         emit_msg(m, R_from(e), aer_reply(m, m.term, false));               // :1059-1063
@@ -915,7 +917,7 @@ __device__ __noinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& nq)
     if (type == RA_EV_REQUEST_VOTE) {
         if (R_term(e) > m.term) {                                          // :1091-1098
             update_term_and_voted_for(m, R_term(e), SLOT_NONE);
-            nq_push(nq, e);
+            nq_push(nq, NX_REDISPATCH);
             return RA_FOLLOWER;
         }
         reply_vote(m, R_from(e), RA_EV_REQUEST_VOTE_RES, m.term, 0, false);     // :1107-1109
@@ -924,7 +926,7 @@ __device__ __noinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& nq)
     if (type == RA_EV_PRE_VOTE) {
         if (R_term(e) > m.term) {                                          // :1099-1106
             update_term_and_voted_for(m, R_term(e), SLOT_NONE);
-            nq_push(nq, e);
+            nq_push(nq, NX_REDISPATCH);
             return RA_FOLLOWER;
         }
         return process_pre_vote(m, RA_CANDIDATE, e);                       // :1110-1114
@@ -939,14 +941,14 @@ __device__ __noinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& nq)
 }
 
 // ---- handle_pre_vote/2 :1173-1261 -----------------------------------------------------------
-__device__ __noinline__ u32 handle_pre_vote(Member& m, const Rec& e, NextQ& nq)
+__device__ __forceinline__ u32 handle_pre_vote(Member& m, const Rec& e, NextQ& nq)
 {
     const u32 type = R_type(e);
     if (type == RA_EV_AER) {
         if (R_term(e) >= m.term) {                                         // :1175-1180
             update_term(m, R_term(e));
             MT_SET(m.meta, 15, 4, 0);
-            nq_push(nq, e);
+            nq_push(nq, NX_REDISPATCH);
             return RA_FOLLOWER;
         }
         return RA_PRE_VOTE;
@@ -955,7 +957,7 @@ __device__ __noinline__ u32 handle_pre_vote(Member& m, const Rec& e, NextQ& nq)
         if (R_term(e) > m.term) {                                          // :1196-1201
             update_term(m, R_term(e));
             MT_SET(m.meta, 15, 4, 0);
-            nq_push(nq, e);
+            nq_push(nq, NX_REDISPATCH);
             return RA_FOLLOWER;
         }
         return RA_PRE_VOTE;
@@ -984,11 +986,11 @@ __device__ __noinline__ u32 handle_pre_vote(Member& m, const Rec& e, NextQ& nq)
 }
 
 // ---- handle_await_condition/2 :1900-1941 ------------------------------------------------------
-__device__ __noinline__ u32 handle_await_condition(Member& m, const Rec& e, NextQ& nq)
+__device__ __forceinline__ u32 handle_await_condition(Member& m, const Rec& e, NextQ& nq)
 {
     const Cols& C = *m.C;
     const u32 type = R_type(e);
-    if (type == RA_EV_REQUEST_VOTE) { nq_push(nq, e); return RA_FOLLOWER; }           // :1902-1903
+    if (type == RA_EV_REQUEST_VOTE) { nq_push(nq, NX_REDISPATCH); return RA_FOLLOWER; }           // :1902-1903
     if (type == RA_EV_PRE_VOTE) return process_pre_vote(m, RA_AWAIT_CONDITION, e);    // :1904-1905
     if (type == RA_EV_ELECTION_TIMEOUT) {                                             // :1906-1913
         if (MT_MEMBERSHIP(m.meta) != RA_VOTER) return RA_AWAIT_CONDITION;
@@ -1013,7 +1015,7 @@ __device__ __noinline__ u32 handle_await_condition(Member& m, const Rec& e, Next
         }
         if (ok) {
             MT_SET(m.meta, 13, 2, 0); MT_SET(m.meta, 25, 1, 0);
-            nq_push(nq, e);
+            nq_push(nq, NX_REDISPATCH);
             return RA_FOLLOWER;
         }
         return RA_AWAIT_CONDITION;
@@ -1023,25 +1025,38 @@ __device__ __noinline__ u32 handle_await_condition(Member& m, const Rec& e, Next
 }
 
 // ---- the ra_server_proc shim ------------------------------------------------------------------
+__device__ __forceinline__ Rec synth_event(const Member& m, u32 code, const Rec& in)
+{
+    switch (code) {
+    case NX_PIPELINE:      return mk_rec(m.row, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, RA_EVF_INFO, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    case NX_SELF_PRE_VOTE: return mk_rec(m.row, RA_EV_PRE_VOTE_RES, m.slot, 0, 0, 0, 0, m.term, 0, 0, m.token, 1, 0);
+    case NX_SELF_VOTE:     return mk_rec(m.row, RA_EV_REQUEST_VOTE_RES, m.slot, 0, 0, 0, 0, m.term, 0, 0, 0, 1, 0);
+    case NX_NOOP:          return mk_rec(m.row, RA_EV_COMMAND, RA_NO_SLOT, RA_EVF_NOOP, 1, 0, 0, 0, 0, 0, 0, 0, 0);
+    case NX_TICK:          return mk_rec(m.row, RA_EV_TICK, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    default:               return in;
+    }
+}
+
 __device__ __forceinline__ void process_event(Member& m, const Rec& in)
 {
     const Cols& C = *m.C;
-    Rec pend[8]; u32 np = 0;
-    pend[np++] = in;
+    u32 pend = NX_REDISPATCH, np = 1;          // queue of codes, front = low nibble
     bool chased = false;
     m.c_events++;
     while (np > 0) {
         if (MT_FATAL(m.meta)) return;
-        Rec e = pend[0];
-        np--;
-        for (u32 i = 0; i < np; i++) pend[i] = pend[i + 1];
-        if (R_type(e) == RA_EV_PIPELINE_RPCS && (R_flags(e) & RA_EVF_INFO)) {
+        const u32 code = pend & 15u;
+        pend >>= 4; np--;
+        if (code == NX_PIPELINE ||
+            (code == NX_REDISPATCH && R_type(in) == RA_EV_PIPELINE_RPCS && (R_flags(in) & RA_EVF_INFO))) {
             // contract: one chased pipeline pass per input event; the rest runs next step
             if (chased) { MT_SET(m.meta, 24, 1, 1); m.status |= RA_ST_PIPELINE_PENDING; continue; }
             chased = true;
         }
-        NextQ nq; nq.n = 0;
-        u32 old = m_role(m), nr;
+        const Rec e = synth_event(m, code, in);
+        NextQ nq; nq.codes = 0; nq.n = 0;
+        const u32 old = m_role(m);
+        u32 nr;
         switch (old) {
         case RA_LEADER:          nr = handle_leader(m, e, nq); break;
         case RA_FOLLOWER:        nr = handle_follower(m, e, nq); break;
@@ -1059,19 +1074,20 @@ __device__ __forceinline__ void process_event(Member& m, const Rec& in)
             if (nr == RA_LEADER) m.status |= RA_ST_BECAME_LEADER;
         }
         if (C.pure) {
-            for (u32 i = 0; i < nq.n; i++) { Rec r = nq.q[i]; R_or_flags(r, RA_EVF_NEXT_EVENT); emit_msg(m, m.slot, r); }
+            for (u32 i = 0; i < nq.n; i++) {
+                Rec r = synth_event(m, (nq.codes >> (4 * i)) & 15u, e);
+                R_or_flags(r, RA_EVF_NEXT_EVENT);
+                emit_msg(m, m.slot, r);
+            }
             continue;
         }
         // candidate -> leader: tick_timeout goes ahead of the effects' next events
         // (ra_server_proc.erl:728-730)
-        Rec front[5]; u32 nf = 0;
-        if (nr == RA_LEADER && old == RA_CANDIDATE)
-            front[nf++] = mk_rec(m.row, RA_EV_TICK, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-        for (u32 i = 0; i < nq.n; i++) front[nf++] = nq.q[i];
+        u32 front = nq.codes, nf = nq.n;
+        if (nr == RA_LEADER && old == RA_CANDIDATE) { front = (front << 4) | NX_TICK; nf++; }
         if (nf) {
             if (np + nf > 8) nf = 8 - np;
-            for (u32 i = np; i-- > 0;) pend[i + nf] = pend[i];
-            for (u32 i = 0; i < nf; i++) pend[i] = front[i];
+            pend = (pend << (4 * nf)) | (front & ((nf >= 8) ? 0xFFFFFFFFu : ((1u << (4 * nf)) - 1u)));
             np += nf;
         }
     }
