@@ -14,122 +14,234 @@
 
 #include "raft_step.cuh"
 
-#define THREADS 128
 
 // ------------------------------------------------------------------------------------------
 // the hot kernel
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 warp_sum32(u32 v)
-{
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+#define NST 6                               // shared-memory stages: 6 x 8 KB record planes in flight
+#define PLANE_BYTES (TILE * 64)
+
 __device__ __forceinline__ u64 warp_sum64(u64 v)
 {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-__global__ void __launch_bounds__(THREADS)
+// ---- TMA (cp.async.bulk) + mbarrier, sm_90+/sm_100a --------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_fence_init()
+{ asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
+{
+    // bounded: a TMA that never lands must fail the launch loudly, not hang the GPU
+    for (u32 spins = 0; spins < (1u << 24); spins++) {
+        u32 done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+// one bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_plane(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Shared memory of one CTA (128 member rows):
+//   stage[NST][4][128] x 16 B   record planes staged by TMA, chunk-major (conflict-free LDS.128)
+//   bars[NST]                   one mbarrier per stage
+//   peers[3][8][128] x 8 B      per-thread peer columns (next, match, commit_index_sent), lazy
+struct StepSmem {
+    ulonglong2 stage[NST][4 * TILE];
+    u64 peers[3 * 8 * TILE];
+    u64 bars[NST];
+    u32 mask_mbox;              // OR over the CTA's rows: mailbox planes that hold a record
+    u32 mask_loc;               // same for the host-event planes
+    u32 any_work;
+};
+
+__global__ void __launch_bounds__(TILE)
 raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F)
 {
-    const u32 r = blockIdx.x * THREADS + threadIdx.x;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StepSmem& S = *reinterpret_cast<StepSmem*>(smem_raw);
+    const u32 tid = threadIdx.x;
+    const u32 r = blockIdx.x * TILE + tid;
+    const bool valid = r < C.rows;
     u64 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
-    if (r < C.rows) {
-        ulonglong2 ap = C.ap[r];
-        const u32 slot = r / C.groups, group = r - slot * C.groups;
-        const u32 nloc = C.loc_n[r];
-        u32 mail = 0;
-        if (C.routed)
-            for (u32 s = 0; s < C.members; s++) mail |= C.mbox_n[cur][(size_t)s * C.rows + r];
-        const bool fatal0 = MT_FATAL(ap.y) != 0;
-        const bool pending = MT_PIPE_PEND(ap.y) != 0;
-        if (F.on || nloc || mail || pending) {
-            Member m;
-            m.C = &C; m.row = r; m.slot = slot; m.group = group;
-            const ulonglong2 tc = C.tc[r], lg = C.lg[r], lw = C.lw[r], sn = C.sn[r], tk = C.tk[r], fm = C.fm[r];
-            m.term = tc.x; m.commit = tc.y; m.last_idx = lg.x; m.last_term = lg.y;
-            m.lw_idx = lw.x; m.lw_term = lw.y; m.applied = ap.x; m.meta = ap.y;
-            m.snap_idx = sn.x; m.snap_term = sn.y; m.token = tk.x; m.token_ctr = tk.y;
-            m.first_idx = fm.x; m.macver = fm.y;
-            m.n_msgs = 0; m.n_notes = 0; m.status = 0; m.fatal_code = 0; m.role0 = MT_ROLE(ap.y);
-            m.sent_to = 0; m.pn_type = RA_NOTE_NONE; m.pn_slot = 0; m.pn_a = m.pn_b = m.pn_c = 0;
-            m.w_n = 0; m.w0a = m.w0b = m.w0c = m.w1a = m.w1b = m.w1c = 0;
-            m.c_events = m.c_msgs = m.c_dropped = m.c_elections = 0; m.c_commits = m.c_applied = 0;
-            m.nb = cur ^ 1;
-            if (!fatal0) {
-                if (pending) {
-                    MT_SET(m.meta, 24, 1, 0);
-                    process_event(m, mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
-                }
-                if (C.routed) {
-                    for (u32 s = 0; s < C.members; s++) {
-                        u8* cp = &C.mbox_n[cur][(size_t)s * C.rows + r];
-                        const u32 cnt = *cp;
-                        for (u32 k = 0; k < cnt; k++)
-                            process_event(m, ld_rec(&C.mbox[cur][((size_t)s * RA_MBOX_DEPTH + k) * C.rows + r]));
-                        if (cnt) *cp = 0;
-                    }
-                }
-                for (u32 k = 0; k < nloc; k++) process_event(m, ld_rec(&C.loc[(size_t)k * C.rows + r]));
-            }
-            if (nloc) C.loc_n[r] = 0;
-            if (C.routed) {
-                for (u32 s = 0; s < C.members; s++)
-                    if (s != slot)
-                        C.mbox_n[cur ^ 1][(size_t)slot * C.rows + (size_t)s * C.groups + group] = (u8)((m.sent_to >> (4 * s)) & 15u);
-            }
-            // end of the row's step: STATUS note
-            note_flush(m);
-            if (m.status) {
-                u64 ld = MT_LEADER(m.meta), vf = MT_VOTED(m.meta);
-                u64 b = (vf == SLOT_NONE ? 0xFFull : vf) | ((ld == SLOT_NONE ? 0xFFull : ld) << 8) |
-                        ((u64)m.role0 << 16) | ((u64)MT_ROLE(m.meta) << 24);
-                note_store(m, m.n_notes, RA_NOTE_STATUS, slot, m.status, m.term, b, m.fatal_code);
-                m.n_notes++;
-                if (m.status & RA_ST_FATAL) k_fatal = 1;
-            }
-            C.out_n[r] = m.n_msgs | (m.n_notes << 16);
-            // flood: synthetic host (DESIGN.md "flood host model")
-            if (F.on && !MT_FATAL(m.meta)) {
-                u32 k = 0;
-                if (m.w_n == 2) {
-                    st_rec(&C.loc[(size_t)k * C.rows + r], mk_rec(r, RA_EV_WRITTEN, RA_NO_SLOT, 0, 0, 0, 0, m.w0c, m.w0a, m.w0b, 0, 0, 0)); k++;
-                }
-                if (m.w_n >= 1) {
-                    st_rec(&C.loc[(size_t)k * C.rows + r], mk_rec(r, RA_EV_WRITTEN, RA_NO_SLOT, 0, 0, 0, 0, m.w1c, m.w1a, m.w1b, 0, 0, 0)); k++;
-                }
-                const u32 role = MT_ROLE(m.meta);
-                if (role == RA_LEADER && F.cmds) {
-                    st_rec(&C.loc[(size_t)k * C.rows + r], mk_rec(r, RA_EV_COMMAND, RA_NO_SLOT, 0, F.cmds, 0, 0, 0, 0, 0, 0, 0, 0)); k++;
-                }
-                u32 idle = MT_IDLE(m.meta);
-                if (role == RA_LEADER || (m.status & RA_ST_LEADER_MSG)) idle = 0;
-                else if (idle < 15) idle++;
-                bool fire = false;
-                if (role != RA_LEADER) {
-                    u64 h = mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ ((u64)group * 0xD1B54A32D192ED03ull));
-                    if (F.permille && (h % 1000) < F.permille && ((h / 1000) % C.members) == slot) fire = true;
-                    u64 h2 = mix64(F.seed ^ ((u64)r * 0xA24BAED4963EE407ull) ^ F.step);
-                    if (idle >= 8 + (u32)(h2 % 8)) fire = true;
-                }
-                if (fire) {
-                    st_rec(&C.loc[(size_t)k * C.rows + r], mk_rec(r, RA_EV_ELECTION_TIMEOUT, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)); k++;
-                    idle = 0;
-                }
-                MT_SET(m.meta, 28, 4, idle);
-                C.loc_n[r] = k;
-            }
-            // write back what changed
-            if (m.term != tc.x || m.commit != tc.y) st2(&C.tc[r], m.term, m.commit);
-            if (m.last_idx != lg.x || m.last_term != lg.y) st2(&C.lg[r], m.last_idx, m.last_term);
-            if (m.lw_idx != lw.x || m.lw_term != lw.y) st2(&C.lw[r], m.lw_idx, m.lw_term);
-            if (m.applied != ap.x || m.meta != ap.y) st2(&C.ap[r], m.applied, m.meta);
-            if (m.token != tk.x || m.token_ctr != tk.y) st2(&C.tk[r], m.token, m.token_ctr);
-            if (m.first_idx != fm.x) st2(&C.fm[r], m.first_idx, m.macver);
-            k_events = m.c_events; k_commits = m.c_commits; k_applied = m.c_applied;
-            k_msgs = m.c_msgs; k_dropped = m.c_dropped; k_elect = m.c_elections;
+
+    // ---- what does this row have to do? ---------------------------------------------------
+    ulonglong2 ap = make_ulonglong2(0, 0);
+    u64 cntw = 0; u32 nloc = 0;
+    if (valid) {
+        ap = C.ap[r];
+        nloc = C.loc_n[r];
+        if (C.routed) cntw = C.mbox_cnt[cur][r];
+    }
+    const bool fatal0 = MT_FATAL(ap.y) != 0;
+    const bool pending = valid && MT_PIPE_PEND(ap.y) != 0;
+    u32 my_mbox = 0, my_loc = 0;
+    if (valid && !fatal0) {
+        for (u32 s = 0; s < C.members; s++) {
+            u32 c = (u32)(cntw >> (8 * s)) & 0xffu;
+            my_mbox |= ((1u << c) - 1u) << (RA_MBOX_DEPTH * s);
         }
+        my_loc = (1u << nloc) - 1u;
+    }
+    const bool work = valid && (F.on || nloc || cntw || pending);
+    if (tid == 0) {
+        S.mask_mbox = 0; S.mask_loc = 0; S.any_work = 0;
+        for (int i = 0; i < NST; i++) mbar_init(&S.bars[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    {
+        const u32 wm = __reduce_or_sync(0xffffffffu, my_mbox), wl = __reduce_or_sync(0xffffffffu, my_loc);
+        const u32 ww = __reduce_or_sync(0xffffffffu, work ? 1u : 0u);
+        if ((tid & 31) == 0) {
+            if (wm) atomicOr(&S.mask_mbox, wm);
+            if (wl) atomicOr(&S.mask_loc, wl);
+            if (ww) atomicOr(&S.any_work, 1u);
+        }
+    }
+    __syncthreads();
+    if (!S.any_work) return;                                    // whole CTA idle (uniform)
+    u32 cta_mbox = S.mask_mbox, cta_loc = S.mask_loc;
+
+    Member m;
+    m.C = &C; m.row = r; m.slot = valid ? r / C.groups : 0; m.group = valid ? r - m.slot * C.groups : 0;
+    ulonglong2 tc = make_ulonglong2(0, 0), lg = tc, lw = tc, sn = tc, tk = tc, fm = tc;
+    if (work) { tc = C.tc[r]; lg = C.lg[r]; lw = C.lw[r]; sn = C.sn[r]; tk = C.tk[r]; fm = C.fm[r]; }
+    m.term = tc.x; m.commit = tc.y; m.last_idx = lg.x; m.last_term = lg.y;
+    m.lw_idx = lw.x; m.lw_term = lw.y; m.applied = ap.x; m.meta = ap.y;
+    m.snap_idx = sn.x; m.snap_term = sn.y; m.token = tk.x; m.token_ctr = tk.y;
+    m.first_idx = fm.x; m.macver = fm.y;
+    m.n_msgs = 0; m.n_notes = 0; m.status = 0; m.fatal_code = 0; m.role0 = MT_ROLE(ap.y);
+    m.sent_to = 0; m.pn_type = RA_NOTE_NONE; m.pn_slot = 0; m.pn_a = m.pn_b = m.pn_c = 0;
+    m.w_n = 0; m.w0a = m.w0b = m.w0c = m.w1a = m.w1b = m.w1c = 0;
+    m.c_events = m.c_msgs = m.c_dropped = m.c_elections = 0; m.c_commits = m.c_applied = 0;
+    m.nb = cur ^ 1;
+    m.sp = &S.peers[tid]; m.pstate = 0;
+
+    const bool live = work && !fatal0;
+
+    // ---- inputs: TMA stages the CTA's record planes, NST at a time, in evaluation order ----
+    // (deferred pipeline pass, mailbox planes by sender slot then depth, host-event planes)
+    u32 round = 0;
+    bool do_pending = live && pending;
+    if (do_pending) MT_SET(m.meta, 24, 1, 0);
+    const u32 any_pending = __syncthreads_or(do_pending ? 1 : 0);
+    bool first = true;
+    while (first || (cta_mbox | cta_loc)) {
+        // the next up-to-NST planes
+        u32 pl[NST];
+        u32 mm = cta_mbox, ll = cta_loc;
+#pragma unroll
+        for (int i = 0; i < NST; i++) {
+            if (mm) { u32 b = __ffs(mm) - 1; mm &= mm - 1; pl[i] = b; }
+            else if (ll) { u32 b = __ffs(ll) - 1; ll &= ll - 1; pl[i] = 32 + b; }
+            else pl[i] = 0xffffffffu;
+        }
+        cta_mbox = mm; cta_loc = ll;
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < NST; i++) {
+                if (pl[i] == 0xffffffffu) continue;
+                const ulonglong2* src = (pl[i] < 32)
+                    ? C.mbox[cur] + rec_word(C.tiles, pl[i], blockIdx.x * TILE, 0)
+                    : C.loc + rec_word(C.tiles, pl[i] - 32, blockIdx.x * TILE, 0);
+                mbar_expect_tx(&S.bars[i], PLANE_BYTES);
+                tma_load_plane(&S.stage[i][0], src, PLANE_BYTES, &S.bars[i]);
+            }
+        }
+        // one evaluation site: slot -1 is the deferred pipeline pass (first round only)
+#pragma unroll 1
+        for (int i = (first && any_pending) ? -1 : 0; i < NST; i++) {
+            bool mine; u32 p = 0;
+            if (i < 0) mine = do_pending;
+            else {
+                p = pl[0];
+#pragma unroll
+                for (int q = 1; q < NST; q++) if (q == i) p = pl[q];
+                if (p == 0xffffffffu) break;
+                mine = (p < 32) ? ((my_mbox >> p) & 1u) : ((my_loc >> (p - 32)) & 1u);
+            }
+            if (!__any_sync(0xffffffffu, mine)) continue;       // warp has nothing here
+            if (i >= 0) mbar_wait(&S.bars[i], round & 1u);
+            if (mine) {
+                Rec e;
+                if (i < 0) e = mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+                else {
+                    const ulonglong2* st = &S.stage[i][0];
+                    e.w0 = st[tid]; e.w1 = st[TILE + tid]; e.w2 = st[2 * TILE + tid]; e.w3 = st[3 * TILE + tid];
+                }
+                process_event(m, e);
+            }
+        }
+        first = false;
+        round++;
+        __syncthreads();                                        // stages free before they are refilled
+    }
+
+    if (work) {
+        if (cntw && !fatal0) C.mbox_cnt[cur][r] = 0;
+        if (nloc) C.loc_n[r] = 0;
+        if (C.routed) {
+            for (u32 s = 0; s < C.members; s++)
+                if (s != m.slot)
+                    reinterpret_cast<u8*>(&C.mbox_cnt[cur ^ 1][(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
+        }
+        peers_writeback(m);
+        // end of the row's step: STATUS note
+        note_flush(m);
+        if (m.status) {
+            u64 ld = MT_LEADER(m.meta), vf = MT_VOTED(m.meta);
+            u64 b = (vf == SLOT_NONE ? 0xFFull : vf) | ((ld == SLOT_NONE ? 0xFFull : ld) << 8) |
+                    ((u64)m.role0 << 16) | ((u64)MT_ROLE(m.meta) << 24);
+            note_store(m, m.n_notes, RA_NOTE_STATUS, m.slot, m.status, m.term, b, m.fatal_code);
+            m.n_notes++;
+            if (m.status & RA_ST_FATAL) k_fatal = 1;
+        }
+        C.out_n[r] = m.n_msgs | (m.n_notes << 16);
+        // flood: synthetic host (DESIGN.md "flood host model")
+        if (F.on && !MT_FATAL(m.meta)) {
+            u32 k = 0;
+            if (m.w_n == 2) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_WRITTEN, RA_NO_SLOT, 0, 0, 0, 0, m.w0c, m.w0a, m.w0b, 0, 0, 0)); k++; }
+            if (m.w_n >= 1) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_WRITTEN, RA_NO_SLOT, 0, 0, 0, 0, m.w1c, m.w1a, m.w1b, 0, 0, 0)); k++; }
+            const u32 role = MT_ROLE(m.meta);
+            if (role == RA_LEADER && F.cmds) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_COMMAND, RA_NO_SLOT, 0, F.cmds, 0, 0, 0, 0, 0, 0, 0, 0)); k++; }
+            u32 idle = MT_IDLE(m.meta);
+            if (role == RA_LEADER || (m.status & RA_ST_LEADER_MSG)) idle = 0;
+            else if (idle < 15) idle++;
+            bool fire = false;
+            if (role != RA_LEADER) {
+                u64 h = mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ ((u64)m.group * 0xD1B54A32D192ED03ull));
+                if (F.permille && (h % 1000) < F.permille && ((h / 1000) % C.members) == m.slot) fire = true;
+                u64 h2 = mix64(F.seed ^ ((u64)r * 0xA24BAED4963EE407ull) ^ F.step);
+                if (idle >= 8 + (u32)(h2 % 8)) fire = true;
+            }
+            if (fire) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_ELECTION_TIMEOUT, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)); k++; idle = 0; }
+            MT_SET(m.meta, 28, 4, idle);
+            C.loc_n[r] = k;
+        }
+        // write back what changed
+        if (m.term != tc.x || m.commit != tc.y) st2(&C.tc[r], m.term, m.commit);
+        if (m.last_idx != lg.x || m.last_term != lg.y) st2(&C.lg[r], m.last_idx, m.last_term);
+        if (m.lw_idx != lw.x || m.lw_term != lw.y) st2(&C.lw[r], m.lw_idx, m.lw_term);
+        if (m.applied != ap.x || m.meta != ap.y) st2(&C.ap[r], m.applied, m.meta);
+        if (m.token != tk.x || m.token_ctr != tk.y) st2(&C.tk[r], m.token, m.token_ctr);
+        if (m.first_idx != fm.x) st2(&C.fm[r], m.first_idx, m.macver);
+        k_events = m.c_events; k_commits = m.c_commits; k_applied = m.c_applied;
+        k_msgs = m.c_msgs; k_dropped = m.c_dropped; k_elect = m.c_elections;
     }
     // per-launch device counters: warp reduce, one atomic per warp and counter that moved
     const u32 any = __ballot_sync(0xffffffffu, (k_events | k_fatal) != 0);
@@ -137,7 +249,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         k_events = warp_sum64(k_events); k_commits = warp_sum64(k_commits); k_applied = warp_sum64(k_applied);
         k_msgs = warp_sum64(k_msgs); k_dropped = warp_sum64(k_dropped); k_elect = warp_sum64(k_elect);
         k_fatal = warp_sum64(k_fatal);
-        if ((threadIdx.x & 31) == 0) {
+        if ((tid & 31) == 0) {
             if (k_events)  atomicAdd(&C.counters[0], k_events);
             if (k_commits) atomicAdd(&C.counters[1], k_commits);
             if (k_applied) atomicAdd(&C.counters[2], k_applied);
@@ -167,9 +279,7 @@ __global__ void reset_empty_kernel(const Cols C)
     for (u32 s = 0; s < C.members; s++) { st2(&C.pnm[(size_t)s * C.rows + r], 1, 0); C.pcs[(size_t)s * C.rows + r] = 0; }
     for (u32 k = 0; k < RA_MAX_RUNS; k++) st2(&C.run[(size_t)k * C.rows + r], 0, 0);
     C.loc_n[r] = 0; C.out_n[r] = 0;
-    if (C.routed)
-        for (int b = 0; b < 2; b++)
-            for (u32 s = 0; s < C.members; s++) C.mbox_n[b][(size_t)s * C.rows + r] = 0;
+    if (C.routed) { C.mbox_cnt[0][r] = 0; C.mbox_cnt[1][r] = 0; }
 }
 
 __global__ void load_rows_kernel(const Cols C, const ra_row_state* in, u32 n)
@@ -261,7 +371,7 @@ __global__ void ingest_kernel(const Cols C, const ra_event* ev, u32 n, u32* err)
     while (i + len < n && ev[i + len].row == row && len <= RA_LOCAL_CAP) len++;
     if (len > RA_LOCAL_CAP) { atomicMax(err, 2u); return; }
     if (atomicCAS(&C.loc_n[row], 0u, len) != 0u) { atomicMax(err, 1u); return; }
-    for (u32 k = 0; k < len; k++) st_rec(&C.loc[(size_t)k * C.rows + row], ld_rec(&ev[i + k]));
+    for (u32 k = 0; k < len; k++) st_rec_tiled(C.loc, C.tiles, k, row, ld_rec(&ev[i + k]));
 }
 
 __global__ void clear_loc_kernel(const Cols C)
@@ -406,13 +516,15 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
 #define DA(p, n) if ((rc = dalloc(e, &(p), (n))) != RA_OK) goto bad
         DA(C.tc, R); DA(C.lg, R); DA(C.lw, R); DA(C.ap, R); DA(C.sn, R); DA(C.tk, R); DA(C.fm, R);
         DA(C.cd, 2 * R); DA(C.pnm, M * R); DA(C.pcs, M * R); DA(C.run, RA_MAX_RUNS * R);
-        DA(C.loc, (size_t)RA_LOCAL_CAP * R); DA(C.loc_n, R);
+        C.tiles = (u32)((R + TILE - 1) / TILE);
+        const size_t PW = (size_t)C.tiles * 4 * TILE;             // 16-byte words per tiled plane
+        DA(C.loc, (size_t)RA_LOCAL_CAP * PW); DA(C.loc_n, R);
         DA(C.onote, (size_t)RA_NOTE_CAP * R); DA(C.out_n, R); DA(C.counters, 8);
         if (C.routed) {
-            for (int b = 0; b < 2; b++) { DA(C.mbox[b], M * RA_MBOX_DEPTH * R); DA(C.mbox_n[b], M * R); }
+            for (int b = 0; b < 2; b++) { DA(C.mbox[b], M * RA_MBOX_DEPTH * PW); DA(C.mbox_cnt[b], R); }
             DA(C.omsg, (size_t)RA_MSG_CAP * (C.pure ? R : 1));
         } else {
-            C.mbox[0] = C.mbox[1] = nullptr; C.mbox_n[0] = C.mbox_n[1] = nullptr;
+            C.mbox[0] = C.mbox[1] = nullptr; C.mbox_cnt[0] = C.mbox_cnt[1] = nullptr;
             DA(C.omsg, (size_t)RA_MSG_CAP * R);
         }
         DA(e->d_packed, R + 1); DA(e->d_offs, R + 1); DA(e->d_err, 4);
@@ -420,6 +532,9 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         e->scan_tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp_bytes, e->d_packed, e->d_offs, (int)(R + 1), e->stream);
         if ((ce = cudaMalloc(&e->d_scan_tmp, e->scan_tmp_bytes ? e->scan_tmp_bytes : 16)) != cudaSuccess) { rc = fail(e, ce, "cudaMalloc scan"); goto bad; }
+    }
+    if ((ce = cudaFuncSetAttribute(raft_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem))) != cudaSuccess) {
+        rc = fail(e, ce, "cudaFuncSetAttribute"); goto bad;
     }
     if ((rc = ra_engine_reset_empty(e)) != RA_OK) goto bad;
     *out = e;
@@ -474,7 +589,7 @@ extern "C" int ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n)
 
 static int launch_step(ra_engine* e, const FloodArgs& F)
 {
-    raft_step_kernel<<<nblocks(e->C.rows, THREADS), THREADS, 0, e->stream>>>(e->C, e->cur, F);
+    raft_step_kernel<<<e->C.tiles, TILE, sizeof(StepSmem), e->stream>>>(e->C, e->cur, F);
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(e, ce, "raft_step_kernel");
     if (e->C.routed) e->cur ^= 1;

@@ -69,11 +69,15 @@ struct Cols {
     u64*        pcs;    // commit_index_sent
     // log view: [k][rows] {run_start, run_term}
     ulonglong2* run;
-    // transport / io, all [slot-or-k][rows]
-    ra_event* mbox[2];  // [(src*DEPTH + k)][rows]
-    u8*       mbox_n[2];// [src][rows]
-    ra_event* loc;      // [k][rows] host ("local") events
-    u32*      loc_n;    // [rows]
+    // transport / io.  Input record planes (mailboxes, locals) are TILED: plane p holds, for
+    // every tile of 128 consecutive rows, 4 chunk sub-tiles [chunk j][lane] of 16 bytes, i.e.
+    // the 8 KB a CTA needs from a plane are contiguous (one cp.async.bulk) and land in shared
+    // memory chunk-major (lane-consecutive 16-byte words: conflict-free LDS.128).
+    ulonglong2* mbox[2];   // plane (src*DEPTH + k)
+    u64*        mbox_cnt[2]; // [rows] one byte per sender slot
+    ulonglong2* loc;       // plane k: host ("local") events
+    u32*        loc_n;     // [rows]
+    u32 tiles;             // ceil(rows / 128)
     ra_event* omsg;     // [k][rows] outgoing RPC records (non-routed)
     ra_note*  onote;    // [k][rows]
     u32*      out_n;    // [rows] msgs | notes << 16
@@ -82,6 +86,13 @@ struct Cols {
     u32 max_pipeline, max_batch;
     u32 routed, pure;
 };
+
+#define TILE 128
+// address (in 16-byte words) of chunk j of the record of `row` in tiled plane `plane`
+__device__ __forceinline__ size_t rec_word(u32 tiles, u32 plane, u32 row, u32 j)
+{
+    return (((size_t)plane * tiles + (row >> 7)) * 4 + j) * TILE + (row & (TILE - 1));
+}
 
 struct FloodArgs { u32 on; u32 cmds; u32 permille; u32 _p; u64 seed; u64 step; };
 
@@ -108,6 +119,17 @@ __device__ __forceinline__ void st_rec(ra_event* p, const Rec& r)
 {
     ulonglong2* q = reinterpret_cast<ulonglong2*>(p);
     q[0] = r.w0; q[1] = r.w1; q[2] = r.w2; q[3] = r.w3;
+}
+__device__ __forceinline__ void st_rec_tiled(ulonglong2* base, u32 tiles, u32 plane, u32 row, const Rec& r)
+{
+    ulonglong2* q = base + rec_word(tiles, plane, row, 0);
+    q[0] = r.w0; q[TILE] = r.w1; q[2 * TILE] = r.w2; q[3 * TILE] = r.w3;
+}
+__device__ __forceinline__ Rec ld_rec_tiled(const ulonglong2* base, u32 tiles, u32 plane, u32 row)
+{
+    const ulonglong2* q = base + rec_word(tiles, plane, row, 0);
+    Rec r; r.w0 = q[0]; r.w1 = q[TILE]; r.w2 = q[2 * TILE]; r.w3 = q[3 * TILE];
+    return r;
 }
 // header word: row | type<<32 | from<<40 | flags<<48 | pad<<56 ; second: n | n1<<16 | seq<<32
 __device__ __forceinline__ u32 R_row(const Rec& r)   { return (u32)r.w0.x; }
@@ -167,6 +189,10 @@ struct Member {
     u32 c_events, c_msgs, c_dropped, c_elections;
     u64 c_commits, c_applied;
     int nb;                     // mailbox buffer written this step
+    // per-peer columns staged in shared memory on first use: sp[(f*8 + s) * TILE], f = 0 next,
+    // 1 match, 2 commit_index_sent (this thread's column: consecutive lanes, no bank conflicts)
+    u64* sp;
+    u32 pstate;                 // bit0 loaded, bits 8..15 {next,match} dirty, bits 16..23 commit_sent dirty
 };
 
 __device__ __forceinline__ u32 m_role(const Member& m) { return MT_ROLE(m.meta); }
@@ -178,14 +204,34 @@ __device__ __forceinline__ ulonglong2 run_get(const Member& m, u32 k)
 __device__ __forceinline__ void run_set(const Member& m, u32 k, u64 start, u64 term)
 { st2(&m.C->run[(size_t)k * m.C->rows + m.row], start, term); }
 
-__device__ __forceinline__ ulonglong2 peer_nm(const Member& m, u32 s)
-{ return m.C->pnm[(size_t)s * m.C->rows + m.row]; }
-__device__ __forceinline__ void peer_nm_set(const Member& m, u32 s, u64 next, u64 match)
-{ st2(&m.C->pnm[(size_t)s * m.C->rows + m.row], next, match); }
-__device__ __forceinline__ u64 peer_cs(const Member& m, u32 s)
-{ return m.C->pcs[(size_t)s * m.C->rows + m.row]; }
-__device__ __forceinline__ void peer_cs_set(const Member& m, u32 s, u64 v)
-{ m.C->pcs[(size_t)s * m.C->rows + m.row] = v; }
+__device__ __forceinline__ void peers_ensure(Member& m)
+{
+    if (m.pstate & 1u) return;
+    const Cols& C = *m.C;
+    for (u32 s = 0; s < C.members; s++) {
+        ulonglong2 nm = C.pnm[(size_t)s * C.rows + m.row];
+        m.sp[(0 * 8 + s) * TILE] = nm.x; m.sp[(1 * 8 + s) * TILE] = nm.y;
+        m.sp[(2 * 8 + s) * TILE] = C.pcs[(size_t)s * C.rows + m.row];
+    }
+    m.pstate |= 1u;
+}
+__device__ __forceinline__ ulonglong2 peer_nm(Member& m, u32 s)
+{ peers_ensure(m); return make_ulonglong2(m.sp[(0 * 8 + s) * TILE], m.sp[(1 * 8 + s) * TILE]); }
+__device__ __forceinline__ void peer_nm_set(Member& m, u32 s, u64 next, u64 match)
+{ peers_ensure(m); m.sp[(0 * 8 + s) * TILE] = next; m.sp[(1 * 8 + s) * TILE] = match; m.pstate |= 1u << (8 + s); }
+__device__ __forceinline__ u64 peer_cs(Member& m, u32 s)
+{ peers_ensure(m); return m.sp[(2 * 8 + s) * TILE]; }
+__device__ __forceinline__ void peer_cs_set(Member& m, u32 s, u64 v)
+{ peers_ensure(m); m.sp[(2 * 8 + s) * TILE] = v; m.pstate |= 1u << (16 + s); }
+__device__ __forceinline__ void peers_writeback(Member& m)
+{
+    if (!(m.pstate >> 8)) return;
+    const Cols& C = *m.C;
+    for (u32 s = 0; s < C.members; s++) {
+        if (m.pstate & (1u << (8 + s))) st2(&C.pnm[(size_t)s * C.rows + m.row], m.sp[(0 * 8 + s) * TILE], m.sp[(1 * 8 + s) * TILE]);
+        if (m.pstate & (1u << (16 + s))) C.pcs[(size_t)s * C.rows + m.row] = m.sp[(2 * 8 + s) * TILE];
+    }
+}
 
 // ---- log view -----------------------------------------------------------------------
 
@@ -365,7 +411,7 @@ __device__ __forceinline__ void emit_msg(Member& m, u32 to, Rec r)
         u32 k = (m.sent_to >> (4 * to)) & 15u;
         if (k >= RA_MBOX_DEPTH) { m.status |= RA_ST_MSG_DROPPED; m.c_dropped++; return; }
         R_set_row_seq(r, dst, k);
-        st_rec(&C.mbox[m.nb][((size_t)m.slot * RA_MBOX_DEPTH + k) * C.rows + dst], r);
+        st_rec_tiled(C.mbox[m.nb], C.tiles, m.slot * RA_MBOX_DEPTH + k, dst, r);
         m.sent_to += 1u << (4 * to);
         m.c_msgs++;
         return;
@@ -567,6 +613,7 @@ __device__ __forceinline__ void make_rpcs(Member& m, bool all)
 __device__ __forceinline__ void initialise_peers(Member& m)
 {
     u64 next = m.last_idx + 1;
+    m.pstate |= 1u;                         // every peer cell is overwritten: nothing to load
     for (u32 s = 0; s < m.C->members; s++) {
         peer_nm_set(m, s, next, 0);
         peer_cs_set(m, s, 0);
