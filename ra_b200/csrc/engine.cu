@@ -18,7 +18,7 @@
 // ------------------------------------------------------------------------------------------
 // the hot kernel
 // ------------------------------------------------------------------------------------------
-#define NST 6                               // shared-memory stages: 6 x 8 KB record planes in flight
+#define NST 4                               // shared-memory stages: 4 x 8 KB record planes in flight
 #define PLANE_BYTES (TILE * 64)
 
 __device__ __forceinline__ u64 warp_sum64(u64 v)
@@ -69,7 +69,19 @@ struct StepSmem {
     u32 any_work;
 };
 
-__global__ void __launch_bounds__(TILE)
+// the general path, out of line: rare in a flood, and keeping it out of the hot loop keeps the
+// loop small enough for the instruction cache.  The member travels by copy so that the hot
+// loop's copy stays in registers.
+template <int MM>
+__device__ __noinline__ void slow_event(Member* pm, const Rec* pe)
+{
+    Member m = *pm;
+    process_event<MM>(m, *pe);
+    *pm = m;
+}
+
+template <int MM>
+__global__ void __launch_bounds__(TILE, 4)
 raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -91,7 +103,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     const bool pending = valid && MT_PIPE_PEND(ap.y) != 0;
     u32 my_mbox = 0, my_loc = 0;
     if (valid && !fatal0) {
-        for (u32 s = 0; s < C.members; s++) {
+        for (u32 s = 0; s < NMEM(C); s++) {
             u32 c = (u32)(cntw >> (8 * s)) & 0xffu;
             my_mbox |= ((1u << c) - 1u) << (RA_MBOX_DEPTH * s);
         }
@@ -184,7 +196,12 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
                     const ulonglong2* st = &S.stage[i][0];
                     e.w0 = st[tid]; e.w1 = st[TILE + tid]; e.w2 = st[2 * TILE + tid]; e.w3 = st[3 * TILE + tid];
                 }
-                process_event(m, e);
+                if (MT_FATAL(m.meta)) m.c_events++;
+                else if (!fast_event<MM>(m, e)) {
+                    Member tmp = m; Rec te = e;
+                    slow_event<MM>(&tmp, &te);
+                    m = tmp;
+                }
             }
         }
         first = false;
@@ -196,11 +213,11 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         if (cntw && !fatal0) C.mbox_cnt[cur][r] = 0;
         if (nloc) C.loc_n[r] = 0;
         if (C.routed) {
-            for (u32 s = 0; s < C.members; s++)
+            for (u32 s = 0; s < NMEM(C); s++)
                 if (s != m.slot)
                     reinterpret_cast<u8*>(&C.mbox_cnt[cur ^ 1][(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
         }
-        peers_writeback(m);
+        peers_writeback<MM>(m);
         // end of the row's step: STATUS note
         note_flush(m);
         if (m.status) {
@@ -225,7 +242,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             bool fire = false;
             if (role != RA_LEADER) {
                 u64 h = mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ ((u64)m.group * 0xD1B54A32D192ED03ull));
-                if (F.permille && (h % 1000) < F.permille && ((h / 1000) % C.members) == m.slot) fire = true;
+                if (F.permille && (h % 1000) < F.permille && ((h / 1000) % NMEM(C)) == m.slot) fire = true;
                 u64 h2 = mix64(F.seed ^ ((u64)r * 0xA24BAED4963EE407ull) ^ F.step);
                 if (idle >= 8 + (u32)(h2 % 8)) fire = true;
             }
@@ -533,7 +550,8 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp_bytes, e->d_packed, e->d_offs, (int)(R + 1), e->stream);
         if ((ce = cudaMalloc(&e->d_scan_tmp, e->scan_tmp_bytes ? e->scan_tmp_bytes : 16)) != cudaSuccess) { rc = fail(e, ce, "cudaMalloc scan"); goto bad; }
     }
-    if ((ce = cudaFuncSetAttribute(raft_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem))) != cudaSuccess) {
+    if ((ce = cudaFuncSetAttribute(raft_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem))) != cudaSuccess ||
+        (ce = cudaFuncSetAttribute(raft_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem))) != cudaSuccess) {
         rc = fail(e, ce, "cudaFuncSetAttribute"); goto bad;
     }
     if ((rc = ra_engine_reset_empty(e)) != RA_OK) goto bad;
@@ -589,7 +607,10 @@ extern "C" int ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n)
 
 static int launch_step(ra_engine* e, const FloodArgs& F)
 {
-    raft_step_kernel<<<e->C.tiles, TILE, sizeof(StepSmem), e->stream>>>(e->C, e->cur, F);
+    switch (e->C.members) {
+    case 5:  raft_step_kernel<5><<<e->C.tiles, TILE, sizeof(StepSmem), e->stream>>>(e->C, e->cur, F); break;
+    default: raft_step_kernel<0><<<e->C.tiles, TILE, sizeof(StepSmem), e->stream>>>(e->C, e->cur, F); break;
+    }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(e, ce, "raft_step_kernel");
     if (e->C.routed) e->cur ^= 1;

@@ -53,6 +53,8 @@ typedef unsigned char u8;
 #define MT_VOTER(m, s)    ((u32)(((m) >> (56 + (s))) & 1ull))
 #define MT_SET(m, sh, w, v) ((m) = ((m) & ~((((u64)1 << (w)) - 1) << (sh))) | (((u64)(v) & (((u64)1 << (w)) - 1)) << (sh)))
 #define SLOT_NONE 15u
+// number of members: compile-time when the kernel is specialised (MM != 0), else from the config
+#define NMEM(C) ((u32)(MM ? MM : (C).members))
 
 struct Cols {
     // scalar pairs, one cell per row
@@ -204,30 +206,36 @@ __device__ __forceinline__ ulonglong2 run_get(const Member& m, u32 k)
 __device__ __forceinline__ void run_set(const Member& m, u32 k, u64 start, u64 term)
 { st2(&m.C->run[(size_t)k * m.C->rows + m.row], start, term); }
 
+template <int MM>
 __device__ __forceinline__ void peers_ensure(Member& m)
 {
     if (m.pstate & 1u) return;
     const Cols& C = *m.C;
-    for (u32 s = 0; s < C.members; s++) {
+    for (u32 s = 0; s < NMEM(C); s++) {
         ulonglong2 nm = C.pnm[(size_t)s * C.rows + m.row];
         m.sp[(0 * 8 + s) * TILE] = nm.x; m.sp[(1 * 8 + s) * TILE] = nm.y;
         m.sp[(2 * 8 + s) * TILE] = C.pcs[(size_t)s * C.rows + m.row];
     }
     m.pstate |= 1u;
 }
+template <int MM>
 __device__ __forceinline__ ulonglong2 peer_nm(Member& m, u32 s)
-{ peers_ensure(m); return make_ulonglong2(m.sp[(0 * 8 + s) * TILE], m.sp[(1 * 8 + s) * TILE]); }
+{ peers_ensure<MM>(m); return make_ulonglong2(m.sp[(0 * 8 + s) * TILE], m.sp[(1 * 8 + s) * TILE]); }
+template <int MM>
 __device__ __forceinline__ void peer_nm_set(Member& m, u32 s, u64 next, u64 match)
-{ peers_ensure(m); m.sp[(0 * 8 + s) * TILE] = next; m.sp[(1 * 8 + s) * TILE] = match; m.pstate |= 1u << (8 + s); }
+{ peers_ensure<MM>(m); m.sp[(0 * 8 + s) * TILE] = next; m.sp[(1 * 8 + s) * TILE] = match; m.pstate |= 1u << (8 + s); }
+template <int MM>
 __device__ __forceinline__ u64 peer_cs(Member& m, u32 s)
-{ peers_ensure(m); return m.sp[(2 * 8 + s) * TILE]; }
+{ peers_ensure<MM>(m); return m.sp[(2 * 8 + s) * TILE]; }
+template <int MM>
 __device__ __forceinline__ void peer_cs_set(Member& m, u32 s, u64 v)
-{ peers_ensure(m); m.sp[(2 * 8 + s) * TILE] = v; m.pstate |= 1u << (16 + s); }
+{ peers_ensure<MM>(m); m.sp[(2 * 8 + s) * TILE] = v; m.pstate |= 1u << (16 + s); }
+template <int MM>
 __device__ __forceinline__ void peers_writeback(Member& m)
 {
     if (!(m.pstate >> 8)) return;
     const Cols& C = *m.C;
-    for (u32 s = 0; s < C.members; s++) {
+    for (u32 s = 0; s < NMEM(C); s++) {
         if (m.pstate & (1u << (8 + s))) st2(&C.pnm[(size_t)s * C.rows + m.row], m.sp[(0 * 8 + s) * TILE], m.sp[(1 * 8 + s) * TILE]);
         if (m.pstate & (1u << (16 + s))) C.pcs[(size_t)s * C.rows + m.row] = m.sp[(2 * 8 + s) * TILE];
     }
@@ -399,12 +407,13 @@ __device__ __forceinline__ void note(Member& m, u32 type, u32 slot, u64 a, u64 b
 }
 
 // send one RPC record to the member in `to` of my group
+template <int MM>
 __device__ __forceinline__ void emit_msg(Member& m, u32 to, Rec r)
 {
     const Cols& C = *m.C;
     u32 dst = to * C.groups + m.group;                  // (an id outside the group is the host's business)
     bool is_next = (R_flags(r) & RA_EVF_NEXT_EVENT) != 0;
-    if (C.routed && !is_next && to >= C.members) return;  // no mailbox for an unknown peer
+    if (C.routed && !is_next && to >= NMEM(C)) return;  // no mailbox for an unknown peer
     if (!is_next) R_set_from(r, m.slot);
     R_clear_pad(r);
     if (C.routed && !is_next) {
@@ -452,9 +461,10 @@ __device__ __forceinline__ bool log_up_to_date(u64 idx, u64 term, u64 last_idx, 
     return term > last_term || (term == last_term && idx >= last_idx);
 }
 // required_quorum/1 :3969-3972
+template <int MM>
 __device__ __forceinline__ u32 required_quorum(const Member& m)
 {
-    u32 mask = (u32)(m.meta >> 56) & ((1u << m.C->members) - 1u);
+    u32 mask = (u32)(m.meta >> 56) & ((1u << NMEM(*m.C)) - 1u);
     return (u32)__popc(mask) / 2 + 1;
 }
 
@@ -463,9 +473,10 @@ __device__ __forceinline__ Rec aer_reply(const Member& m, u64 term, bool success
 {
     return mk_rec(0, RA_EV_AER_REPLY, 0, 0, 0, 0, 0, term, m.last_idx + 1, m.lw_idx, m.lw_term, success ? 1 : 0, 0);
 }
+template <int MM>
 __device__ __forceinline__ void reply_vote(Member& m, u32 to, u32 type, u64 term, u64 token, bool granted)
 {
-    emit_msg(m, to, mk_rec(0, type, 0, 0, 0, 0, 0, term, 0, 0, token, granted ? 1 : 0, 0));
+    emit_msg<MM>(m, to, mk_rec(0, type, 0, 0, 0, 0, 0, term, 0, 0, token, granted ? 1 : 0, 0));
 }
 
 // ---- apply / quorum -----------------------------------------------------------------
@@ -485,25 +496,42 @@ __device__ __forceinline__ void apply_to(Member& m, u64 upto)
 
 // evaluate_quorum/2 :3606-3619 with match_indexes/1 :3644-3655 and agreed_commit/1
 // :3657-3661.  The reference sorts [LastWritten | voter match indexes] descending and takes
-// element trunc(N/2)+1; the same element is the smallest value v of the list with
-// #{x >= v} >= trunc(N/2)+1 ... found by rank counting over <= 8 values, no sort.
+// element trunc(N/2)+1.  Here one value per member slot sits in a register (the leader's own
+// slot holds its last_written index, a non-voter contributes 0, which can never be ranked
+// above a real candidate), an odd-even transposition network orders them, and the element is
+// picked by rank: no array in local memory, no data-dependent loop.
+__device__ __forceinline__ void cex(u64& a, u64& b)          // a >= b afterwards
+{
+    const bool sw = a < b;
+    const u64 t = sw ? b : a;
+    b = sw ? a : b;
+    a = t;
+}
+template <int MM>
 __device__ __forceinline__ void evaluate_quorum(Member& m)
 {
-    const u32 M = m.C->members;
-    u64 v[RA_MAX_MEMBERS + 1];
-    u32 n = 0;
-    v[n++] = m.lw_idx;
+    const u32 M = NMEM(*m.C);
+    constexpr int NV = MM ? MM : RA_MAX_MEMBERS;
+    peers_ensure<MM>(m);
+    u64 v[NV];
+    u32 n = 1;
 #pragma unroll
-    for (u32 s = 0; s < RA_MAX_MEMBERS; s++) {
-        if (s < M && s != m.slot && MT_VOTER(m.meta, s)) v[n++] = peer_nm(m, s).y;
+    for (int s = 0; s < NV; s++) {
+        const bool in = (u32)s < M;
+        const bool self = (u32)s == m.slot;
+        const bool voter = in && !self && MT_VOTER(m.meta, s);
+        v[s] = self ? m.lw_idx : (voter ? m.sp[(1 * 8 + s) * TILE] : 0ull);
+        n += voter ? 1u : 0u;
     }
-    u32 nth = n / 2 + 1;
-    u64 best = 0; bool found = false;
-    for (u32 i = 0; i < n; i++) {
-        u32 ge = 0;
-        for (u32 j = 0; j < n; j++) ge += (v[j] >= v[i]) ? 1u : 0u;
-        if (ge >= nth && (!found || v[i] > best)) { best = v[i]; found = true; }
+#pragma unroll
+    for (int pass = 0; pass < NV; pass++) {
+#pragma unroll
+        for (int i = pass & 1; i + 1 < NV; i += 2) cex(v[i], v[i + 1]);
     }
+    const u32 nth = n / 2 + 1;                                  // 1-based rank, descending
+    u64 best = v[0];
+#pragma unroll
+    for (int i = 1; i < NV; i++) best = (nth == (u32)(i + 1)) ? v[i] : best;
     u64 ci0 = m.commit;
     if (srv_fetch_term(m, (i64)best) == m.term) m.commit = best;        // §5.4.2 gate :3625-3629
     if (m.commit > ci0) {
@@ -523,6 +551,7 @@ __device__ __forceinline__ void evaluate_commit_index_follower(Member& m)
 // ---- leader RPC generation --------------------------------------------------------------
 
 // make_append_entries_rpc/6 :2401-2418 -> new next index
+template <int MM>
 __device__ __forceinline__ u64 make_aer(Member& m, u32 peer, i64 prev_idx, u64 prev_term, u64 num)
 {
     u64 last = m.last_idx;
@@ -543,19 +572,20 @@ __device__ __forceinline__ u64 make_aer(Member& m, u32 peer, i64 prev_idx, u64 p
     } else {
         to = from - 1; if (last < to) to = last;
     }
-    emit_msg(m, peer, mk_rec(0, RA_EV_AER, 0, 0, n, n1, 0, m.term, (u64)prev_idx, prev_term, m.commit, d, e));
+    emit_msg<MM>(m, peer, mk_rec(0, RA_EV_AER, 0, 0, n, n1, 0, m.term, (u64)prev_idx, prev_term, m.commit, d, e));
     return to + 1;
 }
 
 // make_rpc_effect/5 :2365-2399
+template <int MM>
 __device__ __forceinline__ u64 make_rpc_effect(Member& m, u32 peer, u64 next, u64 max_batch, bool& snapshot)
 {
     i64 prev = (i64)next - 1;
     snapshot = false;
     u64 pt = log_fetch_term(m, prev);
-    if (pt != RA_UNDEF) return make_aer(m, peer, prev, pt, max_batch);
+    if (pt != RA_UNDEF) return make_aer<MM>(m, peer, prev, pt, max_batch);
     if (!MT_HAS_SNAP(m.meta)) { set_fatal(m, RA_FATAL_NO_SNAPSHOT); return next; }
-    if (prev >= 0 && m.snap_idx == (u64)prev) return make_aer(m, peer, prev, m.snap_term, max_batch);
+    if (prev >= 0 && m.snap_idx == (u64)prev) return make_aer<MM>(m, peer, prev, m.snap_term, max_batch);
     if (!(prev < (i64)m.snap_idx)) { set_fatal(m, RA_FATAL_ASSERT); return next; }
     snapshot = true;
     note(m, RA_NOTE_SEND_SNAPSHOT, peer, peer, m.snap_idx, 0);
@@ -563,27 +593,28 @@ __device__ __forceinline__ u64 make_rpc_effect(Member& m, u32 peer, u64 next, u6
 }
 
 // make_pipelined_rpc_effects/3 :2268-2329 -> More
+template <int MM>
 __device__ __forceinline__ bool make_pipelined_rpcs(Member& m, bool force)
 {
     const Cols& C = *m.C;
     u64 next_log_idx = m.last_idx + 1;
     i64 max_pipe = C.max_pipeline, max_batch = C.max_batch;
     bool more = false;
-    for (u32 s = 0; s < C.members; s++) {
+    for (u32 s = 0; s < NMEM(C); s++) {
         if (s == m.slot) continue;
         if (MT_PSTATUS(m.meta, s) != RA_PEER_NORMAL) continue;
-        ulonglong2 nm = peer_nm(m, s);
-        u64 cs = peer_cs(m, s);
+        ulonglong2 nm = peer_nm<MM>(m, s);
+        u64 cs = peer_cs<MM>(m, s);
         if (!(nm.x < next_log_idx || cs < m.commit)) continue;
         i64 in_flight = (i64)nm.x - (i64)nm.y - 1;
         if (!(in_flight < max_pipe || force)) continue;
         i64 bs = max_pipe - in_flight; if (max_batch < bs) bs = max_batch; if (bs < 1) bs = 1;
         bool snap;
-        u64 nn = make_rpc_effect(m, s, nm.x, (u64)bs, snap);
+        u64 nn = make_rpc_effect<MM>(m, s, nm.x, (u64)bs, snap);
         if (MT_FATAL(m.meta)) return false;
         if (!(nn >= nm.x)) { set_fatal(m, RA_FATAL_ASSERT); return false; }
-        peer_nm_set(m, s, nn, nm.y);
-        peer_cs_set(m, s, m.commit);
+        peer_nm_set<MM>(m, s, nn, nm.y);
+        peer_cs_set<MM>(m, s, m.commit);
         if (snap && !C.pure) MT_SET(m.meta, 32 + 3 * s, 3, RA_PEER_SENDING_SNAPSHOT);
         i64 nif = (i64)nn - (i64)nm.y - 1;
         if (nn < next_log_idx && nif < max_pipe) more = true;
@@ -592,31 +623,33 @@ __device__ __forceinline__ bool make_pipelined_rpcs(Member& m, bool force)
 }
 
 // make_rpcs_for/2 over stale_peers/1 (:2985-3003) or all normal peers (make_all_rpcs/1)
+template <int MM>
 __device__ __forceinline__ void make_rpcs(Member& m, bool all)
 {
     const Cols& C = *m.C;
-    for (u32 s = 0; s < C.members; s++) {
+    for (u32 s = 0; s < NMEM(C); s++) {
         if (s == m.slot) continue;
         if (MT_PSTATUS(m.meta, s) != RA_PEER_NORMAL) continue;
-        ulonglong2 nm = peer_nm(m, s);
+        ulonglong2 nm = peer_nm<MM>(m, s);
         if (!all) {
-            bool stale = ((i64)nm.y < (i64)nm.x - 1) || (peer_cs(m, s) < m.commit);
+            bool stale = ((i64)nm.y < (i64)nm.x - 1) || (peer_cs<MM>(m, s) < m.commit);
             if (!stale) continue;
         }
         bool snap;
-        (void)make_rpc_effect(m, s, nm.x, 1, snap);
+        (void)make_rpc_effect<MM>(m, s, nm.x, 1, snap);
         if (MT_FATAL(m.meta)) return;
     }
 }
 
 // initialise_peers/1 :3207-3215
+template <int MM>
 __device__ __forceinline__ void initialise_peers(Member& m)
 {
     u64 next = m.last_idx + 1;
     m.pstate |= 1u;                         // every peer cell is overwritten: nothing to load
-    for (u32 s = 0; s < m.C->members; s++) {
-        peer_nm_set(m, s, next, 0);
-        peer_cs_set(m, s, 0);
+    for (u32 s = 0; s < NMEM(*m.C); s++) {
+        peer_nm_set<MM>(m, s, next, 0);
+        peer_cs_set<MM>(m, s, 0);
         MT_SET(m.meta, 32 + 3 * s, 3, RA_PEER_NORMAL);
     }
 }
@@ -624,6 +657,7 @@ __device__ __forceinline__ void initialise_peers(Member& m)
 // ---- elections --------------------------------------------------------------------------
 
 // call_for_election/3 :2853-2897
+template <int MM>
 __device__ __forceinline__ u32 call_for_election(Member& m, u32 target, NextQ& nq)
 {
     Rec req;
@@ -641,12 +675,13 @@ __device__ __forceinline__ u32 call_for_election(Member& m, u32 target, NextQ& n
     MT_SET(m.meta, 3, 4, SLOT_NONE);       // leader_id => undefined
     MT_SET(m.meta, 15, 4, 0);              // votes => 0
     nq_push(nq, target == RA_CANDIDATE ? NX_SELF_VOTE : NX_SELF_PRE_VOTE);   // {next_event, cast, VoteForSelf}
-    for (u32 s = 0; s < m.C->members; s++)
-        if (s != m.slot) emit_msg(m, s, req);
+    for (u32 s = 0; s < NMEM(*m.C); s++)
+        if (s != m.slot) emit_msg<MM>(m, s, req);
     return target;
 }
 
 // process_pre_vote/3 :2899-2956
+template <int MM>
 __device__ __forceinline__ u32 process_pre_vote(Member& m, u32 fsm, const Rec& e)
 {
     u64 term = R_term(e), token = R_c(e);
@@ -656,17 +691,17 @@ __device__ __forceinline__ u32 process_pre_vote(Member& m, u32 fsm, const Rec& e
     if (term >= m.term) {
         update_term(m, term);
         if (log_up_to_date(R_a(e), R_b(e), m.last_idx, m.last_term)) {
-            if (version > 1) reply_vote(m, cand, RA_EV_PRE_VOTE_RES, term, token, false);
+            if (version > 1) reply_vote<MM>(m, cand, RA_EV_PRE_VOTE_RES, term, token, false);
             else if (their == eff || (their >= eff && their <= macver))
-                reply_vote(m, cand, RA_EV_PRE_VOTE_RES, term, token, true);
-            else { reply_vote(m, cand, RA_EV_PRE_VOTE_RES, term, token, false); m.status |= RA_ST_START_ELECTION_TMO; }
+                reply_vote<MM>(m, cand, RA_EV_PRE_VOTE_RES, term, token, true);
+            else { reply_vote<MM>(m, cand, RA_EV_PRE_VOTE_RES, term, token, false); m.status |= RA_ST_START_ELECTION_TMO; }
         } else if (fsm == RA_FOLLOWER) {
             m.status |= RA_ST_START_ELECTION_TMO;
         } else {
-            reply_vote(m, cand, RA_EV_PRE_VOTE_RES, term, token, false);
+            reply_vote<MM>(m, cand, RA_EV_PRE_VOTE_RES, term, token, false);
         }
     } else {
-        reply_vote(m, cand, RA_EV_PRE_VOTE_RES, m.term, token, false);
+        reply_vote<MM>(m, cand, RA_EV_PRE_VOTE_RES, m.term, token, false);
     }
     return fsm;
 }
@@ -692,6 +727,7 @@ __device__ __forceinline__ void remember_cond_reply(Member& m, u32 reason, const
 }
 
 // ---- handle_follower/2 :1264-1641 -----------------------------------------------------------
+template <int MM>
 __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& nq)
 {
     const u32 type = R_type(e);
@@ -732,10 +768,10 @@ __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& n
                     if (validated) {                                       // :1313-1326
                         m.commit = leader_commit;
                         evaluate_commit_index_follower(m);
-                        emit_msg(m, leader, aer_reply(m, term, true));
+                        emit_msg<MM>(m, leader, aer_reply(m, term, true));
                     } else {                                               // :1327-1346
                         u64 lvi = m.applied > last_valid ? m.applied : last_valid;
-                        emit_msg(m, leader, mk_rec(0, RA_EV_AER_REPLY, 0, 0, 0, 0, 0, cur, lvi + 1, lvi,
+                        emit_msg<MM>(m, leader, mk_rec(0, RA_EV_AER_REPLY, 0, 0, 0, 0, 0, cur, lvi + 1, lvi,
                                                    srv_fetch_term(m, (i64)lvi), 1, 0));
                     }
                     return RA_FOLLOWER;
@@ -772,7 +808,7 @@ __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& n
             if (r == 1) {                                                  // missing :1373-1387
                 Rec rp = aer_reply(m, term, false);
                 remember_cond_reply(m, 1, rp);
-                emit_msg(m, leader, rp);
+                emit_msg<MM>(m, leader, rp);
                 return RA_AWAIT_CONDITION;
             }
             // term_mismatch :1388-1413 -> mismatch_append_entries_reply/3 :3587-3595
@@ -780,10 +816,10 @@ __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& n
             if (lat == RA_UNDEF) { set_fatal(m, RA_FATAL_ASSERT); return RA_FOLLOWER; }
             Rec rp = mk_rec(0, RA_EV_AER_REPLY, 0, 0, 0, 0, 0, term, la + 1, la, lat, 0, 0);
             remember_cond_reply(m, 2, rp);
-            emit_msg(m, leader, rp);
+            emit_msg<MM>(m, leader, rp);
             return RA_AWAIT_CONDITION;
         }
-        emit_msg(m, leader, aer_reply(m, cur, false));                     // :1415-1424
+        emit_msg<MM>(m, leader, aer_reply(m, cur, false));                     // :1415-1424
         return RA_FOLLOWER;
     }
     if (type == RA_EV_WRITTEN) {                                           // :1441-1458
@@ -791,26 +827,26 @@ __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& n
         log_handle_written(m, R_term(e), R_a(e), R_b(e));
         u32 leader = MT_LEADER(m.meta);
         if ((a != m.lw_idx || b != m.lw_term) && leader != SLOT_NONE)
-            emit_msg(m, leader, aer_reply(m, m.term, true));
+            emit_msg<MM>(m, leader, aer_reply(m, m.term, true));
         return RA_FOLLOWER;
     }
     if (type == RA_EV_PRE_VOTE) {                                          // :1459-1466
         if (MT_MEMBERSHIP(m.meta) != RA_VOTER) return RA_FOLLOWER;
-        return process_pre_vote(m, RA_FOLLOWER, e);
+        return process_pre_vote<MM>(m, RA_FOLLOWER, e);
     }
     if (type == RA_EV_REQUEST_VOTE) {                                      // :1467-1513
         if (MT_MEMBERSHIP(m.meta) != RA_VOTER) return RA_FOLLOWER;
         u64 term = R_term(e), cur = m.term;
         u32 cand = R_from(e), voted = MT_VOTED(m.meta);
         if (term == cur && voted != SLOT_NONE && voted != (cand & 15u)) {
-            reply_vote(m, cand, RA_EV_REQUEST_VOTE_RES, term, 0, false);
+            reply_vote<MM>(m, cand, RA_EV_REQUEST_VOTE_RES, term, 0, false);
         } else if (term >= cur) {
             update_term(m, term);
             if (log_up_to_date(R_a(e), R_b(e), m.last_idx, m.last_term)) {
-                reply_vote(m, cand, RA_EV_REQUEST_VOTE_RES, term, 0, true);
+                reply_vote<MM>(m, cand, RA_EV_REQUEST_VOTE_RES, term, 0, true);
                 update_term_and_voted_for(m, term, cand & 15u);
-            } else reply_vote(m, cand, RA_EV_REQUEST_VOTE_RES, term, 0, false);
-        } else reply_vote(m, cand, RA_EV_REQUEST_VOTE_RES, cur, 0, false);
+            } else reply_vote<MM>(m, cand, RA_EV_REQUEST_VOTE_RES, term, 0, false);
+        } else reply_vote<MM>(m, cand, RA_EV_REQUEST_VOTE_RES, cur, 0, false);
         return RA_FOLLOWER;
     }
     if (type == RA_EV_AER_REPLY) {                                         // :1514-1517
@@ -819,7 +855,7 @@ __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& n
     }
     if (type == RA_EV_ELECTION_TIMEOUT) {                                  // :1603-1610
         if (MT_MEMBERSHIP(m.meta) != RA_VOTER) return RA_FOLLOWER;
-        return call_for_election(m, RA_PRE_VOTE, nq);
+        return call_for_election<MM>(m, RA_PRE_VOTE, nq);
     }
     if (type == RA_EV_COMMAND) {
         u32 l = MT_LEADER(m.meta);
@@ -833,6 +869,7 @@ __device__ __forceinline__ Rec pipeline_event(const Member& m)
 {
     return mk_rec(m.row, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, RA_EVF_INFO, 0, 0, 0, 0, 0, 0, 0, 0, 0);
 }
+template <int MM>
 __device__ __forceinline__ u32 step_down(Member& m, u64 term)
 {
     MT_SET(m.meta, 3, 4, SLOT_NONE);
@@ -840,6 +877,7 @@ __device__ __forceinline__ u32 step_down(Member& m, u64 term)
     return RA_FOLLOWER;
 }
 
+template <int MM>
 __device__ __forceinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
 {
     const Cols& C = *m.C;
@@ -848,24 +886,24 @@ __device__ __forceinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
         u64 term = R_term(e);
         u32 from = R_from(e);
         bool success = R_d(e) != 0;
-        bool known = from < C.members;
+        bool known = from < NMEM(C);
         if (success && term == m.term) {                                   // :522-561
             if (!known) return RA_LEADER;
-            ulonglong2 nm = peer_nm(m, from);
+            ulonglong2 nm = peer_nm<MM>(m, from);
             u64 nn = R_a(e) > nm.x ? R_a(e) : nm.x;
             u64 mm = R_b(e) > nm.y ? R_b(e) : nm.y;
-            peer_nm_set(m, from, nn, mm);
-            evaluate_quorum(m);
+            peer_nm_set<MM>(m, from, nn, mm);
+            evaluate_quorum<MM>(m);
             nq_push(nq, NX_PIPELINE);
             return RA_LEADER;
         }
         if (term > m.term) {                                               // :562-576
             if (!known) return RA_LEADER;
-            return step_down(m, term);
+            return step_down<MM>(m, term);
         }
         if (!success) {                                                    // :577-643
             if (!known) return RA_LEADER;
-            ulonglong2 nm = peer_nm(m, from);
+            ulonglong2 nm = peer_nm<MM>(m, from);
             u64 pnext = R_a(e), plast = R_b(e), plast_term = R_c(e);
             u64 t = log_fetch_term(m, (i64)plast);
             u64 nn = nm.x, mm = nm.y;
@@ -877,8 +915,8 @@ __device__ __forceinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
                 i64 x = a < b ? a : b;
                 nn = x > (i64)nm.y ? (u64)x : nm.y;
             }
-            peer_nm_set(m, from, nn, mm);
-            (void)make_pipelined_rpcs(m, false);
+            peer_nm_set<MM>(m, from, nn, mm);
+            (void)make_pipelined_rpcs<MM>(m, false);
         }
         return RA_LEADER;
     }
@@ -888,55 +926,56 @@ __device__ __forceinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
         u64 from = m.last_idx + 1;
         log_append(m, n, m.term);                                          // append_log_leader/3
         note(m, RA_NOTE_WAL_APPEND, 0, from, from + n - 1, m.term);
-        (void)make_pipelined_rpcs(m, (R_flags(e) & RA_EVF_NOOP) != 0);
+        (void)make_pipelined_rpcs<MM>(m, (R_flags(e) & RA_EVF_NOOP) != 0);
         return RA_LEADER;
     }
     if (type == RA_EV_WRITTEN) {                                           // :730-735
         log_handle_written(m, R_term(e), R_a(e), R_b(e));
-        evaluate_quorum(m);
+        evaluate_quorum<MM>(m);
         nq_push(nq, NX_PIPELINE);
         return RA_LEADER;
     }
     if (type == RA_EV_PIPELINE_RPCS) {                                     // :784-792
-        if (make_pipelined_rpcs(m, false)) nq_push(nq, NX_PIPELINE);
+        if (make_pipelined_rpcs<MM>(m, false)) nq_push(nq, NX_PIPELINE);
         return RA_LEADER;
     }
     if (type == RA_EV_AER) {
-        if (R_term(e) > m.term) { u32 r = step_down(m, R_term(e)); nq_push(nq, NX_REDISPATCH); return r; }   // :826-835
+        if (R_term(e) > m.term) { u32 r = step_down<MM>(m, R_term(e)); nq_push(nq, NX_REDISPATCH); return r; }   // :826-835
         if (R_term(e) == m.term) { set_fatal(m, RA_FATAL_LEADER_SAW_AER_SAME_TERM); return RA_LEADER; } // :836-840
-        emit_msg(m, R_from(e), aer_reply(m, m.term, false));               // :841-845
+        emit_msg<MM>(m, R_from(e), aer_reply(m, m.term, false));               // :841-845
         return RA_LEADER;
     }
     if (type == RA_EV_REQUEST_VOTE) {
         if (R_term(e) > m.term) {                                          // :919-933
-            if (R_from(e) >= C.members) return RA_LEADER;
-            u32 r = step_down(m, R_term(e)); nq_push(nq, NX_REDISPATCH); return r;
+            if (R_from(e) >= NMEM(C)) return RA_LEADER;
+            u32 r = step_down<MM>(m, R_term(e)); nq_push(nq, NX_REDISPATCH); return r;
         }
-        reply_vote(m, R_from(e), RA_EV_REQUEST_VOTE_RES, m.term, 0, false);     // :934-936
+        reply_vote<MM>(m, R_from(e), RA_EV_REQUEST_VOTE_RES, m.term, 0, false);     // :934-936
         return RA_LEADER;
     }
     if (type == RA_EV_PRE_VOTE) {
         if (R_term(e) > m.term) {                                          // :937-951
-            if (R_from(e) >= C.members) return RA_LEADER;
-            u32 r = step_down(m, R_term(e)); nq_push(nq, NX_REDISPATCH); return r;
+            if (R_from(e) >= NMEM(C)) return RA_LEADER;
+            u32 r = step_down<MM>(m, R_term(e)); nq_push(nq, NX_REDISPATCH); return r;
         }
-        make_rpcs(m, true);                                                // :952-957
+        make_rpcs<MM>(m, true);                                                // :952-957
         return RA_LEADER;
     }
-    if (type == RA_EV_TICK) make_rpcs(m, false);                           // ra_server_proc.erl:610-613
+    if (type == RA_EV_TICK) make_rpcs<MM>(m, false);                           // ra_server_proc.erl:610-613
     return RA_LEADER;
 }
 
 // ---- handle_candidate/2 :1026-1171 ----------------------------------------------------------
+template <int MM>
 __device__ __forceinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& nq)
 {
     const u32 type = R_type(e);
     if (type == RA_EV_REQUEST_VOTE_RES) {
         if (R_d(e) && R_term(e) == m.term) {                               // :1028-1044
             u32 nv = MT_VOTES(m.meta) + 1;
-            if (nv == required_quorum(m)) {
+            if (nv == required_quorum<MM>(m)) {
                 MT_SET(m.meta, 3, 4, m.slot);
-                initialise_peers(m);
+                initialise_peers<MM>(m);
                 MT_SET(m.meta, 15, 4, 0);
                 nq_push(nq, NX_NOOP);
                 m.c_elections++;
@@ -954,7 +993,7 @@ __device__ __forceinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& 
             nq_push(nq, NX_REDISPATCH);
             return RA_FOLLOWER;
         }
-        emit_msg(m, R_from(e), aer_reply(m, m.term, false));               // :1059-1063
+        emit_msg<MM>(m, R_from(e), aer_reply(m, m.term, false));               // :1059-1063
         return RA_CANDIDATE;
     }
     if (type == RA_EV_AER_REPLY) {
@@ -967,7 +1006,7 @@ __device__ __forceinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& 
             nq_push(nq, NX_REDISPATCH);
             return RA_FOLLOWER;
         }
-        reply_vote(m, R_from(e), RA_EV_REQUEST_VOTE_RES, m.term, 0, false);     // :1107-1109
+        reply_vote<MM>(m, R_from(e), RA_EV_REQUEST_VOTE_RES, m.term, 0, false);     // :1107-1109
         return RA_CANDIDATE;
     }
     if (type == RA_EV_PRE_VOTE) {
@@ -976,10 +1015,10 @@ __device__ __forceinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& 
             nq_push(nq, NX_REDISPATCH);
             return RA_FOLLOWER;
         }
-        return process_pre_vote(m, RA_CANDIDATE, e);                       // :1110-1114
+        return process_pre_vote<MM>(m, RA_CANDIDATE, e);                       // :1110-1114
     }
     if (type == RA_EV_WRITTEN) { log_handle_written(m, R_term(e), R_a(e), R_b(e)); return RA_CANDIDATE; }
-    if (type == RA_EV_ELECTION_TIMEOUT) return call_for_election(m, RA_CANDIDATE, nq);
+    if (type == RA_EV_ELECTION_TIMEOUT) return call_for_election<MM>(m, RA_CANDIDATE, nq);
     if (type == RA_EV_COMMAND) {
         u32 l = MT_LEADER(m.meta);
         note(m, RA_NOTE_NOT_LEADER, 0, R_n(e), l == SLOT_NONE ? RA_NO_SLOT : l, 0);
@@ -988,6 +1027,7 @@ __device__ __forceinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& 
 }
 
 // ---- handle_pre_vote/2 :1173-1261 -----------------------------------------------------------
+template <int MM>
 __device__ __forceinline__ u32 handle_pre_vote(Member& m, const Rec& e, NextQ& nq)
 {
     const u32 type = R_type(e);
@@ -1017,13 +1057,13 @@ __device__ __forceinline__ u32 handle_pre_vote(Member& m, const Rec& e, NextQ& n
         }
         if (R_d(e) && R_term(e) == m.term && R_c(e) == m.token && MT_MEMBERSHIP(m.meta) == RA_VOTER) {  // :1212-1229
             u32 nv = MT_VOTES(m.meta) + 1;
-            if (nv == required_quorum(m)) return call_for_election(m, RA_CANDIDATE, nq);
+            if (nv == required_quorum<MM>(m)) return call_for_election<MM>(m, RA_CANDIDATE, nq);
             MT_SET(m.meta, 15, 4, nv);
         }
         return RA_PRE_VOTE;
     }
-    if (type == RA_EV_PRE_VOTE) return process_pre_vote(m, RA_PRE_VOTE, e);
-    if (type == RA_EV_ELECTION_TIMEOUT) return call_for_election(m, RA_PRE_VOTE, nq);
+    if (type == RA_EV_PRE_VOTE) return process_pre_vote<MM>(m, RA_PRE_VOTE, e);
+    if (type == RA_EV_ELECTION_TIMEOUT) return call_for_election<MM>(m, RA_PRE_VOTE, nq);
     if (type == RA_EV_WRITTEN) { log_handle_written(m, R_term(e), R_a(e), R_b(e)); return RA_PRE_VOTE; }
     if (type == RA_EV_COMMAND) {
         u32 l = MT_LEADER(m.meta);
@@ -1033,21 +1073,22 @@ __device__ __forceinline__ u32 handle_pre_vote(Member& m, const Rec& e, NextQ& n
 }
 
 // ---- handle_await_condition/2 :1900-1941 ------------------------------------------------------
+template <int MM>
 __device__ __forceinline__ u32 handle_await_condition(Member& m, const Rec& e, NextQ& nq)
 {
     const Cols& C = *m.C;
     const u32 type = R_type(e);
     if (type == RA_EV_REQUEST_VOTE) { nq_push(nq, NX_REDISPATCH); return RA_FOLLOWER; }           // :1902-1903
-    if (type == RA_EV_PRE_VOTE) return process_pre_vote(m, RA_AWAIT_CONDITION, e);    // :1904-1905
+    if (type == RA_EV_PRE_VOTE) return process_pre_vote<MM>(m, RA_AWAIT_CONDITION, e);    // :1904-1905
     if (type == RA_EV_ELECTION_TIMEOUT) {                                             // :1906-1913
         if (MT_MEMBERSHIP(m.meta) != RA_VOTER) return RA_AWAIT_CONDITION;
-        return call_for_election(m, RA_PRE_VOTE, nq);
+        return call_for_election<MM>(m, RA_PRE_VOTE, nq);
     }
     if (type == RA_EV_AWAIT_COND_TIMEOUT) {                                           // :1914-1927
         u32 leader = MT_LEADER(m.meta);
         if (MT_COND_VALID(m.meta) && leader != SLOT_NONE) {
             ulonglong2 c0 = C.cd[m.row], c1 = C.cd[(size_t)C.rows + m.row];
-            emit_msg(m, leader, mk_rec(0, RA_EV_AER_REPLY, 0, 0, 0, 0, 0, c0.x, c0.y, c1.x, c1.y, 0, 0));
+            emit_msg<MM>(m, leader, mk_rec(0, RA_EV_AER_REPLY, 0, 0, 0, 0, 0, c0.x, c0.y, c1.x, c1.y, 0, 0));
             m.status |= RA_ST_LEADER_MSG;
         }
         MT_SET(m.meta, 13, 2, 0); MT_SET(m.meta, 25, 1, 0);
@@ -1084,6 +1125,7 @@ __device__ __forceinline__ Rec synth_event(const Member& m, u32 code, const Rec&
     }
 }
 
+template <int MM>
 __device__ __forceinline__ void process_event(Member& m, const Rec& in)
 {
     const Cols& C = *m.C;
@@ -1105,11 +1147,11 @@ __device__ __forceinline__ void process_event(Member& m, const Rec& in)
         const u32 old = m_role(m);
         u32 nr;
         switch (old) {
-        case RA_LEADER:          nr = handle_leader(m, e, nq); break;
-        case RA_FOLLOWER:        nr = handle_follower(m, e, nq); break;
-        case RA_CANDIDATE:       nr = handle_candidate(m, e, nq); break;
-        case RA_PRE_VOTE:        nr = handle_pre_vote(m, e, nq); break;
-        case RA_AWAIT_CONDITION: nr = handle_await_condition(m, e, nq); break;
+        case RA_LEADER:          nr = handle_leader<MM>(m, e, nq); break;
+        case RA_FOLLOWER:        nr = handle_follower<MM>(m, e, nq); break;
+        case RA_CANDIDATE:       nr = handle_candidate<MM>(m, e, nq); break;
+        case RA_PRE_VOTE:        nr = handle_pre_vote<MM>(m, e, nq); break;
+        case RA_AWAIT_CONDITION: nr = handle_await_condition<MM>(m, e, nq); break;
         default:                 nr = old; break;
         }
         if (MT_FATAL(m.meta)) return;
@@ -1124,7 +1166,7 @@ __device__ __forceinline__ void process_event(Member& m, const Rec& in)
             for (u32 i = 0; i < nq.n; i++) {
                 Rec r = synth_event(m, (nq.codes >> (4 * i)) & 15u, e);
                 R_or_flags(r, RA_EVF_NEXT_EVENT);
-                emit_msg(m, m.slot, r);
+                emit_msg<MM>(m, m.slot, r);
             }
             continue;
         }
@@ -1138,4 +1180,88 @@ __device__ __forceinline__ void process_event(Member& m, const Rec& in)
             np += nf;
         }
     }
+}
+
+
+// ---- steady-state fast paths ---------------------------------------------------------------
+// The flood is dominated by six shapes of event.  Each fast path is the general clause
+// specialised under an explicit guard (every condition the general path would test on the
+// way); anything else -- term changes, log mismatch, elections, multi-run batches ... --
+// takes process_event().  Both routes are diffed against the oracle by the parity tests.
+template <int MM>
+__device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
+{
+    const u32 type = R_type(e);
+    const u32 role = m_role(m);
+    const bool nonempty = m_nruns(m) != 0;
+    if (role == RA_FOLLOWER) {
+        if (type == RA_EV_AER) {
+            // handle_follower(#append_entries_rpc{}) :1266-1371, prev entry = our last entry
+            if (R_term(e) != m.term || R_n1(e) != 0 || !nonempty || R_a(e) != m.last_idx || R_b(e) != m.last_term) return false;
+            const u32 n = R_n(e);
+            const u32 leader = R_from(e);
+            if (n == 0) {                                              // validated empty AER :1313-1326
+                m.c_events++;
+                m.status |= RA_ST_LEADER_MSG;
+                MT_SET(m.meta, 3, 4, leader);
+                m.commit = R_c(e);
+                evaluate_commit_index_follower(m);
+                emit_msg<MM>(m, leader, aer_reply(m, R_term(e), true));
+                return true;
+            }
+            if (R_d(e) != m.last_term || m.last_idx + 1 < m.applied) return false;
+            m.c_events++;
+            m.status |= RA_ST_LEADER_MSG;
+            MT_SET(m.meta, 3, 4, leader);
+            m.commit = R_c(e);                                         // :1349
+            const u64 fst = m.last_idx + 1;
+            m.last_idx += n;                                           // same term: the last run grows
+            note(m, RA_NOTE_WAL_APPEND, 0, fst, m.last_idx, m.last_term);
+            evaluate_commit_index_follower(m);
+            return true;
+        }
+        if (type == RA_EV_WRITTEN) {
+            // handle_follower({ra_log_event,{written,..}}) :1441-1458, range ends at our last entry
+            if (!nonempty || R_b(e) != m.last_idx || R_term(e) != m.last_term) return false;
+            m.c_events++;
+            const bool changed = m.lw_idx != m.last_idx || m.lw_term != m.last_term;
+            m.lw_idx = m.last_idx; m.lw_term = m.last_term;
+            const u32 leader = MT_LEADER(m.meta);
+            if (changed && leader != SLOT_NONE) emit_msg<MM>(m, leader, aer_reply(m, m.term, true));
+            return true;
+        }
+        return false;
+    }
+    if (role == RA_LEADER) {
+        bool tail = false;
+        if (type == RA_EV_COMMAND) {                                   // :644-729
+            const u64 n = R_n(e);
+            if (n == 0 || !nonempty) return false;
+            m.c_events++;
+            const u64 from = m.last_idx + 1;
+            log_append(m, n, m.term);
+            note(m, RA_NOTE_WAL_APPEND, 0, from, from + n - 1, m.term);
+            (void)make_pipelined_rpcs<MM>(m, (R_flags(e) & RA_EVF_NOOP) != 0);
+            return true;
+        }
+        if (type == RA_EV_WRITTEN) {                                   // :730-735
+            if (!nonempty || R_b(e) != m.last_idx || R_term(e) != m.last_term) return false;
+            m.c_events++;
+            m.lw_idx = m.last_idx; m.lw_term = m.last_term;
+            tail = true;
+        } else if (type == RA_EV_AER_REPLY) {                          // :522-561
+            const u32 from = R_from(e);
+            if (!(R_d(e) != 0 && R_term(e) == m.term && from < NMEM(*m.C))) return false;
+            m.c_events++;
+            ulonglong2 nm = peer_nm<MM>(m, from);
+            peer_nm_set<MM>(m, from, R_a(e) > nm.x ? R_a(e) : nm.x, R_b(e) > nm.y ? R_b(e) : nm.y);
+            tail = true;
+        }
+        if (!tail) return false;
+        evaluate_quorum<MM>(m);
+        // {next_event, info, pipeline_rpcs}: one chased pass, the rest is deferred (contract 4)
+        if (make_pipelined_rpcs<MM>(m, false)) { MT_SET(m.meta, 24, 1, 1); m.status |= RA_ST_PIPELINE_PENDING; }
+        return !MT_FATAL(m.meta) || true;
+    }
+    return false;
 }
