@@ -18,8 +18,9 @@
 // ------------------------------------------------------------------------------------------
 // the hot kernel
 // ------------------------------------------------------------------------------------------
-#define NST 4                               // shared-memory stages: 4 x 8 KB record planes in flight
-#define PLANE_BYTES (TILE * 64)
+#define NST 6                               // shared-memory stages per warp: 6 x 2 KB record tiles in flight
+#define TILE_BYTES (RT * 64)
+#define WARPS (CTA_T / 32)
 
 __device__ __forceinline__ u64 warp_sum64(u64 v)
 {
@@ -33,6 +34,8 @@ __device__ __forceinline__ void mbar_init(u64* bar, u32 count)
 { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
 __device__ __forceinline__ void mbar_fence_init()
 { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async()
+{ asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes)
 { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
@@ -50,23 +53,20 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
     __trap();
 }
 // one bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_plane(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar)
+__device__ __forceinline__ void tma_load_tile(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// Shared memory of one CTA (128 member rows):
-//   stage[NST][4][128] x 16 B   record planes staged by TMA, chunk-major (conflict-free LDS.128)
-//   bars[NST]                   one mbarrier per stage
-//   peers[3][8][128] x 8 B      per-thread peer columns (next, match, commit_index_sent), lazy
+// Shared memory of one CTA = 4 independent warps x 32 member rows:
+//   stage[warp][NST][4][32] x 16 B   record tiles staged by TMA, chunk-major (conflict-free LDS.128)
+//   bars[warp][NST]                  one mbarrier per stage
+//   peers[3][8][128] x 8 B           per-thread peer columns (next, match, commit_index_sent), lazy
 struct StepSmem {
-    ulonglong2 stage[NST][4 * TILE];
-    u64 peers[3 * 8 * TILE];
-    u64 bars[NST];
-    u32 mask_mbox;              // OR over the CTA's rows: mailbox planes that hold a record
-    u32 mask_loc;               // same for the host-event planes
-    u32 any_work;
+    ulonglong2 stage[WARPS][NST][4 * RT];
+    u64 peers[3 * 8 * CTA_T];
+    u64 bars[WARPS][NST];
 };
 
 // the general path, out of line: rare in a flood, and keeping it out of the hot loop keeps the
@@ -81,13 +81,14 @@ __device__ __noinline__ void slow_event(Member* pm, const Rec* pe)
 }
 
 template <int MM>
-__global__ void __launch_bounds__(TILE, 4)
+__global__ void __launch_bounds__(CTA_T, 3)
 raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StepSmem& S = *reinterpret_cast<StepSmem*>(smem_raw);
-    const u32 tid = threadIdx.x;
-    const u32 r = blockIdx.x * TILE + tid;
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u32 wtile = blockIdx.x * WARPS + warp;                 // this warp's record tile
+    const u32 r = wtile * RT + lane;
     const bool valid = r < C.rows;
     u64 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
 
@@ -110,33 +111,29 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         my_loc = (1u << nloc) - 1u;
     }
     const bool work = valid && (F.on || nloc || cntw || pending);
-    if (tid == 0) {
-        S.mask_mbox = 0; S.mask_loc = 0; S.any_work = 0;
-        for (int i = 0; i < NST; i++) mbar_init(&S.bars[i], 1);
+    // everything below is per warp: no CTA-wide barrier anywhere in this kernel
+    u32 w_mbox = __reduce_or_sync(0xffffffffu, my_mbox), w_loc = __reduce_or_sync(0xffffffffu, my_loc);
+    if (!__any_sync(0xffffffffu, work)) return;                 // whole warp idle
+    u64* bars = &S.bars[warp][0];
+    if (lane == 0) {
+        for (int i = 0; i < NST; i++) mbar_init(&bars[i], 1);
         mbar_fence_init();
     }
-    __syncthreads();
-    {
-        const u32 wm = __reduce_or_sync(0xffffffffu, my_mbox), wl = __reduce_or_sync(0xffffffffu, my_loc);
-        const u32 ww = __reduce_or_sync(0xffffffffu, work ? 1u : 0u);
-        if ((tid & 31) == 0) {
-            if (wm) atomicOr(&S.mask_mbox, wm);
-            if (wl) atomicOr(&S.mask_loc, wl);
-            if (ww) atomicOr(&S.any_work, 1u);
-        }
-    }
-    __syncthreads();
-    if (!S.any_work) return;                                    // whole CTA idle (uniform)
-    u32 cta_mbox = S.mask_mbox, cta_loc = S.mask_loc;
+    __syncwarp();
 
     Member m;
     m.C = &C; m.row = r; m.slot = valid ? r / C.groups : 0; m.group = valid ? r - m.slot * C.groups : 0;
-    ulonglong2 tc = make_ulonglong2(0, 0), lg = tc, lw = tc, sn = tc, tk = tc, fm = tc;
-    if (work) { tc = C.tc[r]; lg = C.lg[r]; lw = C.lw[r]; sn = C.sn[r]; tk = C.tk[r]; fm = C.fm[r]; }
+    ulonglong2 tc = make_ulonglong2(0, 0), lg = tc, lw = tc, sn = tc, tk = tc, fm = tc, lr = tc;
+    if (work) {
+        tc = C.tc[r]; lg = C.lg[r]; lw = C.lw[r]; sn = C.sn[r]; tk = C.tk[r]; fm = C.fm[r];
+        const u32 nr = MT_NRUNS(ap.y);
+        if (nr) lr = C.run[(size_t)(nr - 1) * C.rows + r];
+    }
     m.term = tc.x; m.commit = tc.y; m.last_idx = lg.x; m.last_term = lg.y;
     m.lw_idx = lw.x; m.lw_term = lw.y; m.applied = ap.x; m.meta = ap.y;
     m.snap_idx = sn.x; m.snap_term = sn.y; m.token = tk.x; m.token_ctr = tk.y;
     m.first_idx = fm.x; m.macver = fm.y;
+    m.lrs = lr.x; m.lrs_ok = MT_NRUNS(ap.y) ? 1u : 0u;
     m.n_msgs = 0; m.n_notes = 0; m.status = 0; m.fatal_code = 0; m.role0 = MT_ROLE(ap.y);
     m.sent_to = 0; m.pn_type = RA_NOTE_NONE; m.pn_slot = 0; m.pn_a = m.pn_b = m.pn_c = 0;
     m.w_n = 0; m.w0a = m.w0b = m.w0c = m.w1a = m.w1b = m.w1c = 0;
@@ -146,33 +143,35 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
 
     const bool live = work && !fatal0;
 
-    // ---- inputs: TMA stages the CTA's record planes, NST at a time, in evaluation order ----
+    // ---- inputs: TMA stages this warp's record tiles, NST at a time, in evaluation order ----
     // (deferred pipeline pass, mailbox planes by sender slot then depth, host-event planes)
     u32 round = 0;
-    bool do_pending = live && pending;
+    const bool do_pending = live && pending;
     if (do_pending) MT_SET(m.meta, 24, 1, 0);
-    const u32 any_pending = __syncthreads_or(do_pending ? 1 : 0);
+    const bool any_pending = __any_sync(0xffffffffu, do_pending);
     bool first = true;
-    while (first || (cta_mbox | cta_loc)) {
-        // the next up-to-NST planes
+    while (first || (w_mbox | w_loc)) {
         u32 pl[NST];
-        u32 mm = cta_mbox, ll = cta_loc;
+        {
+            u32 mm = w_mbox, ll = w_loc;
 #pragma unroll
-        for (int i = 0; i < NST; i++) {
-            if (mm) { u32 b = __ffs(mm) - 1; mm &= mm - 1; pl[i] = b; }
-            else if (ll) { u32 b = __ffs(ll) - 1; ll &= ll - 1; pl[i] = 32 + b; }
-            else pl[i] = 0xffffffffu;
+            for (int i = 0; i < NST; i++) {
+                if (mm) { u32 b = __ffs(mm) - 1; mm &= mm - 1; pl[i] = b; }
+                else if (ll) { u32 b = __ffs(ll) - 1; ll &= ll - 1; pl[i] = 32 + b; }
+                else pl[i] = 0xffffffffu;
+            }
+            w_mbox = mm; w_loc = ll;
         }
-        cta_mbox = mm; cta_loc = ll;
-        if (tid == 0) {
+        if (lane == 0) {
+            if (round) fence_proxy_async();                     // stages were read through the generic proxy
 #pragma unroll
             for (int i = 0; i < NST; i++) {
                 if (pl[i] == 0xffffffffu) continue;
                 const ulonglong2* src = (pl[i] < 32)
-                    ? C.mbox[cur] + rec_word(C.tiles, pl[i], blockIdx.x * TILE, 0)
-                    : C.loc + rec_word(C.tiles, pl[i] - 32, blockIdx.x * TILE, 0);
-                mbar_expect_tx(&S.bars[i], PLANE_BYTES);
-                tma_load_plane(&S.stage[i][0], src, PLANE_BYTES, &S.bars[i]);
+                    ? C.mbox[cur] + rec_word(C.tiles, pl[i], wtile * RT, 0)
+                    : C.loc + rec_word(C.tiles, pl[i] - 32, wtile * RT, 0);
+                mbar_expect_tx(&bars[i], TILE_BYTES);
+                tma_load_tile(&S.stage[warp][i][0], src, TILE_BYTES, &bars[i]);
             }
         }
         // one evaluation site: slot -1 is the deferred pipeline pass (first round only)
@@ -186,18 +185,17 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
                 for (int q = 1; q < NST; q++) if (q == i) p = pl[q];
                 if (p == 0xffffffffu) break;
                 mine = (p < 32) ? ((my_mbox >> p) & 1u) : ((my_loc >> (p - 32)) & 1u);
+                mbar_wait(&bars[i], round & 1u);
             }
-            if (!__any_sync(0xffffffffu, mine)) continue;       // warp has nothing here
-            if (i >= 0) mbar_wait(&S.bars[i], round & 1u);
             if (mine) {
                 Rec e;
                 if (i < 0) e = mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
                 else {
-                    const ulonglong2* st = &S.stage[i][0];
-                    e.w0 = st[tid]; e.w1 = st[TILE + tid]; e.w2 = st[2 * TILE + tid]; e.w3 = st[3 * TILE + tid];
+                    const ulonglong2* st = &S.stage[warp][i][0];
+                    e.w0 = st[lane]; e.w1 = st[RT + lane]; e.w2 = st[2 * RT + lane]; e.w3 = st[3 * RT + lane];
                 }
                 if (MT_FATAL(m.meta)) m.c_events++;
-                else if (!fast_event<MM>(m, e)) {
+                else if (C.pure || !fast_event<MM>(m, e)) {
                     Member tmp = m; Rec te = e;
                     slow_event<MM>(&tmp, &te);
                     m = tmp;
@@ -206,7 +204,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         }
         first = false;
         round++;
-        __syncthreads();                                        // stages free before they are refilled
+        __syncwarp();                                           // stages free before they are refilled
     }
 
     if (work) {
@@ -266,7 +264,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         k_events = warp_sum64(k_events); k_commits = warp_sum64(k_commits); k_applied = warp_sum64(k_applied);
         k_msgs = warp_sum64(k_msgs); k_dropped = warp_sum64(k_dropped); k_elect = warp_sum64(k_elect);
         k_fatal = warp_sum64(k_fatal);
-        if ((tid & 31) == 0) {
+        if (lane == 0) {
             if (k_events)  atomicAdd(&C.counters[0], k_events);
             if (k_commits) atomicAdd(&C.counters[1], k_commits);
             if (k_applied) atomicAdd(&C.counters[2], k_applied);
@@ -533,8 +531,8 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
 #define DA(p, n) if ((rc = dalloc(e, &(p), (n))) != RA_OK) goto bad
         DA(C.tc, R); DA(C.lg, R); DA(C.lw, R); DA(C.ap, R); DA(C.sn, R); DA(C.tk, R); DA(C.fm, R);
         DA(C.cd, 2 * R); DA(C.pnm, M * R); DA(C.pcs, M * R); DA(C.run, RA_MAX_RUNS * R);
-        C.tiles = (u32)((R + TILE - 1) / TILE);
-        const size_t PW = (size_t)C.tiles * 4 * TILE;             // 16-byte words per tiled plane
+        C.tiles = (u32)((R + RT - 1) / RT);
+        const size_t PW = (size_t)C.tiles * 4 * RT;             // 16-byte words per tiled plane
         DA(C.loc, (size_t)RA_LOCAL_CAP * PW); DA(C.loc_n, R);
         DA(C.onote, (size_t)RA_NOTE_CAP * R); DA(C.out_n, R); DA(C.counters, 8);
         if (C.routed) {
@@ -608,8 +606,8 @@ extern "C" int ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n)
 static int launch_step(ra_engine* e, const FloodArgs& F)
 {
     switch (e->C.members) {
-    case 5:  raft_step_kernel<5><<<e->C.tiles, TILE, sizeof(StepSmem), e->stream>>>(e->C, e->cur, F); break;
-    default: raft_step_kernel<0><<<e->C.tiles, TILE, sizeof(StepSmem), e->stream>>>(e->C, e->cur, F); break;
+    case 5:  raft_step_kernel<5><<<(e->C.tiles + WARPS - 1) / WARPS, CTA_T, sizeof(StepSmem), e->stream>>>(e->C, e->cur, F); break;
+    default: raft_step_kernel<0><<<(e->C.tiles + WARPS - 1) / WARPS, CTA_T, sizeof(StepSmem), e->stream>>>(e->C, e->cur, F); break;
     }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(e, ce, "raft_step_kernel");

@@ -72,14 +72,14 @@ struct Cols {
     // log view: [k][rows] {run_start, run_term}
     ulonglong2* run;
     // transport / io.  Input record planes (mailboxes, locals) are TILED: plane p holds, for
-    // every tile of 128 consecutive rows, 4 chunk sub-tiles [chunk j][lane] of 16 bytes, i.e.
-    // the 8 KB a CTA needs from a plane are contiguous (one cp.async.bulk) and land in shared
-    // memory chunk-major (lane-consecutive 16-byte words: conflict-free LDS.128).
+    // every tile of 32 consecutive rows (one warp), 4 chunk sub-tiles [chunk j][lane] of
+    // 16 bytes, i.e. the 2 KB a warp needs from a plane are contiguous (one cp.async.bulk) and
+    // land in shared memory chunk-major (lane-consecutive 16-byte words: conflict-free LDS.128).
     ulonglong2* mbox[2];   // plane (src*DEPTH + k)
     u64*        mbox_cnt[2]; // [rows] one byte per sender slot
     ulonglong2* loc;       // plane k: host ("local") events
     u32*        loc_n;     // [rows]
-    u32 tiles;             // ceil(rows / 128)
+    u32 tiles;             // ceil(rows / 32)
     ra_event* omsg;     // [k][rows] outgoing RPC records (non-routed)
     ra_note*  onote;    // [k][rows]
     u32*      out_n;    // [rows] msgs | notes << 16
@@ -89,11 +89,12 @@ struct Cols {
     u32 routed, pure;
 };
 
-#define TILE 128
+#define CTA_T 128                 // threads per CTA (4 independent warps)
+#define RT 32                     // rows per record tile = one warp
 // address (in 16-byte words) of chunk j of the record of `row` in tiled plane `plane`
 __device__ __forceinline__ size_t rec_word(u32 tiles, u32 plane, u32 row, u32 j)
 {
-    return (((size_t)plane * tiles + (row >> 7)) * 4 + j) * TILE + (row & (TILE - 1));
+    return (((size_t)plane * tiles + (row >> 5)) * 4 + j) * RT + (row & (RT - 1));
 }
 
 struct FloodArgs { u32 on; u32 cmds; u32 permille; u32 _p; u64 seed; u64 step; };
@@ -125,12 +126,12 @@ __device__ __forceinline__ void st_rec(ra_event* p, const Rec& r)
 __device__ __forceinline__ void st_rec_tiled(ulonglong2* base, u32 tiles, u32 plane, u32 row, const Rec& r)
 {
     ulonglong2* q = base + rec_word(tiles, plane, row, 0);
-    q[0] = r.w0; q[TILE] = r.w1; q[2 * TILE] = r.w2; q[3 * TILE] = r.w3;
+    q[0] = r.w0; q[RT] = r.w1; q[2 * RT] = r.w2; q[3 * RT] = r.w3;
 }
 __device__ __forceinline__ Rec ld_rec_tiled(const ulonglong2* base, u32 tiles, u32 plane, u32 row)
 {
     const ulonglong2* q = base + rec_word(tiles, plane, row, 0);
-    Rec r; r.w0 = q[0]; r.w1 = q[TILE]; r.w2 = q[2 * TILE]; r.w3 = q[3 * TILE];
+    Rec r; r.w0 = q[0]; r.w1 = q[RT]; r.w2 = q[2 * RT]; r.w3 = q[3 * RT];
     return r;
 }
 // header word: row | type<<32 | from<<40 | flags<<48 | pad<<56 ; second: n | n1<<16 | seq<<32
@@ -191,8 +192,10 @@ struct Member {
     u32 c_events, c_msgs, c_dropped, c_elections;
     u64 c_commits, c_applied;
     int nb;                     // mailbox buffer written this step
-    // per-peer columns staged in shared memory on first use: sp[(f*8 + s) * TILE], f = 0 next,
+    // per-peer columns staged in shared memory on first use: sp[(f*8 + s) * CTA_T], f = 0 next,
     // 1 match, 2 commit_index_sent (this thread's column: consecutive lanes, no bank conflicts)
+    u64 lrs;                    // start index of the last term run (valid when n_runs > 0 and lrs_ok)
+    u32 lrs_ok;
     u64* sp;
     u32 pstate;                 // bit0 loaded, bits 8..15 {next,match} dirty, bits 16..23 commit_sent dirty
 };
@@ -213,31 +216,31 @@ __device__ __forceinline__ void peers_ensure(Member& m)
     const Cols& C = *m.C;
     for (u32 s = 0; s < NMEM(C); s++) {
         ulonglong2 nm = C.pnm[(size_t)s * C.rows + m.row];
-        m.sp[(0 * 8 + s) * TILE] = nm.x; m.sp[(1 * 8 + s) * TILE] = nm.y;
-        m.sp[(2 * 8 + s) * TILE] = C.pcs[(size_t)s * C.rows + m.row];
+        m.sp[(0 * 8 + s) * CTA_T] = nm.x; m.sp[(1 * 8 + s) * CTA_T] = nm.y;
+        m.sp[(2 * 8 + s) * CTA_T] = C.pcs[(size_t)s * C.rows + m.row];
     }
     m.pstate |= 1u;
 }
 template <int MM>
 __device__ __forceinline__ ulonglong2 peer_nm(Member& m, u32 s)
-{ peers_ensure<MM>(m); return make_ulonglong2(m.sp[(0 * 8 + s) * TILE], m.sp[(1 * 8 + s) * TILE]); }
+{ peers_ensure<MM>(m); return make_ulonglong2(m.sp[(0 * 8 + s) * CTA_T], m.sp[(1 * 8 + s) * CTA_T]); }
 template <int MM>
 __device__ __forceinline__ void peer_nm_set(Member& m, u32 s, u64 next, u64 match)
-{ peers_ensure<MM>(m); m.sp[(0 * 8 + s) * TILE] = next; m.sp[(1 * 8 + s) * TILE] = match; m.pstate |= 1u << (8 + s); }
+{ peers_ensure<MM>(m); m.sp[(0 * 8 + s) * CTA_T] = next; m.sp[(1 * 8 + s) * CTA_T] = match; m.pstate |= 1u << (8 + s); }
 template <int MM>
 __device__ __forceinline__ u64 peer_cs(Member& m, u32 s)
-{ peers_ensure<MM>(m); return m.sp[(2 * 8 + s) * TILE]; }
+{ peers_ensure<MM>(m); return m.sp[(2 * 8 + s) * CTA_T]; }
 template <int MM>
 __device__ __forceinline__ void peer_cs_set(Member& m, u32 s, u64 v)
-{ peers_ensure<MM>(m); m.sp[(2 * 8 + s) * TILE] = v; m.pstate |= 1u << (16 + s); }
+{ peers_ensure<MM>(m); m.sp[(2 * 8 + s) * CTA_T] = v; m.pstate |= 1u << (16 + s); }
 template <int MM>
 __device__ __forceinline__ void peers_writeback(Member& m)
 {
     if (!(m.pstate >> 8)) return;
     const Cols& C = *m.C;
     for (u32 s = 0; s < NMEM(C); s++) {
-        if (m.pstate & (1u << (8 + s))) st2(&C.pnm[(size_t)s * C.rows + m.row], m.sp[(0 * 8 + s) * TILE], m.sp[(1 * 8 + s) * TILE]);
-        if (m.pstate & (1u << (16 + s))) C.pcs[(size_t)s * C.rows + m.row] = m.sp[(2 * 8 + s) * TILE];
+        if (m.pstate & (1u << (8 + s))) st2(&C.pnm[(size_t)s * C.rows + m.row], m.sp[(0 * 8 + s) * CTA_T], m.sp[(1 * 8 + s) * CTA_T]);
+        if (m.pstate & (1u << (16 + s))) C.pcs[(size_t)s * C.rows + m.row] = m.sp[(2 * 8 + s) * CTA_T];
     }
 }
 
@@ -294,6 +297,7 @@ __device__ __forceinline__ void log_append(Member& m, u64 n, u64 term)
         }
         run_set(m, nr, idx, term);
         nr++;
+        m.lrs = idx; m.lrs_ok = 1;
     }
     MT_SET(m.meta, 19, 4, nr);
     m.last_idx = idx + n - 1;
@@ -304,6 +308,7 @@ __device__ __forceinline__ void log_append(Member& m, u64 n, u64 term)
 __device__ __forceinline__ void log_truncate(Member& m, u64 idx, u64 fallback_term)
 {
     u32 nr = m_nruns(m);
+    m.lrs_ok = 0;
     while (nr > 0 && run_get(m, nr - 1).x > idx) nr--;
     if (!log_nonempty(m) || idx < m.first_idx) {
         nr = 0;
@@ -520,7 +525,7 @@ __device__ __forceinline__ void evaluate_quorum(Member& m)
         const bool in = (u32)s < M;
         const bool self = (u32)s == m.slot;
         const bool voter = in && !self && MT_VOTER(m.meta, s);
-        v[s] = self ? m.lw_idx : (voter ? m.sp[(1 * 8 + s) * TILE] : 0ull);
+        v[s] = self ? m.lw_idx : (voter ? m.sp[(1 * 8 + s) * CTA_T] : 0ull);
         n += voter ? 1u : 0u;
     }
 #pragma unroll
@@ -1222,10 +1227,12 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
         }
         if (type == RA_EV_WRITTEN) {
             // handle_follower({ra_log_event,{written,..}}) :1441-1458, range ends at our last entry
-            if (!nonempty || R_b(e) != m.last_idx || R_term(e) != m.last_term) return false;
+            // (every index of the last run has term last_term: ra_log:fetch_term(To) == Term)
+            if (nonempty && !m.lrs_ok) { m.lrs = run_get(m, m_nruns(m) - 1).x; m.lrs_ok = 1; }
+            if (!nonempty || !m.lrs_ok || R_term(e) != m.last_term || R_b(e) > m.last_idx || R_b(e) < m.lrs) return false;
             m.c_events++;
-            const bool changed = m.lw_idx != m.last_idx || m.lw_term != m.last_term;
-            m.lw_idx = m.last_idx; m.lw_term = m.last_term;
+            const bool changed = m.lw_idx != R_b(e) || m.lw_term != m.last_term;
+            m.lw_idx = R_b(e); m.lw_term = m.last_term;
             const u32 leader = MT_LEADER(m.meta);
             if (changed && leader != SLOT_NONE) emit_msg<MM>(m, leader, aer_reply(m, m.term, true));
             return true;
@@ -1245,9 +1252,10 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
             return true;
         }
         if (type == RA_EV_WRITTEN) {                                   // :730-735
-            if (!nonempty || R_b(e) != m.last_idx || R_term(e) != m.last_term) return false;
+            if (nonempty && !m.lrs_ok) { m.lrs = run_get(m, m_nruns(m) - 1).x; m.lrs_ok = 1; }
+            if (!nonempty || !m.lrs_ok || R_term(e) != m.last_term || R_b(e) > m.last_idx || R_b(e) < m.lrs) return false;
             m.c_events++;
-            m.lw_idx = m.last_idx; m.lw_term = m.last_term;
+            m.lw_idx = R_b(e); m.lw_term = m.last_term;
             tail = true;
         } else if (type == RA_EV_AER_REPLY) {                          // :522-561
             const u32 from = R_from(e);
