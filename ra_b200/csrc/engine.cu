@@ -18,7 +18,12 @@
 // ------------------------------------------------------------------------------------------
 // the hot kernel
 // ------------------------------------------------------------------------------------------
-#define NST 6                               // shared-memory stages per warp: 6 x 2 KB record tiles in flight
+#ifndef NST
+#define NST 6                               // shared-memory stages per warp: NST x 2 KB record tiles in flight
+#endif
+#ifndef MINB
+#define MINB 3                              // CTAs per SM the register allocation is held to
+#endif
 #define TILE_BYTES (RT * 64)
 #define WARPS (CTA_T / 32)
 
@@ -63,9 +68,10 @@ __device__ __forceinline__ void tma_load_tile(void* dst_smem, const void* src_gm
 //   stage[warp][NST][4][32] x 16 B   record tiles staged by TMA, chunk-major (conflict-free LDS.128)
 //   bars[warp][NST]                  one mbarrier per stage
 //   peers[3][8][128] x 8 B           per-thread peer columns (next, match, commit_index_sent), lazy
+template <int MM>
 struct StepSmem {
     ulonglong2 stage[WARPS][NST][4 * RT];
-    u64 peers[3 * 8 * CTA_T];
+    u64 peers[3 * PSTR * CTA_T];
     u64 bars[WARPS][NST];
 };
 
@@ -81,16 +87,16 @@ __device__ __noinline__ void slow_event(Member* pm, const Rec* pe)
 }
 
 template <int MM>
-__global__ void __launch_bounds__(CTA_T, 3)
+__global__ void __launch_bounds__(CTA_T, MINB)
 raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    StepSmem& S = *reinterpret_cast<StepSmem*>(smem_raw);
+    StepSmem<MM>& S = *reinterpret_cast<StepSmem<MM>*>(smem_raw);
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u32 wtile = blockIdx.x * WARPS + warp;                 // this warp's record tile
     const u32 r = wtile * RT + lane;
     const bool valid = r < C.rows;
-    u64 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
+    u32 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
 
     // ---- what does this row have to do? ---------------------------------------------------
     ulonglong2 ap = make_ulonglong2(0, 0);
@@ -139,72 +145,61 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     m.w_n = 0; m.w0a = m.w0b = m.w0c = m.w1a = m.w1b = m.w1c = 0;
     m.c_events = m.c_msgs = m.c_dropped = m.c_elections = 0; m.c_commits = m.c_applied = 0;
     m.nb = cur ^ 1;
-    m.sp = &S.peers[tid]; m.pstate = 0;
+    m.sp = &S.peers[tid]; m.pstate = 0; m.pipe_clean = 0; m.pc_last = m.pc_commit = 0;
 
     const bool live = work && !fatal0;
 
-    // ---- inputs: TMA stages this warp's record tiles, NST at a time, in evaluation order ----
-    // (deferred pipeline pass, mailbox planes by sender slot then depth, host-event planes)
-    u32 round = 0;
+    // ---- inputs: TMA stages this warp's record tiles through a ring of NST 2 KB slots, in ------
+    // evaluation order: deferred pipeline pass, mailbox planes by sender slot then depth, then
+    // the host-event planes.  A slot is refilled as soon as the warp has consumed it.
     const bool do_pending = live && pending;
     if (do_pending) MT_SET(m.meta, 24, 1, 0);
-    const bool any_pending = __any_sync(0xffffffffu, do_pending);
-    bool first = true;
-    while (first || (w_mbox | w_loc)) {
-        u32 pl[NST];
-        {
-            u32 mm = w_mbox, ll = w_loc;
-#pragma unroll
-            for (int i = 0; i < NST; i++) {
-                if (mm) { u32 b = __ffs(mm) - 1; mm &= mm - 1; pl[i] = b; }
-                else if (ll) { u32 b = __ffs(ll) - 1; ll &= ll - 1; pl[i] = 32 + b; }
-                else pl[i] = 0xffffffffu;
-            }
-            w_mbox = mm; w_loc = ll;
-        }
-        if (lane == 0) {
-            if (round) fence_proxy_async();                     // stages were read through the generic proxy
-#pragma unroll
-            for (int i = 0; i < NST; i++) {
-                if (pl[i] == 0xffffffffu) continue;
-                const ulonglong2* src = (pl[i] < 32)
-                    ? C.mbox[cur] + rec_word(C.tiles, pl[i], wtile * RT, 0)
-                    : C.loc + rec_word(C.tiles, pl[i] - 32, wtile * RT, 0);
-                mbar_expect_tx(&bars[i], TILE_BYTES);
-                tma_load_tile(&S.stage[warp][i][0], src, TILE_BYTES, &bars[i]);
-            }
-        }
-        // one evaluation site: slot -1 is the deferred pipeline pass (first round only)
+    u64 todo = (u64)w_mbox | ((u64)w_loc << 32);                // planes still to consume
+    u64 toissue = todo;                                         // planes still to request
+    u32 n_issued = 0, n_done = 0;
+    if (lane == 0) {
 #pragma unroll 1
-        for (int i = (first && any_pending) ? -1 : 0; i < NST; i++) {
-            bool mine; u32 p = 0;
-            if (i < 0) mine = do_pending;
-            else {
-                p = pl[0];
-#pragma unroll
-                for (int q = 1; q < NST; q++) if (q == i) p = pl[q];
-                if (p == 0xffffffffu) break;
-                mine = (p < 32) ? ((my_mbox >> p) & 1u) : ((my_loc >> (p - 32)) & 1u);
-                mbar_wait(&bars[i], round & 1u);
-            }
-            if (mine) {
-                Rec e;
-                if (i < 0) e = mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-                else {
-                    const ulonglong2* st = &S.stage[warp][i][0];
-                    e.w0 = st[lane]; e.w1 = st[RT + lane]; e.w2 = st[2 * RT + lane]; e.w3 = st[3 * RT + lane];
-                }
-                if (MT_FATAL(m.meta)) m.c_events++;
-                else if (C.pure || !fast_event<MM>(m, e)) {
-                    Member tmp = m; Rec te = e;
-                    slow_event<MM>(&tmp, &te);
-                    m = tmp;
-                }
-            }
+        while (toissue && n_issued < NST) {
+            const u32 p = __ffsll((long long)toissue) - 1; toissue &= toissue - 1;
+            const ulonglong2* src = (p < 32) ? C.mbox[cur] + rec_word(C.tiles, p, wtile * RT, 0)
+                                             : C.loc + rec_word(C.tiles, p - 32, wtile * RT, 0);
+            mbar_expect_tx(&bars[n_issued], TILE_BYTES);
+            tma_load_tile(&S.stage[warp][n_issued][0], src, TILE_BYTES, &bars[n_issued]);
+            n_issued++;
         }
-        first = false;
-        round++;
-        __syncwarp();                                           // stages free before they are refilled
+    }
+    // one evaluation site; the deferred pipeline pass rides in front as a pseudo plane
+    bool pend_round = __any_sync(0xffffffffu, do_pending);
+#pragma unroll 1
+    while (pend_round || todo) {
+        bool mine; u32 st = 0;
+        Rec e;
+        if (pend_round) {
+            mine = do_pending;
+            e = mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+        } else {
+            const u32 p = __ffsll((long long)todo) - 1; todo &= todo - 1;
+            st = n_done % NST;
+            mine = (p < 32) ? ((my_mbox >> p) & 1u) : ((my_loc >> (p - 32)) & 1u);
+            mbar_wait(&bars[st], (n_done / NST) & 1u);
+            const ulonglong2* sp = &S.stage[warp][st][0];
+            e.w0 = sp[lane]; e.w1 = sp[RT + lane]; e.w2 = sp[2 * RT + lane]; e.w3 = sp[3 * RT + lane];
+        }
+        if (mine) {
+            if (MT_FATAL(m.meta)) m.c_events++;
+            else if (C.pure || !fast_event<MM>(m, e)) { Member tmp = m; Rec te = e; slow_event<MM>(&tmp, &te); m = tmp; }
+        }
+        if (pend_round) { pend_round = false; continue; }
+        n_done++;
+        __syncwarp();                                           // every lane is done with slot st
+        if (lane == 0 && toissue) {
+            const u32 q = __ffsll((long long)toissue) - 1; toissue &= toissue - 1;
+            const ulonglong2* src = (q < 32) ? C.mbox[cur] + rec_word(C.tiles, q, wtile * RT, 0)
+                                             : C.loc + rec_word(C.tiles, q - 32, wtile * RT, 0);
+            fence_proxy_async();                                // slot st was read through the generic proxy
+            mbar_expect_tx(&bars[st], TILE_BYTES);
+            tma_load_tile(&S.stage[warp][st][0], src, TILE_BYTES, &bars[st]);
+        }
     }
 
     if (work) {
@@ -239,10 +234,14 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             else if (idle < 15) idle++;
             bool fire = false;
             if (role != RA_LEADER) {
-                u64 h = mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ ((u64)m.group * 0xD1B54A32D192ED03ull));
-                if (F.permille && (h % 1000) < F.permille && ((h / 1000) % NMEM(C)) == m.slot) fire = true;
-                u64 h2 = mix64(F.seed ^ ((u64)r * 0xA24BAED4963EE407ull) ^ F.step);
-                if (idle >= 8 + (u32)(h2 % 8)) fire = true;
+                if (F.permille) {
+                    u64 h = mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ ((u64)m.group * 0xD1B54A32D192ED03ull));
+                    if ((h % 1000) < F.permille && ((h / 1000) % NMEM(C)) == m.slot) fire = true;
+                }
+                if (idle >= 8) {                                // the hash only matters from 8 idle steps on
+                    u64 h2 = mix64(F.seed ^ ((u64)r * 0xA24BAED4963EE407ull) ^ F.step);
+                    if (idle >= 8 + (u32)(h2 % 8)) fire = true;
+                }
             }
             if (fire) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_ELECTION_TIMEOUT, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)); k++; idle = 0; }
             MT_SET(m.meta, 28, 4, idle);
@@ -258,20 +257,20 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         k_events = m.c_events; k_commits = m.c_commits; k_applied = m.c_applied;
         k_msgs = m.c_msgs; k_dropped = m.c_dropped; k_elect = m.c_elections;
     }
-    // per-launch device counters: warp reduce, one atomic per warp and counter that moved
-    const u32 any = __ballot_sync(0xffffffffu, (k_events | k_fatal) != 0);
-    if (any) {
-        k_events = warp_sum64(k_events); k_commits = warp_sum64(k_commits); k_applied = warp_sum64(k_applied);
-        k_msgs = warp_sum64(k_msgs); k_dropped = warp_sum64(k_dropped); k_elect = warp_sum64(k_elect);
-        k_fatal = warp_sum64(k_fatal);
+    // per-launch device counters: one REDUX per counter, one atomic per warp and counter that moved
+    if (__any_sync(0xffffffffu, (k_events | k_fatal) != 0)) {
+        k_events = __reduce_add_sync(0xffffffffu, k_events); k_commits = __reduce_add_sync(0xffffffffu, k_commits);
+        k_applied = __reduce_add_sync(0xffffffffu, k_applied); k_msgs = __reduce_add_sync(0xffffffffu, k_msgs);
+        k_dropped = __reduce_add_sync(0xffffffffu, k_dropped); k_elect = __reduce_add_sync(0xffffffffu, k_elect);
+        k_fatal = __reduce_add_sync(0xffffffffu, k_fatal);
         if (lane == 0) {
-            if (k_events)  atomicAdd(&C.counters[0], k_events);
-            if (k_commits) atomicAdd(&C.counters[1], k_commits);
-            if (k_applied) atomicAdd(&C.counters[2], k_applied);
-            if (k_msgs)    atomicAdd(&C.counters[3], k_msgs);
-            if (k_dropped) atomicAdd(&C.counters[4], k_dropped);
-            if (k_elect)   atomicAdd(&C.counters[5], k_elect);
-            if (k_fatal)   atomicAdd(&C.counters[6], k_fatal);
+            if (k_events)  atomicAdd(&C.counters[0], (u64)k_events);
+            if (k_commits) atomicAdd(&C.counters[1], (u64)k_commits);
+            if (k_applied) atomicAdd(&C.counters[2], (u64)k_applied);
+            if (k_msgs)    atomicAdd(&C.counters[3], (u64)k_msgs);
+            if (k_dropped) atomicAdd(&C.counters[4], (u64)k_dropped);
+            if (k_elect)   atomicAdd(&C.counters[5], (u64)k_elect);
+            if (k_fatal)   atomicAdd(&C.counters[6], (u64)k_fatal);
         }
     }
 }
@@ -548,8 +547,8 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp_bytes, e->d_packed, e->d_offs, (int)(R + 1), e->stream);
         if ((ce = cudaMalloc(&e->d_scan_tmp, e->scan_tmp_bytes ? e->scan_tmp_bytes : 16)) != cudaSuccess) { rc = fail(e, ce, "cudaMalloc scan"); goto bad; }
     }
-    if ((ce = cudaFuncSetAttribute(raft_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem))) != cudaSuccess ||
-        (ce = cudaFuncSetAttribute(raft_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem))) != cudaSuccess) {
+    if ((ce = cudaFuncSetAttribute(raft_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<0>))) != cudaSuccess ||
+        (ce = cudaFuncSetAttribute(raft_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<5>))) != cudaSuccess) {
         rc = fail(e, ce, "cudaFuncSetAttribute"); goto bad;
     }
     if ((rc = ra_engine_reset_empty(e)) != RA_OK) goto bad;
@@ -606,8 +605,8 @@ extern "C" int ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n)
 static int launch_step(ra_engine* e, const FloodArgs& F)
 {
     switch (e->C.members) {
-    case 5:  raft_step_kernel<5><<<(e->C.tiles + WARPS - 1) / WARPS, CTA_T, sizeof(StepSmem), e->stream>>>(e->C, e->cur, F); break;
-    default: raft_step_kernel<0><<<(e->C.tiles + WARPS - 1) / WARPS, CTA_T, sizeof(StepSmem), e->stream>>>(e->C, e->cur, F); break;
+    case 5:  raft_step_kernel<5><<<(e->C.tiles + WARPS - 1) / WARPS, CTA_T, sizeof(StepSmem<5>), e->stream>>>(e->C, e->cur, F); break;
+    default: raft_step_kernel<0><<<(e->C.tiles + WARPS - 1) / WARPS, CTA_T, sizeof(StepSmem<0>), e->stream>>>(e->C, e->cur, F); break;
     }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(e, ce, "raft_step_kernel");

@@ -55,6 +55,7 @@ typedef unsigned char u8;
 #define SLOT_NONE 15u
 // number of members: compile-time when the kernel is specialised (MM != 0), else from the config
 #define NMEM(C) ((u32)(MM ? MM : (C).members))
+#define PSTR (MM ? MM : RA_MAX_MEMBERS)      // peer slots staged per thread in shared memory
 
 struct Cols {
     // scalar pairs, one cell per row
@@ -190,12 +191,17 @@ struct Member {
     u32 w_n; u64 w0a, w0b, w0c, w1a, w1b, w1c;
     // counters
     u32 c_events, c_msgs, c_dropped, c_elections;
-    u64 c_commits, c_applied;
+    u32 c_commits, c_applied;   // per row and step: far below 2^32
     int nb;                     // mailbox buffer written this step
     // per-peer columns staged in shared memory on first use: sp[(f*8 + s) * CTA_T], f = 0 next,
     // 1 match, 2 commit_index_sent (this thread's column: consecutive lanes, no bank conflicts)
     u64 lrs;                    // start index of the last term run (valid when n_runs > 0 and lrs_ok)
     u32 lrs_ok;
+    // exact shortcut for make_pipelined_rpc_effects: set when a pass found every normal peer with
+    // next_index >= next_log_index and commit_index_sent >= commit_index; stays true while only
+    // success replies (next/match can only grow) arrive and neither the log nor commit_index move
+    u32 pipe_clean;
+    u64 pc_last, pc_commit;     // the (last_index, commit_index) the flag was computed for
     u64* sp;
     u32 pstate;                 // bit0 loaded, bits 8..15 {next,match} dirty, bits 16..23 commit_sent dirty
 };
@@ -216,31 +222,31 @@ __device__ __forceinline__ void peers_ensure(Member& m)
     const Cols& C = *m.C;
     for (u32 s = 0; s < NMEM(C); s++) {
         ulonglong2 nm = C.pnm[(size_t)s * C.rows + m.row];
-        m.sp[(0 * 8 + s) * CTA_T] = nm.x; m.sp[(1 * 8 + s) * CTA_T] = nm.y;
-        m.sp[(2 * 8 + s) * CTA_T] = C.pcs[(size_t)s * C.rows + m.row];
+        m.sp[(0 * PSTR + s) * CTA_T] = nm.x; m.sp[(1 * PSTR + s) * CTA_T] = nm.y;
+        m.sp[(2 * PSTR + s) * CTA_T] = C.pcs[(size_t)s * C.rows + m.row];
     }
     m.pstate |= 1u;
 }
 template <int MM>
 __device__ __forceinline__ ulonglong2 peer_nm(Member& m, u32 s)
-{ peers_ensure<MM>(m); return make_ulonglong2(m.sp[(0 * 8 + s) * CTA_T], m.sp[(1 * 8 + s) * CTA_T]); }
+{ peers_ensure<MM>(m); return make_ulonglong2(m.sp[(0 * PSTR + s) * CTA_T], m.sp[(1 * PSTR + s) * CTA_T]); }
 template <int MM>
 __device__ __forceinline__ void peer_nm_set(Member& m, u32 s, u64 next, u64 match)
-{ peers_ensure<MM>(m); m.sp[(0 * 8 + s) * CTA_T] = next; m.sp[(1 * 8 + s) * CTA_T] = match; m.pstate |= 1u << (8 + s); }
+{ peers_ensure<MM>(m); m.sp[(0 * PSTR + s) * CTA_T] = next; m.sp[(1 * PSTR + s) * CTA_T] = match; m.pstate |= 1u << (8 + s); }
 template <int MM>
 __device__ __forceinline__ u64 peer_cs(Member& m, u32 s)
-{ peers_ensure<MM>(m); return m.sp[(2 * 8 + s) * CTA_T]; }
+{ peers_ensure<MM>(m); return m.sp[(2 * PSTR + s) * CTA_T]; }
 template <int MM>
 __device__ __forceinline__ void peer_cs_set(Member& m, u32 s, u64 v)
-{ peers_ensure<MM>(m); m.sp[(2 * 8 + s) * CTA_T] = v; m.pstate |= 1u << (16 + s); }
+{ peers_ensure<MM>(m); m.sp[(2 * PSTR + s) * CTA_T] = v; m.pstate |= 1u << (16 + s); }
 template <int MM>
 __device__ __forceinline__ void peers_writeback(Member& m)
 {
     if (!(m.pstate >> 8)) return;
     const Cols& C = *m.C;
     for (u32 s = 0; s < NMEM(C); s++) {
-        if (m.pstate & (1u << (8 + s))) st2(&C.pnm[(size_t)s * C.rows + m.row], m.sp[(0 * 8 + s) * CTA_T], m.sp[(1 * 8 + s) * CTA_T]);
-        if (m.pstate & (1u << (16 + s))) C.pcs[(size_t)s * C.rows + m.row] = m.sp[(2 * 8 + s) * CTA_T];
+        if (m.pstate & (1u << (8 + s))) st2(&C.pnm[(size_t)s * C.rows + m.row], m.sp[(0 * PSTR + s) * CTA_T], m.sp[(1 * PSTR + s) * CTA_T]);
+        if (m.pstate & (1u << (16 + s))) C.pcs[(size_t)s * C.rows + m.row] = m.sp[(2 * PSTR + s) * CTA_T];
     }
 }
 
@@ -495,7 +501,7 @@ __device__ __forceinline__ void apply_to(Member& m, u64 upto)
     u64 to = m.last_idx < upto ? m.last_idx : upto;
     if (to < from) return;
     note(m, RA_NOTE_APPLY, 0, from, to, 0);
-    m.c_applied += to - from + 1;
+    m.c_applied += (u32)(to - from + 1);
     m.applied = to;
 }
 
@@ -525,7 +531,7 @@ __device__ __forceinline__ void evaluate_quorum(Member& m)
         const bool in = (u32)s < M;
         const bool self = (u32)s == m.slot;
         const bool voter = in && !self && MT_VOTER(m.meta, s);
-        v[s] = self ? m.lw_idx : (voter ? m.sp[(1 * 8 + s) * CTA_T] : 0ull);
+        v[s] = self ? m.lw_idx : (voter ? m.sp[(1 * PSTR + s) * CTA_T] : 0ull);
         n += voter ? 1u : 0u;
     }
 #pragma unroll
@@ -541,7 +547,7 @@ __device__ __forceinline__ void evaluate_quorum(Member& m)
     if (srv_fetch_term(m, (i64)best) == m.term) m.commit = best;        // §5.4.2 gate :3625-3629
     if (m.commit > ci0) {
         note(m, RA_NOTE_COMMIT, 0, ci0, m.commit, 0);
-        m.c_commits += m.commit - ci0;
+        m.c_commits += (u32)(m.commit - ci0);
     }
     apply_to(m, m.commit);
 }
@@ -602,9 +608,10 @@ template <int MM>
 __device__ __forceinline__ bool make_pipelined_rpcs(Member& m, bool force)
 {
     const Cols& C = *m.C;
+    if (m.pipe_clean && !force && m.pc_last == m.last_idx && m.pc_commit == m.commit) return false;
     u64 next_log_idx = m.last_idx + 1;
     i64 max_pipe = C.max_pipeline, max_batch = C.max_batch;
-    bool more = false;
+    bool more = false, clean = true;
     for (u32 s = 0; s < NMEM(C); s++) {
         if (s == m.slot) continue;
         if (MT_PSTATUS(m.meta, s) != RA_PEER_NORMAL) continue;
@@ -612,7 +619,7 @@ __device__ __forceinline__ bool make_pipelined_rpcs(Member& m, bool force)
         u64 cs = peer_cs<MM>(m, s);
         if (!(nm.x < next_log_idx || cs < m.commit)) continue;
         i64 in_flight = (i64)nm.x - (i64)nm.y - 1;
-        if (!(in_flight < max_pipe || force)) continue;
+        if (!(in_flight < max_pipe || force)) { clean = false; continue; }
         i64 bs = max_pipe - in_flight; if (max_batch < bs) bs = max_batch; if (bs < 1) bs = 1;
         bool snap;
         u64 nn = make_rpc_effect<MM>(m, s, nm.x, (u64)bs, snap);
@@ -623,7 +630,9 @@ __device__ __forceinline__ bool make_pipelined_rpcs(Member& m, bool force)
         if (snap && !C.pure) MT_SET(m.meta, 32 + 3 * s, 3, RA_PEER_SENDING_SNAPSHOT);
         i64 nif = (i64)nn - (i64)nm.y - 1;
         if (nn < next_log_idx && nif < max_pipe) more = true;
+        if (nn < next_log_idx) clean = false;
     }
+    m.pipe_clean = clean ? 1u : 0u; m.pc_last = m.last_idx; m.pc_commit = m.commit;
     return more;
 }
 
@@ -652,6 +661,7 @@ __device__ __forceinline__ void initialise_peers(Member& m)
 {
     u64 next = m.last_idx + 1;
     m.pstate |= 1u;                         // every peer cell is overwritten: nothing to load
+    m.pipe_clean = 0;
     for (u32 s = 0; s < NMEM(*m.C); s++) {
         peer_nm_set<MM>(m, s, next, 0);
         peer_cs_set<MM>(m, s, 0);
@@ -921,6 +931,7 @@ __device__ __forceinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
                 nn = x > (i64)nm.y ? (u64)x : nm.y;
             }
             peer_nm_set<MM>(m, from, nn, mm);
+            m.pipe_clean = 0;                       // next_index may have moved back
             (void)make_pipelined_rpcs<MM>(m, false);
         }
         return RA_LEADER;

@@ -11,7 +11,7 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "csrc", "libra_engine.so")
+_SO = os.environ.get("RA_ENGINE_SO") or os.path.join(_HERE, "csrc", "libra_engine.so")
 _lib = None
 
 
