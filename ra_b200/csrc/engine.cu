@@ -75,188 +75,106 @@ struct StepSmem {
     u64 bars[WARPS][NST];
 };
 
-// the general path, out of line: rare in a flood, and keeping it out of the hot loop keeps the
-// loop small enough for the instruction cache.  The member travels by copy so that the hot
-// loop's copy stays in registers.
-template <int MM>
-__device__ __noinline__ void slow_event(Member* pm, const Rec* pe)
+// ---- the two kernels of a step ---------------------------------------------------------------
+// raft_step_kernel     every row, steady-state fast paths only.  A row whose next event is not
+//                      covered STALLS: it stops, saves its step context (128 B) to a compact list
+//                      and writes its state back as far as it got.
+// raft_general_kernel  one thread per stalled row (dense, so a rare event does not idle 31
+//                      other lanes): resumes at the stalled event with the general path
+//                      (process_event), runs the row's end-of-step.
+// Both run the same end-of-step code; together they evaluate every event exactly once, in order.
+
+struct StallCtx {                      // 8 x 16 bytes
+    u32 row, flags, rem_mbox, rem_loc;
+    u32 n_msgs, n_notes, status, sent_to;
+    u32 pn_type, pn_slot, w_n, role0;
+    u64 pn_a, pn_b;
+    u64 pn_c, w0a;
+    u64 w0b, w0c;
+    u64 w1a, w1b;
+    u64 w1c, _pad;
+};
+#define STALL_PENDING 1u               // the deferred pipeline pass has not run yet
+
+struct RowLoad { ulonglong2 tc, lg, lw, ap, sn, tk, fm; };
+
+__device__ __forceinline__ void member_init(Member& m, const Cols& C, u32 r, const RowLoad& L, u64 lrs, int cur, u64* sp)
 {
-    Member m = *pm;
-    process_event<MM>(m, *pe);
-    *pm = m;
-}
-
-template <int MM>
-__global__ void __launch_bounds__(CTA_T, MINB)
-raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    StepSmem<MM>& S = *reinterpret_cast<StepSmem<MM>*>(smem_raw);
-    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u32 wtile = blockIdx.x * WARPS + warp;                 // this warp's record tile
-    const u32 r = wtile * RT + lane;
-    const bool valid = r < C.rows;
-    u32 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
-
-    // ---- what does this row have to do? ---------------------------------------------------
-    ulonglong2 ap = make_ulonglong2(0, 0);
-    u64 cntw = 0; u32 nloc = 0;
-    if (valid) {
-        ap = C.ap[r];
-        nloc = C.loc_n[r];
-        if (C.routed) cntw = C.mbox_cnt[cur][r];
-    }
-    const bool fatal0 = MT_FATAL(ap.y) != 0;
-    const bool pending = valid && MT_PIPE_PEND(ap.y) != 0;
-    u32 my_mbox = 0, my_loc = 0;
-    if (valid && !fatal0) {
-        for (u32 s = 0; s < NMEM(C); s++) {
-            u32 c = (u32)(cntw >> (8 * s)) & 0xffu;
-            my_mbox |= ((1u << c) - 1u) << (RA_MBOX_DEPTH * s);
-        }
-        my_loc = (1u << nloc) - 1u;
-    }
-    const bool work = valid && (F.on || nloc || cntw || pending);
-    // everything below is per warp: no CTA-wide barrier anywhere in this kernel
-    u32 w_mbox = __reduce_or_sync(0xffffffffu, my_mbox), w_loc = __reduce_or_sync(0xffffffffu, my_loc);
-    if (!__any_sync(0xffffffffu, work)) return;                 // whole warp idle
-    u64* bars = &S.bars[warp][0];
-    if (lane == 0) {
-        for (int i = 0; i < NST; i++) mbar_init(&bars[i], 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-
-    Member m;
-    m.C = &C; m.row = r; m.slot = valid ? r / C.groups : 0; m.group = valid ? r - m.slot * C.groups : 0;
-    ulonglong2 tc = make_ulonglong2(0, 0), lg = tc, lw = tc, sn = tc, tk = tc, fm = tc, lr = tc;
-    if (work) {
-        tc = C.tc[r]; lg = C.lg[r]; lw = C.lw[r]; sn = C.sn[r]; tk = C.tk[r]; fm = C.fm[r];
-        const u32 nr = MT_NRUNS(ap.y);
-        if (nr) lr = C.run[(size_t)(nr - 1) * C.rows + r];
-    }
-    m.term = tc.x; m.commit = tc.y; m.last_idx = lg.x; m.last_term = lg.y;
-    m.lw_idx = lw.x; m.lw_term = lw.y; m.applied = ap.x; m.meta = ap.y;
-    m.snap_idx = sn.x; m.snap_term = sn.y; m.token = tk.x; m.token_ctr = tk.y;
-    m.first_idx = fm.x; m.macver = fm.y;
-    m.lrs = lr.x; m.lrs_ok = MT_NRUNS(ap.y) ? 1u : 0u;
-    m.n_msgs = 0; m.n_notes = 0; m.status = 0; m.fatal_code = 0; m.role0 = MT_ROLE(ap.y);
+    m.C = &C; m.row = r; m.slot = r / C.groups; m.group = r - m.slot * C.groups;
+    m.term = L.tc.x; m.commit = L.tc.y; m.last_idx = L.lg.x; m.last_term = L.lg.y;
+    m.lw_idx = L.lw.x; m.lw_term = L.lw.y; m.applied = L.ap.x; m.meta = L.ap.y;
+    m.snap_idx = L.sn.x; m.snap_term = L.sn.y; m.token = L.tk.x; m.token_ctr = L.tk.y;
+    m.first_idx = L.fm.x; m.macver = L.fm.y;
+    m.lrs = lrs; m.lrs_ok = MT_NRUNS(L.ap.y) ? 1u : 0u;
+    m.n_msgs = 0; m.n_notes = 0; m.status = 0; m.fatal_code = 0; m.role0 = MT_ROLE(L.ap.y);
     m.sent_to = 0; m.pn_type = RA_NOTE_NONE; m.pn_slot = 0; m.pn_a = m.pn_b = m.pn_c = 0;
     m.w_n = 0; m.w0a = m.w0b = m.w0c = m.w1a = m.w1b = m.w1c = 0;
     m.c_events = m.c_msgs = m.c_dropped = m.c_elections = 0; m.c_commits = m.c_applied = 0;
     m.nb = cur ^ 1;
-    m.sp = &S.peers[tid]; m.pstate = 0; m.pipe_clean = 0; m.pc_last = m.pc_commit = 0;
+    m.sp = sp; m.pstate = 0; m.pipe_clean = 0; m.pc_last = m.pc_commit = 0;
+}
 
-    const bool live = work && !fatal0;
+__device__ __forceinline__ void member_writeback(const Member& m, const Cols& C, u32 r, const RowLoad& L)
+{
+    if (m.term != L.tc.x || m.commit != L.tc.y) st2(&C.tc[r], m.term, m.commit);
+    if (m.last_idx != L.lg.x || m.last_term != L.lg.y) st2(&C.lg[r], m.last_idx, m.last_term);
+    if (m.lw_idx != L.lw.x || m.lw_term != L.lw.y) st2(&C.lw[r], m.lw_idx, m.lw_term);
+    if (m.applied != L.ap.x || m.meta != L.ap.y) st2(&C.ap[r], m.applied, m.meta);
+    if (m.token != L.tk.x || m.token_ctr != L.tk.y) st2(&C.tk[r], m.token, m.token_ctr);
+    if (m.first_idx != L.fm.x) st2(&C.fm[r], m.first_idx, m.macver);
+}
 
-    // ---- inputs: TMA stages this warp's record tiles through a ring of NST 2 KB slots, in ------
-    // evaluation order: deferred pipeline pass, mailbox planes by sender slot then depth, then
-    // the host-event planes.  A slot is refilled as soon as the warp has consumed it.
-    const bool do_pending = live && pending;
-    if (do_pending) MT_SET(m.meta, 24, 1, 0);
-    u64 todo = (u64)w_mbox | ((u64)w_loc << 32);                // planes still to consume
-    u64 toissue = todo;                                         // planes still to request
-    u32 n_issued = 0, n_done = 0;
-    if (lane == 0) {
-#pragma unroll 1
-        while (toissue && n_issued < NST) {
-            const u32 p = __ffsll((long long)toissue) - 1; toissue &= toissue - 1;
-            const ulonglong2* src = (p < 32) ? C.mbox[cur] + rec_word(C.tiles, p, wtile * RT, 0)
-                                             : C.loc + rec_word(C.tiles, p - 32, wtile * RT, 0);
-            mbar_expect_tx(&bars[n_issued], TILE_BYTES);
-            tma_load_tile(&S.stage[warp][n_issued][0], src, TILE_BYTES, &bars[n_issued]);
-            n_issued++;
-        }
+// end of a row's step: publish mailbox counts, STATUS note, output counts, flood host model
+template <int MM>
+__device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, int cur, const FloodArgs& F)
+{
+    u32 fatal = 0;
+    if (C.routed) {
+        for (u32 s = 0; s < NMEM(C); s++)
+            if (s != m.slot)
+                reinterpret_cast<u8*>(&C.mbox_cnt[cur ^ 1][(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
     }
-    // one evaluation site; the deferred pipeline pass rides in front as a pseudo plane
-    bool pend_round = __any_sync(0xffffffffu, do_pending);
-#pragma unroll 1
-    while (pend_round || todo) {
-        bool mine; u32 st = 0;
-        Rec e;
-        if (pend_round) {
-            mine = do_pending;
-            e = mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-        } else {
-            const u32 p = __ffsll((long long)todo) - 1; todo &= todo - 1;
-            st = n_done % NST;
-            mine = (p < 32) ? ((my_mbox >> p) & 1u) : ((my_loc >> (p - 32)) & 1u);
-            mbar_wait(&bars[st], (n_done / NST) & 1u);
-            const ulonglong2* sp = &S.stage[warp][st][0];
-            e.w0 = sp[lane]; e.w1 = sp[RT + lane]; e.w2 = sp[2 * RT + lane]; e.w3 = sp[3 * RT + lane];
-        }
-        if (mine) {
-            if (MT_FATAL(m.meta)) m.c_events++;
-            else if (C.pure || !fast_event<MM>(m, e)) { Member tmp = m; Rec te = e; slow_event<MM>(&tmp, &te); m = tmp; }
-        }
-        if (pend_round) { pend_round = false; continue; }
-        n_done++;
-        __syncwarp();                                           // every lane is done with slot st
-        if (lane == 0 && toissue) {
-            const u32 q = __ffsll((long long)toissue) - 1; toissue &= toissue - 1;
-            const ulonglong2* src = (q < 32) ? C.mbox[cur] + rec_word(C.tiles, q, wtile * RT, 0)
-                                             : C.loc + rec_word(C.tiles, q - 32, wtile * RT, 0);
-            fence_proxy_async();                                // slot st was read through the generic proxy
-            mbar_expect_tx(&bars[st], TILE_BYTES);
-            tma_load_tile(&S.stage[warp][st][0], src, TILE_BYTES, &bars[st]);
-        }
+    note_flush(m);
+    if (m.status) {
+        u64 ld = MT_LEADER(m.meta), vf = MT_VOTED(m.meta);
+        u64 b = (vf == SLOT_NONE ? 0xFFull : vf) | ((ld == SLOT_NONE ? 0xFFull : ld) << 8) |
+                ((u64)m.role0 << 16) | ((u64)MT_ROLE(m.meta) << 24);
+        note_store(m, m.n_notes, RA_NOTE_STATUS, m.slot, m.status, m.term, b, m.fatal_code);
+        m.n_notes++;
+        if (m.status & RA_ST_FATAL) fatal = 1;
     }
-
-    if (work) {
-        if (cntw && !fatal0) C.mbox_cnt[cur][r] = 0;
-        if (nloc) C.loc_n[r] = 0;
-        if (C.routed) {
-            for (u32 s = 0; s < NMEM(C); s++)
-                if (s != m.slot)
-                    reinterpret_cast<u8*>(&C.mbox_cnt[cur ^ 1][(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
-        }
-        peers_writeback<MM>(m);
-        // end of the row's step: STATUS note
-        note_flush(m);
-        if (m.status) {
-            u64 ld = MT_LEADER(m.meta), vf = MT_VOTED(m.meta);
-            u64 b = (vf == SLOT_NONE ? 0xFFull : vf) | ((ld == SLOT_NONE ? 0xFFull : ld) << 8) |
-                    ((u64)m.role0 << 16) | ((u64)MT_ROLE(m.meta) << 24);
-            note_store(m, m.n_notes, RA_NOTE_STATUS, m.slot, m.status, m.term, b, m.fatal_code);
-            m.n_notes++;
-            if (m.status & RA_ST_FATAL) k_fatal = 1;
-        }
-        C.out_n[r] = m.n_msgs | (m.n_notes << 16);
-        // flood: synthetic host (DESIGN.md "flood host model")
-        if (F.on && !MT_FATAL(m.meta)) {
-            u32 k = 0;
-            if (m.w_n == 2) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_WRITTEN, RA_NO_SLOT, 0, 0, 0, 0, m.w0c, m.w0a, m.w0b, 0, 0, 0)); k++; }
-            if (m.w_n >= 1) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_WRITTEN, RA_NO_SLOT, 0, 0, 0, 0, m.w1c, m.w1a, m.w1b, 0, 0, 0)); k++; }
-            const u32 role = MT_ROLE(m.meta);
-            if (role == RA_LEADER && F.cmds) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_COMMAND, RA_NO_SLOT, 0, F.cmds, 0, 0, 0, 0, 0, 0, 0, 0)); k++; }
-            u32 idle = MT_IDLE(m.meta);
-            if (role == RA_LEADER || (m.status & RA_ST_LEADER_MSG)) idle = 0;
-            else if (idle < 15) idle++;
-            bool fire = false;
-            if (role != RA_LEADER) {
-                if (F.permille) {
-                    u64 h = mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ ((u64)m.group * 0xD1B54A32D192ED03ull));
-                    if ((h % 1000) < F.permille && ((h / 1000) % NMEM(C)) == m.slot) fire = true;
-                }
-                if (idle >= 8) {                                // the hash only matters from 8 idle steps on
-                    u64 h2 = mix64(F.seed ^ ((u64)r * 0xA24BAED4963EE407ull) ^ F.step);
-                    if (idle >= 8 + (u32)(h2 % 8)) fire = true;
-                }
+    C.out_n[r] = m.n_msgs | (m.n_notes << 16);
+    // flood: synthetic host (DESIGN.md "flood host model")
+    if (F.on && !MT_FATAL(m.meta)) {
+        u32 k = 0;
+        if (m.w_n == 2) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_WRITTEN, RA_NO_SLOT, 0, 0, 0, 0, m.w0c, m.w0a, m.w0b, 0, 0, 0)); k++; }
+        if (m.w_n >= 1) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_WRITTEN, RA_NO_SLOT, 0, 0, 0, 0, m.w1c, m.w1a, m.w1b, 0, 0, 0)); k++; }
+        const u32 role = MT_ROLE(m.meta);
+        if (role == RA_LEADER && F.cmds) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_COMMAND, RA_NO_SLOT, 0, F.cmds, 0, 0, 0, 0, 0, 0, 0, 0)); k++; }
+        u32 idle = MT_IDLE(m.meta);
+        if (role == RA_LEADER || (m.status & RA_ST_LEADER_MSG)) idle = 0;
+        else if (idle < 15) idle++;
+        bool fire = false;
+        if (role != RA_LEADER) {
+            if (F.permille) {
+                u64 h = mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ ((u64)m.group * 0xD1B54A32D192ED03ull));
+                if ((h % 1000) < F.permille && ((h / 1000) % NMEM(C)) == m.slot) fire = true;
             }
-            if (fire) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_ELECTION_TIMEOUT, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)); k++; idle = 0; }
-            MT_SET(m.meta, 28, 4, idle);
-            C.loc_n[r] = k;
+            if (idle >= 8) {                                // the hash only matters from 8 idle steps on
+                u64 h2 = mix64(F.seed ^ ((u64)r * 0xA24BAED4963EE407ull) ^ F.step);
+                if (idle >= 8 + (u32)(h2 % 8)) fire = true;
+            }
         }
-        // write back what changed
-        if (m.term != tc.x || m.commit != tc.y) st2(&C.tc[r], m.term, m.commit);
-        if (m.last_idx != lg.x || m.last_term != lg.y) st2(&C.lg[r], m.last_idx, m.last_term);
-        if (m.lw_idx != lw.x || m.lw_term != lw.y) st2(&C.lw[r], m.lw_idx, m.lw_term);
-        if (m.applied != ap.x || m.meta != ap.y) st2(&C.ap[r], m.applied, m.meta);
-        if (m.token != tk.x || m.token_ctr != tk.y) st2(&C.tk[r], m.token, m.token_ctr);
-        if (m.first_idx != fm.x) st2(&C.fm[r], m.first_idx, m.macver);
-        k_events = m.c_events; k_commits = m.c_commits; k_applied = m.c_applied;
-        k_msgs = m.c_msgs; k_dropped = m.c_dropped; k_elect = m.c_elections;
+        if (fire) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_ELECTION_TIMEOUT, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)); k++; idle = 0; }
+        MT_SET(m.meta, 28, 4, idle);
+        C.loc_n[r] = k;
     }
+    return fatal;
+}
+
+__device__ __forceinline__ void flush_counters(const Cols& C, u32 lane, u32 k_events, u32 k_commits, u32 k_applied,
+                                               u32 k_msgs, u32 k_dropped, u32 k_elect, u32 k_fatal)
+{
     // per-launch device counters: one REDUX per counter, one atomic per warp and counter that moved
     if (__any_sync(0xffffffffu, (k_events | k_fatal) != 0)) {
         k_events = __reduce_add_sync(0xffffffffu, k_events); k_commits = __reduce_add_sync(0xffffffffu, k_commits);
@@ -272,6 +190,191 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             if (k_elect)   atomicAdd(&C.counters[5], (u64)k_elect);
             if (k_fatal)   atomicAdd(&C.counters[6], (u64)k_fatal);
         }
+    }
+}
+
+template <int MM>
+__global__ void __launch_bounds__(CTA_T, MINB)
+raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F,
+                 StallCtx* __restrict__ stall_list, u32* __restrict__ stall_count, u32* __restrict__ stall_count_next)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StepSmem<MM>& S = *reinterpret_cast<StepSmem<MM>*>(smem_raw);
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u32 wtile = blockIdx.x * WARPS + warp;                 // this warp's record tile
+    const u32 r = wtile * RT + lane;
+    const bool valid = r < C.rows;
+    u32 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
+    if (blockIdx.x == 0 && tid == 0) *stall_count_next = 0;    // the list of the step after this one
+
+    // ---- what does this row have to do? ---------------------------------------------------
+    RowLoad L;
+    L.ap = make_ulonglong2(0, 0);
+    u64 cntw = 0; u32 nloc = 0;
+    if (valid) {
+        L.ap = C.ap[r];
+        nloc = C.loc_n[r];
+        if (C.routed) cntw = C.mbox_cnt[cur][r];
+    }
+    const bool fatal0 = MT_FATAL(L.ap.y) != 0;
+    const bool pending = valid && MT_PIPE_PEND(L.ap.y) != 0;
+    u32 my_mbox = 0, my_loc = 0;
+    if (valid && !fatal0) {
+        for (u32 s = 0; s < NMEM(C); s++) {
+            u32 c = (u32)(cntw >> (8 * s)) & 0xffu;
+            my_mbox |= ((1u << c) - 1u) << (RA_MBOX_DEPTH * s);
+        }
+        my_loc = (1u << nloc) - 1u;
+    }
+    const bool work = valid && (F.on || nloc || cntw || pending);
+    // everything below is per warp: no CTA-wide barrier anywhere in this kernel
+    const u32 w_mbox = __reduce_or_sync(0xffffffffu, my_mbox), w_loc = __reduce_or_sync(0xffffffffu, my_loc);
+    if (!__any_sync(0xffffffffu, work)) return;                 // whole warp idle
+    u64* bars = &S.bars[warp][0];
+    if (lane == 0) {
+        for (int i = 0; i < NST; i++) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    ulonglong2 lr = make_ulonglong2(0, 0);
+    L.tc = L.lg = L.lw = L.sn = L.tk = L.fm = lr;
+    if (work) {
+        L.tc = C.tc[r]; L.lg = C.lg[r]; L.lw = C.lw[r]; L.sn = C.sn[r]; L.tk = C.tk[r]; L.fm = C.fm[r];
+        const u32 nr = MT_NRUNS(L.ap.y);
+        if (nr) lr = C.run[(size_t)(nr - 1) * C.rows + r];
+    }
+    Member m;
+    member_init(m, C, valid ? r : 0, L, lr.x, cur, &S.peers[tid]);
+    m.row = r;
+
+    const bool live = work && !fatal0;
+    bool stalled = false;
+    u32 stall_flags = 0;
+
+    // ---- inputs: TMA stages this warp's record tiles through a ring of NST 2 KB slots, in ------
+    // evaluation order: deferred pipeline pass, mailbox planes by sender slot then depth, then
+    // the host-event planes.  A slot is refilled as soon as the warp has consumed it.
+    if (live && pending) {                                       // pipeline_rpcs is not a fast path
+        stalled = true; stall_flags = STALL_PENDING;
+    }
+    u64 todo = (u64)w_mbox | ((u64)w_loc << 32);                // planes still to consume
+    u64 toissue = todo;                                         // planes still to request
+    u32 n_issued = 0, n_done = 0;
+    if (lane == 0) {
+#pragma unroll 1
+        while (toissue && n_issued < NST) {
+            const u32 p = __ffsll((long long)toissue) - 1; toissue &= toissue - 1;
+            const ulonglong2* src = (p < 32) ? C.mbox[cur] + rec_word(C.tiles, p, wtile * RT, 0)
+                                             : C.loc + rec_word(C.tiles, p - 32, wtile * RT, 0);
+            mbar_expect_tx(&bars[n_issued], TILE_BYTES);
+            tma_load_tile(&S.stage[warp][n_issued][0], src, TILE_BYTES, &bars[n_issued]);
+            n_issued++;
+        }
+    }
+    u32 rem_mbox = my_mbox, rem_loc = my_loc;                   // this row's planes not yet evaluated
+#pragma unroll 1
+    while (todo) {
+        const u32 p = __ffsll((long long)todo) - 1; todo &= todo - 1;
+        const u32 st = n_done % NST;
+        const bool mine = !stalled && ((p < 32) ? ((my_mbox >> p) & 1u) : ((my_loc >> (p - 32)) & 1u));
+        mbar_wait(&bars[st], (n_done / NST) & 1u);
+        if (mine) {
+            const ulonglong2* sp = &S.stage[warp][st][0];
+            Rec e; e.w0 = sp[lane]; e.w1 = sp[RT + lane]; e.w2 = sp[2 * RT + lane]; e.w3 = sp[3 * RT + lane];
+            if (MT_FATAL(m.meta)) m.c_events++;
+            else if (C.pure || !fast_event<MM>(m, e)) stalled = true;
+            if (!stalled) { if (p < 32) rem_mbox &= ~(1u << p); else rem_loc &= ~(1u << (p - 32)); }
+        }
+        n_done++;
+        __syncwarp();                                           // every lane is done with slot st
+        if (lane == 0 && toissue) {
+            const u32 q = __ffsll((long long)toissue) - 1; toissue &= toissue - 1;
+            const ulonglong2* src = (q < 32) ? C.mbox[cur] + rec_word(C.tiles, q, wtile * RT, 0)
+                                             : C.loc + rec_word(C.tiles, q - 32, wtile * RT, 0);
+            fence_proxy_async();                                // slot st was read through the generic proxy
+            mbar_expect_tx(&bars[st], TILE_BYTES);
+            tma_load_tile(&S.stage[warp][st][0], src, TILE_BYTES, &bars[st]);
+        }
+    }
+
+    if (work) {
+        if (cntw && !fatal0) C.mbox_cnt[cur][r] = 0;
+        if (nloc) C.loc_n[r] = 0;
+        peers_writeback<MM>(m);
+        if (!stalled) k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
+        member_writeback(m, C, r, L);
+        k_events = m.c_events; k_commits = m.c_commits; k_applied = m.c_applied;
+        k_msgs = m.c_msgs; k_dropped = m.c_dropped; k_elect = m.c_elections;
+    }
+    // stalled rows: hand the rest of the step to raft_general_kernel
+    const u32 sm = __ballot_sync(0xffffffffu, stalled);
+    if (sm) {
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(stall_count, (u32)__popc(sm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (stalled) {
+            ulonglong2* q = reinterpret_cast<ulonglong2*>(&stall_list[base + __popc(sm & ((1u << lane) - 1u))]);
+            q[0] = make_ulonglong2((u64)r | ((u64)stall_flags << 32), (u64)rem_mbox | ((u64)rem_loc << 32));
+            q[1] = make_ulonglong2((u64)m.n_msgs | ((u64)m.n_notes << 32), (u64)m.status | ((u64)m.sent_to << 32));
+            q[2] = make_ulonglong2((u64)m.pn_type | ((u64)m.pn_slot << 32), (u64)m.w_n | ((u64)m.role0 << 32));
+            q[3] = make_ulonglong2(m.pn_a, m.pn_b);
+            q[4] = make_ulonglong2(m.pn_c, m.w0a);
+            q[5] = make_ulonglong2(m.w0b, m.w0c);
+            q[6] = make_ulonglong2(m.w1a, m.w1b);
+            q[7] = make_ulonglong2(m.w1c, 0);
+        }
+    }
+    flush_counters(C, lane, k_events, k_commits, k_applied, k_msgs, k_dropped, k_elect, k_fatal);
+}
+
+// general path for the stalled rows of this step (one thread per list entry)
+__global__ void __launch_bounds__(CTA_T)
+raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F,
+                    const StallCtx* __restrict__ stall_list, const u32* __restrict__ stall_count)
+{
+    constexpr int MM = 0;
+    __shared__ u64 s_peers[3 * RA_MAX_MEMBERS * CTA_T];
+    const u32 tid = threadIdx.x, lane = tid & 31u;
+    const u32 n = *stall_count;
+    for (u32 base = blockIdx.x * CTA_T; base < n; base += gridDim.x * CTA_T) {
+        const u32 i = base + tid;
+        u32 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
+        if (i < n) {
+            const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&stall_list[i]);
+            const ulonglong2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
+            const u32 r = (u32)q0.x, flags = (u32)(q0.x >> 32);
+            u32 rem_mbox = (u32)q0.y, rem_loc = (u32)(q0.y >> 32);
+            RowLoad L;
+            L.tc = C.tc[r]; L.lg = C.lg[r]; L.lw = C.lw[r]; L.ap = C.ap[r]; L.sn = C.sn[r]; L.tk = C.tk[r]; L.fm = C.fm[r];
+            Member m;
+            member_init(m, C, r, L, 0, cur, &s_peers[tid]);
+            m.lrs_ok = 0;
+            m.n_msgs = (u32)q1.x; m.n_notes = (u32)(q1.x >> 32); m.status = (u32)q1.y; m.sent_to = (u32)(q1.y >> 32);
+            m.pn_type = (u32)q2.x; m.pn_slot = (u32)(q2.x >> 32); m.w_n = (u32)q2.y; m.role0 = (u32)(q2.y >> 32);
+            m.pn_a = q3.x; m.pn_b = q3.y; m.pn_c = q4.x; m.w0a = q4.y; m.w0b = q5.x; m.w0c = q5.y;
+            m.w1a = q6.x; m.w1b = q6.y; m.w1c = q7.x;
+            if (flags & STALL_PENDING) {
+                MT_SET(m.meta, 24, 1, 0);
+                process_event<MM>(m, mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+            }
+#pragma unroll 1
+            while (rem_mbox) {
+                const u32 p = __ffs(rem_mbox) - 1; rem_mbox &= rem_mbox - 1;
+                process_event<MM>(m, ld_rec_tiled(C.mbox[cur], C.tiles, p, r));
+            }
+#pragma unroll 1
+            while (rem_loc) {
+                const u32 p = __ffs(rem_loc) - 1; rem_loc &= rem_loc - 1;
+                process_event<MM>(m, ld_rec_tiled(C.loc, C.tiles, p, r));
+            }
+            peers_writeback<MM>(m);
+            k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
+            member_writeback(m, C, r, L);
+            k_events = m.c_events; k_commits = m.c_commits; k_applied = m.c_applied;
+            k_msgs = m.c_msgs; k_dropped = m.c_dropped; k_elect = m.c_elections;
+        }
+        flush_counters(C, lane, k_events, k_commits, k_applied, k_msgs, k_dropped, k_elect, k_fatal);
     }
 }
 
@@ -439,8 +542,10 @@ struct ra_engine {
     ra_note* d_notes; size_t d_notes_cap;
     u64 *d_packed, *d_offs; void* d_scan_tmp; size_t scan_tmp_bytes;
     u32* d_err;
+    StallCtx* d_stall; u32* d_stall_cnt;      // d_stall_cnt[2]: alternating per step
     ra_row_state* d_rows; size_t d_rows_cap;
     float last_ms; u32 last_launches;
+    u32 general_grid;
     char err[256];
 };
 
@@ -500,6 +605,7 @@ extern "C" int ra_engine_reset_empty(ra_engine* e)
     reset_empty_kernel<<<nblocks(e->C.rows, 256), 256, 0, e->stream>>>(e->C);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(e->C.counters, 0, 8 * sizeof(u64), e->stream));
+    CK(cudaMemsetAsync(e->d_stall_cnt, 0, 4 * sizeof(u32), e->stream));
     e->cur = 0; e->step_no = 0; e->steps = 0;
     CK(cudaStreamSynchronize(e->stream));
     return RA_OK;
@@ -542,6 +648,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
             DA(C.omsg, (size_t)RA_MSG_CAP * R);
         }
         DA(e->d_packed, R + 1); DA(e->d_offs, R + 1); DA(e->d_err, 4);
+        DA(e->d_stall, R); DA(e->d_stall_cnt, 4);
 #undef DA
         e->scan_tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp_bytes, e->d_packed, e->d_offs, (int)(R + 1), e->stream);
@@ -550,6 +657,11 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
     if ((ce = cudaFuncSetAttribute(raft_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<0>))) != cudaSuccess ||
         (ce = cudaFuncSetAttribute(raft_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<5>))) != cudaSuccess) {
         rc = fail(e, ce, "cudaFuncSetAttribute"); goto bad;
+    }
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        e->general_grid = (u32)sms * 2;
     }
     if ((rc = ra_engine_reset_empty(e)) != RA_OK) goto bad;
     *out = e;
@@ -604,12 +716,17 @@ extern "C" int ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n)
 
 static int launch_step(ra_engine* e, const FloodArgs& F)
 {
+    const u32 grid = (e->C.tiles + WARPS - 1) / WARPS;
+    u32* cnt = e->d_stall_cnt + (e->steps & 1), *cnt_next = e->d_stall_cnt + ((e->steps + 1) & 1);
     switch (e->C.members) {
-    case 5:  raft_step_kernel<5><<<(e->C.tiles + WARPS - 1) / WARPS, CTA_T, sizeof(StepSmem<5>), e->stream>>>(e->C, e->cur, F); break;
-    default: raft_step_kernel<0><<<(e->C.tiles + WARPS - 1) / WARPS, CTA_T, sizeof(StepSmem<0>), e->stream>>>(e->C, e->cur, F); break;
+    case 5:  raft_step_kernel<5><<<grid, CTA_T, sizeof(StepSmem<5>), e->stream>>>(e->C, e->cur, F, e->d_stall, cnt, cnt_next); break;
+    default: raft_step_kernel<0><<<grid, CTA_T, sizeof(StepSmem<0>), e->stream>>>(e->C, e->cur, F, e->d_stall, cnt, cnt_next); break;
     }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(e, ce, "raft_step_kernel");
+    raft_general_kernel<<<e->general_grid, CTA_T, 0, e->stream>>>(e->C, e->cur, F, e->d_stall, cnt);
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) return fail(e, ce, "raft_general_kernel");
     if (e->C.routed) e->cur ^= 1;
     e->steps++;
     return RA_OK;
@@ -679,7 +796,7 @@ extern "C" int ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per
     }
     CK(cudaEventRecord(e->ev1, e->stream));
     e->step_no += n_steps;
-    e->last_launches = n_steps;
+    e->last_launches = 2 * n_steps;
     return RA_OK;
 }
 
