@@ -285,6 +285,9 @@ int  ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per_step,
                      uint32_t election_permille, uint64_t seed);
 int  ra_engine_sync(ra_engine* e);
 int  ra_engine_counters(ra_engine* e, ra_counters* out);     /* syncs */
+/* diagnostics: out[role * 16 + event_type] = events that were not covered by a steady-state fast
+   path and went through the general kernel (8 roles x 16 types = 128 counters) */
+int  ra_engine_stall_histogram(ra_engine* e, uint64_t* out128);
 /* elapsed device time (ms) of the raft_step kernel over the last flood call, CUDA events
    on the engine's stream, and its launch count */
 int  ra_engine_last_kernel_ms(ra_engine* e, float* ms, uint32_t* launches);

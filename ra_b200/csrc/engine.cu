@@ -19,10 +19,10 @@
 // the hot kernel
 // ------------------------------------------------------------------------------------------
 #ifndef NST
-#define NST 6                               // shared-memory stages per warp: NST x 2 KB record tiles in flight
+#define NST 4                               // shared-memory stages per warp: NST x 2 KB record tiles in flight
 #endif
 #ifndef MINB
-#define MINB 3                              // CTAs per SM the register allocation is held to
+#define MINB 4                              // CTAs per SM the register allocation is held to
 #endif
 #define TILE_BYTES (RT * 64)
 #define WARPS (CTA_T / 32)
@@ -283,7 +283,10 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             const ulonglong2* sp = &S.stage[warp][st][0];
             Rec e; e.w0 = sp[lane]; e.w1 = sp[RT + lane]; e.w2 = sp[2 * RT + lane]; e.w3 = sp[3 * RT + lane];
             if (MT_FATAL(m.meta)) m.c_events++;
-            else if (C.pure || !fast_event<MM>(m, e)) stalled = true;
+            else if (C.pure || !fast_event<MM>(m, e)) {
+                stalled = true;
+                atomicAdd(&C.counters[8 + (m_role(m) & 7u) * 16 + (R_type(e) & 15u)], 1ull);   // diagnostics
+            }
             if (!stalled) { if (p < 32) rem_mbox &= ~(1u << p); else rem_loc &= ~(1u << (p - 32)); }
         }
         n_done++;
@@ -361,12 +364,16 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
 #pragma unroll 1
             while (rem_mbox) {
                 const u32 p = __ffs(rem_mbox) - 1; rem_mbox &= rem_mbox - 1;
-                process_event<MM>(m, ld_rec_tiled(C.mbox[cur], C.tiles, p, r));
+                const Rec e = ld_rec_tiled(C.mbox[cur], C.tiles, p, r);
+                if (MT_FATAL(m.meta)) m.c_events++;
+                else if (C.pure || !fast_event<MM>(m, e)) process_event<MM>(m, e);
             }
 #pragma unroll 1
             while (rem_loc) {
                 const u32 p = __ffs(rem_loc) - 1; rem_loc &= rem_loc - 1;
-                process_event<MM>(m, ld_rec_tiled(C.loc, C.tiles, p, r));
+                const Rec e = ld_rec_tiled(C.loc, C.tiles, p, r);
+                if (MT_FATAL(m.meta)) m.c_events++;
+                else if (C.pure || !fast_event<MM>(m, e)) process_event<MM>(m, e);
             }
             peers_writeback<MM>(m);
             k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
@@ -604,7 +611,7 @@ extern "C" int ra_engine_reset_empty(ra_engine* e)
     CK(cudaSetDevice(e->cfg.device));
     reset_empty_kernel<<<nblocks(e->C.rows, 256), 256, 0, e->stream>>>(e->C);
     CK(cudaGetLastError());
-    CK(cudaMemsetAsync(e->C.counters, 0, 8 * sizeof(u64), e->stream));
+    CK(cudaMemsetAsync(e->C.counters, 0, (8 + 8 * 16) * sizeof(u64), e->stream));
     CK(cudaMemsetAsync(e->d_stall_cnt, 0, 4 * sizeof(u32), e->stream));
     e->cur = 0; e->step_no = 0; e->steps = 0;
     CK(cudaStreamSynchronize(e->stream));
@@ -639,7 +646,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         C.tiles = (u32)((R + RT - 1) / RT);
         const size_t PW = (size_t)C.tiles * 4 * RT;             // 16-byte words per tiled plane
         DA(C.loc, (size_t)RA_LOCAL_CAP * PW); DA(C.loc_n, R);
-        DA(C.onote, (size_t)RA_NOTE_CAP * R); DA(C.out_n, R); DA(C.counters, 8);
+        DA(C.onote, (size_t)RA_NOTE_CAP * R); DA(C.out_n, R); DA(C.counters, 8 + 8 * 16);
         if (C.routed) {
             for (int b = 0; b < 2; b++) { DA(C.mbox[b], M * RA_MBOX_DEPTH * PW); DA(C.mbox_cnt[b], R); }
             DA(C.omsg, (size_t)RA_MSG_CAP * (C.pure ? R : 1));
@@ -797,6 +804,15 @@ extern "C" int ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per
     CK(cudaEventRecord(e->ev1, e->stream));
     e->step_no += n_steps;
     e->last_launches = 2 * n_steps;
+    return RA_OK;
+}
+
+extern "C" int ra_engine_stall_histogram(ra_engine* e, uint64_t* out128)
+{
+    if (!e || !out128) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(out128, e->C.counters + 8, 128 * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     return RA_OK;
 }
 

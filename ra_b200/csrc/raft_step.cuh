@@ -84,7 +84,7 @@ struct Cols {
     ra_event* omsg;     // [k][rows] outgoing RPC records (non-routed)
     ra_note*  onote;    // [k][rows]
     u32*      out_n;    // [rows] msgs | notes << 16
-    u64*      counters; // ra_counters as 8 x u64
+    u64*      counters; // ra_counters as 8 x u64, then [8 + role*16 + type]: events that left the fast kernel
     u32 rows, groups, members;
     u32 max_pipeline, max_batch;
     u32 routed, pure;
@@ -1248,10 +1248,35 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
             if (changed && leader != SLOT_NONE) emit_msg<MM>(m, leader, aer_reply(m, m.term, true));
             return true;
         }
+        if (type == RA_EV_PRE_VOTE) {                                  // :1459-1466
+            m.c_events++;
+            if (MT_MEMBERSHIP(m.meta) == RA_VOTER) (void)process_pre_vote<MM>(m, RA_FOLLOWER, e);
+            return true;
+        }
+        if (type == RA_EV_PRE_VOTE_RES || type == RA_EV_REQUEST_VOTE_RES) {   // :1593-1598: ignored
+            m.c_events++;
+            return true;
+        }
+        if (type == RA_EV_ELECTION_TIMEOUT) {
+            // :1603-1610 -> call_for_election(pre_vote) :2873-2897, then the queued vote for self
+            // (handle_pre_vote :1212-1229): one vote, which is not yet a quorum
+            if (MT_MEMBERSHIP(m.meta) != RA_VOTER || required_quorum<MM>(m) == 1 || m.C->pure) return false;
+            m.c_events++;
+            NextQ nq; nq.codes = 0; nq.n = 0;
+            (void)call_for_election<MM>(m, RA_PRE_VOTE, nq);
+            MT_SET(m.meta, 0, 3, RA_PRE_VOTE);
+            m.status |= RA_ST_ROLE_CHANGED;
+            MT_SET(m.meta, 15, 4, 1);
+            return true;
+        }
         return false;
     }
     if (role == RA_LEADER) {
         bool tail = false;
+        if (type == RA_EV_PRE_VOTE_RES || type == RA_EV_REQUEST_VOTE_RES) {   // :958-963: ignored
+            m.c_events++;
+            return true;
+        }
         if (type == RA_EV_COMMAND) {                                   // :644-729
             const u64 n = R_n(e);
             if (n == 0 || !nonempty) return false;

@@ -53,7 +53,7 @@ EXPORTS = ["ra_engine_create", "ra_engine_destroy", "ra_engine_load_rows", "ra_e
            "ra_engine_read_rows", "ra_engine_step", "ra_engine_flood", "ra_engine_sync",
            "ra_engine_counters", "ra_engine_last_kernel_ms", "ra_engine_strerror",
            "ra_engine_last_cuda_error", "ra_engine_get_cfg", "ra_engine_alloc_host",
-           "ra_engine_free_host"]
+           "ra_engine_free_host", "ra_engine_stall_histogram"]
 HOSTSIM_EXPORTS = ["ra_hostsim_create", "ra_hostsim_destroy", "ra_hostsim_run", "ra_hostsim_stats"]
 
 
@@ -86,6 +86,15 @@ class Engine(abi.Backend):
 
     def sync(self) -> None:
         self._check(lib().ra_engine_sync(self._h), "sync")
+
+    def stall_histogram(self) -> dict:
+        """{(role, event_type): count} of events that took the general kernel."""
+        arr = (C.c_uint64 * 128)()
+        f = lib().ra_engine_stall_histogram
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        self._check(f(self._h, arr), "stall_histogram")
+        return {(i // 16, i % 16): int(arr[i]) for i in range(128) if arr[i]}
 
     def last_kernel_ms(self):
         ms = C.c_float(0)

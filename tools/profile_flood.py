@@ -20,3 +20,11 @@ e.step([abi.ev_simple(e.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(a.
 e.flood(a.settle, 1, a.permille, seed=0xA00)
 e.flood(a.steps, 1, a.permille, seed=0xA00)
 print(e.counters(), e.last_kernel_ms())
+names = ["none", "AER", "AER_REPLY", "REQ_VOTE", "REQ_VOTE_RES", "PRE_VOTE", "PRE_VOTE_RES", "WRITTEN", "COMMAND",
+         "ELECTION_TMO", "AWAIT_TMO", "PIPELINE", "TICK"]
+roles = ["follower", "candidate", "pre_vote", "leader", "await_condition"]
+h = e.stall_histogram()
+tot = sum(h.values())
+print("events that left the fast kernel: %d of %d (%.2f%%)" % (tot, e.counters()["events"], 100.0 * tot / max(1, e.counters()["events"])))
+for (ro, ty), v in sorted(h.items(), key=lambda kv: -kv[1]):
+    print("  %-16s %-14s %10d" % (roles[ro] if ro < 5 else ro, names[ty] if ty < 13 else ty, v))
