@@ -1208,8 +1208,18 @@ template <int MM>
 __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
 {
     const u32 type = R_type(e);
-    const u32 role = m_role(m);
+    u32 role = m_role(m);
     const bool nonempty = m_nruns(m) != 0;
+    if (role == RA_PRE_VOTE && type == RA_EV_AER && R_term(e) >= m.term && !m.C->pure) {
+        // handle_pre_vote(#append_entries_rpc{}) :1175-1180: back to follower, the rpc is
+        // re-queued ({next_event, Msg}) and handled as a follower right away
+        update_term(m, R_term(e));
+        MT_SET(m.meta, 15, 4, 0);
+        MT_SET(m.meta, 0, 3, RA_FOLLOWER);
+        m.status |= RA_ST_ROLE_CHANGED;
+        m.meta &= ~(0xFFFFFFull << 32);                            // become/3 :2166-2175
+        role = RA_FOLLOWER;
+    }
     if (role == RA_FOLLOWER) {
         if (type == RA_EV_AER) {
             // handle_follower(#append_entries_rpc{}) :1266-1371, prev entry = our last entry
@@ -1275,6 +1285,12 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
         bool tail = false;
         if (type == RA_EV_PRE_VOTE_RES || type == RA_EV_REQUEST_VOTE_RES) {   // :958-963: ignored
             m.c_events++;
+            return true;
+        }
+        if (type == RA_EV_PRE_VOTE) {                                  // :952-957 enforce leadership
+            if (R_term(e) > m.term) return false;
+            m.c_events++;
+            make_rpcs<MM>(m, true);
             return true;
         }
         if (type == RA_EV_COMMAND) {                                   // :644-729
