@@ -221,6 +221,12 @@ typedef struct ra_engine_cfg {
                                      shown to the host.  0: every RPC record is returned. */
     uint32_t pure;                /* 1: do not chase {next_event,_}; return it as a record
                                      (the shape ra_server_SUITE asserts on)               */
+    uint32_t n_shards;            /* 0 or 1: every member of a group lives in this engine.  N > 1 (needs
+                                     route_on_device): member (group g, slot s) lives in the engine with
+                                     shard == (g + s) mod N, at local group index g div N; n_groups is then
+                                     the LOCAL group count per slot.  RPC records for other shards go to the
+                                     outbox (ra_engine_set_outbox) and come back through ra_engine_deliver */
+    uint32_t shard;
     uint32_t _reserved;
 } ra_engine_cfg;
 
@@ -291,6 +297,19 @@ int  ra_engine_stall_histogram(ra_engine* e, uint64_t* out128);
 /* elapsed device time (ms) of the raft_step kernel over the last flood call, CUDA events
    on the engine's stream, and its launch count */
 int  ra_engine_last_kernel_ms(ra_engine* e, float* ms, uint32_t* launches);
+
+/*
+ * Cross-shard transport (n_shards > 1).  The caller owns the exchange (NCCL all-to-all in
+ * ra_b200/sharded.py): `outbox` is n_shards buckets of `cap` 64-byte records, bucket d holds the
+ * records for shard d of the current step, counts[d] their number (both DEVICE pointers, reset by
+ * the engine before every step).  ra_engine_deliver scatters what other shards sent into this
+ * engine's mailboxes for the next step: bucket b = records from shard b, counts[b] of them.
+ * ra_engine_set_stream makes the engine enqueue on the caller's CUDA stream (e.g. the one NCCL
+ * collectives are ordered on).
+ */
+int  ra_engine_set_stream(ra_engine* e, void* cuda_stream);
+int  ra_engine_set_outbox(ra_engine* e, void* outbox, uint32_t* counts, uint32_t cap);
+int  ra_engine_deliver(ra_engine* e, const void* inbox, const uint32_t* counts, uint32_t cap);
 
 /*
  * The same flood driven from the HOST through ra_engine_step (host buffers, H2D of the

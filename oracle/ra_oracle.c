@@ -1303,6 +1303,7 @@ int ra_oracle_create(const ra_engine_cfg *cfg, ra_oracle **out)
 {
     if (!cfg || !out || cfg->n_members < 1 || cfg->n_members > RA_MAX_MEMBERS || cfg->n_groups == 0)
         return RA_E_INVAL;
+    if (cfg->n_shards > 1) return RA_E_INVAL;      /* the oracle is the unsharded truth */
     ra_oracle *o = (ra_oracle *)calloc(1, sizeof *o);
     if (!o) return RA_E_NOMEM;
     o->cfg = *cfg;

@@ -134,7 +134,7 @@ class RaEngineCfg(C.Structure):
     _fields_ = [("n_groups", C.c_uint32), ("n_members", C.c_uint32),
                 ("max_pipeline_count", C.c_uint32), ("max_aer_batch", C.c_uint32),
                 ("device", C.c_int32), ("route_on_device", C.c_uint32), ("pure", C.c_uint32),
-                ("_reserved", C.c_uint32)]
+                ("n_shards", C.c_uint32), ("shard", C.c_uint32), ("_reserved", C.c_uint32)]
 
 
 class RaCounters(C.Structure):
@@ -208,14 +208,14 @@ class Backend:
 
     def __init__(self, lib: C.CDLL, prefix: str, n_groups: int, n_members: int, *, device: int = 0,
                  route_on_device: bool = False, pure: bool = False, max_pipeline_count: int = 4096,
-                 max_aer_batch: int = 128):
+                 max_aer_batch: int = 128, n_shards: int = 1, shard: int = 0):
         self._lib = lib
         self._p = prefix
         self.n_groups = n_groups
         self.n_members = n_members
         self.n_rows = n_groups * n_members
         self.cfg = RaEngineCfg(n_groups, n_members, max_pipeline_count, max_aer_batch, device,
-                               1 if route_on_device else 0, 1 if pure else 0, 0)
+                               1 if route_on_device else 0, 1 if pure else 0, n_shards, shard, 0)
         self._h = C.c_void_p()
         f = self._fn("create")
         f.restype = C.c_int
@@ -281,10 +281,13 @@ class Backend:
         n = len(events)
         ev = (RaEvent * max(n, 1))(*events)
         if msgs_cap is None:
-            msgs_cap = (self.n_rows if self.cfg.route_on_device else max(n, 1)) * RA_MSG_CAP + RA_MSG_CAP * 64
-            msgs_cap = min(msgs_cap, self.n_rows * RA_MSG_CAP)
+            if self.cfg.route_on_device and not self.cfg.pure:
+                msgs_cap = 1024                       # routed: RPC records never reach the host
+            else:
+                msgs_cap = min(max(n, 1) * RA_MSG_CAP + RA_MSG_CAP * 64, self.n_rows * RA_MSG_CAP)
         if notes_cap is None:
-            notes_cap = self.n_rows * RA_NOTE_CAP
+            touched = self.n_rows if self.cfg.route_on_device else min(self.n_rows, max(n, 1) + 64)
+            notes_cap = touched * RA_NOTE_CAP
         msgs = (RaEvent * msgs_cap)()
         notes = (RaNote * notes_cap)()
         nm = C.c_size_t(0)

@@ -130,9 +130,12 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
 {
     u32 fatal = 0;
     if (C.routed) {
-        for (u32 s = 0; s < NMEM(C); s++)
-            if (s != m.slot)
-                reinterpret_cast<u8*>(&C.mbox_cnt[cur ^ 1][(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
+        for (u32 s = 0; s < NMEM(C); s++) {
+            if (s == m.slot) continue;
+            // a remote member's count is set when its records are delivered (deliver_kernel)
+            if (C.n_shards > 1 && (C.shard + s + 8u * C.n_shards - m.slot) % C.n_shards != C.shard) continue;
+            reinterpret_cast<u8*>(&C.mbox_cnt[cur ^ 1][(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
+        }
     }
     note_flush(m);
     if (m.status) {
@@ -156,12 +159,18 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
         else if (idle < 15) idle++;
         bool fire = false;
         if (role != RA_LEADER) {
+            // the model is keyed by GLOBAL group / row ids so that a sharded run equals the unsharded one
+            u64 gg = m.group, gr = r;
+            if (C.n_shards > 1) {
+                gg = (u64)C.n_shards * m.group + (C.shard + 8u * C.n_shards - m.slot) % C.n_shards;
+                gr = (u64)m.slot * C.groups * C.n_shards + gg;
+            }
             if (F.permille) {
-                u64 h = mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ ((u64)m.group * 0xD1B54A32D192ED03ull));
+                u64 h = mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ (gg * 0xD1B54A32D192ED03ull));
                 if ((h % 1000) < F.permille && ((h / 1000) % NMEM(C)) == m.slot) fire = true;
             }
             if (idle >= 8) {                                // the hash only matters from 8 idle steps on
-                u64 h2 = mix64(F.seed ^ ((u64)r * 0xA24BAED4963EE407ull) ^ F.step);
+                u64 h2 = mix64(F.seed ^ (gr * 0xA24BAED4963EE407ull) ^ F.step);
                 if (idle >= 8 + (u32)(h2 % 8)) fire = true;
             }
         }
@@ -498,6 +507,32 @@ __global__ void ingest_kernel(const Cols C, const ra_event* ev, u32 n, u32* err)
     for (u32 k = 0; k < len; k++) st_rec_tiled(C.loc, C.tiles, k, row, ld_rec(&ev[i + k]));
 }
 
+// records that other shards sent to members of this engine -> mailbox planes of the next step.
+// The slot is fixed by the record itself (sender slot, k-th record of that sender for this row),
+// the receiver's count byte becomes max(k + 1).
+__global__ void deliver_kernel(const Cols C, const int buf, const ra_event* inbox, const u32* counts, u32 cap)
+{
+    const u32 b = blockIdx.y;
+    const u32 n = counts[b] < cap ? counts[b] : cap;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Rec r = ld_rec(&inbox[(size_t)b * cap + i]);
+        const u32 row = R_row(r), from = R_from(r), k = (u32)(r.w0.y >> 32);
+        if (row >= C.rows || from >= C.members || k >= RA_MBOX_DEPTH) continue;
+        st_rec_tiled(C.mbox[buf], C.tiles, from * RA_MBOX_DEPTH + k, row, r);
+        // byte `from` of the row's count word := max(old, k + 1)
+        u32* w = reinterpret_cast<u32*>(&C.mbox_cnt[buf][row]) + (from >> 2);
+        const u32 sh = 8u * (from & 3u);
+        u32 old = *w;
+        for (;;) {
+            if (((old >> sh) & 0xffu) >= k + 1) break;
+            const u32 upd = (old & ~(0xffu << sh)) | ((k + 1) << sh);
+            const u32 seen = atomicCAS(w, old, upd);
+            if (seen == old) break;
+            old = seen;
+        }
+    }
+}
+
 __global__ void clear_loc_kernel(const Cols C)
 {
     const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -538,7 +573,7 @@ __global__ void gather_kernel(const Cols C, const u64* offs, ra_event* msgs, u64
 struct ra_engine {
     ra_engine_cfg cfg;
     Cols C;
-    cudaStream_t stream;
+    cudaStream_t stream; int own_stream;
     cudaEvent_t ev0, ev1;
     int cur;
     u64 step_no, steps;
@@ -601,7 +636,7 @@ extern "C" void ra_engine_destroy(ra_engine* e)
     for (int i = 0; i < e->n_allocs; i++) cudaFree(e->allocs[i]);
     cudaFree(e->d_ev); cudaFree(e->d_msgs); cudaFree(e->d_notes); cudaFree(e->d_rows); cudaFree(e->d_scan_tmp);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
-    cudaStreamDestroy(e->stream);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
     free(e);
 }
 
@@ -622,6 +657,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
 {
     if (!cfg || !out || cfg->n_members < 1 || cfg->n_members > RA_MAX_MEMBERS || cfg->n_groups == 0) return RA_E_INVAL;
     if ((u64)cfg->n_groups * cfg->n_members > 0x7fffffffull) return RA_E_INVAL;
+    if (cfg->n_shards > 1 && (!cfg->route_on_device || cfg->shard >= cfg->n_shards || cfg->n_shards > 64)) return RA_E_INVAL;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev) return RA_E_NODEVICE;
     ra_engine* e = (ra_engine*)calloc(1, sizeof(ra_engine));
@@ -633,6 +669,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
     cudaError_t ce;
     if ((ce = cudaSetDevice(cfg->device)) != cudaSuccess) { rc = fail(e, ce, "cudaSetDevice"); goto bad; }
     if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail(e, ce, "cudaStreamCreate"); goto bad; }
+    e->own_stream = 1;
     cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
     {
         Cols& C = e->C;
@@ -640,6 +677,8 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         C.rows = (u32)R; C.groups = cfg->n_groups; C.members = cfg->n_members;
         C.max_pipeline = e->cfg.max_pipeline_count; C.max_batch = e->cfg.max_aer_batch;
         C.routed = cfg->route_on_device ? 1 : 0; C.pure = cfg->pure ? 1 : 0;
+        C.n_shards = cfg->n_shards > 1 ? cfg->n_shards : 1; C.shard = cfg->n_shards > 1 ? cfg->shard : 0;
+        C.outbox = nullptr; C.out_cnt = nullptr; C.out_cap = 0;
 #define DA(p, n) if ((rc = dalloc(e, &(p), (n))) != RA_OK) goto bad
         DA(C.tc, R); DA(C.lg, R); DA(C.lw, R); DA(C.ap, R); DA(C.sn, R); DA(C.tk, R); DA(C.fm, R);
         DA(C.cd, 2 * R); DA(C.pnm, M * R); DA(C.pcs, M * R); DA(C.run, RA_MAX_RUNS * R);
@@ -723,6 +762,11 @@ extern "C" int ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n)
 
 static int launch_step(ra_engine* e, const FloodArgs& F)
 {
+    if (e->C.n_shards > 1) {
+        if (!e->C.outbox) return RA_E_INVAL;                    // ra_engine_set_outbox first
+        cudaError_t c0 = cudaMemsetAsync(e->C.out_cnt, 0, e->C.n_shards * sizeof(u32), e->stream);
+        if (c0 != cudaSuccess) return fail(e, c0, "cudaMemsetAsync out_cnt");
+    }
     const u32 grid = (e->C.tiles + WARPS - 1) / WARPS;
     u32* cnt = e->d_stall_cnt + (e->steps & 1), *cnt_next = e->d_stall_cnt + ((e->steps + 1) & 1);
     switch (e->C.members) {
@@ -813,6 +857,35 @@ extern "C" int ra_engine_stall_histogram(ra_engine* e, uint64_t* out128)
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaMemcpyAsync(out128, e->C.counters + 8, 128 * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    return RA_OK;
+}
+
+extern "C" int ra_engine_set_stream(ra_engine* e, void* cuda_stream)
+{
+    if (!e) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    e->stream = (cudaStream_t)cuda_stream;
+    e->own_stream = 0;
+    return RA_OK;
+}
+
+extern "C" int ra_engine_set_outbox(ra_engine* e, void* outbox, uint32_t* counts, uint32_t cap)
+{
+    if (!e || e->C.n_shards < 2 || !outbox || !counts || !cap) return RA_E_INVAL;
+    e->C.outbox = (ra_event*)outbox; e->C.out_cnt = counts; e->C.out_cap = cap;
+    return RA_OK;
+}
+
+extern "C" int ra_engine_deliver(ra_engine* e, const void* inbox, const uint32_t* counts, uint32_t cap)
+{
+    if (!e || e->C.n_shards < 2 || !inbox || !counts || !cap) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    // e->cur is the buffer the next step reads: the one the last step's senders wrote into
+    dim3 grid(nblocks(cap, 256) < 512 ? nblocks(cap, 256) : 512, e->C.n_shards);
+    deliver_kernel<<<grid, 256, 0, e->stream>>>(e->C, e->cur, (const ra_event*)inbox, counts, cap);
+    CK(cudaGetLastError());
     return RA_OK;
 }
 

@@ -88,6 +88,13 @@ struct Cols {
     u32 rows, groups, members;
     u32 max_pipeline, max_batch;
     u32 routed, pure;
+    // cross-shard transport (n_shards > 1): member (g, s) lives on shard (g + s) mod N at local
+    // group index g div N, so a record from slot s to slot t of the same group always goes to
+    // shard (shard + t - s) mod N and to the SAME local row index t * groups + q there.
+    u32 n_shards, shard;
+    ra_event* outbox;      // [n_shards][out_cap] dense buckets, one per destination shard
+    u32*      out_cnt;     // [n_shards]
+    u32       out_cap;
 };
 
 #define CTA_T 128                 // threads per CTA (4 independent warps)
@@ -431,6 +438,24 @@ __device__ __forceinline__ void emit_msg(Member& m, u32 to, Rec r)
         u32 k = (m.sent_to >> (4 * to)) & 15u;
         if (k >= RA_MBOX_DEPTH) { m.status |= RA_ST_MSG_DROPPED; m.c_dropped++; return; }
         R_set_row_seq(r, dst, k);
+        if (C.n_shards > 1) {
+            const u32 ds = (C.shard + to + 8u * C.n_shards - m.slot) % C.n_shards;
+            if (ds != C.shard) {
+                // bucket of the destination shard: one atomic per group of converged lanes
+                const u32 act = __activemask();
+                const u32 grp = __match_any_sync(act, ds);
+                const u32 ldr = __ffs(grp) - 1;
+                u32 base = 0;
+                if ((threadIdx.x & 31u) == ldr) base = atomicAdd(&C.out_cnt[ds], (u32)__popc(grp));
+                base = __shfl_sync(grp, base, ldr);
+                const u32 pos = base + __popc(grp & ((1u << (threadIdx.x & 31u)) - 1u));
+                if (pos >= C.out_cap) { m.status |= RA_ST_MSG_DROPPED; m.c_dropped++; return; }
+                st_rec(&C.outbox[(size_t)ds * C.out_cap + pos], r);
+                m.sent_to += 1u << (4 * to);
+                m.c_msgs++;
+                return;
+            }
+        }
         st_rec_tiled(C.mbox[m.nb], C.tiles, m.slot * RA_MBOX_DEPTH + k, dst, r);
         m.sent_to += 1u << (4 * to);
         m.c_msgs++;

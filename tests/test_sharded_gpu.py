@@ -1,0 +1,57 @@
+"""`-m gpu`: members of a group spread over shards (SURVEY §8e / BASELINE config 4 placement).
+
+N engines in one process on one GPU, exchanging their cross-shard RPC buckets by device copies
+(`LocalTransport`); the NCCL transport moves the same buckets with all_to_all_single and is
+exercised by tests/test_sharded_nccl.py on a multi-GPU box.  The sharded run must leave every
+member bit-identical to the UNSHARDED oracle run of the same groups.
+"""
+import pytest
+
+from oracle_lib import Oracle
+from ra_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # shards, members, local groups per slot, steps, election permille
+    (2, 5, 300, 80, 10),
+    (4, 3, 128, 60, 0),
+    (8, 5, 96, 80, 20),
+    (3, 7, 100, 60, 10),
+    (5, 5, 200, 50, 10),      # N == M: every member of a group on its own shard
+]
+
+
+@pytest.mark.parametrize("n,m,gl,steps,permille", CASES)
+def test_sharded_flood_equals_unsharded_oracle(n, m, gl, steps, permille):
+    from ra_b200.sharded import LocalTransport, Shard, ShardedFlood
+    shards = [Shard(gl, m, n, k) for k in range(n)]
+    fl = ShardedFlood(LocalTransport(shards))
+    fl.bootstrap()
+    fl.run(steps, 1, permille, seed=77)
+    fl.sync()
+    g = n * gl
+    o = Oracle(g, m, route_on_device=True)
+    o.reset_empty()
+    o.step([abi.ev_simple(o.row_of(i, 0), abi.EV_ELECTION_TIMEOUT) for i in range(g)])
+    o.flood(steps, 1, permille, seed=77, threads=8)
+    want = {r.row: r.key()[1:] for r in o.read_rows(range(o.n_rows))}
+    seen = 0
+    for s in shards:
+        for r in s.eng.read_rows(range(s.eng.n_rows)):
+            assert r.key()[1:] == want[s.global_row(r.row, g)], (s.shard, r.row)
+            seen += 1
+    assert seen == g * m
+    co, ce = o.counters(), fl.counters()
+    for k in ("events", "commits", "applied", "msgs_out", "msgs_dropped", "elections_won", "fatal_rows"):
+        assert ce[k] == co[k], k
+    assert co["commits"] > 0 and co["msgs_dropped"] == 0
+
+
+def test_placement_math():
+    from ra_b200.sharded import global_group, local_group, shard_of
+    for n in (1, 2, 3, 8):
+        for g in range(50):
+            for s in range(5):
+                k = shard_of(g, s, n)
+                assert global_group(local_group(g, n), s, k, n) == g
