@@ -34,6 +34,9 @@ sys.path.insert(0, ROOT)
 B_COMMIT = {3: 40 + 104 * 3 + 2 * (169 + 185) + (128 + 8 * 3) + 2 * (145 + 8 * 3),
             5: 2884, 7: 4282}
 METRIC = "committed entries/sec across N Raft groups; HBM GB/s vs roofline"
+# dram__bytes_read.sum + dram__bytes_write.sum of raft_step_kernel per launch, from the last
+# `ncu --set full` capture of this workload (profiles/, see profiles/README.md); None until measured
+TRAFFIC_BYTES = None
 
 
 def b_commit(m: int) -> int:
@@ -144,37 +147,85 @@ def run_engine(args):
     rank, world, local = dist_init(args.gpus)
     G, M = args.groups, args.members
     dev = local
-    eng = Engine(G, M, device=dev, route_on_device=True)
-    eng.reset_empty()
-    eng.step([abi.ev_simple(eng.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(G)])
-    eng.flood(args.settle, args.cmds, args.permille, seed=args.seed + rank)       # elect leaders, fill the pipeline
-    eng.flood(args.warmup, args.cmds, args.permille, seed=args.seed + rank)       # W untimed warm-up steps
+    spread = world > 1 and args.placement == "spread"
+    if spread:
+        # members of a group on different GPUs; cross-shard RPC records by NCCL all-to-all
+        from ra_b200.sharded import NcclTransport, Shard, ShardedFlood
+        torch.cuda.set_device(dev)
+        sh = Shard(G, M, world, rank, device=dev)
+        eng = sh.eng
+        fl = ShardedFlood(NcclTransport(sh))
+        fl.bootstrap()
+        seed = args.seed                                         # one global host model
+        flood = lambda n: fl.run(n, args.cmds, args.permille, seed)
+    else:
+        eng = Engine(G, M, device=dev, route_on_device=True)
+        eng.reset_empty()
+        eng.step([abi.ev_simple(eng.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(G)])
+        seed = args.seed + rank
+        flood = lambda n: eng.flood(n, args.cmds, args.permille, seed=seed, sync=False)
+    flood(args.settle)                                           # elect leaders, fill the pipeline
+    flood(args.warmup)                                           # W untimed warm-up steps
+    torch.cuda.synchronize(dev)
+    eng.sync()
     c0 = eng.counters()
     sampler = ClockSampler(dev)
     sampler.start()
     barrier_sync(world, local)
-    eng.flood(args.steps, args.cmds, args.permille, seed=args.seed + rank, sync=False)
-    eng.sync()
+    if spread:
+        # the engine runs on torch's current stream in this mode: time with torch CUDA events on it
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        flood(args.steps)
+        t1.record()
+        torch.cuda.synchronize(dev)
+        ms, launches = t0.elapsed_time(t1), 3 * args.steps
+    else:
+        flood(args.steps)
+        eng.sync()
+        ms, launches = eng.last_kernel_ms()                      # CUDA events on the engine's stream
     barrier_sync(world, local)
-    ms, launches = eng.last_kernel_ms()                       # CUDA events on the engine's stream
     clocks = sampler.stop()
     c1 = eng.counters()
     commits = c1["commits"] - c0["commits"]
     events = c1["events"] - c0["events"]
+    dropped = c1["msgs_dropped"] - c0["msgs_dropped"]
     ms_max, commits_all, events_all = reduce_max_sum(world, local, ms, commits, events)
     value = commits_all / (ms_max * 1e-3)
 
     # e2e: the same flood through ra_engine_step with pinned host buffers (rank-local engine)
     e2e = None
     if not args.no_e2e:
-        eng2 = Engine(G, M, device=dev, route_on_device=True)
-        eng2.reset_empty()
-        hf = HostFlood(eng2)
-        hf.run(args.settle, args.cmds, args.permille, seed=args.seed + rank, bootstrap=True)
-        hf.run(min(args.warmup, 10), args.cmds, args.permille, seed=args.seed + rank)
+        if spread:
+            from ra_b200.sharded import NcclTransport, Shard
+            sh2 = Shard(G, M, world, rank, device=dev)
+            eng2 = sh2.eng
+            tr2 = NcclTransport(sh2)
+            eng2.reset_empty()
+            hf = HostFlood(eng2)
+            hf.run(0, args.cmds, args.permille, seed=args.seed, bootstrap=True)
+            tr2.exchange()
+
+            def host_steps(n):
+                h2d = d2h = 0
+                t_0 = time.perf_counter()
+                for _ in range(n):
+                    st_ = hf.run(1, args.cmds, args.permille, seed=args.seed)
+                    tr2.exchange()
+                    h2d += st_["h2d_bytes"]; d2h += st_["d2h_bytes"]
+                torch.cuda.synchronize(dev)
+                return dict(seconds=time.perf_counter() - t_0, h2d_bytes=h2d, d2h_bytes=d2h)
+        else:
+            eng2 = Engine(G, M, device=dev, route_on_device=True)
+            eng2.reset_empty()
+            hf = HostFlood(eng2)
+            hf.run(0, args.cmds, args.permille, seed=seed, bootstrap=True)
+            host_steps = lambda n: hf.run(n, args.cmds, args.permille, seed=seed)
+        host_steps(args.settle)
+        host_steps(min(args.warmup, 10))
         d0 = eng2.counters()
         barrier_sync(world, local)
-        st = hf.run(args.e2e_steps, args.cmds, args.permille, seed=args.seed + rank)
+        st = host_steps(args.e2e_steps)
         barrier_sync(world, local)
         d1 = eng2.counters()
         sec, ec, _ = reduce_max_sum(world, local, st["seconds"], d1["commits"] - d0["commits"], 0)
@@ -182,7 +233,7 @@ def run_engine(args):
                "h2d_bytes_per_step": st["h2d_bytes"] // args.e2e_steps,
                "d2h_bytes_per_step": st["d2h_bytes"] // args.e2e_steps,
                "steps": args.e2e_steps, "ms_per_step": sec * 1e3 / args.e2e_steps,
-               "gpu_launches_per_step": 6}
+               "gpu_launches_per_step": 7 + (3 if spread else 0)}
         hf.close()
         eng2.close()
 
@@ -190,7 +241,10 @@ def run_engine(args):
         return
     peak, peak_src = hbm_peak()
     bc = b_commit(M)
-    achieved = (commits / (ms * 1e-3)) * bc / 1e9               # this rank's kernel, GB/s
+    achieved = (commits / (ms * 1e-3)) * bc / 1e9               # this rank, GB/s
+    par = ("members of a group on different GPUs ((group+slot) mod N); cross-shard RPC records by NCCL "
+           "all_to_all_single (bucket counts + equal-size buckets) every step" if spread else
+           "groups sharded by rank, every member of a group on one GPU, no data-path collective")
     out = {
         "metric": METRIC, "value": value, "unit": "commits/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -199,15 +253,18 @@ def run_engine(args):
                                "leader per step, %.1f%% election timeouts per step (BASELINE.json configs[2] shape)"
                                % (G, M, args.cmds, args.permille / 10.0),
                    "groups_per_gpu": G, "members": M, "cmds_per_step": args.cmds,
-                   "election_permille": args.permille, "parallelism": "groups sharded by rank, no data-path collective",
+                   "election_permille": args.permille, "parallelism": par,
+                   "placement": "spread" if spread else "group",
                    "l2": "working set (SoA %.0f MB + mailboxes) exceeds the 126 MB L2; no explicit flush"
                          % (G * M * 392 / 1e6),
-                   "events_per_step": events / args.steps, "commits_per_step": commits / args.steps},
+                   "events_per_step": events / args.steps, "commits_per_step": commits / args.steps,
+                   "msgs_dropped": dropped},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "bytes_per_commit": bc, "kernel": "raft_step_kernel"},
+                     "frac": achieved / peak, "traffic": TRAFFIC_BYTES, "peak_source": peak_src,
+                     "bytes_per_commit": bc, "algorithmic_bytes_per_launch": bc * commits / args.steps,
+                     "kernel": "raft_step_kernel (+ raft_general_kernel for the rows that leave the fast paths)"},
     }
     if e2e:
         out["e2e"] = e2e
@@ -275,6 +332,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--cpu-groups", type=int, default=20_000)
     ap.add_argument("--cpu-steps", type=int, default=100)
+    ap.add_argument("--placement", default="spread", choices=["spread", "group"],
+                    help="N>1: spread = members of a group on different GPUs + NCCL all-to-all of RPC records; "
+                         "group = whole groups per GPU, no collective")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
