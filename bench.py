@@ -148,13 +148,15 @@ def run_engine(args):
     G, M = args.groups, args.members
     dev = local
     spread = world > 1 and args.placement == "spread"
+    peer = False
     if spread:
         # members of a group on different GPUs; cross-shard RPC records by NCCL all-to-all
-        from ra_b200.sharded import NcclTransport, Shard, ShardedFlood
+        from ra_b200.sharded import NcclTransport, NvlinkPeerTransport, Shard, ShardedFlood
         torch.cuda.set_device(dev)
-        sh = Shard(G, M, world, rank, device=dev)
+        peer = args.transport == "peer" and world <= 8
+        sh = Shard(G, M, world, rank, device=dev, buckets=not peer)
         eng = sh.eng
-        fl = ShardedFlood(NcclTransport(sh))
+        fl = ShardedFlood(NvlinkPeerTransport(sh) if peer else NcclTransport(sh))
         fl.bootstrap()
         seed = args.seed                                         # one global host model
         flood = lambda n: fl.run(n, args.cmds, args.permille, seed)
@@ -197,10 +199,10 @@ def run_engine(args):
     e2e = None
     if not args.no_e2e:
         if spread:
-            from ra_b200.sharded import NcclTransport, Shard
-            sh2 = Shard(G, M, world, rank, device=dev)
+            from ra_b200.sharded import NcclTransport, NvlinkPeerTransport, Shard
+            sh2 = Shard(G, M, world, rank, device=dev, buckets=not peer)
             eng2 = sh2.eng
-            tr2 = NcclTransport(sh2)
+            tr2 = NvlinkPeerTransport(sh2) if peer else NcclTransport(sh2)
             eng2.reset_empty()
             hf = HostFlood(eng2)
             hf.run(0, args.cmds, args.permille, seed=args.seed, bootstrap=True)
@@ -242,8 +244,12 @@ def run_engine(args):
     peak, peak_src = hbm_peak()
     bc = b_commit(M)
     achieved = (commits / (ms * 1e-3)) * bc / 1e9               # this rank, GB/s
-    par = ("members of a group on different GPUs ((group+slot) mod N); cross-shard RPC records by NCCL "
-           "all_to_all_single (bucket counts + equal-size buckets) every step" if spread else
+    par = ("members of a group on different GPUs ((group+slot) mod N); " +
+           ("RPC records are stored by the step kernels straight into the destination GPU's mailbox planes "
+            "over NVLink (CUDA IPC peer mappings); one 1-element NCCL all-reduce per step keeps the shards in lock step"
+            if spread and peer else
+            "cross-shard RPC records by NCCL all_to_all_single (bucket counts + equal-size buckets) every step")
+           if spread else
            "groups sharded by rank, every member of a group on one GPU, no data-path collective")
     out = {
         "metric": METRIC, "value": value, "unit": "commits/s", "n_gpus": world, "steps": args.steps,
@@ -335,6 +341,9 @@ def main():
     ap.add_argument("--placement", default="spread", choices=["spread", "group"],
                     help="N>1: spread = members of a group on different GPUs + NCCL all-to-all of RPC records; "
                          "group = whole groups per GPU, no collective")
+    ap.add_argument("--transport", default="peer", choices=["peer", "a2a"],
+                    help="spread placement: peer = NVLink peer stores from inside the step kernels; "
+                         "a2a = per-destination buckets + NCCL all_to_all_single + deliver kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -312,6 +312,23 @@ int  ra_engine_set_outbox(ra_engine* e, void* outbox, uint32_t* counts, uint32_t
 int  ra_engine_deliver(ra_engine* e, const void* inbox, const uint32_t* counts, uint32_t cap);
 
 /*
+ * Peer transport (n_shards <= 8, GPUs of one NVLink/NVSwitch domain): instead of bucket +
+ * all-to-all + deliver, every shard maps the mailbox buffers of the others and the step kernels
+ * store each RPC record straight into the destination GPU's mailbox plane over NVLink -- compute
+ * and transfer are one kernel.  The caller only has to keep the shards in lock step (one barrier
+ * between steps).  ra_engine_peer_get returns this engine's buffers as device pointers (same
+ * process) ; ra_engine_ipc_export / _import move them between processes as CUDA IPC handles.
+ * ra_engine_peer_set(shard, ...) registers shard's buffers; once all n_shards are registered
+ * (own shard included automatically) the kernels switch to peer stores.
+ */
+typedef struct ra_peer_ptrs { void* mbox[2]; void* mbox_cnt[2]; } ra_peer_ptrs;
+typedef struct ra_ipc_handles { unsigned char h[4][64]; } ra_ipc_handles;
+int  ra_engine_peer_get(ra_engine* e, ra_peer_ptrs* out);
+int  ra_engine_peer_set(ra_engine* e, uint32_t shard, const ra_peer_ptrs* p);
+int  ra_engine_ipc_export(ra_engine* e, ra_ipc_handles* out);
+int  ra_engine_ipc_import(ra_engine* e, uint32_t shard, const ra_ipc_handles* h);
+
+/*
  * The same flood driven from the HOST through ra_engine_step (host buffers, H2D of the
  * step's events and D2H of its notes inside every step): what an Erlang batching process
  * in front of many ra_server_procs would do.  The host model (WAL completion, clients,

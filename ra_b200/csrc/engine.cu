@@ -132,9 +132,13 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
     if (C.routed) {
         for (u32 s = 0; s < NMEM(C); s++) {
             if (s == m.slot) continue;
-            // a remote member's count is set when its records are delivered (deliver_kernel)
-            if (C.n_shards > 1 && (C.shard + s + 8u * C.n_shards - m.slot) % C.n_shards != C.shard) continue;
-            reinterpret_cast<u8*>(&C.mbox_cnt[cur ^ 1][(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
+            u64* cnt = C.mbox_cnt[cur ^ 1];
+            if (C.n_shards > 1) {
+                const u32 ds = (C.shard + s + 8u * C.n_shards - m.slot) % C.n_shards;
+                if (C.peer_mode) cnt = C.peer_cnt[cur ^ 1][ds];          // byte store over NVLink
+                else if (ds != C.shard) continue;   // set when the records are delivered (deliver_kernel)
+            }
+            reinterpret_cast<u8*>(&cnt[(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
         }
     }
     note_flush(m);
@@ -679,6 +683,8 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         C.routed = cfg->route_on_device ? 1 : 0; C.pure = cfg->pure ? 1 : 0;
         C.n_shards = cfg->n_shards > 1 ? cfg->n_shards : 1; C.shard = cfg->n_shards > 1 ? cfg->shard : 0;
         C.outbox = nullptr; C.out_cnt = nullptr; C.out_cap = 0;
+        C.peer_mode = 0;
+        for (int b = 0; b < 2; b++) for (int k = 0; k < 8; k++) { C.peer_mbox[b][k] = nullptr; C.peer_cnt[b][k] = nullptr; }
 #define DA(p, n) if ((rc = dalloc(e, &(p), (n))) != RA_OK) goto bad
         DA(C.tc, R); DA(C.lg, R); DA(C.lw, R); DA(C.ap, R); DA(C.sn, R); DA(C.tk, R); DA(C.fm, R);
         DA(C.cd, 2 * R); DA(C.pnm, M * R); DA(C.pcs, M * R); DA(C.run, RA_MAX_RUNS * R);
@@ -763,9 +769,11 @@ extern "C" int ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n)
 static int launch_step(ra_engine* e, const FloodArgs& F)
 {
     if (e->C.n_shards > 1) {
-        if (!e->C.outbox) return RA_E_INVAL;                    // ra_engine_set_outbox first
-        cudaError_t c0 = cudaMemsetAsync(e->C.out_cnt, 0, e->C.n_shards * sizeof(u32), e->stream);
-        if (c0 != cudaSuccess) return fail(e, c0, "cudaMemsetAsync out_cnt");
+        if (!e->C.peer_mode) {
+            if (!e->C.outbox) return RA_E_INVAL;                // ra_engine_set_outbox / peer_set first
+            cudaError_t c0 = cudaMemsetAsync(e->C.out_cnt, 0, e->C.n_shards * sizeof(u32), e->stream);
+            if (c0 != cudaSuccess) return fail(e, c0, "cudaMemsetAsync out_cnt");
+        }
     }
     const u32 grid = (e->C.tiles + WARPS - 1) / WARPS;
     u32* cnt = e->d_stall_cnt + (e->steps & 1), *cnt_next = e->d_stall_cnt + ((e->steps + 1) & 1);
@@ -887,6 +895,51 @@ extern "C" int ra_engine_deliver(ra_engine* e, const void* inbox, const uint32_t
     deliver_kernel<<<grid, 256, 0, e->stream>>>(e->C, e->cur, (const ra_event*)inbox, counts, cap);
     CK(cudaGetLastError());
     return RA_OK;
+}
+
+extern "C" int ra_engine_peer_get(ra_engine* e, ra_peer_ptrs* out)
+{
+    if (!e || !out || !e->C.routed) return RA_E_INVAL;
+    for (int b = 0; b < 2; b++) { out->mbox[b] = e->C.mbox[b]; out->mbox_cnt[b] = e->C.mbox_cnt[b]; }
+    return RA_OK;
+}
+
+extern "C" int ra_engine_peer_set(ra_engine* e, uint32_t shard, const ra_peer_ptrs* p)
+{
+    if (!e || !p || e->C.n_shards < 2 || e->C.n_shards > 8 || shard >= e->C.n_shards) return RA_E_INVAL;
+    Cols& C = e->C;
+    for (int b = 0; b < 2; b++) { C.peer_mbox[b][shard] = (ulonglong2*)p->mbox[b]; C.peer_cnt[b][shard] = (u64*)p->mbox_cnt[b]; }
+    for (int b = 0; b < 2; b++) { C.peer_mbox[b][C.shard] = C.mbox[b]; C.peer_cnt[b][C.shard] = C.mbox_cnt[b]; }
+    bool all = true;
+    for (u32 k = 0; k < C.n_shards; k++) all = all && C.peer_mbox[0][k] && C.peer_mbox[1][k] && C.peer_cnt[0][k] && C.peer_cnt[1][k];
+    C.peer_mode = all ? 1 : 0;
+    return RA_OK;
+}
+
+extern "C" int ra_engine_ipc_export(ra_engine* e, ra_ipc_handles* out)
+{
+    if (!e || !out || !e->C.routed) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->h[0], e->C.mbox[0]));
+    CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->h[1], e->C.mbox[1]));
+    CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->h[2], e->C.mbox_cnt[0]));
+    CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->h[3], e->C.mbox_cnt[1]));
+    return RA_OK;
+}
+
+extern "C" int ra_engine_ipc_import(ra_engine* e, uint32_t shard, const ra_ipc_handles* h)
+{
+    if (!e || !h) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    ra_peer_ptrs p;
+    void* q[4];
+    for (int i = 0; i < 4; i++) {
+        cudaIpcMemHandle_t hh; memcpy(&hh, h->h[i], sizeof hh);
+        CK(cudaIpcOpenMemHandle(&q[i], hh, cudaIpcMemLazyEnablePeerAccess));
+    }
+    p.mbox[0] = q[0]; p.mbox[1] = q[1]; p.mbox_cnt[0] = q[2]; p.mbox_cnt[1] = q[3];
+    return ra_engine_peer_set(e, shard, &p);
 }
 
 extern "C" int ra_engine_get_cfg(ra_engine* e, ra_engine_cfg* out)

@@ -95,6 +95,11 @@ struct Cols {
     ra_event* outbox;      // [n_shards][out_cap] dense buckets, one per destination shard
     u32*      out_cnt;     // [n_shards]
     u32       out_cap;
+    // peer transport: the mailbox buffers of every shard, mapped into this GPU's address space
+    // (own shard included); records are stored straight into the destination GPU's HBM
+    u32         peer_mode;
+    ulonglong2* peer_mbox[2][8];
+    u64*        peer_cnt[2][8];
 };
 
 #define CTA_T 128                 // threads per CTA (4 independent warps)
@@ -440,6 +445,13 @@ __device__ __forceinline__ void emit_msg(Member& m, u32 to, Rec r)
         R_set_row_seq(r, dst, k);
         if (C.n_shards > 1) {
             const u32 ds = (C.shard + to + 8u * C.n_shards - m.slot) % C.n_shards;
+            if (C.peer_mode) {
+                // NVLink peer store into the destination GPU's mailbox plane (same local row index)
+                st_rec_tiled(C.peer_mbox[m.nb][ds], C.tiles, m.slot * RA_MBOX_DEPTH + k, dst, r);
+                m.sent_to += 1u << (4 * to);
+                m.c_msgs++;
+                return;
+            }
             if (ds != C.shard) {
                 // bucket of the destination shard: one atomic per group of converged lanes
                 const u32 act = __activemask();

@@ -46,31 +46,63 @@ def _declare(l):
     l.ra_engine_set_outbox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     l.ra_engine_deliver.restype = C.c_int
     l.ra_engine_deliver.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    for n in ("ra_engine_peer_get", "ra_engine_ipc_export"):
+        getattr(l, n).restype = C.c_int
+        getattr(l, n).argtypes = [C.c_void_p, C.c_void_p]
+    for n in ("ra_engine_peer_set", "ra_engine_ipc_import"):
+        getattr(l, n).restype = C.c_int
+        getattr(l, n).argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+
+
+class PeerPtrs(C.Structure):
+    _fields_ = [("mbox", C.c_void_p * 2), ("mbox_cnt", C.c_void_p * 2)]
+
+
+class IpcHandles(C.Structure):
+    _fields_ = [("h", (C.c_ubyte * 64) * 4)]
 
 
 class Shard:
     """One shard = one engine + its exchange buffers (torch tensors on the engine's device)."""
 
     def __init__(self, groups_local: int, members: int, n_shards: int, shard: int, device: int = 0,
-                 cap: int | None = None, **kw):
+                 cap: int | None = None, buckets: bool = True, **kw):
         _declare(lib())
         self.n_shards, self.shard, self.dev = n_shards, shard, device
         self.eng = Engine(groups_local, members, device=device, route_on_device=True, n_shards=n_shards,
                           shard=shard, **kw)
         rows = groups_local * members
         # per destination and step: ~3.1 records per row on average in a flood, spread over N shards
-        self.cap = cap or max(1024, (rows * 5) // n_shards)
+        self.cap = cap or max(1024, (rows * 4) // n_shards)
         tdev = torch.device("cuda", device)
-        self.outbox = torch.zeros((n_shards, self.cap, 64), dtype=torch.uint8, device=tdev)
-        self.inbox = torch.zeros((n_shards, self.cap, 64), dtype=torch.uint8, device=tdev)
-        self.out_cnt = torch.zeros(n_shards, dtype=torch.int32, device=tdev)
-        self.in_cnt = torch.zeros(n_shards, dtype=torch.int32, device=tdev)
         with torch.cuda.device(tdev):
             stream = torch.cuda.current_stream(tdev).cuda_stream
         e = self.eng
         e._check(lib().ra_engine_set_stream(e._h, C.c_void_p(stream)), "set_stream")
-        e._check(lib().ra_engine_set_outbox(e._h, C.c_void_p(self.outbox.data_ptr()),
-                                            C.c_void_p(self.out_cnt.data_ptr()), self.cap), "set_outbox")
+        if buckets:                      # bucket + all-to-all transport; not needed for peer stores
+            self.outbox = torch.zeros((n_shards, self.cap, 64), dtype=torch.uint8, device=tdev)
+            self.inbox = torch.zeros((n_shards, self.cap, 64), dtype=torch.uint8, device=tdev)
+            self.out_cnt = torch.zeros(n_shards, dtype=torch.int32, device=tdev)
+            self.in_cnt = torch.zeros(n_shards, dtype=torch.int32, device=tdev)
+            e._check(lib().ra_engine_set_outbox(e._h, C.c_void_p(self.outbox.data_ptr()),
+                                                C.c_void_p(self.out_cnt.data_ptr()), self.cap), "set_outbox")
+
+    def peer_ptrs(self) -> "PeerPtrs":
+        p = PeerPtrs()
+        self.eng._check(lib().ra_engine_peer_get(self.eng._h, C.byref(p)), "peer_get")
+        return p
+
+    def peer_set(self, shard: int, p: "PeerPtrs") -> None:
+        self.eng._check(lib().ra_engine_peer_set(self.eng._h, shard, C.byref(p)), "peer_set")
+
+    def ipc_export(self) -> bytes:
+        h = IpcHandles()
+        self.eng._check(lib().ra_engine_ipc_export(self.eng._h, C.byref(h)), "ipc_export")
+        return bytes(h)
+
+    def ipc_import(self, shard: int, raw: bytes) -> None:
+        h = IpcHandles.from_buffer_copy(raw)
+        self.eng._check(lib().ra_engine_ipc_import(self.eng._h, shard, C.byref(h)), "ipc_import")
 
     def deliver(self) -> None:
         e = self.eng
@@ -118,6 +150,45 @@ class NcclTransport:
         self.dist.all_to_all_single(s.in_cnt, s.out_cnt)
         self.dist.all_to_all_single(s.inbox.view(s.n_shards, -1), s.outbox.view(s.n_shards, -1))
         s.deliver()
+
+
+class LocalPeerTransport:
+    """All shards in this process on one device, peer-store mode: every shard knows the others'
+    mailbox buffers and writes into them directly; nothing to exchange between steps."""
+
+    def __init__(self, shards: Sequence[Shard]):
+        self.shards = list(shards)
+        ptrs = {s.shard: s.peer_ptrs() for s in self.shards}
+        for s in self.shards:
+            for k, p in ptrs.items():
+                if k != s.shard:
+                    s.peer_set(k, p)
+
+    def exchange(self) -> None:
+        pass
+
+
+class NvlinkPeerTransport:
+    """One shard per rank on one NVLink/NVSwitch domain: mailbox buffers are mapped across
+    processes with CUDA IPC at start-up, the step kernels store RPC records straight into the
+    destination GPU's HBM, and the only per-step collective is the lock-step barrier (a 1-element
+    NCCL all-reduce on the compute stream)."""
+
+    def __init__(self, shard: Shard):
+        import torch.distributed as dist
+        self.dist = dist
+        self.shard = shard
+        self.shards = [shard]
+        handles = [None] * dist.get_world_size()
+        dist.all_gather_object(handles, shard.ipc_export())
+        for k, raw in enumerate(handles):
+            if k != shard.shard:
+                shard.ipc_import(k, raw)
+        self._tok = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", shard.dev))
+        dist.barrier()
+
+    def exchange(self) -> None:
+        self.dist.all_reduce(self._tok)          # lock step: nobody starts step t+1 before all finished t
 
 
 class ShardedFlood:

@@ -22,11 +22,12 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("transport", ["buckets", "peer"])
 @pytest.mark.parametrize("n,m,gl,steps,permille", CASES)
-def test_sharded_flood_equals_unsharded_oracle(n, m, gl, steps, permille):
-    from ra_b200.sharded import LocalTransport, Shard, ShardedFlood
-    shards = [Shard(gl, m, n, k) for k in range(n)]
-    fl = ShardedFlood(LocalTransport(shards))
+def test_sharded_flood_equals_unsharded_oracle(n, m, gl, steps, permille, transport):
+    from ra_b200.sharded import LocalPeerTransport, LocalTransport, Shard, ShardedFlood
+    shards = [Shard(gl, m, n, k, buckets=(transport == "buckets")) for k in range(n)]
+    fl = ShardedFlood(LocalTransport(shards) if transport == "buckets" else LocalPeerTransport(shards))
     fl.bootstrap()
     fl.run(steps, 1, permille, seed=77)
     fl.sync()

@@ -22,8 +22,9 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("transport", ["a2a", "peer"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_nccl_sharded_flood_equals_oracle(world, tmp_path):
+def test_nccl_sharded_flood_equals_oracle(world, transport, tmp_path):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
@@ -33,14 +34,15 @@ def test_nccl_sharded_flood_equals_oracle(world, tmp_path):
         sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
         import torch, torch.distributed as dist
         from ra_b200 import abi
-        from ra_b200.sharded import Shard, NcclTransport, ShardedFlood
+        from ra_b200.sharded import Shard, NcclTransport, NvlinkPeerTransport, ShardedFlood
         from oracle_lib import Oracle
         rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         gl, m, steps = 256, 5, 70
-        sh = Shard(gl, m, world, rank, device=local)
-        fl = ShardedFlood(NcclTransport(sh))
+        peer = %r == "peer"
+        sh = Shard(gl, m, world, rank, device=local, buckets=not peer)
+        fl = ShardedFlood(NvlinkPeerTransport(sh) if peer else NcclTransport(sh))
         fl.bootstrap()
         fl.run(steps, 1, 10, seed=31)
         fl.sync()
@@ -60,7 +62,7 @@ def test_nccl_sharded_flood_equals_oracle(world, tmp_path):
         if rank == 0:
             print("RESULT", int(t[0]), int(t[1]), int(t[2]), o.counters()["commits"])
         dist.destroy_process_group()
-    """ % (ROOT, ROOT)))
+    """ % (ROOT, ROOT, transport)))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
