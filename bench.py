@@ -204,6 +204,7 @@ def run_engine(args):
             eng2 = sh2.eng
             tr2 = NvlinkPeerTransport(sh2) if peer else NcclTransport(sh2)
             eng2.reset_empty()
+            tr2.exchange_barrier()
             hf = HostFlood(eng2)
             hf.run(0, args.cmds, args.permille, seed=args.seed, bootstrap=True)
             tr2.exchange()

@@ -135,6 +135,9 @@ class LocalTransport:
         for s in self.shards:
             s.deliver()
 
+    def exchange_barrier(self) -> None:
+        pass
+
 
 class NcclTransport:
     """One shard per rank: two all_to_all_single calls per step (counts, then equal-size buckets)."""
@@ -151,6 +154,9 @@ class NcclTransport:
         self.dist.all_to_all_single(s.inbox.view(s.n_shards, -1), s.outbox.view(s.n_shards, -1))
         s.deliver()
 
+    def exchange_barrier(self) -> None:
+        pass
+
 
 class LocalPeerTransport:
     """All shards in this process on one device, peer-store mode: every shard knows the others'
@@ -165,6 +171,9 @@ class LocalPeerTransport:
                     s.peer_set(k, p)
 
     def exchange(self) -> None:
+        pass
+
+    def exchange_barrier(self) -> None:
         pass
 
 
@@ -190,6 +199,10 @@ class NvlinkPeerTransport:
     def exchange(self) -> None:
         self.dist.all_reduce(self._tok)          # lock step: nobody starts step t+1 before all finished t
 
+    def exchange_barrier(self) -> None:
+        torch.cuda.synchronize(self.shard.dev)
+        self.dist.barrier()
+
 
 class ShardedFlood:
     """The flood of ra_engine_flood over sharded members: step, exchange, deliver, repeat."""
@@ -198,8 +211,12 @@ class ShardedFlood:
         self.t = transport
 
     def bootstrap(self) -> None:
+        # every shard must be reset before any shard steps: with peer stores a step writes into
+        # the other shards' mailboxes
         for s in self.t.shards:
             s.eng.reset_empty()
+        self.t.exchange_barrier()
+        for s in self.t.shards:
             s.eng.step(s.bootstrap_events())
         self.t.exchange()
 
