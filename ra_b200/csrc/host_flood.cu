@@ -9,6 +9,7 @@
 #include <chrono>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../include/ra_engine.h"
@@ -28,6 +29,8 @@ struct ra_hostsim {
     ra_engine* e;
     u32 groups, members, rows;
     std::vector<unsigned char> role, idle;
+    u32 threads;
+    std::vector<std::vector<ra_event>> tmp;
     ra_event* ev;  size_t ev_cap;     // pinned
     ra_event* msgs; size_t msgs_cap;  // pinned
     ra_note* notes; size_t notes_cap; // pinned
@@ -53,6 +56,13 @@ extern "C" int ra_hostsim_create(ra_engine* e, ra_hostsim** out)
     ra_hostsim* s = new ra_hostsim();
     s->e = e; s->groups = groups; s->members = members; s->rows = groups * members;
     s->role.assign(s->rows, RA_FOLLOWER); s->idle.assign(s->rows, 0);
+    {
+        unsigned hc = std::thread::hardware_concurrency();
+        const char* env = getenv("RA_HOSTSIM_THREADS");
+        s->threads = env ? (u32)atoi(env) : (hc > 16 ? 16u : (hc ? hc : 1u));
+        if (s->threads < 1) s->threads = 1;
+        s->tmp.resize(s->threads);
+    }
     s->ev_cap = (size_t)s->rows * RA_LOCAL_CAP; s->msgs_cap = 1024; s->notes_cap = (size_t)s->rows * RA_NOTE_CAP;
     s->ev = (ra_event*)ra_engine_alloc_host(s->ev_cap * sizeof(ra_event));
     s->msgs = (ra_event*)ra_engine_alloc_host(s->msgs_cap * sizeof(ra_event));
@@ -77,15 +87,19 @@ static inline void put(ra_event* e, u32 row, u32 type, u32 n, u64 term, u64 a, u
     e->term = term; e->a = a; e->b = b;
 }
 
-// notes of one step -> events of the next (the flood host model)
-static void model(ra_hostsim* s, size_t n_notes, u32 cmds, u32 permille, u64 seed, bool run_model)
+// notes of one step -> events of the next (the flood host model), rows [r0, r1)
+static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u32 r0, u32 r1, ra_event* out,
+                          u32 cmds, u32 permille, u64 seed, bool run_model)
 {
-    size_t ne = 0, i = 0;
-    for (u32 row = 0; row < s->rows; row++) {
+    // first note of row r0 (notes are ordered by row)
+    size_t lo = 0, hi = n_notes;
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (notes[mid].row < r0) lo = mid + 1; else hi = mid; }
+    size_t ne = 0, i = lo;
+    for (u32 row = r0; row < r1; row++) {
         const ra_note* w0 = nullptr; const ra_note* w1 = nullptr;
         u32 status = 0; bool fatal = false;
-        for (; i < n_notes && s->notes[i].row == row; i++) {
-            const ra_note& n = s->notes[i];
+        for (; i < n_notes && notes[i].row == row; i++) {
+            const ra_note& n = notes[i];
             if (n.type == RA_NOTE_WAL_APPEND) { w0 = w1; w1 = &n; }
             else if (n.type == RA_NOTE_STATUS) {
                 status = n.aux;
@@ -94,10 +108,10 @@ static void model(ra_hostsim* s, size_t n_notes, u32 cmds, u32 permille, u64 see
             }
         }
         if (!run_model || fatal) continue;
-        if (w0) put(&s->ev[ne++], row, RA_EV_WRITTEN, 0, w0->c, w0->a, w0->b);
-        if (w1) put(&s->ev[ne++], row, RA_EV_WRITTEN, 0, w1->c, w1->a, w1->b);
+        if (w0) put(&out[ne++], row, RA_EV_WRITTEN, 0, w0->c, w0->a, w0->b);
+        if (w1) put(&out[ne++], row, RA_EV_WRITTEN, 0, w1->c, w1->a, w1->b);
         const u32 role = s->role[row];
-        if (role == RA_LEADER && cmds) put(&s->ev[ne++], row, RA_EV_COMMAND, cmds, 0, 0, 0);
+        if (role == RA_LEADER && cmds) put(&out[ne++], row, RA_EV_COMMAND, cmds, 0, 0, 0);
         u32 idle = s->idle[row];
         if (role == RA_LEADER || (status & RA_ST_LEADER_MSG)) idle = 0;
         else if (idle < 15) idle++;
@@ -109,10 +123,38 @@ static void model(ra_hostsim* s, size_t n_notes, u32 cmds, u32 permille, u64 see
             u64 h2 = mix64(seed ^ ((u64)row * 0xA24BAED4963EE407ull) ^ s->step);
             if (idle >= 8 + (u32)(h2 % 8)) fire = true;
         }
-        if (fire) { put(&s->ev[ne++], row, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0); idle = 0; }
+        if (fire) { put(&out[ne++], row, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0); idle = 0; }
         s->idle[row] = (unsigned char)idle;
     }
-    s->n_ev = ne;
+    return ne;
+}
+
+// the model over all rows, on s->threads host threads: each thread fills a private buffer for
+// its row range, then the pieces are concatenated (row order is kept) into the pinned batch
+static void model(ra_hostsim* s, size_t n_notes, u32 cmds, u32 permille, u64 seed, bool run_model)
+{
+    const u32 T = s->threads;
+    if (T <= 1 || s->rows < 4096) {
+        s->n_ev = model_range(s, s->notes, n_notes, 0, s->rows, s->ev, cmds, permille, seed, run_model);
+        return;
+    }
+    std::vector<size_t> cnt(T, 0);
+    std::vector<std::thread> th;
+    for (u32 t = 0; t < T; t++) {
+        th.emplace_back([=, &cnt]() {
+            const u32 r0 = (u32)((u64)s->rows * t / T), r1 = (u32)((u64)s->rows * (t + 1) / T);
+            if (s->tmp[t].size() < (size_t)(r1 - r0) * RA_LOCAL_CAP) s->tmp[t].resize((size_t)(r1 - r0) * RA_LOCAL_CAP);
+            cnt[t] = model_range(s, s->notes, n_notes, r0, r1, s->tmp[t].data(), cmds, permille, seed, run_model);
+        });
+    }
+    for (auto& x : th) x.join();
+    th.clear();
+    std::vector<size_t> off(T + 1, 0);
+    for (u32 t = 0; t < T; t++) off[t + 1] = off[t] + cnt[t];
+    for (u32 t = 0; t < T; t++)
+        th.emplace_back([=, &off, &cnt]() { if (cnt[t]) memcpy(s->ev + off[t], s->tmp[t].data(), cnt[t] * sizeof(ra_event)); });
+    for (auto& x : th) x.join();
+    s->n_ev = off[T];
 }
 
 extern "C" int ra_hostsim_run(ra_hostsim* s, uint32_t n_steps, uint32_t cmds, uint32_t permille,

@@ -73,7 +73,7 @@ class Shard:
                           shard=shard, **kw)
         rows = groups_local * members
         # per destination and step: ~3.1 records per row on average in a flood, spread over N shards
-        self.cap = cap or max(1024, (rows * 4) // n_shards)
+        self.cap = cap or max(4096, (rows * 6) // n_shards)
         tdev = torch.device("cuda", device)
         with torch.cuda.device(tdev):
             stream = torch.cuda.current_stream(tdev).cuda_stream
