@@ -1566,10 +1566,10 @@ static void host_model(ra_oracle *o, ctx_t *c, u64 step, u32 cmds, u32 permille,
     if (m->role == RA_LEADER || (c->status & RA_ST_LEADER_MSG)) m->idle = 0;
     else m->idle++;
     if (m->role != RA_LEADER) {
-        u64 h = mix64(seed ^ (step * 0x9E3779B97F4A7C15ull) ^ ((u64)g * 0xD1B54A32D192ED03ull));
-        if (permille && (h % 1000) < permille && ((h / 1000) % o->cfg.n_members) == m->self_slot) fire = 1;
-        u64 h2 = mix64(seed ^ ((u64)row * 0xA24BAED4963EE407ull) ^ step);
-        if (m->idle >= 8 + (h2 % 8)) fire = 1;
+        u32 h = (u32)(mix64(seed ^ (step * 0x9E3779B97F4A7C15ull) ^ ((u64)g * 0xD1B54A32D192ED03ull)) >> 32);
+        if (permille && (h % 1000u) < permille && ((h / 1000u) % o->cfg.n_members) == m->self_slot) fire = 1;
+        u32 h2 = (u32)(mix64(seed ^ ((u64)row * 0xA24BAED4963EE407ull) ^ step) >> 32);
+        if (m->idle >= 8 + (h2 & 7u)) fire = 1;
     }
     if (fire) {
         ra_event e; memset(&e, 0, sizeof e);

@@ -170,12 +170,12 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
                 gr = (u64)m.slot * C.groups * C.n_shards + gg;
             }
             if (F.permille) {
-                u64 h = mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ (gg * 0xD1B54A32D192ED03ull));
-                if ((h % 1000) < F.permille && ((h / 1000) % NMEM(C)) == m.slot) fire = true;
+                const u32 h = (u32)(mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ (gg * 0xD1B54A32D192ED03ull)) >> 32);
+                if ((h % 1000u) < F.permille && ((h / 1000u) % NMEM(C)) == m.slot) fire = true;
             }
             if (idle >= 8) {                                // the hash only matters from 8 idle steps on
-                u64 h2 = mix64(F.seed ^ (gr * 0xA24BAED4963EE407ull) ^ F.step);
-                if (idle >= 8 + (u32)(h2 % 8)) fire = true;
+                const u32 h2 = (u32)(mix64(F.seed ^ (gr * 0xA24BAED4963EE407ull) ^ F.step) >> 32);
+                if (idle >= 8 + (h2 & 7u)) fire = true;
             }
         }
         if (fire) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_ELECTION_TIMEOUT, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)); k++; idle = 0; }
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(CTA_T)
 raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F,
                     const StallCtx* __restrict__ stall_list, const u32* __restrict__ stall_count)
 {
-    constexpr int MM = 0;
+    constexpr int MM = MK_MM(0, TR_RUNTIME);
     __shared__ u64 s_peers[3 * RA_MAX_MEMBERS * CTA_T];
     const u32 tid = threadIdx.x, lane = tid & 31u;
     const u32 n = *stall_count;
@@ -706,10 +706,11 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp_bytes, e->d_packed, e->d_offs, (int)(R + 1), e->stream);
         if ((ce = cudaMalloc(&e->d_scan_tmp, e->scan_tmp_bytes ? e->scan_tmp_bytes : 16)) != cudaSuccess) { rc = fail(e, ce, "cudaMalloc scan"); goto bad; }
     }
-    if ((ce = cudaFuncSetAttribute(raft_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<0>))) != cudaSuccess ||
-        (ce = cudaFuncSetAttribute(raft_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem<5>))) != cudaSuccess) {
-        rc = fail(e, ce, "cudaFuncSetAttribute"); goto bad;
-    }
+#define SMEM_ATTR(MEMB, TRN) \
+    if ((ce = cudaFuncSetAttribute(raft_step_kernel<MK_MM(MEMB, TRN)>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   (int)sizeof(StepSmem<MK_MM(MEMB, TRN)>))) != cudaSuccess) { rc = fail(e, ce, "cudaFuncSetAttribute"); goto bad; }
+    SMEM_ATTR(0, TR_RUNTIME) SMEM_ATTR(5, TR_LOCAL) SMEM_ATTR(5, TR_PEER) SMEM_ATTR(5, TR_BUCKET) SMEM_ATTR(5, TR_HOST)
+#undef SMEM_ATTR
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -777,10 +778,21 @@ static int launch_step(ra_engine* e, const FloodArgs& F)
     }
     const u32 grid = (e->C.tiles + WARPS - 1) / WARPS;
     u32* cnt = e->d_stall_cnt + (e->steps & 1), *cnt_next = e->d_stall_cnt + ((e->steps + 1) & 1);
-    switch (e->C.members) {
-    case 5:  raft_step_kernel<5><<<grid, CTA_T, sizeof(StepSmem<5>), e->stream>>>(e->C, e->cur, F, e->d_stall, cnt, cnt_next); break;
-    default: raft_step_kernel<0><<<grid, CTA_T, sizeof(StepSmem<0>), e->stream>>>(e->C, e->cur, F, e->d_stall, cnt, cnt_next); break;
+    // one specialisation of the hot kernel per (member count, transport): see MK_MM
+    const int tr = !e->C.routed ? TR_HOST : (e->C.n_shards > 1 ? (e->C.peer_mode ? TR_PEER : TR_BUCKET) : TR_LOCAL);
+#define LAUNCH(MEMB, TRN) raft_step_kernel<MK_MM(MEMB, TRN)><<<grid, CTA_T, sizeof(StepSmem<MK_MM(MEMB, TRN)>), e->stream>>>( \
+        e->C, e->cur, F, e->d_stall, cnt, cnt_next)
+    if (e->C.members == 5) {
+        switch (tr) {
+        case TR_LOCAL:  LAUNCH(5, TR_LOCAL); break;
+        case TR_PEER:   LAUNCH(5, TR_PEER); break;
+        case TR_BUCKET: LAUNCH(5, TR_BUCKET); break;
+        default:        LAUNCH(5, TR_HOST); break;
+        }
+    } else {
+        LAUNCH(0, TR_RUNTIME);
     }
+#undef LAUNCH
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(e, ce, "raft_step_kernel");
     raft_general_kernel<<<e->general_grid, CTA_T, 0, e->stream>>>(e->C, e->cur, F, e->d_stall, cnt);

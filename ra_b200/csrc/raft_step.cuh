@@ -53,9 +53,20 @@ typedef unsigned char u8;
 #define MT_VOTER(m, s)    ((u32)(((m) >> (56 + (s))) & 1ull))
 #define MT_SET(m, sh, w, v) ((m) = ((m) & ~((((u64)1 << (w)) - 1) << (sh))) | (((u64)(v) & (((u64)1 << (w)) - 1)) << (sh)))
 #define SLOT_NONE 15u
-// number of members: compile-time when the kernel is specialised (MM != 0), else from the config
-#define NMEM(C) ((u32)(MM ? MM : (C).members))
-#define PSTR (MM ? MM : RA_MAX_MEMBERS)      // peer slots staged per thread in shared memory
+// The template int of the device functions carries two compile-time specialisations:
+//   low byte  = number of members (0: read it from the config)
+//   next byte = transport of the RPC records (0: decide at run time)
+// so that the hot kernel contains the code of exactly one transport (instruction-cache footprint).
+#define TR_RUNTIME 0
+#define TR_LOCAL   1   /* route_on_device, one shard: mailbox planes of this GPU          */
+#define TR_PEER    2   /* n_shards > 1: NVLink peer stores into the destination GPU      */
+#define TR_BUCKET  3   /* n_shards > 1: per-destination buckets for the all-to-all       */
+#define TR_HOST    4   /* not routed: records returned to the host (omsg slots)          */
+#define MK_MM(members, tr) ((members) | ((tr) << 8))
+#define MMEM (MM & 0xff)
+#define MTR  ((MM >> 8) & 0xff)
+#define NMEM(C) ((u32)(MMEM ? MMEM : (C).members))
+#define PSTR (MMEM ? MMEM : RA_MAX_MEMBERS)      // peer slots staged per thread in shared memory
 
 struct Cols {
     // scalar pairs, one cell per row
@@ -241,16 +252,16 @@ __device__ __forceinline__ void peers_ensure(Member& m)
 }
 template <int MM>
 __device__ __forceinline__ ulonglong2 peer_nm(Member& m, u32 s)
-{ peers_ensure<MM>(m); return make_ulonglong2(m.sp[(0 * PSTR + s) * CTA_T], m.sp[(1 * PSTR + s) * CTA_T]); }
+{ return make_ulonglong2(m.sp[(0 * PSTR + s) * CTA_T], m.sp[(1 * PSTR + s) * CTA_T]); }
 template <int MM>
 __device__ __forceinline__ void peer_nm_set(Member& m, u32 s, u64 next, u64 match)
-{ peers_ensure<MM>(m); m.sp[(0 * PSTR + s) * CTA_T] = next; m.sp[(1 * PSTR + s) * CTA_T] = match; m.pstate |= 1u << (8 + s); }
+{ m.sp[(0 * PSTR + s) * CTA_T] = next; m.sp[(1 * PSTR + s) * CTA_T] = match; m.pstate |= 1u << (8 + s); }
 template <int MM>
 __device__ __forceinline__ u64 peer_cs(Member& m, u32 s)
-{ peers_ensure<MM>(m); return m.sp[(2 * PSTR + s) * CTA_T]; }
+{ return m.sp[(2 * PSTR + s) * CTA_T]; }
 template <int MM>
 __device__ __forceinline__ void peer_cs_set(Member& m, u32 s, u64 v)
-{ peers_ensure<MM>(m); m.sp[(2 * PSTR + s) * CTA_T] = v; m.pstate |= 1u << (16 + s); }
+{ m.sp[(2 * PSTR + s) * CTA_T] = v; m.pstate |= 1u << (16 + s); }
 template <int MM>
 __device__ __forceinline__ void peers_writeback(Member& m)
 {
@@ -435,17 +446,20 @@ __device__ __forceinline__ void emit_msg(Member& m, u32 to, Rec r)
 {
     const Cols& C = *m.C;
     u32 dst = to * C.groups + m.group;                  // (an id outside the group is the host's business)
-    bool is_next = (R_flags(r) & RA_EVF_NEXT_EVENT) != 0;
-    if (C.routed && !is_next && to >= NMEM(C)) return;  // no mailbox for an unknown peer
+    const bool is_next = (R_flags(r) & RA_EVF_NEXT_EVENT) != 0;
+    const bool routed = MTR == TR_RUNTIME ? (C.routed != 0) : (MTR != TR_HOST);
+    if (routed && !is_next && to >= NMEM(C)) return;    // no mailbox for an unknown peer
     if (!is_next) R_set_from(r, m.slot);
     R_clear_pad(r);
-    if (C.routed && !is_next) {
+    if (routed && !is_next) {
         u32 k = (m.sent_to >> (4 * to)) & 15u;
         if (k >= RA_MBOX_DEPTH) { m.status |= RA_ST_MSG_DROPPED; m.c_dropped++; return; }
         R_set_row_seq(r, dst, k);
-        if (C.n_shards > 1) {
+        const bool sharded = MTR == TR_RUNTIME ? (C.n_shards > 1) : (MTR == TR_PEER || MTR == TR_BUCKET);
+        if (sharded) {
             const u32 ds = (C.shard + to + 8u * C.n_shards - m.slot) % C.n_shards;
-            if (C.peer_mode) {
+            const bool peer = MTR == TR_RUNTIME ? (C.peer_mode != 0) : (MTR == TR_PEER);
+            if (peer) {
                 // NVLink peer store into the destination GPU's mailbox plane (same local row index)
                 st_rec_tiled(C.peer_mbox[m.nb][ds], C.tiles, m.slot * RA_MBOX_DEPTH + k, dst, r);
                 m.sent_to += 1u << (4 * to);
@@ -559,8 +573,7 @@ template <int MM>
 __device__ __forceinline__ void evaluate_quorum(Member& m)
 {
     const u32 M = NMEM(*m.C);
-    constexpr int NV = MM ? MM : RA_MAX_MEMBERS;
-    peers_ensure<MM>(m);
+    constexpr int NV = MMEM ? MMEM : RA_MAX_MEMBERS;
     u64 v[NV];
     u32 n = 1;
 #pragma unroll
@@ -640,12 +653,17 @@ __device__ __forceinline__ u64 make_rpc_effect(Member& m, u32 peer, u64 next, u6
     return m.snap_idx;
 }
 
-// make_pipelined_rpc_effects/3 :2268-2329 -> More
+// The leader's three ways of walking its peers share one loop (one inlined copy of
+// make_rpc_effect/5 in the hot kernel):
+//   RP_PIPELINE  make_pipelined_rpc_effects/3 :2268-2329 -> More
+//   RP_STALE     make_rpcs/1 over stale_peers/1 :2985-3003 (tick)       } batch 1, peers are
+//   RP_ALL       make_all_rpcs/1 :2337-2350 (enforce leadership)        } not updated
+enum { RP_PIPELINE = 0, RP_STALE = 1, RP_ALL = 2 };
 template <int MM>
-__device__ __forceinline__ bool make_pipelined_rpcs(Member& m, bool force)
+__device__ __forceinline__ bool rpc_pass(Member& m, u32 mode, bool force)
 {
     const Cols& C = *m.C;
-    if (m.pipe_clean && !force && m.pc_last == m.last_idx && m.pc_commit == m.commit) return false;
+    if (mode == RP_PIPELINE && m.pipe_clean && !force && m.pc_last == m.last_idx && m.pc_commit == m.commit) return false;
     u64 next_log_idx = m.last_idx + 1;
     i64 max_pipe = C.max_pipeline, max_batch = C.max_batch;
     bool more = false, clean = true;
@@ -654,13 +672,20 @@ __device__ __forceinline__ bool make_pipelined_rpcs(Member& m, bool force)
         if (MT_PSTATUS(m.meta, s) != RA_PEER_NORMAL) continue;
         ulonglong2 nm = peer_nm<MM>(m, s);
         u64 cs = peer_cs<MM>(m, s);
-        if (!(nm.x < next_log_idx || cs < m.commit)) continue;
-        i64 in_flight = (i64)nm.x - (i64)nm.y - 1;
-        if (!(in_flight < max_pipe || force)) { clean = false; continue; }
-        i64 bs = max_pipe - in_flight; if (max_batch < bs) bs = max_batch; if (bs < 1) bs = 1;
+        i64 bs = 1;
+        if (mode == RP_PIPELINE) {
+            if (!(nm.x < next_log_idx || cs < m.commit)) continue;
+            i64 in_flight = (i64)nm.x - (i64)nm.y - 1;
+            if (!(in_flight < max_pipe || force)) { clean = false; continue; }
+            bs = max_pipe - in_flight; if (max_batch < bs) bs = max_batch; if (bs < 1) bs = 1;
+        } else if (mode == RP_STALE) {
+            bool stale = ((i64)nm.y < (i64)nm.x - 1) || (cs < m.commit);
+            if (!stale) continue;
+        }
         bool snap;
         u64 nn = make_rpc_effect<MM>(m, s, nm.x, (u64)bs, snap);
         if (MT_FATAL(m.meta)) return false;
+        if (mode != RP_PIPELINE) continue;
         if (!(nn >= nm.x)) { set_fatal(m, RA_FATAL_ASSERT); return false; }
         peer_nm_set<MM>(m, s, nn, nm.y);
         peer_cs_set<MM>(m, s, m.commit);
@@ -669,28 +694,13 @@ __device__ __forceinline__ bool make_pipelined_rpcs(Member& m, bool force)
         if (nn < next_log_idx && nif < max_pipe) more = true;
         if (nn < next_log_idx) clean = false;
     }
-    m.pipe_clean = clean ? 1u : 0u; m.pc_last = m.last_idx; m.pc_commit = m.commit;
+    if (mode == RP_PIPELINE) { m.pipe_clean = clean ? 1u : 0u; m.pc_last = m.last_idx; m.pc_commit = m.commit; }
     return more;
 }
-
-// make_rpcs_for/2 over stale_peers/1 (:2985-3003) or all normal peers (make_all_rpcs/1)
 template <int MM>
-__device__ __forceinline__ void make_rpcs(Member& m, bool all)
-{
-    const Cols& C = *m.C;
-    for (u32 s = 0; s < NMEM(C); s++) {
-        if (s == m.slot) continue;
-        if (MT_PSTATUS(m.meta, s) != RA_PEER_NORMAL) continue;
-        ulonglong2 nm = peer_nm<MM>(m, s);
-        if (!all) {
-            bool stale = ((i64)nm.y < (i64)nm.x - 1) || (peer_cs<MM>(m, s) < m.commit);
-            if (!stale) continue;
-        }
-        bool snap;
-        (void)make_rpc_effect<MM>(m, s, nm.x, 1, snap);
-        if (MT_FATAL(m.meta)) return;
-    }
-}
+__device__ __forceinline__ bool make_pipelined_rpcs(Member& m, bool force) { return rpc_pass<MM>(m, RP_PIPELINE, force); }
+template <int MM>
+__device__ __forceinline__ void make_rpcs(Member& m, bool all) { (void)rpc_pass<MM>(m, all ? RP_ALL : RP_STALE, false); }
 
 // initialise_peers/1 :3207-3215
 template <int MM>
@@ -732,29 +742,28 @@ __device__ __forceinline__ u32 call_for_election(Member& m, u32 target, NextQ& n
     return target;
 }
 
-// process_pre_vote/3 :2899-2956
+// process_pre_vote/3 :2899-2956 (one reply site)
 template <int MM>
 __device__ __forceinline__ u32 process_pre_vote(Member& m, u32 fsm, const Rec& e)
 {
     u64 term = R_term(e), token = R_c(e);
     u32 version = (u32)(R_d(e) & 0xffffffffull), their = (u32)(R_d(e) >> 32);
     u32 macver = (u32)(m.macver & 0xffffffffull), eff = (u32)(m.macver >> 32);
-    u32 cand = R_from(e);
+    bool send = true, granted = false, tmo = false;
+    u64 rterm = term;
     if (term >= m.term) {
         update_term(m, term);
         if (log_up_to_date(R_a(e), R_b(e), m.last_idx, m.last_term)) {
-            if (version > 1) reply_vote<MM>(m, cand, RA_EV_PRE_VOTE_RES, term, token, false);
-            else if (their == eff || (their >= eff && their <= macver))
-                reply_vote<MM>(m, cand, RA_EV_PRE_VOTE_RES, term, token, true);
-            else { reply_vote<MM>(m, cand, RA_EV_PRE_VOTE_RES, term, token, false); m.status |= RA_ST_START_ELECTION_TMO; }
-        } else if (fsm == RA_FOLLOWER) {
-            m.status |= RA_ST_START_ELECTION_TMO;
-        } else {
-            reply_vote<MM>(m, cand, RA_EV_PRE_VOTE_RES, term, token, false);
-        }
+            if (version > 1) granted = false;                                   // :2914-2917
+            else if (their == eff || (their >= eff && their <= macver)) granted = true;   // :2918-2928
+            else { granted = false; tmo = true; }                               // :2929-2934
+        } else if (fsm == RA_FOLLOWER) { send = false; tmo = true; }            // :2941-2942
+        else granted = false;                                                   // :2943-2945
     } else {
-        reply_vote<MM>(m, cand, RA_EV_PRE_VOTE_RES, m.term, token, false);
+        rterm = m.term;                                                         // :2948-2956
     }
+    if (tmo) m.status |= RA_ST_START_ELECTION_TMO;
+    if (send) reply_vote<MM>(m, R_from(e), RA_EV_PRE_VOTE_RES, rterm, token, granted);
     return fsm;
 }
 
@@ -1182,6 +1191,7 @@ template <int MM>
 __device__ __forceinline__ void process_event(Member& m, const Rec& in)
 {
     const Cols& C = *m.C;
+    peers_ensure<MM>(m);                       // general path: any clause may touch the peer columns
     u32 pend = NX_REDISPATCH, np = 1;          // queue of codes, front = low nibble
     bool chased = false;
     m.c_events++;
@@ -1237,10 +1247,12 @@ __device__ __forceinline__ void process_event(Member& m, const Rec& in)
 
 
 // ---- steady-state fast paths ---------------------------------------------------------------
-// The flood is dominated by six shapes of event.  Each fast path is the general clause
+// The flood is dominated by a handful of event shapes.  Each fast path is the general clause
 // specialised under an explicit guard (every condition the general path would test on the
-// way); anything else -- term changes, log mismatch, elections, multi-run batches ... --
-// takes process_event().  Both routes are diffed against the oracle by the parity tests.
+// way); anything else -- term changes, log mismatch, candidates, multi-run batches ... --
+// takes process_event() in raft_general_kernel.  Both routes are diffed against the oracle by
+// the parity tests.  Shared tails (apply, reply, quorum, rpc pass) have ONE call site each: the
+// hot kernel has to stay small enough for the instruction cache.
 template <int MM>
 __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
 {
@@ -1258,53 +1270,42 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
         role = RA_FOLLOWER;
     }
     if (role == RA_FOLLOWER) {
+        bool apply = false, reply = false;
+        u64 reply_term = 0;
+        u32 leader = MT_LEADER(m.meta);
         if (type == RA_EV_AER) {
             // handle_follower(#append_entries_rpc{}) :1266-1371, prev entry = our last entry
             if (R_term(e) != m.term || R_n1(e) != 0 || !nonempty || R_a(e) != m.last_idx || R_b(e) != m.last_term) return false;
             const u32 n = R_n(e);
-            const u32 leader = R_from(e);
-            if (n == 0) {                                              // validated empty AER :1313-1326
-                m.c_events++;
-                m.status |= RA_ST_LEADER_MSG;
-                MT_SET(m.meta, 3, 4, leader);
-                m.commit = R_c(e);
-                evaluate_commit_index_follower(m);
-                emit_msg<MM>(m, leader, aer_reply(m, R_term(e), true));
-                return true;
-            }
-            if (R_d(e) != m.last_term || m.last_idx + 1 < m.applied) return false;
+            if (n != 0 && (R_d(e) != m.last_term || m.last_idx + 1 < m.applied)) return false;
             m.c_events++;
+            leader = R_from(e);
             m.status |= RA_ST_LEADER_MSG;
             MT_SET(m.meta, 3, 4, leader);
-            m.commit = R_c(e);                                         // :1349
-            const u64 fst = m.last_idx + 1;
-            m.last_idx += n;                                           // same term: the last run grows
-            note(m, RA_NOTE_WAL_APPEND, 0, fst, m.last_idx, m.last_term);
-            evaluate_commit_index_follower(m);
-            return true;
-        }
-        if (type == RA_EV_WRITTEN) {
-            // handle_follower({ra_log_event,{written,..}}) :1441-1458, range ends at our last entry
+            m.commit = R_c(e);                                         // :1314-1315 / :1349
+            if (n == 0) {                                              // validated empty AER :1313-1326
+                reply = true; reply_term = R_term(e);
+            } else {
+                const u64 fst = m.last_idx + 1;
+                m.last_idx += n;                                       // same term: the last run grows
+                note(m, RA_NOTE_WAL_APPEND, 0, fst, m.last_idx, m.last_term);
+            }
+            apply = true;
+        } else if (type == RA_EV_WRITTEN) {
+            // handle_follower({ra_log_event,{written,..}}) :1441-1458, range ends inside the last run
             // (every index of the last run has term last_term: ra_log:fetch_term(To) == Term)
             if (nonempty && !m.lrs_ok) { m.lrs = run_get(m, m_nruns(m) - 1).x; m.lrs_ok = 1; }
             if (!nonempty || !m.lrs_ok || R_term(e) != m.last_term || R_b(e) > m.last_idx || R_b(e) < m.lrs) return false;
             m.c_events++;
-            const bool changed = m.lw_idx != R_b(e) || m.lw_term != m.last_term;
+            reply = (m.lw_idx != R_b(e) || m.lw_term != m.last_term) && leader != SLOT_NONE;
+            reply_term = m.term;
             m.lw_idx = R_b(e); m.lw_term = m.last_term;
-            const u32 leader = MT_LEADER(m.meta);
-            if (changed && leader != SLOT_NONE) emit_msg<MM>(m, leader, aer_reply(m, m.term, true));
-            return true;
-        }
-        if (type == RA_EV_PRE_VOTE) {                                  // :1459-1466
+        } else if (type == RA_EV_PRE_VOTE) {                           // :1459-1466
             m.c_events++;
             if (MT_MEMBERSHIP(m.meta) == RA_VOTER) (void)process_pre_vote<MM>(m, RA_FOLLOWER, e);
-            return true;
-        }
-        if (type == RA_EV_PRE_VOTE_RES || type == RA_EV_REQUEST_VOTE_RES) {   // :1593-1598: ignored
+        } else if (type == RA_EV_PRE_VOTE_RES || type == RA_EV_REQUEST_VOTE_RES) {   // :1593-1598: ignored
             m.c_events++;
-            return true;
-        }
-        if (type == RA_EV_ELECTION_TIMEOUT) {
+        } else if (type == RA_EV_ELECTION_TIMEOUT) {
             // :1603-1610 -> call_for_election(pre_vote) :2873-2897, then the queued vote for self
             // (handle_pre_vote :1212-1229): one vote, which is not yet a quorum
             if (MT_MEMBERSHIP(m.meta) != RA_VOTER || required_quorum<MM>(m) == 1 || m.C->pure) return false;
@@ -1314,51 +1315,49 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
             MT_SET(m.meta, 0, 3, RA_PRE_VOTE);
             m.status |= RA_ST_ROLE_CHANGED;
             MT_SET(m.meta, 15, 4, 1);
-            return true;
-        }
-        return false;
+        } else return false;
+        if (apply) evaluate_commit_index_follower(m);
+        if (reply) emit_msg<MM>(m, leader, aer_reply(m, reply_term, true));
+        return true;
     }
     if (role == RA_LEADER) {
-        bool tail = false;
         if (type == RA_EV_PRE_VOTE_RES || type == RA_EV_REQUEST_VOTE_RES) {   // :958-963: ignored
             m.c_events++;
             return true;
         }
+        peers_ensure<MM>(m);              // the ONE place the hot kernel stages the peer columns
+        bool quorum = false, chase = false, force = false;
+        u32 mode = RP_PIPELINE;
         if (type == RA_EV_PRE_VOTE) {                                  // :952-957 enforce leadership
             if (R_term(e) > m.term) return false;
             m.c_events++;
-            make_rpcs<MM>(m, true);
-            return true;
-        }
-        if (type == RA_EV_COMMAND) {                                   // :644-729
+            mode = RP_ALL;
+        } else if (type == RA_EV_COMMAND) {                            // :644-729
             const u64 n = R_n(e);
             if (n == 0 || !nonempty) return false;
             m.c_events++;
             const u64 from = m.last_idx + 1;
             log_append(m, n, m.term);
             note(m, RA_NOTE_WAL_APPEND, 0, from, from + n - 1, m.term);
-            (void)make_pipelined_rpcs<MM>(m, (R_flags(e) & RA_EVF_NOOP) != 0);
-            return true;
-        }
-        if (type == RA_EV_WRITTEN) {                                   // :730-735
+            force = (R_flags(e) & RA_EVF_NOOP) != 0;
+        } else if (type == RA_EV_WRITTEN) {                            // :730-735
             if (nonempty && !m.lrs_ok) { m.lrs = run_get(m, m_nruns(m) - 1).x; m.lrs_ok = 1; }
             if (!nonempty || !m.lrs_ok || R_term(e) != m.last_term || R_b(e) > m.last_idx || R_b(e) < m.lrs) return false;
             m.c_events++;
             m.lw_idx = R_b(e); m.lw_term = m.last_term;
-            tail = true;
+            quorum = chase = true;
         } else if (type == RA_EV_AER_REPLY) {                          // :522-561
             const u32 from = R_from(e);
             if (!(R_d(e) != 0 && R_term(e) == m.term && from < NMEM(*m.C))) return false;
             m.c_events++;
             ulonglong2 nm = peer_nm<MM>(m, from);
             peer_nm_set<MM>(m, from, R_a(e) > nm.x ? R_a(e) : nm.x, R_b(e) > nm.y ? R_b(e) : nm.y);
-            tail = true;
-        }
-        if (!tail) return false;
-        evaluate_quorum<MM>(m);
-        // {next_event, info, pipeline_rpcs}: one chased pass, the rest is deferred (contract 4)
-        if (make_pipelined_rpcs<MM>(m, false)) { MT_SET(m.meta, 24, 1, 1); m.status |= RA_ST_PIPELINE_PENDING; }
-        return !MT_FATAL(m.meta) || true;
+            quorum = chase = true;
+        } else return false;
+        if (quorum) evaluate_quorum<MM>(m);
+        // a chased {next_event, info, pipeline_rpcs}: one pass, the rest is deferred (contract 4)
+        if (rpc_pass<MM>(m, mode, force) && chase) { MT_SET(m.meta, 24, 1, 1); m.status |= RA_ST_PIPELINE_PENDING; }
+        return true;
     }
     return false;
 }
