@@ -46,6 +46,7 @@ __device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes)
 __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
 {
     // bounded: a TMA that never lands must fail the launch loudly, not hang the GPU
+#pragma unroll 1
     for (u32 spins = 0; spins < (1u << 24); spins++) {
         u32 done;
         asm volatile(
@@ -154,10 +155,10 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
     // flood: synthetic host (DESIGN.md "flood host model")
     if (F.on && !MT_FATAL(m.meta)) {
         u32 k = 0;
-        if (m.w_n == 2) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_WRITTEN, RA_NO_SLOT, 0, 0, 0, 0, m.w0c, m.w0a, m.w0b, 0, 0, 0)); k++; }
-        if (m.w_n >= 1) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_WRITTEN, RA_NO_SLOT, 0, 0, 0, 0, m.w1c, m.w1a, m.w1b, 0, 0, 0)); k++; }
+        if (m.w_n == 2) { put_local(C.loc, C.tiles, k, r, RA_EV_WRITTEN, 0, m.w0c, m.w0a, m.w0b); k++; }
+        if (m.w_n >= 1) { put_local(C.loc, C.tiles, k, r, RA_EV_WRITTEN, 0, m.w1c, m.w1a, m.w1b); k++; }
         const u32 role = MT_ROLE(m.meta);
-        if (role == RA_LEADER && F.cmds) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_COMMAND, RA_NO_SLOT, 0, F.cmds, 0, 0, 0, 0, 0, 0, 0, 0)); k++; }
+        if (role == RA_LEADER && F.cmds) { put_local(C.loc, C.tiles, k, r, RA_EV_COMMAND, F.cmds, 0, 0, 0); k++; }
         u32 idle = MT_IDLE(m.meta);
         if (role == RA_LEADER || (m.status & RA_ST_LEADER_MSG)) idle = 0;
         else if (idle < 15) idle++;
@@ -178,7 +179,7 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
                 if (idle >= 8 + (h2 & 7u)) fire = true;
             }
         }
-        if (fire) { st_rec_tiled(C.loc, C.tiles, k, r, mk_rec(r, RA_EV_ELECTION_TIMEOUT, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)); k++; idle = 0; }
+        if (fire) { put_local(C.loc, C.tiles, k, r, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0); k++; idle = 0; }
         MT_SET(m.meta, 28, 4, idle);
         C.loc_n[r] = k;
     }

@@ -411,11 +411,23 @@ __device__ __forceinline__ void set_fatal(Member& m, u32 code)
     MT_SET(m.meta, 26, 1, 1);
 }
 
+// out of line on purpose (scalar arguments only, nothing of the member escapes): called from many
+// places, and the hot kernel has to stay small
+__device__ __noinline__ void note_store_raw(ra_note* slot_ptr, u32 row, u32 type, u32 slot, u32 aux, u64 a, u64 b, u64 c)
+{
+    ulonglong2* q = reinterpret_cast<ulonglong2*>(slot_ptr);
+    q[0] = make_ulonglong2((u64)row | ((u64)(type & 0xff) << 32) | ((u64)(slot & 0xff) << 40) | ((u64)(aux & 0xffff) << 48), a);
+    q[1] = make_ulonglong2(b, c);
+}
 __device__ __forceinline__ void note_store(Member& m, u32 k, u32 type, u32 slot, u32 aux, u64 a, u64 b, u64 c)
 {
-    ulonglong2* q = reinterpret_cast<ulonglong2*>(&m.C->onote[(size_t)k * m.C->rows + m.row]);
-    q[0] = make_ulonglong2((u64)m.row | ((u64)(type & 0xff) << 32) | ((u64)(slot & 0xff) << 40) | ((u64)(aux & 0xffff) << 48), a);
-    q[1] = make_ulonglong2(b, c);
+    note_store_raw(&m.C->onote[(size_t)k * m.C->rows + m.row], m.row, type, slot, aux, a, b, c);
+}
+
+// a host ("local") event record into tiled plane k; out of line for the same reason
+__device__ __noinline__ void put_local(ulonglong2* loc, u32 tiles, u32 k, u32 row, u32 type, u32 n, u64 term, u64 a, u64 b)
+{
+    st_rec_tiled(loc, tiles, k, row, mk_rec(row, type, RA_NO_SLOT, 0, n, 0, 0, term, a, b, 0, 0, 0));
 }
 
 __device__ __forceinline__ void note_flush(Member& m)
