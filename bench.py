@@ -236,6 +236,8 @@ def run_engine(args):
                "h2d_bytes_per_step": st["h2d_bytes"] // args.e2e_steps,
                "d2h_bytes_per_step": st["d2h_bytes"] // args.e2e_steps,
                "steps": args.e2e_steps, "ms_per_step": sec * 1e3 / args.e2e_steps,
+               "engine_call_ms_per_step": st.get("step_seconds", 0.0) * 1e3 / args.e2e_steps,
+               "host_model_ms_per_step": st.get("model_seconds", 0.0) * 1e3 / args.e2e_steps,
                "gpu_launches_per_step": 7 + (3 if spread else 0)}
         hf.close()
         eng2.close()

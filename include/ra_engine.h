@@ -344,6 +344,8 @@ int  ra_hostsim_run(ra_hostsim* s, uint32_t n_steps, uint32_t cmds_per_step,
 /* bytes moved over PCIe by the last ra_hostsim_run and its wall time in seconds */
 int  ra_hostsim_stats(ra_hostsim* s, uint64_t* h2d_bytes, uint64_t* d2h_bytes, double* seconds,
                       uint64_t* engine_calls);
+/* where the wall time of the last run went: inside ra_engine_step vs in the host model */
+int  ra_hostsim_breakdown(ra_hostsim* s, double* step_seconds, double* model_seconds);
 
 /* pinned host memory for callers that want zero-copy staging of their batches */
 void* ra_engine_alloc_host(size_t bytes);

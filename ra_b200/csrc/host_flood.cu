@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <thread>
+#include <omp.h>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../include/ra_engine.h"
@@ -31,6 +32,8 @@ struct ra_hostsim {
     std::vector<unsigned char> role, idle;
     u32 threads;
     std::vector<std::vector<ra_event>> tmp;
+    std::vector<size_t> cnt, off;
+    double t_model, t_step;          // seconds spent in the host model / inside ra_engine_step
     ra_event* ev;  size_t ev_cap;     // pinned
     ra_event* msgs; size_t msgs_cap;  // pinned
     ra_note* notes; size_t notes_cap; // pinned
@@ -62,6 +65,7 @@ extern "C" int ra_hostsim_create(ra_engine* e, ra_hostsim** out)
         s->threads = env ? (u32)atoi(env) : (hc > 16 ? 16u : (hc ? hc : 1u));
         if (s->threads < 1) s->threads = 1;
         s->tmp.resize(s->threads);
+        s->cnt.assign(s->threads, 0); s->off.assign(s->threads + 1, 0);
     }
     s->ev_cap = (size_t)s->rows * RA_LOCAL_CAP; s->msgs_cap = 1024; s->notes_cap = (size_t)s->rows * RA_NOTE_CAP;
     s->ev = (ra_event*)ra_engine_alloc_host(s->ev_cap * sizeof(ra_event));
@@ -129,31 +133,32 @@ static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u
     return ne;
 }
 
-// the model over all rows, on s->threads host threads: each thread fills a private buffer for
-// its row range, then the pieces are concatenated (row order is kept) into the pinned batch
+// the model over all rows on s->threads host threads (OpenMP keeps the team alive between steps):
+// each thread fills a private buffer for its row range, then the pieces are copied, in row
+// order, into the pinned batch
 static void model(ra_hostsim* s, size_t n_notes, u32 cmds, u32 permille, u64 seed, bool run_model)
 {
-    const u32 T = s->threads;
+    const int T = (int)s->threads;
     if (T <= 1 || s->rows < 4096) {
         s->n_ev = model_range(s, s->notes, n_notes, 0, s->rows, s->ev, cmds, permille, seed, run_model);
         return;
     }
-    std::vector<size_t> cnt(T, 0);
-    std::vector<std::thread> th;
-    for (u32 t = 0; t < T; t++) {
-        th.emplace_back([=, &cnt]() {
-            const u32 r0 = (u32)((u64)s->rows * t / T), r1 = (u32)((u64)s->rows * (t + 1) / T);
-            if (s->tmp[t].size() < (size_t)(r1 - r0) * RA_LOCAL_CAP) s->tmp[t].resize((size_t)(r1 - r0) * RA_LOCAL_CAP);
-            cnt[t] = model_range(s, s->notes, n_notes, r0, r1, s->tmp[t].data(), cmds, permille, seed, run_model);
-        });
+    std::vector<size_t>& cnt = s->cnt;
+    std::vector<size_t>& off = s->off;
+#pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num();
+        const u32 r0 = (u32)((u64)s->rows * t / T), r1 = (u32)((u64)s->rows * (t + 1) / T);
+        if (s->tmp[t].size() < (size_t)(r1 - r0) * RA_LOCAL_CAP) s->tmp[t].resize((size_t)(r1 - r0) * RA_LOCAL_CAP);
+        cnt[t] = model_range(s, s->notes, n_notes, r0, r1, s->tmp[t].data(), cmds, permille, seed, run_model);
+#pragma omp barrier
+#pragma omp single
+        {
+            off[0] = 0;
+            for (int k = 0; k < T; k++) off[k + 1] = off[k] + cnt[k];
+        }
+        if (cnt[t]) memcpy(s->ev + off[t], s->tmp[t].data(), cnt[t] * sizeof(ra_event));
     }
-    for (auto& x : th) x.join();
-    th.clear();
-    std::vector<size_t> off(T + 1, 0);
-    for (u32 t = 0; t < T; t++) off[t + 1] = off[t] + cnt[t];
-    for (u32 t = 0; t < T; t++)
-        th.emplace_back([=, &off, &cnt]() { if (cnt[t]) memcpy(s->ev + off[t], s->tmp[t].data(), cnt[t] * sizeof(ra_event)); });
-    for (auto& x : th) x.join();
     s->n_ev = off[T];
 }
 
@@ -163,6 +168,7 @@ extern "C" int ra_hostsim_run(ra_hostsim* s, uint32_t n_steps, uint32_t cmds, ui
     if (!s) return RA_E_INVAL;
     auto t0 = std::chrono::steady_clock::now();
     s->h2d = s->d2h = s->calls = 0;
+    s->t_model = s->t_step = 0;
     size_t nm = 0, nn = 0;
     int rc;
     if (bootstrap) {
@@ -174,10 +180,15 @@ extern "C" int ra_hostsim_run(ra_hostsim* s, uint32_t n_steps, uint32_t cmds, ui
         s->n_ev = 0;
     }
     for (u32 t = 0; t < n_steps; t++) {
+        auto a0 = std::chrono::steady_clock::now();
         rc = ra_engine_step(s->e, s->ev, s->n_ev, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
         if (rc) return rc;
+        auto a1 = std::chrono::steady_clock::now();
         s->h2d += (u64)s->n_ev * sizeof(ra_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
         model(s, nn, cmds, permille, seed, true);
+        auto a2 = std::chrono::steady_clock::now();
+        s->t_step += std::chrono::duration<double>(a1 - a0).count();
+        s->t_model += std::chrono::duration<double>(a2 - a1).count();
         s->step++;
     }
     s->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -188,5 +199,13 @@ extern "C" int ra_hostsim_stats(ra_hostsim* s, uint64_t* h2d, uint64_t* d2h, dou
 {
     if (!s) return RA_E_INVAL;
     if (h2d) *h2d = s->h2d; if (d2h) *d2h = s->d2h; if (seconds) *seconds = s->seconds; if (calls) *calls = s->calls;
+    return RA_OK;
+}
+
+/* where the wall time of the last run went: inside ra_engine_step vs in the host model */
+extern "C" int ra_hostsim_breakdown(ra_hostsim* s, double* step_seconds, double* model_seconds)
+{
+    if (!s) return RA_E_INVAL;
+    if (step_seconds) *step_seconds = s->t_step; if (model_seconds) *model_seconds = s->t_model;
     return RA_OK;
 }

@@ -56,7 +56,8 @@ EXPORTS = ["ra_engine_create", "ra_engine_destroy", "ra_engine_load_rows", "ra_e
            "ra_engine_free_host", "ra_engine_stall_histogram", "ra_engine_set_stream",
            "ra_engine_set_outbox", "ra_engine_deliver", "ra_engine_peer_get", "ra_engine_peer_set",
            "ra_engine_ipc_export", "ra_engine_ipc_import"]
-HOSTSIM_EXPORTS = ["ra_hostsim_create", "ra_hostsim_destroy", "ra_hostsim_run", "ra_hostsim_stats"]
+HOSTSIM_EXPORTS = ["ra_hostsim_create", "ra_hostsim_destroy", "ra_hostsim_run", "ra_hostsim_stats",
+                   "ra_hostsim_breakdown"]
 
 
 class Engine(abi.Backend):
@@ -120,8 +121,13 @@ class HostFlood:
         h2d, d2h, calls = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         sec = C.c_double(0)
         lib().ra_hostsim_stats(self._h, C.byref(h2d), C.byref(d2h), C.byref(sec), C.byref(calls))
+        ts, tm = C.c_double(0), C.c_double(0)
+        f = lib().ra_hostsim_breakdown
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        f(self._h, C.byref(ts), C.byref(tm))
         return dict(h2d_bytes=int(h2d.value), d2h_bytes=int(d2h.value), seconds=float(sec.value),
-                    engine_calls=int(calls.value))
+                    engine_calls=int(calls.value), step_seconds=float(ts.value), model_seconds=float(tm.value))
 
     def close(self) -> None:
         if self._h:
