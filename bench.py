@@ -36,7 +36,7 @@ B_COMMIT = {3: 40 + 104 * 3 + 2 * (169 + 185) + (128 + 8 * 3) + 2 * (145 + 8 * 3
 METRIC = "committed entries/sec across N Raft groups; HBM GB/s vs roofline"
 # dram__bytes_read.sum + dram__bytes_write.sum of raft_step_kernel per launch, from the last
 # `ncu --set full` capture of this workload (profiles/, see profiles/README.md); None until measured
-TRAFFIC_BYTES = None
+TRAFFIC_BYTES = 450_190_336      # profiles/r01_v9_raft_step_ncu_full.txt (250.0 MB read + 200.2 MB written)
 
 
 def b_commit(m: int) -> int:
