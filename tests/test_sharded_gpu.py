@@ -19,6 +19,7 @@ CASES = [
     (8, 5, 96, 80, 20),
     (3, 7, 100, 60, 10),
     (5, 5, 200, 50, 10),      # N == M: every member of a group on its own shard
+    (8, 5, 256, 70, 10),      # the shape of tests/test_sharded_nccl.py at world 8
 ]
 
 
@@ -56,3 +57,16 @@ def test_placement_math():
             for s in range(5):
                 k = shard_of(g, s, n)
                 assert global_group(local_group(g, n), s, k, n) == g
+
+
+def test_undersized_buckets_are_counted_not_silent():
+    """The bucket transport has a capacity per destination and step; overflowing it is a counted
+    drop (`msgs_dropped`, RA_ST_MSG_DROPPED), like the reference's nosuspend send -- never silent."""
+    from ra_b200.sharded import LocalTransport, Shard, ShardedFlood
+    n, m, gl = 8, 5, 256
+    shards = [Shard(gl, m, n, k, cap=300) for k in range(n)]
+    fl = ShardedFlood(LocalTransport(shards))
+    fl.bootstrap()
+    fl.run(40, 1, 10, seed=31)
+    fl.sync()
+    assert fl.counters()["msgs_dropped"] > 0
