@@ -97,32 +97,32 @@ struct StallCtx {                      // 8 x 16 bytes
 };
 #define STALL_PENDING 1u               // the deferred pipeline pass has not run yet
 
-struct RowLoad { ulonglong2 tc, lg, lw, ap, sn, tk, fm; };
-
-__device__ __forceinline__ void member_init(Member& m, const Cols& C, u32 r, const RowLoad& L, u64 lrs, int cur, u64* sp)
+__device__ __forceinline__ void member_init(Member& m, const Cols& C, u32 r, ulonglong2 tc, ulonglong2 lg, ulonglong2 lw,
+                                            ulonglong2 ap, u64 lrs, int cur, u64* sp)
 {
     m.C = &C; m.row = r; m.slot = r / C.groups; m.group = r - m.slot * C.groups;
-    m.term = L.tc.x; m.commit = L.tc.y; m.last_idx = L.lg.x; m.last_term = L.lg.y;
-    m.lw_idx = L.lw.x; m.lw_term = L.lw.y; m.applied = L.ap.x; m.meta = L.ap.y;
-    m.snap_idx = L.sn.x; m.snap_term = L.sn.y; m.token = L.tk.x; m.token_ctr = L.tk.y;
-    m.first_idx = L.fm.x; m.macver = L.fm.y;
-    m.lrs = lrs; m.lrs_ok = MT_NRUNS(L.ap.y) ? 1u : 0u;
-    m.n_msgs = 0; m.n_notes = 0; m.status = 0; m.fatal_code = 0; m.role0 = MT_ROLE(L.ap.y);
+    m.term = tc.x; m.commit = tc.y; m.last_idx = lg.x; m.last_term = lg.y;
+    m.lw_idx = lw.x; m.lw_term = lw.y; m.applied = ap.x; m.meta = ap.y;
+    m.snap_idx = m.snap_term = m.token = m.token_ctr = m.first_idx = m.macver = 0; m.cold = 0;
+    m.lrs = lrs; m.lrs_ok = MT_NRUNS(ap.y) ? 1u : 0u;
+    m.n_msgs = 0; m.n_notes = 0; m.status = 0; m.fatal_code = 0; m.role0 = MT_ROLE(ap.y);
     m.sent_to = 0; m.pn_type = RA_NOTE_NONE; m.pn_slot = 0; m.pn_a = m.pn_b = m.pn_c = 0;
     m.w_n = 0; m.w0a = m.w0b = m.w0c = m.w1a = m.w1b = m.w1c = 0;
     m.c_events = m.c_msgs = m.c_dropped = m.c_elections = 0; m.c_commits = m.c_applied = 0;
     m.nb = cur ^ 1;
-    m.sp = sp; m.pstate = 0; m.pipe_clean = 0; m.pc_last = m.pc_commit = 0;
+    m.sp = sp; m.pstate = 0; m.pipe_clean = 0;
 }
 
-__device__ __forceinline__ void member_writeback(const Member& m, const Cols& C, u32 r, const RowLoad& L)
+// The four hot pairs change on practically every step of an active row (commit_index,
+// last_index, last_written, last_applied / meta), so they are stored unconditionally: keeping
+// their loaded values around just to skip a store costs 16 registers per thread.
+__device__ __forceinline__ void member_writeback(const Member& m, const Cols& C, u32 r)
 {
-    if (m.term != L.tc.x || m.commit != L.tc.y) st2(&C.tc[r], m.term, m.commit);
-    if (m.last_idx != L.lg.x || m.last_term != L.lg.y) st2(&C.lg[r], m.last_idx, m.last_term);
-    if (m.lw_idx != L.lw.x || m.lw_term != L.lw.y) st2(&C.lw[r], m.lw_idx, m.lw_term);
-    if (m.applied != L.ap.x || m.meta != L.ap.y) st2(&C.ap[r], m.applied, m.meta);
-    if (m.token != L.tk.x || m.token_ctr != L.tk.y) st2(&C.tk[r], m.token, m.token_ctr);
-    if (m.first_idx != L.fm.x) st2(&C.fm[r], m.first_idx, m.macver);
+    st2(&C.tc[r], m.term, m.commit);
+    st2(&C.lg[r], m.last_idx, m.last_term);
+    st2(&C.lw[r], m.lw_idx, m.lw_term);
+    st2(&C.ap[r], m.applied, m.meta);
+    cold_writeback(m);
 }
 
 // end of a row's step: publish mailbox counts, STATUS note, output counts, flood host model
@@ -222,16 +222,15 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     if (blockIdx.x == 0 && tid == 0) *stall_count_next = 0;    // the list of the step after this one
 
     // ---- what does this row have to do? ---------------------------------------------------
-    RowLoad L;
-    L.ap = make_ulonglong2(0, 0);
+    ulonglong2 ap = make_ulonglong2(0, 0);
     u64 cntw = 0; u32 nloc = 0;
     if (valid) {
-        L.ap = C.ap[r];
+        ap = C.ap[r];
         nloc = C.loc_n[r];
         if (C.routed) cntw = C.mbox_cnt[cur][r];
     }
-    const bool fatal0 = MT_FATAL(L.ap.y) != 0;
-    const bool pending = valid && MT_PIPE_PEND(L.ap.y) != 0;
+    const bool fatal0 = MT_FATAL(ap.y) != 0;
+    const bool pending = valid && MT_PIPE_PEND(ap.y) != 0;
     u32 my_mbox = 0, my_loc = 0;
     if (valid && !fatal0) {
         for (u32 s = 0; s < NMEM(C); s++) {
@@ -251,16 +250,17 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     }
     __syncwarp();
 
-    ulonglong2 lr = make_ulonglong2(0, 0);
-    L.tc = L.lg = L.lw = L.sn = L.tk = L.fm = lr;
-    if (work) {
-        L.tc = C.tc[r]; L.lg = C.lg[r]; L.lw = C.lw[r]; L.sn = C.sn[r]; L.tk = C.tk[r]; L.fm = C.fm[r];
-        const u32 nr = MT_NRUNS(L.ap.y);
-        if (nr) lr = C.run[(size_t)(nr - 1) * C.rows + r];
-    }
     Member m;
-    member_init(m, C, valid ? r : 0, L, lr.x, cur, &S.peers[tid]);
-    m.row = r;
+    {
+        ulonglong2 z = make_ulonglong2(0, 0), tc = z, lg = z, lw = z, lr = z;
+        if (work) {
+            tc = C.tc[r]; lg = C.lg[r]; lw = C.lw[r];
+            const u32 nr = MT_NRUNS(ap.y);
+            if (nr) lr = C.run[(size_t)(nr - 1) * C.rows + r];
+        }
+        member_init(m, C, valid ? r : 0, tc, lg, lw, ap, lr.x, cur, &S.peers[tid]);
+        m.row = r;
+    }
 
     const bool live = work && !fatal0;
     bool stalled = false;
@@ -269,8 +269,9 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     // ---- inputs: TMA stages this warp's record tiles through a ring of NST 2 KB slots, in ------
     // evaluation order: deferred pipeline pass, mailbox planes by sender slot then depth, then
     // the host-event planes.  A slot is refilled as soon as the warp has consumed it.
+    u32 rem_mbox = 0, rem_loc = 0;                              // a stalled row's planes not yet evaluated
     if (live && pending) {                                       // pipeline_rpcs is not a fast path
-        stalled = true; stall_flags = STALL_PENDING;
+        stalled = true; stall_flags = STALL_PENDING; rem_mbox = my_mbox; rem_loc = my_loc;
     }
     u64 todo = (u64)w_mbox | ((u64)w_loc << 32);                // planes still to consume
     u64 toissue = todo;                                         // planes still to request
@@ -286,7 +287,6 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             n_issued++;
         }
     }
-    u32 rem_mbox = my_mbox, rem_loc = my_loc;                   // this row's planes not yet evaluated
 #pragma unroll 1
     while (todo) {
         const u32 p = __ffsll((long long)todo) - 1; todo &= todo - 1;
@@ -298,10 +298,11 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             Rec e; e.w0 = sp[lane]; e.w1 = sp[RT + lane]; e.w2 = sp[2 * RT + lane]; e.w3 = sp[3 * RT + lane];
             if (MT_FATAL(m.meta)) m.c_events++;
             else if (C.pure || !fast_event<MM>(m, e)) {
-                stalled = true;
+                stalled = true;                                 // planes are consumed in bit order:
+                if (p < 32) { rem_mbox = my_mbox & ~((1u << p) - 1u); rem_loc = my_loc; }      // p and up
+                else        { rem_mbox = 0; rem_loc = my_loc & ~((1u << (p - 32)) - 1u); }
                 atomicAdd(&C.counters[8 + (m_role(m) & 7u) * 16 + (R_type(e) & 15u)], 1ull);   // diagnostics
             }
-            if (!stalled) { if (p < 32) rem_mbox &= ~(1u << p); else rem_loc &= ~(1u << (p - 32)); }
         }
         n_done++;
         __syncwarp();                                           // every lane is done with slot st
@@ -320,7 +321,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         if (nloc) C.loc_n[r] = 0;
         peers_writeback<MM>(m);
         if (!stalled) k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
-        member_writeback(m, C, r, L);
+        member_writeback(m, C, r);
         k_events = m.c_events; k_commits = m.c_commits; k_applied = m.c_applied;
         k_msgs = m.c_msgs; k_dropped = m.c_dropped; k_elect = m.c_elections;
     }
@@ -362,10 +363,9 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
             const ulonglong2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
             const u32 r = (u32)q0.x, flags = (u32)(q0.x >> 32);
             u32 rem_mbox = (u32)q0.y, rem_loc = (u32)(q0.y >> 32);
-            RowLoad L;
-            L.tc = C.tc[r]; L.lg = C.lg[r]; L.lw = C.lw[r]; L.ap = C.ap[r]; L.sn = C.sn[r]; L.tk = C.tk[r]; L.fm = C.fm[r];
             Member m;
-            member_init(m, C, r, L, 0, cur, &s_peers[tid]);
+            member_init(m, C, r, C.tc[r], C.lg[r], C.lw[r], C.ap[r], 0, cur, &s_peers[tid]);
+            cold_ensure(m);
             m.lrs_ok = 0;
             m.n_msgs = (u32)q1.x; m.n_notes = (u32)(q1.x >> 32); m.status = (u32)q1.y; m.sent_to = (u32)(q1.y >> 32);
             m.pn_type = (u32)q2.x; m.pn_slot = (u32)(q2.x >> 32); m.w_n = (u32)q2.y; m.role0 = (u32)(q2.y >> 32);
@@ -391,7 +391,7 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
             }
             peers_writeback<MM>(m);
             k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
-            member_writeback(m, C, r, L);
+            member_writeback(m, C, r);
             k_events = m.c_events; k_commits = m.c_commits; k_applied = m.c_applied;
             k_msgs = m.c_msgs; k_dropped = m.c_dropped; k_elect = m.c_elections;
         }

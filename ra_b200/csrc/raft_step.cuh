@@ -220,18 +220,38 @@ struct Member {
     // 1 match, 2 commit_index_sent (this thread's column: consecutive lanes, no bank conflicts)
     u64 lrs;                    // start index of the last term run (valid when n_runs > 0 and lrs_ok)
     u32 lrs_ok;
+    // snap_*, token*, first_idx, macver are COLD: the hot kernel does not load them up front;
+    // whoever needs one calls cold_ensure() first (bit0 loaded, bit1 modified)
+    u32 cold;
     // exact shortcut for make_pipelined_rpc_effects: set when a pass found every normal peer with
     // next_index >= next_log_index and commit_index_sent >= commit_index; stays true while only
     // success replies (next/match can only grow) arrive and neither the log nor commit_index move
-    u32 pipe_clean;
-    u64 pc_last, pc_commit;     // the (last_index, commit_index) the flag was computed for
+    u32 pipe_clean;             // cleared wherever last_index or commit_index move
     u64* sp;
     u32 pstate;                 // bit0 loaded, bits 8..15 {next,match} dirty, bits 16..23 commit_sent dirty
 };
 
 __device__ __forceinline__ u32 m_role(const Member& m) { return MT_ROLE(m.meta); }
 __device__ __forceinline__ u32 m_nruns(const Member& m) { return MT_NRUNS(m.meta); }
-__device__ __forceinline__ bool log_nonempty(const Member& m) { return m.first_idx <= m.last_idx; }
+// a member's log view is non-empty iff it holds at least one term run (first_index = start of
+// run 0 then, last_index + 1 otherwise: load_rows enforces it, every mutation keeps it)
+__device__ __forceinline__ bool log_nonempty(const Member& m) { return MT_NRUNS(m.meta) != 0; }
+__device__ __forceinline__ void cold_ensure(Member& m)
+{
+    if (m.cold & 1u) return;
+    const Cols& C = *m.C;
+    const ulonglong2 sn = C.sn[m.row], tk = C.tk[m.row], fm = C.fm[m.row];
+    m.snap_idx = sn.x; m.snap_term = sn.y; m.token = tk.x; m.token_ctr = tk.y;
+    m.first_idx = fm.x; m.macver = fm.y;
+    m.cold |= 1u;
+}
+__device__ __forceinline__ void cold_writeback(const Member& m)
+{
+    if (!(m.cold & 2u)) return;
+    const Cols& C = *m.C;
+    st2(&C.tk[m.row], m.token, m.token_ctr);
+    st2(&C.fm[m.row], m.first_idx, m.macver);
+}
 
 __device__ __forceinline__ ulonglong2 run_get(const Member& m, u32 k)
 { return m.C->run[(size_t)k * m.C->rows + m.row]; }
@@ -275,17 +295,18 @@ __device__ __forceinline__ void peers_writeback(Member& m)
 
 // ---- log view -----------------------------------------------------------------------
 
-// run that holds idx (idx must be in range); returns k, fills start/term/end
+// run that holds idx (idx <= last_index, log non-empty); returns k, fills start/term/end.
+// term = RA_UNDEF when idx lies below the first run, i.e. below first_index.
 __device__ __forceinline__ u32 run_find(const Member& m, u64 idx, u64& start, u64& term, u64& end)
 {
     u32 nr = m_nruns(m);
     u64 e = m.last_idx;
     for (u32 k = nr; k-- > 0;) {
         ulonglong2 r = run_get(m, k);
-        if (r.x <= idx || k == 0) { start = r.x; term = r.y; end = e; return k; }
+        if (r.x <= idx) { start = r.x; term = r.y; end = e; return k; }
         e = r.x - 1;
     }
-    start = m.first_idx; term = m.last_term; end = m.last_idx;
+    start = idx; term = RA_UNDEF; end = e;
     return 0;
 }
 
@@ -294,18 +315,21 @@ __device__ __forceinline__ u64 log_fetch_term(const Member& m, i64 idx)
 {
     if (idx < 0) return RA_UNDEF;
     u64 i = (u64)idx;
-    if (!log_nonempty(m) || i < m.first_idx || i > m.last_idx) return RA_UNDEF;
-    if (i == m.last_idx) return m.last_term;
+    if (!log_nonempty(m) || i > m.last_idx) return RA_UNDEF;
+    if (i == m.last_idx || (m.lrs_ok && i >= m.lrs)) return m.last_term;     // inside the last run
     u64 s, t, e; run_find(m, i, s, t, e);
     return t;
 }
 
 // ra_server:fetch_term/2 (:3158-3169): falls back on the snapshot
-__device__ __forceinline__ u64 srv_fetch_term(const Member& m, i64 idx)
+__device__ __forceinline__ u64 srv_fetch_term(Member& m, i64 idx)
 {
     u64 t = log_fetch_term(m, idx);
     if (t != RA_UNDEF) return t;
-    if (idx >= 0 && MT_HAS_SNAP(m.meta) && m.snap_idx == (u64)idx) return m.snap_term;
+    if (idx >= 0 && MT_HAS_SNAP(m.meta)) {
+        cold_ensure(m);
+        if (m.snap_idx == (u64)idx) return m.snap_term;
+    }
     return RA_UNDEF;
 }
 
@@ -316,13 +340,14 @@ __device__ __forceinline__ void log_append(Member& m, u64 n, u64 term)
     u32 nr = m_nruns(m);
     u64 idx = m.last_idx + 1;
     bool empty = !log_nonempty(m);
-    if (empty) { m.first_idx = idx; nr = 0; }
+    if (empty) { cold_ensure(m); m.first_idx = idx; m.cold |= 2u; nr = 0; }
     if (empty || nr == 0 || term != m.last_term) {
         if (nr == RA_MAX_RUNS) {
             // contract: forget the oldest run (horizon of RA_MAX_RUNS term runs)
             for (u32 k = 0; k + 1 < RA_MAX_RUNS; k++) { ulonglong2 r = run_get(m, k + 1); run_set(m, k, r.x, r.y); }
             nr = RA_MAX_RUNS - 1;
-            m.first_idx = run_get(m, 0).x;
+            cold_ensure(m);
+            m.first_idx = run_get(m, 0).x; m.cold |= 2u;
         }
         run_set(m, nr, idx, term);
         nr++;
@@ -331,6 +356,7 @@ __device__ __forceinline__ void log_append(Member& m, u64 n, u64 term)
     MT_SET(m.meta, 19, 4, nr);
     m.last_idx = idx + n - 1;
     m.last_term = term;
+    m.pipe_clean = 0;                          // next_log_index moved
 }
 
 // drop everything above idx; `fallback_term` is used when idx is no longer inside the log
@@ -339,9 +365,10 @@ __device__ __forceinline__ void log_truncate(Member& m, u64 idx, u64 fallback_te
     u32 nr = m_nruns(m);
     m.lrs_ok = 0;
     while (nr > 0 && run_get(m, nr - 1).x > idx) nr--;
+    cold_ensure(m);
     if (!log_nonempty(m) || idx < m.first_idx) {
         nr = 0;
-        m.first_idx = idx + 1;
+        m.first_idx = idx + 1; m.cold |= 2u;
         m.last_term = fallback_term;
     } else {
         m.last_term = run_get(m, nr - 1).y;
@@ -607,6 +634,7 @@ __device__ __forceinline__ void evaluate_quorum(Member& m)
     for (int i = 1; i < NV; i++) best = (nth == (u32)(i + 1)) ? v[i] : best;
     u64 ci0 = m.commit;
     if (srv_fetch_term(m, (i64)best) == m.term) m.commit = best;        // §5.4.2 gate :3625-3629
+    if (m.commit != ci0) m.pipe_clean = 0;
     if (m.commit > ci0) {
         note(m, RA_NOTE_COMMIT, 0, ci0, m.commit, 0);
         m.c_commits += (u32)(m.commit - ci0);
@@ -631,8 +659,12 @@ __device__ __forceinline__ u64 make_aer(Member& m, u32 peer, i64 prev_idx, u64 p
     u64 from = (u64)(prev_idx + 1);
     u64 to = (u64)prev_idx + num; if (last < to) to = last;
     u32 n = 0, n1 = 0; u64 d = 0, e = 0;
-    if (to >= from && log_nonempty(m) && from >= m.first_idx && from <= m.last_idx) {
-        u64 s, t, end; u32 k = run_find(m, from, s, t, end);
+    u64 s = 0, t = RA_UNDEF, end = 0; u32 k = 0;
+    if (to >= from && log_nonempty(m) && from <= m.last_idx) {
+        if (m.lrs_ok && from >= m.lrs) { s = m.lrs; t = m.last_term; end = m.last_idx; k = m_nruns(m) - 1; }
+        else k = run_find(m, from, s, t, end);
+    }
+    if (t != RA_UNDEF) {                                   // `from` is inside the log
         d = t;
         if (end < to) {                                   // second run; contract: cut after it
             n1 = (u32)(end - from + 1);
@@ -658,6 +690,7 @@ __device__ __forceinline__ u64 make_rpc_effect(Member& m, u32 peer, u64 next, u6
     u64 pt = log_fetch_term(m, prev);
     if (pt != RA_UNDEF) return make_aer<MM>(m, peer, prev, pt, max_batch);
     if (!MT_HAS_SNAP(m.meta)) { set_fatal(m, RA_FATAL_NO_SNAPSHOT); return next; }
+    cold_ensure(m);
     if (prev >= 0 && m.snap_idx == (u64)prev) return make_aer<MM>(m, peer, prev, m.snap_term, max_batch);
     if (!(prev < (i64)m.snap_idx)) { set_fatal(m, RA_FATAL_ASSERT); return next; }
     snapshot = true;
@@ -675,7 +708,7 @@ template <int MM>
 __device__ __forceinline__ bool rpc_pass(Member& m, u32 mode, bool force)
 {
     const Cols& C = *m.C;
-    if (mode == RP_PIPELINE && m.pipe_clean && !force && m.pc_last == m.last_idx && m.pc_commit == m.commit) return false;
+    if (mode == RP_PIPELINE && m.pipe_clean && !force) return false;
     u64 next_log_idx = m.last_idx + 1;
     i64 max_pipe = C.max_pipeline, max_batch = C.max_batch;
     bool more = false, clean = true;
@@ -706,7 +739,7 @@ __device__ __forceinline__ bool rpc_pass(Member& m, u32 mode, bool force)
         if (nn < next_log_idx && nif < max_pipe) more = true;
         if (nn < next_log_idx) clean = false;
     }
-    if (mode == RP_PIPELINE) { m.pipe_clean = clean ? 1u : 0u; m.pc_last = m.last_idx; m.pc_commit = m.commit; }
+    if (mode == RP_PIPELINE) m.pipe_clean = clean ? 1u : 0u;
     return more;
 }
 template <int MM>
@@ -735,6 +768,7 @@ template <int MM>
 __device__ __forceinline__ u32 call_for_election(Member& m, u32 target, NextQ& nq)
 {
     Rec req;
+    cold_ensure(m);
     if (target == RA_CANDIDATE) {
         u64 nt = m.term + 1;
         req = mk_rec(0, RA_EV_REQUEST_VOTE, 0, 0, 0, 0, 0, nt, m.last_idx, m.last_term, 0, 0, 0);
@@ -744,7 +778,7 @@ __device__ __forceinline__ u32 call_for_election(Member& m, u32 target, NextQ& n
         u64 mv = m.macver & 0xffffffffull;
         req = mk_rec(0, RA_EV_PRE_VOTE, 0, 0, 0, 0, 0, m.term, m.last_idx, m.last_term, token, 1ull | (mv << 32), 0);
         update_term_and_voted_for(m, m.term, m.slot);
-        m.token = token;
+        m.token = token; m.cold |= 2u;
     }
     MT_SET(m.meta, 3, 4, SLOT_NONE);       // leader_id => undefined
     MT_SET(m.meta, 15, 4, 0);              // votes => 0
@@ -758,6 +792,7 @@ __device__ __forceinline__ u32 call_for_election(Member& m, u32 target, NextQ& n
 template <int MM>
 __device__ __forceinline__ u32 process_pre_vote(Member& m, u32 fsm, const Rec& e)
 {
+    cold_ensure(m);
     u64 term = R_term(e), token = R_c(e);
     u32 version = (u32)(R_d(e) & 0xffffffffull), their = (u32)(R_d(e) >> 32);
     u32 macver = (u32)(m.macver & 0xffffffffull), eff = (u32)(m.macver >> 32);
@@ -818,8 +853,9 @@ __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& n
                 // drop_existing/3 :3673-3681, run by run instead of entry by entry
                 u64 idx = pl_idx + 1, stop = pl_idx + n0;
                 while (idx <= stop) {
-                    if (!log_nonempty(m) || idx < m.first_idx || idx > m.last_idx) break;
+                    if (!log_nonempty(m) || idx > m.last_idx) break;
                     u64 s, t, end; run_find(m, idx, s, t, end);
+                    if (t == RA_UNDEF) break;
                     bool first_piece = (n1 != 0) && (idx - (pl_idx + 1) < n1);
                     u64 et = (n1 == 0 || first_piece) ? R_d(e) : R_e(e);
                     u64 pe = first_piece ? pl_idx + n1 : stop;
@@ -1204,6 +1240,7 @@ __device__ __forceinline__ void process_event(Member& m, const Rec& in)
 {
     const Cols& C = *m.C;
     peers_ensure<MM>(m);                       // general path: any clause may touch the peer columns
+    cold_ensure(m);                            // ... and the cold pairs
     u32 pend = NX_REDISPATCH, np = 1;          // queue of codes, front = low nibble
     bool chased = false;
     m.c_events++;
