@@ -72,7 +72,8 @@ __device__ __forceinline__ void tma_load_tile(void* dst_smem, const void* src_gm
 template <int MM>
 struct StepSmem {
     ulonglong2 stage[WARPS][NST][4 * RT];
-    u64 peers[3 * PSTR * CTA_T];
+    ulonglong2 peers_nm[PSTR * CTA_T];       // [s][thread] {next_index, match_index}
+    u64 peers_cs[PSTR * CTA_T];              // [s][thread] commit_index_sent (directly behind peers_nm)
     u64 bars[WARPS][NST];
 };
 
@@ -98,7 +99,7 @@ struct StallCtx {                      // 8 x 16 bytes
 #define STALL_PENDING 1u               // the deferred pipeline pass has not run yet
 
 __device__ __forceinline__ void member_init(Member& m, const Cols& C, u32 r, ulonglong2 tc, ulonglong2 lg, ulonglong2 lw,
-                                            ulonglong2 ap, u64 lrs, int cur, u64* sp)
+                                            ulonglong2 ap, u64 lrs, int cur, ulonglong2* sp)
 {
     m.C = &C; m.row = r; m.slot = r / C.groups; m.group = r - m.slot * C.groups;
     m.term = tc.x; m.commit = tc.y; m.last_idx = lg.x; m.last_term = lg.y;
@@ -123,6 +124,7 @@ __device__ __forceinline__ void member_writeback(const Member& m, const Cols& C,
     st2(&C.lw[r], m.lw_idx, m.lw_term);
     st2(&C.ap[r], m.applied, m.meta);
     cold_writeback(m);
+    lrs_writeback(m);
 }
 
 // end of a row's step: publish mailbox counts, STATUS note, output counts, flood host model
@@ -130,13 +132,16 @@ template <int MM>
 __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, int cur, const FloodArgs& F)
 {
     u32 fatal = 0;
-    if (C.routed) {
+    const bool routed = MTR == TR_RUNTIME ? (C.routed != 0) : (MTR != TR_HOST);
+    if (routed) {
+        const bool sharded = MTR == TR_RUNTIME ? (C.n_shards > 1) : (MTR == TR_PEER || MTR == TR_BUCKET);
+        const bool peer = MTR == TR_RUNTIME ? (C.peer_mode != 0) : (MTR == TR_PEER);
         for (u32 s = 0; s < NMEM(C); s++) {
             if (s == m.slot) continue;
             u64* cnt = C.mbox_cnt[cur ^ 1];
-            if (C.n_shards > 1) {
+            if (sharded) {
                 const u32 ds = (C.shard + s + 8u * C.n_shards - m.slot) % C.n_shards;
-                if (C.peer_mode) cnt = C.peer_cnt[cur ^ 1][ds];          // byte store over NVLink
+                if (peer) cnt = C.peer_cnt[cur ^ 1][ds];                 // byte store over NVLink
                 else if (ds != C.shard) continue;   // set when the records are delivered (deliver_kernel)
             }
             reinterpret_cast<u8*>(&cnt[(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
@@ -222,12 +227,15 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     if (blockIdx.x == 0 && tid == 0) *stall_count_next = 0;    // the list of the step after this one
 
     // ---- what does this row have to do? ---------------------------------------------------
-    ulonglong2 ap = make_ulonglong2(0, 0);
-    u64 cntw = 0; u32 nloc = 0;
+    // every per-row input of the step is requested up front, in one round trip to HBM
+    const ulonglong2 z2 = make_ulonglong2(0, 0);
+    ulonglong2 ap = z2, tc = z2, lg = z2, lw = z2;
+    u64 cntw = 0, lrs = 0; u32 nloc = 0;
     if (valid) {
         ap = C.ap[r];
         nloc = C.loc_n[r];
         if (C.routed) cntw = C.mbox_cnt[cur][r];
+        tc = C.tc[r]; lg = C.lg[r]; lw = C.lw[r]; lrs = C.lrs[r];
     }
     const bool fatal0 = MT_FATAL(ap.y) != 0;
     const bool pending = valid && MT_PIPE_PEND(ap.y) != 0;
@@ -251,16 +259,9 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     __syncwarp();
 
     Member m;
-    {
-        ulonglong2 z = make_ulonglong2(0, 0), tc = z, lg = z, lw = z, lr = z;
-        if (work) {
-            tc = C.tc[r]; lg = C.lg[r]; lw = C.lw[r];
-            const u32 nr = MT_NRUNS(ap.y);
-            if (nr) lr = C.run[(size_t)(nr - 1) * C.rows + r];
-        }
-        member_init(m, C, valid ? r : 0, tc, lg, lw, ap, lr.x, cur, &S.peers[tid]);
-        m.row = r;
-    }
+    member_init(m, C, valid ? r : 0, tc, lg, lw, ap, lrs, cur, &S.peers_nm[tid]);
+    m.row = r;
+    if (work && !fatal0 && MT_ROLE(ap.y) == RA_LEADER) peers_prefetch<MM>(m);
 
     const bool live = work && !fatal0;
     bool stalled = false;
@@ -319,6 +320,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     if (work) {
         if (cntw && !fatal0) C.mbox_cnt[cur][r] = 0;
         if (nloc) C.loc_n[r] = 0;
+        if ((m.pstate & 3u) == 2u) asm volatile("cp.async.wait_all;" ::: "memory");   // prefetch never consumed
         peers_writeback<MM>(m);
         if (!stalled) k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
         member_writeback(m, C, r);
@@ -352,7 +354,7 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
                     const StallCtx* __restrict__ stall_list, const u32* __restrict__ stall_count)
 {
     constexpr int MM = MK_MM(0, TR_RUNTIME);
-    __shared__ u64 s_peers[3 * RA_MAX_MEMBERS * CTA_T];
+    __shared__ ulonglong2 s_peers[RA_MAX_MEMBERS * CTA_T + RA_MAX_MEMBERS * CTA_T / 2];   // nm[8][T] then cs[8][T]
     const u32 tid = threadIdx.x, lane = tid & 31u;
     const u32 n = *stall_count;
     for (u32 base = blockIdx.x * CTA_T; base < n; base += gridDim.x * CTA_T) {
@@ -416,6 +418,7 @@ __global__ void reset_empty_kernel(const Cols C)
     st2(&C.cd[r], 0, 0); st2(&C.cd[(size_t)C.rows + r], 0, 0);
     for (u32 s = 0; s < C.members; s++) { st2(&C.pnm[(size_t)s * C.rows + r], 1, 0); C.pcs[(size_t)s * C.rows + r] = 0; }
     for (u32 k = 0; k < RA_MAX_RUNS; k++) st2(&C.run[(size_t)k * C.rows + r], 0, 0);
+    C.lrs[r] = 0;
     C.loc_n[r] = 0; C.out_n[r] = 0;
     if (C.routed) { C.mbox_cnt[0][r] = 0; C.mbox_cnt[1][r] = 0; }
 }
@@ -457,6 +460,7 @@ __global__ void load_rows_kernel(const Cols C, const ra_row_state* in, u32 n)
     }
     for (u32 k = 0; k < RA_MAX_RUNS; k++)
         st2(&C.run[(size_t)k * C.rows + r], k < s.n_runs ? s.run_start[k] : 0, k < s.n_runs ? s.run_term[k] : 0);
+    C.lrs[r] = s.n_runs ? s.run_start[s.n_runs - 1] : 0;
     C.loc_n[r] = 0;
 }
 
@@ -688,7 +692,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         for (int b = 0; b < 2; b++) for (int k = 0; k < 8; k++) { C.peer_mbox[b][k] = nullptr; C.peer_cnt[b][k] = nullptr; }
 #define DA(p, n) if ((rc = dalloc(e, &(p), (n))) != RA_OK) goto bad
         DA(C.tc, R); DA(C.lg, R); DA(C.lw, R); DA(C.ap, R); DA(C.sn, R); DA(C.tk, R); DA(C.fm, R);
-        DA(C.cd, 2 * R); DA(C.pnm, M * R); DA(C.pcs, M * R); DA(C.run, RA_MAX_RUNS * R);
+        DA(C.cd, 2 * R); DA(C.pnm, M * R); DA(C.pcs, M * R); DA(C.run, RA_MAX_RUNS * R); DA(C.lrs, R);
         C.tiles = (u32)((R + RT - 1) / RT);
         const size_t PW = (size_t)C.tiles * 4 * RT;             // 16-byte words per tiled plane
         DA(C.loc, (size_t)RA_LOCAL_CAP * PW); DA(C.loc_n, R);

@@ -83,6 +83,8 @@ struct Cols {
     u64*        pcs;    // commit_index_sent
     // log view: [k][rows] {run_start, run_term}
     ulonglong2* run;
+    u64*        lrs;    // [rows] start index of the LAST run (copy of run[n_runs-1].x; 0 when the log is
+                        // empty): lets the step kernel load it together with the other pairs
     // transport / io.  Input record planes (mailboxes, locals) are TILED: plane p holds, for
     // every tile of 32 consecutive rows (one warp), 4 chunk sub-tiles [chunk j][lane] of
     // 16 bytes, i.e. the 2 KB a warp needs from a plane are contiguous (one cp.async.bulk) and
@@ -113,7 +115,9 @@ struct Cols {
     u64*        peer_cnt[2][8];
 };
 
+#ifndef CTA_T
 #define CTA_T 128                 // threads per CTA (4 independent warps)
+#endif
 #define RT 32                     // rows per record tile = one warp
 // address (in 16-byte words) of chunk j of the record of `row` in tiled plane `plane`
 __device__ __forceinline__ size_t rec_word(u32 tiles, u32 plane, u32 row, u32 j)
@@ -221,13 +225,14 @@ struct Member {
     u64 lrs;                    // start index of the last term run (valid when n_runs > 0 and lrs_ok)
     u32 lrs_ok;
     // snap_*, token*, first_idx, macver are COLD: the hot kernel does not load them up front;
-    // whoever needs one calls cold_ensure() first (bit0 loaded, bit1 modified)
+    // whoever needs one calls cold_ensure() first (bit0 loaded, bit1 modified; bit2: the
+    // last run changed, Cols::lrs has to be rewritten)
     u32 cold;
     // exact shortcut for make_pipelined_rpc_effects: set when a pass found every normal peer with
     // next_index >= next_log_index and commit_index_sent >= commit_index; stays true while only
     // success replies (next/match can only grow) arrive and neither the log nor commit_index move
     u32 pipe_clean;             // cleared wherever last_index or commit_index move
-    u64* sp;
+    ulonglong2* sp;             // &nm[0][thread] of the per-thread peer columns in shared memory
     u32 pstate;                 // bit0 loaded, bits 8..15 {next,match} dirty, bits 16..23 commit_sent dirty
 };
 
@@ -257,39 +262,71 @@ __device__ __forceinline__ ulonglong2 run_get(const Member& m, u32 k)
 { return m.C->run[(size_t)k * m.C->rows + m.row]; }
 __device__ __forceinline__ void run_set(const Member& m, u32 k, u64 start, u64 term)
 { st2(&m.C->run[(size_t)k * m.C->rows + m.row], start, term); }
+__device__ __forceinline__ void lrs_writeback(const Member& m)
+{
+    if (!(m.cold & 4u)) return;
+    const u32 nr = MT_NRUNS(m.meta);
+    m.C->lrs[m.row] = nr ? (m.lrs_ok ? m.lrs : run_get(m, nr - 1).x) : 0ull;
+}
 
+// Per-thread peer columns in shared memory (dynamic peer index without local memory):
+//   nm[s][thread] 16 B {next_index, match_index},  cs[s][thread] 8 B commit_index_sent.
+// m.sp points at nm[0][thread].
+template <int MM>
+__device__ __forceinline__ ulonglong2* peer_nm_p(const Member& m, u32 s) { return m.sp + s * CTA_T; }
+template <int MM>
+__device__ __forceinline__ u64* peer_cs_p(const Member& m, u32 s)
+{ return reinterpret_cast<u64*>(m.sp + PSTR * CTA_T) - threadIdx.x + s * CTA_T; }
+
+// asynchronous global -> shared copies of the row's peer cells (LDGSTS): issued as soon as the
+// role is known, waited for at the first use, so the DRAM latency hides behind the record tiles
+template <int MM>
+__device__ __forceinline__ void peers_prefetch(Member& m)
+{
+    const Cols& C = *m.C;
+    for (u32 s = 0; s < NMEM(C); s++) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::
+                     "r"((u32)__cvta_generic_to_shared(peer_nm_p<MM>(m, s))), "l"(&C.pnm[(size_t)s * C.rows + m.row]) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::
+                     "r"((u32)__cvta_generic_to_shared(peer_cs_p<MM>(m, s))), "l"(&C.pcs[(size_t)s * C.rows + m.row]) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    m.pstate |= 2u;
+}
 template <int MM>
 __device__ __forceinline__ void peers_ensure(Member& m)
 {
     if (m.pstate & 1u) return;
+    if (m.pstate & 2u) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        m.pstate |= 1u;
+        return;
+    }
     const Cols& C = *m.C;
     for (u32 s = 0; s < NMEM(C); s++) {
-        ulonglong2 nm = C.pnm[(size_t)s * C.rows + m.row];
-        m.sp[(0 * PSTR + s) * CTA_T] = nm.x; m.sp[(1 * PSTR + s) * CTA_T] = nm.y;
-        m.sp[(2 * PSTR + s) * CTA_T] = C.pcs[(size_t)s * C.rows + m.row];
+        *peer_nm_p<MM>(m, s) = C.pnm[(size_t)s * C.rows + m.row];
+        *peer_cs_p<MM>(m, s) = C.pcs[(size_t)s * C.rows + m.row];
     }
     m.pstate |= 1u;
 }
 template <int MM>
-__device__ __forceinline__ ulonglong2 peer_nm(Member& m, u32 s)
-{ return make_ulonglong2(m.sp[(0 * PSTR + s) * CTA_T], m.sp[(1 * PSTR + s) * CTA_T]); }
+__device__ __forceinline__ ulonglong2 peer_nm(Member& m, u32 s) { return *peer_nm_p<MM>(m, s); }
 template <int MM>
 __device__ __forceinline__ void peer_nm_set(Member& m, u32 s, u64 next, u64 match)
-{ m.sp[(0 * PSTR + s) * CTA_T] = next; m.sp[(1 * PSTR + s) * CTA_T] = match; m.pstate |= 1u << (8 + s); }
+{ *peer_nm_p<MM>(m, s) = make_ulonglong2(next, match); m.pstate |= 1u << (8 + s); }
 template <int MM>
-__device__ __forceinline__ u64 peer_cs(Member& m, u32 s)
-{ return m.sp[(2 * PSTR + s) * CTA_T]; }
+__device__ __forceinline__ u64 peer_cs(Member& m, u32 s) { return *peer_cs_p<MM>(m, s); }
 template <int MM>
 __device__ __forceinline__ void peer_cs_set(Member& m, u32 s, u64 v)
-{ m.sp[(2 * PSTR + s) * CTA_T] = v; m.pstate |= 1u << (16 + s); }
+{ *peer_cs_p<MM>(m, s) = v; m.pstate |= 1u << (16 + s); }
 template <int MM>
 __device__ __forceinline__ void peers_writeback(Member& m)
 {
     if (!(m.pstate >> 8)) return;
     const Cols& C = *m.C;
     for (u32 s = 0; s < NMEM(C); s++) {
-        if (m.pstate & (1u << (8 + s))) st2(&C.pnm[(size_t)s * C.rows + m.row], m.sp[(0 * PSTR + s) * CTA_T], m.sp[(1 * PSTR + s) * CTA_T]);
-        if (m.pstate & (1u << (16 + s))) C.pcs[(size_t)s * C.rows + m.row] = m.sp[(2 * PSTR + s) * CTA_T];
+        if (m.pstate & (1u << (8 + s))) { ulonglong2 v = *peer_nm_p<MM>(m, s); st2(&C.pnm[(size_t)s * C.rows + m.row], v.x, v.y); }
+        if (m.pstate & (1u << (16 + s))) C.pcs[(size_t)s * C.rows + m.row] = *peer_cs_p<MM>(m, s);
     }
 }
 
@@ -351,7 +388,7 @@ __device__ __forceinline__ void log_append(Member& m, u64 n, u64 term)
         }
         run_set(m, nr, idx, term);
         nr++;
-        m.lrs = idx; m.lrs_ok = 1;
+        m.lrs = idx; m.lrs_ok = 1; m.cold |= 4u;
     }
     MT_SET(m.meta, 19, 4, nr);
     m.last_idx = idx + n - 1;
@@ -363,7 +400,7 @@ __device__ __forceinline__ void log_append(Member& m, u64 n, u64 term)
 __device__ __forceinline__ void log_truncate(Member& m, u64 idx, u64 fallback_term)
 {
     u32 nr = m_nruns(m);
-    m.lrs_ok = 0;
+    m.lrs_ok = 0; m.cold |= 4u;
     while (nr > 0 && run_get(m, nr - 1).x > idx) nr--;
     cold_ensure(m);
     if (!log_nonempty(m) || idx < m.first_idx) {
@@ -620,7 +657,7 @@ __device__ __forceinline__ void evaluate_quorum(Member& m)
         const bool in = (u32)s < M;
         const bool self = (u32)s == m.slot;
         const bool voter = in && !self && MT_VOTER(m.meta, s);
-        v[s] = self ? m.lw_idx : (voter ? m.sp[(1 * PSTR + s) * CTA_T] : 0ull);
+        v[s] = self ? m.lw_idx : (voter ? peer_nm_p<MM>(m, s)->y : 0ull);
         n += voter ? 1u : 0u;
     }
 #pragma unroll
