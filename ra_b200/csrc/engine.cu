@@ -19,12 +19,20 @@
 // the hot kernel
 // ------------------------------------------------------------------------------------------
 #ifndef NST
-#define NST 4                               // shared-memory stages per warp: NST x 2 KB record tiles in flight
+#define NST 3                               // shared-memory stages per warp: NST x 2 KB record tiles in flight
 #endif
 #ifndef MINB
-#define MINB 4                              // CTAs per SM the register allocation is held to
+#define MINB 5                              // CTAs per SM the register allocation is held to: 20 warps,
+                                            // <= 96 registers (no spills), 5 x 39 KB of shared memory
 #endif
 #define TILE_BYTES (RT * 64)
+// bytes of a record tile worth fetching: heads only (chunks 0-1) unless a record of the tile has a tail.
+// tail_mask: bit s = some record from sender slot s, bit 8 + k = host slot k (planes 32..)
+__device__ __forceinline__ unsigned plane_bytes(unsigned tail_mask, unsigned p)
+{
+    const unsigned bit = p < 32 ? (p / RA_MBOX_DEPTH) : (8u + p - 32u);
+    return ((tail_mask >> bit) & 1u) ? TILE_BYTES : TILE_BYTES / 2;
+}
 #define WARPS (CTA_T / 32)
 
 __device__ __forceinline__ u64 warp_sum64(u64 v)
@@ -79,22 +87,18 @@ struct StepSmem {
 
 // ---- the two kernels of a step ---------------------------------------------------------------
 // raft_step_kernel     every row, steady-state fast paths only.  A row whose next event is not
-//                      covered STALLS: it stops, saves its step context (128 B) to a compact list
+//                      covered STALLS: it stops, saves its step context (64 B) to a compact list
 //                      and writes its state back as far as it got.
 // raft_general_kernel  one thread per stalled row (dense, so a rare event does not idle 31
 //                      other lanes): resumes at the stalled event with the general path
 //                      (process_event), runs the row's end-of-step.
 // Both run the same end-of-step code; together they evaluate every event exactly once, in order.
 
-struct StallCtx {                      // 8 x 16 bytes
+struct StallCtx {                      // 4 x 16 bytes
     u32 row, flags, rem_mbox, rem_loc;
-    u32 n_msgs, n_notes, status, sent_to;
-    u32 pn_type, pn_slot, w_n, role0;
+    u32 n_msgs_notes, status, sent_to, pn_type_slot_wk;
     u64 pn_a, pn_b;
-    u64 pn_c, w0a;
-    u64 w0b, w0c;
-    u64 w1a, w1b;
-    u64 w1c, _pad;
+    u64 pn_c, _pad;
 };
 #define STALL_PENDING 1u               // the deferred pipeline pass has not run yet
 
@@ -104,12 +108,11 @@ __device__ __forceinline__ void member_init(Member& m, const Cols& C, u32 r, ulo
     m.C = &C; m.row = r; m.slot = r / C.groups; m.group = r - m.slot * C.groups;
     m.term = tc.x; m.commit = tc.y; m.last_idx = lg.x; m.last_term = lg.y;
     m.lw_idx = lw.x; m.lw_term = lw.y; m.applied = ap.x; m.meta = ap.y;
-    m.snap_idx = m.snap_term = m.token = m.token_ctr = m.first_idx = m.macver = 0; m.cold = 0;
+    m.cold = 0;
     m.lrs = lrs; m.lrs_ok = MT_NRUNS(ap.y) ? 1u : 0u;
-    m.n_msgs = 0; m.n_notes = 0; m.status = 0; m.fatal_code = 0; m.role0 = MT_ROLE(ap.y);
+    m.n_msgs = 0; m.n_notes = 0; m.status = MT_ROLE(ap.y) << 16; m.wk = 0;
     m.sent_to = 0; m.pn_type = RA_NOTE_NONE; m.pn_slot = 0; m.pn_a = m.pn_b = m.pn_c = 0;
-    m.w_n = 0; m.w0a = m.w0b = m.w0c = m.w1a = m.w1b = m.w1c = 0;
-    m.c_events = m.c_msgs = m.c_dropped = m.c_elections = 0; m.c_commits = m.c_applied = 0;
+    m.c_pack = 0; m.c_commits = m.c_applied = 0;
     m.nb = cur ^ 1;
     m.sp = sp; m.pstate = 0; m.pipe_clean = 0;
 }
@@ -123,7 +126,6 @@ __device__ __forceinline__ void member_writeback(const Member& m, const Cols& C,
     st2(&C.lg[r], m.last_idx, m.last_term);
     st2(&C.lw[r], m.lw_idx, m.lw_term);
     st2(&C.ap[r], m.applied, m.meta);
-    cold_writeback(m);
     lrs_writeback(m);
 }
 
@@ -148,11 +150,11 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
         }
     }
     note_flush(m);
-    if (m.status) {
+    if (m.status & 0xffffu) {
         u64 ld = MT_LEADER(m.meta), vf = MT_VOTED(m.meta);
         u64 b = (vf == SLOT_NONE ? 0xFFull : vf) | ((ld == SLOT_NONE ? 0xFFull : ld) << 8) |
-                ((u64)m.role0 << 16) | ((u64)MT_ROLE(m.meta) << 24);
-        note_store(m, m.n_notes, RA_NOTE_STATUS, m.slot, m.status, m.term, b, m.fatal_code);
+                ((u64)((m.status >> 16) & 7u) << 16) | ((u64)MT_ROLE(m.meta) << 24);
+        note_store(m, m.n_notes, RA_NOTE_STATUS, m.slot, m.status & 0xffffu, m.term, b, (m.status >> 20) & 0xffu);
         m.n_notes++;
         if (m.status & RA_ST_FATAL) fatal = 1;
     }
@@ -160,8 +162,18 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
     // flood: synthetic host (DESIGN.md "flood host model")
     if (F.on && !MT_FATAL(m.meta)) {
         u32 k = 0;
-        if (m.w_n == 2) { put_local(C.loc, C.tiles, k, r, RA_EV_WRITTEN, 0, m.w0c, m.w0a, m.w0b); k++; }
-        if (m.w_n >= 1) { put_local(C.loc, C.tiles, k, r, RA_EV_WRITTEN, 0, m.w1c, m.w1a, m.w1b); k++; }
+        // {written, Term, {From, To}} for the (last two) WAL_APPEND notes of this step: read back
+        // from the row's own note slots instead of being carried in registers through the step
+        if ((m.wk & 3u) == 2) {
+            const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&C.onote[(size_t)((m.wk >> 8) & 15u) * C.rows + r]);
+            const ulonglong2 h = q[0], t = q[1];
+            put_local(C.loc, C.tiles, k, r, RA_EV_WRITTEN, 0, t.y, h.y, t.x); k++;
+        }
+        if ((m.wk & 3u) >= 1) {
+            const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&C.onote[(size_t)((m.wk >> 4) & 15u) * C.rows + r]);
+            const ulonglong2 h = q[0], t = q[1];
+            put_local(C.loc, C.tiles, k, r, RA_EV_WRITTEN, 0, t.y, h.y, t.x); k++;
+        }
         const u32 role = MT_ROLE(m.meta);
         if (role == RA_LEADER && F.cmds) { put_local(C.loc, C.tiles, k, r, RA_EV_COMMAND, F.cmds, 0, 0, 0); k++; }
         u32 idle = MT_IDLE(m.meta);
@@ -239,17 +251,20 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     }
     const bool fatal0 = MT_FATAL(ap.y) != 0;
     const bool pending = valid && MT_PIPE_PEND(ap.y) != 0;
-    u32 my_mbox = 0, my_loc = 0;
-    if (valid && !fatal0) {
+    u32 my_mbox = 0, my_loc = 0, my_tail = 0;                   // my_tail: senders (bits 0..7) / host slots (8..)
+    if (valid && !fatal0) {                                     // whose records carry a 32-byte tail
         for (u32 s = 0; s < NMEM(C); s++) {
-            u32 c = (u32)(cntw >> (8 * s)) & 0xffu;
-            my_mbox |= ((1u << c) - 1u) << (RA_MBOX_DEPTH * s);
+            const u32 c = (u32)(cntw >> (8 * s)) & 0xffu;
+            my_mbox |= ((1u << (c & 7u)) - 1u) << (RA_MBOX_DEPTH * s);
+            my_tail |= ((c >> 3) & 1u) << s;
         }
-        my_loc = (1u << nloc) - 1u;
+        my_loc = (1u << (nloc & 7u)) - 1u;
+        my_tail |= nloc & 0xff00u;
     }
     const bool work = valid && (F.on || nloc || cntw || pending);
     // everything below is per warp: no CTA-wide barrier anywhere in this kernel
     const u32 w_mbox = __reduce_or_sync(0xffffffffu, my_mbox), w_loc = __reduce_or_sync(0xffffffffu, my_loc);
+    const u32 w_tail = __reduce_or_sync(0xffffffffu, my_tail);
     if (!__any_sync(0xffffffffu, work)) return;                 // whole warp idle
     u64* bars = &S.bars[warp][0];
     if (lane == 0) {
@@ -283,8 +298,9 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             const u32 p = __ffsll((long long)toissue) - 1; toissue &= toissue - 1;
             const ulonglong2* src = (p < 32) ? C.mbox[cur] + rec_word(C.tiles, p, wtile * RT, 0)
                                              : C.loc + rec_word(C.tiles, p - 32, wtile * RT, 0);
-            mbar_expect_tx(&bars[n_issued], TILE_BYTES);
-            tma_load_tile(&S.stage[warp][n_issued][0], src, TILE_BYTES, &bars[n_issued]);
+            const u32 bytes = plane_bytes(w_tail, p);
+            mbar_expect_tx(&bars[n_issued], bytes);
+            tma_load_tile(&S.stage[warp][n_issued][0], src, bytes, &bars[n_issued]);
             n_issued++;
         }
     }
@@ -296,8 +312,11 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         mbar_wait(&bars[st], (n_done / NST) & 1u);
         if (mine) {
             const ulonglong2* sp = &S.stage[warp][st][0];
-            Rec e; e.w0 = sp[lane]; e.w1 = sp[RT + lane]; e.w2 = sp[2 * RT + lane]; e.w3 = sp[3 * RT + lane];
-            if (MT_FATAL(m.meta)) m.c_events++;
+            const ulonglong2 c0 = sp[lane], c1 = sp[RT + lane];
+            ulonglong2 t2 = make_ulonglong2(0, 0), t3 = t2;
+            if (rec_has_tail(c0)) { t2 = sp[2 * RT + lane]; t3 = sp[3 * RT + lane]; }
+            const Rec e = rec_decode(c0, c1, t2, t3, r);
+            if (MT_FATAL(m.meta)) m.c_pack += 1u;
             else if (C.pure || !fast_event<MM>(m, e)) {
                 stalled = true;                                 // planes are consumed in bit order:
                 if (p < 32) { rem_mbox = my_mbox & ~((1u << p) - 1u); rem_loc = my_loc; }      // p and up
@@ -312,8 +331,9 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             const ulonglong2* src = (q < 32) ? C.mbox[cur] + rec_word(C.tiles, q, wtile * RT, 0)
                                              : C.loc + rec_word(C.tiles, q - 32, wtile * RT, 0);
             fence_proxy_async();                                // slot st was read through the generic proxy
-            mbar_expect_tx(&bars[st], TILE_BYTES);
-            tma_load_tile(&S.stage[warp][st][0], src, TILE_BYTES, &bars[st]);
+            const u32 bytes = plane_bytes(w_tail, q);
+            mbar_expect_tx(&bars[st], bytes);
+            tma_load_tile(&S.stage[warp][st][0], src, bytes, &bars[st]);
         }
     }
 
@@ -324,8 +344,8 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         peers_writeback<MM>(m);
         if (!stalled) k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
         member_writeback(m, C, r);
-        k_events = m.c_events; k_commits = m.c_commits; k_applied = m.c_applied;
-        k_msgs = m.c_msgs; k_dropped = m.c_dropped; k_elect = m.c_elections;
+        k_events = m.c_pack & 0xffu; k_commits = m.c_commits; k_applied = m.c_applied;
+        k_msgs = (m.c_pack >> 8) & 0xffu; k_dropped = m.c_pack >> 20; k_elect = (m.c_pack >> 16) & 15u;
     }
     // stalled rows: hand the rest of the step to raft_general_kernel
     const u32 sm = __ballot_sync(0xffffffffu, stalled);
@@ -336,13 +356,10 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         if (stalled) {
             ulonglong2* q = reinterpret_cast<ulonglong2*>(&stall_list[base + __popc(sm & ((1u << lane) - 1u))]);
             q[0] = make_ulonglong2((u64)r | ((u64)stall_flags << 32), (u64)rem_mbox | ((u64)rem_loc << 32));
-            q[1] = make_ulonglong2((u64)m.n_msgs | ((u64)m.n_notes << 32), (u64)m.status | ((u64)m.sent_to << 32));
-            q[2] = make_ulonglong2((u64)m.pn_type | ((u64)m.pn_slot << 32), (u64)m.w_n | ((u64)m.role0 << 32));
-            q[3] = make_ulonglong2(m.pn_a, m.pn_b);
-            q[4] = make_ulonglong2(m.pn_c, m.w0a);
-            q[5] = make_ulonglong2(m.w0b, m.w0c);
-            q[6] = make_ulonglong2(m.w1a, m.w1b);
-            q[7] = make_ulonglong2(m.w1c, 0);
+            q[1] = make_ulonglong2((u64)(m.n_msgs | (m.n_notes << 16)) | ((u64)m.status << 32),
+                                   (u64)m.sent_to | ((u64)(m.pn_type | (m.pn_slot << 8) | (m.wk << 16)) << 32));
+            q[2] = make_ulonglong2(m.pn_a, m.pn_b);
+            q[3] = make_ulonglong2(m.pn_c, 0);
         }
     }
     flush_counters(C, lane, k_events, k_commits, k_applied, k_msgs, k_dropped, k_elect, k_fatal);
@@ -362,17 +379,16 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
         u32 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
         if (i < n) {
             const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&stall_list[i]);
-            const ulonglong2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
+            const ulonglong2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
             const u32 r = (u32)q0.x, flags = (u32)(q0.x >> 32);
             u32 rem_mbox = (u32)q0.y, rem_loc = (u32)(q0.y >> 32);
             Member m;
             member_init(m, C, r, C.tc[r], C.lg[r], C.lw[r], C.ap[r], 0, cur, &s_peers[tid]);
-            cold_ensure(m);
             m.lrs_ok = 0;
-            m.n_msgs = (u32)q1.x; m.n_notes = (u32)(q1.x >> 32); m.status = (u32)q1.y; m.sent_to = (u32)(q1.y >> 32);
-            m.pn_type = (u32)q2.x; m.pn_slot = (u32)(q2.x >> 32); m.w_n = (u32)q2.y; m.role0 = (u32)(q2.y >> 32);
-            m.pn_a = q3.x; m.pn_b = q3.y; m.pn_c = q4.x; m.w0a = q4.y; m.w0b = q5.x; m.w0c = q5.y;
-            m.w1a = q6.x; m.w1b = q6.y; m.w1c = q7.x;
+            m.n_msgs = (u32)q1.x & 0xffffu; m.n_notes = ((u32)q1.x >> 16) & 0xffffu; m.status = (u32)(q1.x >> 32);
+            m.sent_to = (u32)q1.y;
+            { const u32 w = (u32)(q1.y >> 32); m.pn_type = w & 0xffu; m.pn_slot = (w >> 8) & 0xffu; m.wk = w >> 16; }
+            m.pn_a = q2.x; m.pn_b = q2.y; m.pn_c = q3.x;
             if (flags & STALL_PENDING) {
                 MT_SET(m.meta, 24, 1, 0);
                 process_event<MM>(m, mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
@@ -380,22 +396,22 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
 #pragma unroll 1
             while (rem_mbox) {
                 const u32 p = __ffs(rem_mbox) - 1; rem_mbox &= rem_mbox - 1;
-                const Rec e = ld_rec_tiled(C.mbox[cur], C.tiles, p, r);
-                if (MT_FATAL(m.meta)) m.c_events++;
+                const Rec e = ld_rec_plane(C.mbox[cur], C.tiles, p, r);
+                if (MT_FATAL(m.meta)) m.c_pack += 1u;
                 else if (C.pure || !fast_event<MM>(m, e)) process_event<MM>(m, e);
             }
 #pragma unroll 1
             while (rem_loc) {
                 const u32 p = __ffs(rem_loc) - 1; rem_loc &= rem_loc - 1;
-                const Rec e = ld_rec_tiled(C.loc, C.tiles, p, r);
-                if (MT_FATAL(m.meta)) m.c_events++;
+                const Rec e = ld_rec_plane(C.loc, C.tiles, p, r);
+                if (MT_FATAL(m.meta)) m.c_pack += 1u;
                 else if (C.pure || !fast_event<MM>(m, e)) process_event<MM>(m, e);
             }
             peers_writeback<MM>(m);
             k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
             member_writeback(m, C, r);
-            k_events = m.c_events; k_commits = m.c_commits; k_applied = m.c_applied;
-            k_msgs = m.c_msgs; k_dropped = m.c_dropped; k_elect = m.c_elections;
+            k_events = m.c_pack & 0xffu; k_commits = m.c_commits; k_applied = m.c_applied;
+            k_msgs = (m.c_pack >> 8) & 0xffu; k_dropped = m.c_pack >> 20; k_elect = (m.c_pack >> 16) & 15u;
         }
         flush_counters(C, lane, k_events, k_commits, k_applied, k_msgs, k_dropped, k_elect, k_fatal);
     }
@@ -513,7 +529,10 @@ __global__ void ingest_kernel(const Cols C, const ra_event* ev, u32 n, u32* err)
     while (i + len < n && ev[i + len].row == row && len <= RA_LOCAL_CAP) len++;
     if (len > RA_LOCAL_CAP) { atomicMax(err, 2u); return; }
     if (atomicCAS(&C.loc_n[row], 0u, len) != 0u) { atomicMax(err, 1u); return; }
-    for (u32 k = 0; k < len; k++) st_rec_tiled(C.loc, C.tiles, k, row, ld_rec(&ev[i + k]));
+    u32 tails = 0;
+    for (u32 k = 0; k < len; k++)
+        if (st_rec_plane(C.loc, C.tiles, k, row, ld_rec(&ev[i + k]))) tails |= 0x100u << k;
+    if (tails) atomicOr(&C.loc_n[row], tails);
 }
 
 // records that other shards sent to members of this engine -> mailbox planes of the next step.
@@ -527,15 +546,16 @@ __global__ void deliver_kernel(const Cols C, const int buf, const ra_event* inbo
         const Rec r = ld_rec(&inbox[(size_t)b * cap + i]);
         const u32 row = R_row(r), from = R_from(r), k = (u32)(r.w0.y >> 32);
         if (row >= C.rows || from >= C.members || k >= RA_MBOX_DEPTH) continue;
-        st_rec_tiled(C.mbox[buf], C.tiles, from * RA_MBOX_DEPTH + k, row, r);
-        // byte `from` of the row's count word := max(old, k + 1)
+        const u32 tail = st_rec_plane(C.mbox[buf], C.tiles, from * RA_MBOX_DEPTH + k, row, r) ? 8u : 0u;
+        // byte `from` of the row's count word := max(old count, k + 1) | tail flag
         u32* w = reinterpret_cast<u32*>(&C.mbox_cnt[buf][row]) + (from >> 2);
         const u32 sh = 8u * (from & 3u);
         u32 old = *w;
         for (;;) {
-            if (((old >> sh) & 0xffu) >= k + 1) break;
-            const u32 upd = (old & ~(0xffu << sh)) | ((k + 1) << sh);
-            const u32 seen = atomicCAS(w, old, upd);
+            const u32 ob = (old >> sh) & 0xffu;
+            const u32 nb = ((ob & 7u) >= k + 1 ? (ob & 7u) : k + 1) | (ob & 8u) | tail;
+            if (nb == ob) break;
+            const u32 seen = atomicCAS(w, old, (old & ~(0xffu << sh)) | (nb << sh));
             if (seen == old) break;
             old = seen;
         }

@@ -151,16 +151,59 @@ __device__ __forceinline__ void st_rec(ra_event* p, const Rec& r)
     ulonglong2* q = reinterpret_cast<ulonglong2*>(p);
     q[0] = r.w0; q[1] = r.w1; q[2] = r.w2; q[3] = r.w3;
 }
-__device__ __forceinline__ void st_rec_tiled(ulonglong2* base, u32 tiles, u32 plane, u32 row, const Rec& r)
+// ---- record planes: 32-byte head + optional 32-byte tail ---------------------------------------
+// Inside the engine (mailbox and host-event planes) a record is stored as
+//   chunk 0 {H, term}   chunk 1 {x, y}   [chunk 2 {c, d}   chunk 3 {e, -}]
+//   H = type | from << 8 | flags << 16 | shape << 24 | dbit << 31 | n << 32 | n1 << 48
+// The shape says how a..e are rebuilt -- a lossless re-encoding that does not depend on the type:
+//   RS_LONG   a = x, b = y, c d e from the tail
+//   RS_PLAIN  a = x, b = y, c = d = e = 0                       written, command, vote requests ...
+//   RS_REPLY  a = x, b = y, c = term, d = dbit, e = 0           append_entries_reply in steady state
+//   RS_AER    a = x, b = term, c = y, d = dbit ? term : 0, e = 0  append_entries_rpc in steady state
+// Chunks 0 and 1 of a tile are contiguous (1 KB), so a tile none of whose records has a tail costs
+// half the bytes to write and to fetch; whether a tail exists travels with the record counts
+// (bit 3 of the per-sender count nibble / bits 8.. of loc_n).
+enum { RS_LONG = 0, RS_PLAIN = 1, RS_REPLY = 2, RS_AER = 3 };
+__device__ __forceinline__ bool st_rec_plane(ulonglong2* base, u32 tiles, u32 plane, u32 row, const Rec& r)
 {
+    const u64 term = r.w1.x, a = r.w1.y, b = r.w2.x, c = r.w2.y, d = r.w3.x, e = r.w3.y;
+    u32 shape = RS_LONG, dbit = 0;
+    u64 y = b;
+    if (e == 0) {
+        if ((c | d) == 0) shape = RS_PLAIN;
+        else if (c == term && d <= 1) { shape = RS_REPLY; dbit = (u32)d; }
+        else if (b == term && (d == 0 || d == term)) { shape = RS_AER; y = c; dbit = d != 0; }
+    }
+    const u64 H = ((r.w0.x >> 32) & 0x00FFFFFFull) | ((u64)shape << 24) | ((u64)dbit << 31) | (r.w0.y << 32);
     ulonglong2* q = base + rec_word(tiles, plane, row, 0);
-    q[0] = r.w0; q[RT] = r.w1; q[2 * RT] = r.w2; q[3 * RT] = r.w3;
+    q[0] = make_ulonglong2(H, term); q[RT] = make_ulonglong2(a, y);
+    if (shape != RS_LONG) return false;
+    q[2 * RT] = make_ulonglong2(c, d); q[3 * RT] = make_ulonglong2(e, 0);
+    return true;
 }
-__device__ __forceinline__ Rec ld_rec_tiled(const ulonglong2* base, u32 tiles, u32 plane, u32 row)
+__device__ __forceinline__ bool rec_has_tail(const ulonglong2& c0) { return ((u32)(c0.x >> 24) & 3u) == RS_LONG; }
+__device__ __forceinline__ Rec rec_decode(const ulonglong2& c0, const ulonglong2& c1, const ulonglong2& t2, const ulonglong2& t3, u32 row)
+{
+    const u64 H = c0.x, term = c0.y;
+    const u32 shape = (u32)(H >> 24) & 3u;
+    const u64 dbit = (H >> 31) & 1ull;
+    Rec r;
+    r.w0.x = (u64)row | ((H & 0x00FFFFFFull) << 32);
+    r.w0.y = H >> 32;
+    r.w1.x = term; r.w1.y = c1.x;
+    r.w2.x = shape == RS_AER ? term : c1.y;
+    r.w2.y = shape == RS_LONG ? t2.x : shape == RS_REPLY ? term : shape == RS_AER ? c1.y : 0ull;
+    r.w3.x = shape == RS_LONG ? t2.y : shape == RS_REPLY ? dbit : shape == RS_AER ? (dbit ? term : 0ull) : 0ull;
+    r.w3.y = shape == RS_LONG ? t3.x : 0ull;
+    return r;
+}
+__device__ __forceinline__ Rec ld_rec_plane(const ulonglong2* base, u32 tiles, u32 plane, u32 row)
 {
     const ulonglong2* q = base + rec_word(tiles, plane, row, 0);
-    Rec r; r.w0 = q[0]; r.w1 = q[RT]; r.w2 = q[2 * RT]; r.w3 = q[3 * RT];
-    return r;
+    const ulonglong2 c0 = q[0], c1 = q[RT];
+    ulonglong2 t2 = make_ulonglong2(0, 0), t3 = t2;
+    if (rec_has_tail(c0)) { t2 = q[2 * RT]; t3 = q[3 * RT]; }
+    return rec_decode(c0, c1, t2, t3, row);
 }
 // header word: row | type<<32 | from<<40 | flags<<48 | pad<<56 ; second: n | n1<<16 | seq<<32
 __device__ __forceinline__ u32 R_row(const Rec& r)   { return (u32)r.w0.x; }
@@ -208,25 +251,23 @@ struct Member {
     u32 row, slot, group;
     // scalars (registers)
     u64 term, commit, last_idx, last_term, lw_idx, lw_term, applied, meta;
-    u64 snap_idx, snap_term, token, token_ctr, first_idx, macver;
     // outputs
-    u32 n_msgs, n_notes, status, fatal_code, role0;
+    u32 n_msgs, n_notes;
+    u32 status;                 // RA_ST_* (bits 0-15) | role at the start of the step << 16 | fatal code << 20
+    u32 wk;                     // WAL_APPEND notes of this step: count (0..2) | index of the last << 4 | of the one before << 8
     u32 sent_to;                // 4 bits per peer slot: records put in (me -> slot) this step
     // one note kept back so that a continuing WAL_APPEND / APPLY can merge into it
     u32 pn_type, pn_slot; u64 pn_a, pn_b, pn_c;
     // flood host model: the last two finalised WAL_APPEND notes
-    u32 w_n; u64 w0a, w0b, w0c, w1a, w1b, w1c;
     // counters
-    u32 c_events, c_msgs, c_dropped, c_elections;
+    u32 c_pack;                 // events | msgs << 8 | elections << 16 | dropped << 20
     u32 c_commits, c_applied;   // per row and step: far below 2^32
     int nb;                     // mailbox buffer written this step
     // per-peer columns staged in shared memory on first use: sp[(f*8 + s) * CTA_T], f = 0 next,
     // 1 match, 2 commit_index_sent (this thread's column: consecutive lanes, no bank conflicts)
     u64 lrs;                    // start index of the last term run (valid when n_runs > 0 and lrs_ok)
     u32 lrs_ok;
-    // snap_*, token*, first_idx, macver are COLD: the hot kernel does not load them up front;
-    // whoever needs one calls cold_ensure() first (bit0 loaded, bit1 modified; bit2: the
-    // last run changed, Cols::lrs has to be rewritten)
+    // bit2: the last run changed, Cols::lrs has to be rewritten (bits 0-1 unused)
     u32 cold;
     // exact shortcut for make_pipelined_rpc_effects: set when a pass found every normal peer with
     // next_index >= next_log_index and commit_index_sent >= commit_index; stays true while only
@@ -241,22 +282,17 @@ __device__ __forceinline__ u32 m_nruns(const Member& m) { return MT_NRUNS(m.meta
 // a member's log view is non-empty iff it holds at least one term run (first_index = start of
 // run 0 then, last_index + 1 otherwise: load_rows enforces it, every mutation keeps it)
 __device__ __forceinline__ bool log_nonempty(const Member& m) { return MT_NRUNS(m.meta) != 0; }
-__device__ __forceinline__ void cold_ensure(Member& m)
-{
-    if (m.cold & 1u) return;
-    const Cols& C = *m.C;
-    const ulonglong2 sn = C.sn[m.row], tk = C.tk[m.row], fm = C.fm[m.row];
-    m.snap_idx = sn.x; m.snap_term = sn.y; m.token = tk.x; m.token_ctr = tk.y;
-    m.first_idx = fm.x; m.macver = fm.y;
-    m.cold |= 1u;
-}
-__device__ __forceinline__ void cold_writeback(const Member& m)
-{
-    if (!(m.cold & 2u)) return;
-    const Cols& C = *m.C;
-    st2(&C.tk[m.row], m.token, m.token_ctr);
-    st2(&C.fm[m.row], m.first_idx, m.macver);
-}
+// COLD row fields -- snapshot index/term, pre-vote token and counter, first_index, machine
+// versions -- are not kept in registers at all: the few clauses that need one read it from
+// its column (and write it straight back), which keeps ~12 registers out of the hot kernel.
+__device__ __forceinline__ u64 snap_idx(const Member& m)  { return m.C->sn[m.row].x; }
+__device__ __forceinline__ u64 snap_term(const Member& m) { return m.C->sn[m.row].y; }
+__device__ __forceinline__ u64 tok(const Member& m)       { return m.C->tk[m.row].x; }
+__device__ __forceinline__ u64 tok_ctr(const Member& m)   { return m.C->tk[m.row].y; }
+__device__ __forceinline__ void tok_set(const Member& m, u64 token, u64 ctr) { st2(&m.C->tk[m.row], token, ctr); }
+__device__ __forceinline__ u64 first_idx(const Member& m) { return m.C->fm[m.row].x; }
+__device__ __forceinline__ u64 macver(const Member& m)    { return m.C->fm[m.row].y; }
+__device__ __forceinline__ void first_idx_set(const Member& m, u64 v) { m.C->fm[m.row].x = v; }
 
 __device__ __forceinline__ ulonglong2 run_get(const Member& m, u32 k)
 { return m.C->run[(size_t)k * m.C->rows + m.row]; }
@@ -364,8 +400,7 @@ __device__ __forceinline__ u64 srv_fetch_term(Member& m, i64 idx)
     u64 t = log_fetch_term(m, idx);
     if (t != RA_UNDEF) return t;
     if (idx >= 0 && MT_HAS_SNAP(m.meta)) {
-        cold_ensure(m);
-        if (m.snap_idx == (u64)idx) return m.snap_term;
+        if (snap_idx(m) == (u64)idx) return snap_term(m);
     }
     return RA_UNDEF;
 }
@@ -377,14 +412,13 @@ __device__ __forceinline__ void log_append(Member& m, u64 n, u64 term)
     u32 nr = m_nruns(m);
     u64 idx = m.last_idx + 1;
     bool empty = !log_nonempty(m);
-    if (empty) { cold_ensure(m); m.first_idx = idx; m.cold |= 2u; nr = 0; }
+    if (empty) { first_idx_set(m, idx); nr = 0; }
     if (empty || nr == 0 || term != m.last_term) {
         if (nr == RA_MAX_RUNS) {
             // contract: forget the oldest run (horizon of RA_MAX_RUNS term runs)
             for (u32 k = 0; k + 1 < RA_MAX_RUNS; k++) { ulonglong2 r = run_get(m, k + 1); run_set(m, k, r.x, r.y); }
             nr = RA_MAX_RUNS - 1;
-            cold_ensure(m);
-            m.first_idx = run_get(m, 0).x; m.cold |= 2u;
+            first_idx_set(m, run_get(m, 0).x);
         }
         run_set(m, nr, idx, term);
         nr++;
@@ -402,10 +436,9 @@ __device__ __forceinline__ void log_truncate(Member& m, u64 idx, u64 fallback_te
     u32 nr = m_nruns(m);
     m.lrs_ok = 0; m.cold |= 4u;
     while (nr > 0 && run_get(m, nr - 1).x > idx) nr--;
-    cold_ensure(m);
-    if (!log_nonempty(m) || idx < m.first_idx) {
+    if (!log_nonempty(m) || idx < first_idx(m)) {
         nr = 0;
-        m.first_idx = idx + 1; m.cold |= 2u;
+        first_idx_set(m, idx + 1);
         m.last_term = fallback_term;
     } else {
         m.last_term = run_get(m, nr - 1).y;
@@ -419,16 +452,16 @@ __device__ __forceinline__ bool log_set_last_index(Member& m, u64 idx)
 {
     u64 t = log_fetch_term(m, (i64)idx);
     bool has = MT_HAS_SNAP(m.meta) != 0;
-    bool at_snap = has && m.snap_idx == idx;
+    bool at_snap = has && snap_idx(m) == idx;
     if (t == RA_UNDEF && !at_snap) return false;
     if (at_snap) {
-        log_truncate(m, idx, m.snap_term);
-        m.last_term = m.snap_term;
-        m.lw_idx = m.snap_idx; m.lw_term = m.snap_term;
+        log_truncate(m, idx, snap_term(m));
+        m.last_term = snap_term(m);
+        m.lw_idx = snap_idx(m); m.lw_term = snap_term(m);
         return true;
     }
     u64 lwidx = idx < m.lw_idx ? idx : m.lw_idx;
-    u64 lwterm = (has && m.snap_idx == lwidx) ? m.snap_term : log_fetch_term(m, (i64)lwidx);
+    u64 lwterm = (has && snap_idx(m) == lwidx) ? snap_term(m) : log_fetch_term(m, (i64)lwidx);
     log_truncate(m, idx, t);
     m.last_term = t;
     m.lw_idx = lwidx; m.lw_term = lwterm;
@@ -442,21 +475,21 @@ __device__ __forceinline__ void log_handle_written(Member& m, u64 term, u64 from
     u64 cur = to;
     bool has = MT_HAS_SNAP(m.meta) != 0;
     for (int guard = 0; guard < 2 * RA_MAX_RUNS + 4; guard++) {
-        bool in = log_nonempty(m) && cur >= m.first_idx && cur <= m.last_idx;
+        bool in = log_nonempty(m) && cur >= first_idx(m) && cur <= m.last_idx;
         if (in) {
             u64 s, t, e; run_find(m, cur, s, t, e);
             if (t == term) { m.lw_idx = cur; m.lw_term = term; return; }
-            u64 lo = s > m.first_idx ? s : m.first_idx;      // every index in [lo,cur] mismatches
+            u64 lo = s > first_idx(m) ? s : first_idx(m);      // every index in [lo,cur] mismatches
             if (from > lo) return;                            // the walk ends inside the run
             if (lo == 0 || lo - 1 < from) return;
             cur = lo - 1;
             continue;
         }
-        if (has && cur <= m.snap_idx) return;                 // :871-881
+        if (has && cur <= snap_idx(m)) return;                 // :871-881
         if (cur > m.last_idx) {
             // undefined above the log: the walk either meets the snapshot clause first ...
-            u64 stop = cur < m.snap_idx ? cur : m.snap_idx;
-            if (has && m.snap_idx > m.last_idx && stop >= from) return;
+            u64 stop = cur < snap_idx(m) ? cur : snap_idx(m);
+            if (has && snap_idx(m) > m.last_idx && stop >= from) return;
             // ... or reaches last_index
             if (m.last_idx < from) return;
             cur = m.last_idx;
@@ -471,7 +504,7 @@ __device__ __forceinline__ void log_handle_written(Member& m, u64 term, u64 from
 
 __device__ __forceinline__ void set_fatal(Member& m, u32 code)
 {
-    if (!(m.status & RA_ST_FATAL)) { m.status |= RA_ST_FATAL; m.fatal_code = code; }
+    if (!(m.status & RA_ST_FATAL)) m.status |= RA_ST_FATAL | ((code & 0xffu) << 20);
     MT_SET(m.meta, 26, 1, 1);
 }
 
@@ -491,17 +524,18 @@ __device__ __forceinline__ void note_store(Member& m, u32 k, u32 type, u32 slot,
 // a host ("local") event record into tiled plane k; out of line for the same reason
 __device__ __noinline__ void put_local(ulonglong2* loc, u32 tiles, u32 k, u32 row, u32 type, u32 n, u64 term, u64 a, u64 b)
 {
-    st_rec_tiled(loc, tiles, k, row, mk_rec(row, type, RA_NO_SLOT, 0, n, 0, 0, term, a, b, 0, 0, 0));
+    ulonglong2* q = loc + rec_word(tiles, k, row, 0);               // RS_PLAIN: head only
+    q[0] = make_ulonglong2((u64)type | ((u64)RA_NO_SLOT << 8) | ((u64)RS_PLAIN << 24) | ((u64)(n & 0xffff) << 32), term);
+    q[RT] = make_ulonglong2(a, b);
 }
 
 __device__ __forceinline__ void note_flush(Member& m)
 {
     if (m.pn_type == RA_NOTE_NONE) return;
     note_store(m, m.n_notes - 1, m.pn_type, m.pn_slot, 0, m.pn_a, m.pn_b, m.pn_c);
-    if (m.pn_type == RA_NOTE_WAL_APPEND) {
-        m.w0a = m.w1a; m.w0b = m.w1b; m.w0c = m.w1c;
-        m.w1a = m.pn_a; m.w1b = m.pn_b; m.w1c = m.pn_c;
-        if (m.w_n < 2) m.w_n++;
+    if (m.pn_type == RA_NOTE_WAL_APPEND) {          // the flood host model reads the last two back (row_end_of_step)
+        const u32 n = m.wk & 3u;
+        m.wk = (n < 2 ? n + 1 : 2u) | ((m.n_notes - 1) << 4) | ((m.wk & 0xf0u) << 4);
     }
     m.pn_type = RA_NOTE_NONE;
 }
@@ -528,8 +562,8 @@ __device__ __forceinline__ void emit_msg(Member& m, u32 to, Rec r)
     if (!is_next) R_set_from(r, m.slot);
     R_clear_pad(r);
     if (routed && !is_next) {
-        u32 k = (m.sent_to >> (4 * to)) & 15u;
-        if (k >= RA_MBOX_DEPTH) { m.status |= RA_ST_MSG_DROPPED; m.c_dropped++; return; }
+        u32 k = (m.sent_to >> (4 * to)) & 7u;        // bit 3 of the nibble: some record has a tail
+        if (k >= RA_MBOX_DEPTH) { m.status |= RA_ST_MSG_DROPPED; m.c_pack += 1u << 20; return; }
         R_set_row_seq(r, dst, k);
         const bool sharded = MTR == TR_RUNTIME ? (C.n_shards > 1) : (MTR == TR_PEER || MTR == TR_BUCKET);
         if (sharded) {
@@ -537,9 +571,9 @@ __device__ __forceinline__ void emit_msg(Member& m, u32 to, Rec r)
             const bool peer = MTR == TR_RUNTIME ? (C.peer_mode != 0) : (MTR == TR_PEER);
             if (peer) {
                 // NVLink peer store into the destination GPU's mailbox plane (same local row index)
-                st_rec_tiled(C.peer_mbox[m.nb][ds], C.tiles, m.slot * RA_MBOX_DEPTH + k, dst, r);
+                if (st_rec_plane(C.peer_mbox[m.nb][ds], C.tiles, m.slot * RA_MBOX_DEPTH + k, dst, r)) m.sent_to |= 8u << (4 * to);
                 m.sent_to += 1u << (4 * to);
-                m.c_msgs++;
+                m.c_pack += 1u << 8;
                 return;
             }
             if (ds != C.shard) {
@@ -551,23 +585,23 @@ __device__ __forceinline__ void emit_msg(Member& m, u32 to, Rec r)
                 if ((threadIdx.x & 31u) == ldr) base = atomicAdd(&C.out_cnt[ds], (u32)__popc(grp));
                 base = __shfl_sync(grp, base, ldr);
                 const u32 pos = base + __popc(grp & ((1u << (threadIdx.x & 31u)) - 1u));
-                if (pos >= C.out_cap) { m.status |= RA_ST_MSG_DROPPED; m.c_dropped++; return; }
+                if (pos >= C.out_cap) { m.status |= RA_ST_MSG_DROPPED; m.c_pack += 1u << 20; return; }
                 st_rec(&C.outbox[(size_t)ds * C.out_cap + pos], r);
                 m.sent_to += 1u << (4 * to);
-                m.c_msgs++;
+                m.c_pack += 1u << 8;
                 return;
             }
         }
-        st_rec_tiled(C.mbox[m.nb], C.tiles, m.slot * RA_MBOX_DEPTH + k, dst, r);
+        if (st_rec_plane(C.mbox[m.nb], C.tiles, m.slot * RA_MBOX_DEPTH + k, dst, r)) m.sent_to |= 8u << (4 * to);
         m.sent_to += 1u << (4 * to);
-        m.c_msgs++;
+        m.c_pack += 1u << 8;
         return;
     }
-    if (m.n_msgs >= RA_MSG_CAP) { m.status |= RA_ST_MSG_DROPPED; m.c_dropped++; return; }
+    if (m.n_msgs >= RA_MSG_CAP) { m.status |= RA_ST_MSG_DROPPED; m.c_pack += 1u << 20; return; }
     R_set_row_seq(r, dst, m.n_msgs);
     st_rec(&C.omsg[(size_t)m.n_msgs * C.rows + m.row], r);
     m.n_msgs++;
-    m.c_msgs++;
+    m.c_pack += 1u << 8;
 }
 
 // ---- next-event queue (gen_statem semantics: new next_events go to the front) ----------
@@ -727,12 +761,11 @@ __device__ __forceinline__ u64 make_rpc_effect(Member& m, u32 peer, u64 next, u6
     u64 pt = log_fetch_term(m, prev);
     if (pt != RA_UNDEF) return make_aer<MM>(m, peer, prev, pt, max_batch);
     if (!MT_HAS_SNAP(m.meta)) { set_fatal(m, RA_FATAL_NO_SNAPSHOT); return next; }
-    cold_ensure(m);
-    if (prev >= 0 && m.snap_idx == (u64)prev) return make_aer<MM>(m, peer, prev, m.snap_term, max_batch);
-    if (!(prev < (i64)m.snap_idx)) { set_fatal(m, RA_FATAL_ASSERT); return next; }
+    if (prev >= 0 && snap_idx(m) == (u64)prev) return make_aer<MM>(m, peer, prev, snap_term(m), max_batch);
+    if (!(prev < (i64)snap_idx(m))) { set_fatal(m, RA_FATAL_ASSERT); return next; }
     snapshot = true;
-    note(m, RA_NOTE_SEND_SNAPSHOT, peer, peer, m.snap_idx, 0);
-    return m.snap_idx;
+    note(m, RA_NOTE_SEND_SNAPSHOT, peer, peer, snap_idx(m), 0);
+    return snap_idx(m);
 }
 
 // The leader's three ways of walking its peers share one loop (one inlined copy of
@@ -805,17 +838,16 @@ template <int MM>
 __device__ __forceinline__ u32 call_for_election(Member& m, u32 target, NextQ& nq)
 {
     Rec req;
-    cold_ensure(m);
     if (target == RA_CANDIDATE) {
         u64 nt = m.term + 1;
         req = mk_rec(0, RA_EV_REQUEST_VOTE, 0, 0, 0, 0, 0, nt, m.last_idx, m.last_term, 0, 0, 0);
         update_term_and_voted_for(m, nt, m.slot);
     } else {
-        u64 token = ++m.token_ctr;                                  // make_ref()
-        u64 mv = m.macver & 0xffffffffull;
+        u64 token = tok_ctr(m) + 1;                                 // make_ref()
+        u64 mv = macver(m) & 0xffffffffull;
         req = mk_rec(0, RA_EV_PRE_VOTE, 0, 0, 0, 0, 0, m.term, m.last_idx, m.last_term, token, 1ull | (mv << 32), 0);
         update_term_and_voted_for(m, m.term, m.slot);
-        m.token = token; m.cold |= 2u;
+        tok_set(m, token, token);
     }
     MT_SET(m.meta, 3, 4, SLOT_NONE);       // leader_id => undefined
     MT_SET(m.meta, 15, 4, 0);              // votes => 0
@@ -829,10 +861,10 @@ __device__ __forceinline__ u32 call_for_election(Member& m, u32 target, NextQ& n
 template <int MM>
 __device__ __forceinline__ u32 process_pre_vote(Member& m, u32 fsm, const Rec& e)
 {
-    cold_ensure(m);
     u64 term = R_term(e), token = R_c(e);
     u32 version = (u32)(R_d(e) & 0xffffffffull), their = (u32)(R_d(e) >> 32);
-    u32 macver = (u32)(m.macver & 0xffffffffull), eff = (u32)(m.macver >> 32);
+    const u64 mvs = macver(m);
+    u32 macver = (u32)(mvs & 0xffffffffull), eff = (u32)(mvs >> 32);
     bool send = true, granted = false, tmo = false;
     u64 rterm = term;
     if (term >= m.term) {
@@ -856,7 +888,7 @@ __device__ __forceinline__ u32 has_entry(const Member& m, u64 idx, u64 term)
 {
     u64 t = log_fetch_term(m, (i64)idx);
     if (t == RA_UNDEF) {
-        if (MT_HAS_SNAP(m.meta) && m.snap_idx == idx) return m.snap_term == term ? 0u : 2u;
+        if (MT_HAS_SNAP(m.meta) && snap_idx(m) == idx) return snap_term(m) == term ? 0u : 2u;
         return 1u;
     }
     return t == term ? 0u : 2u;
@@ -931,7 +963,7 @@ __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& n
                 m.commit = leader_commit;
                 if (fst <= m.last_idx) {
                     u64 pt = log_fetch_term(m, (i64)fst - 1);
-                    log_truncate(m, fst - 1, pt != RA_UNDEF ? pt : m.snap_term);
+                    log_truncate(m, fst - 1, pt != RA_UNDEF ? pt : snap_term(m));
                 }
                 // remaining entries fst..stop: at most two term pieces
                 u64 split = (n1 != 0) ? pl_idx + n1 : stop;       // last index of the first piece
@@ -1125,7 +1157,7 @@ __device__ __forceinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& 
                 initialise_peers<MM>(m);
                 MT_SET(m.meta, 15, 4, 0);
                 nq_push(nq, NX_NOOP);
-                m.c_elections++;
+                m.c_pack += 1u << 16;
                 return RA_LEADER;
             }
             MT_SET(m.meta, 15, 4, nv);
@@ -1202,7 +1234,7 @@ __device__ __forceinline__ u32 handle_pre_vote(Member& m, const Rec& e, NextQ& n
             MT_SET(m.meta, 15, 4, 0);
             return RA_FOLLOWER;
         }
-        if (R_d(e) && R_term(e) == m.term && R_c(e) == m.token && MT_MEMBERSHIP(m.meta) == RA_VOTER) {  // :1212-1229
+        if (R_d(e) && R_term(e) == m.term && R_c(e) == tok(m) && MT_MEMBERSHIP(m.meta) == RA_VOTER) {  // :1212-1229
             u32 nv = MT_VOTES(m.meta) + 1;
             if (nv == required_quorum<MM>(m)) return call_for_election<MM>(m, RA_CANDIDATE, nq);
             MT_SET(m.meta, 15, 4, nv);
@@ -1264,7 +1296,7 @@ __device__ __forceinline__ Rec synth_event(const Member& m, u32 code, const Rec&
 {
     switch (code) {
     case NX_PIPELINE:      return mk_rec(m.row, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, RA_EVF_INFO, 0, 0, 0, 0, 0, 0, 0, 0, 0);
-    case NX_SELF_PRE_VOTE: return mk_rec(m.row, RA_EV_PRE_VOTE_RES, m.slot, 0, 0, 0, 0, m.term, 0, 0, m.token, 1, 0);
+    case NX_SELF_PRE_VOTE: return mk_rec(m.row, RA_EV_PRE_VOTE_RES, m.slot, 0, 0, 0, 0, m.term, 0, 0, tok(m), 1, 0);
     case NX_SELF_VOTE:     return mk_rec(m.row, RA_EV_REQUEST_VOTE_RES, m.slot, 0, 0, 0, 0, m.term, 0, 0, 0, 1, 0);
     case NX_NOOP:          return mk_rec(m.row, RA_EV_COMMAND, RA_NO_SLOT, RA_EVF_NOOP, 1, 0, 0, 0, 0, 0, 0, 0, 0);
     case NX_TICK:          return mk_rec(m.row, RA_EV_TICK, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
@@ -1277,10 +1309,9 @@ __device__ __forceinline__ void process_event(Member& m, const Rec& in)
 {
     const Cols& C = *m.C;
     peers_ensure<MM>(m);                       // general path: any clause may touch the peer columns
-    cold_ensure(m);                            // ... and the cold pairs
     u32 pend = NX_REDISPATCH, np = 1;          // queue of codes, front = low nibble
     bool chased = false;
-    m.c_events++;
+    m.c_pack += 1u;
     while (np > 0) {
         if (MT_FATAL(m.meta)) return;
         const u32 code = pend & 15u;
@@ -1364,7 +1395,7 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
             if (R_term(e) != m.term || R_n1(e) != 0 || !nonempty || R_a(e) != m.last_idx || R_b(e) != m.last_term) return false;
             const u32 n = R_n(e);
             if (n != 0 && (R_d(e) != m.last_term || m.last_idx + 1 < m.applied)) return false;
-            m.c_events++;
+            m.c_pack += 1u;
             leader = R_from(e);
             m.status |= RA_ST_LEADER_MSG;
             MT_SET(m.meta, 3, 4, leader);
@@ -1382,20 +1413,20 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
             // (every index of the last run has term last_term: ra_log:fetch_term(To) == Term)
             if (nonempty && !m.lrs_ok) { m.lrs = run_get(m, m_nruns(m) - 1).x; m.lrs_ok = 1; }
             if (!nonempty || !m.lrs_ok || R_term(e) != m.last_term || R_b(e) > m.last_idx || R_b(e) < m.lrs) return false;
-            m.c_events++;
+            m.c_pack += 1u;
             reply = (m.lw_idx != R_b(e) || m.lw_term != m.last_term) && leader != SLOT_NONE;
             reply_term = m.term;
             m.lw_idx = R_b(e); m.lw_term = m.last_term;
         } else if (type == RA_EV_PRE_VOTE) {                           // :1459-1466
-            m.c_events++;
+            m.c_pack += 1u;
             if (MT_MEMBERSHIP(m.meta) == RA_VOTER) (void)process_pre_vote<MM>(m, RA_FOLLOWER, e);
         } else if (type == RA_EV_PRE_VOTE_RES || type == RA_EV_REQUEST_VOTE_RES) {   // :1593-1598: ignored
-            m.c_events++;
+            m.c_pack += 1u;
         } else if (type == RA_EV_ELECTION_TIMEOUT) {
             // :1603-1610 -> call_for_election(pre_vote) :2873-2897, then the queued vote for self
             // (handle_pre_vote :1212-1229): one vote, which is not yet a quorum
             if (MT_MEMBERSHIP(m.meta) != RA_VOTER || required_quorum<MM>(m) == 1 || m.C->pure) return false;
-            m.c_events++;
+            m.c_pack += 1u;
             NextQ nq; nq.codes = 0; nq.n = 0;
             (void)call_for_election<MM>(m, RA_PRE_VOTE, nq);
             MT_SET(m.meta, 0, 3, RA_PRE_VOTE);
@@ -1408,7 +1439,7 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
     }
     if (role == RA_LEADER) {
         if (type == RA_EV_PRE_VOTE_RES || type == RA_EV_REQUEST_VOTE_RES) {   // :958-963: ignored
-            m.c_events++;
+            m.c_pack += 1u;
             return true;
         }
         peers_ensure<MM>(m);              // the ONE place the hot kernel stages the peer columns
@@ -1416,12 +1447,12 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
         u32 mode = RP_PIPELINE;
         if (type == RA_EV_PRE_VOTE) {                                  // :952-957 enforce leadership
             if (R_term(e) > m.term) return false;
-            m.c_events++;
+            m.c_pack += 1u;
             mode = RP_ALL;
         } else if (type == RA_EV_COMMAND) {                            // :644-729
             const u64 n = R_n(e);
             if (n == 0 || !nonempty) return false;
-            m.c_events++;
+            m.c_pack += 1u;
             const u64 from = m.last_idx + 1;
             log_append(m, n, m.term);
             note(m, RA_NOTE_WAL_APPEND, 0, from, from + n - 1, m.term);
@@ -1429,13 +1460,13 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
         } else if (type == RA_EV_WRITTEN) {                            // :730-735
             if (nonempty && !m.lrs_ok) { m.lrs = run_get(m, m_nruns(m) - 1).x; m.lrs_ok = 1; }
             if (!nonempty || !m.lrs_ok || R_term(e) != m.last_term || R_b(e) > m.last_idx || R_b(e) < m.lrs) return false;
-            m.c_events++;
+            m.c_pack += 1u;
             m.lw_idx = R_b(e); m.lw_term = m.last_term;
             quorum = chase = true;
         } else if (type == RA_EV_AER_REPLY) {                          // :522-561
             const u32 from = R_from(e);
             if (!(R_d(e) != 0 && R_term(e) == m.term && from < NMEM(*m.C))) return false;
-            m.c_events++;
+            m.c_pack += 1u;
             ulonglong2 nm = peer_nm<MM>(m, from);
             peer_nm_set<MM>(m, from, R_a(e) > nm.x ? R_a(e) : nm.x, R_b(e) > nm.y ? R_b(e) : nm.y);
             quorum = chase = true;
