@@ -224,6 +224,15 @@ __device__ __forceinline__ void flush_counters(const Cols& C, u32 lane, u32 k_ev
     }
 }
 
+// plane bit masks: 32 bits cover groups of up to 7 members, the generic kernel needs 36
+template <bool SMALL> struct PlaneMask { typedef u32 type; };
+template <> struct PlaneMask<false> { typedef u64 type; };
+__device__ __forceinline__ u32 mask_ffs(u32 m) { return (u32)__ffs((int)m) - 1u; }
+__device__ __forceinline__ u32 mask_ffs(u64 m) { return (u32)__ffsll((long long)m) - 1u; }
+__device__ __forceinline__ u32 mask_or_warp(u32 m) { return __reduce_or_sync(0xffffffffu, m); }
+__device__ __forceinline__ u64 mask_or_warp(u64 m)
+{ return (u64)__reduce_or_sync(0xffffffffu, (u32)m) | ((u64)__reduce_or_sync(0xffffffffu, (u32)(m >> 32)) << 32); }
+
 template <int MM>
 __global__ void __launch_bounds__(CTA_T, MINB)
 raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F,
@@ -251,19 +260,24 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     }
     const bool fatal0 = MT_FATAL(ap.y) != 0;
     const bool pending = valid && MT_PIPE_PEND(ap.y) != 0;
-    u32 my_mbox = 0, my_loc = 0, my_tail = 0;                   // my_tail: senders (bits 0..7) / host slots (8..)
+    // planes of this row: mailbox plane (sender s, depth k) = bit s * DEPTH + k, host slot k = bit NPM + k
+    constexpr u32 NPM = (MMEM ? MMEM : RA_MAX_MEMBERS) * RA_MBOX_DEPTH;
+    typedef typename PlaneMask<(NPM + RA_LOCAL_CAP <= 32)>::type mask_t;
+    mask_t mine = 0;
+    u32 my_tail = 0;                                            // senders (bits 0..7) / host slots (8..)
     if (valid && !fatal0) {                                     // whose records carry a 32-byte tail
+        u32 mb = 0;
         for (u32 s = 0; s < NMEM(C); s++) {
             const u32 c = (u32)(cntw >> (8 * s)) & 0xffu;
-            my_mbox |= ((1u << (c & 7u)) - 1u) << (RA_MBOX_DEPTH * s);
+            mb |= ((1u << (c & 7u)) - 1u) << (RA_MBOX_DEPTH * s);
             my_tail |= ((c >> 3) & 1u) << s;
         }
-        my_loc = (1u << (nloc & 7u)) - 1u;
+        mine = (mask_t)mb | ((mask_t)((1u << (nloc & 7u)) - 1u) << NPM);
         my_tail |= nloc & 0xff00u;
     }
     const bool work = valid && (F.on || nloc || cntw || pending);
     // everything below is per warp: no CTA-wide barrier anywhere in this kernel
-    const u32 w_mbox = __reduce_or_sync(0xffffffffu, my_mbox), w_loc = __reduce_or_sync(0xffffffffu, my_loc);
+    mask_t todo = mask_or_warp(mine);                           // planes still to consume
     const u32 w_tail = __reduce_or_sync(0xffffffffu, my_tail);
     if (!__any_sync(0xffffffffu, work)) return;                 // whole warp idle
     u64* bars = &S.bars[warp][0];
@@ -278,39 +292,40 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     m.row = r;
     if (work && !fatal0 && MT_ROLE(ap.y) == RA_LEADER) peers_prefetch<MM>(m);
 
-    const bool live = work && !fatal0;
     bool stalled = false;
     u32 stall_flags = 0;
 
     // ---- inputs: TMA stages this warp's record tiles through a ring of NST 2 KB slots, in ------
     // evaluation order: deferred pipeline pass, mailbox planes by sender slot then depth, then
     // the host-event planes.  A slot is refilled as soon as the warp has consumed it.
-    u32 rem_mbox = 0, rem_loc = 0;                              // a stalled row's planes not yet evaluated
-    if (live && pending) {                                       // pipeline_rpcs is not a fast path
-        stalled = true; stall_flags = STALL_PENDING; rem_mbox = my_mbox; rem_loc = my_loc;
+    mask_t rem = 0;                                             // a stalled row's planes not yet evaluated
+    if (work && !fatal0 && pending) {                           // pipeline_rpcs is not a fast path
+        stalled = true; stall_flags = STALL_PENDING; rem = mine;
     }
-    u64 todo = (u64)w_mbox | ((u64)w_loc << 32);                // planes still to consume
-    u64 toissue = todo;                                         // planes still to request
-    u32 n_issued = 0, n_done = 0;
-    if (lane == 0) {
-#pragma unroll 1
-        while (toissue && n_issued < NST) {
-            const u32 p = __ffsll((long long)toissue) - 1; toissue &= toissue - 1;
-            const ulonglong2* src = (p < 32) ? C.mbox[cur] + rec_word(C.tiles, p, wtile * RT, 0)
-                                             : C.loc + rec_word(C.tiles, p - 32, wtile * RT, 0);
-            const u32 bytes = plane_bytes(w_tail, p);
-            mbar_expect_tx(&bars[n_issued], bytes);
-            tma_load_tile(&S.stage[warp][n_issued][0], src, bytes, &bars[n_issued]);
-            n_issued++;
-        }
-    }
+    mask_t toissue = todo;                                      // planes still to request
+    u32 n_issued = 0, n_done = 0, st_issue = 0, st = 0, par = 0; // ring positions = counters mod NST, phase parity
+    const size_t plane_words = (size_t)C.tiles * (4 * RT);      // 16-byte words per plane
+    const ulonglong2* const mb_base = C.mbox[cur] + (size_t)wtile * (4 * RT);
+    const ulonglong2* const lc_base = C.loc + (size_t)wtile * (4 * RT) - (size_t)NPM * plane_words;
 #pragma unroll 1
     while (todo) {
-        const u32 p = __ffsll((long long)todo) - 1; todo &= todo - 1;
-        const u32 st = n_done % NST;
-        const bool mine = !stalled && ((p < 32) ? ((my_mbox >> p) & 1u) : ((my_loc >> (p - 32)) & 1u));
-        mbar_wait(&bars[st], (n_done / NST) & 1u);
-        if (mine) {
+        if (lane == 0) {
+#pragma unroll 1
+            while (toissue && n_issued < n_done + NST) {
+                const u32 q = mask_ffs(toissue); toissue &= toissue - 1;
+                const ulonglong2* src = (q < NPM ? mb_base : lc_base) + (size_t)q * plane_words;
+                const u32 tbit = q < NPM ? q / RA_MBOX_DEPTH : 8u + q - NPM;
+                const u32 bytes = ((w_tail >> tbit) & 1u) ? TILE_BYTES : TILE_BYTES / 2;
+                fence_proxy_async();                            // the slot was read through the generic proxy
+                mbar_expect_tx(&bars[st_issue], bytes);
+                tma_load_tile(&S.stage[warp][st_issue][0], src, bytes, &bars[st_issue]);
+                n_issued++; st_issue = st_issue + 1 == NST ? 0 : st_issue + 1;
+            }
+        }
+        const u32 p = mask_ffs(todo); todo &= todo - 1;
+        const bool my = !stalled && ((mine >> p) & 1u);
+        mbar_wait(&bars[st], par);
+        if (my) {
             const ulonglong2* sp = &S.stage[warp][st][0];
             const ulonglong2 c0 = sp[lane], c1 = sp[RT + lane];
             ulonglong2 t2 = make_ulonglong2(0, 0), t3 = t2;
@@ -319,23 +334,15 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             if (MT_FATAL(m.meta)) m.c_pack += 1u;
             else if (C.pure || !fast_event<MM>(m, e)) {
                 stalled = true;                                 // planes are consumed in bit order:
-                if (p < 32) { rem_mbox = my_mbox & ~((1u << p) - 1u); rem_loc = my_loc; }      // p and up
-                else        { rem_mbox = 0; rem_loc = my_loc & ~((1u << (p - 32)) - 1u); }
+                rem = mine & ~(((mask_t)1 << p) - 1);           // p and up are left for the general kernel
                 atomicAdd(&C.counters[8 + (m_role(m) & 7u) * 16 + (R_type(e) & 15u)], 1ull);   // diagnostics
             }
         }
         n_done++;
-        __syncwarp();                                           // every lane is done with slot st
-        if (lane == 0 && toissue) {
-            const u32 q = __ffsll((long long)toissue) - 1; toissue &= toissue - 1;
-            const ulonglong2* src = (q < 32) ? C.mbox[cur] + rec_word(C.tiles, q, wtile * RT, 0)
-                                             : C.loc + rec_word(C.tiles, q - 32, wtile * RT, 0);
-            fence_proxy_async();                                // slot st was read through the generic proxy
-            const u32 bytes = plane_bytes(w_tail, q);
-            mbar_expect_tx(&bars[st], bytes);
-            tma_load_tile(&S.stage[warp][st][0], src, bytes, &bars[st]);
-        }
+        if (++st == NST) { st = 0; par ^= 1u; }
+        __syncwarp();                                           // every lane is done with the slot
     }
+    const u32 rem_mbox = (u32)(rem & (((mask_t)1 << (NPM - 1) << 1) - 1)), rem_loc = (u32)(rem >> (NPM - 1) >> 1);
 
     if (work) {
         if (cntw && !fatal0) C.mbox_cnt[cur][r] = 0;
