@@ -219,11 +219,46 @@ def run_engine(args):
                 torch.cuda.synchronize(dev)
                 return dict(seconds=time.perf_counter() - t_0, h2d_bytes=h2d, d2h_bytes=d2h)
         else:
-            eng2 = Engine(G, M, device=dev, route_on_device=True)
-            eng2.reset_empty()
-            hf = HostFlood(eng2)
-            hf.run(0, args.cmds, args.permille, seed=seed, bootstrap=True)
-            host_steps = lambda n: hf.run(n, args.cmds, args.permille, seed=seed)
+            # K independent engines (disjoint groups) driven from K host threads: while one engine's notes
+            # travel device->host and its host model runs, another engine's events travel host->device
+            # (PCIe is full duplex) and its kernels run.  Every step still goes through ra_engine_step.
+            import threading
+            K = max(1, min(args.e2e_engines, G))
+            engs = [Engine(G // K + (1 if i < G % K else 0), M, device=dev, route_on_device=True) for i in range(K)]
+            hfs = [HostFlood(e_) for e_ in engs]
+            for e_, h_ in zip(engs, hfs):
+                e_.reset_empty()
+                h_.run(0, args.cmds, args.permille, seed=seed, bootstrap=True)
+
+            def host_steps(n):
+                res = [None] * K
+                def work(i):
+                    res[i] = hfs[i].run(n, args.cmds, args.permille, seed=seed + i)
+                t_0 = time.perf_counter()
+                ths = [threading.Thread(target=work, args=(i,)) for i in range(K)]
+                for t_ in ths: t_.start()
+                for t_ in ths: t_.join()
+                wall = time.perf_counter() - t_0
+                return dict(seconds=wall, h2d_bytes=sum(r_["h2d_bytes"] for r_ in res),
+                            d2h_bytes=sum(r_["d2h_bytes"] for r_ in res),
+                            step_seconds=max(r_["step_seconds"] for r_ in res),
+                            model_seconds=max(r_["model_seconds"] for r_ in res))
+
+            class _Multi:                                   # counters / close over all K engines
+                def counters(self):
+                    tot = {}
+                    for e_ in engs:
+                        for k_, v_ in e_.counters().items():
+                            tot[k_] = tot.get(k_, 0) + v_
+                    return tot
+                def close(self):
+                    for e_ in engs: e_.close()
+            eng2 = _Multi()
+
+            class _MultiHf:
+                def close(self):
+                    for h_ in hfs: h_.close()
+            hf = _MultiHf()
         host_steps(args.settle)
         host_steps(min(args.warmup, 10))
         d0 = eng2.counters()
@@ -238,7 +273,8 @@ def run_engine(args):
                "steps": args.e2e_steps, "ms_per_step": sec * 1e3 / args.e2e_steps,
                "engine_call_ms_per_step": st.get("step_seconds", 0.0) * 1e3 / args.e2e_steps,
                "host_model_ms_per_step": st.get("model_seconds", 0.0) * 1e3 / args.e2e_steps,
-               "gpu_launches_per_step": 7 + (3 if spread else 0)}
+               "gpu_launches_per_step": (7 + 3) if spread else 7 * max(1, min(args.e2e_engines, G)),
+               "engines": 1 if spread else max(1, min(args.e2e_engines, G))}
         hf.close()
         eng2.close()
 
@@ -339,6 +375,8 @@ def main():
     ap.add_argument("--settle", type=int, default=40, help="untimed steps to elect leaders and fill the pipeline")
     ap.add_argument("--seed", type=int, default=0xA00)
     ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--e2e-engines", type=int, default=1,
+                    help="e2e leg at N=1: independent engines (disjoint groups) driven by as many host threads")
     ap.add_argument("--cpu-groups", type=int, default=20_000)
     ap.add_argument("--cpu-steps", type=int, default=100)
     ap.add_argument("--placement", default="spread", choices=["spread", "group"],
@@ -352,10 +390,19 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_engine(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_engine(args)
+    finally:
+        sys.stdout.flush()
+        try:                                   # no "destroy_process_group() was not called" noise after the JSON line
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 if __name__ == "__main__":

@@ -105,7 +105,13 @@ struct StallCtx {                      // 4 x 16 bytes
 __device__ __forceinline__ void member_init(Member& m, const Cols& C, u32 r, ulonglong2 tc, ulonglong2 lg, ulonglong2 lw,
                                             ulonglong2 ap, u64 lrs, int cur, ulonglong2* sp)
 {
-    m.C = &C; m.row = r; m.slot = r / C.groups; m.group = r - m.slot * C.groups;
+    m.C = &C; m.row = r;
+    {   // slot = r / groups through the precomputed reciprocal floor(2^32 / groups): off by at most one
+        u32 q = __umulhi(r, C.groups_inv), rem = r - q * C.groups;
+        if (rem >= C.groups) { q++; rem -= C.groups; }
+        if (rem >= C.groups) { q++; rem -= C.groups; }
+        m.slot = q; m.group = rem;
+    }
     m.term = tc.x; m.commit = tc.y; m.last_idx = lg.x; m.last_term = lg.y;
     m.lw_idx = lw.x; m.lw_term = lw.y; m.applied = ap.x; m.meta = ap.y;
     m.cold = 0;
@@ -399,20 +405,21 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
             if (flags & STALL_PENDING) {
                 MT_SET(m.meta, 24, 1, 0);
                 process_event<MM>(m, mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+                m.cold &= ~8u;
             }
 #pragma unroll 1
             while (rem_mbox) {
                 const u32 p = __ffs(rem_mbox) - 1; rem_mbox &= rem_mbox - 1;
                 const Rec e = ld_rec_plane(C.mbox[cur], C.tiles, p, r);
                 if (MT_FATAL(m.meta)) m.c_pack += 1u;
-                else if (C.pure || !fast_event<MM>(m, e)) process_event<MM>(m, e);
+                else if (C.pure || !fast_event<MM>(m, e)) { process_event<MM>(m, e); m.cold &= ~8u; }
             }
 #pragma unroll 1
             while (rem_loc) {
                 const u32 p = __ffs(rem_loc) - 1; rem_loc &= rem_loc - 1;
                 const Rec e = ld_rec_plane(C.loc, C.tiles, p, r);
                 if (MT_FATAL(m.meta)) m.c_pack += 1u;
-                else if (C.pure || !fast_event<MM>(m, e)) process_event<MM>(m, e);
+                else if (C.pure || !fast_event<MM>(m, e)) { process_event<MM>(m, e); m.cold &= ~8u; }
             }
             peers_writeback<MM>(m);
             k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
@@ -711,6 +718,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         Cols& C = e->C;
         const size_t R = (size_t)cfg->n_groups * cfg->n_members, M = cfg->n_members;
         C.rows = (u32)R; C.groups = cfg->n_groups; C.members = cfg->n_members;
+        C.groups_inv = cfg->n_groups > 1 ? (u32)(0x100000000ull / cfg->n_groups) : 0xFFFFFFFFu;
         C.max_pipeline = e->cfg.max_pipeline_count; C.max_batch = e->cfg.max_aer_batch;
         C.routed = cfg->route_on_device ? 1 : 0; C.pure = cfg->pure ? 1 : 0;
         C.n_shards = cfg->n_shards > 1 ? cfg->n_shards : 1; C.shard = cfg->n_shards > 1 ? cfg->shard : 0;

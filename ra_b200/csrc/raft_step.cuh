@@ -99,6 +99,7 @@ struct Cols {
     u32*      out_n;    // [rows] msgs | notes << 16
     u64*      counters; // ra_counters as 8 x u64, then [8 + role*16 + type]: events that left the fast kernel
     u32 rows, groups, members;
+    u32 groups_inv;        // floor(2^32 / groups)
     u32 max_pipeline, max_batch;
     u32 routed, pure;
     // cross-shard transport (n_shards > 1): member (g, s) lives on shard (g + s) mod N at local
@@ -267,7 +268,8 @@ struct Member {
     // 1 match, 2 commit_index_sent (this thread's column: consecutive lanes, no bank conflicts)
     u64 lrs;                    // start index of the last term run (valid when n_runs > 0 and lrs_ok)
     u32 lrs_ok;
-    // bit2: the last run changed, Cols::lrs has to be rewritten (bits 0-1 unused)
+    // bit2: the last run changed, Cols::lrs has to be rewritten; bit3: evaluate_quorum ran in this
+    // step and none of its inputs (last_written, match indexes, log tail) moved since
     u32 cold;
     // exact shortcut for make_pipelined_rpc_effects: set when a pass found every normal peer with
     // next_index >= next_log_index and commit_index_sent >= commit_index; stays true while only
@@ -428,13 +430,14 @@ __device__ __forceinline__ void log_append(Member& m, u64 n, u64 term)
     m.last_idx = idx + n - 1;
     m.last_term = term;
     m.pipe_clean = 0;                          // next_log_index moved
+    m.cold &= ~8u;                             // apply_to may reach further now
 }
 
 // drop everything above idx; `fallback_term` is used when idx is no longer inside the log
 __device__ __forceinline__ void log_truncate(Member& m, u64 idx, u64 fallback_term)
 {
     u32 nr = m_nruns(m);
-    m.lrs_ok = 0; m.cold |= 4u;
+    m.lrs_ok = 0; m.cold = (m.cold | 4u) & ~8u;
     while (nr > 0 && run_get(m, nr - 1).x > idx) nr--;
     if (!log_nonempty(m) || idx < first_idx(m)) {
         nr = 0;
@@ -711,6 +714,7 @@ __device__ __forceinline__ void evaluate_quorum(Member& m)
         m.c_commits += (u32)(m.commit - ci0);
     }
     apply_to(m, m.commit);
+    m.cold |= 8u;
 }
 
 // evaluate_commit_index_follower/2 :2229-2263
@@ -1309,6 +1313,7 @@ __device__ __forceinline__ void process_event(Member& m, const Rec& in)
 {
     const Cols& C = *m.C;
     peers_ensure<MM>(m);                       // general path: any clause may touch the peer columns
+    m.cold &= ~8u;                             // ... or an input of evaluate_quorum
     u32 pend = NX_REDISPATCH, np = 1;          // queue of codes, front = low nibble
     bool chased = false;
     m.c_pack += 1u;
@@ -1462,16 +1467,19 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
             if (!nonempty || !m.lrs_ok || R_term(e) != m.last_term || R_b(e) > m.last_idx || R_b(e) < m.lrs) return false;
             m.c_pack += 1u;
             m.lw_idx = R_b(e); m.lw_term = m.last_term;
+            m.cold &= ~8u;
             quorum = chase = true;
         } else if (type == RA_EV_AER_REPLY) {                          // :522-561
             const u32 from = R_from(e);
             if (!(R_d(e) != 0 && R_term(e) == m.term && from < NMEM(*m.C))) return false;
             m.c_pack += 1u;
             ulonglong2 nm = peer_nm<MM>(m, from);
+            if (R_b(e) > nm.y) m.cold &= ~8u;                          // a match index moves
             peer_nm_set<MM>(m, from, R_a(e) > nm.x ? R_a(e) : nm.x, R_b(e) > nm.y ? R_b(e) : nm.y);
             quorum = chase = true;
         } else return false;
-        if (quorum) evaluate_quorum<MM>(m);
+        // exact shortcut: nothing evaluate_quorum reads has moved since it last ran in this step
+        if (quorum && !(m.cold & 8u)) evaluate_quorum<MM>(m);
         // a chased {next_event, info, pipeline_rpcs}: one pass, the rest is deferred (contract 4)
         if (rpc_pass<MM>(m, mode, force) && chase) { MT_SET(m.meta, 24, 1, 1); m.status |= RA_ST_PIPELINE_PENDING; }
         return true;
