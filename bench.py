@@ -36,7 +36,7 @@ B_COMMIT = {3: 40 + 104 * 3 + 2 * (169 + 185) + (128 + 8 * 3) + 2 * (145 + 8 * 3
 METRIC = "committed entries/sec across N Raft groups; HBM GB/s vs roofline"
 # dram__bytes_read.sum + dram__bytes_write.sum of raft_step_kernel per launch, from the last
 # `ncu --set full` capture of this workload (profiles/, see profiles/README.md); None until measured
-TRAFFIC_BYTES = 450_190_336      # profiles/r01_v9_raft_step_ncu_full.txt (250.0 MB read + 200.2 MB written)
+TRAFFIC_BYTES = 250_279_424      # profiles/r01_v12_raft_step_ncu_full.txt (136.0 MB read + 114.3 MB written)
 
 
 def b_commit(m: int) -> int:
@@ -318,12 +318,36 @@ def run_engine(args):
     print(json.dumps(out))
 
 
+def effective_cpus() -> int:
+    """Host cores this process may actually use: min(online CPUs, affinity mask, cgroup CPU quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, -(-int(txt[0]) // int(txt[1]))))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, -(-q // per)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 def cpu_baseline(args, sample_groups: int, steps: int, threads: int | None = None) -> dict:
     """The oracle (CPU port of ra_server's hot path) on a bounded sample of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import Oracle
     from ra_b200 import abi
-    cores = threads or os.cpu_count() or 1
+    cores = threads or effective_cpus()
     o = Oracle(sample_groups, args.members, route_on_device=True)
     o.reset_empty()
     o.step([abi.ev_simple(o.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(sample_groups)])
@@ -377,8 +401,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--e2e-engines", type=int, default=1,
                     help="e2e leg at N=1: independent engines (disjoint groups) driven by as many host threads")
-    ap.add_argument("--cpu-groups", type=int, default=20_000)
-    ap.add_argument("--cpu-steps", type=int, default=100)
+    ap.add_argument("--cpu-groups", type=int, default=50_000)
+    ap.add_argument("--cpu-steps", type=int, default=300)
     ap.add_argument("--placement", default="spread", choices=["spread", "group"],
                     help="N>1: spread = members of a group on different GPUs + NCCL all-to-all of RPC records; "
                          "group = whole groups per GPU, no collective")

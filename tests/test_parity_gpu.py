@@ -32,6 +32,9 @@ TRACES = [
     (4, 1, 60, 2, {}),                                                              # single-member groups
     (10, 8, 120, 13, dict(p_drop=0.0, p_dup=0.0, p_delay=0.0, p_adversarial=0.0)),  # clean network
     (6, 5, 200, 17, dict(max_cmd=200, p_cmd=0.9)),                                  # batches > max_aer_batch
+    # SURVEY 8d config 5 (7 members: lagging fsync, dropped AERs -> missing / await_condition / back-off,
+    # leader changes with unreplicated tails) at 2000 groups, every record and note diffed
+    (2000, 7, 60, 29, dict(p_drop=0.005, p_withhold_written=0.02, p_timeout=0.003, p_dup=0.0, p_adversarial=0.0)),
 ]
 
 
