@@ -53,17 +53,61 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.
+
+    Primary source: NVML polled from a thread (~1 kHz, so a 20 ms region still gets samples);
+    secondary: an `nvidia-smi -lms` child (its first line can take longer than the region)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    MASKS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.proc = None
         self.lines = []
+        self.nv = []            # (sm_mhz, max_mhz, reasons bitmask)
+        self._stop = threading.Event()
+        self._nvt = None
+
+    def _nvml_loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = getattr(torch.cuda.get_device_properties(self.idx), "uuid", None)
+                if uuid is not None:
+                    u = "GPU-" + str(uuid)
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(u)
+                    except Exception:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(u.encode())
+            except Exception:
+                h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self._stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = int(reasons_fn(h))
+                except Exception:
+                    rs = 0
+                self.nv.append((float(sm), float(mx), rs))
+                time.sleep(0.0005)
+        except Exception:
+            return
 
     def start(self):
+        try:
+            self._nvt = threading.Thread(target=self._nvml_loop, daemon=True)
+            self._nvt.start()
+        except Exception:
+            self._nvt = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -78,6 +122,18 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self) -> dict:
+        self._stop.set()                                       # NVML samples end with the timed region
+        if self._nvt is not None:
+            self._nvt.join(timeout=1.0)
+        if self.nv:
+            sm = sorted(x[0] for x in self.nv)
+            bits = 0
+            for x in self.nv:
+                bits |= x[2]
+            if self.proc:
+                self.proc.terminate()
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(x[1] for x in self.nv),
+                    "reasons": sorted(n for n, m in self.MASKS if bits & m), "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -101,7 +157,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def dist_init(n_gpus: int):
@@ -198,6 +254,8 @@ def run_engine(args):
     # e2e: the same flood through ra_engine_step with pinned host buffers (rank-local engine)
     e2e = None
     if not args.no_e2e:
+        # host-model threads: the CPUs this job may really use, shared by the ranks of the node
+        os.environ.setdefault("RA_HOSTSIM_THREADS", str(max(1, min(16, effective_cpus() // max(1, world)))))
         if spread:
             from ra_b200.sharded import NcclTransport, NvlinkPeerTransport, Shard
             sh2 = Shard(G, M, world, rank, device=dev, buckets=not peer)
