@@ -69,8 +69,7 @@ class ClockSampler:
         self.nv = []            # (sm_mhz, max_mhz, reasons bitmask)
         self._stop = threading.Event()
         self._nvt = None
-
-    def _nvml_loop(self):
+        self._nvml = None       # (module, handle, max clock, reasons fn): set up BEFORE the timed region
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -89,23 +88,32 @@ class ClockSampler:
             if h is None:
                 h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
             mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
                 getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)          # make sure the query works
+            self._nvml = (pynvml, h, float(mx), fn)
+        except Exception:
+            self._nvml = None
+
+    def _nvml_loop(self):
+        try:
+            pynvml, h, mx, reasons_fn = self._nvml
             while not self._stop.is_set():
                 sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                 try:
                     rs = int(reasons_fn(h))
                 except Exception:
                     rs = 0
-                self.nv.append((float(sm), float(mx), rs))
+                self.nv.append((float(sm), mx, rs))
                 time.sleep(0.0005)
         except Exception:
             return
 
     def start(self):
         try:
-            self._nvt = threading.Thread(target=self._nvml_loop, daemon=True)
-            self._nvt.start()
+            if self._nvml is not None:
+                self._nvt = threading.Thread(target=self._nvml_loop, daemon=True)
+                self._nvt.start()
         except Exception:
             self._nvt = None
         try:
