@@ -13,6 +13,7 @@
 #include <new>
 
 #include "raft_step.cuh"
+#include "raft_row.cuh"
 
 
 // ------------------------------------------------------------------------------------------
@@ -93,121 +94,6 @@ struct StepSmem {
 //                      other lanes): resumes at the stalled event with the general path
 //                      (process_event), runs the row's end-of-step.
 // Both run the same end-of-step code; together they evaluate every event exactly once, in order.
-
-struct StallCtx {                      // 4 x 16 bytes
-    u32 row, flags, rem_mbox, rem_loc;
-    u32 n_msgs_notes, status, sent_to, pn_type_slot_wk;
-    u64 pn_a, pn_b;
-    u64 pn_c, _pad;
-};
-#define STALL_PENDING 1u               // the deferred pipeline pass has not run yet
-
-__device__ __forceinline__ void member_init(Member& m, const Cols& C, u32 r, ulonglong2 tc, ulonglong2 lg, ulonglong2 lw,
-                                            ulonglong2 ap, u64 lrs, int cur, ulonglong2* sp)
-{
-    m.C = &C; m.row = r;
-    {   // slot = r / groups through the precomputed reciprocal floor(2^32 / groups): off by at most one
-        u32 q = __umulhi(r, C.groups_inv), rem = r - q * C.groups;
-        if (rem >= C.groups) { q++; rem -= C.groups; }
-        if (rem >= C.groups) { q++; rem -= C.groups; }
-        m.slot = q; m.group = rem;
-    }
-    m.term = tc.x; m.commit = tc.y; m.last_idx = lg.x; m.last_term = lg.y;
-    m.lw_idx = lw.x; m.lw_term = lw.y; m.applied = ap.x; m.meta = ap.y;
-    m.cold = 0;
-    m.lrs = lrs; m.lrs_ok = MT_NRUNS(ap.y) ? 1u : 0u;
-    m.n_msgs = 0; m.n_notes = 0; m.status = MT_ROLE(ap.y) << 16; m.wk = 0;
-    m.sent_to = 0; m.pn_type = RA_NOTE_NONE; m.pn_slot = 0; m.pn_a = m.pn_b = m.pn_c = 0;
-    m.c_pack = 0; m.c_commits = m.c_applied = 0;
-    m.nb = cur ^ 1;
-    m.sp = sp; m.pstate = 0; m.pipe_clean = 0;
-}
-
-// The four hot pairs change on practically every step of an active row (commit_index,
-// last_index, last_written, last_applied / meta), so they are stored unconditionally: keeping
-// their loaded values around just to skip a store costs 16 registers per thread.
-__device__ __forceinline__ void member_writeback(const Member& m, const Cols& C, u32 r)
-{
-    st2(&C.tc[r], m.term, m.commit);
-    st2(&C.lg[r], m.last_idx, m.last_term);
-    st2(&C.lw[r], m.lw_idx, m.lw_term);
-    st2(&C.ap[r], m.applied, m.meta);
-    lrs_writeback(m);
-}
-
-// end of a row's step: publish mailbox counts, STATUS note, output counts, flood host model
-template <int MM>
-__device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, int cur, const FloodArgs& F)
-{
-    u32 fatal = 0;
-    const bool routed = MTR == TR_RUNTIME ? (C.routed != 0) : (MTR != TR_HOST);
-    if (routed) {
-        const bool sharded = MTR == TR_RUNTIME ? (C.n_shards > 1) : (MTR == TR_PEER || MTR == TR_BUCKET);
-        const bool peer = MTR == TR_RUNTIME ? (C.peer_mode != 0) : (MTR == TR_PEER);
-        for (u32 s = 0; s < NMEM(C); s++) {
-            if (s == m.slot) continue;
-            u64* cnt = C.mbox_cnt[cur ^ 1];
-            if (sharded) {
-                const u32 ds = (C.shard + s + 8u * C.n_shards - m.slot) % C.n_shards;
-                if (peer) cnt = C.peer_cnt[cur ^ 1][ds];                 // byte store over NVLink
-                else if (ds != C.shard) continue;   // set when the records are delivered (deliver_kernel)
-            }
-            reinterpret_cast<u8*>(&cnt[(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
-        }
-    }
-    note_flush(m);
-    if (m.status & 0xffffu) {
-        u64 ld = MT_LEADER(m.meta), vf = MT_VOTED(m.meta);
-        u64 b = (vf == SLOT_NONE ? 0xFFull : vf) | ((ld == SLOT_NONE ? 0xFFull : ld) << 8) |
-                ((u64)((m.status >> 16) & 7u) << 16) | ((u64)MT_ROLE(m.meta) << 24);
-        note_store(m, m.n_notes, RA_NOTE_STATUS, m.slot, m.status & 0xffffu, m.term, b, (m.status >> 20) & 0xffu);
-        m.n_notes++;
-        if (m.status & RA_ST_FATAL) fatal = 1;
-    }
-    C.out_n[r] = m.n_msgs | (m.n_notes << 16);
-    // flood: synthetic host (DESIGN.md "flood host model")
-    if (F.on && !MT_FATAL(m.meta)) {
-        u32 k = 0;
-        // {written, Term, {From, To}} for the (last two) WAL_APPEND notes of this step: read back
-        // from the row's own note slots instead of being carried in registers through the step
-        if ((m.wk & 3u) == 2) {
-            const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&C.onote[(size_t)((m.wk >> 8) & 15u) * C.rows + r]);
-            const ulonglong2 h = q[0], t = q[1];
-            put_local(C.loc, C.tiles, k, r, RA_EV_WRITTEN, 0, t.y, h.y, t.x); k++;
-        }
-        if ((m.wk & 3u) >= 1) {
-            const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&C.onote[(size_t)((m.wk >> 4) & 15u) * C.rows + r]);
-            const ulonglong2 h = q[0], t = q[1];
-            put_local(C.loc, C.tiles, k, r, RA_EV_WRITTEN, 0, t.y, h.y, t.x); k++;
-        }
-        const u32 role = MT_ROLE(m.meta);
-        if (role == RA_LEADER && F.cmds) { put_local(C.loc, C.tiles, k, r, RA_EV_COMMAND, F.cmds, 0, 0, 0); k++; }
-        u32 idle = MT_IDLE(m.meta);
-        if (role == RA_LEADER || (m.status & RA_ST_LEADER_MSG)) idle = 0;
-        else if (idle < 15) idle++;
-        bool fire = false;
-        if (role != RA_LEADER) {
-            // the model is keyed by GLOBAL group / row ids so that a sharded run equals the unsharded one
-            u64 gg = m.group, gr = r;
-            if (C.n_shards > 1) {
-                gg = (u64)C.n_shards * m.group + (C.shard + 8u * C.n_shards - m.slot) % C.n_shards;
-                gr = (u64)m.slot * C.groups * C.n_shards + gg;
-            }
-            if (F.permille) {
-                const u32 h = (u32)(mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ (gg * 0xD1B54A32D192ED03ull)) >> 32);
-                if ((h % 1000u) < F.permille && ((h / 1000u) % NMEM(C)) == m.slot) fire = true;
-            }
-            if (idle >= 8) {                                // the hash only matters from 8 idle steps on
-                const u32 h2 = (u32)(mix64(F.seed ^ (gr * 0xA24BAED4963EE407ull) ^ F.step) >> 32);
-                if (idle >= 8 + (h2 & 7u)) fire = true;
-            }
-        }
-        if (fire) { put_local(C.loc, C.tiles, k, r, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0); k++; idle = 0; }
-        MT_SET(m.meta, 28, 4, idle);
-        C.loc_n[r] = k;
-    }
-    return fatal;
-}
 
 __device__ __forceinline__ void flush_counters(const Cols& C, u32 lane, u32 k_events, u32 k_commits, u32 k_applied,
                                                u32 k_msgs, u32 k_dropped, u32 k_elect, u32 k_fatal)
@@ -438,97 +324,21 @@ __global__ void reset_empty_kernel(const Cols C)
 {
     const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= C.rows) return;
-    // ra_server_SUITE:empty_state/2: term 0, log {0 => 0}, peers next=1 match=0, all voters
-    u64 meta = 0;
-    MT_SET(meta, 0, 3, RA_FOLLOWER); MT_SET(meta, 3, 4, SLOT_NONE); MT_SET(meta, 7, 4, SLOT_NONE);
-    MT_SET(meta, 19, 4, 1); MT_SET(meta, 27, 1, 1);
-    MT_SET(meta, 56, 8, (1u << C.members) - 1u);
-    st2(&C.tc[r], 0, 0); st2(&C.lg[r], 0, 0); st2(&C.lw[r], 0, 0); st2(&C.ap[r], 0, meta);
-    st2(&C.sn[r], 0, 0); st2(&C.tk[r], 0, 0); st2(&C.fm[r], 0, 0);
-    st2(&C.cd[r], 0, 0); st2(&C.cd[(size_t)C.rows + r], 0, 0);
-    for (u32 s = 0; s < C.members; s++) { st2(&C.pnm[(size_t)s * C.rows + r], 1, 0); C.pcs[(size_t)s * C.rows + r] = 0; }
-    for (u32 k = 0; k < RA_MAX_RUNS; k++) st2(&C.run[(size_t)k * C.rows + r], 0, 0);
-    C.lrs[r] = 0;
-    C.loc_n[r] = 0; C.out_n[r] = 0;
-    if (C.routed) { C.mbox_cnt[0][r] = 0; C.mbox_cnt[1][r] = 0; }
+    reset_row(C, r);
 }
 
 __global__ void load_rows_kernel(const Cols C, const ra_row_state* in, u32 n)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const ra_row_state& s = in[i];
-    const u32 r = s.row;
-    u64 meta = 0;
-    MT_SET(meta, 0, 3, s.role);
-    MT_SET(meta, 3, 4, s.leader_slot == RA_NO_SLOT ? SLOT_NONE : s.leader_slot);
-    MT_SET(meta, 7, 4, s.voted_for == RA_NO_SLOT ? SLOT_NONE : s.voted_for);
-    MT_SET(meta, 11, 2, s.membership); MT_SET(meta, 13, 2, s.condition);
-    MT_SET(meta, 15, 4, s.votes); MT_SET(meta, 19, 4, s.n_runs);
-    MT_SET(meta, 23, 1, s.has_snapshot ? 1 : 0);
-    MT_SET(meta, 24, 1, (s.flags & 1) ? 1 : 0); MT_SET(meta, 25, 1, (s.flags & 2) ? 1 : 0);
-    MT_SET(meta, 26, 1, (s.flags & 4) ? 1 : 0);
-    MT_SET(meta, 27, 1, s.machine_version >= s.effective_machine_version ? 1 : 0);
-    u32 voters = 0;
-    for (u32 p = 0; p < RA_MAX_MEMBERS; p++) {
-        MT_SET(meta, 32 + 3 * p, 3, s.peers[p].status);
-        if (s.peers[p].voter) voters |= 1u << p;
-    }
-    MT_SET(meta, 56, 8, voters);
-    st2(&C.tc[r], s.current_term, s.commit_index);
-    st2(&C.lg[r], s.last_index, s.last_term);
-    st2(&C.lw[r], s.last_written_index, s.last_written_term);
-    st2(&C.ap[r], s.last_applied, meta);
-    st2(&C.sn[r], s.snapshot_index, s.snapshot_term);
-    st2(&C.tk[r], s.pre_vote_token, s.token_counter);
-    st2(&C.fm[r], s.first_index, (u64)s.machine_version | ((u64)s.effective_machine_version << 32));
-    st2(&C.cd[r], s.cond_reply_term, s.cond_reply_next_index);
-    st2(&C.cd[(size_t)C.rows + r], s.cond_reply_last_index, s.cond_reply_last_term);
-    for (u32 p = 0; p < C.members; p++) {
-        st2(&C.pnm[(size_t)p * C.rows + r], s.peers[p].next_index, s.peers[p].match_index);
-        C.pcs[(size_t)p * C.rows + r] = s.peers[p].commit_index_sent;
-    }
-    for (u32 k = 0; k < RA_MAX_RUNS; k++)
-        st2(&C.run[(size_t)k * C.rows + r], k < s.n_runs ? s.run_start[k] : 0, k < s.n_runs ? s.run_term[k] : 0);
-    C.lrs[r] = s.n_runs ? s.run_start[s.n_runs - 1] : 0;
-    C.loc_n[r] = 0;
+    load_row(C, in[i]);
 }
 
 __global__ void read_rows_kernel(const Cols C, ra_row_state* out, u32 n)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    ra_row_state& s = out[i];
-    const u32 r = s.row;
-    const ulonglong2 tc = C.tc[r], lg = C.lg[r], lw = C.lw[r], ap = C.ap[r], sn = C.sn[r], tk = C.tk[r], fm = C.fm[r];
-    const u64 meta = ap.y;
-    s.role = MT_ROLE(meta); s.self_slot = r / C.groups; s.n_members = C.members;
-    u32 l = MT_LEADER(meta), v = MT_VOTED(meta);
-    s.leader_slot = l == SLOT_NONE ? RA_NO_SLOT : l; s.voted_for = v == SLOT_NONE ? RA_NO_SLOT : v;
-    s.membership = MT_MEMBERSHIP(meta); s.condition = MT_COND(meta); s.has_snapshot = MT_HAS_SNAP(meta);
-    s.votes = MT_VOTES(meta); s.machine_version = (u32)fm.y; s.effective_machine_version = (u32)(fm.y >> 32);
-    s.n_runs = MT_NRUNS(meta);
-    s.flags = MT_PIPE_PEND(meta) | (MT_COND_VALID(meta) << 1) | (MT_FATAL(meta) << 2);
-    s.current_term = tc.x; s.commit_index = tc.y; s.last_applied = ap.x;
-    s.pre_vote_token = tk.x; s.token_counter = tk.y;
-    s.first_index = fm.x; s.last_index = lg.x; s.last_term = lg.y;
-    s.last_written_index = lw.x; s.last_written_term = lw.y;
-    s.snapshot_index = sn.x; s.snapshot_term = sn.y;
-    for (u32 k = 0; k < RA_MAX_RUNS; k++) {
-        ulonglong2 rr = C.run[(size_t)k * C.rows + r];
-        s.run_start[k] = k < s.n_runs ? rr.x : 0; s.run_term[k] = k < s.n_runs ? rr.y : 0;
-    }
-    ulonglong2 c0 = C.cd[r], c1 = C.cd[(size_t)C.rows + r];
-    s.cond_reply_term = c0.x; s.cond_reply_next_index = c0.y; s.cond_reply_last_index = c1.x; s.cond_reply_last_term = c1.y;
-    for (u32 p = 0; p < RA_MAX_MEMBERS; p++) {
-        ra_peer_init& pi = s.peers[p];
-        if (p < C.members) {
-            ulonglong2 nm = C.pnm[(size_t)p * C.rows + r];
-            pi.next_index = nm.x; pi.match_index = nm.y; pi.commit_index_sent = C.pcs[(size_t)p * C.rows + r];
-            pi.status = MT_PSTATUS(meta, p); pi.voter = MT_VOTER(meta, p);
-        } else { pi.next_index = pi.match_index = pi.commit_index_sent = 0; pi.status = 0; pi.voter = 0; }
-        for (int q = 0; q < 6; q++) pi._pad[q] = 0;
-    }
+    read_row(C, out[i]);
 }
 
 // flat host batch -> per-row local slots.  err[0]: 1 = ungrouped, 2 = too many for a row, 3 = bad row
