@@ -321,6 +321,7 @@ __device__ __forceinline__ u64* peer_cs_p(const Member& m, u32 s)
 template <int MM>
 __device__ __forceinline__ void peers_prefetch(Member& m)
 {
+#ifndef RA_HOST_EMU
     const Cols& C = *m.C;
     for (u32 s = 0; s < NMEM(C); s++) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::
@@ -330,16 +331,21 @@ __device__ __forceinline__ void peers_prefetch(Member& m)
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     m.pstate |= 2u;
+#else
+    (void)m;                                    // host emulation (tests/emu): peers_ensure loads on first use
+#endif
 }
 template <int MM>
 __device__ __forceinline__ void peers_ensure(Member& m)
 {
     if (m.pstate & 1u) return;
+#ifndef RA_HOST_EMU
     if (m.pstate & 2u) {
         asm volatile("cp.async.wait_all;" ::: "memory");
         m.pstate |= 1u;
         return;
     }
+#endif
     const Cols& C = *m.C;
     for (u32 s = 0; s < NMEM(C); s++) {
         *peer_nm_p<MM>(m, s) = C.pnm[(size_t)s * C.rows + m.row];

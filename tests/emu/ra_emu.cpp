@@ -1,0 +1,334 @@
+/* TEST INFRASTRUCTURE -- not part of the product, never loaded by ra_b200/.
+ *
+ * Host emulation of the engine's two step kernels: the DEVICE LOGIC headers of the product
+ * (ra_b200/csrc/raft_step.cuh, raft_row.cuh -- fast_event, process_event, emit_msg, the record
+ * head/tail codec, row_end_of_step, load_row / read_row ...) are compiled here as plain C++
+ * through tests/emu/cuda_shim.h and driven one row at a time with the control flow of
+ * raft_step_kernel (fast paths until a row stalls) and raft_general_kernel (resume from the
+ * 64-byte stall context).  What is NOT covered is the kernels' own frame in engine.cu (TMA ring,
+ * warp reductions, launch plumbing): that is what the `-m gpu` tests are for.  The point of this
+ * library is that the CPU test tier diffs the very source the GPU runs against the oracle
+ * (tests/test_emu_parity.py), so a logic regression shows up before any GPU time is spent.
+ *
+ * Same C ABI as include/ra_engine.h with the prefix ra_emu_ (single shard only).
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include "cuda_shim.h"
+#include "../../ra_b200/csrc/raft_step.cuh"
+#include "../../ra_b200/csrc/raft_row.cuh"
+
+struct ra_emu {
+    ra_engine_cfg cfg;
+    Cols C;
+    int cur;
+    u64 step_no, steps;
+    void* allocs[64]; int n_allocs;
+};
+
+template <typename T>
+static int halloc(ra_emu* e, T** p, size_t count)
+{
+    void* q = calloc(count ? count : 1, sizeof(T));
+    if (!q) return RA_E_NOMEM;
+    e->allocs[e->n_allocs++] = q;
+    *p = (T*)q;
+    return RA_OK;
+}
+
+extern "C" void ra_emu_destroy(ra_emu* e)
+{
+    if (!e) return;
+    for (int i = 0; i < e->n_allocs; i++) free(e->allocs[i]);
+    free(e);
+}
+
+extern "C" int ra_emu_reset_empty(ra_emu* e)
+{
+    if (!e) return RA_E_INVAL;
+    for (u32 r = 0; r < e->C.rows; r++) reset_row(e->C, r);
+    memset(e->C.counters, 0, (8 + 8 * 16) * sizeof(u64));
+    e->cur = 0; e->step_no = 0; e->steps = 0;
+    return RA_OK;
+}
+
+extern "C" int ra_emu_create(const ra_engine_cfg* cfg, ra_emu** out)
+{
+    if (!cfg || !out || cfg->n_members < 1 || cfg->n_members > RA_MAX_MEMBERS || cfg->n_groups == 0) return RA_E_INVAL;
+    if ((u64)cfg->n_groups * cfg->n_members > 0x7fffffffull) return RA_E_INVAL;
+    if (cfg->n_shards > 1) return RA_E_INVAL;                       // single shard only
+    ra_emu* e = (ra_emu*)calloc(1, sizeof(ra_emu));
+    if (!e) return RA_E_NOMEM;
+    e->cfg = *cfg;
+    if (e->cfg.max_pipeline_count == 0) e->cfg.max_pipeline_count = 4096;
+    if (e->cfg.max_aer_batch == 0) e->cfg.max_aer_batch = 128;
+    int rc = RA_OK;
+    Cols& C = e->C;
+    const size_t R = (size_t)cfg->n_groups * cfg->n_members, M = cfg->n_members;
+    C.rows = (u32)R; C.groups = cfg->n_groups; C.members = cfg->n_members;
+    C.groups_inv = cfg->n_groups > 1 ? (u32)(0x100000000ull / cfg->n_groups) : 0xFFFFFFFFu;
+    C.max_pipeline = e->cfg.max_pipeline_count; C.max_batch = e->cfg.max_aer_batch;
+    C.routed = cfg->route_on_device ? 1 : 0; C.pure = cfg->pure ? 1 : 0;
+    C.n_shards = 1; C.shard = 0;
+    C.outbox = nullptr; C.out_cnt = nullptr; C.out_cap = 0;
+    C.peer_mode = 0;
+    for (int b = 0; b < 2; b++) for (int k = 0; k < 8; k++) { C.peer_mbox[b][k] = nullptr; C.peer_cnt[b][k] = nullptr; }
+#define HA(p, n) if ((rc = halloc(e, &(p), (n))) != RA_OK) goto bad
+    HA(C.tc, R); HA(C.lg, R); HA(C.lw, R); HA(C.ap, R); HA(C.sn, R); HA(C.tk, R); HA(C.fm, R);
+    HA(C.cd, 2 * R); HA(C.pnm, M * R); HA(C.pcs, M * R); HA(C.run, RA_MAX_RUNS * R); HA(C.lrs, R);
+    C.tiles = (u32)((R + RT - 1) / RT);
+    {
+        const size_t PW = (size_t)C.tiles * 4 * RT;
+        HA(C.loc, (size_t)RA_LOCAL_CAP * PW); HA(C.loc_n, R);
+        HA(C.onote, (size_t)RA_NOTE_CAP * R); HA(C.out_n, R); HA(C.counters, 8 + 8 * 16);
+        if (C.routed) {
+            for (int b = 0; b < 2; b++) { HA(C.mbox[b], M * RA_MBOX_DEPTH * PW); HA(C.mbox_cnt[b], R); }
+            HA(C.omsg, (size_t)RA_MSG_CAP * (C.pure ? R : 1));
+        } else {
+            C.mbox[0] = C.mbox[1] = nullptr; C.mbox_cnt[0] = C.mbox_cnt[1] = nullptr;
+            HA(C.omsg, (size_t)RA_MSG_CAP * R);
+        }
+    }
+#undef HA
+    if ((rc = ra_emu_reset_empty(e)) != RA_OK) goto bad;
+    *out = e;
+    return RA_OK;
+bad:
+    ra_emu_destroy(e);
+    return rc;
+}
+
+extern "C" int ra_emu_get_cfg(ra_emu* e, ra_engine_cfg* out)
+{
+    if (!e || !out) return RA_E_INVAL;
+    *out = e->cfg;
+    return RA_OK;
+}
+
+extern "C" int ra_emu_load_rows(ra_emu* e, const ra_row_state* rows, size_t n)
+{
+    if (!e || (!rows && n)) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++)
+        if (rows[i].row >= e->C.rows || rows[i].n_runs > RA_MAX_RUNS || rows[i].n_members != e->C.members) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) load_row(e->C, rows[i]);
+    return RA_OK;
+}
+
+extern "C" int ra_emu_read_rows(ra_emu* e, ra_row_state* rows, size_t n)
+{
+    if (!e || (!rows && n)) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) if (rows[i].row >= e->C.rows) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) read_row(e->C, rows[i]);
+    return RA_OK;
+}
+
+// ---- one row through one step: raft_step_kernel, then raft_general_kernel if it stalled -------
+
+struct Scratch { ulonglong2 nm[RA_MAX_MEMBERS]; u64 cs[RA_MAX_MEMBERS]; };   // the per-thread shared-memory columns
+
+static void add_counters(const Cols& C, const Member& m, u32 k_fatal)
+{
+    C.counters[0] += m.c_pack & 0xffu; C.counters[1] += m.c_commits; C.counters[2] += m.c_applied;
+    C.counters[3] += (m.c_pack >> 8) & 0xffu; C.counters[4] += m.c_pack >> 20; C.counters[5] += (m.c_pack >> 16) & 15u;
+    C.counters[6] += k_fatal;
+}
+
+// the general kernel's body for one stall context (engine.cu: raft_general_kernel)
+static void general_row(const Cols& C, int cur, const FloodArgs& F, const StallCtx& ctx)
+{
+    constexpr int MM = MK_MM(0, TR_RUNTIME);
+    Scratch sc;
+    const u32 r = ctx.row, flags = ctx.flags;
+    u32 rem_mbox = ctx.rem_mbox, rem_loc = ctx.rem_loc;
+    Member m;
+    member_init(m, C, r, C.tc[r], C.lg[r], C.lw[r], C.ap[r], 0, cur, sc.nm);
+    m.lrs_ok = 0;
+    m.n_msgs = ctx.n_msgs_notes & 0xffffu; m.n_notes = (ctx.n_msgs_notes >> 16) & 0xffffu; m.status = ctx.status;
+    m.sent_to = ctx.sent_to;
+    { const u32 w = ctx.pn_type_slot_wk; m.pn_type = w & 0xffu; m.pn_slot = (w >> 8) & 0xffu; m.wk = w >> 16; }
+    m.pn_a = ctx.pn_a; m.pn_b = ctx.pn_b; m.pn_c = ctx.pn_c;
+    if (flags & STALL_PENDING) {
+        MT_SET(m.meta, 24, 1, 0);
+        process_event<MM>(m, mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+        m.cold &= ~8u;
+    }
+    while (rem_mbox) {
+        const u32 p = __ffs(rem_mbox) - 1; rem_mbox &= rem_mbox - 1;
+        const Rec e = ld_rec_plane(C.mbox[cur], C.tiles, p, r);
+        if (MT_FATAL(m.meta)) m.c_pack += 1u;
+        else if (C.pure || !fast_event<MM>(m, e)) { process_event<MM>(m, e); m.cold &= ~8u; }
+    }
+    while (rem_loc) {
+        const u32 p = __ffs(rem_loc) - 1; rem_loc &= rem_loc - 1;
+        const Rec e = ld_rec_plane(C.loc, C.tiles, p, r);
+        if (MT_FATAL(m.meta)) m.c_pack += 1u;
+        else if (C.pure || !fast_event<MM>(m, e)) { process_event<MM>(m, e); m.cold &= ~8u; }
+    }
+    peers_writeback<MM>(m);
+    const u32 k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
+    member_writeback(m, C, r);
+    add_counters(C, m, k_fatal);
+}
+
+// the step kernel's body for one row (engine.cu: raft_step_kernel<MM>); true = the row stalled
+template <int MM>
+static bool step_row(const Cols& C, int cur, const FloodArgs& F, u32 r, StallCtx& ctx)
+{
+    constexpr u32 NPM = (MMEM ? MMEM : RA_MAX_MEMBERS) * RA_MBOX_DEPTH;
+    Scratch sc;
+    const ulonglong2 ap = C.ap[r];
+    const u32 nloc = C.loc_n[r];
+    const u64 cntw = C.routed ? C.mbox_cnt[cur][r] : 0;
+    const ulonglong2 tc = C.tc[r], lg = C.lg[r], lw = C.lw[r];
+    const u64 lrs = C.lrs[r];
+    const bool fatal0 = MT_FATAL(ap.y) != 0;
+    const bool pending = MT_PIPE_PEND(ap.y) != 0;
+    u64 mine = 0;
+    if (!fatal0) {
+        u32 mb = 0;
+        for (u32 s = 0; s < NMEM(C); s++) {
+            const u32 c = (u32)(cntw >> (8 * s)) & 0xffu;
+            mb |= ((1u << (c & 7u)) - 1u) << (RA_MBOX_DEPTH * s);
+        }
+        mine = (u64)mb | ((u64)((1u << (nloc & 7u)) - 1u) << NPM);
+    }
+    const bool work = F.on || nloc || cntw || pending;
+    if (!work) return false;
+    Member m;
+    member_init(m, C, r, tc, lg, lw, ap, lrs, cur, sc.nm);
+    m.row = r;
+    if (!fatal0 && MT_ROLE(ap.y) == RA_LEADER) peers_prefetch<MM>(m);
+    bool stalled = false;
+    u32 stall_flags = 0;
+    u64 rem = 0;
+    if (!fatal0 && pending) { stalled = true; stall_flags = STALL_PENDING; rem = mine; }
+    u64 todo = mine;
+    while (todo) {
+        const u32 p = (u32)__ffsll((long long)todo) - 1u; todo &= todo - 1;
+        if (stalled) continue;
+        const Rec e = p < NPM ? ld_rec_plane(C.mbox[cur], C.tiles, p, r) : ld_rec_plane(C.loc, C.tiles, p - NPM, r);
+        if (MT_FATAL(m.meta)) m.c_pack += 1u;
+        else if (C.pure || !fast_event<MM>(m, e)) {
+            stalled = true;
+            rem = mine & ~(((u64)1 << p) - 1);
+            atomicAdd(&C.counters[8 + (m_role(m) & 7u) * 16 + (R_type(e) & 15u)], 1ull);
+        }
+    }
+    if (cntw && !fatal0) C.mbox_cnt[cur][r] = 0;
+    if (nloc) C.loc_n[r] = 0;
+    peers_writeback<MM>(m);
+    u32 k_fatal = 0;
+    if (!stalled) k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
+    member_writeback(m, C, r);
+    add_counters(C, m, k_fatal);
+    if (stalled) {
+        ctx.row = r; ctx.flags = stall_flags;
+        ctx.rem_mbox = (u32)(rem & (((u64)1 << NPM) - 1)); ctx.rem_loc = (u32)(rem >> NPM);
+        ctx.n_msgs_notes = m.n_msgs | (m.n_notes << 16); ctx.status = m.status; ctx.sent_to = m.sent_to;
+        ctx.pn_type_slot_wk = m.pn_type | (m.pn_slot << 8) | (m.wk << 16);
+        ctx.pn_a = m.pn_a; ctx.pn_b = m.pn_b; ctx.pn_c = m.pn_c; ctx._pad = 0;
+    }
+    return stalled;
+}
+
+static void run_step(ra_emu* e, const FloodArgs& F)
+{
+    const Cols& C = e->C;
+    // same choice of specialisation as launch_step() in engine.cu
+    const int tr = !C.routed ? TR_HOST : TR_LOCAL;
+    for (u32 r = 0; r < C.rows; r++) {
+        StallCtx ctx;
+        bool stalled;
+        if (C.members == 5) stalled = tr == TR_LOCAL ? step_row<MK_MM(5, TR_LOCAL)>(C, e->cur, F, r, ctx)
+                                                     : step_row<MK_MM(5, TR_HOST)>(C, e->cur, F, r, ctx);
+        else stalled = step_row<MK_MM(0, TR_RUNTIME)>(C, e->cur, F, r, ctx);
+        // the general kernel runs after the step kernel; rows only ever write to OTHER rows' mailboxes of
+        // the NEXT step, so handling a stalled row right away is the same thing
+        if (stalled) general_row(C, e->cur, F, ctx);
+    }
+    if (C.routed) e->cur ^= 1;
+    e->steps++;
+}
+
+extern "C" int ra_emu_step(ra_emu* e, const ra_event* ev, size_t n_ev,
+                           ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                           ra_note* notes, size_t notes_cap, size_t* n_notes)
+{
+    if (!e || (!ev && n_ev) || n_ev > 0x7fffffffull) return RA_E_INVAL;
+    const Cols& C = e->C;
+    const u32 R = C.rows;
+    for (u32 r = 0; r < R; r++) C.loc_n[r] = 0;                  // clear_loc_kernel
+    // ingest_kernel: flat batch -> per-row local slots
+    u32 err = 0;
+    for (size_t i = 0; i < n_ev; i++) {
+        const u32 row = ev[i].row;
+        if (row >= R) { if (err < 3) err = 3; continue; }
+        if (i > 0 && ev[i - 1].row == row) continue;
+        u32 len = 1;
+        while (i + len < n_ev && ev[i + len].row == row && len <= RA_LOCAL_CAP) len++;
+        if (len > RA_LOCAL_CAP) { if (err < 2) err = 2; continue; }
+        if (C.loc_n[row] != 0) { if (err < 1) err = 1; continue; }
+        C.loc_n[row] = len;
+        u32 tails = 0;
+        for (u32 k = 0; k < len; k++)
+            if (st_rec_plane(C.loc, C.tiles, k, row, ld_rec(&ev[i + k]))) tails |= 0x100u << k;
+        C.loc_n[row] |= tails;
+    }
+    if (err) {
+        for (u32 r = 0; r < R; r++) C.loc_n[r] = 0;
+        return err == 1 ? RA_E_UNGROUPED : (err == 2 ? RA_E_CAPACITY : RA_E_INVAL);
+    }
+    FloodArgs F; memset(&F, 0, sizeof F);
+    run_step(e, F);
+    // pack_counts + scan + gather: per-row slots -> flat arrays ordered by (row, seq)
+    size_t tm = 0, tn = 0;
+    for (u32 r = 0; r < R; r++) { tm += C.out_n[r] & 0xffffu; tn += C.out_n[r] >> 16; }
+    const bool fits = tm <= msgs_cap && tn <= notes_cap;
+    size_t om = 0, on = 0;
+    for (u32 r = 0; r < R; r++) {
+        const u32 v = C.out_n[r];
+        C.out_n[r] = 0;
+        const u32 nm = v & 0xffffu, nn = v >> 16;
+        if (fits) {
+            for (u32 k = 0; k < nm; k++) st_rec(&msgs[om + k], ld_rec(&C.omsg[(size_t)k * C.rows + r]));
+            for (u32 k = 0; k < nn; k++) notes[on + k] = C.onote[(size_t)k * C.rows + r];
+        }
+        om += nm; on += nn;
+    }
+    if (!fits) return RA_E_CAPACITY;
+    if (n_msgs) *n_msgs = tm;
+    if (n_notes) *n_notes = tn;
+    return RA_OK;
+}
+
+extern "C" int ra_emu_flood(ra_emu* e, uint32_t n_steps, uint32_t cmds_per_step, uint32_t election_permille,
+                            uint64_t seed)
+{
+    if (!e || !e->C.routed) return RA_E_INVAL;
+    for (u32 t = 0; t < n_steps; t++) {
+        FloodArgs F; F.on = 1; F.cmds = cmds_per_step; F.permille = election_permille; F._p = 0;
+        F.seed = seed; F.step = e->step_no + t;
+        run_step(e, F);
+    }
+    e->step_no += n_steps;
+    return RA_OK;
+}
+
+extern "C" int ra_emu_counters(ra_emu* e, ra_counters* out)
+{
+    if (!e || !out) return RA_E_INVAL;
+    const u64* h = e->C.counters;
+    out->events = h[0]; out->commits = h[1]; out->applied = h[2]; out->msgs_out = h[3];
+    out->msgs_dropped = h[4]; out->elections_won = h[5]; out->fatal_rows = h[6]; out->steps = e->steps;
+    return RA_OK;
+}
+
+extern "C" int ra_emu_stall_histogram(ra_emu* e, uint64_t* out128)
+{
+    if (!e || !out128) return RA_E_INVAL;
+    memcpy(out128, e->C.counters + 8, 128 * sizeof(u64));
+    return RA_OK;
+}

@@ -1,0 +1,49 @@
+"""TEST INFRASTRUCTURE: loader for the host emulation of the engine's device logic
+(tests/emu/libra_emu.so = ra_b200/csrc/raft_step.cuh + raft_row.cuh compiled by g++ through
+tests/emu/cuda_shim.h).  Lets the CPU test tier diff the source the GPU runs against the oracle;
+it is never imported by the product package and is not a fallback for it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+from ra_b200 import abi
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_DIR = os.path.join(_ROOT, "tests", "emu")
+_SO = os.path.join(_DIR, "libra_emu.so")
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        srcs = [os.path.join(_DIR, "ra_emu.cpp"), os.path.join(_DIR, "cuda_shim.h"),
+                os.path.join(_ROOT, "ra_b200", "csrc", "raft_step.cuh"),
+                os.path.join(_ROOT, "ra_b200", "csrc", "raft_row.cuh"),
+                os.path.join(_ROOT, "include", "ra_engine.h")]
+        if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
+            subprocess.check_call(["make", "-C", _DIR], stdout=subprocess.DEVNULL)
+        _lib = C.CDLL(_SO)
+        _lib.ra_emu_flood.restype = C.c_int
+        _lib.ra_emu_flood.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
+        _lib.ra_emu_stall_histogram.restype = C.c_int
+        _lib.ra_emu_stall_histogram.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    return _lib
+
+
+class Emu(abi.Backend):
+    name = "emu"
+
+    def __init__(self, n_groups: int, n_members: int, **kw):
+        super().__init__(lib(), "ra_emu", n_groups, n_members, **kw)
+
+    def flood(self, n_steps: int, cmds_per_step: int = 1, election_permille: int = 0, seed: int = 1, **_kw) -> None:
+        self._check(lib().ra_emu_flood(self._h, n_steps, cmds_per_step, election_permille, seed), "flood")
+
+    def stall_histogram(self) -> dict:
+        arr = (C.c_uint64 * 128)()
+        self._check(lib().ra_emu_stall_histogram(self._h, arr), "stall_histogram")
+        return {(i // 16, i % 16): int(v) for i, v in enumerate(arr) if v}

@@ -23,6 +23,9 @@ def make_backend(name: str, n_groups: int, n_members: int, **kw):
     if name == "engine":
         from ra_b200.engine import Engine
         return Engine(n_groups, n_members, **kw)
+    if name == "emu":                                   # the engine's device logic compiled for the host (tests/emu/)
+        from emu_lib import Emu
+        return Emu(n_groups, n_members, **kw)
     raise ValueError(name)
 
 

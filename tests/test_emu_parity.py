@@ -1,0 +1,120 @@
+"""CPU tier: the engine's DEVICE LOGIC (ra_b200/csrc/raft_step.cuh + raft_row.cuh, compiled for the
+host by tests/emu/) against the oracle, with the inputs of the `-m gpu` parity tests.
+
+What this covers: every handler / fast path / codec / end-of-step line the GPU executes, driven
+with the control flow of the two step kernels.  What it does not: the kernels' own frame (TMA
+ring, warp reductions, launches) -- tests/test_parity_gpu.py does that on a B200.
+"""
+import ctypes as C
+
+import pytest
+
+import trace_gen
+from emu_lib import Emu
+from oracle_lib import Oracle
+from ra_b200 import abi
+
+TRACES = [
+    (8, 3, 150, 11, {}),
+    (16, 5, 300, 7, {}),
+    (12, 7, 250, 3, dict(p_drop=0.05, p_withhold_written=0.1)),
+    (32, 5, 200, 5, dict(p_timeout=0.04, p_adversarial=0.05)),
+    (4, 1, 60, 2, {}),
+    (10, 8, 120, 13, dict(p_drop=0.0, p_dup=0.0, p_delay=0.0, p_adversarial=0.0)),
+    (6, 5, 200, 17, dict(max_cmd=200, p_cmd=0.9)),
+    (300, 7, 60, 29, dict(p_drop=0.005, p_withhold_written=0.02, p_timeout=0.003, p_dup=0.0, p_adversarial=0.0)),
+]
+
+
+@pytest.mark.parametrize("g,m,steps,seed,knobs", TRACES)
+def test_trace_parity_emu(g, m, steps, seed, knobs):
+    batches = trace_gen.generate(lambda gg, mm: Oracle(gg, mm), g, m, steps, seed, **knobs)
+    want, want_rows, want_cnt = trace_gen.replay(Oracle(g, m), batches)
+    got, got_rows, got_cnt = trace_gen.replay(Emu(g, m), batches)
+    for t, (w, x) in enumerate(zip(want, got)):
+        assert x[0] == w[0], "RPC records differ at step %d" % t
+        assert x[1] == w[1], "host notes differ at step %d" % t
+    assert got_rows == want_rows
+    assert got_cnt == want_cnt
+
+
+def test_trace_parity_emu_small_pipeline_window():
+    kw = dict(max_pipeline_count=8, max_aer_batch=3)
+    batches = trace_gen.generate(lambda gg, mm: Oracle(gg, mm, **kw), 8, 5, 250, 23, max_cmd=9, p_cmd=0.9)
+    want = trace_gen.replay(Oracle(8, 5, **kw), batches)
+    got = trace_gen.replay(Emu(8, 5, **kw), batches)
+    assert got == want
+
+
+def _rows_bytes(b, n_rows, chunk=65536):
+    out = []
+    for lo in range(0, n_rows, chunk):
+        hi = min(n_rows, lo + chunk)
+        arr = (abi.RaRowState * (hi - lo))()
+        for i in range(hi - lo):
+            arr[i].row = lo + i
+        b._check(b._fn("read_rows")(b._h, arr, hi - lo), "read_rows")
+        out.append(bytes(arr))
+    return b"".join(out)
+
+
+def _bootstrap(b):
+    b.reset_empty()
+    b.step([abi.ev_simple(b.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(b.n_groups)])
+
+
+FLOODS = [
+    (64, 3, 60, 1, 0),
+    (1000, 5, 80, 1, 0),
+    (1000, 5, 120, 2, 10),
+    (500, 7, 100, 1, 20),
+    (333, 1, 20, 3, 0),
+    (200, 5, 150, 64, 30),     # 64-entry commands (config 4 shape), frequent elections
+]
+
+
+@pytest.mark.parametrize("g,m,steps,cmds,permille", FLOODS)
+def test_flood_parity_emu(g, m, steps, cmds, permille):
+    o = Oracle(g, m, route_on_device=True)
+    e = Emu(g, m, route_on_device=True)
+    for b in (o, e):
+        _bootstrap(b)
+    for part in (steps // 3, steps - steps // 3):
+        o.flood(part, cmds, permille, seed=42, threads=2)
+        e.flood(part, cmds, permille, seed=42)
+    assert e.counters() == o.counters()
+    assert o.counters()["commits"] > 0
+    ro, re_ = _rows_bytes(o, o.n_rows), _rows_bytes(e, e.n_rows)
+    sz = C.sizeof(abi.RaRowState)
+    first = next((i // sz for i in range(0, len(ro), sz) if ro[i:i + sz] != re_[i:i + sz]), -1)
+    assert re_ == ro, "first differing row: %d" % first
+
+
+def test_emu_fast_paths_carry_the_steady_state():
+    """The stall histogram of the emulated step kernel: in a clean flood well under 1 % of the events
+    leave the fast paths once leaders are elected (what keeps raft_general_kernel at ~3 % of a step)."""
+    e = Emu(500, 5, route_on_device=True)
+    _bootstrap(e)
+    e.flood(30, 1, 0, seed=3)
+    h0, ev0 = sum(e.stall_histogram().values()), e.counters()["events"]
+    e.flood(50, 1, 0, seed=3)
+    h1, ev1 = sum(e.stall_histogram().values()), e.counters()["events"]
+    assert ev1 - ev0 > 50 * 500 * 5
+    assert (h1 - h0) <= 0.01 * (ev1 - ev0)
+
+
+def test_emu_step_input_validation():
+    e = Emu(4, 3)
+    r0, r1 = e.row_of(0, 0), e.row_of(1, 0)
+    with pytest.raises(abi.RaError) as ei:
+        e.step([abi.ev_command(r0), abi.ev_command(r1), abi.ev_command(r0)])
+    assert ei.value.status == abi.RA_E_UNGROUPED
+    with pytest.raises(abi.RaError) as ei:
+        e.step([abi.ev_command(r0) for _ in range(abi.RA_LOCAL_CAP + 1)])
+    assert ei.value.status == abi.RA_E_CAPACITY
+    with pytest.raises(abi.RaError) as ei:
+        e.step([abi.ev_command(10_000)])
+    assert ei.value.status == abi.RA_E_INVAL
+    msgs, notes = e.step([])
+    assert msgs == [] and notes == []
+    assert e.counters()["events"] == 0

@@ -2,14 +2,15 @@
 
 Each test cites the case it restates in /root/reference/test/ra_server_SUITE.erl (or the
 in-module eunit of src/ra_server.erl).  The same bodies run against the CPU oracle (pins
-the oracle, `-m "not gpu"`) and against the CUDA engine through the C ABI (`-m gpu`).
+the oracle, `-m "not gpu"`), against the engine's device logic compiled for the host (`emu`,
+tests/emu/, also CPU) and against the CUDA engine through the C ABI (`-m gpu`).
 Assertions on machine_state / payloads are dropped: ra_machine:apply/3 stays on the host.
 """
 import pytest
 
 from ra_suite import *  # noqa: F401,F403
 
-BACKENDS = ["oracle", pytest.param("engine", marks=pytest.mark.gpu)]
+BACKENDS = ["oracle", "emu", pytest.param("engine", marks=pytest.mark.gpu)]
 
 
 @pytest.fixture(params=BACKENDS)
