@@ -768,3 +768,64 @@ def test_leader_saw_append_entries_rpc_in_same_term(be):
     assert status(notes) & ST_FATAL
     (n,) = notes_of(notes, NOTE_STATUS)
     assert n.c == FATAL_LEADER_SAW_AER_SAME_TERM
+
+
+def test_candidate_receives_pre_vote(be):
+    """candidate_receives_pre_vote/1, :2503-2525."""
+    nd = Node(be, 5)
+    st = base_state(5)
+    st.votes = 1
+    TOKEN = 777
+    pv = ev_pre_vote(0, N1, 5, TOKEN, 3, 5)
+    role, s, msgs, _ = nd.handle_candidate(pv, st)          # not a lower index: granted
+    (m,) = msgs
+    assert role == CANDIDATE and (m.type, m.c, m.d) == (EV_PRE_VOTE_RES, TOKEN, 1)
+    role, s, msgs, _ = nd.handle_candidate(ev_pre_vote(0, N1, 5, TOKEN, 2, 5), st)   # lower index: refused
+    (m,) = msgs
+    assert role == CANDIDATE and (m.type, m.c, m.d) == (EV_PRE_VOTE_RES, TOKEN, 0)
+    role, s, msgs, _ = nd.handle_candidate(ev_pre_vote(0, N1, 6, TOKEN, 3, 5), st)   # higher term: abdicates
+    assert (role, s.current_term) == (FOLLOWER, 6)
+
+
+def test_leader_receives_pre_vote(be):
+    """leader_receives_pre_vote/1, :2527-2546: an rpc to every peer at once, abdication on a higher term."""
+    nd = Node(be, 5)
+    st = base_state(5)
+    st.votes = 1
+    pv = ev_pre_vote(0, N1, 5, 31337, 3, 5)
+    role, s, msgs, _ = nd.handle_leader(pv, st)
+    rpcs = of_type(msgs, EV_AER)
+    assert role == LEADER and sorted(m.row for m in rpcs) == [N2, N3, N4, N5]
+    assert all((m.term, m.a, m.b, m.c, m.n) == (5, 3, 5, 3, 0) for m in rpcs)
+    role, s, msgs, _ = nd.handle_leader(ev_pre_vote(0, N1, 6, 31337, 3, 5), st)
+    assert (role, s.current_term) == (FOLLOWER, 6)
+
+
+def test_persist_last_applied_with_unwritten(be):
+    """persist_last_applied_with_unwritten/1, :3771-3793, the part that is ra_server's: a follower
+    applies a committed entry before its own written event (last_written stays {0,0});
+    persisted_last_applied itself (ra_log_meta) stays on the host."""
+    nd = Node(be, 3)
+    st = empty_state(3, N1)
+    aer = ev_aer(0, N1, 1, 0, 0, 1, [1])
+    role, s, msgs, notes = nd.handle_follower(aer, st)
+    assert (role, s.leader_slot, s.current_term, s.commit_index, s.last_applied) == (FOLLOWER, N1, 1, 1, 1)
+    assert (s.last_written_index, s.last_written_term) == (0, 0)
+    (ap,) = notes_of(notes, NOTE_APPLY)
+    assert (ap.a, ap.b) == (1, 1)
+    role, s2, msgs, notes = nd.handle_follower(ev_written(0, 1, 1, 1), s)
+    assert (s2.last_written_index, s2.last_written_term, s2.last_applied) == (1, 1, 1)
+
+
+def test_follower_state_resets_peer_status(be):
+    """follower_state_resets_peer_status/1, :2321-2350: handle_state_enter(follower, leader, _) puts
+    every peer status back to normal.  The engine runs become/3 as part of the role change (not in
+    `pure` mode, where one call is exactly one handle_<state>/2 clause)."""
+    nd = Node(be, 3, pure=False)
+    st = base_state(3)
+    st.peers[N2].status = PEER_SENDING_SNAPSHOT
+    st.peers[N3].status = PEER_DISCONNECTED
+    role, s, msgs, notes = nd.handle_leader(ev_request_vote(0, N2, 6, 3, 5), st)    # higher term: steps down
+    assert (role, s.current_term) == (FOLLOWER, 6)
+    assert [s.peers[p].status for p in (N2, N3)] == [PEER_NORMAL, PEER_NORMAL]
+    assert status(notes) & ST_ROLE_CHANGED
