@@ -94,6 +94,7 @@ FLOODS = [
     (500, 7, 100, 1, 20),    # config 5 shape
     (10000, 5, 60, 1, 10),   # config 2 size
     (333, 1, 20, 3, 0),
+    (200, 5, 150, 64, 30),   # 64-entry commands (config 4 shape), frequent elections
 ]
 
 

@@ -13,30 +13,31 @@ from ra_b200 import abi
 pytestmark = pytest.mark.gpu
 
 CASES = [
-    # shards, members, local groups per slot, steps, election permille
-    (2, 5, 300, 80, 10),
-    (4, 3, 128, 60, 0),
-    (8, 5, 96, 80, 20),
-    (3, 7, 100, 60, 10),
-    (5, 5, 200, 50, 10),      # N == M: every member of a group on its own shard
-    (8, 5, 256, 70, 10),      # the shape of tests/test_sharded_nccl.py at world 8
+    # shards, members, local groups per slot, steps, election permille, commands per leader and step
+    (2, 5, 300, 80, 10, 1),
+    (4, 3, 128, 60, 0, 1),
+    (8, 5, 96, 80, 20, 1),
+    (3, 7, 100, 60, 10, 1),
+    (5, 5, 200, 50, 10, 1),   # N == M: every member of a group on its own shard
+    (8, 5, 256, 70, 10, 1),   # the shape of tests/test_sharded_nccl.py at world 8
+    (8, 5, 64, 60, 10, 64),   # 64-entry pipelined AppendEntries, 8 shards
 ]
 
 
 @pytest.mark.parametrize("transport", ["buckets", "peer"])
-@pytest.mark.parametrize("n,m,gl,steps,permille", CASES)
-def test_sharded_flood_equals_unsharded_oracle(n, m, gl, steps, permille, transport):
+@pytest.mark.parametrize("n,m,gl,steps,permille,cmds", CASES)
+def test_sharded_flood_equals_unsharded_oracle(n, m, gl, steps, permille, cmds, transport):
     from ra_b200.sharded import LocalPeerTransport, LocalTransport, Shard, ShardedFlood
     shards = [Shard(gl, m, n, k, buckets=(transport == "buckets")) for k in range(n)]
     fl = ShardedFlood(LocalTransport(shards) if transport == "buckets" else LocalPeerTransport(shards))
     fl.bootstrap()
-    fl.run(steps, 1, permille, seed=77)
+    fl.run(steps, cmds, permille, seed=77)
     fl.sync()
     g = n * gl
     o = Oracle(g, m, route_on_device=True)
     o.reset_empty()
     o.step([abi.ev_simple(o.row_of(i, 0), abi.EV_ELECTION_TIMEOUT) for i in range(g)])
-    o.flood(steps, 1, permille, seed=77, threads=8)
+    o.flood(steps, cmds, permille, seed=77, threads=8)
     want = {r.row: r.key()[1:] for r in o.read_rows(range(o.n_rows))}
     seen = 0
     for s in shards:
