@@ -12,7 +12,9 @@
 #include <thread>
 #include <omp.h>
 #include <vector>
+#ifndef RA_NO_CUDA
 #include <cuda_runtime.h>
+#endif
 #include "../../include/ra_engine.h"
 
 typedef unsigned long long u64;
@@ -42,6 +44,7 @@ struct ra_hostsim {
     u64 h2d, d2h, calls; double seconds;
 };
 
+#ifndef RA_NO_CUDA
 extern "C" void* ra_engine_alloc_host(size_t bytes)
 {
     void* p = nullptr;
@@ -49,6 +52,10 @@ extern "C" void* ra_engine_alloc_host(size_t bytes)
     return p;
 }
 extern "C" void ra_engine_free_host(void* p) { if (p) cudaFreeHost(p); }
+#else   /* tests/emu: this caller over the host emulation of the engine, plain host memory */
+extern "C" void* ra_engine_alloc_host(size_t bytes) { return malloc(bytes ? bytes : 16); }
+extern "C" void ra_engine_free_host(void* p) { free(p); }
+#endif
 
 extern "C" int ra_hostsim_create(ra_engine* e, ra_hostsim** out)
 {

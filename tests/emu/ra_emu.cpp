@@ -332,3 +332,11 @@ extern "C" int ra_emu_stall_histogram(ra_emu* e, uint64_t* out128)
     memcpy(out128, e->C.counters + 8, 128 * sizeof(u64));
     return RA_OK;
 }
+
+/* ---- ra_hostsim (ra_b200/csrc/host_flood.cu, the host-side caller of the ABI used by the e2e
+ * benchmark) over this emulation: the file is compiled into this library with RA_NO_CUDA and
+ * reaches the "engine" through these three forwarding entry points. */
+extern "C" int ra_engine_step(ra_engine* e, const ra_event* ev, size_t n_ev, ra_event* msgs, size_t msgs_cap,
+                              size_t* n_msgs, ra_note* notes, size_t notes_cap, size_t* n_notes)
+{ return ra_emu_step((ra_emu*)e, ev, n_ev, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes); }
+extern "C" int ra_engine_get_cfg(ra_engine* e, ra_engine_cfg* out) { return ra_emu_get_cfg((ra_emu*)e, out); }

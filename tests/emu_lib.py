@@ -47,3 +47,34 @@ class Emu(abi.Backend):
         arr = (C.c_uint64 * 128)()
         self._check(lib().ra_emu_stall_histogram(self._h, arr), "stall_histogram")
         return {(i // 16, i % 16): int(v) for i, v in enumerate(arr) if v}
+
+
+class EmuHostFlood:
+    """ra_hostsim (ra_b200/csrc/host_flood.cu, the host-side ABI caller of the e2e benchmark) compiled
+    into the emulation library and driving an Emu through its step() entry point."""
+
+    def __init__(self, emu: Emu):
+        self.e = emu
+        l = lib()
+        l.ra_hostsim_create.restype = C.c_int
+        l.ra_hostsim_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        l.ra_hostsim_run.restype = C.c_int
+        l.ra_hostsim_run.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int]
+        l.ra_hostsim_stats.restype = C.c_int
+        l.ra_hostsim_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        l.ra_hostsim_destroy.restype = None
+        l.ra_hostsim_destroy.argtypes = [C.c_void_p]
+        self._h = C.c_void_p()
+        emu._check(l.ra_hostsim_create(emu._h, C.byref(self._h)), "hostsim_create")
+
+    def run(self, n_steps: int, cmds: int = 1, permille: int = 0, seed: int = 1, bootstrap: bool = False) -> dict:
+        self.e._check(lib().ra_hostsim_run(self._h, n_steps, cmds, permille, seed, 1 if bootstrap else 0), "hostsim_run")
+        h2d, d2h, calls, sec = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_double(0)
+        lib().ra_hostsim_stats(self._h, C.byref(h2d), C.byref(d2h), C.byref(sec), C.byref(calls))
+        return dict(h2d_bytes=int(h2d.value), d2h_bytes=int(d2h.value), engine_calls=int(calls.value))
+
+    def close(self) -> None:
+        if self._h:
+            lib().ra_hostsim_destroy(self._h)
+            self._h = C.c_void_p()

@@ -118,3 +118,30 @@ def test_emu_step_input_validation():
     msgs, notes = e.step([])
     assert msgs == [] and notes == []
     assert e.counters()["events"] == 0
+
+
+@pytest.mark.parametrize("threads", ["1", "4"])
+def test_host_driven_flood_equals_device_flood_emu(threads, monkeypatch):
+    """ra_hostsim_run (the product's host-side caller, every step through step() with host buffers)
+    leaves exactly the rows the device-side flood leaves, and both equal the oracle -- the CPU twin
+    of tests/test_parity_gpu.py::test_host_driven_flood_equals_device_flood."""
+    from emu_lib import EmuHostFlood
+    monkeypatch.setenv("RA_HOSTSIM_THREADS", threads)
+    g, m, steps = 1200, 5, 70
+    a = Emu(g, m, route_on_device=True)
+    b = Emu(g, m, route_on_device=True)
+    o = Oracle(g, m, route_on_device=True)
+    _bootstrap(a)
+    a.flood(steps, 1, 10, seed=5)
+    _bootstrap(o)
+    o.flood(steps, 1, 10, seed=5, threads=2)
+    b.reset_empty()
+    hf = EmuHostFlood(b)
+    st = hf.run(steps, 1, 10, seed=5, bootstrap=True)
+    assert st["h2d_bytes"] > 0 and st["d2h_bytes"] > 0 and st["engine_calls"] == steps + 1
+    ca, cb, co = a.counters(), b.counters(), o.counters()
+    assert ca == co
+    for k in ("events", "commits", "applied", "msgs_out", "elections_won"):
+        assert cb[k] == ca[k]
+    assert _rows_bytes(b, b.n_rows) == _rows_bytes(a, a.n_rows)
+    hf.close()
