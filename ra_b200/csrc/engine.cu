@@ -1,8 +1,10 @@
 // engine.cu -- C ABI (include/ra_engine.h) of the B200 batched multi-Raft engine.
 //
-// Host side: owns the HBM Struct-of-Arrays, stages host buffers, launches
-//   raft_step_kernel  -- the hot path (raft_step.cuh), one thread per member row
-//   ingest / gather   -- flat host batch <-> per-row slots (plumbing for ra_engine_step)
+// Host side: owns the HBM Struct-of-Arrays, stages host buffers, launches per step
+//   raft_step_kernel     -- the hot path: one thread per member row, steady-state fast paths
+//   raft_general_kernel  -- the rows that left the fast paths, one thread per stalled row
+// (device logic: raft_step.cuh, row helpers: raft_row.cuh) and, around ra_engine_step,
+//   ingest / pack + scan + gather -- flat host batch <-> per-row slots
 // There is no CPU fallback: without a CUDA device ra_engine_create fails with
 // RA_E_NODEVICE and nothing else works.
 #include <cuda_runtime.h>
@@ -20,27 +22,14 @@
 // the hot kernel
 // ------------------------------------------------------------------------------------------
 #ifndef NST
-#define NST 3                               // shared-memory stages per warp: NST x 2 KB record tiles in flight
+#define NST 3                               // shared-memory stages per warp: NST record tiles (1 or 2 KB) in flight
 #endif
 #ifndef MINB
 #define MINB 5                              // CTAs per SM the register allocation is held to: 20 warps,
                                             // <= 96 registers (no spills), 5 x 39 KB of shared memory
 #endif
 #define TILE_BYTES (RT * 64)
-// bytes of a record tile worth fetching: heads only (chunks 0-1) unless a record of the tile has a tail.
-// tail_mask: bit s = some record from sender slot s, bit 8 + k = host slot k (planes 32..)
-__device__ __forceinline__ unsigned plane_bytes(unsigned tail_mask, unsigned p)
-{
-    const unsigned bit = p < 32 ? (p / RA_MBOX_DEPTH) : (8u + p - 32u);
-    return ((tail_mask >> bit) & 1u) ? TILE_BYTES : TILE_BYTES / 2;
-}
 #define WARPS (CTA_T / 32)
-
-__device__ __forceinline__ u64 warp_sum64(u64 v)
-{
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 // ---- TMA (cp.async.bulk) + mbarrier, sm_90+/sm_100a --------------------------------------
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
