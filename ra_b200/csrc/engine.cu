@@ -356,22 +356,7 @@ __global__ void deliver_kernel(const Cols C, const int buf, const ra_event* inbo
     const u32 b = blockIdx.y;
     const u32 n = counts[b] < cap ? counts[b] : cap;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const Rec r = ld_rec(&inbox[(size_t)b * cap + i]);
-        const u32 row = R_row(r), from = R_from(r), k = (u32)(r.w0.y >> 32);
-        if (row >= C.rows || from >= C.members || k >= RA_MBOX_DEPTH) continue;
-        const u32 tail = st_rec_plane(C.mbox[buf], C.tiles, from * RA_MBOX_DEPTH + k, row, r) ? 8u : 0u;
-        // byte `from` of the row's count word := max(old count, k + 1) | tail flag
-        u32* w = reinterpret_cast<u32*>(&C.mbox_cnt[buf][row]) + (from >> 2);
-        const u32 sh = 8u * (from & 3u);
-        u32 old = *w;
-        for (;;) {
-            const u32 ob = (old >> sh) & 0xffu;
-            const u32 nb = ((ob & 7u) >= k + 1 ? (ob & 7u) : k + 1) | (ob & 8u) | tail;
-            if (nb == ob) break;
-            const u32 seen = atomicCAS(w, old, (old & ~(0xffu << sh)) | (nb << sh));
-            if (seen == old) break;
-            old = seen;
-        }
+        deliver_record(C, buf, ld_rec(&inbox[(size_t)b * cap + i]));
     }
 }
 

@@ -29,4 +29,5 @@ static inline unsigned __activemask() { return 1u; }
 template <typename T> static inline unsigned __match_any_sync(unsigned, T) { return 1u; }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+static inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }

@@ -10,7 +10,9 @@
  * library is that the CPU test tier diffs the very source the GPU runs against the oracle
  * (tests/test_emu_parity.py), so a logic regression shows up before any GPU time is spent.
  *
- * Same C ABI as include/ra_engine.h with the prefix ra_emu_ (single shard only).
+ * Same C ABI as include/ra_engine.h with the prefix ra_emu_.  Shards: the bucket transport
+ * (ra_emu_set_outbox / ra_emu_deliver); the peer transport is the same stores through other
+ * base pointers and is left to the GPU tests.
  */
 #include <stdint.h>
 #include <stddef.h>
@@ -59,7 +61,7 @@ extern "C" int ra_emu_create(const ra_engine_cfg* cfg, ra_emu** out)
 {
     if (!cfg || !out || cfg->n_members < 1 || cfg->n_members > RA_MAX_MEMBERS || cfg->n_groups == 0) return RA_E_INVAL;
     if ((u64)cfg->n_groups * cfg->n_members > 0x7fffffffull) return RA_E_INVAL;
-    if (cfg->n_shards > 1) return RA_E_INVAL;                       // single shard only
+    if (cfg->n_shards > 1 && (!cfg->route_on_device || cfg->shard >= cfg->n_shards || cfg->n_shards > 64)) return RA_E_INVAL;
     ra_emu* e = (ra_emu*)calloc(1, sizeof(ra_emu));
     if (!e) return RA_E_NOMEM;
     e->cfg = *cfg;
@@ -72,7 +74,7 @@ extern "C" int ra_emu_create(const ra_engine_cfg* cfg, ra_emu** out)
     C.groups_inv = cfg->n_groups > 1 ? (u32)(0x100000000ull / cfg->n_groups) : 0xFFFFFFFFu;
     C.max_pipeline = e->cfg.max_pipeline_count; C.max_batch = e->cfg.max_aer_batch;
     C.routed = cfg->route_on_device ? 1 : 0; C.pure = cfg->pure ? 1 : 0;
-    C.n_shards = 1; C.shard = 0;
+    C.n_shards = cfg->n_shards > 1 ? cfg->n_shards : 1; C.shard = cfg->n_shards > 1 ? cfg->shard : 0;
     C.outbox = nullptr; C.out_cnt = nullptr; C.out_cap = 0;
     C.peer_mode = 0;
     for (int b = 0; b < 2; b++) for (int k = 0; k < 8; k++) { C.peer_mbox[b][k] = nullptr; C.peer_cnt[b][k] = nullptr; }
@@ -234,23 +236,51 @@ static bool step_row(const Cols& C, int cur, const FloodArgs& F, u32 r, StallCtx
     return stalled;
 }
 
-static void run_step(ra_emu* e, const FloodArgs& F)
+static int run_step(ra_emu* e, const FloodArgs& F)
 {
     const Cols& C = e->C;
+    if (C.n_shards > 1) {
+        if (!C.outbox) return RA_E_INVAL;                       // ra_emu_set_outbox first
+        memset(C.out_cnt, 0, C.n_shards * sizeof(u32));
+    }
     // same choice of specialisation as launch_step() in engine.cu
-    const int tr = !C.routed ? TR_HOST : TR_LOCAL;
+    const int tr = !C.routed ? TR_HOST : (C.n_shards > 1 ? TR_BUCKET : TR_LOCAL);
     for (u32 r = 0; r < C.rows; r++) {
         StallCtx ctx;
         bool stalled;
-        if (C.members == 5) stalled = tr == TR_LOCAL ? step_row<MK_MM(5, TR_LOCAL)>(C, e->cur, F, r, ctx)
-                                                     : step_row<MK_MM(5, TR_HOST)>(C, e->cur, F, r, ctx);
-        else stalled = step_row<MK_MM(0, TR_RUNTIME)>(C, e->cur, F, r, ctx);
+        if (C.members == 5) {
+            switch (tr) {
+            case TR_LOCAL:  stalled = step_row<MK_MM(5, TR_LOCAL)>(C, e->cur, F, r, ctx); break;
+            case TR_BUCKET: stalled = step_row<MK_MM(5, TR_BUCKET)>(C, e->cur, F, r, ctx); break;
+            default:        stalled = step_row<MK_MM(5, TR_HOST)>(C, e->cur, F, r, ctx); break;
+            }
+        } else stalled = step_row<MK_MM(0, TR_RUNTIME)>(C, e->cur, F, r, ctx);
         // the general kernel runs after the step kernel; rows only ever write to OTHER rows' mailboxes of
         // the NEXT step, so handling a stalled row right away is the same thing
         if (stalled) general_row(C, e->cur, F, ctx);
     }
     if (C.routed) e->cur ^= 1;
     e->steps++;
+    return RA_OK;
+}
+
+extern "C" int ra_emu_set_outbox(ra_emu* e, void* outbox, uint32_t* counts, uint32_t cap)
+{
+    if (!e || e->C.n_shards < 2 || !outbox || !counts || !cap) return RA_E_INVAL;
+    e->C.outbox = (ra_event*)outbox; e->C.out_cnt = counts; e->C.out_cap = cap;
+    return RA_OK;
+}
+
+extern "C" int ra_emu_deliver(ra_emu* e, const void* inbox, const uint32_t* counts, uint32_t cap)
+{
+    if (!e || e->C.n_shards < 2 || !inbox || !counts || !cap) return RA_E_INVAL;
+    const ra_event* in = (const ra_event*)inbox;
+    // e->cur is the buffer the next step reads: the one the last step's senders wrote into
+    for (u32 b = 0; b < e->C.n_shards; b++) {
+        const u32 n = counts[b] < cap ? counts[b] : cap;
+        for (u32 i = 0; i < n; i++) deliver_record(e->C, e->cur, ld_rec(&in[(size_t)b * cap + i]));
+    }
+    return RA_OK;
 }
 
 extern "C" int ra_emu_step(ra_emu* e, const ra_event* ev, size_t n_ev,
@@ -282,7 +312,7 @@ extern "C" int ra_emu_step(ra_emu* e, const ra_event* ev, size_t n_ev,
         return err == 1 ? RA_E_UNGROUPED : (err == 2 ? RA_E_CAPACITY : RA_E_INVAL);
     }
     FloodArgs F; memset(&F, 0, sizeof F);
-    run_step(e, F);
+    { const int rc = run_step(e, F); if (rc) return rc; }
     // pack_counts + scan + gather: per-row slots -> flat arrays ordered by (row, seq)
     size_t tm = 0, tn = 0;
     for (u32 r = 0; r < R; r++) { tm += C.out_n[r] & 0xffffu; tn += C.out_n[r] >> 16; }
@@ -311,7 +341,8 @@ extern "C" int ra_emu_flood(ra_emu* e, uint32_t n_steps, uint32_t cmds_per_step,
     for (u32 t = 0; t < n_steps; t++) {
         FloodArgs F; F.on = 1; F.cmds = cmds_per_step; F.permille = election_permille; F._p = 0;
         F.seed = seed; F.step = e->step_no + t;
-        run_step(e, F);
+        const int rc = run_step(e, F);
+        if (rc) return rc;
     }
     e->step_no += n_steps;
     return RA_OK;

@@ -78,3 +78,61 @@ class EmuHostFlood:
         if self._h:
             lib().ra_hostsim_destroy(self._h)
             self._h = C.c_void_p()
+
+
+class EmuShards:
+    """N emulated shards in this process with the bucket transport: the CPU twin of
+    ra_b200.sharded.Shard + LocalTransport + ShardedFlood (member (g, s) on shard (g + s) mod N)."""
+
+    def __init__(self, n_shards: int, groups_local: int, members: int, cap: int = 4096, **kw):
+        l = lib()
+        l.ra_emu_set_outbox.restype = C.c_int
+        l.ra_emu_set_outbox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        l.ra_emu_deliver.restype = C.c_int
+        l.ra_emu_deliver.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        self.n, self.gl, self.m, self.cap = n_shards, groups_local, members, cap
+        self.shards = [Emu(groups_local, members, route_on_device=True, n_shards=n_shards, shard=k, **kw)
+                       for k in range(n_shards)]
+        self.outbox = [(abi.RaEvent * (n_shards * cap))() for _ in range(n_shards)]
+        self.inbox = [(abi.RaEvent * (n_shards * cap))() for _ in range(n_shards)]
+        self.out_cnt = [(C.c_uint32 * n_shards)() for _ in range(n_shards)]
+        self.in_cnt = [(C.c_uint32 * n_shards)() for _ in range(n_shards)]
+        for k, s in enumerate(self.shards):
+            s._check(l.ra_emu_set_outbox(s._h, self.outbox[k], self.out_cnt[k], cap), "set_outbox")
+
+    def exchange(self) -> None:
+        sz = C.sizeof(abi.RaEvent)
+        for b in range(self.n):
+            for a in range(self.n):
+                if a == b:
+                    self.in_cnt[b][a] = 0
+                    continue
+                cnt = min(int(self.out_cnt[a][b]), self.cap)
+                C.memmove(C.byref(self.inbox[b], a * self.cap * sz), C.byref(self.outbox[a], b * self.cap * sz), cnt * sz)
+                self.in_cnt[b][a] = self.out_cnt[a][b]
+        for b, s in enumerate(self.shards):
+            s._check(lib().ra_emu_deliver(s._h, self.inbox[b], self.in_cnt[b], self.cap), "deliver")
+
+    def bootstrap(self) -> None:
+        for s in self.shards:
+            s.reset_empty()
+        for s in self.shards:
+            s.step([abi.ev_simple(s.row_of(q, 0), abi.EV_ELECTION_TIMEOUT) for q in range(self.gl)])
+        self.exchange()
+
+    def run(self, n_steps: int, cmds: int = 1, permille: int = 0, seed: int = 1) -> None:
+        for _ in range(n_steps):
+            for s in self.shards:
+                s.flood(1, cmds, permille, seed)
+            self.exchange()
+
+    def global_row(self, shard: int, local_row: int) -> int:
+        slot, q = divmod(local_row, self.gl)
+        return slot * (self.n * self.gl) + self.n * q + ((shard - slot) % self.n)
+
+    def counters(self) -> dict:
+        tot: dict = {}
+        for s in self.shards:
+            for k, v in s.counters().items():
+                tot[k] = tot.get(k, 0) + v
+        return tot

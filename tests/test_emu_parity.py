@@ -145,3 +145,40 @@ def test_host_driven_flood_equals_device_flood_emu(threads, monkeypatch):
         assert cb[k] == ca[k]
     assert _rows_bytes(b, b.n_rows) == _rows_bytes(a, a.n_rows)
     hf.close()
+
+
+SHARDED = [
+    # shards, members, local groups per slot, steps, election permille, commands per leader and step
+    (2, 5, 96, 60, 10, 1),
+    (4, 3, 64, 50, 0, 1),
+    (8, 5, 32, 60, 20, 1),
+    (3, 7, 40, 50, 10, 1),
+    (8, 5, 64, 60, 10, 64),   # the config-4-shaped case of tests/test_sharded_gpu.py
+]
+
+
+@pytest.mark.parametrize("n,m,gl,steps,permille,cmds", SHARDED)
+def test_sharded_emu_equals_unsharded_oracle(n, m, gl, steps, permille, cmds):
+    """Members of a group on different shards (bucket transport: emit into per-destination buckets,
+    exchange, deliver) must leave every member identical to the UNSHARDED oracle run -- the CPU twin
+    of tests/test_sharded_gpu.py, same device logic."""
+    from emu_lib import EmuShards
+    fl = EmuShards(n, gl, m)
+    fl.bootstrap()
+    fl.run(steps, cmds, permille, seed=77)
+    g = n * gl
+    o = Oracle(g, m, route_on_device=True)
+    o.reset_empty()
+    o.step([abi.ev_simple(o.row_of(i, 0), abi.EV_ELECTION_TIMEOUT) for i in range(g)])
+    o.flood(steps, cmds, permille, seed=77, threads=2)
+    want = {r.row: r.key()[1:] for r in o.read_rows(range(o.n_rows))}
+    seen = 0
+    for k, s in enumerate(fl.shards):
+        for r in s.read_rows(range(s.n_rows)):
+            assert r.key()[1:] == want[fl.global_row(k, r.row)], (k, r.row)
+            seen += 1
+    assert seen == g * m
+    co, ce = o.counters(), fl.counters()
+    for key in ("events", "commits", "applied", "msgs_out", "msgs_dropped", "elections_won", "fatal_rows"):
+        assert ce[key] == co[key], key
+    assert co["commits"] > 0 and co["msgs_dropped"] == 0
