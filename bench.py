@@ -55,7 +55,7 @@ def hbm_peak():
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region.
 
-    Primary source: NVML polled from a thread (~1 kHz, so a 20 ms region still gets samples);
+    Primary source: NVML polled from a thread (~500 Hz, so a 20 ms region still gets samples);
     secondary: an `nvidia-smi -lms` child (its first line can take longer than the region)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -105,7 +105,7 @@ class ClockSampler:
                 except Exception:
                     rs = 0
                 self.nv.append((float(sm), mx, rs))
-                time.sleep(0.0005)
+                time.sleep(0.002)          # ~500 Hz: plenty for a 20 ms region, negligible GIL pressure
         except Exception:
             return
 
