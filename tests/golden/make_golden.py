@@ -89,7 +89,48 @@ def unpack_batches(blob: bytes):
     return out
 
 
+FLOODS = [
+    # groups, members, steps, commands per leader and step, election permille, seed  (device-routed flood)
+    (64, 3, 60, 1, 0, 42),
+    (1000, 5, 120, 2, 10, 42),
+    (500, 7, 100, 1, 20, 42),
+    (200, 5, 150, 64, 30, 42),
+    (10000, 5, 60, 1, 10, 42),       # BASELINE.json configs[1] size
+    (100000, 5, 40, 1, 10, 9),       # configs[2] size
+]
+
+
+def rows_bytes_digest(b, chunk=65536) -> str:
+    h = hashlib.sha256()
+    for lo in range(0, b.n_rows, chunk):
+        hi = min(b.n_rows, lo + chunk)
+        arr = (abi.RaRowState * (hi - lo))()
+        for i in range(hi - lo):
+            arr[i].row = lo + i
+        b._check(b._fn("read_rows")(b._h, arr, hi - lo), "read_rows")
+        h.update(bytes(arr))
+    return h.hexdigest()
+
+
+def flood_digest(b, g, m, steps, cmds, permille, seed, **kw):
+    b.reset_empty()
+    b.step([abi.ev_simple(b.row_of(i, 0), abi.EV_ELECTION_TIMEOUT) for i in range(g)])
+    for part in (steps // 3, steps - steps // 3):          # two calls: the step counter carries over
+        b.flood(part, cmds, permille, seed=seed, **kw)
+    return rows_bytes_digest(b), b.counters()
+
+
 def main():
+    floods = []
+    for (g, m, steps, cmds, permille, seed) in FLOODS:
+        o = Oracle(g, m, route_on_device=True)
+        rows, counters = flood_digest(o, g, m, steps, cmds, permille, seed, threads=8)
+        floods.append(dict(groups=g, members=m, steps=steps, cmds=cmds, permille=permille, seed=seed,
+                           rows_sha256=rows, counters=counters))
+        print("flood", g, m, steps, cmds, permille, counters["commits"])
+        o.close()
+    with open(os.path.join(HERE, "floods.json"), "w") as f:
+        json.dump(floods, f, indent=0)
     for name, (g, m, steps, seed, knobs, cfg) in TRACES.items():
         batches = trace_gen.generate(lambda gg, mm: Oracle(gg, mm, **cfg), g, m, steps, seed, **knobs)
         per_step, rows, counters = replay_digests(Oracle(g, m, **cfg), batches)

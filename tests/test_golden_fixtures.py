@@ -39,3 +39,21 @@ def test_fixtures_match_their_generator():
     g, m, steps, seed, knobs, cfg = G.TRACES[name]
     batches = trace_gen.generate(lambda gg, mm: Oracle(gg, mm, **cfg), g, m, steps, seed, **knobs)
     assert G.pack_batches(batches) == open(os.path.join(HERE, "golden", name + ".events.z"), "rb").read()
+
+
+FLOODS = json.load(open(os.path.join(HERE, "golden", "floods.json")))
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("case", FLOODS, ids=lambda c: "%dx%d" % (c["groups"], c["members"]))
+def test_golden_flood(case, backend):
+    """Device-routed floods (mailboxes + host model inside the engine) against the committed sha256 of
+    every member's final ra_row_state and the counters, up to BASELINE.json's 100k x 5."""
+    g, m = case["groups"], case["members"]
+    if backend != "engine" and g * m > 60_000:
+        pytest.skip("CPU tier: the big floods are for the GPU")
+    b = make_backend(backend, g, m, route_on_device=True)
+    kw = dict(threads=4) if backend == "oracle" else {}
+    rows, counters = G.flood_digest(b, g, m, case["steps"], case["cmds"], case["permille"], case["seed"], **kw)
+    assert counters == case["counters"]
+    assert rows == case["rows_sha256"]
