@@ -262,6 +262,19 @@ int  ra_engine_get_cfg(ra_engine* e, ra_engine_cfg* out);
 
 /* = ra_server:init/1 values (src/ra_server.erl:434-457) + log tail, per row. */
 int  ra_engine_load_rows(ra_engine* e, const ra_row_state* rows, size_t n);
+/* What load_rows requires of the log view of a row (RA_E_INVAL otherwise): n_runs <= RA_MAX_RUNS; the log
+ * is empty (first_index > last_index, n_runs = 0) or its runs start at first_index, ascend strictly, stay
+ * inside [first_index, last_index], carry non-decreasing terms and end in last_term; slots < RA_MAX_MEMBERS. */
+static inline int ra_row_state_valid(const ra_row_state* s)
+{
+    if (s->n_runs > RA_MAX_RUNS || s->n_members < 1 || s->n_members > RA_MAX_MEMBERS || s->self_slot >= s->n_members) return 0;
+    if (s->n_runs == 0) return s->first_index > s->last_index;
+    if (s->first_index > s->last_index || s->run_start[0] != s->first_index) return 0;
+    for (uint32_t k = 1; k < s->n_runs; k++)
+        if (s->run_start[k] <= s->run_start[k - 1] || s->run_term[k] < s->run_term[k - 1]) return 0;
+    return s->run_start[s->n_runs - 1] <= s->last_index && s->run_term[s->n_runs - 1] == s->last_term;
+}
+
 /* Convenience: every row := ra_server_SUITE:empty_state/2 (:4022-4032), current_term 0. */
 int  ra_engine_reset_empty(ra_engine* e);
 /* For the parity diff. `rows[i].row` selects the row; the rest is filled in. */

@@ -1350,7 +1350,7 @@ int ra_oracle_load_rows(ra_oracle *o, const ra_row_state *rows, size_t n)
 {
     for (size_t i = 0; i < n; i++) {
         const ra_row_state *s = &rows[i];
-        if (s->row >= o->n_rows || s->n_runs > RA_MAX_RUNS) return RA_E_INVAL;
+        if (s->row >= o->n_rows || s->n_members != o->cfg.n_members || !ra_row_state_valid(s)) return RA_E_INVAL;
         member_t *m = &o->m[s->row];
         member_init_empty(o, m, s->row);
         m->role = s->role; m->self_slot = s->self_slot; m->n_members = s->n_members;

@@ -566,7 +566,7 @@ extern "C" int ra_engine_load_rows(ra_engine* e, const ra_row_state* rows, size_
     if (!e || (!rows && n)) return RA_E_INVAL;
     if (n == 0) return RA_OK;
     for (size_t i = 0; i < n; i++)
-        if (rows[i].row >= e->C.rows || rows[i].n_runs > RA_MAX_RUNS || rows[i].n_members != e->C.members) return RA_E_INVAL;
+        if (rows[i].row >= e->C.rows || rows[i].n_members != e->C.members || !ra_row_state_valid(&rows[i])) return RA_E_INVAL;
     CK(cudaSetDevice(e->cfg.device));
     int rc = ensure(e, &e->d_rows, &e->d_rows_cap, n); if (rc) return rc;
     CK(cudaMemcpyAsync(e->d_rows, rows, n * sizeof(ra_row_state), cudaMemcpyHostToDevice, e->stream));

@@ -114,7 +114,7 @@ extern "C" int ra_emu_load_rows(ra_emu* e, const ra_row_state* rows, size_t n)
 {
     if (!e || (!rows && n)) return RA_E_INVAL;
     for (size_t i = 0; i < n; i++)
-        if (rows[i].row >= e->C.rows || rows[i].n_runs > RA_MAX_RUNS || rows[i].n_members != e->C.members) return RA_E_INVAL;
+        if (rows[i].row >= e->C.rows || rows[i].n_members != e->C.members || !ra_row_state_valid(&rows[i])) return RA_E_INVAL;
     for (size_t i = 0; i < n; i++) load_row(e->C, rows[i]);
     return RA_OK;
 }

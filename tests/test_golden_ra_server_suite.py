@@ -829,3 +829,27 @@ def test_follower_state_resets_peer_status(be):
     assert (role, s.current_term) == (FOLLOWER, 6)
     assert [s.peers[p].status for p in (N2, N3)] == [PEER_NORMAL, PEER_NORMAL]
     assert status(notes) & ST_ROLE_CHANGED
+
+
+def test_load_rows_rejects_inconsistent_log_views(be):
+    """ra_row_state_valid (include/ra_engine.h): what load_rows requires of a row's log view."""
+    b = make_backend(be, 1, 3)
+    ok = base_state(3)
+    b.load_rows([ok])
+
+    def bad(mut):
+        s = clone(ok)
+        mut(s)
+        with pytest.raises(abi.RaError) as ei:
+            b.load_rows([s])
+        assert ei.value.status == abi.RA_E_INVAL
+
+    bad(lambda s: setattr(s, "n_runs", 0))                          # entries but no runs
+    bad(lambda s: setattr(s, "last_term", 4))                       # last_term is not the last run's term
+    bad(lambda s: s.run_start.__setitem__(0, 1))                    # first run does not start at first_index
+    bad(lambda s: s.run_start.__setitem__(2, 1))                    # run starts not ascending
+    bad(lambda s: s.run_term.__setitem__(2, 0))                     # terms decreasing
+    bad(lambda s: setattr(s, "last_index", 1))                      # a run starts beyond last_index
+    bad(lambda s: setattr(s, "n_members", 5))                       # not this engine's group size
+    bad(lambda s: setattr(s, "row", 99))                            # no such row
+    assert b.read_rows([ok.row])[0].key() == ok.key()               # the good row is untouched
