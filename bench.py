@@ -374,6 +374,9 @@ def run_engine(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": TRAFFIC_BYTES, "peak_source": peak_src,
+                     # also against the nominal HBM3e figure; and what the kernel really moves
+                     "peak_nominal": 8000.0, "frac_nominal": achieved / 8000.0,
+                     "achieved_traffic": (TRAFFIC_BYTES / 1e9) / (ms * 1e-3 / args.steps) if (TRAFFIC_BYTES and world == 1) else None,
                      "bytes_per_commit": bc, "algorithmic_bytes_per_launch": bc * commits / args.steps,
                      "kernel": "raft_step_kernel (+ raft_general_kernel for the rows that leave the fast paths)"},
     }
