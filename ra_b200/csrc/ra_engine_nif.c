@@ -1,6 +1,9 @@
 /* ra_engine_nif.c -- dirty-NIF shim over include/ra_engine.h.
  * erl_nif.h does not exist in this image, so the body is compiled only when the build defines
- * RA_HAVE_ERL_NIF on a box with an OTP toolchain; it is not built or tested here. */
+ * RA_HAVE_ERL_NIF on a box with an OTP toolchain; here it is only syntax-checked against a stub of
+ * the erl_nif API (tests/nif_stub/erl_nif.h, tests/test_abi_exports.py) -- it is not built or run.
+ * Records travel as binaries of the ABI structs (ra_event 64 B, ra_note 32 B, ra_row_state), which
+ * the Erlang side builds / matches with bit syntax. */
 #ifdef RA_HAVE_ERL_NIF
 #include <erl_nif.h>
 #include <string.h>
@@ -56,9 +59,65 @@ static ERL_NIF_TERM step_nif(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]
     return enif_make_tuple2(env, enif_make_binary(env, &m), enif_make_binary(env, &t));
 }
 
+static ERL_NIF_TERM status_term(ErlNifEnv* env, int rc)
+{
+    return rc ? enif_make_tuple2(env, enif_make_atom(env, "error"), enif_make_int(env, rc)) : enif_make_atom(env, "ok");
+}
+
+/* load_rows(Ref, RowsBin) -> ok | {error, Code}: RowsBin = << <<Row:sizeof(ra_row_state)/binary>> ... >> */
+static ERL_NIF_TERM load_rows_nif(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[])
+{
+    ra_engine** e; ErlNifBinary rows;
+    if (argc != 2 || !enif_get_resource(env, argv[0], ENG, (void**)&e) ||
+        !enif_inspect_binary(env, argv[1], &rows) || rows.size % sizeof(ra_row_state)) return enif_make_badarg(env);
+    return status_term(env, ra_engine_load_rows(*e, (const ra_row_state*)rows.data, rows.size / sizeof(ra_row_state)));
+}
+
+/* read_rows(Ref, RowIdsBin) -> RowsBin | {error, Code}: RowIdsBin = << <<Row:32/little>> ... >> */
+static ERL_NIF_TERM read_rows_nif(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[])
+{
+    ra_engine** e; ErlNifBinary ids, out;
+    if (argc != 2 || !enif_get_resource(env, argv[0], ENG, (void**)&e) ||
+        !enif_inspect_binary(env, argv[1], &ids) || ids.size % 4) return enif_make_badarg(env);
+    const size_t n = ids.size / 4;
+    if (!enif_alloc_binary(n * sizeof(ra_row_state), &out)) return enif_make_badarg(env);
+    memset(out.data, 0, out.size);
+    for (size_t i = 0; i < n; i++) memcpy(&((ra_row_state*)out.data)[i].row, ids.data + 4 * i, 4);
+    int rc = ra_engine_read_rows(*e, (ra_row_state*)out.data, n);
+    if (rc) { enif_release_binary(&out); return status_term(env, rc); }
+    return enif_make_binary(env, &out);
+}
+
+/* reset_empty(Ref) -> ok | {error, Code} */
+static ERL_NIF_TERM reset_empty_nif(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[])
+{
+    ra_engine** e;
+    if (argc != 1 || !enif_get_resource(env, argv[0], ENG, (void**)&e)) return enif_make_badarg(env);
+    return status_term(env, ra_engine_reset_empty(*e));
+}
+
+/* counters(Ref) -> #{events => _, commits => _, ...} | {error, Code} */
+static ERL_NIF_TERM counters_nif(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[])
+{
+    ra_engine** e; ra_counters c;
+    if (argc != 1 || !enif_get_resource(env, argv[0], ENG, (void**)&e)) return enif_make_badarg(env);
+    int rc = ra_engine_counters(*e, &c);
+    if (rc) return status_term(env, rc);
+    const char* names[] = {"events", "commits", "applied", "msgs_out", "msgs_dropped", "elections_won", "fatal_rows", "steps"};
+    const uint64_t vals[] = {c.events, c.commits, c.applied, c.msgs_out, c.msgs_dropped, c.elections_won, c.fatal_rows, c.steps};
+    ERL_NIF_TERM map = enif_make_new_map(env);
+    for (int i = 0; i < 8; i++)
+        enif_make_map_put(env, map, enif_make_atom(env, names[i]), enif_make_uint64(env, vals[i]), &map);
+    return map;
+}
+
 static ErlNifFunc funcs[] = {
     {"new", 3, new_nif, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+    {"load_rows", 2, load_rows_nif, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+    {"read_rows", 2, read_rows_nif, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+    {"reset_empty", 1, reset_empty_nif, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"step", 2, step_nif, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+    {"counters", 1, counters_nif, ERL_NIF_DIRTY_JOB_CPU_BOUND},
 };
 ERL_NIF_INIT(ra_engine_nif, funcs, load, NULL, NULL, NULL)
 #else

@@ -44,3 +44,13 @@ def test_no_device_fails_loudly():
     from ra_b200.engine import Engine, EngineUnavailable
     with pytest.raises(EngineUnavailable):
         Engine(1, 3)
+
+
+def test_nif_shim_compiles():
+    """ra_b200/csrc/ra_engine_nif.c (the dirty-NIF shim of INTEGRATION.md) against a stub of erl_nif.h:
+    a syntax / type check only -- there is no Erlang toolchain in this image."""
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-DRA_HAVE_ERL_NIF",
+                        "-I" + os.path.join(ROOT, "tests", "nif_stub"),
+                        os.path.join(ROOT, "ra_b200", "csrc", "ra_engine_nif.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
