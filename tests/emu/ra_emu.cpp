@@ -371,3 +371,16 @@ extern "C" int ra_engine_step(ra_engine* e, const ra_event* ev, size_t n_ev, ra_
                               size_t* n_msgs, ra_note* notes, size_t notes_cap, size_t* n_notes)
 { return ra_emu_step((ra_emu*)e, ev, n_ev, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes); }
 extern "C" int ra_engine_get_cfg(ra_engine* e, ra_engine_cfg* out) { return ra_emu_get_cfg((ra_emu*)e, out); }
+
+/* ---- the record-plane codec on its own: one ABI record through st_rec_plane / ld_rec_plane ---------- */
+extern "C" int ra_emu_codec_roundtrip(const ra_event* in, ra_event* out, int* had_tail)
+{
+    if (!in || !out) return RA_E_INVAL;
+    static thread_local ulonglong2 plane[4 * RT];              // one tile of one plane
+    memset(plane, 0xA5, sizeof plane);                         // stale bytes must not leak into the result
+    const u32 row = in->row & (RT - 1);
+    const bool tail = st_rec_plane(plane, 1, 0, row, ld_rec(in));
+    if (had_tail) *had_tail = tail ? 1 : 0;
+    st_rec(out, ld_rec_plane(plane, 1, 0, row));
+    return RA_OK;
+}

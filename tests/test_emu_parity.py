@@ -182,3 +182,45 @@ def test_sharded_emu_equals_unsharded_oracle(n, m, gl, steps, permille, cmds):
     for key in ("events", "commits", "applied", "msgs_out", "msgs_dropped", "elections_won", "fatal_rows"):
         assert ce[key] == co[key], key
     assert co["commits"] > 0 and co["msgs_dropped"] == 0
+
+
+def test_record_plane_codec_is_lossless():
+    """The 32-byte head / optional tail re-encoding of the record planes (raft_step.cuh: st_rec_plane,
+    rec_decode): every field the logic reads comes back bit-identical for arbitrary records, the shapes
+    the steady state relies on really are heads only, and stale bytes of the tile never leak."""
+    import random
+    from emu_lib import lib
+    l = lib()
+    l.ra_emu_codec_roundtrip.restype = C.c_int
+    l.ra_emu_codec_roundtrip.argtypes = [C.POINTER(abi.RaEvent), C.POINTER(abi.RaEvent), C.POINTER(C.c_int)]
+    rng = random.Random(7)
+    big = [0, 1, 2, 5, 2**32 - 1, 2**32, 2**63, 2**64 - 1]
+
+    def val():
+        return rng.choice(big) if rng.random() < 0.5 else rng.getrandbits(rng.choice([3, 16, 40, 64]))
+
+    def check(e, want_tail=None):
+        out, tail = abi.RaEvent(), C.c_int(-1)
+        assert l.ra_emu_codec_roundtrip(C.byref(e), C.byref(out), C.byref(tail)) == 0
+        # row and seq are positional inside a plane (the reader knows them), _pad is scratch
+        got = (out.type, out.from_slot, out.flags, out.n, out.n1, out.term, out.a, out.b, out.c, out.d, out.e)
+        exp = (e.type, e.from_slot, e.flags, e.n, e.n1, e.term, e.a, e.b, e.c, e.d, e.e)
+        assert got == exp and out._pad == 0
+        if want_tail is not None:
+            assert bool(tail.value) == want_tail
+    for _ in range(20000):
+        t = val()
+        e = abi.RaEvent(row=rng.randrange(1 << 20), type=rng.randrange(16), from_slot=rng.choice([0, 3, 7, 255]),
+                        flags=rng.choice([0, 1, 2, 8, 11]), n=rng.randrange(1 << 16), n1=rng.randrange(1 << 16),
+                        term=t, a=val(), b=rng.choice([t, val()]), c=rng.choice([t, 0, val()]),
+                        d=rng.choice([0, 1, t, val()]), e=rng.choice([0, 0, val()]))
+        check(e)
+    # the steady-state shapes are heads only; anything else carries a tail
+    check(abi.ev_aer(3, 1, 9, 100, 9, 98, [9, 9, 9]), want_tail=False)          # entries of the leader's term
+    check(abi.ev_aer(3, 1, 9, 100, 9, 98, []), want_tail=False)                  # empty AER (commit update)
+    check(abi.ev_aer_reply(3, 2, 9, True, 104, 103, 9), want_tail=False)
+    check(abi.ev_written(3, 9, 101, 103), want_tail=False)
+    check(abi.ev_command(3, 64), want_tail=False)
+    check(abi.ev_aer(3, 1, 9, 100, 8, 98, [9]), want_tail=True)                  # prev entry of an older term
+    check(abi.ev_aer(3, 1, 9, 100, 9, 98, [8, 9]), want_tail=True)               # two term runs
+    check(abi.ev_pre_vote(3, 1, 9, 77, 100, 9), want_tail=True)
