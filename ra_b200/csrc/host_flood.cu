@@ -131,8 +131,10 @@ static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u
             const u32 group = row % s->groups, slot = row / s->groups;
             u32 h = (u32)(mix64(seed ^ (s->step * 0x9E3779B97F4A7C15ull) ^ ((u64)group * 0xD1B54A32D192ED03ull)) >> 32);
             if (permille && (h % 1000u) < permille && ((h / 1000u) % s->members) == slot) fire = true;
-            u32 h2 = (u32)(mix64(seed ^ ((u64)row * 0xA24BAED4963EE407ull) ^ s->step) >> 32);
-            if (idle >= 8 + (h2 & 7u)) fire = true;
+            if (idle >= 8) {                                // the second hash only matters from 8 idle steps on
+                const u32 h2 = (u32)(mix64(seed ^ ((u64)row * 0xA24BAED4963EE407ull) ^ s->step) >> 32);
+                if (idle >= 8 + (h2 & 7u)) fire = true;
+            }
         }
         if (fire) { put(&out[ne++], row, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0); idle = 0; }
         s->idle[row] = (unsigned char)idle;
