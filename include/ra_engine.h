@@ -340,6 +340,10 @@ int  ra_engine_peer_get(ra_engine* e, ra_peer_ptrs* out);
 int  ra_engine_peer_set(ra_engine* e, uint32_t shard, const ra_peer_ptrs* p);
 int  ra_engine_ipc_export(ra_engine* e, ra_ipc_handles* out);
 int  ra_engine_ipc_import(ra_engine* e, uint32_t shard, const ra_ipc_handles* h);
+/* Peer transport, one shard per process: the step barrier as a kernel on the engine's stream (flag
+ * words in every peer's HBM, release / acquire at system scope) instead of a collective.  All shards
+ * must have the same number of rows; never use it with several shards on ONE stream. */
+int  ra_engine_peer_barrier(ra_engine* e);
 
 /*
  * The same flood driven from the HOST through ra_engine_step (host buffers, H2D of the

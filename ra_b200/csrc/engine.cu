@@ -29,6 +29,7 @@
                                             // <= 96 registers (no spills), 5 x 39 KB of shared memory
 #endif
 #define TILE_BYTES (RT * 64)
+#define RA_BAR_WORDS 64                       // barrier flag words behind mbox_cnt[b] (one per source shard)
 #define WARPS (CTA_T / 32)
 
 // ---- TMA (cp.async.bulk) + mbarrier, sm_90+/sm_100a --------------------------------------
@@ -394,6 +395,28 @@ __global__ void gather_kernel(const Cols C, const u64* offs, ra_event* msgs, u64
         }
 }
 
+// Step barrier of the peer transport without a collective: every shard release-stores the step's
+// epoch into its flag word in every peer's HBM (the words behind mbox_cnt[0], reachable through the
+// IPC mappings of the mailboxes) and acquire-spins until all peers' epochs have arrived in its own.
+// One warp, one lane per peer.  Stream order makes the step kernels' peer stores happen-before the
+// release; the acquire on the other side orders them before that shard's next step.
+__global__ void peer_barrier_kernel(const Cols C, const u64 epoch, u32* err)
+{
+    const u32 k = threadIdx.x;
+    if (k >= C.n_shards) return;
+    u64* mine = C.mbox_cnt[0] + C.rows;                      // [source shard]
+    u64* theirs = C.peer_cnt[0][k] + C.rows;                 // all shards have the same number of rows
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(theirs + C.shard), "l"(epoch) : "memory");
+    u64 v = 0;
+    for (u32 spins = 0; spins < (1u << 24); spins++) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + k) : "memory");
+        if (v >= epoch) return;
+        __nanosleep(64);
+    }
+    atomicExch(err + 1, 1u);                                 // a peer never arrived: reported by the next call
+}
+
 // ------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------
@@ -404,6 +427,7 @@ struct ra_engine {
     cudaEvent_t ev0, ev1;
     int cur;
     u64 step_no, steps;
+    u64 bar_epoch;                            // peer transport: barriers passed since the last reset
     void* allocs[64]; int n_allocs;
     // staging
     ra_event* d_ev; size_t d_ev_cap;
@@ -475,7 +499,9 @@ extern "C" int ra_engine_reset_empty(ra_engine* e)
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(e->C.counters, 0, (8 + 8 * 16) * sizeof(u64), e->stream));
     CK(cudaMemsetAsync(e->d_stall_cnt, 0, 4 * sizeof(u32), e->stream));
-    e->cur = 0; e->step_no = 0; e->steps = 0;
+    e->cur = 0; e->step_no = 0; e->steps = 0; e->bar_epoch = 0;
+    if (e->C.routed) CK(cudaMemsetAsync(e->C.mbox_cnt[0] + e->C.rows, 0, RA_BAR_WORDS * sizeof(u64), e->stream));
+    CK(cudaMemsetAsync(e->d_err, 0, 4 * sizeof(u32), e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return RA_OK;
 }
@@ -517,7 +543,9 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         DA(C.loc, (size_t)RA_LOCAL_CAP * PW); DA(C.loc_n, R);
         DA(C.onote, (size_t)RA_NOTE_CAP * R); DA(C.out_n, R); DA(C.counters, 8 + 8 * 16);
         if (C.routed) {
-            for (int b = 0; b < 2; b++) { DA(C.mbox[b], M * RA_MBOX_DEPTH * PW); DA(C.mbox_cnt[b], R); }
+            // + RA_BAR_WORDS: the peer transport's step barrier flags live behind the counts of buffer 0,
+            // so they are covered by the IPC mapping the peers already have
+            for (int b = 0; b < 2; b++) { DA(C.mbox[b], M * RA_MBOX_DEPTH * PW); DA(C.mbox_cnt[b], R + RA_BAR_WORDS); }
             DA(C.omsg, (size_t)RA_MSG_CAP * (C.pure ? R : 1));
         } else {
             C.mbox[0] = C.mbox[1] = nullptr; C.mbox_cnt[0] = C.mbox_cnt[1] = nullptr;
@@ -752,6 +780,16 @@ extern "C" int ra_engine_peer_set(ra_engine* e, uint32_t shard, const ra_peer_pt
     return RA_OK;
 }
 
+extern "C" int ra_engine_peer_barrier(ra_engine* e)
+{
+    if (!e || !e->C.peer_mode) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    e->bar_epoch++;
+    peer_barrier_kernel<<<1, 32, 0, e->stream>>>(e->C, e->bar_epoch, e->d_err);
+    CK(cudaGetLastError());
+    return RA_OK;
+}
+
 extern "C" int ra_engine_ipc_export(ra_engine* e, ra_ipc_handles* out)
 {
     if (!e || !out || !e->C.routed) return RA_E_INVAL;
@@ -790,6 +828,12 @@ extern "C" int ra_engine_sync(ra_engine* e)
     if (!e) return RA_E_INVAL;
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaStreamSynchronize(e->stream));
+    if (e->bar_epoch) {                                       // did a peer barrier give up waiting?
+        u32 h = 0;
+        CK(cudaMemcpyAsync(&h, e->d_err + 1, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (h) { snprintf(e->err, sizeof e->err, "peer barrier timed out (epoch %llu)", (unsigned long long)e->bar_epoch); return RA_E_CUDA; }
+    }
     return RA_OK;
 }
 
