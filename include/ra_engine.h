@@ -241,6 +241,14 @@ typedef struct ra_counters {
     uint64_t elections_won;
     uint64_t fatal_rows;
     uint64_t steps;
+    /* the reference's own counters of this path (src/ra.hrl:324-343), summed over all members */
+    uint64_t aer_received_follower;        /* ?C_RA_SRV_AER_RECEIVED_FOLLOWER        ra_server.erl:1278,1418 */
+    uint64_t aer_received_follower_empty;  /* ?C_RA_SRV_AER_RECEIVED_FOLLOWER_EMPTY  :1290 */
+    uint64_t aer_replies_success;          /* ?C_RA_SRV_AER_REPLIES_SUCCESS          :528  */
+    uint64_t aer_replies_failed;           /* ?C_RA_SRV_AER_REPLIES_FAILED           :590  */
+    uint64_t elections;                    /* ?C_RA_SRV_ELECTIONS                    :2856 */
+    uint64_t pre_vote_elections;           /* ?C_RA_SRV_PRE_VOTE_ELECTIONS           :2878 */
+    uint64_t term_and_voted_for_updates;   /* ?C_RA_SRV_TERM_AND_VOTED_FOR_UPDATES   :3026 */
 } ra_counters;
 
 enum ra_status {

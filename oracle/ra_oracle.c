@@ -368,6 +368,7 @@ static void update_term_and_voted_for(ctx_t *c, u64 term, u8 voted_for)
     m->current_term = term;
     m->voted_for = voted_for;
     c->status |= RA_ST_TERM_VOTE_CHANGED;      /* ra_log_meta:store_sync :3024-3025 */
+    c->cnt->term_and_voted_for_updates++;      /* :3026 */
 }
 
 /* update_term/2 :3033-3037 */
@@ -609,11 +610,13 @@ static u8 call_for_election(ctx_t *c, u8 target, nextq_t *nq)
     msg_t req; memset(&req, 0, sizeof req);
     if (target == RA_CANDIDATE) {
         u64 new_term = m->current_term + 1;
+        c->cnt->elections++;                                     /* :2856 */
         req.type = RA_EV_REQUEST_VOTE; req.term = new_term; req.a = last_idx; req.b = last_term;
         self.type = RA_EV_REQUEST_VOTE_RES; self.term = new_term; self.d = 1;
         update_term_and_voted_for(c, new_term, m->self_slot);
     } else {
         u64 token = ++m->token_counter;                          /* make_ref() */
+        c->cnt->pre_vote_elections++;                            /* :2878 */
         req.type = RA_EV_PRE_VOTE; req.term = m->current_term; req.a = last_idx; req.b = last_term;
         req.c = token; req.d = (u64)1 /* ?RA_PROTO_VERSION */ | ((u64)m->machine_version << 32);
         self.type = RA_EV_PRE_VOTE_RES; self.term = m->current_term; self.c = token; self.d = 1;
@@ -695,6 +698,7 @@ static u8 handle_follower(ctx_t *c, const msg_t *e, nextq_t *nq)
     case RA_EV_AER: {
         u64 term = e->term, cur = m->current_term;
         u32 leader = e->from_slot;
+        c->cnt->aer_received_follower++;                                     /* :1278 and :1418 */
         if (term >= cur) {                                                   /* :1266-1414 */
             u64 pl_idx = e->a, pl_term = e->b, leader_commit = e->c;
             c->status |= RA_ST_LEADER_MSG;                                   /* {record_leader_msg,_} */
@@ -710,6 +714,7 @@ static u8 handle_follower(ctx_t *c, const msg_t *e, nextq_t *nq)
                     last_valid = idx; k++;
                 }
                 if (k == n0) {                                               /* Entries == [] :1288 */
+                    c->cnt->aer_received_follower_empty++;                   /* :1290 */
                     u64 local_last = m->log.last_index;
                     int validated;
                     if (n0 == 0 && local_last > pl_idx) {                    /* :1294-1303 */
@@ -867,6 +872,7 @@ static u8 handle_leader(ctx_t *c, const msg_t *e, nextq_t *nq, int pure)
         u32 from = e->from_slot;
         int success = e->d != 0;
         if (success && term == m->current_term) {                            /* :522-561 */
+            c->cnt->aer_replies_success++;                                   /* :528 */
             if (!is_peer(m, from)) return RA_LEADER;
             peer_t *p = &m->peers[from];
             if (e->b > p->match_index) p->match_index = e->b;                /* max(MI, LastIdx) */
@@ -881,6 +887,7 @@ static u8 handle_leader(ctx_t *c, const msg_t *e, nextq_t *nq, int pure)
         }
         if (!success) {                                                      /* :577-643 */
             if (!is_peer(m, from)) return RA_LEADER;
+            c->cnt->aer_replies_failed++;                                    /* :590 */
             peer_t *p = &m->peers[from];
             u64 peer_next = e->a, peer_last = e->b, peer_last_term = e->c;
             u64 mi = p->match_index, ni = p->next_index;
@@ -1644,6 +1651,13 @@ int ra_oracle_flood(ra_oracle *o, uint32_t n_steps, uint32_t cmds_per_step,
         o->cnt.msgs_dropped += args[i].cnt.msgs_dropped;
         o->cnt.elections_won += args[i].cnt.elections_won;
         o->cnt.fatal_rows += args[i].cnt.fatal_rows;
+        o->cnt.aer_received_follower += args[i].cnt.aer_received_follower;
+        o->cnt.aer_received_follower_empty += args[i].cnt.aer_received_follower_empty;
+        o->cnt.aer_replies_success += args[i].cnt.aer_replies_success;
+        o->cnt.aer_replies_failed += args[i].cnt.aer_replies_failed;
+        o->cnt.elections += args[i].cnt.elections;
+        o->cnt.pre_vote_elections += args[i].cnt.pre_vote_elections;
+        o->cnt.term_and_voted_for_updates += args[i].cnt.term_and_voted_for_updates;
     }
     o->cur ^= (int)(n_steps & 1);
     o->step_no += n_steps;

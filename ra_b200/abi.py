@@ -140,7 +140,11 @@ class RaEngineCfg(C.Structure):
 class RaCounters(C.Structure):
     _fields_ = [("events", C.c_uint64), ("commits", C.c_uint64), ("applied", C.c_uint64),
                 ("msgs_out", C.c_uint64), ("msgs_dropped", C.c_uint64),
-                ("elections_won", C.c_uint64), ("fatal_rows", C.c_uint64), ("steps", C.c_uint64)]
+                ("elections_won", C.c_uint64), ("fatal_rows", C.c_uint64), ("steps", C.c_uint64),
+                ("aer_received_follower", C.c_uint64), ("aer_received_follower_empty", C.c_uint64),
+                ("aer_replies_success", C.c_uint64), ("aer_replies_failed", C.c_uint64),
+                ("elections", C.c_uint64), ("pre_vote_elections", C.c_uint64),
+                ("term_and_voted_for_updates", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -31,6 +31,10 @@
 #define TILE_BYTES (RT * 64)
 #define RA_BAR_WORDS 64                       // barrier flag words behind mbox_cnt[b] (one per source shard)
 #define WARPS (CTA_T / 32)
+// Cols::counters: [0..7] ra_counters' aggregate fields, [8..135] stall histogram (role x type),
+// [136..142] the reference's per-path counters in the order of Member::c_ref (CR_*)
+#define RA_N_COUNTERS (8 + 8 * 16 + 8)
+#define RA_CNT_REF 136
 
 // ---- TMA (cp.async.bulk) + mbarrier, sm_90+/sm_100a --------------------------------------
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -115,6 +119,26 @@ __device__ __forceinline__ u32 mask_or_warp(u32 m) { return __reduce_or_sync(0xf
 __device__ __forceinline__ u64 mask_or_warp(u64 m)
 { return (u64)__reduce_or_sync(0xffffffffu, (u32)m) | ((u64)__reduce_or_sync(0xffffffffu, (u32)(m >> 32)) << 32); }
 
+// the reference's counters: 7 byte-wide fields per row -> two 16-bit-field words per reduction
+// (32 lanes x 255 < 65536), one atomic per warp and counter that moved
+__device__ __forceinline__ void flush_ref_counters(const Cols& C, u32 lane, u64 c_ref)
+{
+    if (!__any_sync(0xffffffffu, c_ref != 0)) return;
+    u32 w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const u32 lo = (u32)(c_ref >> (16 * k)) & 0xffu, hi = (u32)(c_ref >> (16 * k + 8)) & 0xffu;
+        w[k] = __reduce_add_sync(0xffffffffu, lo | (hi << 16));
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (w[k] & 0xffffu) atomicAdd(&C.counters[RA_CNT_REF + 2 * k], (u64)(w[k] & 0xffffu));
+            if (2 * k + 1 < 7 && (w[k] >> 16)) atomicAdd(&C.counters[RA_CNT_REF + 2 * k + 1], (u64)(w[k] >> 16));
+        }
+    }
+}
+
 template <int MM>
 __global__ void __launch_bounds__(CTA_T, MINB)
 raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F,
@@ -127,6 +151,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     const u32 r = wtile * RT + lane;
     const bool valid = r < C.rows;
     u32 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
+    u64 k_ref = 0;
     if (blockIdx.x == 0 && tid == 0) *stall_count_next = 0;    // the list of the step after this one
 
     // ---- what does this row have to do? ---------------------------------------------------
@@ -235,6 +260,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         member_writeback(m, C, r);
         k_events = m.c_pack & 0xffu; k_commits = m.c_commits; k_applied = m.c_applied;
         k_msgs = (m.c_pack >> 8) & 0xffu; k_dropped = m.c_pack >> 20; k_elect = (m.c_pack >> 16) & 15u;
+        k_ref = m.c_ref;
     }
     // stalled rows: hand the rest of the step to raft_general_kernel
     const u32 sm = __ballot_sync(0xffffffffu, stalled);
@@ -252,6 +278,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         }
     }
     flush_counters(C, lane, k_events, k_commits, k_applied, k_msgs, k_dropped, k_elect, k_fatal);
+    flush_ref_counters(C, lane, k_ref);
 }
 
 // general path for the stalled rows of this step (one thread per list entry)
@@ -266,6 +293,7 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
     for (u32 base = blockIdx.x * CTA_T; base < n; base += gridDim.x * CTA_T) {
         const u32 i = base + tid;
         u32 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
+        u64 k_ref = 0;
         if (i < n) {
             const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&stall_list[i]);
             const ulonglong2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
@@ -302,8 +330,10 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
             member_writeback(m, C, r);
             k_events = m.c_pack & 0xffu; k_commits = m.c_commits; k_applied = m.c_applied;
             k_msgs = (m.c_pack >> 8) & 0xffu; k_dropped = m.c_pack >> 20; k_elect = (m.c_pack >> 16) & 15u;
+            k_ref = m.c_ref;
         }
         flush_counters(C, lane, k_events, k_commits, k_applied, k_msgs, k_dropped, k_elect, k_fatal);
+        flush_ref_counters(C, lane, k_ref);
     }
 }
 
@@ -497,7 +527,7 @@ extern "C" int ra_engine_reset_empty(ra_engine* e)
     CK(cudaSetDevice(e->cfg.device));
     reset_empty_kernel<<<nblocks(e->C.rows, 256), 256, 0, e->stream>>>(e->C);
     CK(cudaGetLastError());
-    CK(cudaMemsetAsync(e->C.counters, 0, (8 + 8 * 16) * sizeof(u64), e->stream));
+    CK(cudaMemsetAsync(e->C.counters, 0, RA_N_COUNTERS * sizeof(u64), e->stream));
     CK(cudaMemsetAsync(e->d_stall_cnt, 0, 4 * sizeof(u32), e->stream));
     e->cur = 0; e->step_no = 0; e->steps = 0; e->bar_epoch = 0;
     if (e->C.routed) CK(cudaMemsetAsync(e->C.mbox_cnt[0] + e->C.rows, 0, RA_BAR_WORDS * sizeof(u64), e->stream));
@@ -541,7 +571,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         C.tiles = (u32)((R + RT - 1) / RT);
         const size_t PW = (size_t)C.tiles * 4 * RT;             // 16-byte words per tiled plane
         DA(C.loc, (size_t)RA_LOCAL_CAP * PW); DA(C.loc_n, R);
-        DA(C.onote, (size_t)RA_NOTE_CAP * R); DA(C.out_n, R); DA(C.counters, 8 + 8 * 16);
+        DA(C.onote, (size_t)RA_NOTE_CAP * R); DA(C.out_n, R); DA(C.counters, RA_N_COUNTERS);
         if (C.routed) {
             // + RA_BAR_WORDS: the peer transport's step barrier flags live behind the counts of buffer 0,
             // so they are covered by the IPC mapping the peers already have
@@ -853,9 +883,13 @@ extern "C" int ra_engine_counters(ra_engine* e, ra_counters* out)
 {
     if (!e || !out) return RA_E_INVAL;
     CK(cudaSetDevice(e->cfg.device));
-    u64 h[8];
+    u64 h[RA_N_COUNTERS];
     CK(cudaMemcpyAsync(h, e->C.counters, sizeof h, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    out->aer_received_follower = h[RA_CNT_REF + 0]; out->aer_received_follower_empty = h[RA_CNT_REF + 1];
+    out->aer_replies_success = h[RA_CNT_REF + 2]; out->aer_replies_failed = h[RA_CNT_REF + 3];
+    out->elections = h[RA_CNT_REF + 4]; out->pre_vote_elections = h[RA_CNT_REF + 5];
+    out->term_and_voted_for_updates = h[RA_CNT_REF + 6];
     out->events = h[0]; out->commits = h[1]; out->applied = h[2]; out->msgs_out = h[3];
     out->msgs_dropped = h[4]; out->elections_won = h[5]; out->fatal_rows = h[6]; out->steps = e->steps;
     return RA_OK;

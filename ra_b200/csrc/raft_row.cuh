@@ -29,7 +29,7 @@ __device__ __forceinline__ void member_init(Member& m, const Cols& C, u32 r, ulo
     m.lrs = lrs; m.lrs_ok = MT_NRUNS(ap.y) ? 1u : 0u;
     m.n_msgs = 0; m.n_notes = 0; m.status = MT_ROLE(ap.y) << 16; m.wk = 0;
     m.sent_to = 0; m.pn_type = RA_NOTE_NONE; m.pn_slot = 0; m.pn_a = m.pn_b = m.pn_c = 0;
-    m.c_pack = 0; m.c_commits = m.c_applied = 0;
+    m.c_pack = 0; m.c_ref = 0; m.c_commits = m.c_applied = 0;
     m.nb = cur ^ 1;
     m.sp = sp; m.pstate = 0; m.pipe_clean = 0;
 }

@@ -262,6 +262,7 @@ struct Member {
     // flood host model: the last two finalised WAL_APPEND notes
     // counters
     u32 c_pack;                 // events | msgs << 8 | elections << 16 | dropped << 20
+    u64 c_ref;                  // the reference's counters of this path, 8 bits each (CR_*)
     u32 c_commits, c_applied;   // per row and step: far below 2^32
     int nb;                     // mailbox buffer written this step
     // per-peer columns staged in shared memory on first use: sp[(f*8 + s) * CTA_T], f = 0 next,
@@ -623,10 +624,16 @@ __device__ __forceinline__ void nq_push(NextQ& q, u32 code) { q.codes |= code <<
 
 // ---- term / vote --------------------------------------------------------------------
 
+// shifts of the reference's per-path counters inside Member::c_ref (ra.hrl:324-343)
+enum { CR_AER_RX = 0, CR_AER_RX_EMPTY = 8, CR_REPLY_OK = 16, CR_REPLY_FAIL = 24, CR_ELECTIONS = 32, CR_PRE_VOTE_ELECTIONS = 40,
+       CR_TERM_VOTE = 48 };
+#define CR_INC(m, f) ((m).c_ref += 1ull << (f))
+
 // update_term_and_voted_for/3 :3014-3031
 __device__ __forceinline__ void update_term_and_voted_for(Member& m, u64 term, u32 voted)
 {
     if (term == m.term && voted == MT_VOTED(m.meta)) return;
+    CR_INC(m, CR_TERM_VOTE);                                            // :3026
     m.term = term;
     MT_SET(m.meta, 7, 4, voted);
     m.status |= RA_ST_TERM_VOTE_CHANGED;
@@ -850,10 +857,12 @@ __device__ __forceinline__ u32 call_for_election(Member& m, u32 target, NextQ& n
     Rec req;
     if (target == RA_CANDIDATE) {
         u64 nt = m.term + 1;
+        CR_INC(m, CR_ELECTIONS);                                        // :2856
         req = mk_rec(0, RA_EV_REQUEST_VOTE, 0, 0, 0, 0, 0, nt, m.last_idx, m.last_term, 0, 0, 0);
         update_term_and_voted_for(m, nt, m.slot);
     } else {
         u64 token = tok_ctr(m) + 1;                                 // make_ref()
+        CR_INC(m, CR_PRE_VOTE_ELECTIONS);                               // :2878
         u64 mv = macver(m) & 0xffffffffull;
         req = mk_rec(0, RA_EV_PRE_VOTE, 0, 0, 0, 0, 0, m.term, m.last_idx, m.last_term, token, 1ull | (mv << 32), 0);
         update_term_and_voted_for(m, m.term, m.slot);
@@ -921,6 +930,7 @@ __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& n
     if (type == RA_EV_AER) {
         u64 term = R_term(e), cur = m.term;
         u32 leader = R_from(e);
+        CR_INC(m, CR_AER_RX);                                              // :1278 and :1418
         if (term >= cur) {
             u64 pl_idx = R_a(e), pl_term = R_b(e), leader_commit = R_c(e);
             u32 n0 = R_n(e), n1 = R_n1(e);
@@ -945,6 +955,7 @@ __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& n
                 u64 k = idx - (pl_idx + 1);
                 u64 last_valid = idx - 1;
                 if (k == n0) {                                             // Entries == [] :1288
+                    CR_INC(m, CR_AER_RX_EMPTY);                            // :1290
                     u64 local_last = m.last_idx;
                     bool validated;
                     if (n0 == 0 && local_last > pl_idx) {                  // :1294-1303
@@ -1076,6 +1087,7 @@ __device__ __forceinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
         bool success = R_d(e) != 0;
         bool known = from < NMEM(C);
         if (success && term == m.term) {                                   // :522-561
+            CR_INC(m, CR_REPLY_OK);                                        // :528
             if (!known) return RA_LEADER;
             ulonglong2 nm = peer_nm<MM>(m, from);
             u64 nn = R_a(e) > nm.x ? R_a(e) : nm.x;
@@ -1091,6 +1103,7 @@ __device__ __forceinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
         }
         if (!success) {                                                    // :577-643
             if (!known) return RA_LEADER;
+            CR_INC(m, CR_REPLY_FAIL);                                      // :590
             ulonglong2 nm = peer_nm<MM>(m, from);
             u64 pnext = R_a(e), plast = R_b(e), plast_term = R_c(e);
             u64 t = log_fetch_term(m, (i64)plast);
@@ -1407,6 +1420,7 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
             const u32 n = R_n(e);
             if (n != 0 && (R_d(e) != m.last_term || m.last_idx + 1 < m.applied)) return false;
             m.c_pack += 1u;
+            m.c_ref += (1ull << CR_AER_RX) + (n == 0 ? 1ull << CR_AER_RX_EMPTY : 0ull);   // :1278, :1290
             leader = R_from(e);
             m.status |= RA_ST_LEADER_MSG;
             MT_SET(m.meta, 3, 4, leader);
@@ -1479,6 +1493,7 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
             const u32 from = R_from(e);
             if (!(R_d(e) != 0 && R_term(e) == m.term && from < NMEM(*m.C))) return false;
             m.c_pack += 1u;
+            CR_INC(m, CR_REPLY_OK);                                    // :528
             ulonglong2 nm = peer_nm<MM>(m, from);
             if (R_b(e) > nm.y) m.cold &= ~8u;                          // a match index moves
             peer_nm_set<MM>(m, from, R_a(e) > nm.x ? R_a(e) : nm.x, R_b(e) > nm.y ? R_b(e) : nm.y);

@@ -52,7 +52,7 @@ extern "C" int ra_emu_reset_empty(ra_emu* e)
 {
     if (!e) return RA_E_INVAL;
     for (u32 r = 0; r < e->C.rows; r++) reset_row(e->C, r);
-    memset(e->C.counters, 0, (8 + 8 * 16) * sizeof(u64));
+    memset(e->C.counters, 0, (8 + 8 * 16 + 8) * sizeof(u64));
     e->cur = 0; e->step_no = 0; e->steps = 0;
     return RA_OK;
 }
@@ -85,7 +85,7 @@ extern "C" int ra_emu_create(const ra_engine_cfg* cfg, ra_emu** out)
     {
         const size_t PW = (size_t)C.tiles * 4 * RT;
         HA(C.loc, (size_t)RA_LOCAL_CAP * PW); HA(C.loc_n, R);
-        HA(C.onote, (size_t)RA_NOTE_CAP * R); HA(C.out_n, R); HA(C.counters, 8 + 8 * 16);
+        HA(C.onote, (size_t)RA_NOTE_CAP * R); HA(C.out_n, R); HA(C.counters, 8 + 8 * 16 + 8);
         if (C.routed) {
             for (int b = 0; b < 2; b++) { HA(C.mbox[b], M * RA_MBOX_DEPTH * PW); HA(C.mbox_cnt[b], R); }
             HA(C.omsg, (size_t)RA_MSG_CAP * (C.pure ? R : 1));
@@ -136,6 +136,7 @@ static void add_counters(const Cols& C, const Member& m, u32 k_fatal)
     C.counters[0] += m.c_pack & 0xffu; C.counters[1] += m.c_commits; C.counters[2] += m.c_applied;
     C.counters[3] += (m.c_pack >> 8) & 0xffu; C.counters[4] += m.c_pack >> 20; C.counters[5] += (m.c_pack >> 16) & 15u;
     C.counters[6] += k_fatal;
+    for (int f = 0; f < 7; f++) C.counters[136 + f] += (m.c_ref >> (8 * f)) & 0xffu;   // the reference's counters
 }
 
 // the general kernel's body for one stall context (engine.cu: raft_general_kernel)
@@ -354,6 +355,9 @@ extern "C" int ra_emu_counters(ra_emu* e, ra_counters* out)
     const u64* h = e->C.counters;
     out->events = h[0]; out->commits = h[1]; out->applied = h[2]; out->msgs_out = h[3];
     out->msgs_dropped = h[4]; out->elections_won = h[5]; out->fatal_rows = h[6]; out->steps = e->steps;
+    out->aer_received_follower = h[136]; out->aer_received_follower_empty = h[137]; out->aer_replies_success = h[138];
+    out->aer_replies_failed = h[139]; out->elections = h[140]; out->pre_vote_elections = h[141];
+    out->term_and_voted_for_updates = h[142];
     return RA_OK;
 }
 
