@@ -354,6 +354,28 @@ int  ra_engine_ipc_import(ra_engine* e, uint32_t shard, const ra_ipc_handles* h)
 int  ra_engine_peer_barrier(ra_engine* e);
 
 /*
+ * Written-event source: ra_log_wal:complete_batch/1 (src/ra_log_wal.erl:784-808) tells every
+ * writer of a WAL batch {ra_log_event, {written, Term, Seq}} with Seq a ra_seq (src/ra_seq.erl: ascending
+ * indexes and {From, To} ranges).  ra_wal_batch_to_events turns one batch -- an array of writers -- into the
+ * grouped event array of ra_engine_step: one RA_EV_WRITTEN per range, ranges of a writer ascending and
+ * adjacent (ra_log:handle_event/2 :849-896 ends at the highest index of the seq whose term matches, which
+ * is what the ranges applied in ascending order leave), writers in the order given.  A writer takes at
+ * most `max_per_row` (<= RA_LOCAL_CAP, minus what the caller reserves for other events of that row)
+ * records of one step: the rest is reported through `resume` and goes into the next step.
+ */
+typedef struct ra_wal_writer {
+    uint32_t row;                 /* the member (UId) the WAL wrote for                      */
+    uint32_t n_ranges;
+    uint64_t term;                /* #batch_writer.term                                      */
+    const uint64_t* ranges;       /* n_ranges x {from, to}, ascending, non-overlapping       */
+} ra_wal_writer;
+typedef struct ra_wal_resume { uint32_t writer, range; } ra_wal_resume;   /* first range not emitted */
+/* returns the number of events written to `out` (<= cap); *resume = {n_writers, 0} when the batch is done.
+ * Start with *resume = {0, 0}; call again (next step) while resume->writer < n_writers. */
+size_t ra_wal_batch_to_events(const ra_wal_writer* writers, size_t n_writers, uint32_t max_per_row,
+                              ra_event* out, size_t cap, ra_wal_resume* resume);
+
+/*
  * The same flood driven from the HOST through ra_engine_step (host buffers, H2D of the
  * step's events and D2H of its notes inside every step): what an Erlang batching process
  * in front of many ra_server_procs would do.  The host model (WAL completion, clients,

@@ -218,3 +218,30 @@ extern "C" int ra_hostsim_breakdown(ra_hostsim* s, double* step_seconds, double*
     if (step_seconds) *step_seconds = s->t_step; if (model_seconds) *model_seconds = s->t_model;
     return RA_OK;
 }
+
+
+// ---- written-event source: one WAL batch -> one grouped event array (include/ra_engine.h) -----------
+// Within one call a row gets at most max_per_row records and every row's records are adjacent; a writer
+// whose ranges do not fit stops the call there (its remaining ranges must not be reordered behind other
+// rows of a later call, and a second run of the same row in one batch would break the grouping contract).
+extern "C" size_t ra_wal_batch_to_events(const ra_wal_writer* w, size_t n, uint32_t max_per_row,
+                                         ra_event* out, size_t cap, ra_wal_resume* resume)
+{
+    if (!w || !out || !resume || max_per_row == 0 || max_per_row > RA_LOCAL_CAP) return 0;
+    size_t ne = 0;
+    u32 wi = resume->writer, ri = resume->range;
+    u32 run_row = 0xFFFFFFFFu, taken = 0;           // records of the current run of one row (a writer that
+    while (wi < n) {                                // changed term mid-batch is notified twice, back to back)
+        const ra_wal_writer& x = w[wi];
+        if (x.row != run_row) { run_row = x.row; taken = 0; }
+        while (ri < x.n_ranges && taken < max_per_row && ne < cap) {
+            put(&out[ne++], x.row, RA_EV_WRITTEN, 0, x.term, x.ranges[2 * ri], x.ranges[2 * ri + 1]);
+            ri++; taken++;
+        }
+        if (ri < x.n_ranges) break;                 // out of room for this row (or for the batch): resume here
+        wi++; ri = 0;
+        if (ne >= cap) break;
+    }
+    resume->writer = wi; resume->range = ri;
+    return ne;
+}
