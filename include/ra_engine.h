@@ -75,7 +75,13 @@ enum ra_event_type {
     RA_EV_ELECTION_TIMEOUT  = 9,  /* election_timeout                              */
     RA_EV_AWAIT_COND_TIMEOUT= 10, /* await_condition_timeout                       */
     RA_EV_PIPELINE_RPCS     = 11, /* pipeline_rpcs            ra_server.erl:784-792 */
-    RA_EV_TICK              = 12  /* leader tick -> make_rpcs ra_server_proc.erl:610 */
+    RA_EV_TICK              = 12, /* leader tick -> make_rpcs ra_server_proc.erl:610 */
+    /* consistent queries: the heartbeat round of ra_server.erl:846-918, :3700-3825 */
+    RA_EV_HEARTBEAT_RPC     = 13, /* #heartbeat_rpc{}   from_slot=leader term a=query_index          */
+    RA_EV_HEARTBEAT_REPLY   = 14, /* {Peer,#heartbeat_reply{}}  from_slot=peer term a=query_index    */
+    RA_EV_CONSISTENT_QUERY  = 15  /* {consistent_query|consistent_aux,_,_} handed to the leader; the
+                                     host holds the query refs and submits one only while cluster
+                                     changes are permitted (it keeps `pending_consistent_queries`)  */
 };
 
 /* ra_event.flags */
@@ -99,6 +105,9 @@ enum ra_event_type {
  *  PRE_VOTE_RES    voter       term      -               -              token          granted(0/1)
  *  WRITTEN         -           term      from            to                                        (Seq = [{from,to}])
  *  COMMAND         -           -         -               -              -              -            n = number of commands
+ *  HEARTBEAT_RPC   leader      term      query_index
+ *  HEARTBEAT_REPLY replier     term      query_index
+ *  CONSISTENT_QUERY -
  */
 typedef struct ra_event {
     uint32_t row;        /* destination member row                                  */
@@ -125,7 +134,12 @@ enum ra_note_type {
     RA_NOTE_STATUS     = 5, /* end-of-step summary: aux=flags, a=term, b=voted_for|leader<<8|
                                role_old<<16|role_new<<24, c=detail                         */
     RA_NOTE_SEND_SNAPSHOT = 6, /* a=peer slot b=snapshot index  ({send_snapshot,..} :2395) */
-    RA_NOTE_NOT_LEADER = 7  /* COMMAND reached a non-leader: a=n commands b=leader slot   */
+    RA_NOTE_NOT_LEADER = 7, /* COMMAND / CONSISTENT_QUERY reached a non-leader: a=n commands b=leader slot */
+    RA_NOTE_QUERY_INDEX = 8,  /* the query just submitted waits for heartbeats: a=its query_index
+                                 b=commit_index it must read at (queries_waiting_heartbeats, :3722-3739) */
+    RA_NOTE_QUERY_AGREED = 9, /* a=query_index a quorum has confirmed: every waiting query <= a is
+                                 applied by the host (heartbeat_rpc_quorum/3, :3766-3784)              */
+    RA_NOTE_QUERY_APPLY = 10  /* no peers: apply the query just submitted right away (:3729-3731)      */
 };
 
 /* RA_NOTE_STATUS aux flags */
@@ -146,7 +160,8 @@ enum ra_fatal {
     RA_FATAL_WRITE_INTEGRITY = 2,          /* ra_log:write/2 {error,{integrity_error,_}}  :1369    */
     RA_FATAL_SET_LAST_INDEX_NOT_FOUND = 3, /* {ok,L} = ra_log:set_last_index(..) badmatch :1301    */
     RA_FATAL_ASSERT = 4,                   /* a ?assert / ?assertNot in the reference failed       */
-    RA_FATAL_NO_SNAPSHOT = 5               /* make_rpc_effect: prev entry and snapshot both absent :2378 */
+    RA_FATAL_NO_SNAPSHOT = 5,              /* make_rpc_effect: prev entry and snapshot both absent :2378 */
+    RA_FATAL_LEADER_SAW_HEARTBEAT_SAME_TERM = 6 /* exit(leader_saw_heartbeat_rpc_in_same_term) :894 */
 };
 
 typedef struct ra_note {
@@ -287,6 +302,18 @@ static inline int ra_row_state_valid(const ra_row_state* s)
 int  ra_engine_reset_empty(ra_engine* e);
 /* For the parity diff. `rows[i].row` selects the row; the rest is filled in. */
 int  ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n);
+
+/* Consistent-query state of a member (kept apart from ra_row_state): its own query_index
+ * (ra_server_state(), :96), every peer's (ra_peer_state(), ra.hrl:63-75) and the highest index the
+ * host has been told a quorum agreed on.  load/read like the rows; zero after reset / load_rows. */
+typedef struct ra_query_state {
+    uint32_t row, _pad;
+    uint64_t query_index;
+    uint64_t agreed_index;
+    uint64_t peer_query_index[RA_MAX_MEMBERS];
+} ra_query_state;
+int  ra_engine_load_query_state(ra_engine* e, const ra_query_state* q, size_t n);
+int  ra_engine_read_query_state(ra_engine* e, ra_query_state* q, size_t n);
 
 /*
  * Evaluate one batch.  ev[0..n_ev): events for one row must be adjacent and are applied

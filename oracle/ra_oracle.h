@@ -22,6 +22,8 @@ void ra_oracle_destroy(ra_oracle* o);
 int  ra_oracle_load_rows(ra_oracle* o, const ra_row_state* rows, size_t n);
 int  ra_oracle_reset_empty(ra_oracle* o);
 int  ra_oracle_read_rows(ra_oracle* o, ra_row_state* rows, size_t n);
+int  ra_oracle_load_query_state(ra_oracle* o, const ra_query_state* q, size_t n);
+int  ra_oracle_read_query_state(ra_oracle* o, ra_query_state* q, size_t n);
 int  ra_oracle_step(ra_oracle* o, const ra_event* ev, size_t n_ev,
                     ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
                     ra_note* notes, size_t notes_cap, size_t* n_notes);

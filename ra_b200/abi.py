@@ -34,7 +34,7 @@ PEER_NORMAL, PEER_SENDING_SNAPSHOT, PEER_SNAPSHOT_BACKOFF, PEER_SUSPENDED, PEER_
 # enum ra_event_type
 (EV_NONE, EV_AER, EV_AER_REPLY, EV_REQUEST_VOTE, EV_REQUEST_VOTE_RES, EV_PRE_VOTE,
  EV_PRE_VOTE_RES, EV_WRITTEN, EV_COMMAND, EV_ELECTION_TIMEOUT, EV_AWAIT_COND_TIMEOUT,
- EV_PIPELINE_RPCS, EV_TICK) = range(13)
+ EV_PIPELINE_RPCS, EV_TICK, EV_HEARTBEAT_RPC, EV_HEARTBEAT_REPLY, EV_CONSISTENT_QUERY) = range(16)
 
 EVF_NOOP = 0x01
 EVF_NEXT_EVENT = 0x02
@@ -42,7 +42,7 @@ EVF_INFO = 0x08
 
 # enum ra_note_type
 (NOTE_NONE, NOTE_WAL_APPEND, NOTE_TRUNCATE, NOTE_COMMIT, NOTE_APPLY, NOTE_STATUS,
- NOTE_SEND_SNAPSHOT, NOTE_NOT_LEADER) = range(8)
+ NOTE_SEND_SNAPSHOT, NOTE_NOT_LEADER, NOTE_QUERY_INDEX, NOTE_QUERY_AGREED, NOTE_QUERY_APPLY) = range(11)
 
 ST_TERM_VOTE_CHANGED = 0x0001
 ST_ROLE_CHANGED = 0x0002
@@ -60,6 +60,7 @@ FATAL_WRITE_INTEGRITY = 2
 FATAL_SET_LAST_INDEX_NOT_FOUND = 3
 FATAL_ASSERT = 4
 FATAL_NO_SNAPSHOT = 5
+FATAL_LEADER_SAW_HEARTBEAT_SAME_TERM = 6
 
 RA_OK, RA_E_INVAL, RA_E_NOMEM, RA_E_CUDA, RA_E_UNGROUPED, RA_E_CAPACITY, RA_E_NODEVICE = 0, -1, -2, -3, -4, -5, -6
 
@@ -128,6 +129,14 @@ class RaRowState(C.Structure):
                  self.cond_reply_last_term) if (self.flags & 2) else None,
                 tuple((p.next_index, p.match_index, p.commit_index_sent, p.status, p.voter)
                       for p in list(self.peers)[: self.n_members]))
+
+
+class RaQueryState(C.Structure):
+    _fields_ = [("row", C.c_uint32), ("_pad", C.c_uint32), ("query_index", C.c_uint64),
+                ("agreed_index", C.c_uint64), ("peer_query_index", C.c_uint64 * RA_MAX_MEMBERS)]
+
+    def key(self, n_members: int = RA_MAX_MEMBERS) -> Tuple:
+        return (self.row, self.query_index, self.agreed_index, tuple(self.peer_query_index[:n_members]))
 
 
 class RaEngineCfg(C.Structure):
@@ -280,6 +289,24 @@ class Backend:
         self._check(self._fn("read_rows")(self._h, arr, len(ids)), "read_rows")
         return list(arr)
 
+    def load_query_state(self, qs: Sequence[RaQueryState]) -> None:
+        f = self._fn("load_query_state")
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.POINTER(RaQueryState), C.c_size_t]
+        arr = (RaQueryState * max(len(qs), 1))(*qs)
+        self._check(f(self._h, arr, len(qs)), "load_query_state")
+
+    def read_query_state(self, row_ids: Iterable[int]) -> List[RaQueryState]:
+        f = self._fn("read_query_state")
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.POINTER(RaQueryState), C.c_size_t]
+        ids = list(row_ids)
+        arr = (RaQueryState * max(len(ids), 1))()
+        for i, r in enumerate(ids):
+            arr[i].row = r
+        self._check(f(self._h, arr, len(ids)), "read_query_state")
+        return list(arr)[: len(ids)]
+
     def step(self, events: Sequence[RaEvent], msgs_cap: int | None = None,
              notes_cap: int | None = None) -> Tuple[List[RaEvent], List[RaNote]]:
         n = len(events)
@@ -352,6 +379,18 @@ def ev_pre_vote_result(row, term, token, granted, voter=RA_NO_SLOT):
 def ev_written(row, term, first, last):
     """{ra_log_event, {written, Term, [{First, Last}]}}."""
     return RaEvent(row=row, type=EV_WRITTEN, from_slot=RA_NO_SLOT, term=term, a=first, b=last)
+
+
+def ev_heartbeat_rpc(row, leader, term, query_index):
+    return RaEvent(row=row, type=EV_HEARTBEAT_RPC, from_slot=leader, term=term, a=query_index)
+
+
+def ev_heartbeat_reply(row, peer, term, query_index):
+    return RaEvent(row=row, type=EV_HEARTBEAT_REPLY, from_slot=peer, term=term, a=query_index)
+
+
+def ev_consistent_query(row):
+    return RaEvent(row=row, type=EV_CONSISTENT_QUERY, from_slot=RA_NO_SLOT)
 
 
 def ev_command(row, n=1, noop=False):

@@ -361,6 +361,17 @@ __global__ void read_rows_kernel(const Cols C, ra_row_state* out, u32 n)
     read_row(C, out[i]);
 }
 
+__global__ void load_query_kernel(const Cols C, const ra_query_state* in, u32 n)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) load_query_row(C, in[i]);
+}
+__global__ void read_query_kernel(const Cols C, ra_query_state* out, u32 n)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) read_query_row(C, out[i]);
+}
+
 // flat host batch -> per-row local slots.  err[0]: 1 = ungrouped, 2 = too many for a row, 3 = bad row
 __global__ void ingest_kernel(const Cols C, const ra_event* ev, u32 n, u32* err)
 {
@@ -568,6 +579,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
 #define DA(p, n) if ((rc = dalloc(e, &(p), (n))) != RA_OK) goto bad
         DA(C.tc, R); DA(C.lg, R); DA(C.lw, R); DA(C.ap, R); DA(C.sn, R); DA(C.tk, R); DA(C.fm, R);
         DA(C.cd, 2 * R); DA(C.pnm, M * R); DA(C.pcs, M * R); DA(C.run, RA_MAX_RUNS * R); DA(C.lrs, R);
+        DA(C.qi, R); DA(C.qa, R); DA(C.pqi, M * R);
         C.tiles = (u32)((R + RT - 1) / RT);
         const size_t PW = (size_t)C.tiles * 4 * RT;             // 16-byte words per tiled plane
         DA(C.loc, (size_t)RA_LOCAL_CAP * PW); DA(C.loc_n, R);
@@ -648,6 +660,32 @@ extern "C" int ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n)
     CK(cudaStreamSynchronize(e->stream));
     return RA_OK;
 }
+
+static int query_io(ra_engine* e, ra_query_state* q, size_t n, bool load)
+{
+    if (!e || (!q && n)) return RA_E_INVAL;
+    if (n == 0) return RA_OK;
+    for (size_t i = 0; i < n; i++) if (q[i].row >= e->C.rows) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    ra_query_state* d = nullptr;
+    CK(cudaMalloc(&d, n * sizeof(ra_query_state)));
+    cudaError_t ce = cudaMemcpyAsync(d, q, n * sizeof(ra_query_state), cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess) {
+        if (load) load_query_kernel<<<nblocks(n, 128), 128, 0, e->stream>>>(e->C, d, (u32)n);
+        else {
+            read_query_kernel<<<nblocks(n, 128), 128, 0, e->stream>>>(e->C, d, (u32)n);
+            ce = cudaMemcpyAsync(q, d, n * sizeof(ra_query_state), cudaMemcpyDeviceToHost, e->stream);
+        }
+    }
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    cudaFree(d);
+    return ce == cudaSuccess ? RA_OK : fail(e, ce, "query state");
+}
+extern "C" int ra_engine_load_query_state(ra_engine* e, const ra_query_state* q, size_t n)
+{ return query_io(e, const_cast<ra_query_state*>(q), n, true); }
+extern "C" int ra_engine_read_query_state(ra_engine* e, ra_query_state* q, size_t n)
+{ return query_io(e, q, n, false); }
 
 static int launch_step(ra_engine* e, const FloodArgs& F)
 {

@@ -135,6 +135,8 @@ __device__ __forceinline__ void reset_row(const Cols& C, const u32 r)
     for (u32 s = 0; s < C.members; s++) { st2(&C.pnm[(size_t)s * C.rows + r], 1, 0); C.pcs[(size_t)s * C.rows + r] = 0; }
     for (u32 k = 0; k < RA_MAX_RUNS; k++) st2(&C.run[(size_t)k * C.rows + r], 0, 0);
     C.lrs[r] = 0;
+    C.qi[r] = 0; C.qa[r] = 0;
+    for (u32 s = 0; s < C.members; s++) C.pqi[(size_t)s * C.rows + r] = 0;
     C.loc_n[r] = 0; C.out_n[r] = 0;
     if (C.routed) { C.mbox_cnt[0][r] = 0; C.mbox_cnt[1][r] = 0; }
 }
@@ -174,6 +176,8 @@ __device__ __forceinline__ void load_row(const Cols& C, const ra_row_state& s)
     for (u32 k = 0; k < RA_MAX_RUNS; k++)
         st2(&C.run[(size_t)k * C.rows + r], k < s.n_runs ? s.run_start[k] : 0, k < s.n_runs ? s.run_term[k] : 0);
     C.lrs[r] = s.n_runs ? s.run_start[s.n_runs - 1] : 0;
+    C.qi[r] = 0; C.qa[r] = 0;
+    for (u32 p = 0; p < C.members; p++) C.pqi[(size_t)p * C.rows + r] = 0;
     C.loc_n[r] = 0;
 }
 
@@ -231,4 +235,18 @@ __device__ __forceinline__ void deliver_record(const Cols& C, const int buf, con
         if (seen == old) break;
         old = seen;
     }
+}
+
+// ---- consistent-query state of a row <-> ra_query_state ----------------------------------------
+__device__ __forceinline__ void load_query_row(const Cols& C, const ra_query_state& q)
+{
+    const u32 r = q.row;
+    C.qi[r] = q.query_index; C.qa[r] = q.agreed_index;
+    for (u32 p = 0; p < C.members; p++) C.pqi[(size_t)p * C.rows + r] = q.peer_query_index[p];
+}
+__device__ __forceinline__ void read_query_row(const Cols& C, ra_query_state& q)
+{
+    const u32 r = q.row;
+    q._pad = 0; q.query_index = C.qi[r]; q.agreed_index = C.qa[r];
+    for (u32 p = 0; p < RA_MAX_MEMBERS; p++) q.peer_query_index[p] = p < C.members ? C.pqi[(size_t)p * C.rows + r] : 0;
 }

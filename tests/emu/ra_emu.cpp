@@ -81,6 +81,7 @@ extern "C" int ra_emu_create(const ra_engine_cfg* cfg, ra_emu** out)
 #define HA(p, n) if ((rc = halloc(e, &(p), (n))) != RA_OK) goto bad
     HA(C.tc, R); HA(C.lg, R); HA(C.lw, R); HA(C.ap, R); HA(C.sn, R); HA(C.tk, R); HA(C.fm, R);
     HA(C.cd, 2 * R); HA(C.pnm, M * R); HA(C.pcs, M * R); HA(C.run, RA_MAX_RUNS * R); HA(C.lrs, R);
+    HA(C.qi, R); HA(C.qa, R); HA(C.pqi, M * R);
     C.tiles = (u32)((R + RT - 1) / RT);
     {
         const size_t PW = (size_t)C.tiles * 4 * RT;
@@ -124,6 +125,22 @@ extern "C" int ra_emu_read_rows(ra_emu* e, ra_row_state* rows, size_t n)
     if (!e || (!rows && n)) return RA_E_INVAL;
     for (size_t i = 0; i < n; i++) if (rows[i].row >= e->C.rows) return RA_E_INVAL;
     for (size_t i = 0; i < n; i++) read_row(e->C, rows[i]);
+    return RA_OK;
+}
+
+extern "C" int ra_emu_load_query_state(ra_emu* e, const ra_query_state* q, size_t n)
+{
+    if (!e || (!q && n)) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) if (q[i].row >= e->C.rows) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) load_query_row(e->C, q[i]);
+    return RA_OK;
+}
+
+extern "C" int ra_emu_read_query_state(ra_emu* e, ra_query_state* q, size_t n)
+{
+    if (!e || (!q && n)) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) if (q[i].row >= e->C.rows) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) read_query_row(e->C, q[i]);
     return RA_OK;
 }
 
