@@ -28,6 +28,11 @@
 #define MINB 5                              // CTAs per SM the register allocation is held to: 20 warps,
                                             // <= 96 registers (no spills), 5 x 39 KB of shared memory
 #endif
+#ifdef RA_RING_1K
+#ifndef NSLOT
+#define NSLOT 6                             // RA_RING_1K: 1 KB ring slots per warp (experimental, see NOTES_r2_prep.md)
+#endif
+#endif
 #define TILE_BYTES (RT * 64)
 #define RA_BAR_WORDS 64                       // barrier flag words behind mbox_cnt[b] (one per source shard)
 #define WARPS (CTA_T / 32)
@@ -74,10 +79,18 @@ __device__ __forceinline__ void tma_load_tile(void* dst_smem, const void* src_gm
 //   peers[3][8][128] x 8 B           per-thread peer columns (next, match, commit_index_sent), lazy
 template <int MM>
 struct StepSmem {
+#ifdef RA_RING_1K
+    ulonglong2 stage[WARPS][NSLOT][2 * RT];  // 1 KB slots: a tile's heads in one slot, its tails (if any) in the next
+#else
     ulonglong2 stage[WARPS][NST][4 * RT];
+#endif
     ulonglong2 peers_nm[PSTR * CTA_T];       // [s][thread] {next_index, match_index}
     u64 peers_cs[PSTR * CTA_T];              // [s][thread] commit_index_sent (directly behind peers_nm)
+#ifdef RA_RING_1K
+    u64 bars[WARPS][NSLOT];
+#else
     u64 bars[WARPS][NST];
+#endif
 };
 
 // ---- the two kernels of a step ---------------------------------------------------------------
@@ -189,7 +202,11 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     if (!__any_sync(0xffffffffu, work)) return;                 // whole warp idle
     u64* bars = &S.bars[warp][0];
     if (lane == 0) {
+#ifdef RA_RING_1K
+        for (int i = 0; i < NSLOT; i++) mbar_init(&bars[i], 1);
+#else
         for (int i = 0; i < NST; i++) mbar_init(&bars[i], 1);
+#endif
         mbar_fence_init();
     }
     __syncwarp();
@@ -209,6 +226,58 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     if (work && !fatal0 && pending) {                           // pipeline_rpcs is not a fast path
         stalled = true; stall_flags = STALL_PENDING; rem = mine;
     }
+#ifdef RA_RING_1K
+    // ---- experimental ring of NSLOT 1 KB slots: a tile takes one slot (heads) or two (heads, tails) ----
+    mask_t toissue = todo;
+    u32 si = 0, hd = 0, nfree = NSLOT, par = 0;                 // issue / consume positions, free slots, phase bits
+    const size_t plane_words = (size_t)C.tiles * (4 * RT);
+    const ulonglong2* const mb_base = C.mbox[cur] + (size_t)wtile * (4 * RT);
+    const ulonglong2* const lc_base = C.loc + (size_t)wtile * (4 * RT) - (size_t)NPM * plane_words;
+#pragma unroll 1
+    while (todo) {
+        if (lane == 0) {
+#pragma unroll 1
+            while (toissue) {
+                const u32 q = mask_ffs(toissue);
+                const u32 tbit = q < NPM ? q / RA_MBOX_DEPTH : 8u + q - NPM;
+                const u32 need = 1u + ((w_tail >> tbit) & 1u);
+                if (nfree < need) break;
+                toissue &= toissue - 1;
+                const ulonglong2* src = (q < NPM ? mb_base : lc_base) + (size_t)q * plane_words;
+                fence_proxy_async();                            // the slots were read through the generic proxy
+                mbar_expect_tx(&bars[si], need * (TILE_BYTES / 2));
+                tma_load_tile(&S.stage[warp][si][0], src, TILE_BYTES / 2, &bars[si]);
+                const u32 s2 = si + 1 == NSLOT ? 0 : si + 1;
+                if (need == 2) tma_load_tile(&S.stage[warp][s2][0], src + 2 * RT, TILE_BYTES / 2, &bars[si]);
+                si = need == 2 ? (s2 + 1 == NSLOT ? 0 : s2 + 1) : s2;
+                nfree -= need;
+            }
+        }
+        const u32 p = mask_ffs(todo); todo &= todo - 1;
+        const u32 pbit = p < NPM ? p / RA_MBOX_DEPTH : 8u + p - NPM;
+        const u32 need = 1u + ((w_tail >> pbit) & 1u);
+        const u32 h2 = hd + 1 == NSLOT ? 0 : hd + 1;
+        const bool my = !stalled && ((mine >> p) & 1u);
+        mbar_wait(&bars[hd], (par >> hd) & 1u);
+        if (my) {
+            const ulonglong2* sp = &S.stage[warp][hd][0];
+            const ulonglong2 c0 = sp[lane], c1 = sp[RT + lane];
+            ulonglong2 t2 = make_ulonglong2(0, 0), t3 = t2;
+            if (rec_has_tail(c0)) { const ulonglong2* tp = &S.stage[warp][h2][0]; t2 = tp[lane]; t3 = tp[RT + lane]; }
+            const Rec e = rec_decode(c0, c1, t2, t3, r);
+            if (MT_FATAL(m.meta)) m.c_pack += 1u;
+            else if (C.pure || !fast_event<MM>(m, e)) {
+                stalled = true;
+                rem = mine & ~(((mask_t)1 << p) - 1);
+                atomicAdd(&C.counters[8 + (m_role(m) & 7u) * 16 + (R_type(e) & 15u)], 1ull);
+            }
+        }
+        par ^= 1u << hd;                                        // this slot's barrier completed one more phase
+        hd = need == 2 ? (h2 + 1 == NSLOT ? 0 : h2 + 1) : h2;
+        nfree += need;                                          // (only lane 0 uses it)
+        __syncwarp();                                           // every lane is done with the slot(s)
+    }
+#else
     mask_t toissue = todo;                                      // planes still to request
     u32 n_issued = 0, n_done = 0, st_issue = 0, st = 0, par = 0; // ring positions = counters mod NST, phase parity
     const size_t plane_words = (size_t)C.tiles * (4 * RT);      // 16-byte words per plane
@@ -249,6 +318,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         if (++st == NST) { st = 0; par ^= 1u; }
         __syncwarp();                                           // every lane is done with the slot
     }
+#endif
     const u32 rem_mbox = (u32)(rem & (((mask_t)1 << (NPM - 1) << 1) - 1)), rem_loc = (u32)(rem >> (NPM - 1) >> 1);
 
     if (work) {
