@@ -132,7 +132,9 @@ enum ra_note_type {
     RA_NOTE_COMMIT     = 3, /* a=old commit_index b=new      ({aux,eval}, :3611-3614)     */
     RA_NOTE_APPLY      = 4, /* a=first b=last index to run through ra_machine:apply/3     */
     RA_NOTE_STATUS     = 5, /* end-of-step summary: aux=flags, a=term, b=voted_for|leader<<8|
-                               role_old<<16|role_new<<24, c=detail                         */
+                               role_old<<16|role_new<<24, c=detail.  When the only flag is
+                               RA_ST_LEADER_MSG and the row has another note in this step, there is
+                               no STATUS note: the flags are the aux of the row's LAST note       */
     RA_NOTE_SEND_SNAPSHOT = 6, /* a=peer slot b=snapshot index  ({send_snapshot,..} :2395) */
     RA_NOTE_NOT_LEADER = 7, /* COMMAND / CONSISTENT_QUERY reached a non-leader: a=n commands b=leader slot */
     RA_NOTE_QUERY_INDEX = 8,  /* the query just submitted waits for heartbeats: a=its query_index

@@ -1371,6 +1371,10 @@ static void ctx_finish(ctx_t *c)
 {
     member_t *m = c->m;
     if (c->status == 0) return;
+    if (c->status == RA_ST_LEADER_MSG && c->n_notes > 0) {   /* rides in the aux of the row's last note */
+        c->notes[c->n_notes - 1].aux = (uint16_t)c->status;
+        return;
+    }
     ra_note *n = &c->notes[c->n_notes++];           /* one slot is always reserved */
     n->row = m->row; n->type = RA_NOTE_STATUS; n->slot = m->self_slot; n->aux = (uint16_t)c->status;
     n->a = m->current_term;

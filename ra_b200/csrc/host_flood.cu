@@ -109,8 +109,10 @@ static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u
     for (u32 row = r0; row < r1; row++) {
         const ra_note* w0 = nullptr; const ra_note* w1 = nullptr;
         u32 status = 0; bool fatal = false;
+        const ra_note* last = nullptr;
         for (; i < n_notes && notes[i].row == row; i++) {
             const ra_note& n = notes[i];
+            last = &n;
             if (n.type == RA_NOTE_WAL_APPEND) { w0 = w1; w1 = &n; }
             else if (n.type == RA_NOTE_STATUS) {
                 status = n.aux;
@@ -118,6 +120,7 @@ static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u
                 if (n.aux & RA_ST_FATAL) fatal = true;
             }
         }
+        if (last && last->type != RA_NOTE_STATUS) status |= last->aux;   // flags riding in the last note
         if (!run_model || fatal) continue;
         if (w0) put(&out[ne++], row, RA_EV_WRITTEN, 0, w0->c, w0->a, w0->b);
         if (w1) put(&out[ne++], row, RA_EV_WRITTEN, 0, w1->c, w1->a, w1->b);

@@ -66,8 +66,12 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
             reinterpret_cast<u8*>(&cnt[(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
         }
     }
-    note_flush(m);
-    if (m.status & 0xffffu) {
+    // record_leader_msg alone (the steady state of a follower) does not get a STATUS note of its own: the
+    // flags ride in the aux field of the row's last note of the step (include/ra_engine.h, RA_NOTE_STATUS)
+    const u32 st16 = m.status & 0xffffu;
+    const bool elide = st16 == RA_ST_LEADER_MSG && m.pn_type != RA_NOTE_NONE;
+    note_flush(m, elide ? st16 : 0u);
+    if (st16 && !elide) {
         u64 ld = MT_LEADER(m.meta), vf = MT_VOTED(m.meta);
         u64 b = (vf == SLOT_NONE ? 0xFFull : vf) | ((ld == SLOT_NONE ? 0xFFull : ld) << 8) |
                 ((u64)((m.status >> 16) & 7u) << 16) | ((u64)MT_ROLE(m.meta) << 24);

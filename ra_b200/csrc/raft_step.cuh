@@ -553,10 +553,11 @@ __device__ __noinline__ void put_local(ulonglong2* loc, u32 tiles, u32 k, u32 ro
     q[RT] = make_ulonglong2(a, b);
 }
 
-__device__ __forceinline__ void note_flush(Member& m)
+// `aux`: the row's step flags when this is the last note of the step and no STATUS note follows
+__device__ __forceinline__ void note_flush(Member& m, u32 aux = 0)
 {
     if (m.pn_type == RA_NOTE_NONE) return;
-    note_store(m, m.n_notes - 1, m.pn_type, m.pn_slot, 0, m.pn_a, m.pn_b, m.pn_c);
+    note_store(m, m.n_notes - 1, m.pn_type, m.pn_slot, aux, m.pn_a, m.pn_b, m.pn_c);
     if (m.pn_type == RA_NOTE_WAL_APPEND) {          // the flood host model reads the last two back (row_end_of_step)
         const u32 n = m.wk & 3u;
         m.wk = (n < 2 ? n + 1 : 2u) | ((m.n_notes - 1) << 4) | ((m.wk & 0xf0u) << 4);

@@ -110,7 +110,10 @@ class Cluster:
             if rng.random() < self.p_dup:
                 self._post(copy_ev(m), 1)
         saw_leader = set()
-        for n in notes:
+        for i, n in enumerate(notes):
+            last_of_row = i + 1 == len(notes) or notes[i + 1].row != n.row
+            if last_of_row and n.type != abi.NOTE_STATUS and (n.aux & abi.ST_LEADER_MSG):
+                saw_leader.add(n.row)                      # flags riding in the row's last note
             if n.type == abi.NOTE_WAL_APPEND:
                 if rng.random() < self.p_withhold:
                     self._post(abi.ev_written(n.row, n.c, n.a, n.b), rng.randint(3, 12))   # lagging fsync
