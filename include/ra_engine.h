@@ -383,6 +383,22 @@ int  ra_engine_ipc_import(ra_engine* e, uint32_t shard, const ra_ipc_handles* h)
 int  ra_engine_peer_barrier(ra_engine* e);
 
 /*
+ * The same call for batches made only of events the HOST originates (written, command(s), timeouts, tick,
+ * pipeline_rpcs, consistent_query): 32-byte records, half the host->device bytes of a step.  Same grouping
+ * contract, same outputs; an RPC type in such a batch is RA_E_INVAL.
+ */
+typedef struct ra_host_event {
+    uint32_t row;
+    uint8_t  type;       /* enum ra_event_type, host-origin types only */
+    uint8_t  flags;      /* RA_EVF_*                                   */
+    uint16_t n;          /* COMMAND: number of commands                */
+    uint64_t term, a, b; /* WRITTEN: term, from, to                    */
+} ra_host_event;
+int  ra_engine_step_host(ra_engine* e, const ra_host_event* ev, size_t n_ev,
+                         ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                         ra_note* notes, size_t notes_cap, size_t* n_notes);
+
+/*
  * Written-event source: ra_log_wal:complete_batch/1 (src/ra_log_wal.erl:784-808) tells every
  * writer of a WAL batch {ra_log_event, {written, Term, Seq}} with Seq a ra_seq (src/ra_seq.erl: ascending
  * indexes and {From, To} ranges).  ra_wal_batch_to_events turns one batch -- an array of writers -- into the

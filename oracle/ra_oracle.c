@@ -1832,6 +1832,26 @@ int ra_oracle_flood(ra_oracle *o, uint32_t n_steps, uint32_t cmds_per_step,
     return RA_OK;
 }
 
+/* ra_engine_step_host: the same step for a batch of 32-byte host-origin events */
+int ra_oracle_step_host(ra_oracle *o, const ra_host_event *ev, size_t n_ev,
+                        ra_event *msgs, size_t msgs_cap, size_t *n_msgs,
+                        ra_note *notes, size_t notes_cap, size_t *n_notes)
+{
+    if (!o || (!ev && n_ev)) return RA_E_INVAL;
+    ra_event *w = (ra_event *)calloc(n_ev ? n_ev : 1, sizeof(ra_event));
+    if (!w) return RA_E_NOMEM;
+    for (size_t i = 0; i < n_ev; i++) {
+        const u8 t = ev[i].type;
+        if (!(t == RA_EV_WRITTEN || t == RA_EV_COMMAND || t == RA_EV_ELECTION_TIMEOUT || t == RA_EV_AWAIT_COND_TIMEOUT ||
+              t == RA_EV_PIPELINE_RPCS || t == RA_EV_TICK || t == RA_EV_CONSISTENT_QUERY)) { free(w); return RA_E_INVAL; }
+        w[i].row = ev[i].row; w[i].type = t; w[i].from_slot = RA_NO_SLOT; w[i].flags = ev[i].flags; w[i].n = ev[i].n;
+        w[i].term = ev[i].term; w[i].a = ev[i].a; w[i].b = ev[i].b;
+    }
+    int rc = ra_oracle_step(o, w, n_ev, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes);
+    free(w);
+    return rc;
+}
+
 int ra_oracle_counters(ra_oracle *o, ra_counters *out)
 {
     if (!o || !out) return RA_E_INVAL;

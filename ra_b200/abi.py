@@ -131,6 +131,16 @@ class RaRowState(C.Structure):
                       for p in list(self.peers)[: self.n_members]))
 
 
+class RaHostEvent(C.Structure):
+    """ra_host_event: 32-byte record for batches of host-origin events (ra_engine_step_host)."""
+    _fields_ = [("row", C.c_uint32), ("type", C.c_uint8), ("flags", C.c_uint8), ("n", C.c_uint16),
+                ("term", C.c_uint64), ("a", C.c_uint64), ("b", C.c_uint64)]
+
+    @classmethod
+    def of(cls, e: "RaEvent") -> "RaHostEvent":
+        return cls(row=e.row, type=e.type, flags=e.flags, n=e.n, term=e.term, a=e.a, b=e.b)
+
+
 class RaQueryState(C.Structure):
     _fields_ = [("row", C.c_uint32), ("_pad", C.c_uint32), ("query_index", C.c_uint64),
                 ("agreed_index", C.c_uint64), ("peer_query_index", C.c_uint64 * RA_MAX_MEMBERS)]
@@ -160,6 +170,7 @@ class RaCounters(C.Structure):
 
 
 assert C.sizeof(RaEvent) == 64
+assert C.sizeof(RaHostEvent) == 32
 assert C.sizeof(RaNote) == 32
 assert C.sizeof(RaPeerInit) == 32
 
@@ -288,6 +299,25 @@ class Backend:
             arr[i].row = r
         self._check(self._fn("read_rows")(self._h, arr, len(ids)), "read_rows")
         return list(arr)
+
+    def step_host(self, events: Sequence[RaEvent]) -> Tuple[List[RaEvent], List[RaNote]]:
+        """step() for a batch of host-origin events, handed over as 32-byte records."""
+        f = self._fn("step_host")
+        f.restype = C.c_int
+        sz = C.c_size_t
+        f.argtypes = [C.c_void_p, C.POINTER(RaHostEvent), sz, C.POINTER(RaEvent), sz, C.POINTER(sz),
+                      C.POINTER(RaNote), sz, C.POINTER(sz)]
+        n = len(events)
+        ev = (RaHostEvent * max(n, 1))(*[RaHostEvent.of(e) for e in events])
+        msgs_cap = max(64, n * RA_MSG_CAP)
+        notes_cap = max(64, n * RA_NOTE_CAP + 64)
+        if self.cfg.route_on_device and not self.cfg.pure:
+            msgs_cap, notes_cap = 1024, max(64, self.n_rows * RA_NOTE_CAP)
+        msgs = (RaEvent * msgs_cap)()
+        notes = (RaNote * notes_cap)()
+        nm, nn = sz(0), sz(0)
+        self._check(f(self._h, ev, n, msgs, msgs_cap, C.byref(nm), notes, notes_cap, C.byref(nn)), "step_host")
+        return list(msgs[: nm.value]), list(notes[: nn.value])
 
     def load_query_state(self, qs: Sequence[RaQueryState]) -> None:
         f = self._fn("load_query_state")

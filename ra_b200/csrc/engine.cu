@@ -460,6 +460,33 @@ __global__ void ingest_kernel(const Cols C, const ra_event* ev, u32 n, u32* err)
     if (tails) atomicOr(&C.loc_n[row], tails);
 }
 
+// the same for a batch of 32-byte host events: every record is a head (RS_PLAIN); err 3 also for an RPC type
+__device__ __forceinline__ bool host_event_type_ok(u32 t)
+{
+    return t == RA_EV_WRITTEN || t == RA_EV_COMMAND || t == RA_EV_ELECTION_TIMEOUT || t == RA_EV_AWAIT_COND_TIMEOUT ||
+           t == RA_EV_PIPELINE_RPCS || t == RA_EV_TICK || t == RA_EV_CONSISTENT_QUERY;
+}
+__global__ void ingest_host_kernel(const Cols C, const ra_host_event* ev, u32 n, u32* err)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 row = ev[i].row;
+    if (row >= C.rows || !host_event_type_ok(ev[i].type)) { atomicMax(err, 3u); return; }
+    if (i > 0 && ev[i - 1].row == row) return;                 // not the head of its run
+    u32 len = 1;
+    while (i + len < n && ev[i + len].row == row && len <= RA_LOCAL_CAP) len++;
+    if (len > RA_LOCAL_CAP) { atomicMax(err, 2u); return; }
+    if (atomicCAS(&C.loc_n[row], 0u, len) != 0u) { atomicMax(err, 1u); return; }
+    for (u32 k = 0; k < len; k++) {
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(&ev[i + k]);
+        const ulonglong2 h = src[0], t = src[1];               // {row | type<<32 | flags<<40 | n<<48, term}, {a, b}
+        ulonglong2* q = C.loc + rec_word(C.tiles, k, row, 0);
+        const u64 type = (h.x >> 32) & 0xffull, flags = (h.x >> 40) & 0xffull, nn = (h.x >> 48) & 0xffffull;
+        q[0] = make_ulonglong2(type | ((u64)RA_NO_SLOT << 8) | (flags << 16) | ((u64)RS_PLAIN << 24) | (nn << 32), h.y);
+        q[RT] = t;
+    }
+}
+
 // records that other shards sent to members of this engine -> mailbox planes of the next step.
 // The slot is fixed by the record itself (sender slot, k-th record of that sender for this row),
 // the receiver's count byte becomes max(k + 1).
@@ -793,9 +820,9 @@ static int launch_step(ra_engine* e, const FloodArgs& F)
     return RA_OK;
 }
 
-extern "C" int ra_engine_step(ra_engine* e, const ra_event* ev, size_t n_ev,
-                              ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
-                              ra_note* notes, size_t notes_cap, size_t* n_notes)
+static int step_impl(ra_engine* e, const void* ev, size_t n_ev, bool host32,
+                     ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                     ra_note* notes, size_t notes_cap, size_t* n_notes)
 {
     if (!e || (!ev && n_ev) || n_ev > 0x7fffffffull) return RA_E_INVAL;
     CK(cudaSetDevice(e->cfg.device));
@@ -803,14 +830,17 @@ extern "C" int ra_engine_step(ra_engine* e, const ra_event* ev, size_t n_ev,
     int rc;
     // a step() after flood() must not see the flood host model's queued locals
     if (n_ev) {
-        if ((rc = ensure(e, &e->d_ev, &e->d_ev_cap, n_ev))) return rc;
-        CK(cudaMemcpyAsync(e->d_ev, ev, n_ev * sizeof(ra_event), cudaMemcpyHostToDevice, e->stream));
+        if ((rc = ensure(e, &e->d_ev, &e->d_ev_cap, n_ev))) return rc;          // (sized for 64-byte records)
+        CK(cudaMemcpyAsync(e->d_ev, ev, n_ev * (host32 ? sizeof(ra_host_event) : sizeof(ra_event)),
+                           cudaMemcpyHostToDevice, e->stream));
     }
     u32 h_err = 0;
     clear_loc_kernel<<<nblocks(R, 256), 256, 0, e->stream>>>(e->C);
     CK(cudaMemsetAsync(e->d_err, 0, sizeof(u32), e->stream));
     if (n_ev) {
-        ingest_kernel<<<nblocks(n_ev, 256), 256, 0, e->stream>>>(e->C, e->d_ev, (u32)n_ev, e->d_err);
+        if (host32) ingest_host_kernel<<<nblocks(n_ev, 256), 256, 0, e->stream>>>(
+                        e->C, reinterpret_cast<const ra_host_event*>(e->d_ev), (u32)n_ev, e->d_err);
+        else ingest_kernel<<<nblocks(n_ev, 256), 256, 0, e->stream>>>(e->C, e->d_ev, (u32)n_ev, e->d_err);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&h_err, e->d_err, sizeof(u32), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
@@ -842,6 +872,16 @@ extern "C" int ra_engine_step(ra_engine* e, const ra_event* ev, size_t n_ev,
     if (n_notes) *n_notes = tn;
     return RA_OK;
 }
+
+extern "C" int ra_engine_step(ra_engine* e, const ra_event* ev, size_t n_ev,
+                              ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                              ra_note* notes, size_t notes_cap, size_t* n_notes)
+{ return step_impl(e, ev, n_ev, false, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes); }
+
+extern "C" int ra_engine_step_host(ra_engine* e, const ra_host_event* ev, size_t n_ev,
+                                   ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                                   ra_note* notes, size_t notes_cap, size_t* n_notes)
+{ return step_impl(e, ev, n_ev, true, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes); }
 
 extern "C" int ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per_step,
                                uint32_t election_permille, uint64_t seed)

@@ -33,10 +33,10 @@ struct ra_hostsim {
     u32 groups, members, rows;
     std::vector<unsigned char> role, idle;
     u32 threads;
-    std::vector<std::vector<ra_event>> tmp;
+    std::vector<std::vector<ra_host_event>> tmp;
     std::vector<size_t> cnt, off;
     double t_model, t_step;          // seconds spent in the host model / inside ra_engine_step
-    ra_event* ev;  size_t ev_cap;     // pinned
+    ra_host_event* ev;  size_t ev_cap; // pinned; the flood only has host-origin events: 32-byte records
     ra_event* msgs; size_t msgs_cap;  // pinned
     ra_note* notes; size_t notes_cap; // pinned
     size_t n_ev;
@@ -75,7 +75,7 @@ extern "C" int ra_hostsim_create(ra_engine* e, ra_hostsim** out)
         s->cnt.assign(s->threads, 0); s->off.assign(s->threads + 1, 0);
     }
     s->ev_cap = (size_t)s->rows * RA_LOCAL_CAP; s->msgs_cap = 1024; s->notes_cap = (size_t)s->rows * RA_NOTE_CAP;
-    s->ev = (ra_event*)ra_engine_alloc_host(s->ev_cap * sizeof(ra_event));
+    s->ev = (ra_host_event*)ra_engine_alloc_host(s->ev_cap * sizeof(ra_host_event));
     s->msgs = (ra_event*)ra_engine_alloc_host(s->msgs_cap * sizeof(ra_event));
     s->notes = (ra_note*)ra_engine_alloc_host(s->notes_cap * sizeof(ra_note));
     if (!s->ev || !s->msgs || !s->notes) { delete s; return RA_E_NOMEM; }
@@ -91,6 +91,10 @@ extern "C" void ra_hostsim_destroy(ra_hostsim* s)
     delete s;
 }
 
+static inline void put(ra_host_event* e, u32 row, u32 type, u32 n, u64 term, u64 a, u64 b)
+{
+    e->row = row; e->type = (uint8_t)type; e->flags = 0; e->n = (uint16_t)n; e->term = term; e->a = a; e->b = b;
+}
 static inline void put(ra_event* e, u32 row, u32 type, u32 n, u64 term, u64 a, u64 b)
 {
     memset(e, 0, sizeof *e);
@@ -99,7 +103,7 @@ static inline void put(ra_event* e, u32 row, u32 type, u32 n, u64 term, u64 a, u
 }
 
 // notes of one step -> events of the next (the flood host model), rows [r0, r1)
-static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u32 r0, u32 r1, ra_event* out,
+static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u32 r0, u32 r1, ra_host_event* out,
                           u32 cmds, u32 permille, u64 seed, bool run_model)
 {
     // first note of row r0 (notes are ordered by row)
@@ -169,7 +173,7 @@ static void model(ra_hostsim* s, size_t n_notes, u32 cmds, u32 permille, u64 see
             off[0] = 0;
             for (int k = 0; k < T; k++) off[k + 1] = off[k] + cnt[k];
         }
-        if (cnt[t]) memcpy(s->ev + off[t], s->tmp[t].data(), cnt[t] * sizeof(ra_event));
+        if (cnt[t]) memcpy(s->ev + off[t], s->tmp[t].data(), cnt[t] * sizeof(ra_host_event));
     }
     s->n_ev = off[T];
 }
@@ -185,18 +189,18 @@ extern "C" int ra_hostsim_run(ra_hostsim* s, uint32_t n_steps, uint32_t cmds, ui
     int rc;
     if (bootstrap) {
         for (u32 g = 0; g < s->groups; g++) put(&s->ev[g], g, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0);
-        rc = ra_engine_step(s->e, s->ev, s->groups, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
+        rc = ra_engine_step_host(s->e, s->ev, s->groups, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
         if (rc) return rc;
-        s->h2d += (u64)s->groups * sizeof(ra_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
+        s->h2d += (u64)s->groups * sizeof(ra_host_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
         model(s, nn, cmds, permille, seed, false);         // roles only; no model run for this step
         s->n_ev = 0;
     }
     for (u32 t = 0; t < n_steps; t++) {
         auto a0 = std::chrono::steady_clock::now();
-        rc = ra_engine_step(s->e, s->ev, s->n_ev, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
+        rc = ra_engine_step_host(s->e, s->ev, s->n_ev, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
         if (rc) return rc;
         auto a1 = std::chrono::steady_clock::now();
-        s->h2d += (u64)s->n_ev * sizeof(ra_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
+        s->h2d += (u64)s->n_ev * sizeof(ra_host_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
         model(s, nn, cmds, permille, seed, true);
         auto a2 = std::chrono::steady_clock::now();
         s->t_step += std::chrono::duration<double>(a1 - a0).count();

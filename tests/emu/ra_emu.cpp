@@ -352,6 +352,25 @@ extern "C" int ra_emu_step(ra_emu* e, const ra_event* ev, size_t n_ev,
     return RA_OK;
 }
 
+extern "C" int ra_emu_step_host(ra_emu* e, const ra_host_event* ev, size_t n_ev,
+                                ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                                ra_note* notes, size_t notes_cap, size_t* n_notes)
+{
+    if (!e || (!ev && n_ev)) return RA_E_INVAL;
+    ra_event* w = (ra_event*)calloc(n_ev ? n_ev : 1, sizeof(ra_event));
+    if (!w) return RA_E_NOMEM;
+    for (size_t i = 0; i < n_ev; i++) {
+        const u32 t = ev[i].type;
+        if (!(t == RA_EV_WRITTEN || t == RA_EV_COMMAND || t == RA_EV_ELECTION_TIMEOUT || t == RA_EV_AWAIT_COND_TIMEOUT ||
+              t == RA_EV_PIPELINE_RPCS || t == RA_EV_TICK || t == RA_EV_CONSISTENT_QUERY)) { free(w); return RA_E_INVAL; }
+        w[i].row = ev[i].row; w[i].type = (uint8_t)t; w[i].from_slot = RA_NO_SLOT; w[i].flags = ev[i].flags; w[i].n = ev[i].n;
+        w[i].term = ev[i].term; w[i].a = ev[i].a; w[i].b = ev[i].b;
+    }
+    const int rc = ra_emu_step(e, w, n_ev, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes);
+    free(w);
+    return rc;
+}
+
 extern "C" int ra_emu_flood(ra_emu* e, uint32_t n_steps, uint32_t cmds_per_step, uint32_t election_permille,
                             uint64_t seed)
 {
@@ -405,3 +424,6 @@ extern "C" int ra_emu_codec_roundtrip(const ra_event* in, ra_event* out, int* ha
     st_rec(out, ld_rec_plane(plane, 1, 0, row));
     return RA_OK;
 }
+extern "C" int ra_engine_step_host(ra_engine* e, const ra_host_event* ev, size_t n_ev, ra_event* msgs, size_t msgs_cap,
+                                   size_t* n_msgs, ra_note* notes, size_t notes_cap, size_t* n_notes)
+{ return ra_emu_step_host((ra_emu*)e, ev, n_ev, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes); }

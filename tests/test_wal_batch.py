@@ -105,3 +105,35 @@ def test_flood_driven_by_wal_batches_equals_per_note_written_events():
     ra, rb = [r.key() for r in a.read_rows(range(a.n_rows))], [r.key() for r in b.read_rows(range(b.n_rows))]
     assert ra == rb and a.counters() == b.counters()
     assert a.counters()["commits"] > 0
+
+
+@pytest.mark.parametrize("be", ["oracle", "emu", pytest.param("engine", marks=pytest.mark.gpu)])
+def test_step_host_equals_step(be):
+    """ra_engine_step_host: the same batch as 32-byte host events leaves the same records, notes and rows."""
+    g, m = 24, 3
+    outs = []
+    for use_host in (False, True):
+        b = make_backend(be, g, m, route_on_device=True)
+        b.reset_empty()
+        res = []
+        evs = [abi.ev_simple(b.row_of(i, 0), abi.EV_ELECTION_TIMEOUT) for i in range(g)]
+        for _ in range(25):
+            msgs, notes = (b.step_host if use_host else b.step)(evs)
+            res.append(([x.key() for x in msgs], [x.key() for x in notes]))
+            evs = []
+            by_row = {}
+            for n in notes:
+                if n.type == abi.NOTE_WAL_APPEND:
+                    by_row.setdefault(n.row, []).append(abi.ev_written(n.row, n.c, n.a, n.b))
+            for r in b.read_rows(range(b.n_rows)):
+                if r.role == abi.LEADER:
+                    by_row.setdefault(r.row, []).append(abi.ev_command(r.row, 2))
+            for row in sorted(by_row):
+                evs += by_row[row][:abi.RA_LOCAL_CAP]
+        outs.append((res, [r.key() for r in b.read_rows(range(b.n_rows))], b.counters()))
+    assert outs[0] == outs[1]
+    assert outs[0][2]["commits"] > 0
+    b = make_backend(be, g, m)
+    with pytest.raises(abi.RaError) as ei:                      # an RPC is not a host event
+        b.step_host([abi.ev_aer(0, 1, 1, 0, 0, 0, [])])
+    assert ei.value.status == abi.RA_E_INVAL
