@@ -141,7 +141,9 @@ enum ra_note_type {
                                  b=commit_index it must read at (queries_waiting_heartbeats, :3722-3739) */
     RA_NOTE_QUERY_AGREED = 9, /* a=query_index a quorum has confirmed: every waiting query <= a is
                                  applied by the host (heartbeat_rpc_quorum/3, :3766-3784)              */
-    RA_NOTE_QUERY_APPLY = 10  /* no peers: apply the query just submitted right away (:3729-3731)      */
+    RA_NOTE_QUERY_APPLY = 10, /* no peers: apply the query just submitted right away (:3729-3731)      */
+    RA_NOTE_CANCEL_SNAPSHOT_RETRY = 11 /* slot=a=peer: {cancel_snapshot_retry_timer, Peer}: make_all_rpcs/1
+                                 (:2337-2350) also reaches out to a peer in snapshot_backoff          */
 };
 
 /* RA_NOTE_STATUS aux flags */

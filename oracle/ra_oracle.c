@@ -620,10 +620,14 @@ static void update_heartbeat_rpc_effects(ctx_t *c)
 static void make_rpcs(ctx_t *c, int all)
 {
     member_t *m = c->m;
+    if (all)                                   /* make_all_rpcs/1: CancelEffects ++ EffectsAER ++ EffectsHR */
+        for (u32 s = 0; s < m->n_members; s++)
+            if (s != m->self_slot && m->peers[s].status == RA_PEER_SNAPSHOT_BACKOFF)
+                note(c, RA_NOTE_CANCEL_SNAPSHOT_RETRY, (u8)s, s, 0, 0);
     for (u32 s = 0; s < m->n_members; s++) {
         peer_t *p = &m->peers[s];
         if (s == m->self_slot) continue;
-        if (p->status != RA_PEER_NORMAL) continue;
+        if (p->status != RA_PEER_NORMAL && !(all && p->status == RA_PEER_SNAPSHOT_BACKOFF)) continue;
         if (!all) {
             int stale = ((i64)p->match_index < (i64)p->next_index - 1) ||
                         (p->commit_index_sent < m->commit_index);

@@ -42,7 +42,8 @@ EVF_INFO = 0x08
 
 # enum ra_note_type
 (NOTE_NONE, NOTE_WAL_APPEND, NOTE_TRUNCATE, NOTE_COMMIT, NOTE_APPLY, NOTE_STATUS,
- NOTE_SEND_SNAPSHOT, NOTE_NOT_LEADER, NOTE_QUERY_INDEX, NOTE_QUERY_AGREED, NOTE_QUERY_APPLY) = range(11)
+ NOTE_SEND_SNAPSHOT, NOTE_NOT_LEADER, NOTE_QUERY_INDEX, NOTE_QUERY_AGREED, NOTE_QUERY_APPLY,
+ NOTE_CANCEL_SNAPSHOT_RETRY) = range(12)
 
 ST_TERM_VOTE_CHANGED = 0x0001
 ST_ROLE_CHANGED = 0x0002

@@ -872,14 +872,21 @@ enum { RP_PIPELINE = 0, RP_STALE = 1, RP_ALL = 2 };
 template <int MM>
 __device__ __forceinline__ bool rpc_pass(Member& m, u32 mode, bool force, const bool heartbeats = true)
 {
+    // (`heartbeats` = false in the hot kernel: its one RP_ALL call site has made sure that no consistent
+    // query is in flight and that every peer is `normal`, so neither heartbeats nor backoff peers exist)
     const Cols& C = *m.C;
     if (mode == RP_PIPELINE && m.pipe_clean && !force) return false;
     u64 next_log_idx = m.last_idx + 1;
     i64 max_pipe = C.max_pipeline, max_batch = C.max_batch;
     bool more = false, clean = true;
+    if (heartbeats && mode == RP_ALL)          // make_all_rpcs/1: CancelEffects ++ EffectsAER ++ EffectsHR
+        for (u32 s = 0; s < NMEM(C); s++)
+            if (s != m.slot && MT_PSTATUS(m.meta, s) == RA_PEER_SNAPSHOT_BACKOFF)
+                note(m, RA_NOTE_CANCEL_SNAPSHOT_RETRY, s, s, 0, 0);
     for (u32 s = 0; s < NMEM(C); s++) {
         if (s == m.slot) continue;
-        if (MT_PSTATUS(m.meta, s) != RA_PEER_NORMAL) continue;
+        if (MT_PSTATUS(m.meta, s) != RA_PEER_NORMAL &&
+            !(heartbeats && mode == RP_ALL && MT_PSTATUS(m.meta, s) == RA_PEER_SNAPSHOT_BACKOFF)) continue;
         ulonglong2 nm = peer_nm<MM>(m, s);
         u64 cs = peer_cs<MM>(m, s);
         i64 bs = 1;
@@ -1631,7 +1638,7 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
         u32 mode = RP_PIPELINE;
         if (type == RA_EV_PRE_VOTE) {                                  // :952-957 enforce leadership
             // (with a consistent query in flight make_all_rpcs also re-sends heartbeats: general path)
-            if (R_term(e) > m.term || q_index(m) != 0) return false;
+            if (R_term(e) > m.term || ((m.meta >> 32) & 0xFFFFFFull) != 0 || q_index(m) != 0) return false;
             m.c_pack += 1u;
             mode = RP_ALL;
         } else if (type == RA_EV_COMMAND) {                            // :644-729

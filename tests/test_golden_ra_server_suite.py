@@ -887,3 +887,21 @@ def test_reference_counters(be):
     assert role == CANDIDATE
     d = delta()
     assert d["elections"] == 1 and d["term_and_voted_for_updates"] == 2
+
+
+def test_leader_pre_vote_sends_rpc_to_backoff_peer(be):
+    """leader_pre_vote_sends_snapshot_to_backoff_peer/1, :2548-2574: make_all_rpcs/1 (:2337-2350) cancels the
+    snapshot retry timer of a peer in snapshot_backoff and sends it an rpc as well."""
+    nd = Node(be, 3)
+    st = base_state(3)
+    st.votes = 1
+    st.peers[N2].status = PEER_SNAPSHOT_BACKOFF
+    role, s, msgs, notes = nd.handle_leader(ev_pre_vote(0, N1, 5, 77, 3, 5), st)
+    assert role == LEADER
+    assert [(n.slot, n.a) for n in notes_of(notes, NOTE_CANCEL_SNAPSHOT_RETRY)] == [(N2, N2)]
+    assert sorted(m.row for m in of_type(msgs, EV_AER)) == [N2, N3]
+    # a tick (make_rpcs/1 over stale_peers/1) still leaves the backoff peer alone
+    st.peers[N2].match_index = 1
+    st.peers[N3].match_index = 1
+    role, s, msgs, notes = nd.handle_leader(ev_simple(0, EV_TICK), st)
+    assert [m.row for m in of_type(msgs, EV_AER)] == [N3] and notes_of(notes, NOTE_CANCEL_SNAPSHOT_RETRY) == []
