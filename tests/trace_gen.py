@@ -26,13 +26,14 @@ class Cluster:
     """Network + WAL + clients around one backend (non-routed engine or oracle)."""
 
     def __init__(self, backend, seed: int, *, p_drop=0.02, p_dup=0.01, p_delay=0.15, p_cmd=0.5,
-                 p_timeout=0.01, p_adversarial=0.01, p_withhold_written=0.05, max_cmd=3):
+                 p_timeout=0.01, p_adversarial=0.01, p_withhold_written=0.05, max_cmd=3, p_query=0.0):
         self.b = backend
         self.rng = random.Random(seed)
         self.p_drop, self.p_dup, self.p_delay = p_drop, p_dup, p_delay
         self.p_cmd, self.p_timeout, self.p_adv = p_cmd, p_timeout, p_adversarial
         self.p_withhold = p_withhold_written
         self.max_cmd = max_cmd
+        self.p_query = p_query                                  # consistent queries handed to leaders
         self.queues: Dict[int, deque] = defaultdict(deque)      # row -> events ready now
         self.delayed: List[Tuple[int, abi.RaEvent]] = []        # (due_step, event)
         self.step_no = 0
@@ -58,6 +59,8 @@ class Cluster:
             role = self.roles.get(row, abi.FOLLOWER)
             if role == abi.LEADER and rng.random() < self.p_cmd:
                 self.queues[row].append(abi.ev_command(row, rng.randint(1, self.max_cmd)))
+            if self.p_query and rng.random() < (self.p_query if role == abi.LEADER else self.p_query * 0.05):
+                self.queues[row].append(abi.ev_consistent_query(row))
             elif rng.random() < self.p_cmd * 0.02:
                 self.queues[row].append(abi.ev_command(row, 1))           # misdirected command
             if rng.random() < self.p_timeout or self.idle[row] > 12 + (row % 7):
