@@ -59,10 +59,10 @@ class Cluster:
             role = self.roles.get(row, abi.FOLLOWER)
             if role == abi.LEADER and rng.random() < self.p_cmd:
                 self.queues[row].append(abi.ev_command(row, rng.randint(1, self.max_cmd)))
-            if self.p_query and rng.random() < (self.p_query if role == abi.LEADER else self.p_query * 0.05):
-                self.queues[row].append(abi.ev_consistent_query(row))
             elif rng.random() < self.p_cmd * 0.02:
                 self.queues[row].append(abi.ev_command(row, 1))           # misdirected command
+            if self.p_query and rng.random() < (self.p_query if role == abi.LEADER else self.p_query * 0.05):
+                self.queues[row].append(abi.ev_consistent_query(row))
             if rng.random() < self.p_timeout or self.idle[row] > 12 + (row % 7):
                 self.queues[row].append(abi.ev_simple(row, abi.EV_ELECTION_TIMEOUT))
                 self.idle[row] = 0
