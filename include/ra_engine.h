@@ -75,7 +75,13 @@ enum ra_event_type {
     RA_EV_ELECTION_TIMEOUT  = 9,  /* election_timeout                              */
     RA_EV_AWAIT_COND_TIMEOUT= 10, /* await_condition_timeout                       */
     RA_EV_PIPELINE_RPCS     = 11, /* pipeline_rpcs            ra_server.erl:784-792 */
-    RA_EV_TICK              = 12  /* leader tick -> make_rpcs ra_server_proc.erl:610 */
+    RA_EV_TICK              = 12, /* leader tick -> make_rpcs ra_server_proc.erl:610 */
+    /* consistent queries: the heartbeat round of ra_server.erl:846-918, :3700-3825 */
+    RA_EV_HEARTBEAT_RPC     = 13, /* #heartbeat_rpc{}   from_slot=leader term a=query_index          */
+    RA_EV_HEARTBEAT_REPLY   = 14, /* {Peer,#heartbeat_reply{}}  from_slot=peer term a=query_index    */
+    RA_EV_CONSISTENT_QUERY  = 15  /* {consistent_query|consistent_aux,_,_} handed to the leader; the
+                                     host holds the query refs and submits one only while cluster
+                                     changes are permitted (it keeps `pending_consistent_queries`)  */
 };
 
 /* ra_event.flags */
@@ -99,6 +105,9 @@ enum ra_event_type {
  *  PRE_VOTE_RES    voter       term      -               -              token          granted(0/1)
  *  WRITTEN         -           term      from            to                                        (Seq = [{from,to}])
  *  COMMAND         -           -         -               -              -              -            n = number of commands
+ *  HEARTBEAT_RPC   leader      term      query_index
+ *  HEARTBEAT_REPLY replier     term      query_index
+ *  CONSISTENT_QUERY -
  */
 typedef struct ra_event {
     uint32_t row;        /* destination member row                                  */
@@ -123,9 +132,18 @@ enum ra_note_type {
     RA_NOTE_COMMIT     = 3, /* a=old commit_index b=new      ({aux,eval}, :3611-3614)     */
     RA_NOTE_APPLY      = 4, /* a=first b=last index to run through ra_machine:apply/3     */
     RA_NOTE_STATUS     = 5, /* end-of-step summary: aux=flags, a=term, b=voted_for|leader<<8|
-                               role_old<<16|role_new<<24, c=detail                         */
+                               role_old<<16|role_new<<24, c=detail.  When the only flag is
+                               RA_ST_LEADER_MSG and the row has another note in this step, there is
+                               no STATUS note: the flags are the aux of the row's LAST note       */
     RA_NOTE_SEND_SNAPSHOT = 6, /* a=peer slot b=snapshot index  ({send_snapshot,..} :2395) */
-    RA_NOTE_NOT_LEADER = 7  /* COMMAND reached a non-leader: a=n commands b=leader slot   */
+    RA_NOTE_NOT_LEADER = 7, /* COMMAND / CONSISTENT_QUERY reached a non-leader: a=n commands b=leader slot */
+    RA_NOTE_QUERY_INDEX = 8,  /* the query just submitted waits for heartbeats: a=its query_index
+                                 b=commit_index it must read at (queries_waiting_heartbeats, :3722-3739) */
+    RA_NOTE_QUERY_AGREED = 9, /* a=query_index a quorum has confirmed: every waiting query <= a is
+                                 applied by the host (heartbeat_rpc_quorum/3, :3766-3784)              */
+    RA_NOTE_QUERY_APPLY = 10, /* no peers: apply the query just submitted right away (:3729-3731)      */
+    RA_NOTE_CANCEL_SNAPSHOT_RETRY = 11 /* slot=a=peer: {cancel_snapshot_retry_timer, Peer}: make_all_rpcs/1
+                                 (:2337-2350) also reaches out to a peer in snapshot_backoff          */
 };
 
 /* RA_NOTE_STATUS aux flags */
@@ -146,7 +164,8 @@ enum ra_fatal {
     RA_FATAL_WRITE_INTEGRITY = 2,          /* ra_log:write/2 {error,{integrity_error,_}}  :1369    */
     RA_FATAL_SET_LAST_INDEX_NOT_FOUND = 3, /* {ok,L} = ra_log:set_last_index(..) badmatch :1301    */
     RA_FATAL_ASSERT = 4,                   /* a ?assert / ?assertNot in the reference failed       */
-    RA_FATAL_NO_SNAPSHOT = 5               /* make_rpc_effect: prev entry and snapshot both absent :2378 */
+    RA_FATAL_NO_SNAPSHOT = 5,              /* make_rpc_effect: prev entry and snapshot both absent :2378 */
+    RA_FATAL_LEADER_SAW_HEARTBEAT_SAME_TERM = 6 /* exit(leader_saw_heartbeat_rpc_in_same_term) :894 */
 };
 
 typedef struct ra_note {
@@ -241,6 +260,14 @@ typedef struct ra_counters {
     uint64_t elections_won;
     uint64_t fatal_rows;
     uint64_t steps;
+    /* the reference's own counters of this path (src/ra.hrl:324-343), summed over all members */
+    uint64_t aer_received_follower;        /* ?C_RA_SRV_AER_RECEIVED_FOLLOWER        ra_server.erl:1278,1418 */
+    uint64_t aer_received_follower_empty;  /* ?C_RA_SRV_AER_RECEIVED_FOLLOWER_EMPTY  :1290 */
+    uint64_t aer_replies_success;          /* ?C_RA_SRV_AER_REPLIES_SUCCESS          :528  */
+    uint64_t aer_replies_failed;           /* ?C_RA_SRV_AER_REPLIES_FAILED           :590  */
+    uint64_t elections;                    /* ?C_RA_SRV_ELECTIONS                    :2856 */
+    uint64_t pre_vote_elections;           /* ?C_RA_SRV_PRE_VOTE_ELECTIONS           :2878 */
+    uint64_t term_and_voted_for_updates;   /* ?C_RA_SRV_TERM_AND_VOTED_FOR_UPDATES   :3026 */
 } ra_counters;
 
 enum ra_status {
@@ -279,6 +306,18 @@ static inline int ra_row_state_valid(const ra_row_state* s)
 int  ra_engine_reset_empty(ra_engine* e);
 /* For the parity diff. `rows[i].row` selects the row; the rest is filled in. */
 int  ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n);
+
+/* Consistent-query state of a member (kept apart from ra_row_state): its own query_index
+ * (ra_server_state(), :96), every peer's (ra_peer_state(), ra.hrl:63-75) and the highest index the
+ * host has been told a quorum agreed on.  load/read like the rows; zero after reset / load_rows. */
+typedef struct ra_query_state {
+    uint32_t row, _pad;
+    uint64_t query_index;
+    uint64_t agreed_index;
+    uint64_t peer_query_index[RA_MAX_MEMBERS];
+} ra_query_state;
+int  ra_engine_load_query_state(ra_engine* e, const ra_query_state* q, size_t n);
+int  ra_engine_read_query_state(ra_engine* e, ra_query_state* q, size_t n);
 
 /*
  * Evaluate one batch.  ev[0..n_ev): events for one row must be adjacent and are applied
@@ -340,6 +379,48 @@ int  ra_engine_peer_get(ra_engine* e, ra_peer_ptrs* out);
 int  ra_engine_peer_set(ra_engine* e, uint32_t shard, const ra_peer_ptrs* p);
 int  ra_engine_ipc_export(ra_engine* e, ra_ipc_handles* out);
 int  ra_engine_ipc_import(ra_engine* e, uint32_t shard, const ra_ipc_handles* h);
+/* Peer transport, one shard per process: the step barrier as a kernel on the engine's stream (flag
+ * words in every peer's HBM, release / acquire at system scope) instead of a collective.  All shards
+ * must have the same number of rows; never use it with several shards on ONE stream. */
+int  ra_engine_peer_barrier(ra_engine* e);
+
+/*
+ * The same call for batches made only of events the HOST originates (written, command(s), timeouts, tick,
+ * pipeline_rpcs, consistent_query): 32-byte records, half the host->device bytes of a step.  Same grouping
+ * contract, same outputs; an RPC type in such a batch is RA_E_INVAL.
+ */
+typedef struct ra_host_event {
+    uint32_t row;
+    uint8_t  type;       /* enum ra_event_type, host-origin types only */
+    uint8_t  flags;      /* RA_EVF_*                                   */
+    uint16_t n;          /* COMMAND: number of commands                */
+    uint64_t term, a, b; /* WRITTEN: term, from, to                    */
+} ra_host_event;
+int  ra_engine_step_host(ra_engine* e, const ra_host_event* ev, size_t n_ev,
+                         ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                         ra_note* notes, size_t notes_cap, size_t* n_notes);
+
+/*
+ * Written-event source: ra_log_wal:complete_batch/1 (src/ra_log_wal.erl:784-808) tells every
+ * writer of a WAL batch {ra_log_event, {written, Term, Seq}} with Seq a ra_seq (src/ra_seq.erl: ascending
+ * indexes and {From, To} ranges).  ra_wal_batch_to_events turns one batch -- an array of writers -- into the
+ * grouped event array of ra_engine_step: one RA_EV_WRITTEN per range, ranges of a writer ascending and
+ * adjacent (ra_log:handle_event/2 :849-896 ends at the highest index of the seq whose term matches, which
+ * is what the ranges applied in ascending order leave), writers in the order given.  A writer takes at
+ * most `max_per_row` (<= RA_LOCAL_CAP, minus what the caller reserves for other events of that row)
+ * records of one step: the rest is reported through `resume` and goes into the next step.
+ */
+typedef struct ra_wal_writer {
+    uint32_t row;                 /* the member (UId) the WAL wrote for                      */
+    uint32_t n_ranges;
+    uint64_t term;                /* #batch_writer.term                                      */
+    const uint64_t* ranges;       /* n_ranges x {from, to}, ascending, non-overlapping       */
+} ra_wal_writer;
+typedef struct ra_wal_resume { uint32_t writer, range; } ra_wal_resume;   /* first range not emitted */
+/* returns the number of events written to `out` (<= cap); *resume = {n_writers, 0} when the batch is done.
+ * Start with *resume = {0, 0}; call again (next step) while resume->writer < n_writers. */
+size_t ra_wal_batch_to_events(const ra_wal_writer* writers, size_t n_writers, uint32_t max_per_row,
+                              ra_event* out, size_t cap, ra_wal_resume* resume);
 
 /*
  * The same flood driven from the HOST through ra_engine_step (host buffers, H2D of the

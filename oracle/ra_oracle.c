@@ -54,6 +54,7 @@ typedef uint8_t  u8;
 /* ------------------------------------------------------------------ */
 typedef struct {
     u64 next_index, match_index, commit_index_sent;
+    u64 query_index;                 /* consistent queries, ra.hrl:63-75 */
     u8  status, voter;
 } peer_t;
 
@@ -79,6 +80,8 @@ typedef struct {
     u32 votes, machine_version, effective_machine_version;
     u64 current_term, commit_index, last_applied;
     u64 pre_vote_token, token_counter;
+    u64 query_index;                 /* ra_server_state() :96 */
+    u64 agreed_index;                /* highest query index a quorum confirmed and the host was told */
     u64 cond_reply_term, cond_reply_next, cond_reply_last_index, cond_reply_last_term;
     peer_t peers[RA_MAX_MEMBERS];
     log_t log;
@@ -368,6 +371,8 @@ static void update_term_and_voted_for(ctx_t *c, u64 term, u8 voted_for)
     m->current_term = term;
     m->voted_for = voted_for;
     c->status |= RA_ST_TERM_VOTE_CHANGED;      /* ra_log_meta:store_sync :3024-3025 */
+    c->cnt->term_and_voted_for_updates++;      /* :3026 */
+    for (u32 p = 0; p < RA_MAX_MEMBERS; p++) m->peers[p].query_index = 0;   /* reset_query_index/1 :3029 */
 }
 
 /* update_term/2 :3033-3037 */
@@ -564,15 +569,65 @@ static int make_pipelined_rpc_effects(ctx_t *c, int force, int pure)
     return more;
 }
 
+/* ---- consistent queries: the heartbeat round, :3700-3825 ------------------------------ */
+static void send_heartbeat_reply(ctx_t *c, u32 to, u64 term, u64 query_index)
+{   /* heartbeat_reply/2 :3700-3702, cast to the rpc's leader_id */
+    msg_t r; memset(&r, 0, sizeof r);
+    r.type = RA_EV_HEARTBEAT_REPLY; r.term = term; r.a = query_index;
+    emit_msg(c, to, &r);
+}
+/* heartbeat_rpc_effects/4 :3749-3771: normal peers whose query_index lags */
+static void heartbeat_rpc_effects(ctx_t *c, u64 query_index)
+{
+    member_t *m = c->m;
+    for (u32 s = 0; s < m->n_members; s++) {
+        if (s == m->self_slot) continue;
+        if (m->peers[s].status != RA_PEER_NORMAL) continue;
+        if (!(m->peers[s].query_index < query_index)) continue;
+        msg_t r; memset(&r, 0, sizeof r);
+        r.type = RA_EV_HEARTBEAT_RPC; r.term = m->current_term; r.a = query_index;
+        emit_msg(c, s, &r);
+    }
+}
+/* get_current_query_quorum/1 :3796-3797 over query_indexes/1 :3632-3642 */
+static u64 query_quorum(const member_t *m)
+{
+    u64 v[RA_MAX_MEMBERS]; size_t n = 0;
+    v[n++] = m->query_index;
+    for (u32 s = 0; s < m->n_members; s++)
+        if (s != m->self_slot && m->peers[s].voter) v[n++] = m->peers[s].query_index;
+    return ra_oracle_agreed_commit(v, n);
+}
+/* what the waiting queries learn: every one with an index <= agreed is applied by the host */
+static void query_agreed(ctx_t *c, u64 agreed)
+{
+    member_t *m = c->m;
+    if (agreed > m->agreed_index) {
+        m->agreed_index = agreed;
+        note(c, RA_NOTE_QUERY_AGREED, 0, agreed, 0, 0);
+    }
+}
+/* update_heartbeat_rpc_effects/1 :3704-3720 (tick, enforce leadership) */
+static void update_heartbeat_rpc_effects(ctx_t *c)
+{
+    member_t *m = c->m;
+    if (m->n_members <= 1) query_agreed(c, m->query_index);       /* no peers: apply everything waiting */
+    else heartbeat_rpc_effects(c, m->query_index);
+}
+
 /* make_rpcs_for/2 :2352-2360 over stale_peers/1 :2985-3003 (all=0) or every normal
    peer (make_all_rpcs/1 :2337-2350, all=1); batch size 1, peers are not updated */
 static void make_rpcs(ctx_t *c, int all)
 {
     member_t *m = c->m;
+    if (all)                                   /* make_all_rpcs/1: CancelEffects ++ EffectsAER ++ EffectsHR */
+        for (u32 s = 0; s < m->n_members; s++)
+            if (s != m->self_slot && m->peers[s].status == RA_PEER_SNAPSHOT_BACKOFF)
+                note(c, RA_NOTE_CANCEL_SNAPSHOT_RETRY, (u8)s, s, 0, 0);
     for (u32 s = 0; s < m->n_members; s++) {
         peer_t *p = &m->peers[s];
         if (s == m->self_slot) continue;
-        if (p->status != RA_PEER_NORMAL) continue;
+        if (p->status != RA_PEER_NORMAL && !(all && p->status == RA_PEER_SNAPSHOT_BACKOFF)) continue;
         if (!all) {
             int stale = ((i64)p->match_index < (i64)p->next_index - 1) ||
                         (p->commit_index_sent < m->commit_index);
@@ -582,6 +637,7 @@ static void make_rpcs(ctx_t *c, int all)
         (void)make_rpc_effect(c, s, p->next_index, 1, &snap);
         if (c->m->fatal) return;
     }
+    update_heartbeat_rpc_effects(c);                          /* EffectsAER ++ EffectsHR */
 }
 
 /* initialise_peers/1 :3207-3215 */
@@ -592,6 +648,7 @@ static void initialise_peers(member_t *m)
         m->peers[s].next_index = next;
         m->peers[s].match_index = 0;
         m->peers[s].commit_index_sent = 0;
+        m->peers[s].query_index = 0;
         m->peers[s].status = RA_PEER_NORMAL;
     }
 }
@@ -609,11 +666,13 @@ static u8 call_for_election(ctx_t *c, u8 target, nextq_t *nq)
     msg_t req; memset(&req, 0, sizeof req);
     if (target == RA_CANDIDATE) {
         u64 new_term = m->current_term + 1;
+        c->cnt->elections++;                                     /* :2856 */
         req.type = RA_EV_REQUEST_VOTE; req.term = new_term; req.a = last_idx; req.b = last_term;
         self.type = RA_EV_REQUEST_VOTE_RES; self.term = new_term; self.d = 1;
         update_term_and_voted_for(c, new_term, m->self_slot);
     } else {
         u64 token = ++m->token_counter;                          /* make_ref() */
+        c->cnt->pre_vote_elections++;                            /* :2878 */
         req.type = RA_EV_PRE_VOTE; req.term = m->current_term; req.a = last_idx; req.b = last_term;
         req.c = token; req.d = (u64)1 /* ?RA_PROTO_VERSION */ | ((u64)m->machine_version << 32);
         self.type = RA_EV_PRE_VOTE_RES; self.term = m->current_term; self.c = token; self.d = 1;
@@ -695,6 +754,7 @@ static u8 handle_follower(ctx_t *c, const msg_t *e, nextq_t *nq)
     case RA_EV_AER: {
         u64 term = e->term, cur = m->current_term;
         u32 leader = e->from_slot;
+        c->cnt->aer_received_follower++;                                     /* :1278 and :1418 */
         if (term >= cur) {                                                   /* :1266-1414 */
             u64 pl_idx = e->a, pl_term = e->b, leader_commit = e->c;
             c->status |= RA_ST_LEADER_MSG;                                   /* {record_leader_msg,_} */
@@ -710,6 +770,7 @@ static u8 handle_follower(ctx_t *c, const msg_t *e, nextq_t *nq)
                     last_valid = idx; k++;
                 }
                 if (k == n0) {                                               /* Entries == [] :1288 */
+                    c->cnt->aer_received_follower_empty++;                   /* :1290 */
                     u64 local_last = m->log.last_index;
                     int validated;
                     if (n0 == 0 && local_last > pl_idx) {                    /* :1294-1303 */
@@ -836,6 +897,21 @@ static u8 handle_follower(ctx_t *c, const msg_t *e, nextq_t *nq)
     case RA_EV_COMMAND:                       /* ra_server_proc.erl:827-845: redirect / reject */
         note(c, RA_NOTE_NOT_LEADER, 0, e->n, m->leader_slot, 0);
         return RA_FOLLOWER;
+    case RA_EV_CONSISTENT_QUERY:              /* only a leader answers consistent queries */
+        note(c, RA_NOTE_NOT_LEADER, 0, 0, m->leader_slot, 0);
+        return RA_FOLLOWER;
+    case RA_EV_HEARTBEAT_RPC:
+        if (e->term >= m->current_term) {                                    /* :1425-1434 */
+            update_term(c, e->term);
+            m->leader_slot = e->from_slot;
+            send_heartbeat_reply(c, e->from_slot, e->term, e->a);
+        } else {                                                             /* :1435-1440 */
+            send_heartbeat_reply(c, e->from_slot, m->current_term, e->a);
+        }
+        return RA_FOLLOWER;
+    case RA_EV_HEARTBEAT_REPLY:                                              /* :1518-1521 */
+        update_term(c, e->term > m->current_term ? e->term : m->current_term);
+        return RA_FOLLOWER;
     default:                                  /* :1593-1602, :1639-1641 */
         return RA_FOLLOWER;
     }
@@ -867,6 +943,7 @@ static u8 handle_leader(ctx_t *c, const msg_t *e, nextq_t *nq, int pure)
         u32 from = e->from_slot;
         int success = e->d != 0;
         if (success && term == m->current_term) {                            /* :522-561 */
+            c->cnt->aer_replies_success++;                                   /* :528 */
             if (!is_peer(m, from)) return RA_LEADER;
             peer_t *p = &m->peers[from];
             if (e->b > p->match_index) p->match_index = e->b;                /* max(MI, LastIdx) */
@@ -881,6 +958,7 @@ static u8 handle_leader(ctx_t *c, const msg_t *e, nextq_t *nq, int pure)
         }
         if (!success) {                                                      /* :577-643 */
             if (!is_peer(m, from)) return RA_LEADER;
+            c->cnt->aer_replies_failed++;                                    /* :590 */
             peer_t *p = &m->peers[from];
             u64 peer_next = e->a, peer_last = e->b, peer_last_term = e->c;
             u64 mi = p->match_index, ni = p->next_index;
@@ -954,6 +1032,36 @@ static u8 handle_leader(ctx_t *c, const msg_t *e, nextq_t *nq, int pure)
     case RA_EV_TICK:                                        /* ra_server_proc.erl:610-613 */
         make_rpcs(c, 0);
         return RA_LEADER;
+    case RA_EV_CONSISTENT_QUERY:                            /* :846-851 + make_heartbeat_rpc_effects/2 :3722-3739 */
+        if (m->n_members <= 1) {                            /* no peers: apply right away */
+            note(c, RA_NOTE_QUERY_APPLY, 0, m->commit_index, 0, 0);
+            return RA_LEADER;
+        }
+        m->query_index++;
+        heartbeat_rpc_effects(c, m->query_index);
+        note(c, RA_NOTE_QUERY_INDEX, 0, m->query_index, m->commit_index, 0);
+        return RA_LEADER;
+    case RA_EV_HEARTBEAT_RPC:
+        if (e->term > m->current_term) {                                     /* :871-880 */
+            u8 r = step_down(c, e->term);
+            next_event(nq, e, 0);
+            return r;
+        }
+        if (e->term < m->current_term) {                                     /* :881-888 */
+            send_heartbeat_reply(c, e->from_slot, m->current_term, e->a);
+            return RA_LEADER;
+        }
+        set_fatal(c, RA_FATAL_LEADER_SAW_HEARTBEAT_SAME_TERM);               /* :889-894 */
+        return RA_LEADER;
+    case RA_EV_HEARTBEAT_REPLY:                                              /* :895-918 */
+        if (e->term == m->current_term) {                   /* heartbeat_rpc_quorum/3 :3773-3795 */
+            if (is_peer(m, e->from_slot) && e->a > m->peers[e->from_slot].query_index)
+                m->peers[e->from_slot].query_index = e->a;
+            query_agreed(c, query_quorum(m));
+            return RA_LEADER;
+        }
+        if (e->term > m->current_term) return step_down(c, e->term);
+        return RA_LEADER;                                   /* lower term: ignored */
     default:                                                /* :958-963, :1021-1023 */
         return RA_LEADER;
     }
@@ -1026,6 +1134,23 @@ static u8 handle_candidate(ctx_t *c, const msg_t *e, nextq_t *nq)
     case RA_EV_COMMAND:                                     /* ra_server_proc.erl:680-684 reject */
         note(c, RA_NOTE_NOT_LEADER, 0, e->n, m->leader_slot, 0);
         return RA_CANDIDATE;
+    case RA_EV_CONSISTENT_QUERY:
+        note(c, RA_NOTE_NOT_LEADER, 0, 0, m->leader_slot, 0);
+        return RA_CANDIDATE;
+    case RA_EV_HEARTBEAT_RPC:
+        if (e->term >= m->current_term) {                                    /* :1064-1067 */
+            update_term_and_voted_for(c, e->term, RA_NO_SLOT);
+            next_event(nq, e, 0);
+            return RA_FOLLOWER;
+        }
+        send_heartbeat_reply(c, e->from_slot, m->current_term, e->a);        /* :1068-1073 */
+        return RA_CANDIDATE;
+    case RA_EV_HEARTBEAT_REPLY:
+        if (e->term > m->current_term) {                                     /* :1074-1081 */
+            update_term_and_voted_for(c, e->term, RA_NO_SLOT);
+            return RA_FOLLOWER;
+        }
+        return RA_CANDIDATE;
     default:
         return RA_CANDIDATE;
     }
@@ -1078,6 +1203,25 @@ static u8 handle_pre_vote(ctx_t *c, const msg_t *e, nextq_t *nq)
     case RA_EV_COMMAND:                                     /* ra_server_proc.erl:746-750 reject */
         note(c, RA_NOTE_NOT_LEADER, 0, e->n, m->leader_slot, 0);
         return RA_PRE_VOTE;
+    case RA_EV_CONSISTENT_QUERY:
+        note(c, RA_NOTE_NOT_LEADER, 0, 0, m->leader_slot, 0);
+        return RA_PRE_VOTE;
+    case RA_EV_HEARTBEAT_RPC:
+        if (e->term >= m->current_term) {                                    /* :1181-1186 */
+            update_term(c, e->term);
+            m->votes = 0;
+            next_event(nq, e, 0);
+            return RA_FOLLOWER;
+        }
+        send_heartbeat_reply(c, e->from_slot, m->current_term, e->a);        /* :1187-1191 */
+        return RA_PRE_VOTE;
+    case RA_EV_HEARTBEAT_REPLY:
+        if (e->term > m->current_term) {                                     /* :1192-1195 */
+            m->votes = 0;
+            update_term(c, e->term);
+            return RA_FOLLOWER;
+        }
+        return RA_PRE_VOTE;
     default:
         return RA_PRE_VOTE;
     }
@@ -1128,6 +1272,9 @@ static u8 handle_await_condition(ctx_t *c, const msg_t *e, nextq_t *nq)
         }
         return RA_AWAIT_CONDITION;
     }
+    case RA_EV_CONSISTENT_QUERY:
+        note(c, RA_NOTE_NOT_LEADER, 0, 0, m->leader_slot, 0);
+        return RA_AWAIT_CONDITION;
     case RA_EV_COMMAND:                                     /* ra_server_proc.erl:1144-1163 postponed */
         c->status |= RA_ST_CMD_POSTPONED;
         return RA_AWAIT_CONDITION;
@@ -1228,6 +1375,10 @@ static void ctx_finish(ctx_t *c)
 {
     member_t *m = c->m;
     if (c->status == 0) return;
+    if (c->status == RA_ST_LEADER_MSG && c->n_notes > 0) {   /* rides in the aux of the row's last note */
+        c->notes[c->n_notes - 1].aux = (uint16_t)c->status;
+        return;
+    }
     ra_note *n = &c->notes[c->n_notes++];           /* one slot is always reserved */
     n->row = m->row; n->type = RA_NOTE_STATUS; n->slot = m->self_slot; n->aux = (uint16_t)c->status;
     n->a = m->current_term;
@@ -1372,7 +1523,9 @@ int ra_oracle_load_rows(ra_oracle *o, const ra_row_state *rows, size_t n)
             m->peers[p].commit_index_sent = s->peers[p].commit_index_sent;
             m->peers[p].status = s->peers[p].status;
             m->peers[p].voter = s->peers[p].voter;
+            m->peers[p].query_index = 0;
         }
+        m->query_index = 0; m->agreed_index = 0;
         log_t *l = &m->log;
         l->first_index = s->first_index; l->last_index = s->last_index; l->last_term = s->last_term;
         l->lw_idx = s->last_written_index; l->lw_term = s->last_written_term;
@@ -1386,6 +1539,30 @@ int ra_oracle_load_rows(ra_oracle *o, const ra_row_state *rows, size_t n)
                 for (u64 i = s->run_start[r]; i <= end; i++) l->terms[i - l->store_base] = s->run_term[r];
             }
         }
+    }
+    return RA_OK;
+}
+
+int ra_oracle_load_query_state(ra_oracle *o, const ra_query_state *q, size_t n)
+{
+    if (!o || (!q && n)) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) if (q[i].row >= o->n_rows) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) {
+        member_t *m = &o->m[q[i].row];
+        m->query_index = q[i].query_index; m->agreed_index = q[i].agreed_index;
+        for (u32 p = 0; p < RA_MAX_MEMBERS; p++) m->peers[p].query_index = q[i].peer_query_index[p];
+    }
+    return RA_OK;
+}
+
+int ra_oracle_read_query_state(ra_oracle *o, ra_query_state *q, size_t n)
+{
+    if (!o || (!q && n)) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) if (q[i].row >= o->n_rows) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) {
+        const member_t *m = &o->m[q[i].row];
+        q[i]._pad = 0; q[i].query_index = m->query_index; q[i].agreed_index = m->agreed_index;
+        for (u32 p = 0; p < RA_MAX_MEMBERS; p++) q[i].peer_query_index[p] = p < m->n_members ? m->peers[p].query_index : 0;
     }
     return RA_OK;
 }
@@ -1644,12 +1821,39 @@ int ra_oracle_flood(ra_oracle *o, uint32_t n_steps, uint32_t cmds_per_step,
         o->cnt.msgs_dropped += args[i].cnt.msgs_dropped;
         o->cnt.elections_won += args[i].cnt.elections_won;
         o->cnt.fatal_rows += args[i].cnt.fatal_rows;
+        o->cnt.aer_received_follower += args[i].cnt.aer_received_follower;
+        o->cnt.aer_received_follower_empty += args[i].cnt.aer_received_follower_empty;
+        o->cnt.aer_replies_success += args[i].cnt.aer_replies_success;
+        o->cnt.aer_replies_failed += args[i].cnt.aer_replies_failed;
+        o->cnt.elections += args[i].cnt.elections;
+        o->cnt.pre_vote_elections += args[i].cnt.pre_vote_elections;
+        o->cnt.term_and_voted_for_updates += args[i].cnt.term_and_voted_for_updates;
     }
     o->cur ^= (int)(n_steps & 1);
     o->step_no += n_steps;
     o->cnt.steps += n_steps;
     free(args); free(th);
     return RA_OK;
+}
+
+/* ra_engine_step_host: the same step for a batch of 32-byte host-origin events */
+int ra_oracle_step_host(ra_oracle *o, const ra_host_event *ev, size_t n_ev,
+                        ra_event *msgs, size_t msgs_cap, size_t *n_msgs,
+                        ra_note *notes, size_t notes_cap, size_t *n_notes)
+{
+    if (!o || (!ev && n_ev)) return RA_E_INVAL;
+    ra_event *w = (ra_event *)calloc(n_ev ? n_ev : 1, sizeof(ra_event));
+    if (!w) return RA_E_NOMEM;
+    for (size_t i = 0; i < n_ev; i++) {
+        const u8 t = ev[i].type;
+        if (!(t == RA_EV_WRITTEN || t == RA_EV_COMMAND || t == RA_EV_ELECTION_TIMEOUT || t == RA_EV_AWAIT_COND_TIMEOUT ||
+              t == RA_EV_PIPELINE_RPCS || t == RA_EV_TICK || t == RA_EV_CONSISTENT_QUERY)) { free(w); return RA_E_INVAL; }
+        w[i].row = ev[i].row; w[i].type = t; w[i].from_slot = RA_NO_SLOT; w[i].flags = ev[i].flags; w[i].n = ev[i].n;
+        w[i].term = ev[i].term; w[i].a = ev[i].a; w[i].b = ev[i].b;
+    }
+    int rc = ra_oracle_step(o, w, n_ev, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes);
+    free(w);
+    return rc;
 }
 
 int ra_oracle_counters(ra_oracle *o, ra_counters *out)

@@ -22,12 +22,16 @@ void ra_oracle_destroy(ra_oracle* o);
 int  ra_oracle_load_rows(ra_oracle* o, const ra_row_state* rows, size_t n);
 int  ra_oracle_reset_empty(ra_oracle* o);
 int  ra_oracle_read_rows(ra_oracle* o, ra_row_state* rows, size_t n);
+int  ra_oracle_load_query_state(ra_oracle* o, const ra_query_state* q, size_t n);
+int  ra_oracle_read_query_state(ra_oracle* o, ra_query_state* q, size_t n);
 int  ra_oracle_step(ra_oracle* o, const ra_event* ev, size_t n_ev,
                     ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
                     ra_note* notes, size_t notes_cap, size_t* n_notes);
 /* threads > 1: groups are sharded statically over that many pthreads */
 int  ra_oracle_flood(ra_oracle* o, uint32_t n_steps, uint32_t cmds_per_step,
                      uint32_t election_permille, uint64_t seed, uint32_t threads);
+int  ra_oracle_step_host(ra_oracle* o, const ra_host_event* ev, size_t n_ev, ra_event* msgs, size_t msgs_cap,
+                         size_t* n_msgs, ra_note* notes, size_t notes_cap, size_t* n_notes);
 int  ra_oracle_counters(ra_oracle* o, ra_counters* out);
 
 /* in-module KAT of the reference: agreed_commit/1, src/ra_server.erl:3657-3661 */

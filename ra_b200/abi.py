@@ -34,7 +34,7 @@ PEER_NORMAL, PEER_SENDING_SNAPSHOT, PEER_SNAPSHOT_BACKOFF, PEER_SUSPENDED, PEER_
 # enum ra_event_type
 (EV_NONE, EV_AER, EV_AER_REPLY, EV_REQUEST_VOTE, EV_REQUEST_VOTE_RES, EV_PRE_VOTE,
  EV_PRE_VOTE_RES, EV_WRITTEN, EV_COMMAND, EV_ELECTION_TIMEOUT, EV_AWAIT_COND_TIMEOUT,
- EV_PIPELINE_RPCS, EV_TICK) = range(13)
+ EV_PIPELINE_RPCS, EV_TICK, EV_HEARTBEAT_RPC, EV_HEARTBEAT_REPLY, EV_CONSISTENT_QUERY) = range(16)
 
 EVF_NOOP = 0x01
 EVF_NEXT_EVENT = 0x02
@@ -42,7 +42,8 @@ EVF_INFO = 0x08
 
 # enum ra_note_type
 (NOTE_NONE, NOTE_WAL_APPEND, NOTE_TRUNCATE, NOTE_COMMIT, NOTE_APPLY, NOTE_STATUS,
- NOTE_SEND_SNAPSHOT, NOTE_NOT_LEADER) = range(8)
+ NOTE_SEND_SNAPSHOT, NOTE_NOT_LEADER, NOTE_QUERY_INDEX, NOTE_QUERY_AGREED, NOTE_QUERY_APPLY,
+ NOTE_CANCEL_SNAPSHOT_RETRY) = range(12)
 
 ST_TERM_VOTE_CHANGED = 0x0001
 ST_ROLE_CHANGED = 0x0002
@@ -60,6 +61,7 @@ FATAL_WRITE_INTEGRITY = 2
 FATAL_SET_LAST_INDEX_NOT_FOUND = 3
 FATAL_ASSERT = 4
 FATAL_NO_SNAPSHOT = 5
+FATAL_LEADER_SAW_HEARTBEAT_SAME_TERM = 6
 
 RA_OK, RA_E_INVAL, RA_E_NOMEM, RA_E_CUDA, RA_E_UNGROUPED, RA_E_CAPACITY, RA_E_NODEVICE = 0, -1, -2, -3, -4, -5, -6
 
@@ -130,6 +132,24 @@ class RaRowState(C.Structure):
                       for p in list(self.peers)[: self.n_members]))
 
 
+class RaHostEvent(C.Structure):
+    """ra_host_event: 32-byte record for batches of host-origin events (ra_engine_step_host)."""
+    _fields_ = [("row", C.c_uint32), ("type", C.c_uint8), ("flags", C.c_uint8), ("n", C.c_uint16),
+                ("term", C.c_uint64), ("a", C.c_uint64), ("b", C.c_uint64)]
+
+    @classmethod
+    def of(cls, e: "RaEvent") -> "RaHostEvent":
+        return cls(row=e.row, type=e.type, flags=e.flags, n=e.n, term=e.term, a=e.a, b=e.b)
+
+
+class RaQueryState(C.Structure):
+    _fields_ = [("row", C.c_uint32), ("_pad", C.c_uint32), ("query_index", C.c_uint64),
+                ("agreed_index", C.c_uint64), ("peer_query_index", C.c_uint64 * RA_MAX_MEMBERS)]
+
+    def key(self, n_members: int = RA_MAX_MEMBERS) -> Tuple:
+        return (self.row, self.query_index, self.agreed_index, tuple(self.peer_query_index[:n_members]))
+
+
 class RaEngineCfg(C.Structure):
     _fields_ = [("n_groups", C.c_uint32), ("n_members", C.c_uint32),
                 ("max_pipeline_count", C.c_uint32), ("max_aer_batch", C.c_uint32),
@@ -140,13 +160,18 @@ class RaEngineCfg(C.Structure):
 class RaCounters(C.Structure):
     _fields_ = [("events", C.c_uint64), ("commits", C.c_uint64), ("applied", C.c_uint64),
                 ("msgs_out", C.c_uint64), ("msgs_dropped", C.c_uint64),
-                ("elections_won", C.c_uint64), ("fatal_rows", C.c_uint64), ("steps", C.c_uint64)]
+                ("elections_won", C.c_uint64), ("fatal_rows", C.c_uint64), ("steps", C.c_uint64),
+                ("aer_received_follower", C.c_uint64), ("aer_received_follower_empty", C.c_uint64),
+                ("aer_replies_success", C.c_uint64), ("aer_replies_failed", C.c_uint64),
+                ("elections", C.c_uint64), ("pre_vote_elections", C.c_uint64),
+                ("term_and_voted_for_updates", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
 assert C.sizeof(RaEvent) == 64
+assert C.sizeof(RaHostEvent) == 32
 assert C.sizeof(RaNote) == 32
 assert C.sizeof(RaPeerInit) == 32
 
@@ -276,6 +301,43 @@ class Backend:
         self._check(self._fn("read_rows")(self._h, arr, len(ids)), "read_rows")
         return list(arr)
 
+    def step_host(self, events: Sequence[RaEvent]) -> Tuple[List[RaEvent], List[RaNote]]:
+        """step() for a batch of host-origin events, handed over as 32-byte records."""
+        f = self._fn("step_host")
+        f.restype = C.c_int
+        sz = C.c_size_t
+        f.argtypes = [C.c_void_p, C.POINTER(RaHostEvent), sz, C.POINTER(RaEvent), sz, C.POINTER(sz),
+                      C.POINTER(RaNote), sz, C.POINTER(sz)]
+        n = len(events)
+        ev = (RaHostEvent * max(n, 1))(*[RaHostEvent.of(e) for e in events])
+        msgs_cap = max(64, n * RA_MSG_CAP)
+        notes_cap = max(64, n * RA_NOTE_CAP + 64)
+        if self.cfg.route_on_device and not self.cfg.pure:
+            msgs_cap, notes_cap = 1024, max(64, self.n_rows * RA_NOTE_CAP)
+        msgs = (RaEvent * msgs_cap)()
+        notes = (RaNote * notes_cap)()
+        nm, nn = sz(0), sz(0)
+        self._check(f(self._h, ev, n, msgs, msgs_cap, C.byref(nm), notes, notes_cap, C.byref(nn)), "step_host")
+        return list(msgs[: nm.value]), list(notes[: nn.value])
+
+    def load_query_state(self, qs: Sequence[RaQueryState]) -> None:
+        f = self._fn("load_query_state")
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.POINTER(RaQueryState), C.c_size_t]
+        arr = (RaQueryState * max(len(qs), 1))(*qs)
+        self._check(f(self._h, arr, len(qs)), "load_query_state")
+
+    def read_query_state(self, row_ids: Iterable[int]) -> List[RaQueryState]:
+        f = self._fn("read_query_state")
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.POINTER(RaQueryState), C.c_size_t]
+        ids = list(row_ids)
+        arr = (RaQueryState * max(len(ids), 1))()
+        for i, r in enumerate(ids):
+            arr[i].row = r
+        self._check(f(self._h, arr, len(ids)), "read_query_state")
+        return list(arr)[: len(ids)]
+
     def step(self, events: Sequence[RaEvent], msgs_cap: int | None = None,
              notes_cap: int | None = None) -> Tuple[List[RaEvent], List[RaNote]]:
         n = len(events)
@@ -348,6 +410,18 @@ def ev_pre_vote_result(row, term, token, granted, voter=RA_NO_SLOT):
 def ev_written(row, term, first, last):
     """{ra_log_event, {written, Term, [{First, Last}]}}."""
     return RaEvent(row=row, type=EV_WRITTEN, from_slot=RA_NO_SLOT, term=term, a=first, b=last)
+
+
+def ev_heartbeat_rpc(row, leader, term, query_index):
+    return RaEvent(row=row, type=EV_HEARTBEAT_RPC, from_slot=leader, term=term, a=query_index)
+
+
+def ev_heartbeat_reply(row, peer, term, query_index):
+    return RaEvent(row=row, type=EV_HEARTBEAT_REPLY, from_slot=peer, term=term, a=query_index)
+
+
+def ev_consistent_query(row):
+    return RaEvent(row=row, type=EV_CONSISTENT_QUERY, from_slot=RA_NO_SLOT)
 
 
 def ev_command(row, n=1, noop=False):

@@ -28,8 +28,18 @@
 #define MINB 5                              // CTAs per SM the register allocation is held to: 20 warps,
                                             // <= 96 registers (no spills), 5 x 39 KB of shared memory
 #endif
+#ifdef RA_RING_1K
+#ifndef NSLOT
+#define NSLOT 6                             // RA_RING_1K: 1 KB ring slots per warp (experimental, see NOTES_r2_prep.md)
+#endif
+#endif
 #define TILE_BYTES (RT * 64)
+#define RA_BAR_WORDS 64                       // barrier flag words behind mbox_cnt[b] (one per source shard)
 #define WARPS (CTA_T / 32)
+// Cols::counters: [0..7] ra_counters' aggregate fields, [8..135] stall histogram (role x type),
+// [136..142] the reference's per-path counters in the order of Member::c_ref (CR_*)
+#define RA_N_COUNTERS (8 + 8 * 16 + 8)
+#define RA_CNT_REF 136
 
 // ---- TMA (cp.async.bulk) + mbarrier, sm_90+/sm_100a --------------------------------------
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -69,10 +79,18 @@ __device__ __forceinline__ void tma_load_tile(void* dst_smem, const void* src_gm
 //   peers[3][8][128] x 8 B           per-thread peer columns (next, match, commit_index_sent), lazy
 template <int MM>
 struct StepSmem {
+#ifdef RA_RING_1K
+    ulonglong2 stage[WARPS][NSLOT][2 * RT];  // 1 KB slots: a tile's heads in one slot, its tails (if any) in the next
+#else
     ulonglong2 stage[WARPS][NST][4 * RT];
+#endif
     ulonglong2 peers_nm[PSTR * CTA_T];       // [s][thread] {next_index, match_index}
     u64 peers_cs[PSTR * CTA_T];              // [s][thread] commit_index_sent (directly behind peers_nm)
+#ifdef RA_RING_1K
+    u64 bars[WARPS][NSLOT];
+#else
     u64 bars[WARPS][NST];
+#endif
 };
 
 // ---- the two kernels of a step ---------------------------------------------------------------
@@ -114,6 +132,26 @@ __device__ __forceinline__ u32 mask_or_warp(u32 m) { return __reduce_or_sync(0xf
 __device__ __forceinline__ u64 mask_or_warp(u64 m)
 { return (u64)__reduce_or_sync(0xffffffffu, (u32)m) | ((u64)__reduce_or_sync(0xffffffffu, (u32)(m >> 32)) << 32); }
 
+// the reference's counters: 7 byte-wide fields per row -> two 16-bit-field words per reduction
+// (32 lanes x 255 < 65536), one atomic per warp and counter that moved
+__device__ __forceinline__ void flush_ref_counters(const Cols& C, u32 lane, u64 c_ref)
+{
+    if (!__any_sync(0xffffffffu, c_ref != 0)) return;
+    u32 w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const u32 lo = (u32)(c_ref >> (16 * k)) & 0xffu, hi = (u32)(c_ref >> (16 * k + 8)) & 0xffu;
+        w[k] = __reduce_add_sync(0xffffffffu, lo | (hi << 16));
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (w[k] & 0xffffu) atomicAdd(&C.counters[RA_CNT_REF + 2 * k], (u64)(w[k] & 0xffffu));
+            if (2 * k + 1 < 7 && (w[k] >> 16)) atomicAdd(&C.counters[RA_CNT_REF + 2 * k + 1], (u64)(w[k] >> 16));
+        }
+    }
+}
+
 template <int MM>
 __global__ void __launch_bounds__(CTA_T, MINB)
 raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F,
@@ -126,6 +164,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     const u32 r = wtile * RT + lane;
     const bool valid = r < C.rows;
     u32 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
+    u64 k_ref = 0;
     if (blockIdx.x == 0 && tid == 0) *stall_count_next = 0;    // the list of the step after this one
 
     // ---- what does this row have to do? ---------------------------------------------------
@@ -163,7 +202,11 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     if (!__any_sync(0xffffffffu, work)) return;                 // whole warp idle
     u64* bars = &S.bars[warp][0];
     if (lane == 0) {
+#ifdef RA_RING_1K
+        for (int i = 0; i < NSLOT; i++) mbar_init(&bars[i], 1);
+#else
         for (int i = 0; i < NST; i++) mbar_init(&bars[i], 1);
+#endif
         mbar_fence_init();
     }
     __syncwarp();
@@ -183,6 +226,58 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     if (work && !fatal0 && pending) {                           // pipeline_rpcs is not a fast path
         stalled = true; stall_flags = STALL_PENDING; rem = mine;
     }
+#ifdef RA_RING_1K
+    // ---- experimental ring of NSLOT 1 KB slots: a tile takes one slot (heads) or two (heads, tails) ----
+    mask_t toissue = todo;
+    u32 si = 0, hd = 0, nfree = NSLOT, par = 0;                 // issue / consume positions, free slots, phase bits
+    const size_t plane_words = (size_t)C.tiles * (4 * RT);
+    const ulonglong2* const mb_base = C.mbox[cur] + (size_t)wtile * (4 * RT);
+    const ulonglong2* const lc_base = C.loc + (size_t)wtile * (4 * RT) - (size_t)NPM * plane_words;
+#pragma unroll 1
+    while (todo) {
+        if (lane == 0) {
+#pragma unroll 1
+            while (toissue) {
+                const u32 q = mask_ffs(toissue);
+                const u32 tbit = q < NPM ? q / RA_MBOX_DEPTH : 8u + q - NPM;
+                const u32 need = 1u + ((w_tail >> tbit) & 1u);
+                if (nfree < need) break;
+                toissue &= toissue - 1;
+                const ulonglong2* src = (q < NPM ? mb_base : lc_base) + (size_t)q * plane_words;
+                fence_proxy_async();                            // the slots were read through the generic proxy
+                mbar_expect_tx(&bars[si], need * (TILE_BYTES / 2));
+                tma_load_tile(&S.stage[warp][si][0], src, TILE_BYTES / 2, &bars[si]);
+                const u32 s2 = si + 1 == NSLOT ? 0 : si + 1;
+                if (need == 2) tma_load_tile(&S.stage[warp][s2][0], src + 2 * RT, TILE_BYTES / 2, &bars[si]);
+                si = need == 2 ? (s2 + 1 == NSLOT ? 0 : s2 + 1) : s2;
+                nfree -= need;
+            }
+        }
+        const u32 p = mask_ffs(todo); todo &= todo - 1;
+        const u32 pbit = p < NPM ? p / RA_MBOX_DEPTH : 8u + p - NPM;
+        const u32 need = 1u + ((w_tail >> pbit) & 1u);
+        const u32 h2 = hd + 1 == NSLOT ? 0 : hd + 1;
+        const bool my = !stalled && ((mine >> p) & 1u);
+        mbar_wait(&bars[hd], (par >> hd) & 1u);
+        if (my) {
+            const ulonglong2* sp = &S.stage[warp][hd][0];
+            const ulonglong2 c0 = sp[lane], c1 = sp[RT + lane];
+            ulonglong2 t2 = make_ulonglong2(0, 0), t3 = t2;
+            if (rec_has_tail(c0)) { const ulonglong2* tp = &S.stage[warp][h2][0]; t2 = tp[lane]; t3 = tp[RT + lane]; }
+            const Rec e = rec_decode(c0, c1, t2, t3, r);
+            if (MT_FATAL(m.meta)) m.c_pack += 1u;
+            else if (C.pure || !fast_event<MM>(m, e)) {
+                stalled = true;
+                rem = mine & ~(((mask_t)1 << p) - 1);
+                atomicAdd(&C.counters[8 + (m_role(m) & 7u) * 16 + (R_type(e) & 15u)], 1ull);
+            }
+        }
+        par ^= 1u << hd;                                        // this slot's barrier completed one more phase
+        hd = need == 2 ? (h2 + 1 == NSLOT ? 0 : h2 + 1) : h2;
+        nfree += need;                                          // (only lane 0 uses it)
+        __syncwarp();                                           // every lane is done with the slot(s)
+    }
+#else
     mask_t toissue = todo;                                      // planes still to request
     u32 n_issued = 0, n_done = 0, st_issue = 0, st = 0, par = 0; // ring positions = counters mod NST, phase parity
     const size_t plane_words = (size_t)C.tiles * (4 * RT);      // 16-byte words per plane
@@ -223,6 +318,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         if (++st == NST) { st = 0; par ^= 1u; }
         __syncwarp();                                           // every lane is done with the slot
     }
+#endif
     const u32 rem_mbox = (u32)(rem & (((mask_t)1 << (NPM - 1) << 1) - 1)), rem_loc = (u32)(rem >> (NPM - 1) >> 1);
 
     if (work) {
@@ -234,6 +330,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         member_writeback(m, C, r);
         k_events = m.c_pack & 0xffu; k_commits = m.c_commits; k_applied = m.c_applied;
         k_msgs = (m.c_pack >> 8) & 0xffu; k_dropped = m.c_pack >> 20; k_elect = (m.c_pack >> 16) & 15u;
+        k_ref = m.c_ref;
     }
     // stalled rows: hand the rest of the step to raft_general_kernel
     const u32 sm = __ballot_sync(0xffffffffu, stalled);
@@ -251,6 +348,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         }
     }
     flush_counters(C, lane, k_events, k_commits, k_applied, k_msgs, k_dropped, k_elect, k_fatal);
+    flush_ref_counters(C, lane, k_ref);
 }
 
 // general path for the stalled rows of this step (one thread per list entry)
@@ -265,6 +363,7 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
     for (u32 base = blockIdx.x * CTA_T; base < n; base += gridDim.x * CTA_T) {
         const u32 i = base + tid;
         u32 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
+        u64 k_ref = 0;
         if (i < n) {
             const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&stall_list[i]);
             const ulonglong2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
@@ -301,8 +400,10 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
             member_writeback(m, C, r);
             k_events = m.c_pack & 0xffu; k_commits = m.c_commits; k_applied = m.c_applied;
             k_msgs = (m.c_pack >> 8) & 0xffu; k_dropped = m.c_pack >> 20; k_elect = (m.c_pack >> 16) & 15u;
+            k_ref = m.c_ref;
         }
         flush_counters(C, lane, k_events, k_commits, k_applied, k_msgs, k_dropped, k_elect, k_fatal);
+        flush_ref_counters(C, lane, k_ref);
     }
 }
 
@@ -330,6 +431,17 @@ __global__ void read_rows_kernel(const Cols C, ra_row_state* out, u32 n)
     read_row(C, out[i]);
 }
 
+__global__ void load_query_kernel(const Cols C, const ra_query_state* in, u32 n)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) load_query_row(C, in[i]);
+}
+__global__ void read_query_kernel(const Cols C, ra_query_state* out, u32 n)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) read_query_row(C, out[i]);
+}
+
 // flat host batch -> per-row local slots.  err[0]: 1 = ungrouped, 2 = too many for a row, 3 = bad row
 __global__ void ingest_kernel(const Cols C, const ra_event* ev, u32 n, u32* err)
 {
@@ -346,6 +458,33 @@ __global__ void ingest_kernel(const Cols C, const ra_event* ev, u32 n, u32* err)
     for (u32 k = 0; k < len; k++)
         if (st_rec_plane(C.loc, C.tiles, k, row, ld_rec(&ev[i + k]))) tails |= 0x100u << k;
     if (tails) atomicOr(&C.loc_n[row], tails);
+}
+
+// the same for a batch of 32-byte host events: every record is a head (RS_PLAIN); err 3 also for an RPC type
+__device__ __forceinline__ bool host_event_type_ok(u32 t)
+{
+    return t == RA_EV_WRITTEN || t == RA_EV_COMMAND || t == RA_EV_ELECTION_TIMEOUT || t == RA_EV_AWAIT_COND_TIMEOUT ||
+           t == RA_EV_PIPELINE_RPCS || t == RA_EV_TICK || t == RA_EV_CONSISTENT_QUERY;
+}
+__global__ void ingest_host_kernel(const Cols C, const ra_host_event* ev, u32 n, u32* err)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 row = ev[i].row;
+    if (row >= C.rows || !host_event_type_ok(ev[i].type)) { atomicMax(err, 3u); return; }
+    if (i > 0 && ev[i - 1].row == row) return;                 // not the head of its run
+    u32 len = 1;
+    while (i + len < n && ev[i + len].row == row && len <= RA_LOCAL_CAP) len++;
+    if (len > RA_LOCAL_CAP) { atomicMax(err, 2u); return; }
+    if (atomicCAS(&C.loc_n[row], 0u, len) != 0u) { atomicMax(err, 1u); return; }
+    for (u32 k = 0; k < len; k++) {
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(&ev[i + k]);
+        const ulonglong2 h = src[0], t = src[1];               // {row | type<<32 | flags<<40 | n<<48, term}, {a, b}
+        ulonglong2* q = C.loc + rec_word(C.tiles, k, row, 0);
+        const u64 type = (h.x >> 32) & 0xffull, flags = (h.x >> 40) & 0xffull, nn = (h.x >> 48) & 0xffffull;
+        q[0] = make_ulonglong2(type | ((u64)RA_NO_SLOT << 8) | (flags << 16) | ((u64)RS_PLAIN << 24) | (nn << 32), h.y);
+        q[RT] = t;
+    }
 }
 
 // records that other shards sent to members of this engine -> mailbox planes of the next step.
@@ -394,6 +533,28 @@ __global__ void gather_kernel(const Cols C, const u64* offs, ra_event* msgs, u64
         }
 }
 
+// Step barrier of the peer transport without a collective: every shard release-stores the step's
+// epoch into its flag word in every peer's HBM (the words behind mbox_cnt[0], reachable through the
+// IPC mappings of the mailboxes) and acquire-spins until all peers' epochs have arrived in its own.
+// One warp, one lane per peer.  Stream order makes the step kernels' peer stores happen-before the
+// release; the acquire on the other side orders them before that shard's next step.
+__global__ void peer_barrier_kernel(const Cols C, const u64 epoch, u32* err)
+{
+    const u32 k = threadIdx.x;
+    if (k >= C.n_shards) return;
+    u64* mine = C.mbox_cnt[0] + C.rows;                      // [source shard]
+    u64* theirs = C.peer_cnt[0][k] + C.rows;                 // all shards have the same number of rows
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(theirs + C.shard), "l"(epoch) : "memory");
+    u64 v = 0;
+    for (u32 spins = 0; spins < (1u << 24); spins++) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + k) : "memory");
+        if (v >= epoch) return;
+        __nanosleep(64);
+    }
+    atomicExch(err + 1, 1u);                                 // a peer never arrived: reported by the next call
+}
+
 // ------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------
@@ -404,6 +565,7 @@ struct ra_engine {
     cudaEvent_t ev0, ev1;
     int cur;
     u64 step_no, steps;
+    u64 bar_epoch;                            // peer transport: barriers passed since the last reset
     void* allocs[64]; int n_allocs;
     // staging
     ra_event* d_ev; size_t d_ev_cap;
@@ -473,9 +635,11 @@ extern "C" int ra_engine_reset_empty(ra_engine* e)
     CK(cudaSetDevice(e->cfg.device));
     reset_empty_kernel<<<nblocks(e->C.rows, 256), 256, 0, e->stream>>>(e->C);
     CK(cudaGetLastError());
-    CK(cudaMemsetAsync(e->C.counters, 0, (8 + 8 * 16) * sizeof(u64), e->stream));
+    CK(cudaMemsetAsync(e->C.counters, 0, RA_N_COUNTERS * sizeof(u64), e->stream));
     CK(cudaMemsetAsync(e->d_stall_cnt, 0, 4 * sizeof(u32), e->stream));
-    e->cur = 0; e->step_no = 0; e->steps = 0;
+    e->cur = 0; e->step_no = 0; e->steps = 0; e->bar_epoch = 0;
+    if (e->C.routed) CK(cudaMemsetAsync(e->C.mbox_cnt[0] + e->C.rows, 0, RA_BAR_WORDS * sizeof(u64), e->stream));
+    CK(cudaMemsetAsync(e->d_err, 0, 4 * sizeof(u32), e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return RA_OK;
 }
@@ -512,12 +676,15 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
 #define DA(p, n) if ((rc = dalloc(e, &(p), (n))) != RA_OK) goto bad
         DA(C.tc, R); DA(C.lg, R); DA(C.lw, R); DA(C.ap, R); DA(C.sn, R); DA(C.tk, R); DA(C.fm, R);
         DA(C.cd, 2 * R); DA(C.pnm, M * R); DA(C.pcs, M * R); DA(C.run, RA_MAX_RUNS * R); DA(C.lrs, R);
+        DA(C.qi, R); DA(C.qa, R); DA(C.pqi, M * R);
         C.tiles = (u32)((R + RT - 1) / RT);
         const size_t PW = (size_t)C.tiles * 4 * RT;             // 16-byte words per tiled plane
         DA(C.loc, (size_t)RA_LOCAL_CAP * PW); DA(C.loc_n, R);
-        DA(C.onote, (size_t)RA_NOTE_CAP * R); DA(C.out_n, R); DA(C.counters, 8 + 8 * 16);
+        DA(C.onote, (size_t)RA_NOTE_CAP * R); DA(C.out_n, R); DA(C.counters, RA_N_COUNTERS);
         if (C.routed) {
-            for (int b = 0; b < 2; b++) { DA(C.mbox[b], M * RA_MBOX_DEPTH * PW); DA(C.mbox_cnt[b], R); }
+            // + RA_BAR_WORDS: the peer transport's step barrier flags live behind the counts of buffer 0,
+            // so they are covered by the IPC mapping the peers already have
+            for (int b = 0; b < 2; b++) { DA(C.mbox[b], M * RA_MBOX_DEPTH * PW); DA(C.mbox_cnt[b], R + RA_BAR_WORDS); }
             DA(C.omsg, (size_t)RA_MSG_CAP * (C.pure ? R : 1));
         } else {
             C.mbox[0] = C.mbox[1] = nullptr; C.mbox_cnt[0] = C.mbox_cnt[1] = nullptr;
@@ -591,6 +758,32 @@ extern "C" int ra_engine_read_rows(ra_engine* e, ra_row_state* rows, size_t n)
     return RA_OK;
 }
 
+static int query_io(ra_engine* e, ra_query_state* q, size_t n, bool load)
+{
+    if (!e || (!q && n)) return RA_E_INVAL;
+    if (n == 0) return RA_OK;
+    for (size_t i = 0; i < n; i++) if (q[i].row >= e->C.rows) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    ra_query_state* d = nullptr;
+    CK(cudaMalloc(&d, n * sizeof(ra_query_state)));
+    cudaError_t ce = cudaMemcpyAsync(d, q, n * sizeof(ra_query_state), cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess) {
+        if (load) load_query_kernel<<<nblocks(n, 128), 128, 0, e->stream>>>(e->C, d, (u32)n);
+        else {
+            read_query_kernel<<<nblocks(n, 128), 128, 0, e->stream>>>(e->C, d, (u32)n);
+            ce = cudaMemcpyAsync(q, d, n * sizeof(ra_query_state), cudaMemcpyDeviceToHost, e->stream);
+        }
+    }
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    cudaFree(d);
+    return ce == cudaSuccess ? RA_OK : fail(e, ce, "query state");
+}
+extern "C" int ra_engine_load_query_state(ra_engine* e, const ra_query_state* q, size_t n)
+{ return query_io(e, const_cast<ra_query_state*>(q), n, true); }
+extern "C" int ra_engine_read_query_state(ra_engine* e, ra_query_state* q, size_t n)
+{ return query_io(e, q, n, false); }
+
 static int launch_step(ra_engine* e, const FloodArgs& F)
 {
     if (e->C.n_shards > 1) {
@@ -627,9 +820,9 @@ static int launch_step(ra_engine* e, const FloodArgs& F)
     return RA_OK;
 }
 
-extern "C" int ra_engine_step(ra_engine* e, const ra_event* ev, size_t n_ev,
-                              ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
-                              ra_note* notes, size_t notes_cap, size_t* n_notes)
+static int step_impl(ra_engine* e, const void* ev, size_t n_ev, bool host32,
+                     ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                     ra_note* notes, size_t notes_cap, size_t* n_notes)
 {
     if (!e || (!ev && n_ev) || n_ev > 0x7fffffffull) return RA_E_INVAL;
     CK(cudaSetDevice(e->cfg.device));
@@ -637,14 +830,17 @@ extern "C" int ra_engine_step(ra_engine* e, const ra_event* ev, size_t n_ev,
     int rc;
     // a step() after flood() must not see the flood host model's queued locals
     if (n_ev) {
-        if ((rc = ensure(e, &e->d_ev, &e->d_ev_cap, n_ev))) return rc;
-        CK(cudaMemcpyAsync(e->d_ev, ev, n_ev * sizeof(ra_event), cudaMemcpyHostToDevice, e->stream));
+        if ((rc = ensure(e, &e->d_ev, &e->d_ev_cap, n_ev))) return rc;          // (sized for 64-byte records)
+        CK(cudaMemcpyAsync(e->d_ev, ev, n_ev * (host32 ? sizeof(ra_host_event) : sizeof(ra_event)),
+                           cudaMemcpyHostToDevice, e->stream));
     }
     u32 h_err = 0;
     clear_loc_kernel<<<nblocks(R, 256), 256, 0, e->stream>>>(e->C);
     CK(cudaMemsetAsync(e->d_err, 0, sizeof(u32), e->stream));
     if (n_ev) {
-        ingest_kernel<<<nblocks(n_ev, 256), 256, 0, e->stream>>>(e->C, e->d_ev, (u32)n_ev, e->d_err);
+        if (host32) ingest_host_kernel<<<nblocks(n_ev, 256), 256, 0, e->stream>>>(
+                        e->C, reinterpret_cast<const ra_host_event*>(e->d_ev), (u32)n_ev, e->d_err);
+        else ingest_kernel<<<nblocks(n_ev, 256), 256, 0, e->stream>>>(e->C, e->d_ev, (u32)n_ev, e->d_err);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&h_err, e->d_err, sizeof(u32), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
@@ -676,6 +872,16 @@ extern "C" int ra_engine_step(ra_engine* e, const ra_event* ev, size_t n_ev,
     if (n_notes) *n_notes = tn;
     return RA_OK;
 }
+
+extern "C" int ra_engine_step(ra_engine* e, const ra_event* ev, size_t n_ev,
+                              ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                              ra_note* notes, size_t notes_cap, size_t* n_notes)
+{ return step_impl(e, ev, n_ev, false, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes); }
+
+extern "C" int ra_engine_step_host(ra_engine* e, const ra_host_event* ev, size_t n_ev,
+                                   ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                                   ra_note* notes, size_t notes_cap, size_t* n_notes)
+{ return step_impl(e, ev, n_ev, true, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes); }
 
 extern "C" int ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per_step,
                                uint32_t election_permille, uint64_t seed)
@@ -752,6 +958,16 @@ extern "C" int ra_engine_peer_set(ra_engine* e, uint32_t shard, const ra_peer_pt
     return RA_OK;
 }
 
+extern "C" int ra_engine_peer_barrier(ra_engine* e)
+{
+    if (!e || !e->C.peer_mode) return RA_E_INVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    e->bar_epoch++;
+    peer_barrier_kernel<<<1, 32, 0, e->stream>>>(e->C, e->bar_epoch, e->d_err);
+    CK(cudaGetLastError());
+    return RA_OK;
+}
+
 extern "C" int ra_engine_ipc_export(ra_engine* e, ra_ipc_handles* out)
 {
     if (!e || !out || !e->C.routed) return RA_E_INVAL;
@@ -790,6 +1006,12 @@ extern "C" int ra_engine_sync(ra_engine* e)
     if (!e) return RA_E_INVAL;
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaStreamSynchronize(e->stream));
+    if (e->bar_epoch) {                                       // did a peer barrier give up waiting?
+        u32 h = 0;
+        CK(cudaMemcpyAsync(&h, e->d_err + 1, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (h) { snprintf(e->err, sizeof e->err, "peer barrier timed out (epoch %llu)", (unsigned long long)e->bar_epoch); return RA_E_CUDA; }
+    }
     return RA_OK;
 }
 
@@ -809,9 +1031,13 @@ extern "C" int ra_engine_counters(ra_engine* e, ra_counters* out)
 {
     if (!e || !out) return RA_E_INVAL;
     CK(cudaSetDevice(e->cfg.device));
-    u64 h[8];
+    u64 h[RA_N_COUNTERS];
     CK(cudaMemcpyAsync(h, e->C.counters, sizeof h, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    out->aer_received_follower = h[RA_CNT_REF + 0]; out->aer_received_follower_empty = h[RA_CNT_REF + 1];
+    out->aer_replies_success = h[RA_CNT_REF + 2]; out->aer_replies_failed = h[RA_CNT_REF + 3];
+    out->elections = h[RA_CNT_REF + 4]; out->pre_vote_elections = h[RA_CNT_REF + 5];
+    out->term_and_voted_for_updates = h[RA_CNT_REF + 6];
     out->events = h[0]; out->commits = h[1]; out->applied = h[2]; out->msgs_out = h[3];
     out->msgs_dropped = h[4]; out->elections_won = h[5]; out->fatal_rows = h[6]; out->steps = e->steps;
     return RA_OK;

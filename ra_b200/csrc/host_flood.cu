@@ -33,10 +33,10 @@ struct ra_hostsim {
     u32 groups, members, rows;
     std::vector<unsigned char> role, idle;
     u32 threads;
-    std::vector<std::vector<ra_event>> tmp;
+    std::vector<std::vector<ra_host_event>> tmp;
     std::vector<size_t> cnt, off;
     double t_model, t_step;          // seconds spent in the host model / inside ra_engine_step
-    ra_event* ev;  size_t ev_cap;     // pinned
+    ra_host_event* ev;  size_t ev_cap; // pinned; the flood only has host-origin events: 32-byte records
     ra_event* msgs; size_t msgs_cap;  // pinned
     ra_note* notes; size_t notes_cap; // pinned
     size_t n_ev;
@@ -75,7 +75,7 @@ extern "C" int ra_hostsim_create(ra_engine* e, ra_hostsim** out)
         s->cnt.assign(s->threads, 0); s->off.assign(s->threads + 1, 0);
     }
     s->ev_cap = (size_t)s->rows * RA_LOCAL_CAP; s->msgs_cap = 1024; s->notes_cap = (size_t)s->rows * RA_NOTE_CAP;
-    s->ev = (ra_event*)ra_engine_alloc_host(s->ev_cap * sizeof(ra_event));
+    s->ev = (ra_host_event*)ra_engine_alloc_host(s->ev_cap * sizeof(ra_host_event));
     s->msgs = (ra_event*)ra_engine_alloc_host(s->msgs_cap * sizeof(ra_event));
     s->notes = (ra_note*)ra_engine_alloc_host(s->notes_cap * sizeof(ra_note));
     if (!s->ev || !s->msgs || !s->notes) { delete s; return RA_E_NOMEM; }
@@ -91,6 +91,10 @@ extern "C" void ra_hostsim_destroy(ra_hostsim* s)
     delete s;
 }
 
+static inline void put(ra_host_event* e, u32 row, u32 type, u32 n, u64 term, u64 a, u64 b)
+{
+    e->row = row; e->type = (uint8_t)type; e->flags = 0; e->n = (uint16_t)n; e->term = term; e->a = a; e->b = b;
+}
 static inline void put(ra_event* e, u32 row, u32 type, u32 n, u64 term, u64 a, u64 b)
 {
     memset(e, 0, sizeof *e);
@@ -99,7 +103,7 @@ static inline void put(ra_event* e, u32 row, u32 type, u32 n, u64 term, u64 a, u
 }
 
 // notes of one step -> events of the next (the flood host model), rows [r0, r1)
-static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u32 r0, u32 r1, ra_event* out,
+static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u32 r0, u32 r1, ra_host_event* out,
                           u32 cmds, u32 permille, u64 seed, bool run_model)
 {
     // first note of row r0 (notes are ordered by row)
@@ -109,8 +113,10 @@ static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u
     for (u32 row = r0; row < r1; row++) {
         const ra_note* w0 = nullptr; const ra_note* w1 = nullptr;
         u32 status = 0; bool fatal = false;
+        const ra_note* last = nullptr;
         for (; i < n_notes && notes[i].row == row; i++) {
             const ra_note& n = notes[i];
+            last = &n;
             if (n.type == RA_NOTE_WAL_APPEND) { w0 = w1; w1 = &n; }
             else if (n.type == RA_NOTE_STATUS) {
                 status = n.aux;
@@ -118,6 +124,7 @@ static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u
                 if (n.aux & RA_ST_FATAL) fatal = true;
             }
         }
+        if (last && last->type != RA_NOTE_STATUS) status |= last->aux;   // flags riding in the last note
         if (!run_model || fatal) continue;
         if (w0) put(&out[ne++], row, RA_EV_WRITTEN, 0, w0->c, w0->a, w0->b);
         if (w1) put(&out[ne++], row, RA_EV_WRITTEN, 0, w1->c, w1->a, w1->b);
@@ -166,7 +173,7 @@ static void model(ra_hostsim* s, size_t n_notes, u32 cmds, u32 permille, u64 see
             off[0] = 0;
             for (int k = 0; k < T; k++) off[k + 1] = off[k] + cnt[k];
         }
-        if (cnt[t]) memcpy(s->ev + off[t], s->tmp[t].data(), cnt[t] * sizeof(ra_event));
+        if (cnt[t]) memcpy(s->ev + off[t], s->tmp[t].data(), cnt[t] * sizeof(ra_host_event));
     }
     s->n_ev = off[T];
 }
@@ -182,18 +189,18 @@ extern "C" int ra_hostsim_run(ra_hostsim* s, uint32_t n_steps, uint32_t cmds, ui
     int rc;
     if (bootstrap) {
         for (u32 g = 0; g < s->groups; g++) put(&s->ev[g], g, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0);
-        rc = ra_engine_step(s->e, s->ev, s->groups, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
+        rc = ra_engine_step_host(s->e, s->ev, s->groups, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
         if (rc) return rc;
-        s->h2d += (u64)s->groups * sizeof(ra_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
+        s->h2d += (u64)s->groups * sizeof(ra_host_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
         model(s, nn, cmds, permille, seed, false);         // roles only; no model run for this step
         s->n_ev = 0;
     }
     for (u32 t = 0; t < n_steps; t++) {
         auto a0 = std::chrono::steady_clock::now();
-        rc = ra_engine_step(s->e, s->ev, s->n_ev, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
+        rc = ra_engine_step_host(s->e, s->ev, s->n_ev, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
         if (rc) return rc;
         auto a1 = std::chrono::steady_clock::now();
-        s->h2d += (u64)s->n_ev * sizeof(ra_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
+        s->h2d += (u64)s->n_ev * sizeof(ra_host_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
         model(s, nn, cmds, permille, seed, true);
         auto a2 = std::chrono::steady_clock::now();
         s->t_step += std::chrono::duration<double>(a1 - a0).count();
@@ -217,4 +224,31 @@ extern "C" int ra_hostsim_breakdown(ra_hostsim* s, double* step_seconds, double*
     if (!s) return RA_E_INVAL;
     if (step_seconds) *step_seconds = s->t_step; if (model_seconds) *model_seconds = s->t_model;
     return RA_OK;
+}
+
+
+// ---- written-event source: one WAL batch -> one grouped event array (include/ra_engine.h) -----------
+// Within one call a row gets at most max_per_row records and every row's records are adjacent; a writer
+// whose ranges do not fit stops the call there (its remaining ranges must not be reordered behind other
+// rows of a later call, and a second run of the same row in one batch would break the grouping contract).
+extern "C" size_t ra_wal_batch_to_events(const ra_wal_writer* w, size_t n, uint32_t max_per_row,
+                                         ra_event* out, size_t cap, ra_wal_resume* resume)
+{
+    if (!w || !out || !resume || max_per_row == 0 || max_per_row > RA_LOCAL_CAP) return 0;
+    size_t ne = 0;
+    u32 wi = resume->writer, ri = resume->range;
+    u32 run_row = 0xFFFFFFFFu, taken = 0;           // records of the current run of one row (a writer that
+    while (wi < n) {                                // changed term mid-batch is notified twice, back to back)
+        const ra_wal_writer& x = w[wi];
+        if (x.row != run_row) { run_row = x.row; taken = 0; }
+        while (ri < x.n_ranges && taken < max_per_row && ne < cap) {
+            put(&out[ne++], x.row, RA_EV_WRITTEN, 0, x.term, x.ranges[2 * ri], x.ranges[2 * ri + 1]);
+            ri++; taken++;
+        }
+        if (ri < x.n_ranges) break;                 // out of room for this row (or for the batch): resume here
+        wi++; ri = 0;
+        if (ne >= cap) break;
+    }
+    resume->writer = wi; resume->range = ri;
+    return ne;
 }

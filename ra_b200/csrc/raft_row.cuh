@@ -29,7 +29,7 @@ __device__ __forceinline__ void member_init(Member& m, const Cols& C, u32 r, ulo
     m.lrs = lrs; m.lrs_ok = MT_NRUNS(ap.y) ? 1u : 0u;
     m.n_msgs = 0; m.n_notes = 0; m.status = MT_ROLE(ap.y) << 16; m.wk = 0;
     m.sent_to = 0; m.pn_type = RA_NOTE_NONE; m.pn_slot = 0; m.pn_a = m.pn_b = m.pn_c = 0;
-    m.c_pack = 0; m.c_commits = m.c_applied = 0;
+    m.c_pack = 0; m.c_ref = 0; m.c_commits = m.c_applied = 0;
     m.nb = cur ^ 1;
     m.sp = sp; m.pstate = 0; m.pipe_clean = 0;
 }
@@ -66,8 +66,12 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
             reinterpret_cast<u8*>(&cnt[(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
         }
     }
-    note_flush(m);
-    if (m.status & 0xffffu) {
+    // record_leader_msg alone (the steady state of a follower) does not get a STATUS note of its own: the
+    // flags ride in the aux field of the row's last note of the step (include/ra_engine.h, RA_NOTE_STATUS)
+    const u32 st16 = m.status & 0xffffu;
+    const bool elide = st16 == RA_ST_LEADER_MSG && m.pn_type != RA_NOTE_NONE;
+    note_flush(m, elide ? st16 : 0u);
+    if (st16 && !elide) {
         u64 ld = MT_LEADER(m.meta), vf = MT_VOTED(m.meta);
         u64 b = (vf == SLOT_NONE ? 0xFFull : vf) | ((ld == SLOT_NONE ? 0xFFull : ld) << 8) |
                 ((u64)((m.status >> 16) & 7u) << 16) | ((u64)MT_ROLE(m.meta) << 24);
@@ -135,6 +139,8 @@ __device__ __forceinline__ void reset_row(const Cols& C, const u32 r)
     for (u32 s = 0; s < C.members; s++) { st2(&C.pnm[(size_t)s * C.rows + r], 1, 0); C.pcs[(size_t)s * C.rows + r] = 0; }
     for (u32 k = 0; k < RA_MAX_RUNS; k++) st2(&C.run[(size_t)k * C.rows + r], 0, 0);
     C.lrs[r] = 0;
+    C.qi[r] = 0; C.qa[r] = 0;
+    for (u32 s = 0; s < C.members; s++) C.pqi[(size_t)s * C.rows + r] = 0;
     C.loc_n[r] = 0; C.out_n[r] = 0;
     if (C.routed) { C.mbox_cnt[0][r] = 0; C.mbox_cnt[1][r] = 0; }
 }
@@ -174,6 +180,8 @@ __device__ __forceinline__ void load_row(const Cols& C, const ra_row_state& s)
     for (u32 k = 0; k < RA_MAX_RUNS; k++)
         st2(&C.run[(size_t)k * C.rows + r], k < s.n_runs ? s.run_start[k] : 0, k < s.n_runs ? s.run_term[k] : 0);
     C.lrs[r] = s.n_runs ? s.run_start[s.n_runs - 1] : 0;
+    C.qi[r] = 0; C.qa[r] = 0;
+    for (u32 p = 0; p < C.members; p++) C.pqi[(size_t)p * C.rows + r] = 0;
     C.loc_n[r] = 0;
 }
 
@@ -231,4 +239,18 @@ __device__ __forceinline__ void deliver_record(const Cols& C, const int buf, con
         if (seen == old) break;
         old = seen;
     }
+}
+
+// ---- consistent-query state of a row <-> ra_query_state ----------------------------------------
+__device__ __forceinline__ void load_query_row(const Cols& C, const ra_query_state& q)
+{
+    const u32 r = q.row;
+    C.qi[r] = q.query_index; C.qa[r] = q.agreed_index;
+    for (u32 p = 0; p < C.members; p++) C.pqi[(size_t)p * C.rows + r] = q.peer_query_index[p];
+}
+__device__ __forceinline__ void read_query_row(const Cols& C, ra_query_state& q)
+{
+    const u32 r = q.row;
+    q._pad = 0; q.query_index = C.qi[r]; q.agreed_index = C.qa[r];
+    for (u32 p = 0; p < RA_MAX_MEMBERS; p++) q.peer_query_index[p] = p < C.members ? C.pqi[(size_t)p * C.rows + r] : 0;
 }

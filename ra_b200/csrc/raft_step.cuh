@@ -83,6 +83,11 @@ struct Cols {
     u64*        pcs;    // commit_index_sent
     // log view: [k][rows] {run_start, run_term}
     ulonglong2* run;
+    // consistent queries: own query_index, highest index the host was told a quorum agreed on, and per
+    // peer slot s: [s][rows] the peer's query_index (ra_server_state() :96, ra_peer_state() ra.hrl:63-75)
+    u64*        qi;
+    u64*        qa;
+    u64*        pqi;
     u64*        lrs;    // [rows] start index of the LAST run (copy of run[n_runs-1].x; 0 when the log is
                         // empty): lets the step kernel load it together with the other pairs
     // transport / io.  Input record planes (mailboxes, locals) are TILED: plane p holds, for
@@ -262,6 +267,7 @@ struct Member {
     // flood host model: the last two finalised WAL_APPEND notes
     // counters
     u32 c_pack;                 // events | msgs << 8 | elections << 16 | dropped << 20
+    u64 c_ref;                  // the reference's counters of this path, 8 bits each (CR_*)
     u32 c_commits, c_applied;   // per row and step: far below 2^32
     int nb;                     // mailbox buffer written this step
     // per-peer columns staged in shared memory on first use: sp[(f*8 + s) * CTA_T], f = 0 next,
@@ -295,6 +301,15 @@ __device__ __forceinline__ void tok_set(const Member& m, u64 token, u64 ctr) { s
 __device__ __forceinline__ u64 first_idx(const Member& m) { return m.C->fm[m.row].x; }
 __device__ __forceinline__ u64 macver(const Member& m)    { return m.C->fm[m.row].y; }
 __device__ __forceinline__ void first_idx_set(const Member& m, u64 v) { m.C->fm[m.row].x = v; }
+// consistent-query indexes: same treatment (cold; read and written in place)
+__device__ __forceinline__ u64& q_index(const Member& m)  { return m.C->qi[m.row]; }
+__device__ __forceinline__ u64& q_agreed(const Member& m) { return m.C->qa[m.row]; }
+__device__ __forceinline__ u64& q_peer(const Member& m, u32 s) { return m.C->pqi[(size_t)s * m.C->rows + m.row]; }
+// reset_query_index/1 :3743-3747 (out of line: reached from the hot kernel only on a term / vote change)
+__device__ __noinline__ void reset_query_indexes(u64* pqi, u32 rows, u32 row, u32 members)
+{
+    for (u32 s = 0; s < members; s++) pqi[(size_t)s * rows + row] = 0;
+}
 
 __device__ __forceinline__ ulonglong2 run_get(const Member& m, u32 k)
 { return m.C->run[(size_t)k * m.C->rows + m.row]; }
@@ -538,10 +553,11 @@ __device__ __noinline__ void put_local(ulonglong2* loc, u32 tiles, u32 k, u32 ro
     q[RT] = make_ulonglong2(a, b);
 }
 
-__device__ __forceinline__ void note_flush(Member& m)
+// `aux`: the row's step flags when this is the last note of the step and no STATUS note follows
+__device__ __forceinline__ void note_flush(Member& m, u32 aux = 0)
 {
     if (m.pn_type == RA_NOTE_NONE) return;
-    note_store(m, m.n_notes - 1, m.pn_type, m.pn_slot, 0, m.pn_a, m.pn_b, m.pn_c);
+    note_store(m, m.n_notes - 1, m.pn_type, m.pn_slot, aux, m.pn_a, m.pn_b, m.pn_c);
     if (m.pn_type == RA_NOTE_WAL_APPEND) {          // the flood host model reads the last two back (row_end_of_step)
         const u32 n = m.wk & 3u;
         m.wk = (n < 2 ? n + 1 : 2u) | ((m.n_notes - 1) << 4) | ((m.wk & 0xf0u) << 4);
@@ -623,10 +639,17 @@ __device__ __forceinline__ void nq_push(NextQ& q, u32 code) { q.codes |= code <<
 
 // ---- term / vote --------------------------------------------------------------------
 
+// shifts of the reference's per-path counters inside Member::c_ref (ra.hrl:324-343)
+enum { CR_AER_RX = 0, CR_AER_RX_EMPTY = 8, CR_REPLY_OK = 16, CR_REPLY_FAIL = 24, CR_ELECTIONS = 32, CR_PRE_VOTE_ELECTIONS = 40,
+       CR_TERM_VOTE = 48 };
+#define CR_INC(m, f) ((m).c_ref += 1ull << (f))
+
 // update_term_and_voted_for/3 :3014-3031
 __device__ __forceinline__ void update_term_and_voted_for(Member& m, u64 term, u32 voted)
 {
     if (term == m.term && voted == MT_VOTED(m.meta)) return;
+    CR_INC(m, CR_TERM_VOTE);                                            // :3026
+    reset_query_indexes(m.C->pqi, m.C->rows, m.row, m.C->members);      // :3029
     m.term = term;
     MT_SET(m.meta, 7, 4, voted);
     m.status |= RA_ST_TERM_VOTE_CHANGED;
@@ -778,6 +801,68 @@ __device__ __forceinline__ u64 make_rpc_effect(Member& m, u32 peer, u64 next, u6
     return snap_idx(m);
 }
 
+// ---- consistent queries: the heartbeat round, :3700-3825 (general path only) ------------------
+// heartbeat_reply/2 :3700-3702, cast to the rpc's leader_id
+template <int MM>
+__device__ __forceinline__ void send_heartbeat_reply(Member& m, u32 to, u64 term, u64 query_index)
+{
+    emit_msg<MM>(m, to, mk_rec(0, RA_EV_HEARTBEAT_REPLY, 0, 0, 0, 0, 0, term, query_index, 0, 0, 0, 0));
+}
+// heartbeat_rpc_effects/4 :3749-3771: normal peers whose query_index lags
+template <int MM>
+__device__ __forceinline__ void heartbeat_rpc_effects(Member& m, u64 query_index)
+{
+    for (u32 s = 0; s < NMEM(*m.C); s++) {
+        if (s == m.slot) continue;
+        if (MT_PSTATUS(m.meta, s) != RA_PEER_NORMAL) continue;
+        if (!(q_peer(m, s) < query_index)) continue;
+        emit_msg<MM>(m, s, mk_rec(0, RA_EV_HEARTBEAT_RPC, 0, 0, 0, 0, 0, m.term, query_index, 0, 0, 0, 0));
+    }
+}
+// get_current_query_quorum/1 :3796-3797 = agreed_commit(query_indexes/1 :3632-3642): own index and the
+// voter peers', same rank select as evaluate_quorum
+template <int MM>
+__device__ __forceinline__ u64 query_quorum(Member& m)
+{
+    const u32 M = NMEM(*m.C);
+    constexpr int NV = MMEM ? MMEM : RA_MAX_MEMBERS;
+    u64 v[NV];
+    u32 n = 1;
+#pragma unroll
+    for (int s = 0; s < NV; s++) {
+        const bool in = (u32)s < M;
+        const bool self = (u32)s == m.slot;
+        const bool voter = in && !self && MT_VOTER(m.meta, s);
+        v[s] = self ? q_index(m) : (voter ? q_peer(m, s) : 0ull);
+        n += voter ? 1u : 0u;
+    }
+#pragma unroll
+    for (int pass = 0; pass < NV; pass++) {
+#pragma unroll
+        for (int i = pass & 1; i + 1 < NV; i += 2) cex(v[i], v[i + 1]);
+    }
+    const u32 nth = n / 2 + 1;
+    u64 best = v[0];
+#pragma unroll
+    for (int i = 1; i < NV; i++) best = (nth == (u32)(i + 1)) ? v[i] : best;
+    return best;
+}
+// what the waiting queries learn: every one with an index <= agreed is applied by the host
+__device__ __forceinline__ void query_agreed(Member& m, u64 agreed)
+{
+    if (agreed > q_agreed(m)) {
+        q_agreed(m) = agreed;
+        note(m, RA_NOTE_QUERY_AGREED, 0, agreed, 0, 0);
+    }
+}
+// update_heartbeat_rpc_effects/1 :3704-3720 (tick, enforce leadership)
+template <int MM>
+__device__ __forceinline__ void update_heartbeat_rpc_effects(Member& m)
+{
+    if (NMEM(*m.C) <= 1) query_agreed(m, q_index(m));         // no peers: apply everything waiting
+    else heartbeat_rpc_effects<MM>(m, q_index(m));
+}
+
 // The leader's three ways of walking its peers share one loop (one inlined copy of
 // make_rpc_effect/5 in the hot kernel):
 //   RP_PIPELINE  make_pipelined_rpc_effects/3 :2268-2329 -> More
@@ -785,16 +870,23 @@ __device__ __forceinline__ u64 make_rpc_effect(Member& m, u32 peer, u64 next, u6
 //   RP_ALL       make_all_rpcs/1 :2337-2350 (enforce leadership)        } not updated
 enum { RP_PIPELINE = 0, RP_STALE = 1, RP_ALL = 2 };
 template <int MM>
-__device__ __forceinline__ bool rpc_pass(Member& m, u32 mode, bool force)
+__device__ __forceinline__ bool rpc_pass(Member& m, u32 mode, bool force, const bool heartbeats = true)
 {
+    // (`heartbeats` = false in the hot kernel: its one RP_ALL call site has made sure that no consistent
+    // query is in flight and that every peer is `normal`, so neither heartbeats nor backoff peers exist)
     const Cols& C = *m.C;
     if (mode == RP_PIPELINE && m.pipe_clean && !force) return false;
     u64 next_log_idx = m.last_idx + 1;
     i64 max_pipe = C.max_pipeline, max_batch = C.max_batch;
     bool more = false, clean = true;
+    if (heartbeats && mode == RP_ALL)          // make_all_rpcs/1: CancelEffects ++ EffectsAER ++ EffectsHR
+        for (u32 s = 0; s < NMEM(C); s++)
+            if (s != m.slot && MT_PSTATUS(m.meta, s) == RA_PEER_SNAPSHOT_BACKOFF)
+                note(m, RA_NOTE_CANCEL_SNAPSHOT_RETRY, s, s, 0, 0);
     for (u32 s = 0; s < NMEM(C); s++) {
         if (s == m.slot) continue;
-        if (MT_PSTATUS(m.meta, s) != RA_PEER_NORMAL) continue;
+        if (MT_PSTATUS(m.meta, s) != RA_PEER_NORMAL &&
+            !(heartbeats && mode == RP_ALL && MT_PSTATUS(m.meta, s) == RA_PEER_SNAPSHOT_BACKOFF)) continue;
         ulonglong2 nm = peer_nm<MM>(m, s);
         u64 cs = peer_cs<MM>(m, s);
         i64 bs = 1;
@@ -820,6 +912,7 @@ __device__ __forceinline__ bool rpc_pass(Member& m, u32 mode, bool force)
         if (nn < next_log_idx) clean = false;
     }
     if (mode == RP_PIPELINE) m.pipe_clean = clean ? 1u : 0u;
+    else if (heartbeats) update_heartbeat_rpc_effects<MM>(m);  // make_rpcs / make_all_rpcs: EffectsAER ++ EffectsHR
     return more;
 }
 template <int MM>
@@ -837,6 +930,7 @@ __device__ __forceinline__ void initialise_peers(Member& m)
     for (u32 s = 0; s < NMEM(*m.C); s++) {
         peer_nm_set<MM>(m, s, next, 0);
         peer_cs_set<MM>(m, s, 0);
+        q_peer(m, s) = 0;                   // new_peer/0 :2963-2968
         MT_SET(m.meta, 32 + 3 * s, 3, RA_PEER_NORMAL);
     }
 }
@@ -850,10 +944,12 @@ __device__ __forceinline__ u32 call_for_election(Member& m, u32 target, NextQ& n
     Rec req;
     if (target == RA_CANDIDATE) {
         u64 nt = m.term + 1;
+        CR_INC(m, CR_ELECTIONS);                                        // :2856
         req = mk_rec(0, RA_EV_REQUEST_VOTE, 0, 0, 0, 0, 0, nt, m.last_idx, m.last_term, 0, 0, 0);
         update_term_and_voted_for(m, nt, m.slot);
     } else {
         u64 token = tok_ctr(m) + 1;                                 // make_ref()
+        CR_INC(m, CR_PRE_VOTE_ELECTIONS);                               // :2878
         u64 mv = macver(m) & 0xffffffffull;
         req = mk_rec(0, RA_EV_PRE_VOTE, 0, 0, 0, 0, 0, m.term, m.last_idx, m.last_term, token, 1ull | (mv << 32), 0);
         update_term_and_voted_for(m, m.term, m.slot);
@@ -921,6 +1017,7 @@ __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& n
     if (type == RA_EV_AER) {
         u64 term = R_term(e), cur = m.term;
         u32 leader = R_from(e);
+        CR_INC(m, CR_AER_RX);                                              // :1278 and :1418
         if (term >= cur) {
             u64 pl_idx = R_a(e), pl_term = R_b(e), leader_commit = R_c(e);
             u32 n0 = R_n(e), n1 = R_n1(e);
@@ -945,6 +1042,7 @@ __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& n
                 u64 k = idx - (pl_idx + 1);
                 u64 last_valid = idx - 1;
                 if (k == n0) {                                             // Entries == [] :1288
+                    CR_INC(m, CR_AER_RX_EMPTY);                            // :1290
                     u64 local_last = m.last_idx;
                     bool validated;
                     if (n0 == 0 && local_last > pl_idx) {                  // :1294-1303
@@ -1049,6 +1147,22 @@ __device__ __forceinline__ u32 handle_follower(Member& m, const Rec& e, NextQ& n
         u32 l = MT_LEADER(m.meta);
         note(m, RA_NOTE_NOT_LEADER, 0, R_n(e), l == SLOT_NONE ? RA_NO_SLOT : l, 0);
     }
+    if (type == RA_EV_CONSISTENT_QUERY) {                                  // only a leader answers consistent queries
+        u32 l = MT_LEADER(m.meta);
+        note(m, RA_NOTE_NOT_LEADER, 0, 0, l == SLOT_NONE ? RA_NO_SLOT : l, 0);
+    }
+    if (type == RA_EV_HEARTBEAT_RPC) {
+        if (R_term(e) >= m.term) {                                         // :1425-1434
+            update_term(m, R_term(e));
+            MT_SET(m.meta, 3, 4, R_from(e));
+            send_heartbeat_reply<MM>(m, R_from(e), R_term(e), R_a(e));
+        } else send_heartbeat_reply<MM>(m, R_from(e), m.term, R_a(e));     // :1435-1440
+        return RA_FOLLOWER;
+    }
+    if (type == RA_EV_HEARTBEAT_REPLY) {                                   // :1518-1521
+        update_term(m, R_term(e) > m.term ? R_term(e) : m.term);
+        return RA_FOLLOWER;
+    }
     return RA_FOLLOWER;
 }
 
@@ -1076,6 +1190,7 @@ __device__ __forceinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
         bool success = R_d(e) != 0;
         bool known = from < NMEM(C);
         if (success && term == m.term) {                                   // :522-561
+            CR_INC(m, CR_REPLY_OK);                                        // :528
             if (!known) return RA_LEADER;
             ulonglong2 nm = peer_nm<MM>(m, from);
             u64 nn = R_a(e) > nm.x ? R_a(e) : nm.x;
@@ -1091,6 +1206,7 @@ __device__ __forceinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
         }
         if (!success) {                                                    // :577-643
             if (!known) return RA_LEADER;
+            CR_INC(m, CR_REPLY_FAIL);                                      // :590
             ulonglong2 nm = peer_nm<MM>(m, from);
             u64 pnext = R_a(e), plast = R_b(e), plast_term = R_c(e);
             u64 t = log_fetch_term(m, (i64)plast);
@@ -1149,6 +1265,29 @@ __device__ __forceinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
         }
         make_rpcs<MM>(m, true);                                                // :952-957
         return RA_LEADER;
+    }
+    if (type == RA_EV_CONSISTENT_QUERY) {                  // :846-851 + make_heartbeat_rpc_effects/2 :3722-3739
+        if (NMEM(C) <= 1) { note(m, RA_NOTE_QUERY_APPLY, 0, m.commit, 0, 0); return RA_LEADER; }   // no peers
+        const u64 qi = ++q_index(m);
+        heartbeat_rpc_effects<MM>(m, qi);
+        note(m, RA_NOTE_QUERY_INDEX, 0, qi, m.commit, 0);
+        return RA_LEADER;
+    }
+    if (type == RA_EV_HEARTBEAT_RPC) {
+        if (R_term(e) > m.term) { u32 r = step_down<MM>(m, R_term(e)); nq_push(nq, NX_REDISPATCH); return r; }   // :871-880
+        if (R_term(e) < m.term) { send_heartbeat_reply<MM>(m, R_from(e), m.term, R_a(e)); return RA_LEADER; }    // :881-888
+        set_fatal(m, RA_FATAL_LEADER_SAW_HEARTBEAT_SAME_TERM);                                                    // :889-894
+        return RA_LEADER;
+    }
+    if (type == RA_EV_HEARTBEAT_REPLY) {                                   // :895-918
+        if (R_term(e) == m.term) {                                         // heartbeat_rpc_quorum/3 :3773-3795
+            const u32 from = R_from(e);
+            if (from < NMEM(C) && R_a(e) > q_peer(m, from)) q_peer(m, from) = R_a(e);   // update_peer_query_index/3
+            query_agreed(m, query_quorum<MM>(m));
+            return RA_LEADER;
+        }
+        if (R_term(e) > m.term) return step_down<MM>(m, R_term(e));
+        return RA_LEADER;                                                  // lower term: ignored
     }
     if (type == RA_EV_TICK) make_rpcs<MM>(m, false);                           // ra_server_proc.erl:610-613
     return RA_LEADER;
@@ -1212,6 +1351,23 @@ __device__ __forceinline__ u32 handle_candidate(Member& m, const Rec& e, NextQ& 
         u32 l = MT_LEADER(m.meta);
         note(m, RA_NOTE_NOT_LEADER, 0, R_n(e), l == SLOT_NONE ? RA_NO_SLOT : l, 0);
     }
+    if (type == RA_EV_CONSISTENT_QUERY) {
+        u32 l = MT_LEADER(m.meta);
+        note(m, RA_NOTE_NOT_LEADER, 0, 0, l == SLOT_NONE ? RA_NO_SLOT : l, 0);
+    }
+    if (type == RA_EV_HEARTBEAT_RPC) {
+        if (R_term(e) >= m.term) {                                         // :1064-1067
+            update_term_and_voted_for(m, R_term(e), SLOT_NONE);
+            nq_push(nq, NX_REDISPATCH);
+            return RA_FOLLOWER;
+        }
+        send_heartbeat_reply<MM>(m, R_from(e), m.term, R_a(e));            // :1068-1073
+        return RA_CANDIDATE;
+    }
+    if (type == RA_EV_HEARTBEAT_REPLY && R_term(e) > m.term) {             // :1074-1081
+        update_term_and_voted_for(m, R_term(e), SLOT_NONE);
+        return RA_FOLLOWER;
+    }
     return RA_CANDIDATE;
 }
 
@@ -1258,6 +1414,25 @@ __device__ __forceinline__ u32 handle_pre_vote(Member& m, const Rec& e, NextQ& n
         u32 l = MT_LEADER(m.meta);
         note(m, RA_NOTE_NOT_LEADER, 0, R_n(e), l == SLOT_NONE ? RA_NO_SLOT : l, 0);
     }
+    if (type == RA_EV_CONSISTENT_QUERY) {
+        u32 l = MT_LEADER(m.meta);
+        note(m, RA_NOTE_NOT_LEADER, 0, 0, l == SLOT_NONE ? RA_NO_SLOT : l, 0);
+    }
+    if (type == RA_EV_HEARTBEAT_RPC) {
+        if (R_term(e) >= m.term) {                                         // :1181-1186
+            update_term(m, R_term(e));
+            MT_SET(m.meta, 15, 4, 0);
+            nq_push(nq, NX_REDISPATCH);
+            return RA_FOLLOWER;
+        }
+        send_heartbeat_reply<MM>(m, R_from(e), m.term, R_a(e));            // :1187-1191
+        return RA_PRE_VOTE;
+    }
+    if (type == RA_EV_HEARTBEAT_REPLY && R_term(e) > m.term) {             // :1192-1195
+        MT_SET(m.meta, 15, 4, 0);
+        update_term(m, R_term(e));
+        return RA_FOLLOWER;
+    }
     return RA_PRE_VOTE;
 }
 
@@ -1298,7 +1473,11 @@ __device__ __forceinline__ u32 handle_await_condition(Member& m, const Rec& e, N
         return RA_AWAIT_CONDITION;
     }
     if (type == RA_EV_COMMAND) m.status |= RA_ST_CMD_POSTPONED;
-    return RA_AWAIT_CONDITION;
+    if (type == RA_EV_CONSISTENT_QUERY) {
+        u32 l = MT_LEADER(m.meta);
+        note(m, RA_NOTE_NOT_LEADER, 0, 0, l == SLOT_NONE ? RA_NO_SLOT : l, 0);
+    }
+    return RA_AWAIT_CONDITION;                 // heartbeat rpcs and replies are dropped here (:1938-1940)
 }
 
 // ---- the ra_server_proc shim ------------------------------------------------------------------
@@ -1407,6 +1586,7 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
             const u32 n = R_n(e);
             if (n != 0 && (R_d(e) != m.last_term || m.last_idx + 1 < m.applied)) return false;
             m.c_pack += 1u;
+            m.c_ref += (1ull << CR_AER_RX) + (n == 0 ? 1ull << CR_AER_RX_EMPTY : 0ull);   // :1278, :1290
             leader = R_from(e);
             m.status |= RA_ST_LEADER_MSG;
             MT_SET(m.meta, 3, 4, leader);
@@ -1457,7 +1637,8 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
         bool quorum = false, chase = false, force = false;
         u32 mode = RP_PIPELINE;
         if (type == RA_EV_PRE_VOTE) {                                  // :952-957 enforce leadership
-            if (R_term(e) > m.term) return false;
+            // (with a consistent query in flight make_all_rpcs also re-sends heartbeats: general path)
+            if (R_term(e) > m.term || ((m.meta >> 32) & 0xFFFFFFull) != 0 || q_index(m) != 0) return false;
             m.c_pack += 1u;
             mode = RP_ALL;
         } else if (type == RA_EV_COMMAND) {                            // :644-729
@@ -1479,6 +1660,7 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
             const u32 from = R_from(e);
             if (!(R_d(e) != 0 && R_term(e) == m.term && from < NMEM(*m.C))) return false;
             m.c_pack += 1u;
+            CR_INC(m, CR_REPLY_OK);                                    // :528
             ulonglong2 nm = peer_nm<MM>(m, from);
             if (R_b(e) > nm.y) m.cold &= ~8u;                          // a match index moves
             peer_nm_set<MM>(m, from, R_a(e) > nm.x ? R_a(e) : nm.x, R_b(e) > nm.y ? R_b(e) : nm.y);
@@ -1487,7 +1669,7 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
         // exact shortcut: nothing evaluate_quorum reads has moved since it last ran in this step
         if (quorum && !(m.cold & 8u)) evaluate_quorum<MM>(m);
         // a chased {next_event, info, pipeline_rpcs}: one pass, the rest is deferred (contract 4)
-        if (rpc_pass<MM>(m, mode, force) && chase) { MT_SET(m.meta, 24, 1, 1); m.status |= RA_ST_PIPELINE_PENDING; }
+        if (rpc_pass<MM>(m, mode, force, false) && chase) { MT_SET(m.meta, 24, 1, 1); m.status |= RA_ST_PIPELINE_PENDING; }
         return true;
     }
     return false;

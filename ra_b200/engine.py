@@ -55,7 +55,9 @@ EXPORTS = ["ra_engine_create", "ra_engine_destroy", "ra_engine_load_rows", "ra_e
            "ra_engine_last_cuda_error", "ra_engine_get_cfg", "ra_engine_alloc_host",
            "ra_engine_free_host", "ra_engine_stall_histogram", "ra_engine_set_stream",
            "ra_engine_set_outbox", "ra_engine_deliver", "ra_engine_peer_get", "ra_engine_peer_set",
-           "ra_engine_ipc_export", "ra_engine_ipc_import"]
+           "ra_engine_ipc_export", "ra_engine_ipc_import", "ra_engine_peer_barrier",
+           "ra_engine_load_query_state", "ra_engine_read_query_state", "ra_engine_step_host"]
+HOST_EXPORTS = ["ra_wal_batch_to_events"]            # host-only helpers of the same library
 HOSTSIM_EXPORTS = ["ra_hostsim_create", "ra_hostsim_destroy", "ra_hostsim_run", "ra_hostsim_stats",
                    "ra_hostsim_breakdown"]
 

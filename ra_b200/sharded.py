@@ -49,6 +49,8 @@ def _declare(l):
     for n in ("ra_engine_peer_get", "ra_engine_ipc_export"):
         getattr(l, n).restype = C.c_int
         getattr(l, n).argtypes = [C.c_void_p, C.c_void_p]
+    l.ra_engine_peer_barrier.restype = C.c_int
+    l.ra_engine_peer_barrier.argtypes = [C.c_void_p]
     for n in ("ra_engine_peer_set", "ra_engine_ipc_import"):
         getattr(l, n).restype = C.c_int
         getattr(l, n).argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
@@ -103,6 +105,9 @@ class Shard:
     def ipc_import(self, shard: int, raw: bytes) -> None:
         h = IpcHandles.from_buffer_copy(raw)
         self.eng._check(lib().ra_engine_ipc_import(self.eng._h, shard, C.byref(h)), "ipc_import")
+
+    def peer_barrier(self) -> None:
+        self.eng._check(lib().ra_engine_peer_barrier(self.eng._h), "peer_barrier")
 
     def deliver(self) -> None:
         e = self.eng
@@ -183,11 +188,15 @@ class NvlinkPeerTransport:
     destination GPU's HBM, and the only per-step collective is the lock-step barrier (a 1-element
     NCCL all-reduce on the compute stream)."""
 
-    def __init__(self, shard: Shard):
+    def __init__(self, shard: Shard, device_barrier: bool | None = None):
+        import os
         import torch.distributed as dist
         self.dist = dist
         self.shard = shard
         self.shards = [shard]
+        # step barrier: a kernel on the engine's stream (flag words in the peers' HBM) or a 1-element all-reduce
+        self.device_barrier = (os.environ.get("RA_PEER_BARRIER", "nccl") == "device") if device_barrier is None \
+            else device_barrier
         handles = [None] * dist.get_world_size()
         dist.all_gather_object(handles, shard.ipc_export())
         for k, raw in enumerate(handles):
@@ -197,7 +206,10 @@ class NvlinkPeerTransport:
         dist.barrier()
 
     def exchange(self) -> None:
-        self.dist.all_reduce(self._tok)          # lock step: nobody starts step t+1 before all finished t
+        if self.device_barrier:
+            self.shard.peer_barrier()            # lock step without a collective
+        else:
+            self.dist.all_reduce(self._tok)      # lock step: nobody starts step t+1 before all finished t
 
     def exchange_barrier(self) -> None:
         torch.cuda.synchronize(self.shard.dev)

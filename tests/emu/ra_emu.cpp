@@ -52,7 +52,7 @@ extern "C" int ra_emu_reset_empty(ra_emu* e)
 {
     if (!e) return RA_E_INVAL;
     for (u32 r = 0; r < e->C.rows; r++) reset_row(e->C, r);
-    memset(e->C.counters, 0, (8 + 8 * 16) * sizeof(u64));
+    memset(e->C.counters, 0, (8 + 8 * 16 + 8) * sizeof(u64));
     e->cur = 0; e->step_no = 0; e->steps = 0;
     return RA_OK;
 }
@@ -81,11 +81,12 @@ extern "C" int ra_emu_create(const ra_engine_cfg* cfg, ra_emu** out)
 #define HA(p, n) if ((rc = halloc(e, &(p), (n))) != RA_OK) goto bad
     HA(C.tc, R); HA(C.lg, R); HA(C.lw, R); HA(C.ap, R); HA(C.sn, R); HA(C.tk, R); HA(C.fm, R);
     HA(C.cd, 2 * R); HA(C.pnm, M * R); HA(C.pcs, M * R); HA(C.run, RA_MAX_RUNS * R); HA(C.lrs, R);
+    HA(C.qi, R); HA(C.qa, R); HA(C.pqi, M * R);
     C.tiles = (u32)((R + RT - 1) / RT);
     {
         const size_t PW = (size_t)C.tiles * 4 * RT;
         HA(C.loc, (size_t)RA_LOCAL_CAP * PW); HA(C.loc_n, R);
-        HA(C.onote, (size_t)RA_NOTE_CAP * R); HA(C.out_n, R); HA(C.counters, 8 + 8 * 16);
+        HA(C.onote, (size_t)RA_NOTE_CAP * R); HA(C.out_n, R); HA(C.counters, 8 + 8 * 16 + 8);
         if (C.routed) {
             for (int b = 0; b < 2; b++) { HA(C.mbox[b], M * RA_MBOX_DEPTH * PW); HA(C.mbox_cnt[b], R); }
             HA(C.omsg, (size_t)RA_MSG_CAP * (C.pure ? R : 1));
@@ -127,6 +128,22 @@ extern "C" int ra_emu_read_rows(ra_emu* e, ra_row_state* rows, size_t n)
     return RA_OK;
 }
 
+extern "C" int ra_emu_load_query_state(ra_emu* e, const ra_query_state* q, size_t n)
+{
+    if (!e || (!q && n)) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) if (q[i].row >= e->C.rows) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) load_query_row(e->C, q[i]);
+    return RA_OK;
+}
+
+extern "C" int ra_emu_read_query_state(ra_emu* e, ra_query_state* q, size_t n)
+{
+    if (!e || (!q && n)) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) if (q[i].row >= e->C.rows) return RA_E_INVAL;
+    for (size_t i = 0; i < n; i++) read_query_row(e->C, q[i]);
+    return RA_OK;
+}
+
 // ---- one row through one step: raft_step_kernel, then raft_general_kernel if it stalled -------
 
 struct Scratch { ulonglong2 nm[RA_MAX_MEMBERS]; u64 cs[RA_MAX_MEMBERS]; };   // the per-thread shared-memory columns
@@ -136,6 +153,7 @@ static void add_counters(const Cols& C, const Member& m, u32 k_fatal)
     C.counters[0] += m.c_pack & 0xffu; C.counters[1] += m.c_commits; C.counters[2] += m.c_applied;
     C.counters[3] += (m.c_pack >> 8) & 0xffu; C.counters[4] += m.c_pack >> 20; C.counters[5] += (m.c_pack >> 16) & 15u;
     C.counters[6] += k_fatal;
+    for (int f = 0; f < 7; f++) C.counters[136 + f] += (m.c_ref >> (8 * f)) & 0xffu;   // the reference's counters
 }
 
 // the general kernel's body for one stall context (engine.cu: raft_general_kernel)
@@ -334,6 +352,25 @@ extern "C" int ra_emu_step(ra_emu* e, const ra_event* ev, size_t n_ev,
     return RA_OK;
 }
 
+extern "C" int ra_emu_step_host(ra_emu* e, const ra_host_event* ev, size_t n_ev,
+                                ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                                ra_note* notes, size_t notes_cap, size_t* n_notes)
+{
+    if (!e || (!ev && n_ev)) return RA_E_INVAL;
+    ra_event* w = (ra_event*)calloc(n_ev ? n_ev : 1, sizeof(ra_event));
+    if (!w) return RA_E_NOMEM;
+    for (size_t i = 0; i < n_ev; i++) {
+        const u32 t = ev[i].type;
+        if (!(t == RA_EV_WRITTEN || t == RA_EV_COMMAND || t == RA_EV_ELECTION_TIMEOUT || t == RA_EV_AWAIT_COND_TIMEOUT ||
+              t == RA_EV_PIPELINE_RPCS || t == RA_EV_TICK || t == RA_EV_CONSISTENT_QUERY)) { free(w); return RA_E_INVAL; }
+        w[i].row = ev[i].row; w[i].type = (uint8_t)t; w[i].from_slot = RA_NO_SLOT; w[i].flags = ev[i].flags; w[i].n = ev[i].n;
+        w[i].term = ev[i].term; w[i].a = ev[i].a; w[i].b = ev[i].b;
+    }
+    const int rc = ra_emu_step(e, w, n_ev, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes);
+    free(w);
+    return rc;
+}
+
 extern "C" int ra_emu_flood(ra_emu* e, uint32_t n_steps, uint32_t cmds_per_step, uint32_t election_permille,
                             uint64_t seed)
 {
@@ -354,6 +391,9 @@ extern "C" int ra_emu_counters(ra_emu* e, ra_counters* out)
     const u64* h = e->C.counters;
     out->events = h[0]; out->commits = h[1]; out->applied = h[2]; out->msgs_out = h[3];
     out->msgs_dropped = h[4]; out->elections_won = h[5]; out->fatal_rows = h[6]; out->steps = e->steps;
+    out->aer_received_follower = h[136]; out->aer_received_follower_empty = h[137]; out->aer_replies_success = h[138];
+    out->aer_replies_failed = h[139]; out->elections = h[140]; out->pre_vote_elections = h[141];
+    out->term_and_voted_for_updates = h[142];
     return RA_OK;
 }
 
@@ -384,3 +424,6 @@ extern "C" int ra_emu_codec_roundtrip(const ra_event* in, ra_event* out, int* ha
     st_rec(out, ld_rec_plane(plane, 1, 0, row));
     return RA_OK;
 }
+extern "C" int ra_engine_step_host(ra_engine* e, const ra_host_event* ev, size_t n_ev, ra_event* msgs, size_t msgs_cap,
+                                   size_t* n_msgs, ra_note* notes, size_t notes_cap, size_t* n_notes)
+{ return ra_emu_step_host((ra_emu*)e, ev, n_ev, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes); }

@@ -112,7 +112,7 @@ def status(notes: Sequence[abi.RaNote]) -> int:
     for n in notes:
         if n.type == abi.NOTE_STATUS:
             return n.aux
-    return 0
+    return notes[-1].aux if notes else 0       # record_leader_msg alone rides in the last note's aux
 
 
 def notes_of(notes: Sequence[abi.RaNote], t: int) -> List[abi.RaNote]:

@@ -27,8 +27,9 @@ def test_header_symbols_exported():
     src = open(os.path.join(ROOT, "include", "ra_engine.h")).read()
     sim = sorted(set(re.findall(r"\b(ra_hostsim_[a-z_]+)\s*\(", src)))
     assert sim == sorted(engine.HOSTSIM_EXPORTS)
-    for n in sim:
+    for n in sim + engine.HOST_EXPORTS:
         assert hasattr(lib, n), n
+    assert sorted(set(re.findall(r"\b(ra_wal_[a-z_]+)\s*\(", src))) == sorted(engine.HOST_EXPORTS)
 
 
 def test_record_sizes_match_header():

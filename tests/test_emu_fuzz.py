@@ -80,7 +80,13 @@ def random_event(rng: random.Random, s: abi.RaRowState, m: int) -> abi.RaEvent:
     t = max(0, term + rng.choice([-1, 0, 0, 0, 1]))
     near = lambda x: max(0, x + rng.choice([-2, -1, 0, 0, 0, 1, 2]))
     kind = rng.choice(["aer", "aer", "reply", "reply", "rv", "rvres", "pv", "pvres", "written", "cmd",
-                       "etmo", "ctmo", "tick", "pipe"])
+                       "etmo", "ctmo", "tick", "pipe", "hb", "hbr", "cq"])
+    if kind == "hb":
+        return abi.ev_heartbeat_rpc(row, other, t, rng.randint(0, 4))
+    if kind == "hbr":
+        return abi.ev_heartbeat_reply(row, rng.choice([other, other, 7]), t, rng.randint(0, 4))
+    if kind == "cq":
+        return abi.ev_consistent_query(row)
     if kind == "aer":
         prev = near(last)
         pt = rng.randint(0, t)
@@ -142,12 +148,20 @@ def test_fuzz_state_event_pairs(m, pure):
             for _ in range(rng.choice([1, 1, 2])):
                 events.append(random_event(rng, st, m))
         rows = [s.row for s in states]
+        qs = []
+        for st in states:                                   # consistent-query indexes of the row and its peers
+            q = abi.RaQueryState(row=st.row, query_index=rng.randint(0, 4), agreed_index=rng.randint(0, 2))
+            for p in range(m):
+                q.peer_query_index[p] = rng.randint(0, 4)
+            qs.append(q)
         outs = []
         for b in (o, e):
             b.load_rows(states)
+            b.load_query_state(qs)
             msgs, notes = b.step([_copy(x) for x in events])
             outs.append(([x.key() for x in msgs], [x.key() for x in notes],
-                         [r.key() for r in b.read_rows(rows)], b.counters()))
+                         [r.key() for r in b.read_rows(rows)], b.counters(),
+                         [q.key(m) for q in b.read_query_state(rows)]))
         w, x = outs
         if w != x:
             # narrow it down to the first row that differs, for the message
@@ -160,3 +174,4 @@ def test_fuzz_state_event_pairs(m, pure):
             assert w[0] == x[0], "round %d: RPC records differ" % rnd
             assert w[1] == x[1], "round %d: notes differ" % rnd
             assert w[3] == x[3], "round %d: counters differ" % rnd
+            assert w[4] == x[4], "round %d: query state differs" % rnd

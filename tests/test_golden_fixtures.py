@@ -28,7 +28,7 @@ def test_golden_trace(name, backend):
     for t, (got, want) in enumerate(zip(per_step, meta["step_sha256"])):
         assert got == want, "outputs of step %d differ from the fixture" % t
     assert rows == meta["rows_sha256"]
-    assert counters == meta["counters"]
+    assert {k: counters[k] for k in meta["counters"]} == meta["counters"]      # (a fixture may predate a counter)
 
 
 def test_fixtures_match_their_generator():
@@ -53,5 +53,5 @@ def test_golden_flood(case, backend):
     b = make_backend(backend, g, m, route_on_device=True)
     kw = dict(threads=4) if backend == "oracle" else {}
     rows, counters = G.flood_digest(b, g, m, case["steps"], case["cmds"], case["permille"], case["seed"], **kw)
-    assert counters == case["counters"]
+    assert {k: counters[k] for k in case["counters"]} == case["counters"]
     assert rows == case["rows_sha256"]

@@ -853,3 +853,55 @@ def test_load_rows_rejects_inconsistent_log_views(be):
     bad(lambda s: setattr(s, "n_members", 5))                       # not this engine's group size
     bad(lambda s: setattr(s, "row", 99))                            # no such row
     assert b.read_rows([ok.row])[0].key() == ok.key()               # the good row is untouched
+
+
+def test_reference_counters(be):
+    """The reference's own counters of this path (ra.hrl:324-343): where ra_server.erl increments them
+    (:528, :590, :1278, :1290, :1418, :2856, :2878, :3026)."""
+    nd = Node(be, 3)
+    st = base_state(3)
+    c0 = nd.b.counters()
+
+    def delta():
+        c = nd.b.counters()
+        return {k: c[k] - c0[k] for k in ("aer_received_follower", "aer_received_follower_empty", "aer_replies_success",
+                                           "aer_replies_failed", "elections", "pre_vote_elections",
+                                           "term_and_voted_for_updates") if c[k] != c0[k]}
+    nd.handle_follower(ev_aer(0, N2, 5, 3, 5, 3, []), st)                 # up to date, no entries
+    assert delta() == dict(aer_received_follower=1, aer_received_follower_empty=1)
+    nd.handle_follower(ev_aer(0, N2, 4, 3, 5, 3, []), st)                 # stale term: counted too (:1418)
+    assert delta() == dict(aer_received_follower=2, aer_received_follower_empty=1)
+    nd.handle_follower(ev_aer(0, N2, 5, 3, 5, 3, [5]), st)                # one new entry: not "empty"
+    assert delta()["aer_received_follower"] == 3 and delta()["aer_received_follower_empty"] == 1
+    nd.handle_leader(ev_aer_reply(0, N2, 5, True, 4, 3, 5), st)
+    nd.handle_leader(ev_aer_reply(0, N2, 5, False, 4, 3, 5), st)
+    d = delta()
+    assert (d["aer_replies_success"], d["aer_replies_failed"]) == (1, 1)
+    nd.handle_follower(ev_simple(0, EV_ELECTION_TIMEOUT), st)             # pre-vote round: votes for itself
+    d = delta()
+    assert d["pre_vote_elections"] == 1 and d["term_and_voted_for_updates"] == 1 and "elections" not in d
+    pv = clone(st)
+    pv.votes = 1
+    pv.pre_vote_token = 9
+    role, s, _, _ = nd.handle_pre_vote(ev_pre_vote_result(0, 5, 9, True), pv)   # quorum of 3: becomes candidate
+    assert role == CANDIDATE
+    d = delta()
+    assert d["elections"] == 1 and d["term_and_voted_for_updates"] == 2
+
+
+def test_leader_pre_vote_sends_rpc_to_backoff_peer(be):
+    """leader_pre_vote_sends_snapshot_to_backoff_peer/1, :2548-2574: make_all_rpcs/1 (:2337-2350) cancels the
+    snapshot retry timer of a peer in snapshot_backoff and sends it an rpc as well."""
+    nd = Node(be, 3)
+    st = base_state(3)
+    st.votes = 1
+    st.peers[N2].status = PEER_SNAPSHOT_BACKOFF
+    role, s, msgs, notes = nd.handle_leader(ev_pre_vote(0, N1, 5, 77, 3, 5), st)
+    assert role == LEADER
+    assert [(n.slot, n.a) for n in notes_of(notes, NOTE_CANCEL_SNAPSHOT_RETRY)] == [(N2, N2)]
+    assert sorted(m.row for m in of_type(msgs, EV_AER)) == [N2, N3]
+    # a tick (make_rpcs/1 over stale_peers/1) still leaves the backoff peer alone
+    st.peers[N2].match_index = 1
+    st.peers[N3].match_index = 1
+    role, s, msgs, notes = nd.handle_leader(ev_simple(0, EV_TICK), st)
+    assert [m.row for m in of_type(msgs, EV_AER)] == [N3] and notes_of(notes, NOTE_CANCEL_SNAPSHOT_RETRY) == []

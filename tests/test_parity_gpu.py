@@ -35,6 +35,7 @@ TRACES = [
     # SURVEY 8d config 5 (7 members: lagging fsync, dropped AERs -> missing / await_condition / back-off,
     # leader changes with unreplicated tails) at 2000 groups, every record and note diffed
     (2000, 7, 60, 29, dict(p_drop=0.005, p_withhold_written=0.02, p_timeout=0.003, p_dup=0.0, p_adversarial=0.0)),
+    (24, 5, 250, 41, dict(p_query=0.3, p_timeout=0.02)),          # consistent queries: heartbeat rounds in the loop
 ]
 
 

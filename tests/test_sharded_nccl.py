@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("transport", ["a2a", "peer"])
+@pytest.mark.parametrize("transport", ["a2a", "peer", "peer-devbar"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_nccl_sharded_flood_equals_oracle(world, transport, tmp_path):
     import torch
@@ -42,7 +42,8 @@ def test_nccl_sharded_flood_equals_oracle(world, transport, tmp_path):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         gl, m, steps = 256, 5, 70
-        peer = %r == "peer"
+        peer = %r.startswith("peer")
+        os.environ["RA_PEER_BARRIER"] = "device" if %r.endswith("devbar") else "nccl"
         sh = Shard(gl, m, world, rank, device=local, buckets=not peer)
         fl = ShardedFlood(NvlinkPeerTransport(sh) if peer else NcclTransport(sh))
         fl.bootstrap()
@@ -64,7 +65,7 @@ def test_nccl_sharded_flood_equals_oracle(world, transport, tmp_path):
         if rank == 0:
             print("RESULT", int(t[0]), int(t[1]), int(t[2]), o.counters()["commits"])
         dist.destroy_process_group()
-    """ % (ROOT, ROOT, transport)))
+    """ % (ROOT, ROOT, transport, transport)))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],

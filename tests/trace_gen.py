@@ -26,13 +26,14 @@ class Cluster:
     """Network + WAL + clients around one backend (non-routed engine or oracle)."""
 
     def __init__(self, backend, seed: int, *, p_drop=0.02, p_dup=0.01, p_delay=0.15, p_cmd=0.5,
-                 p_timeout=0.01, p_adversarial=0.01, p_withhold_written=0.05, max_cmd=3):
+                 p_timeout=0.01, p_adversarial=0.01, p_withhold_written=0.05, max_cmd=3, p_query=0.0):
         self.b = backend
         self.rng = random.Random(seed)
         self.p_drop, self.p_dup, self.p_delay = p_drop, p_dup, p_delay
         self.p_cmd, self.p_timeout, self.p_adv = p_cmd, p_timeout, p_adversarial
         self.p_withhold = p_withhold_written
         self.max_cmd = max_cmd
+        self.p_query = p_query                                  # consistent queries handed to leaders
         self.queues: Dict[int, deque] = defaultdict(deque)      # row -> events ready now
         self.delayed: List[Tuple[int, abi.RaEvent]] = []        # (due_step, event)
         self.step_no = 0
@@ -60,6 +61,8 @@ class Cluster:
                 self.queues[row].append(abi.ev_command(row, rng.randint(1, self.max_cmd)))
             elif rng.random() < self.p_cmd * 0.02:
                 self.queues[row].append(abi.ev_command(row, 1))           # misdirected command
+            if self.p_query and rng.random() < (self.p_query if role == abi.LEADER else self.p_query * 0.05):
+                self.queues[row].append(abi.ev_consistent_query(row))
             if rng.random() < self.p_timeout or self.idle[row] > 12 + (row % 7):
                 self.queues[row].append(abi.ev_simple(row, abi.EV_ELECTION_TIMEOUT))
                 self.idle[row] = 0
@@ -110,7 +113,10 @@ class Cluster:
             if rng.random() < self.p_dup:
                 self._post(copy_ev(m), 1)
         saw_leader = set()
-        for n in notes:
+        for i, n in enumerate(notes):
+            last_of_row = i + 1 == len(notes) or notes[i + 1].row != n.row
+            if last_of_row and n.type != abi.NOTE_STATUS and (n.aux & abi.ST_LEADER_MSG):
+                saw_leader.add(n.row)                      # flags riding in the row's last note
             if n.type == abi.NOTE_WAL_APPEND:
                 if rng.random() < self.p_withhold:
                     self._post(abi.ev_written(n.row, n.c, n.a, n.b), rng.randint(3, 12))   # lagging fsync
