@@ -33,7 +33,10 @@ extern "C" {
 #define RA_MBOX_DEPTH    4      /* per (src,dst) messages per step in routed mode    */
 #define RA_LOCAL_CAP     4      /* host ("local") events per row per step            */
 #define RA_MSG_CAP       16     /* outgoing RPC records per row per step             */
-#define RA_NOTE_CAP      8      /* host notes per row per step                       */
+#define RA_NOTE_CAP      16     /* host notes per row per step (cfg.note_cap may lower it) */
+#define RA_NOTE_RESERVE  4      /* a row takes its next event of a step only while at least this many
+                                   note slots (+ the one kept for STATUS) are free, so that no event's
+                                   notes are ever cut off half-way: see "note budget" below  */
 
 /* ra_state(), src/ra_server.erl:116-119 (the five states on the hot path) */
 enum ra_role {
@@ -156,7 +159,11 @@ enum ra_note_type {
 #define RA_ST_FATAL               0x0040u /* c = enum ra_fatal; the reference would exit/crash    */
 #define RA_ST_CMD_POSTPONED       0x0080u /* COMMAND while in await_condition (proc postpones)    */
 #define RA_ST_BECAME_LEADER       0x0100u
-#define RA_ST_NOTE_OVERFLOW       0x0200u
+#define RA_ST_NOTE_OVERFLOW       0x0200u /* note budget: the row stopped taking events for this step.  Mailbox
+                                             records it had not reached are dropped (and counted, like a full
+                                             transport); the host events it had not reached were NOT consumed:
+                                             STATUS.c bits 8..15 = how many (the LAST ones of the row's run in
+                                             ev[]) -- submit them again in the next call                        */
 
 enum ra_fatal {
     RA_FATAL_NONE = 0,
@@ -165,7 +172,10 @@ enum ra_fatal {
     RA_FATAL_SET_LAST_INDEX_NOT_FOUND = 3, /* {ok,L} = ra_log:set_last_index(..) badmatch :1301    */
     RA_FATAL_ASSERT = 4,                   /* a ?assert / ?assertNot in the reference failed       */
     RA_FATAL_NO_SNAPSHOT = 5,              /* make_rpc_effect: prev entry and snapshot both absent :2378 */
-    RA_FATAL_LEADER_SAW_HEARTBEAT_SAME_TERM = 6 /* exit(leader_saw_heartbeat_rpc_in_same_term) :894 */
+    RA_FATAL_LEADER_SAW_HEARTBEAT_SAME_TERM = 6, /* exit(leader_saw_heartbeat_rpc_in_same_term) :894 */
+    RA_FATAL_NOTE_OVERFLOW = 7             /* one event produced more notes than the budget reserves (only a burst
+                                              of SEND_SNAPSHOT / CANCEL_SNAPSHOT_RETRY notes can): nothing is lost
+                                              silently -- the row stops like a crashed server and is reloaded    */
 };
 
 typedef struct ra_note {
@@ -246,7 +256,8 @@ typedef struct ra_engine_cfg {
                                      the LOCAL group count per slot.  RPC records for other shards go to the
                                      outbox (ra_engine_set_outbox) and come back through ra_engine_deliver */
     uint32_t shard;
-    uint32_t _reserved;
+    uint32_t note_cap;            /* 0 = RA_NOTE_CAP; else notes per row per step, RA_NOTE_RESERVE + 2 .. RA_NOTE_CAP
+                                     (a smaller value only makes the note budget bite earlier: tests)      */
 } ra_engine_cfg;
 
 typedef struct ra_engine ra_engine;

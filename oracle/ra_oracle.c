@@ -101,6 +101,7 @@ struct ra_oracle {
     ra_event *loc;                   /* [k*n_rows + row] */
     u8 *loc_n;
     u64 step_no;
+    u32 note_cap;                    /* notes per row per step (cfg.note_cap or RA_NOTE_CAP) */
 };
 
 /* per-row, per-step output context */
@@ -111,6 +112,7 @@ typedef struct {
     ra_note  notes[RA_NOTE_CAP]; u32 n_notes;
     u32 status;                 /* RA_ST_* */
     u32 fatal_code;
+    u32 unconsumed;             /* host events refused by the note budget */
     u8  role_at_start;
     u8  sent_to[RA_MAX_MEMBERS]; /* routed mode: records put in (self -> slot) mailbox */
     ra_counters *cnt;
@@ -324,11 +326,28 @@ static void note(ctx_t *c, u8 type, u8 slot, u64 a, u64 b, u64 cc)
         ra_note *p = &c->notes[c->n_notes - 1];
         if (p->type == RA_NOTE_APPLY && p->b + 1 == a) { p->b = b; return; }
     }
-    if (c->n_notes >= RA_NOTE_CAP - 1) { c->status |= RA_ST_NOTE_OVERFLOW; return; }
+    if (c->n_notes >= c->o->note_cap - 1) {
+        /* contract (include/ra_engine.h, note budget): unreachable while an event stays within
+           RA_NOTE_RESERVE notes; otherwise nothing is lost silently -- the row stops */
+        c->status |= RA_ST_NOTE_OVERFLOW; set_fatal(c, RA_FATAL_NOTE_OVERFLOW); return;
+    }
     ra_note *n = &c->notes[c->n_notes++];
     n->row = c->m->row; n->type = type; n->slot = slot; n->aux = 0;
     n->a = a; n->b = b; n->c = cc;
 }
+
+/* contract: the note budget.  A row takes the next event of its step only while RA_NOTE_RESERVE
+   slots + the STATUS slot are free; mailbox records it does not reach are dropped and counted,
+   host events are left unconsumed (STATUS.c bits 8..15) */
+static int note_budget_ok(const ctx_t *c) { return c->n_notes + RA_NOTE_RESERVE + 1u <= c->o->note_cap; }
+static void budget_drop_record(ctx_t *c)
+{ c->status |= RA_ST_NOTE_OVERFLOW | RA_ST_MSG_DROPPED; c->cnt->msgs_dropped++; }
+static void budget_refuse_local(ctx_t *c) { c->status |= RA_ST_NOTE_OVERFLOW; c->unconsumed++; }
+static void process_event(ctx_t *c, const ra_event *in);
+static void take_record(ctx_t *c, const ra_event *e)
+{ if (!c->m->fatal && !note_budget_ok(c)) budget_drop_record(c); else process_event(c, e); }
+static void take_local(ctx_t *c, const ra_event *e)
+{ if (!c->m->fatal && !note_budget_ok(c)) budget_refuse_local(c); else process_event(c, e); }
 
 static u32 row_of(const ra_oracle *o, u32 group, u32 slot) { return slot * o->cfg.n_groups + group; }
 static u32 group_of(const ra_oracle *o, u32 row) { return row % o->cfg.n_groups; }
@@ -1384,7 +1403,7 @@ static void ctx_finish(ctx_t *c)
     n->a = m->current_term;
     n->b = (u64)m->voted_for | ((u64)m->leader_slot << 8) | ((u64)c->role_at_start << 16) |
            ((u64)m->role << 24);
-    n->c = c->fatal_code;
+    n->c = c->fatal_code | ((u64)c->unconsumed << 8);
     if (c->status & RA_ST_FATAL) c->cnt->fatal_rows++;
 }
 
@@ -1403,7 +1422,7 @@ static void process_row_prologue(ctx_t *c)
         for (u32 s = 0; s < m->n_members; s++) {
             u8 *cnt = &o->mbox_n[cb][(size_t)s * o->n_rows + m->row];
             for (u32 k = 0; k < *cnt; k++)
-                process_event(c, &o->mbox[cb][((size_t)s * RA_MBOX_DEPTH + k) * o->n_rows + m->row]);
+                take_record(c, &o->mbox[cb][((size_t)s * RA_MBOX_DEPTH + k) * o->n_rows + m->row]);
             *cnt = 0;
         }
     }
@@ -1458,6 +1477,8 @@ int ra_oracle_create(const ra_engine_cfg *cfg, ra_oracle **out)
     ra_oracle *o = (ra_oracle *)calloc(1, sizeof *o);
     if (!o) return RA_E_NOMEM;
     o->cfg = *cfg;
+    if (cfg->note_cap && (cfg->note_cap < RA_NOTE_RESERVE + 2 || cfg->note_cap > RA_NOTE_CAP)) { free(o); return RA_E_INVAL; }
+    o->note_cap = cfg->note_cap ? cfg->note_cap : RA_NOTE_CAP;
     if (o->cfg.max_pipeline_count == 0) o->cfg.max_pipeline_count = 4096;
     if (o->cfg.max_aer_batch == 0) o->cfg.max_aer_batch = 128;
     o->n_rows = cfg->n_groups * cfg->n_members;
@@ -1668,7 +1689,7 @@ int ra_oracle_step(ra_oracle *o, const ra_event *ev, size_t n_ev,
         if (!m->fatal) {
             process_row_prologue(&c);
             if (todo[r] == 1)
-                for (size_t i = first[r]; i < n_ev && ev[i].row == r; i++) process_event(&c, &ev[i]);
+                for (size_t i = first[r]; i < n_ev && ev[i].row == r; i++) take_local(&c, &ev[i]);
         }
         publish_mbox_counts(&c);
         ctx_finish(&c);
@@ -1778,7 +1799,7 @@ static void flood_groups(ra_oracle *o, u32 g0, u32 g1, u32 n_steps, u32 cmds, u3
                     u32 nl = o->loc_n[row];
                     for (u32 k = 0; k < nl; k++) {
                         ra_event e = o->loc[(size_t)k * o->n_rows + row];
-                        process_event(&c, &e);
+                        take_local(&c, &e);
                     }
                 }
                 o->loc_n[row] = 0;

@@ -20,7 +20,8 @@ RA_UNDEF_TERM = 0xFFFFFFFFFFFFFFFF
 RA_MBOX_DEPTH = 4
 RA_LOCAL_CAP = 4
 RA_MSG_CAP = 16
-RA_NOTE_CAP = 8
+RA_NOTE_CAP = 16
+RA_NOTE_RESERVE = 4
 
 # enum ra_role
 FOLLOWER, CANDIDATE, PRE_VOTE, LEADER, AWAIT_CONDITION = 0, 1, 2, 3, 4
@@ -62,6 +63,7 @@ FATAL_SET_LAST_INDEX_NOT_FOUND = 3
 FATAL_ASSERT = 4
 FATAL_NO_SNAPSHOT = 5
 FATAL_LEADER_SAW_HEARTBEAT_SAME_TERM = 6
+FATAL_NOTE_OVERFLOW = 7
 
 RA_OK, RA_E_INVAL, RA_E_NOMEM, RA_E_CUDA, RA_E_UNGROUPED, RA_E_CAPACITY, RA_E_NODEVICE = 0, -1, -2, -3, -4, -5, -6
 
@@ -154,7 +156,7 @@ class RaEngineCfg(C.Structure):
     _fields_ = [("n_groups", C.c_uint32), ("n_members", C.c_uint32),
                 ("max_pipeline_count", C.c_uint32), ("max_aer_batch", C.c_uint32),
                 ("device", C.c_int32), ("route_on_device", C.c_uint32), ("pure", C.c_uint32),
-                ("n_shards", C.c_uint32), ("shard", C.c_uint32), ("_reserved", C.c_uint32)]
+                ("n_shards", C.c_uint32), ("shard", C.c_uint32), ("note_cap", C.c_uint32)]
 
 
 class RaCounters(C.Structure):
@@ -233,14 +235,14 @@ class Backend:
 
     def __init__(self, lib: C.CDLL, prefix: str, n_groups: int, n_members: int, *, device: int = 0,
                  route_on_device: bool = False, pure: bool = False, max_pipeline_count: int = 4096,
-                 max_aer_batch: int = 128, n_shards: int = 1, shard: int = 0):
+                 max_aer_batch: int = 128, n_shards: int = 1, shard: int = 0, note_cap: int = 0):
         self._lib = lib
         self._p = prefix
         self.n_groups = n_groups
         self.n_members = n_members
         self.n_rows = n_groups * n_members
         self.cfg = RaEngineCfg(n_groups, n_members, max_pipeline_count, max_aer_batch, device,
-                               1 if route_on_device else 0, 1 if pure else 0, n_shards, shard, 0)
+                               1 if route_on_device else 0, 1 if pure else 0, n_shards, shard, note_cap)
         self._h = C.c_void_p()
         f = self._fn("create")
         f.restype = C.c_int

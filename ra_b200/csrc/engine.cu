@@ -266,7 +266,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             if (rec_has_tail(c0)) { const ulonglong2* tp = &S.stage[warp][h2][0]; t2 = tp[lane]; t3 = tp[RT + lane]; }
             const Rec e = rec_decode(c0, c1, t2, t3, r);
             if (MT_FATAL(m.meta)) m.c_pack += 1u;
-            else if (C.pure || !fast_event<MM>(m, e)) {
+            else if (!note_budget_ok(m) || C.pure || !fast_event<MM>(m, e)) {
                 stalled = true;
                 rem = mine & ~(((mask_t)1 << p) - 1);
                 atomicAdd(&C.counters[8 + (m_role(m) & 7u) * 16 + (R_type(e) & 15u)], 1ull);
@@ -308,7 +308,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             if (rec_has_tail(c0)) { t2 = sp[2 * RT + lane]; t3 = sp[3 * RT + lane]; }
             const Rec e = rec_decode(c0, c1, t2, t3, r);
             if (MT_FATAL(m.meta)) m.c_pack += 1u;
-            else if (C.pure || !fast_event<MM>(m, e)) {
+            else if (!note_budget_ok(m) || C.pure || !fast_event<MM>(m, e)) {
                 stalled = true;                                 // planes are consumed in bit order:
                 rem = mine & ~(((mask_t)1 << p) - 1);           // p and up are left for the general kernel
                 atomicAdd(&C.counters[8 + (m_role(m) & 7u) * 16 + (R_type(e) & 15u)], 1ull);   // diagnostics
@@ -386,6 +386,7 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
                 const u32 p = __ffs(rem_mbox) - 1; rem_mbox &= rem_mbox - 1;
                 const Rec e = ld_rec_plane(C.mbox[cur], C.tiles, p, r);
                 if (MT_FATAL(m.meta)) m.c_pack += 1u;
+                else if (!note_budget_ok(m)) budget_drop_record(m);
                 else if (C.pure || !fast_event<MM>(m, e)) { process_event<MM>(m, e); m.cold &= ~8u; }
             }
 #pragma unroll 1
@@ -393,6 +394,7 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
                 const u32 p = __ffs(rem_loc) - 1; rem_loc &= rem_loc - 1;
                 const Rec e = ld_rec_plane(C.loc, C.tiles, p, r);
                 if (MT_FATAL(m.meta)) m.c_pack += 1u;
+                else if (!note_budget_ok(m)) budget_refuse_local(m);
                 else if (C.pure || !fast_event<MM>(m, e)) { process_event<MM>(m, e); m.cold &= ~8u; }
             }
             peers_writeback<MM>(m);
@@ -649,6 +651,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
     if (!cfg || !out || cfg->n_members < 1 || cfg->n_members > RA_MAX_MEMBERS || cfg->n_groups == 0) return RA_E_INVAL;
     if ((u64)cfg->n_groups * cfg->n_members > 0x7fffffffull) return RA_E_INVAL;
     if (cfg->n_shards > 1 && (!cfg->route_on_device || cfg->shard >= cfg->n_shards || cfg->n_shards > 64)) return RA_E_INVAL;
+    if (cfg->note_cap && (cfg->note_cap < RA_NOTE_RESERVE + 2 || cfg->note_cap > RA_NOTE_CAP)) return RA_E_INVAL;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev) return RA_E_NODEVICE;
     ra_engine* e = (ra_engine*)calloc(1, sizeof(ra_engine));
@@ -669,6 +672,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         C.groups_inv = cfg->n_groups > 1 ? (u32)(0x100000000ull / cfg->n_groups) : 0xFFFFFFFFu;
         C.max_pipeline = e->cfg.max_pipeline_count; C.max_batch = e->cfg.max_aer_batch;
         C.routed = cfg->route_on_device ? 1 : 0; C.pure = cfg->pure ? 1 : 0;
+        C.note_cap = cfg->note_cap ? cfg->note_cap : RA_NOTE_CAP;
         C.n_shards = cfg->n_shards > 1 ? cfg->n_shards : 1; C.shard = cfg->n_shards > 1 ? cfg->shard : 0;
         C.outbox = nullptr; C.out_cnt = nullptr; C.out_cap = 0;
         C.peer_mode = 0;

@@ -75,7 +75,8 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
         u64 ld = MT_LEADER(m.meta), vf = MT_VOTED(m.meta);
         u64 b = (vf == SLOT_NONE ? 0xFFull : vf) | ((ld == SLOT_NONE ? 0xFFull : ld) << 8) |
                 ((u64)((m.status >> 16) & 7u) << 16) | ((u64)MT_ROLE(m.meta) << 24);
-        note_store(m, m.n_notes, RA_NOTE_STATUS, m.slot, m.status & 0xffffu, m.term, b, (m.status >> 20) & 0xffu);
+        note_store(m, m.n_notes, RA_NOTE_STATUS, m.slot, m.status & 0xffffu, m.term, b,
+                   ((m.status >> 20) & 0xffu) | ((u64)(m.status >> 28) << 8));
         m.n_notes++;
         if (m.status & RA_ST_FATAL) fatal = 1;
     }

@@ -107,6 +107,7 @@ struct Cols {
     u32 groups_inv;        // floor(2^32 / groups)
     u32 max_pipeline, max_batch;
     u32 routed, pure;
+    u32 note_cap;          // notes per row per step (<= RA_NOTE_CAP), see note_budget_ok()
     // cross-shard transport (n_shards > 1): member (g, s) lives on shard (g + s) mod N at local
     // group index g div N, so a record from slot s to slot t of the same group always goes to
     // shard (shard + t - s) mod N and to the SAME local row index t * groups + q there.
@@ -259,7 +260,7 @@ struct Member {
     u64 term, commit, last_idx, last_term, lw_idx, lw_term, applied, meta;
     // outputs
     u32 n_msgs, n_notes;
-    u32 status;                 // RA_ST_* (bits 0-15) | role at the start of the step << 16 | fatal code << 20
+    u32 status;                 // RA_ST_* (bits 0-15) | role at the start of the step << 16 | fatal code << 20 | host events not consumed << 28
     u32 wk;                     // WAL_APPEND notes of this step: count (0..2) | index of the last << 4 | of the one before << 8
     u32 sent_to;                // 4 bits per peer slot: records put in (me -> slot) this step
     // one note kept back so that a continuing WAL_APPEND / APPLY can merge into it
@@ -569,11 +570,26 @@ __device__ __forceinline__ void note(Member& m, u32 type, u32 slot, u64 a, u64 b
 {
     if (m.pn_type == type && type == RA_NOTE_WAL_APPEND && m.pn_c == c && m.pn_b + 1 == a) { m.pn_b = b; return; }
     if (m.pn_type == type && type == RA_NOTE_APPLY && m.pn_b + 1 == a) { m.pn_b = b; return; }
-    if (m.n_notes >= RA_NOTE_CAP - 1) { m.status |= RA_ST_NOTE_OVERFLOW; return; }
+    if (m.n_notes >= m.C->note_cap - 1) {
+        // Cannot happen while an event stays within RA_NOTE_RESERVE notes (note_budget_ok is checked before every
+        // event); a burst of per-peer notes can exceed it.  Never lose a note silently: the row stops like a
+        // crashed server (the host reloads it from what it persisted).
+        m.status |= RA_ST_NOTE_OVERFLOW; set_fatal(m, RA_FATAL_NOTE_OVERFLOW); return;
+    }
     note_flush(m);
     m.n_notes++;
     m.pn_type = type; m.pn_slot = slot; m.pn_a = a; m.pn_b = b; m.pn_c = c;
 }
+
+// Note budget (include/ra_engine.h, RA_NOTE_RESERVE): a row takes the next event of its step only while
+// RA_NOTE_RESERVE slots + the STATUS slot are free.  Otherwise it stops for this step: mailbox records it has
+// not reached are dropped and counted like a full transport (Raft tolerates loss, the tick path re-sends),
+// host events are left unconsumed and reported (RA_ST_NOTE_OVERFLOW, STATUS.c bits 8..15).
+__device__ __forceinline__ bool note_budget_ok(const Member& m) { return m.n_notes + RA_NOTE_RESERVE + 1u <= m.C->note_cap; }
+__device__ __forceinline__ void budget_drop_record(Member& m)
+{ m.status |= RA_ST_NOTE_OVERFLOW | RA_ST_MSG_DROPPED; m.c_pack += 1u << 20; }
+__device__ __forceinline__ void budget_refuse_local(Member& m)
+{ m.status |= RA_ST_NOTE_OVERFLOW; m.status += 1u << 28; }          // bits 28..31: host events not consumed
 
 // send one RPC record to the member in `to` of my group
 template <int MM>

@@ -74,6 +74,7 @@ extern "C" int ra_emu_create(const ra_engine_cfg* cfg, ra_emu** out)
     C.groups_inv = cfg->n_groups > 1 ? (u32)(0x100000000ull / cfg->n_groups) : 0xFFFFFFFFu;
     C.max_pipeline = e->cfg.max_pipeline_count; C.max_batch = e->cfg.max_aer_batch;
     C.routed = cfg->route_on_device ? 1 : 0; C.pure = cfg->pure ? 1 : 0;
+    C.note_cap = cfg->note_cap ? cfg->note_cap : RA_NOTE_CAP;
     C.n_shards = cfg->n_shards > 1 ? cfg->n_shards : 1; C.shard = cfg->n_shards > 1 ? cfg->shard : 0;
     C.outbox = nullptr; C.out_cnt = nullptr; C.out_cap = 0;
     C.peer_mode = 0;
@@ -179,12 +180,14 @@ static void general_row(const Cols& C, int cur, const FloodArgs& F, const StallC
         const u32 p = __ffs(rem_mbox) - 1; rem_mbox &= rem_mbox - 1;
         const Rec e = ld_rec_plane(C.mbox[cur], C.tiles, p, r);
         if (MT_FATAL(m.meta)) m.c_pack += 1u;
+        else if (!note_budget_ok(m)) budget_drop_record(m);
         else if (C.pure || !fast_event<MM>(m, e)) { process_event<MM>(m, e); m.cold &= ~8u; }
     }
     while (rem_loc) {
         const u32 p = __ffs(rem_loc) - 1; rem_loc &= rem_loc - 1;
         const Rec e = ld_rec_plane(C.loc, C.tiles, p, r);
         if (MT_FATAL(m.meta)) m.c_pack += 1u;
+        else if (!note_budget_ok(m)) budget_refuse_local(m);
         else if (C.pure || !fast_event<MM>(m, e)) { process_event<MM>(m, e); m.cold &= ~8u; }
     }
     peers_writeback<MM>(m);
@@ -231,7 +234,7 @@ static bool step_row(const Cols& C, int cur, const FloodArgs& F, u32 r, StallCtx
         if (stalled) continue;
         const Rec e = p < NPM ? ld_rec_plane(C.mbox[cur], C.tiles, p, r) : ld_rec_plane(C.loc, C.tiles, p - NPM, r);
         if (MT_FATAL(m.meta)) m.c_pack += 1u;
-        else if (C.pure || !fast_event<MM>(m, e)) {
+        else if (!note_budget_ok(m) || C.pure || !fast_event<MM>(m, e)) {
             stalled = true;
             rem = mine & ~(((u64)1 << p) - 1);
             atomicAdd(&C.counters[8 + (m_role(m) & 7u) * 16 + (R_type(e) & 15u)], 1ull);
