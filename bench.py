@@ -285,30 +285,19 @@ def run_engine(args):
                 torch.cuda.synchronize(dev)
                 return dict(seconds=time.perf_counter() - t_0, h2d_bytes=h2d, d2h_bytes=d2h)
         else:
-            # K independent engines (disjoint groups) driven from K host threads: while one engine's notes
-            # travel device->host and its host model runs, another engine's events travel host->device
-            # (PCIe is full duplex) and its kernels run.  Every step still goes through ra_engine_step.
-            import threading
+            # K engines (disjoint sets of groups) driven by ONE host thread through the split-phase calls
+            # ra_engine_submit_host / ra_engine_collect: while the notes of one partition travel device->host and
+            # its host model runs, another partition's batch travels host->device and its kernels run.  Every
+            # step of every partition still goes through the public C ABI with host buffers.
             K = max(1, min(args.e2e_engines, G))
             engs = [Engine(G // K + (1 if i < G % K else 0), M, device=dev, route_on_device=True) for i in range(K)]
-            hfs = [HostFlood(e_) for e_ in engs]
-            for e_, h_ in zip(engs, hfs):
+            for e_ in engs:
                 e_.reset_empty()
-                h_.run(0, args.cmds, args.permille, seed=seed, bootstrap=True)
+            hf = HostFlood(engs)
+            hf.run(0, args.cmds, args.permille, seed=seed, bootstrap=True)
 
             def host_steps(n):
-                res = [None] * K
-                def work(i):
-                    res[i] = hfs[i].run(n, args.cmds, args.permille, seed=seed + i)
-                t_0 = time.perf_counter()
-                ths = [threading.Thread(target=work, args=(i,)) for i in range(K)]
-                for t_ in ths: t_.start()
-                for t_ in ths: t_.join()
-                wall = time.perf_counter() - t_0
-                return dict(seconds=wall, h2d_bytes=sum(r_["h2d_bytes"] for r_ in res),
-                            d2h_bytes=sum(r_["d2h_bytes"] for r_ in res),
-                            step_seconds=max(r_["step_seconds"] for r_ in res),
-                            model_seconds=max(r_["model_seconds"] for r_ in res))
+                return hf.run(n, args.cmds, args.permille, seed=seed)
 
             class _Multi:                                   # counters / close over all K engines
                 def counters(self):
@@ -320,11 +309,6 @@ def run_engine(args):
                 def close(self):
                     for e_ in engs: e_.close()
             eng2 = _Multi()
-
-            class _MultiHf:
-                def close(self):
-                    for h_ in hfs: h_.close()
-            hf = _MultiHf()
         host_steps(args.settle)
         host_steps(min(args.warmup, 10))
         d0 = eng2.counters()
@@ -339,7 +323,7 @@ def run_engine(args):
                "steps": args.e2e_steps, "ms_per_step": sec * 1e3 / args.e2e_steps,
                "engine_call_ms_per_step": st.get("step_seconds", 0.0) * 1e3 / args.e2e_steps,
                "host_model_ms_per_step": st.get("model_seconds", 0.0) * 1e3 / args.e2e_steps,
-               "gpu_launches_per_step": (7 + 3) if spread else 7 * max(1, min(args.e2e_engines, G)),
+               "gpu_launches_per_step": (6 + 1) if spread else 6 * max(1, min(args.e2e_engines, G)),
                "engines": 1 if spread else max(1, min(args.e2e_engines, G))}
         hf.close()
         eng2.close()
@@ -468,8 +452,9 @@ def main():
     ap.add_argument("--settle", type=int, default=40, help="untimed steps to elect leaders and fill the pipeline")
     ap.add_argument("--seed", type=int, default=0xA00)
     ap.add_argument("--e2e-steps", type=int, default=30)
-    ap.add_argument("--e2e-engines", type=int, default=1,
-                    help="e2e leg at N=1: independent engines (disjoint groups) driven by as many host threads")
+    ap.add_argument("--e2e-engines", type=int, default=4,
+                    help="e2e leg at N=1: partitions (engines holding disjoint groups) one host thread pipelines "
+                         "through ra_engine_submit_host / ra_engine_collect")
     ap.add_argument("--cpu-groups", type=int, default=50_000)
     ap.add_argument("--cpu-steps", type=int, default=300)
     ap.add_argument("--placement", default="spread", choices=["spread", "group"],

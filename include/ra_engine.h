@@ -288,7 +288,8 @@ enum ra_status {
     RA_E_CUDA = -3,       /* CUDA runtime error, see ra_engine_strerror     */
     RA_E_UNGROUPED = -4,  /* events of one row are not adjacent in the batch */
     RA_E_CAPACITY = -5,   /* more than RA_LOCAL_CAP events for one row, or out buffers too small */
-    RA_E_NODEVICE = -6
+    RA_E_NODEVICE = -6,
+    RA_E_BUSY = -7        /* submit/collect: no free slot, or a submitted batch is still to be collected */
 };
 
 /* Lifecycle.  The engine owns the HBM Struct-of-Arrays; callers own all host buffers and
@@ -341,6 +342,19 @@ int  ra_engine_step(ra_engine* e,
                     const ra_event* ev, size_t n_ev,
                     ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
                     ra_note*  notes, size_t notes_cap, size_t* n_notes);
+
+/*
+ * Capacity.  A row emits at most RA_MSG_CAP records and RA_NOTE_CAP notes per step, and rows WITHOUT an
+ * event in the batch can emit too (a deferred pipeline pass, mailbox records in route_on_device mode), so
+ * n_ev * CAP is not a bound -- rows * CAP is.  A call whose outputs exceed msgs_cap / notes_cap returns
+ * RA_E_CAPACITY with *n_msgs / *n_notes = the sizes needed; the step HAS been evaluated and nothing is lost:
+ * the outputs stay in the engine until ra_engine_fetch_output takes them (no other step call is accepted
+ * before that).  RA_E_CAPACITY for more than RA_LOCAL_CAP events of one row, RA_E_UNGROUPED and RA_E_INVAL
+ * (bad row / type) reject the whole batch: no row has changed.
+ */
+int  ra_engine_pending_output(ra_engine* e, size_t* n_msgs, size_t* n_notes);
+int  ra_engine_fetch_output(ra_engine* e, ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                            ra_note* notes, size_t notes_cap, size_t* n_notes);
 
 /*
  * Benchmark transport + synthetic host, all on the device (no host copies):
@@ -412,6 +426,28 @@ int  ra_engine_step_host(ra_engine* e, const ra_host_event* ev, size_t n_ev,
                          ra_note* notes, size_t notes_cap, size_t* n_notes);
 
 /*
+ * Split-phase form of ra_engine_step[_host].  submit enqueues the whole call -- host->device copy of the
+ * batch, the kernels, and the write-back of the outputs, which the last kernel stores straight into the
+ * caller's buffers when they are pinned (ra_engine_alloc_host / ra_engine_register_host; into an internal
+ * pinned staging area otherwise) -- and returns without waiting; collect waits for the OLDEST submitted call
+ * and returns its status and output counts.  Up to two calls may be in flight per engine (the copy of batch
+ * t+1 overlaps the kernels and the output of batch t); RA_E_BUSY beyond that.  The buffers of a submitted call
+ * (ev, msgs, notes) belong to the engine until it is collected.  With several engines (disjoint sets of
+ * groups) one host thread keeps all of them busy: submit to each, then collect each.
+ * If a batch is rejected (ungrouped / capacity / bad row), collect returns the error, no row has changed, and
+ * every call submitted behind it is rejected with the same status.
+ */
+int  ra_engine_submit(ra_engine* e, const ra_event* ev, size_t n_ev,
+                      ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap);
+int  ra_engine_submit_host(ra_engine* e, const ra_host_event* ev, size_t n_ev,
+                           ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap);
+int  ra_engine_collect(ra_engine* e, size_t* n_msgs, size_t* n_notes);
+/* pin + map caller-owned host memory once (cudaHostRegister), e.g. a NIF's resource buffers */
+int  ra_engine_register_host(void* p, size_t bytes);
+int  ra_engine_unregister_host(void* p);
+
+
+/*
  * Written-event source: ra_log_wal:complete_batch/1 (src/ra_log_wal.erl:784-808) tells every
  * writer of a WAL batch {ra_log_event, {written, Term, Seq}} with Seq a ra_seq (src/ra_seq.erl: ascending
  * indexes and {From, To} ranges).  ra_wal_batch_to_events turns one batch -- an array of writers -- into the
@@ -442,6 +478,9 @@ size_t ra_wal_batch_to_events(const ra_wal_writer* writers, size_t n_writers, ui
  */
 typedef struct ra_hostsim ra_hostsim;
 int  ra_hostsim_create(ra_engine* e, ra_hostsim** out);
+/* the same over K engines holding disjoint sets of groups (partition p runs the model with seed + p): one
+   host thread keeps all of them busy through ra_engine_submit_host / ra_engine_collect */
+int  ra_hostsim_create_multi(ra_engine* const* engines, uint32_t n, ra_hostsim** out);
 void ra_hostsim_destroy(ra_hostsim* s);
 /* bootstrap != 0: first send election_timeout to slot 0 of every group (ra:trigger_election) */
 int  ra_hostsim_run(ra_hostsim* s, uint32_t n_steps, uint32_t cmds_per_step,

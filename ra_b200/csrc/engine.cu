@@ -9,6 +9,7 @@
 // RA_E_NODEVICE and nothing else works.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -27,11 +28,6 @@
 #ifndef MINB
 #define MINB 5                              // CTAs per SM the register allocation is held to: 20 warps,
                                             // <= 96 registers (no spills), 5 x 39 KB of shared memory
-#endif
-#ifdef RA_RING_1K
-#ifndef NSLOT
-#define NSLOT 6                             // RA_RING_1K: 1 KB ring slots per warp (experimental, see NOTES_r2_prep.md)
-#endif
 #endif
 #define TILE_BYTES (RT * 64)
 #define RA_BAR_WORDS 64                       // barrier flag words behind mbox_cnt[b] (one per source shard)
@@ -79,18 +75,10 @@ __device__ __forceinline__ void tma_load_tile(void* dst_smem, const void* src_gm
 //   peers[3][8][128] x 8 B           per-thread peer columns (next, match, commit_index_sent), lazy
 template <int MM>
 struct StepSmem {
-#ifdef RA_RING_1K
-    ulonglong2 stage[WARPS][NSLOT][2 * RT];  // 1 KB slots: a tile's heads in one slot, its tails (if any) in the next
-#else
     ulonglong2 stage[WARPS][NST][4 * RT];
-#endif
     ulonglong2 peers_nm[PSTR * CTA_T];       // [s][thread] {next_index, match_index}
     u64 peers_cs[PSTR * CTA_T];              // [s][thread] commit_index_sent (directly behind peers_nm)
-#ifdef RA_RING_1K
-    u64 bars[WARPS][NSLOT];
-#else
     u64 bars[WARPS][NST];
-#endif
 };
 
 // ---- the two kernels of a step ---------------------------------------------------------------
@@ -106,7 +94,7 @@ __device__ __forceinline__ void flush_counters(const Cols& C, u32 lane, u32 k_ev
                                                u32 k_msgs, u32 k_dropped, u32 k_elect, u32 k_fatal)
 {
     // per-launch device counters: one REDUX per counter, one atomic per warp and counter that moved
-    if (__any_sync(0xffffffffu, (k_events | k_fatal) != 0)) {
+    if (__any_sync(0xffffffffu, (k_events | k_fatal | k_dropped | k_msgs) != 0)) {
         k_events = __reduce_add_sync(0xffffffffu, k_events); k_commits = __reduce_add_sync(0xffffffffu, k_commits);
         k_applied = __reduce_add_sync(0xffffffffu, k_applied); k_msgs = __reduce_add_sync(0xffffffffu, k_msgs);
         k_dropped = __reduce_add_sync(0xffffffffu, k_dropped); k_elect = __reduce_add_sync(0xffffffffu, k_elect);
@@ -160,7 +148,18 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StepSmem<MM>& S = *reinterpret_cast<StepSmem<MM>*>(smem_raw);
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+#ifdef RA_INTERLEAVE
+    // CTAs are handed their tiles slot-interleaved: consecutive CTAs work on different slots' row ranges, so that
+    // the long-running warps of one kind of row (a slot full of leaders) are spread over the whole launch
+    // instead of filling its first wave.  (grid = per * members CTAs, see launch_step)
+    u32 wtile;
+    {
+        const u32 k = C.members, per = gridDim.x / k;
+        wtile = ((blockIdx.x % k) * per + blockIdx.x / k) * WARPS + warp;
+    }
+#else
     const u32 wtile = blockIdx.x * WARPS + warp;                 // this warp's record tile
+#endif
     const u32 r = wtile * RT + lane;
     const bool valid = r < C.rows;
     u32 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
@@ -178,6 +177,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         if (C.routed) cntw = C.mbox_cnt[cur][r];
         tc = C.tc[r]; lg = C.lg[r]; lw = C.lw[r]; lrs = C.lrs[r];
     }
+    if (*C.abort) return;                                       // a host batch was rejected: nothing may change
     const bool fatal0 = MT_FATAL(ap.y) != 0;
     const bool pending = valid && MT_PIPE_PEND(ap.y) != 0;
     // planes of this row: mailbox plane (sender s, depth k) = bit s * DEPTH + k, host slot k = bit NPM + k
@@ -202,11 +202,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     if (!__any_sync(0xffffffffu, work)) return;                 // whole warp idle
     u64* bars = &S.bars[warp][0];
     if (lane == 0) {
-#ifdef RA_RING_1K
-        for (int i = 0; i < NSLOT; i++) mbar_init(&bars[i], 1);
-#else
         for (int i = 0; i < NST; i++) mbar_init(&bars[i], 1);
-#endif
         mbar_fence_init();
     }
     __syncwarp();
@@ -226,58 +222,6 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     if (work && !fatal0 && pending) {                           // pipeline_rpcs is not a fast path
         stalled = true; stall_flags = STALL_PENDING; rem = mine;
     }
-#ifdef RA_RING_1K
-    // ---- experimental ring of NSLOT 1 KB slots: a tile takes one slot (heads) or two (heads, tails) ----
-    mask_t toissue = todo;
-    u32 si = 0, hd = 0, nfree = NSLOT, par = 0;                 // issue / consume positions, free slots, phase bits
-    const size_t plane_words = (size_t)C.tiles * (4 * RT);
-    const ulonglong2* const mb_base = C.mbox[cur] + (size_t)wtile * (4 * RT);
-    const ulonglong2* const lc_base = C.loc + (size_t)wtile * (4 * RT) - (size_t)NPM * plane_words;
-#pragma unroll 1
-    while (todo) {
-        if (lane == 0) {
-#pragma unroll 1
-            while (toissue) {
-                const u32 q = mask_ffs(toissue);
-                const u32 tbit = q < NPM ? q / RA_MBOX_DEPTH : 8u + q - NPM;
-                const u32 need = 1u + ((w_tail >> tbit) & 1u);
-                if (nfree < need) break;
-                toissue &= toissue - 1;
-                const ulonglong2* src = (q < NPM ? mb_base : lc_base) + (size_t)q * plane_words;
-                fence_proxy_async();                            // the slots were read through the generic proxy
-                mbar_expect_tx(&bars[si], need * (TILE_BYTES / 2));
-                tma_load_tile(&S.stage[warp][si][0], src, TILE_BYTES / 2, &bars[si]);
-                const u32 s2 = si + 1 == NSLOT ? 0 : si + 1;
-                if (need == 2) tma_load_tile(&S.stage[warp][s2][0], src + 2 * RT, TILE_BYTES / 2, &bars[si]);
-                si = need == 2 ? (s2 + 1 == NSLOT ? 0 : s2 + 1) : s2;
-                nfree -= need;
-            }
-        }
-        const u32 p = mask_ffs(todo); todo &= todo - 1;
-        const u32 pbit = p < NPM ? p / RA_MBOX_DEPTH : 8u + p - NPM;
-        const u32 need = 1u + ((w_tail >> pbit) & 1u);
-        const u32 h2 = hd + 1 == NSLOT ? 0 : hd + 1;
-        const bool my = !stalled && ((mine >> p) & 1u);
-        mbar_wait(&bars[hd], (par >> hd) & 1u);
-        if (my) {
-            const ulonglong2* sp = &S.stage[warp][hd][0];
-            const ulonglong2 c0 = sp[lane], c1 = sp[RT + lane];
-            ulonglong2 t2 = make_ulonglong2(0, 0), t3 = t2;
-            if (rec_has_tail(c0)) { const ulonglong2* tp = &S.stage[warp][h2][0]; t2 = tp[lane]; t3 = tp[RT + lane]; }
-            const Rec e = rec_decode(c0, c1, t2, t3, r);
-            if (MT_FATAL(m.meta)) m.c_pack += 1u;
-            else if (!note_budget_ok(m) || C.pure || !fast_event<MM>(m, e)) {
-                stalled = true;
-                rem = mine & ~(((mask_t)1 << p) - 1);
-                atomicAdd(&C.counters[8 + (m_role(m) & 7u) * 16 + (R_type(e) & 15u)], 1ull);
-            }
-        }
-        par ^= 1u << hd;                                        // this slot's barrier completed one more phase
-        hd = need == 2 ? (h2 + 1 == NSLOT ? 0 : h2 + 1) : h2;
-        nfree += need;                                          // (only lane 0 uses it)
-        __syncwarp();                                           // every lane is done with the slot(s)
-    }
-#else
     mask_t toissue = todo;                                      // planes still to request
     u32 n_issued = 0, n_done = 0, st_issue = 0, st = 0, par = 0; // ring positions = counters mod NST, phase parity
     const size_t plane_words = (size_t)C.tiles * (4 * RT);      // 16-byte words per plane
@@ -318,7 +262,6 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         if (++st == NST) { st = 0; par ^= 1u; }
         __syncwarp();                                           // every lane is done with the slot
     }
-#endif
     const u32 rem_mbox = (u32)(rem & (((mask_t)1 << (NPM - 1) << 1) - 1)), rem_loc = (u32)(rem >> (NPM - 1) >> 1);
 
     if (work) {
@@ -359,6 +302,7 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
     constexpr int MM = MK_MM(0, TR_RUNTIME);
     __shared__ ulonglong2 s_peers[RA_MAX_MEMBERS * CTA_T + RA_MAX_MEMBERS * CTA_T / 2];   // nm[8][T] then cs[8][T]
     const u32 tid = threadIdx.x, lane = tid & 31u;
+    if (*C.abort) return;
     const u32 n = *stall_count;
     for (u32 base = blockIdx.x * CTA_T; base < n; base += gridDim.x * CTA_T) {
         const u32 i = base + tid;
@@ -445,10 +389,10 @@ __global__ void read_query_kernel(const Cols C, ra_query_state* out, u32 n)
 }
 
 // flat host batch -> per-row local slots.  err[0]: 1 = ungrouped, 2 = too many for a row, 3 = bad row
-__global__ void ingest_kernel(const Cols C, const ra_event* ev, u32 n, u32* err)
+__global__ void ingest_kernel(const Cols C, const ra_event* ev, u32 n, u32* err, const u32* sticky)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || *sticky) return;
     const u32 row = ev[i].row;
     if (row >= C.rows) { atomicMax(err, 3u); return; }
     if (i > 0 && ev[i - 1].row == row) return;                 // not the head of its run
@@ -468,10 +412,10 @@ __device__ __forceinline__ bool host_event_type_ok(u32 t)
     return t == RA_EV_WRITTEN || t == RA_EV_COMMAND || t == RA_EV_ELECTION_TIMEOUT || t == RA_EV_AWAIT_COND_TIMEOUT ||
            t == RA_EV_PIPELINE_RPCS || t == RA_EV_TICK || t == RA_EV_CONSISTENT_QUERY;
 }
-__global__ void ingest_host_kernel(const Cols C, const ra_host_event* ev, u32 n, u32* err)
+__global__ void ingest_host_kernel(const Cols C, const ra_host_event* ev, u32 n, u32* err, const u32* sticky)
 {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || *sticky) return;
     const u32 row = ev[i].row;
     if (row >= C.rows || !host_event_type_ok(ev[i].type)) { atomicMax(err, 3u); return; }
     if (i > 0 && ev[i - 1].row == row) return;                 // not the head of its run
@@ -507,32 +451,75 @@ __global__ void clear_loc_kernel(const Cols C)
     if (r < C.rows) C.loc_n[r] = 0;
 }
 
-// per-row slots -> flat (row, seq)-ordered arrays; offs = exclusive scan of out_n packed as
-// msgs | notes << 32
-__global__ void pack_counts_kernel(const Cols C, u64* packed)
+// ---- per-row output slots -> the caller's flat (row, seq)-ordered arrays ------------------------------
+// offs = exclusive scan over the rows of out_n unpacked to msgs | notes << 32 (cub, through a transform
+// iterator: no separate pass); offs[rows] = the totals.
+struct PackCounts {
+    __host__ __device__ __forceinline__ u64 operator()(const u32& v) const
+    { return (u64)(v & 0xffffu) | ((u64)(v >> 16) << 32); }
+};
+typedef cub::TransformInputIterator<u64, PackCounts, const u32*> PackedIt;
+
+// What the host reads when a call completes (pinned, mapped: written by gather_out_kernel itself, so a
+// call needs no device->host copy whose size the host would first have to learn).
+struct OutHdr { u64 n_msgs, n_notes; u32 status, _pad; };     // status: ingest error 1..3 | 0x100 = outputs do not fit
+
+// One warp per tile of 32 rows.  The warp's notes (and records) occupy one contiguous range of the output;
+// a small table in shared memory maps every output position to (lane, k), then the range is written in
+// 16-byte chunks, lane-consecutive: every store instruction of the warp is one contiguous 512-byte burst,
+// which is what makes writing straight into HOST memory (PCIe posted writes) efficient.
+// When the totals do not fit the caller's buffers (or the batch was rejected) nothing is written and the
+// per-row slots are left alone, so that ra_engine_fetch_output can gather again.
+__global__ void __launch_bounds__(128)
+gather_out_kernel(const Cols C, const u64* __restrict__ offs, ulonglong2* __restrict__ msgs, const u64 msgs_cap,
+                  ulonglong2* __restrict__ notes, const u64 notes_cap, OutHdr* hdr, const u32* err)
 {
-    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= C.rows) return;
-    const u32 v = C.out_n[r];
-    packed[r] = (u64)(v & 0xffffu) | ((u64)(v >> 16) << 32);
-}
-__global__ void gather_kernel(const Cols C, const u64* offs, ra_event* msgs, u64 msgs_cap, ra_note* notes, u64 notes_cap)
-{
-    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= C.rows) return;
-    const u32 v = C.out_n[r];
-    if (!v) return;
-    C.out_n[r] = 0;
-    const u32 nm = v & 0xffffu, nn = v >> 16;
-    const u64 om = offs[r] & 0xffffffffull, on = offs[r] >> 32;
-    for (u32 k = 0; k < nm; k++)
-        if (om + k < msgs_cap) st_rec(&msgs[om + k], ld_rec(&C.omsg[(size_t)k * C.rows + r]));
-    for (u32 k = 0; k < nn; k++)
-        if (on + k < notes_cap) {
-            const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&C.onote[(size_t)k * C.rows + r]);
-            ulonglong2* d = reinterpret_cast<ulonglong2*>(&notes[on + k]);
-            d[0] = q[0]; d[1] = q[1];
+    __shared__ unsigned short tab[4][32 * (RA_NOTE_CAP > RA_MSG_CAP ? RA_NOTE_CAP : RA_MSG_CAP)];
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u32 tile = blockIdx.x * 4 + warp;
+    const u64 total = offs[C.rows];
+    const u64 tm = total & 0xffffffffull, tn = total >> 32;
+    const u32 bad = *err;
+    const bool fits = tm <= msgs_cap && tn <= notes_cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        hdr->n_msgs = tm; hdr->n_notes = tn; hdr->status = bad | (fits ? 0u : 0x100u);
+    }
+    if (bad || !fits) return;
+    const u32 r = tile * 32 + lane;
+    const bool valid = r < C.rows;
+    const u32 v = valid ? C.out_n[r] : 0u;
+    if (!__any_sync(0xffffffffu, v != 0)) return;
+    const u64 off = offs[valid ? r : C.rows];
+    if (v) C.out_n[r] = 0;
+    unsigned short* t = tab[warp];
+    {   // notes: 2 chunks each
+        const u32 nn = v >> 16;
+        const u64 on = off >> 32;
+        const u64 base = __shfl_sync(0xffffffffu, on, 0);
+        const u32 cnt = (u32)(__shfl_sync(0xffffffffu, on + nn, 31) - base);
+        for (u32 k = 0; k < nn; k++) t[(u32)(on - base) + k] = (unsigned short)((lane << 4) | k);
+        __syncwarp();
+        for (u32 c = lane; c < 2 * cnt; c += 32) {
+            const u32 ent = t[c >> 1];
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(&C.onote[(size_t)(ent & 15u) * C.rows + tile * 32 + (ent >> 4)]);
+            notes[(base << 1) + c] = src[c & 1u];
         }
+        __syncwarp();
+    }
+    {   // RPC records: 4 chunks each
+        const u32 nm = v & 0xffffu;
+        const u64 om = off & 0xffffffffull;
+        const u64 base = __shfl_sync(0xffffffffu, om, 0);
+        const u32 cnt = (u32)(__shfl_sync(0xffffffffu, om + nm, 31) - base);
+        if (cnt == 0) return;
+        for (u32 k = 0; k < nm; k++) t[(u32)(om - base) + k] = (unsigned short)((lane << 4) | k);
+        __syncwarp();
+        for (u32 c = lane; c < 4 * cnt; c += 32) {
+            const u32 ent = t[c >> 2];
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(&C.omsg[(size_t)(ent & 15u) * C.rows + tile * 32 + (ent >> 4)]);
+            msgs[(base << 2) + c] = src[c & 3u];
+        }
+    }
 }
 
 // Step barrier of the peer transport without a collective: every shard release-stores the step's
@@ -560,21 +547,35 @@ __global__ void peer_barrier_kernel(const Cols C, const u64 epoch, u32* err)
 // ------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------
+// one host call in flight (ra_engine_submit .. ra_engine_collect); RA_IO_SLOTS of them per engine
+#define RA_IO_SLOTS 2
+struct IoSlot {
+    int busy;
+    void* d_ev; size_t d_ev_bytes;            // device copy of the call's events
+    OutHdr* hdr;                              // pinned + mapped
+    cudaEvent_t h2d_done, done;
+    // where gather_out_kernel writes: the caller's buffers when they are pinned (ra_engine_alloc_host /
+    // ra_engine_register_host), else the slot's own pinned staging, copied out by ra_engine_collect
+    ra_event* user_msgs; ra_note* user_notes; size_t msgs_cap, notes_cap;
+    ra_event* st_msgs; size_t st_msgs_cap; ra_note* st_notes; size_t st_notes_cap;
+    int staged_msgs, staged_notes;
+};
+
 struct ra_engine {
     ra_engine_cfg cfg;
     Cols C;
     cudaStream_t stream; int own_stream;
+    cudaStream_t copy_stream;                 // host -> device copies of submitted batches
     cudaEvent_t ev0, ev1;
     int cur;
     u64 step_no, steps;
     u64 bar_epoch;                            // peer transport: barriers passed since the last reset
     void* allocs[64]; int n_allocs;
-    // staging
-    ra_event* d_ev; size_t d_ev_cap;
-    ra_event* d_msgs; size_t d_msgs_cap;
-    ra_note* d_notes; size_t d_notes_cap;
-    u64 *d_packed, *d_offs; void* d_scan_tmp; size_t scan_tmp_bytes;
-    u32* d_err;
+    IoSlot io[RA_IO_SLOTS]; u32 io_head, io_tail;   // FIFO: submit fills io[io_head % SLOTS], collect drains io_tail
+    int out_pending;                          // the last collect ended in RA_E_CAPACITY: outputs wait in the row slots
+    int loc_dirty;                            // the flood host model may have left host events queued
+    u64* d_offs; void* d_scan_tmp; size_t scan_tmp_bytes;
+    u32* d_err;                               // [0] sticky ingest error (= Cols::abort), [1] peer barrier timeout
     StallCtx* d_stall; u32* d_stall_cnt;      // d_stall_cnt[2]: alternating per step
     ra_row_state* d_rows; size_t d_rows_cap;
     float last_ms; u32 last_launches;
@@ -613,6 +614,7 @@ extern "C" const char* ra_engine_strerror(int st)
     case RA_E_UNGROUPED: return "events of one row are not adjacent in the batch";
     case RA_E_CAPACITY: return "capacity exceeded (RA_LOCAL_CAP per row, or output buffers too small)";
     case RA_E_NODEVICE: return "no CUDA device: the engine has no CPU fallback";
+    case RA_E_BUSY: return "a submitted batch has not been collected yet (or both submit slots are in flight)";
     default: return "unknown status";
     }
 }
@@ -625,8 +627,18 @@ extern "C" void ra_engine_destroy(ra_engine* e)
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     for (int i = 0; i < e->n_allocs; i++) cudaFree(e->allocs[i]);
-    cudaFree(e->d_ev); cudaFree(e->d_msgs); cudaFree(e->d_notes); cudaFree(e->d_rows); cudaFree(e->d_scan_tmp);
+    cudaFree(e->d_rows); cudaFree(e->d_scan_tmp);
+    for (int i = 0; i < RA_IO_SLOTS; i++) {
+        IoSlot& q = e->io[i];
+        cudaFree(q.d_ev);
+        if (q.hdr) cudaFreeHost(q.hdr);
+        if (q.st_msgs) cudaFreeHost(q.st_msgs);
+        if (q.st_notes) cudaFreeHost(q.st_notes);
+        if (q.h2d_done) cudaEventDestroy(q.h2d_done);
+        if (q.done) cudaEventDestroy(q.done);
+    }
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->stream);
     free(e);
 }
@@ -643,6 +655,8 @@ extern "C" int ra_engine_reset_empty(ra_engine* e)
     if (e->C.routed) CK(cudaMemsetAsync(e->C.mbox_cnt[0] + e->C.rows, 0, RA_BAR_WORDS * sizeof(u64), e->stream));
     CK(cudaMemsetAsync(e->d_err, 0, 4 * sizeof(u32), e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < RA_IO_SLOTS; i++) e->io[i].busy = 0;
+    e->io_head = e->io_tail = 0; e->out_pending = 0; e->loc_dirty = 0;
     return RA_OK;
 }
 
@@ -664,7 +678,15 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
     if ((ce = cudaSetDevice(cfg->device)) != cudaSuccess) { rc = fail(e, ce, "cudaSetDevice"); goto bad; }
     if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail(e, ce, "cudaStreamCreate"); goto bad; }
     e->own_stream = 1;
+    if ((ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail(e, ce, "cudaStreamCreate"); goto bad; }
     cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
+    for (int i = 0; i < RA_IO_SLOTS; i++) {
+        IoSlot& q = e->io[i];
+        if ((ce = cudaHostAlloc((void**)&q.hdr, sizeof(OutHdr), cudaHostAllocMapped | cudaHostAllocPortable)) != cudaSuccess) { rc = fail(e, ce, "cudaHostAlloc"); goto bad; }
+        memset(q.hdr, 0, sizeof(OutHdr));
+        cudaEventCreateWithFlags(&q.h2d_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming);
+    }
     {
         Cols& C = e->C;
         const size_t R = (size_t)cfg->n_groups * cfg->n_members, M = cfg->n_members;
@@ -684,7 +706,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         C.tiles = (u32)((R + RT - 1) / RT);
         const size_t PW = (size_t)C.tiles * 4 * RT;             // 16-byte words per tiled plane
         DA(C.loc, (size_t)RA_LOCAL_CAP * PW); DA(C.loc_n, R);
-        DA(C.onote, (size_t)RA_NOTE_CAP * R); DA(C.out_n, R); DA(C.counters, RA_N_COUNTERS);
+        DA(C.onote, (size_t)RA_NOTE_CAP * R); DA(C.out_n, R + 1); DA(C.counters, RA_N_COUNTERS);   // out_n[R] stays 0: the scan's total
         if (C.routed) {
             // + RA_BAR_WORDS: the peer transport's step barrier flags live behind the counts of buffer 0,
             // so they are covered by the IPC mapping the peers already have
@@ -694,17 +716,19 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
             C.mbox[0] = C.mbox[1] = nullptr; C.mbox_cnt[0] = C.mbox_cnt[1] = nullptr;
             DA(C.omsg, (size_t)RA_MSG_CAP * R);
         }
-        DA(e->d_packed, R + 1); DA(e->d_offs, R + 1); DA(e->d_err, 4);
+        DA(e->d_offs, R + 1); DA(e->d_err, 4);
         DA(e->d_stall, R); DA(e->d_stall_cnt, 4);
 #undef DA
+        C.abort = e->d_err;
         e->scan_tmp_bytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp_bytes, e->d_packed, e->d_offs, (int)(R + 1), e->stream);
+        cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp_bytes, PackedIt(C.out_n, PackCounts()), e->d_offs, (int)(R + 1), e->stream);
         if ((ce = cudaMalloc(&e->d_scan_tmp, e->scan_tmp_bytes ? e->scan_tmp_bytes : 16)) != cudaSuccess) { rc = fail(e, ce, "cudaMalloc scan"); goto bad; }
     }
 #define SMEM_ATTR(MEMB, TRN) \
     if ((ce = cudaFuncSetAttribute(raft_step_kernel<MK_MM(MEMB, TRN)>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)sizeof(StepSmem<MK_MM(MEMB, TRN)>))) != cudaSuccess) { rc = fail(e, ce, "cudaFuncSetAttribute"); goto bad; }
     SMEM_ATTR(0, TR_RUNTIME) SMEM_ATTR(5, TR_LOCAL) SMEM_ATTR(5, TR_PEER) SMEM_ATTR(5, TR_BUCKET) SMEM_ATTR(5, TR_HOST)
+    SMEM_ATTR(3, TR_LOCAL) SMEM_ATTR(7, TR_LOCAL)
 #undef SMEM_ATTR
     {
         int sms = 148;
@@ -797,7 +821,11 @@ static int launch_step(ra_engine* e, const FloodArgs& F)
             if (c0 != cudaSuccess) return fail(e, c0, "cudaMemsetAsync out_cnt");
         }
     }
+#ifdef RA_INTERLEAVE
+    const u32 grid = (((e->C.tiles + WARPS - 1) / WARPS + e->C.members - 1) / e->C.members) * e->C.members;
+#else
     const u32 grid = (e->C.tiles + WARPS - 1) / WARPS;
+#endif
     u32* cnt = e->d_stall_cnt + (e->steps & 1), *cnt_next = e->d_stall_cnt + ((e->steps + 1) & 1);
     // one specialisation of the hot kernel per (member count, transport): see MK_MM
     const int tr = !e->C.routed ? TR_HOST : (e->C.n_shards > 1 ? (e->C.peer_mode ? TR_PEER : TR_BUCKET) : TR_LOCAL);
@@ -810,6 +838,10 @@ static int launch_step(ra_engine* e, const FloodArgs& F)
         case TR_BUCKET: LAUNCH(5, TR_BUCKET); break;
         default:        LAUNCH(5, TR_HOST); break;
         }
+    } else if (e->C.members == 3 && tr == TR_LOCAL) {
+        LAUNCH(3, TR_LOCAL);
+    } else if (e->C.members == 7 && tr == TR_LOCAL) {
+        LAUNCH(7, TR_LOCAL);
     } else {
         LAUNCH(0, TR_RUNTIME);
     }
@@ -824,68 +856,202 @@ static int launch_step(ra_engine* e, const FloodArgs& F)
     return RA_OK;
 }
 
+// ---- one batch through the engine: submit (everything enqueued, nothing waited for) .. collect ---------
+// stream order of one call:   [copy stream] H2D events  ->  [engine stream] ingest -> raft_step -> raft_general
+//   -> scan of the per-row output counts -> gather_out (writes records, notes and the totals into HOST memory)
+// There is no synchronisation inside a call and no device->host copy issued by the host: the one wait is
+// ra_engine_collect's on the call's `done` event.
+static bool host_ptr_mapped(const void* p, void** dev)
+{
+    cudaPointerAttributes a;
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+    *dev = a.devicePointer;
+    return true;
+}
+
+template <typename T>
+static int ensure_pinned(ra_engine* e, T** p, size_t* cap, size_t need)
+{
+    if (*cap >= need && *p) return RA_OK;
+    if (*p) cudaFreeHost(*p);
+    void* q = nullptr;
+    const size_t nc = need < 1024 ? 1024 : need + need / 4;
+    cudaError_t ce = cudaHostAlloc(&q, nc * sizeof(T), cudaHostAllocMapped | cudaHostAllocPortable);
+    if (ce != cudaSuccess) { *p = nullptr; *cap = 0; return fail(e, ce, "cudaHostAlloc staging"); }
+    *p = (T*)q; *cap = nc;
+    return RA_OK;
+}
+
+static int enqueue_gather(ra_engine* e, IoSlot& q)
+{
+    void *dm = nullptr, *dn = nullptr;
+    int rc;
+    q.staged_msgs = q.staged_notes = 0;
+    if (q.msgs_cap && !host_ptr_mapped(q.user_msgs, &dm)) {
+        if ((rc = ensure_pinned(e, &q.st_msgs, &q.st_msgs_cap, q.msgs_cap))) return rc;
+        q.staged_msgs = 1; host_ptr_mapped(q.st_msgs, &dm);
+    }
+    if (q.notes_cap && !host_ptr_mapped(q.user_notes, &dn)) {
+        if ((rc = ensure_pinned(e, &q.st_notes, &q.st_notes_cap, q.notes_cap))) return rc;
+        q.staged_notes = 1; host_ptr_mapped(q.st_notes, &dn);
+    }
+    void* dh = nullptr;
+    host_ptr_mapped(q.hdr, &dh);
+    const u32 R = e->C.rows;
+    CK(cub::DeviceScan::ExclusiveSum(e->d_scan_tmp, e->scan_tmp_bytes, PackedIt(e->C.out_n, PackCounts()), e->d_offs,
+                                     (int)(R + 1), e->stream));
+    gather_out_kernel<<<nblocks(e->C.tiles, 4), 128, 0, e->stream>>>(
+        e->C, e->d_offs, (ulonglong2*)dm, (u64)q.msgs_cap, (ulonglong2*)dn, (u64)q.notes_cap, (OutHdr*)dh, e->d_err);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(q.done, e->stream));
+    return RA_OK;
+}
+
+static int submit_impl(ra_engine* e, const void* ev, size_t n_ev, bool host32,
+                       ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap)
+{
+    if (!e || (!ev && n_ev) || n_ev > 0x7fffffffull || (!msgs && msgs_cap) || (!notes && notes_cap)) return RA_E_INVAL;
+    if (e->out_pending) return RA_E_CAPACITY;                     // ra_engine_fetch_output first
+    IoSlot& q = e->io[e->io_head % RA_IO_SLOTS];
+    if (e->io_head - e->io_tail >= RA_IO_SLOTS || q.busy) return RA_E_BUSY;
+    CK(cudaSetDevice(e->cfg.device));
+    const u32 R = e->C.rows;
+    const size_t bytes = n_ev * (host32 ? sizeof(ra_host_event) : sizeof(ra_event));
+    if (n_ev) {
+        if (q.d_ev_bytes < bytes) {
+            cudaFree(q.d_ev); q.d_ev = nullptr; q.d_ev_bytes = 0;
+            const size_t nb = bytes + bytes / 4 + 4096;
+            CK(cudaMalloc(&q.d_ev, nb));
+            q.d_ev_bytes = nb;
+        }
+        // a pinned source makes this a true asynchronous DMA; a pageable one is staged by the driver
+        CK(cudaMemcpyAsync(q.d_ev, ev, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        CK(cudaEventRecord(q.h2d_done, e->copy_stream));
+        CK(cudaStreamWaitEvent(e->stream, q.h2d_done, 0));
+    }
+    if (e->loc_dirty) {     // a step after flood() must not see the flood host model's queued host events
+        clear_loc_kernel<<<nblocks(R, 256), 256, 0, e->stream>>>(e->C);
+        e->loc_dirty = 0;
+    }
+    if (n_ev) {
+        if (host32) ingest_host_kernel<<<nblocks(n_ev, 256), 256, 0, e->stream>>>(
+                        e->C, reinterpret_cast<const ra_host_event*>(q.d_ev), (u32)n_ev, e->d_err, e->d_err);
+        else ingest_kernel<<<nblocks(n_ev, 256), 256, 0, e->stream>>>(e->C, reinterpret_cast<const ra_event*>(q.d_ev),
+                                                                        (u32)n_ev, e->d_err, e->d_err);
+        CK(cudaGetLastError());
+    }
+    FloodArgs F; memset(&F, 0, sizeof F);
+    int rc;
+    if ((rc = launch_step(e, F))) return rc;
+    q.user_msgs = msgs; q.user_notes = notes; q.msgs_cap = msgs_cap; q.notes_cap = notes_cap;
+    if ((rc = enqueue_gather(e, q))) return rc;
+    q.busy = 1;
+    e->io_head++;
+    return RA_OK;
+}
+
+static int finish_slot(ra_engine* e, IoSlot& q, size_t* n_msgs, size_t* n_notes, bool was_step)
+{
+    CK(cudaEventSynchronize(q.done));
+    const OutHdr h = *q.hdr;
+    if (n_msgs) *n_msgs = (size_t)h.n_msgs;
+    if (n_notes) *n_notes = (size_t)h.n_notes;
+    const u32 bad = h.status & 0xffu;
+    if (bad) {
+        // the batch was rejected by ingest: the step kernels of this call (and of any call submitted behind it)
+        // did nothing.  Undo this call's buffer flip; once the last such call is collected, clean up.
+        if (was_step) { if (e->C.routed) e->cur ^= 1; e->steps--; }
+        if (e->io_head == e->io_tail) {
+            CK(cudaStreamSynchronize(e->stream));
+            clear_loc_kernel<<<nblocks(e->C.rows, 256), 256, 0, e->stream>>>(e->C);
+            CK(cudaMemsetAsync(e->d_err, 0, sizeof(u32), e->stream));
+            CK(cudaStreamSynchronize(e->stream));
+        }
+        return bad == 1 ? RA_E_UNGROUPED : (bad == 2 ? RA_E_CAPACITY : RA_E_INVAL);
+    }
+    if (h.status & 0x100u) { e->out_pending = 1; return RA_E_CAPACITY; }   // nothing lost: ra_engine_fetch_output
+    if (q.staged_msgs && h.n_msgs) memcpy(q.user_msgs, q.st_msgs, (size_t)h.n_msgs * sizeof(ra_event));
+    if (q.staged_notes && h.n_notes) memcpy(q.user_notes, q.st_notes, (size_t)h.n_notes * sizeof(ra_note));
+    return RA_OK;
+}
+
+extern "C" int ra_engine_collect(ra_engine* e, size_t* n_msgs, size_t* n_notes)
+{
+    if (!e) return RA_E_INVAL;
+    if (e->io_head == e->io_tail) return RA_E_INVAL;              // nothing submitted
+    CK(cudaSetDevice(e->cfg.device));
+    IoSlot& q = e->io[e->io_tail % RA_IO_SLOTS];
+    e->io_tail++;
+    q.busy = 0;
+    return finish_slot(e, q, n_msgs, n_notes, true);
+}
+
+extern "C" int ra_engine_submit(ra_engine* e, const ra_event* ev, size_t n_ev,
+                                ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap)
+{ return submit_impl(e, ev, n_ev, false, msgs, msgs_cap, notes, notes_cap); }
+
+extern "C" int ra_engine_submit_host(ra_engine* e, const ra_host_event* ev, size_t n_ev,
+                                     ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap)
+{ return submit_impl(e, ev, n_ev, true, msgs, msgs_cap, notes, notes_cap); }
+
+// outputs that did not fit the buffers of the call that produced them (RA_E_CAPACITY): how many, and again
+extern "C" int ra_engine_pending_output(ra_engine* e, size_t* n_msgs, size_t* n_notes)
+{
+    if (!e) return RA_E_INVAL;
+    const IoSlot& q = e->io[(e->io_tail + RA_IO_SLOTS - 1) % RA_IO_SLOTS];
+    if (n_msgs) *n_msgs = e->out_pending ? (size_t)q.hdr->n_msgs : 0;
+    if (n_notes) *n_notes = e->out_pending ? (size_t)q.hdr->n_notes : 0;
+    return RA_OK;
+}
+
+extern "C" int ra_engine_fetch_output(ra_engine* e, ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                                      ra_note* notes, size_t notes_cap, size_t* n_notes)
+{
+    if (!e || (!msgs && msgs_cap) || (!notes && notes_cap)) return RA_E_INVAL;
+    if (!e->out_pending) { if (n_msgs) *n_msgs = 0; if (n_notes) *n_notes = 0; return RA_OK; }
+    if (e->io_head != e->io_tail) return RA_E_BUSY;
+    CK(cudaSetDevice(e->cfg.device));
+    IoSlot& q = e->io[(e->io_tail + RA_IO_SLOTS - 1) % RA_IO_SLOTS];
+    q.user_msgs = msgs; q.user_notes = notes; q.msgs_cap = msgs_cap; q.notes_cap = notes_cap;
+    int rc = enqueue_gather(e, q);
+    if (rc) return rc;
+    e->out_pending = 0;
+    return finish_slot(e, q, n_msgs, n_notes, false);
+}
+
 static int step_impl(ra_engine* e, const void* ev, size_t n_ev, bool host32,
                      ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
                      ra_note* notes, size_t notes_cap, size_t* n_notes)
 {
-    if (!e || (!ev && n_ev) || n_ev > 0x7fffffffull) return RA_E_INVAL;
-    CK(cudaSetDevice(e->cfg.device));
-    const u32 R = e->C.rows;
-    int rc;
-    // a step() after flood() must not see the flood host model's queued locals
-    if (n_ev) {
-        if ((rc = ensure(e, &e->d_ev, &e->d_ev_cap, n_ev))) return rc;          // (sized for 64-byte records)
-        CK(cudaMemcpyAsync(e->d_ev, ev, n_ev * (host32 ? sizeof(ra_host_event) : sizeof(ra_event)),
-                           cudaMemcpyHostToDevice, e->stream));
-    }
-    u32 h_err = 0;
-    clear_loc_kernel<<<nblocks(R, 256), 256, 0, e->stream>>>(e->C);
-    CK(cudaMemsetAsync(e->d_err, 0, sizeof(u32), e->stream));
-    if (n_ev) {
-        if (host32) ingest_host_kernel<<<nblocks(n_ev, 256), 256, 0, e->stream>>>(
-                        e->C, reinterpret_cast<const ra_host_event*>(e->d_ev), (u32)n_ev, e->d_err);
-        else ingest_kernel<<<nblocks(n_ev, 256), 256, 0, e->stream>>>(e->C, e->d_ev, (u32)n_ev, e->d_err);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&h_err, e->d_err, sizeof(u32), cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
-        if (h_err) {
-            clear_loc_kernel<<<nblocks(R, 256), 256, 0, e->stream>>>(e->C);
-            CK(cudaStreamSynchronize(e->stream));
-            return h_err == 1 ? RA_E_UNGROUPED : (h_err == 2 ? RA_E_CAPACITY : RA_E_INVAL);
-        }
-    }
-    FloodArgs F; memset(&F, 0, sizeof F);
-    if ((rc = launch_step(e, F))) return rc;
-    // per-row slots -> flat arrays ordered by (row, seq)
-    pack_counts_kernel<<<nblocks(R, 256), 256, 0, e->stream>>>(e->C, e->d_packed);
-    CK(cudaMemsetAsync(e->d_packed + R, 0, sizeof(u64), e->stream));
-    CK(cub::DeviceScan::ExclusiveSum(e->d_scan_tmp, e->scan_tmp_bytes, e->d_packed, e->d_offs, (int)(R + 1), e->stream));
-    u64 total = 0;
-    CK(cudaMemcpyAsync(&total, e->d_offs + R, sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    const size_t tm = (size_t)(total & 0xffffffffull), tn = (size_t)(total >> 32);
-    if ((rc = ensure(e, &e->d_msgs, &e->d_msgs_cap, tm ? tm : 1))) return rc;
-    if ((rc = ensure(e, &e->d_notes, &e->d_notes_cap, tn ? tn : 1))) return rc;
-    gather_kernel<<<nblocks(R, 256), 256, 0, e->stream>>>(e->C, e->d_offs, e->d_msgs, tm, e->d_notes, tn);
-    CK(cudaGetLastError());
-    if (tm > msgs_cap || tn > notes_cap) { CK(cudaStreamSynchronize(e->stream)); return RA_E_CAPACITY; }
-    if (tm) CK(cudaMemcpyAsync(msgs, e->d_msgs, tm * sizeof(ra_event), cudaMemcpyDeviceToHost, e->stream));
-    if (tn) CK(cudaMemcpyAsync(notes, e->d_notes, tn * sizeof(ra_note), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    if (n_msgs) *n_msgs = tm;
-    if (n_notes) *n_notes = tn;
-    return RA_OK;
+    if (e && e->io_head != e->io_tail) return RA_E_BUSY;          // collect what was submitted first
+    int rc = submit_impl(e, ev, n_ev, host32, msgs, msgs_cap, notes, notes_cap);
+    if (rc) return rc;
+    return ra_engine_collect(e, n_msgs, n_notes);
 }
 
 extern "C" int ra_engine_step(ra_engine* e, const ra_event* ev, size_t n_ev,
                               ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
-                              ra_note* notes, size_t notes_cap, size_t* n_notes)
+                              ra_note*  notes, size_t notes_cap, size_t* n_notes)
 { return step_impl(e, ev, n_ev, false, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes); }
 
 extern "C" int ra_engine_step_host(ra_engine* e, const ra_host_event* ev, size_t n_ev,
                                    ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
                                    ra_note* notes, size_t notes_cap, size_t* n_notes)
 { return step_impl(e, ev, n_ev, true, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes); }
+
+// caller-owned host buffers (a NIF's resource binaries ...) pinned and mapped once, so that batches built in
+// them are copied by DMA and outputs are written into them directly
+extern "C" int ra_engine_register_host(void* p, size_t bytes)
+{
+    if (!p || !bytes) return RA_E_INVAL;
+    return cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) == cudaSuccess ? RA_OK : RA_E_CUDA;
+}
+extern "C" int ra_engine_unregister_host(void* p)
+{
+    if (!p) return RA_E_INVAL;
+    return cudaHostUnregister(p) == cudaSuccess ? RA_OK : RA_E_CUDA;
+}
 
 extern "C" int ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per_step,
                                uint32_t election_permille, uint64_t seed)
@@ -901,6 +1067,7 @@ extern "C" int ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per
     }
     CK(cudaEventRecord(e->ev1, e->stream));
     e->step_no += n_steps;
+    e->loc_dirty = 1;
     e->last_launches = 2 * n_steps;
     return RA_OK;
 }

@@ -28,19 +28,25 @@ static inline u64 mix64(u64 x)
     return x ^ (x >> 31);
 }
 
-struct ra_hostsim {
+// one engine of the simulation = one partition of the groups, with its own pinned batch / note buffers
+struct Part {
     ra_engine* e;
     u32 groups, members, rows;
     std::vector<unsigned char> role, idle;
-    u32 threads;
-    std::vector<std::vector<ra_host_event>> tmp;
-    std::vector<size_t> cnt, off;
-    double t_model, t_step;          // seconds spent in the host model / inside ra_engine_step
     ra_host_event* ev;  size_t ev_cap; // pinned; the flood only has host-origin events: 32-byte records
     ra_event* msgs; size_t msgs_cap;  // pinned
     ra_note* notes; size_t notes_cap; // pinned
     size_t n_ev;
     u64 step;
+    u64 seed_off;                     // partition p runs the model with seed + p (independent groups)
+};
+
+struct ra_hostsim {
+    std::vector<Part> parts;
+    u32 threads;
+    std::vector<std::vector<ra_host_event>> tmp;
+    std::vector<size_t> cnt, off;
+    double t_model, t_step;          // seconds spent in the host model / waiting inside engine calls
     u64 h2d, d2h, calls; double seconds;
 };
 
@@ -48,7 +54,7 @@ struct ra_hostsim {
 extern "C" void* ra_engine_alloc_host(size_t bytes)
 {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
     return p;
 }
 extern "C" void ra_engine_free_host(void* p) { if (p) cudaFreeHost(p); }
@@ -57,15 +63,38 @@ extern "C" void* ra_engine_alloc_host(size_t bytes) { return malloc(bytes ? byte
 extern "C" void ra_engine_free_host(void* p) { free(p); }
 #endif
 
-extern "C" int ra_hostsim_create(ra_engine* e, ra_hostsim** out)
+extern "C" void ra_hostsim_destroy(ra_hostsim* s)
 {
-    ra_engine_cfg cfg;
-    if (!e || !out || ra_engine_get_cfg(e, &cfg) != RA_OK) return RA_E_INVAL;
-    if (!cfg.route_on_device) return RA_E_INVAL;
-    const u32 groups = cfg.n_groups, members = cfg.n_members;
+    if (!s) return;
+    for (Part& p : s->parts) { ra_engine_free_host(p.ev); ra_engine_free_host(p.msgs); ra_engine_free_host(p.notes); }
+    delete s;
+}
+
+// K engines holding disjoint sets of groups, driven by ONE host thread through ra_engine_submit_host /
+// ra_engine_collect: while the notes of one partition travel to the host and its model runs, the batch of
+// another travels to the device and its kernels run (PCIe is full duplex).
+extern "C" int ra_hostsim_create_multi(ra_engine* const* engines, uint32_t n, ra_hostsim** out)
+{
+    if (!engines || !n || !out) return RA_E_INVAL;
     ra_hostsim* s = new ra_hostsim();
-    s->e = e; s->groups = groups; s->members = members; s->rows = groups * members;
-    s->role.assign(s->rows, RA_FOLLOWER); s->idle.assign(s->rows, 0);
+    s->parts.resize(n);
+    u32 max_rows = 0;
+    for (u32 i = 0; i < n; i++) {
+        Part& p = s->parts[i];
+        ra_engine_cfg cfg;
+        if (!engines[i] || ra_engine_get_cfg(engines[i], &cfg) != RA_OK || !cfg.route_on_device) { ra_hostsim_destroy(s); return RA_E_INVAL; }
+        p.e = engines[i]; p.groups = cfg.n_groups; p.members = cfg.n_members; p.rows = p.groups * p.members;
+        p.role.assign(p.rows, RA_FOLLOWER); p.idle.assign(p.rows, 0);
+        // a flood row emits <= 2 WAL_APPEND + COMMIT + APPLY + STATUS notes per step in steady state; the rare
+        // step that needs more is fetched again with a bigger buffer (RA_E_CAPACITY loses nothing)
+        p.ev_cap = (size_t)p.rows * RA_LOCAL_CAP; p.msgs_cap = 1024; p.notes_cap = (size_t)p.rows * 6;
+        p.ev = (ra_host_event*)ra_engine_alloc_host(p.ev_cap * sizeof(ra_host_event));
+        p.msgs = (ra_event*)ra_engine_alloc_host(p.msgs_cap * sizeof(ra_event));
+        p.notes = (ra_note*)ra_engine_alloc_host(p.notes_cap * sizeof(ra_note));
+        if (!p.ev || !p.msgs || !p.notes) { ra_hostsim_destroy(s); return RA_E_NOMEM; }
+        p.n_ev = 0; p.step = 0; p.seed_off = i;
+        if (p.rows > max_rows) max_rows = p.rows;
+    }
     {
         unsigned hc = std::thread::hardware_concurrency();
         const char* env = getenv("RA_HOSTSIM_THREADS");
@@ -74,22 +103,12 @@ extern "C" int ra_hostsim_create(ra_engine* e, ra_hostsim** out)
         s->tmp.resize(s->threads);
         s->cnt.assign(s->threads, 0); s->off.assign(s->threads + 1, 0);
     }
-    s->ev_cap = (size_t)s->rows * RA_LOCAL_CAP; s->msgs_cap = 1024; s->notes_cap = (size_t)s->rows * RA_NOTE_CAP;
-    s->ev = (ra_host_event*)ra_engine_alloc_host(s->ev_cap * sizeof(ra_host_event));
-    s->msgs = (ra_event*)ra_engine_alloc_host(s->msgs_cap * sizeof(ra_event));
-    s->notes = (ra_note*)ra_engine_alloc_host(s->notes_cap * sizeof(ra_note));
-    if (!s->ev || !s->msgs || !s->notes) { delete s; return RA_E_NOMEM; }
-    s->n_ev = 0; s->step = 0; s->h2d = s->d2h = s->calls = 0; s->seconds = 0;
+    s->h2d = s->d2h = s->calls = 0; s->seconds = 0; s->t_model = s->t_step = 0;
     *out = s;
     return RA_OK;
 }
 
-extern "C" void ra_hostsim_destroy(ra_hostsim* s)
-{
-    if (!s) return;
-    ra_engine_free_host(s->ev); ra_engine_free_host(s->msgs); ra_engine_free_host(s->notes);
-    delete s;
-}
+extern "C" int ra_hostsim_create(ra_engine* e, ra_hostsim** out) { return ra_hostsim_create_multi(&e, 1, out); }
 
 static inline void put(ra_host_event* e, u32 row, u32 type, u32 n, u64 term, u64 a, u64 b)
 {
@@ -102,8 +121,8 @@ static inline void put(ra_event* e, u32 row, u32 type, u32 n, u64 term, u64 a, u
     e->term = term; e->a = a; e->b = b;
 }
 
-// notes of one step -> events of the next (the flood host model), rows [r0, r1)
-static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u32 r0, u32 r1, ra_host_event* out,
+// notes of one step -> events of the next (the flood host model), rows [r0, r1) of one partition
+static size_t model_range(Part* s, const ra_note* notes, size_t n_notes, u32 r0, u32 r1, ra_host_event* out,
                           u32 cmds, u32 permille, u64 seed, bool run_model)
 {
     // first note of row r0 (notes are ordered by row)
@@ -149,14 +168,14 @@ static size_t model_range(ra_hostsim* s, const ra_note* notes, size_t n_notes, u
     return ne;
 }
 
-// the model over all rows on s->threads host threads (OpenMP keeps the team alive between steps):
-// each thread fills a private buffer for its row range, then the pieces are copied, in row
-// order, into the pinned batch
-static void model(ra_hostsim* s, size_t n_notes, u32 cmds, u32 permille, u64 seed, bool run_model)
+// the model over all rows of a partition on s->threads host threads (OpenMP keeps the team alive between
+// steps): each thread fills a private buffer for its row range, then the pieces are copied, in row order, into
+// the partition's pinned batch
+static void model(ra_hostsim* s, Part* p, size_t n_notes, u32 cmds, u32 permille, u64 seed, bool run_model)
 {
     const int T = (int)s->threads;
-    if (T <= 1 || s->rows < 4096) {
-        s->n_ev = model_range(s, s->notes, n_notes, 0, s->rows, s->ev, cmds, permille, seed, run_model);
+    if (T <= 1 || p->rows < 4096) {
+        p->n_ev = model_range(p, p->notes, n_notes, 0, p->rows, p->ev, cmds, permille, seed, run_model);
         return;
     }
     std::vector<size_t>& cnt = s->cnt;
@@ -164,18 +183,44 @@ static void model(ra_hostsim* s, size_t n_notes, u32 cmds, u32 permille, u64 see
 #pragma omp parallel num_threads(T)
     {
         const int t = omp_get_thread_num();
-        const u32 r0 = (u32)((u64)s->rows * t / T), r1 = (u32)((u64)s->rows * (t + 1) / T);
+        const u32 r0 = (u32)((u64)p->rows * t / T), r1 = (u32)((u64)p->rows * (t + 1) / T);
         if (s->tmp[t].size() < (size_t)(r1 - r0) * RA_LOCAL_CAP) s->tmp[t].resize((size_t)(r1 - r0) * RA_LOCAL_CAP);
-        cnt[t] = model_range(s, s->notes, n_notes, r0, r1, s->tmp[t].data(), cmds, permille, seed, run_model);
+        cnt[t] = model_range(p, p->notes, n_notes, r0, r1, s->tmp[t].data(), cmds, permille, seed, run_model);
 #pragma omp barrier
 #pragma omp single
         {
             off[0] = 0;
             for (int k = 0; k < T; k++) off[k + 1] = off[k] + cnt[k];
         }
-        if (cnt[t]) memcpy(s->ev + off[t], s->tmp[t].data(), cnt[t] * sizeof(ra_host_event));
+        if (cnt[t]) memcpy(p->ev + off[t], s->tmp[t].data(), cnt[t] * sizeof(ra_host_event));
     }
-    s->n_ev = off[T];
+    p->n_ev = off[T];
+}
+
+// collect a partition's call; a note buffer that turned out too small is grown and the outputs fetched again
+static int collect_part(ra_hostsim* s, Part* p, size_t* nn)
+{
+    size_t nm = 0;
+    int rc = ra_engine_collect(p->e, &nm, nn);
+#ifndef RA_NO_CUDA
+    if (rc == RA_E_CAPACITY && (*nn > p->notes_cap || nm > p->msgs_cap)) {
+        if (*nn > p->notes_cap) {
+            ra_engine_free_host(p->notes);
+            p->notes_cap = *nn + *nn / 4;
+            p->notes = (ra_note*)ra_engine_alloc_host(p->notes_cap * sizeof(ra_note));
+        }
+        if (nm > p->msgs_cap) {
+            ra_engine_free_host(p->msgs);
+            p->msgs_cap = nm + nm / 4;
+            p->msgs = (ra_event*)ra_engine_alloc_host(p->msgs_cap * sizeof(ra_event));
+        }
+        if (!p->notes || !p->msgs) return RA_E_NOMEM;
+        rc = ra_engine_fetch_output(p->e, p->msgs, p->msgs_cap, &nm, p->notes, p->notes_cap, nn);
+    }
+#endif
+    if (rc) return rc;
+    s->d2h += *nn * sizeof(ra_note) + nm * sizeof(ra_event);
+    return RA_OK;
 }
 
 extern "C" int ra_hostsim_run(ra_hostsim* s, uint32_t n_steps, uint32_t cmds, uint32_t permille,
@@ -185,27 +230,45 @@ extern "C" int ra_hostsim_run(ra_hostsim* s, uint32_t n_steps, uint32_t cmds, ui
     auto t0 = std::chrono::steady_clock::now();
     s->h2d = s->d2h = s->calls = 0;
     s->t_model = s->t_step = 0;
-    size_t nm = 0, nn = 0;
+    size_t nn = 0;
     int rc;
+    const size_t P = s->parts.size();
     if (bootstrap) {
-        for (u32 g = 0; g < s->groups; g++) put(&s->ev[g], g, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0);
-        rc = ra_engine_step_host(s->e, s->ev, s->groups, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
-        if (rc) return rc;
-        s->h2d += (u64)s->groups * sizeof(ra_host_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
-        model(s, nn, cmds, permille, seed, false);         // roles only; no model run for this step
-        s->n_ev = 0;
+        for (Part& p : s->parts) {
+            for (u32 g = 0; g < p.groups; g++) put(&p.ev[g], g, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0);
+            if ((rc = ra_engine_submit_host(p.e, p.ev, p.groups, p.msgs, p.msgs_cap, p.notes, p.notes_cap))) return rc;
+            s->h2d += (u64)p.groups * sizeof(ra_host_event); s->calls++;
+        }
+        for (Part& p : s->parts) {
+            if ((rc = collect_part(s, &p, &nn))) return rc;
+            model(s, &p, nn, cmds, permille, seed + p.seed_off, false);   // roles only; no model run for this step
+            p.n_ev = 0;
+        }
     }
-    for (u32 t = 0; t < n_steps; t++) {
-        auto a0 = std::chrono::steady_clock::now();
-        rc = ra_engine_step_host(s->e, s->ev, s->n_ev, s->msgs, s->msgs_cap, &nm, s->notes, s->notes_cap, &nn);
-        if (rc) return rc;
-        auto a1 = std::chrono::steady_clock::now();
-        s->h2d += (u64)s->n_ev * sizeof(ra_host_event); s->d2h += nn * sizeof(ra_note) + nm * sizeof(ra_event); s->calls++;
-        model(s, nn, cmds, permille, seed, true);
-        auto a2 = std::chrono::steady_clock::now();
-        s->t_step += std::chrono::duration<double>(a1 - a0).count();
-        s->t_model += std::chrono::duration<double>(a2 - a1).count();
-        s->step++;
+    if (n_steps) {
+        // software pipeline over the partitions: every partition always has one call in flight
+        for (Part& p : s->parts) {
+            if ((rc = ra_engine_submit_host(p.e, p.ev, p.n_ev, p.msgs, p.msgs_cap, p.notes, p.notes_cap))) return rc;
+            s->h2d += (u64)p.n_ev * sizeof(ra_host_event); s->calls++;
+        }
+        for (u32 t = 0; t < n_steps; t++) {
+            for (size_t i = 0; i < P; i++) {
+                Part& p = s->parts[i];
+                auto a0 = std::chrono::steady_clock::now();
+                if ((rc = collect_part(s, &p, &nn))) return rc;
+                auto a1 = std::chrono::steady_clock::now();
+                model(s, &p, nn, cmds, permille, seed + p.seed_off, true);
+                p.step++;
+                auto a2 = std::chrono::steady_clock::now();
+                if (t + 1 < n_steps) {
+                    if ((rc = ra_engine_submit_host(p.e, p.ev, p.n_ev, p.msgs, p.msgs_cap, p.notes, p.notes_cap))) return rc;
+                    s->h2d += (u64)p.n_ev * sizeof(ra_host_event); s->calls++;
+                }
+                auto a3 = std::chrono::steady_clock::now();
+                s->t_step += std::chrono::duration<double>(a1 - a0).count() + std::chrono::duration<double>(a3 - a2).count();
+                s->t_model += std::chrono::duration<double>(a2 - a1).count();
+            }
+        }
     }
     s->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return RA_OK;
@@ -218,7 +281,7 @@ extern "C" int ra_hostsim_stats(ra_hostsim* s, uint64_t* h2d, uint64_t* d2h, dou
     return RA_OK;
 }
 
-/* where the wall time of the last run went: inside ra_engine_step vs in the host model */
+/* where the wall time of the last run went: waiting inside engine calls vs in the host model */
 extern "C" int ra_hostsim_breakdown(ra_hostsim* s, double* step_seconds, double* model_seconds)
 {
     if (!s) return RA_E_INVAL;

@@ -103,6 +103,7 @@ struct Cols {
     ra_note*  onote;    // [k][rows]
     u32*      out_n;    // [rows] msgs | notes << 16
     u64*      counters; // ra_counters as 8 x u64, then [8 + role*16 + type]: events that left the fast kernel
+    u32*      abort;    // != 0: a host batch was rejected (ra_engine_submit); the step kernels do nothing until the host has cleaned up
     u32 rows, groups, members;
     u32 groups_inv;        // floor(2^32 / groups)
     u32 max_pipeline, max_batch;
@@ -742,16 +743,27 @@ __device__ __forceinline__ void evaluate_quorum(Member& m)
         v[s] = self ? m.lw_idx : (voter ? peer_nm_p<MM>(m, s)->y : 0ull);
         n += voter ? 1u : 0u;
     }
+    const u32 nth = n / 2 + 1;                                  // 1-based rank, descending
+    const u64 ci0 = m.commit;
+#ifndef RA_NO_QSHORT
+    {
+        // exact shortcut for the common outcome "nothing moves": the nth largest value IS commit_index exactly
+        // when fewer than nth values exceed it and at least nth reach it; increment_commit_index/1 then leaves
+        // commit_index alone whatever fetch_term says (8 of a steady-state leader's 9 evaluations per step)
+        u32 gt = 0, ge = 0;
+#pragma unroll
+        for (int s = 0; s < NV; s++) { gt += v[s] > ci0 ? 1u : 0u; ge += v[s] >= ci0 ? 1u : 0u; }
+        if (gt < nth && ge >= nth) { apply_to(m, m.commit); m.cold |= 8u; return; }
+    }
+#endif
 #pragma unroll
     for (int pass = 0; pass < NV; pass++) {
 #pragma unroll
         for (int i = pass & 1; i + 1 < NV; i += 2) cex(v[i], v[i + 1]);
     }
-    const u32 nth = n / 2 + 1;                                  // 1-based rank, descending
     u64 best = v[0];
 #pragma unroll
     for (int i = 1; i < NV; i++) best = (nth == (u32)(i + 1)) ? v[i] : best;
-    u64 ci0 = m.commit;
     if (srv_fetch_term(m, (i64)best) == m.term) m.commit = best;        // §5.4.2 gate :3625-3629
     if (m.commit != ci0) m.pipe_clean = 0;
     if (m.commit > ci0) {

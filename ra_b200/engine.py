@@ -56,10 +56,12 @@ EXPORTS = ["ra_engine_create", "ra_engine_destroy", "ra_engine_load_rows", "ra_e
            "ra_engine_free_host", "ra_engine_stall_histogram", "ra_engine_set_stream",
            "ra_engine_set_outbox", "ra_engine_deliver", "ra_engine_peer_get", "ra_engine_peer_set",
            "ra_engine_ipc_export", "ra_engine_ipc_import", "ra_engine_peer_barrier",
-           "ra_engine_load_query_state", "ra_engine_read_query_state", "ra_engine_step_host"]
+           "ra_engine_load_query_state", "ra_engine_read_query_state", "ra_engine_step_host",
+           "ra_engine_submit", "ra_engine_submit_host", "ra_engine_collect", "ra_engine_pending_output",
+           "ra_engine_fetch_output", "ra_engine_register_host", "ra_engine_unregister_host"]
 HOST_EXPORTS = ["ra_wal_batch_to_events"]            # host-only helpers of the same library
-HOSTSIM_EXPORTS = ["ra_hostsim_create", "ra_hostsim_destroy", "ra_hostsim_run", "ra_hostsim_stats",
-                   "ra_hostsim_breakdown"]
+HOSTSIM_EXPORTS = ["ra_hostsim_create", "ra_hostsim_create_multi", "ra_hostsim_destroy", "ra_hostsim_run",
+                   "ra_hostsim_stats", "ra_hostsim_breakdown"]
 
 
 class Engine(abi.Backend):
@@ -111,10 +113,18 @@ class Engine(abi.Backend):
 class HostFlood:
     """The flood driven from the host through ra_engine_step (host buffers every step)."""
 
-    def __init__(self, engine: Engine):
-        self.e = engine
+    def __init__(self, engine):
+        """engine: one Engine, or a list of Engines holding disjoint sets of groups (one host thread keeps all of
+        them busy through ra_engine_submit_host / ra_engine_collect: ra_hostsim_create_multi)."""
+        engines = list(engine) if isinstance(engine, (list, tuple)) else [engine]
+        self.e = engines[0]
+        self.engines = engines
         self._h = C.c_void_p()
-        engine._check(lib().ra_hostsim_create(engine._h, C.byref(self._h)), "hostsim_create")
+        f = lib().ra_hostsim_create_multi
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(C.c_void_p)]
+        arr = (C.c_void_p * len(engines))(*[e_._h for e_ in engines])
+        self.e._check(f(arr, len(engines), C.byref(self._h)), "hostsim_create_multi")
 
     def run(self, n_steps: int, cmds_per_step: int = 1, election_permille: int = 0, seed: int = 1,
             bootstrap: bool = False) -> dict:

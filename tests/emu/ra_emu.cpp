@@ -29,6 +29,7 @@ struct ra_emu {
     int cur;
     u64 step_no, steps;
     void* allocs[64]; int n_allocs;
+    int sub_busy, sub_rc; size_t sub_nm, sub_nn;      // the one "submitted" call (ra_engine_submit_host shim)
 };
 
 template <typename T>
@@ -304,6 +305,31 @@ extern "C" int ra_emu_deliver(ra_emu* e, const void* inbox, const uint32_t* coun
     return RA_OK;
 }
 
+// scan + gather_out: per-row slots -> flat arrays ordered by (row, seq).  When they do not fit, nothing is
+// written and the slots stay: RA_E_CAPACITY with the sizes needed, the caller fetches again (engine.cu)
+extern "C" int ra_emu_fetch_output(ra_emu* e, ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
+                                   ra_note* notes, size_t notes_cap, size_t* n_notes)
+{
+    if (!e) return RA_E_INVAL;
+    const Cols& C = e->C;
+    const u32 R = C.rows;
+    size_t tm = 0, tn = 0;
+    for (u32 r = 0; r < R; r++) { tm += C.out_n[r] & 0xffffu; tn += C.out_n[r] >> 16; }
+    if (n_msgs) *n_msgs = tm;
+    if (n_notes) *n_notes = tn;
+    if (tm > msgs_cap || tn > notes_cap) return RA_E_CAPACITY;
+    size_t om = 0, on = 0;
+    for (u32 r = 0; r < R; r++) {
+        const u32 v = C.out_n[r];
+        C.out_n[r] = 0;
+        const u32 nm = v & 0xffffu, nn = v >> 16;
+        for (u32 k = 0; k < nm; k++) st_rec(&msgs[om + k], ld_rec(&C.omsg[(size_t)k * C.rows + r]));
+        for (u32 k = 0; k < nn; k++) notes[on + k] = C.onote[(size_t)k * C.rows + r];
+        om += nm; on += nn;
+    }
+    return RA_OK;
+}
+
 extern "C" int ra_emu_step(ra_emu* e, const ra_event* ev, size_t n_ev,
                            ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
                            ra_note* notes, size_t notes_cap, size_t* n_notes)
@@ -334,25 +360,7 @@ extern "C" int ra_emu_step(ra_emu* e, const ra_event* ev, size_t n_ev,
     }
     FloodArgs F; memset(&F, 0, sizeof F);
     { const int rc = run_step(e, F); if (rc) return rc; }
-    // pack_counts + scan + gather: per-row slots -> flat arrays ordered by (row, seq)
-    size_t tm = 0, tn = 0;
-    for (u32 r = 0; r < R; r++) { tm += C.out_n[r] & 0xffffu; tn += C.out_n[r] >> 16; }
-    const bool fits = tm <= msgs_cap && tn <= notes_cap;
-    size_t om = 0, on = 0;
-    for (u32 r = 0; r < R; r++) {
-        const u32 v = C.out_n[r];
-        C.out_n[r] = 0;
-        const u32 nm = v & 0xffffu, nn = v >> 16;
-        if (fits) {
-            for (u32 k = 0; k < nm; k++) st_rec(&msgs[om + k], ld_rec(&C.omsg[(size_t)k * C.rows + r]));
-            for (u32 k = 0; k < nn; k++) notes[on + k] = C.onote[(size_t)k * C.rows + r];
-        }
-        om += nm; on += nn;
-    }
-    if (!fits) return RA_E_CAPACITY;
-    if (n_msgs) *n_msgs = tm;
-    if (n_notes) *n_notes = tn;
-    return RA_OK;
+    return ra_emu_fetch_output(e, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes);
 }
 
 extern "C" int ra_emu_step_host(ra_emu* e, const ra_host_event* ev, size_t n_ev,
@@ -430,3 +438,22 @@ extern "C" int ra_emu_codec_roundtrip(const ra_event* in, ra_event* out, int* ha
 extern "C" int ra_engine_step_host(ra_engine* e, const ra_host_event* ev, size_t n_ev, ra_event* msgs, size_t msgs_cap,
                                    size_t* n_msgs, ra_note* notes, size_t notes_cap, size_t* n_notes)
 { return ra_emu_step_host((ra_emu*)e, ev, n_ev, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes); }
+/* the split-phase pair: the emulation evaluates at submit and hands the result over at collect */
+extern "C" int ra_engine_submit_host(ra_engine* e, const ra_host_event* ev, size_t n_ev, ra_event* msgs, size_t msgs_cap,
+                                     ra_note* notes, size_t notes_cap)
+{
+    ra_emu* m = (ra_emu*)e;
+    if (!m || m->sub_busy) return RA_E_BUSY;
+    m->sub_rc = ra_emu_step_host(m, ev, n_ev, msgs, msgs_cap, &m->sub_nm, notes, notes_cap, &m->sub_nn);
+    m->sub_busy = 1;
+    return RA_OK;
+}
+extern "C" int ra_engine_collect(ra_engine* e, size_t* n_msgs, size_t* n_notes)
+{
+    ra_emu* m = (ra_emu*)e;
+    if (!m || !m->sub_busy) return RA_E_INVAL;
+    m->sub_busy = 0;
+    if (n_msgs) *n_msgs = m->sub_nm;
+    if (n_notes) *n_notes = m->sub_nn;
+    return m->sub_rc;
+}
