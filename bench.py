@@ -259,6 +259,18 @@ def run_engine(args):
     ms_max, commits_all, events_all = reduce_max_sum(world, local, ms, commits, events)
     value = commits_all / (ms_max * 1e-3)
 
+    # parity of THIS run (the rows the timed region left): every `stride`-th global group is replayed by the CPU
+    # oracle (checker only; groups are independent and the flood host model is keyed by global ids), and every
+    # rank diffs the members of those groups that live on it, field by field
+    parity = None
+    if not args.no_parity:
+        parity = parity_sample(args, eng, world, rank, spread, seed, args.settle + args.warmup + args.steps)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([parity["rows_checked"], parity["rows_bad"]], dtype=torch.int64, device="cuda:%d" % local)
+            dist.all_reduce(t)
+            parity["rows_checked"], parity["rows_bad"] = int(t[0]), int(t[1])
+
     # e2e: the same flood through ra_engine_step with pinned host buffers (rank-local engine)
     e2e = None
     if not args.no_e2e:
@@ -364,11 +376,47 @@ def run_engine(args):
                      "bytes_per_commit": bc, "algorithmic_bytes_per_launch": bc * commits / args.steps,
                      "kernel": "raft_step_kernel (+ raft_general_kernel for the rows that leave the fast paths)"},
     }
+    if parity:
+        out["parity"] = parity
     if e2e:
         out["e2e"] = e2e
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(args, sample_groups=min(G, args.cpu_groups), steps=args.cpu_steps)
     print(json.dumps(out))
+
+
+def parity_sample(args, eng, world: int, rank: int, spread: bool, seed: int, flood_steps: int, stride: int = 97) -> dict:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+    from ra_b200 import abi
+    G, M = args.groups, args.members
+    total = G * world if spread else G                      # groups of the global run this rank belongs to
+    n = (total + stride - 1) // stride
+    while n > 1 and (n - 1) * stride >= total:
+        n -= 1
+    o = Oracle(n, M, route_on_device=True)
+    o.set_sample(stride, 0, total)
+    o.reset_empty()
+    o.step([abi.ev_simple(o.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(n)])
+    o.flood(flood_steps, args.cmds, args.permille, seed=seed, threads=max(1, min(8, effective_cpus() // max(1, world))))
+    want = o.read_rows(range(o.n_rows))
+    ids, exp = [], []
+    for i in range(n):
+        gg = i * stride
+        for s in range(M):
+            if spread:
+                if (gg + s) % world != rank:
+                    continue
+                ids.append(s * G + gg // world)
+            else:
+                ids.append(s * G + gg)
+            exp.append(want[s * n + i])
+    got = eng.read_rows(ids)
+    bad = sum(1 for a, b in zip(got, exp) if a.key()[1:] != b.key()[1:])
+    o.close()
+    return {"rows_checked": len(ids), "rows_bad": bad, "stride": stride,
+            "how": "every %d-th global group replayed by the CPU oracle for all %d steps of this run; each rank "
+                   "diffs its members of those groups (all ra_row_state fields)" % (stride, flood_steps + 1)}
 
 
 def effective_cpus() -> int:
@@ -465,6 +513,7 @@ def main():
                          "a2a = per-destination buckets + NCCL all_to_all_single + deliver kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle replay of every 97th group of this run")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

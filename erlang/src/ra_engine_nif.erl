@@ -8,7 +8,7 @@
 -module(ra_engine_nif).
 
 -export([new/3, load_rows/2, read_rows/2, reset_empty/1, step/2, step_host/2,
-         submit/2, submit_host/2, collect/1, fetch_output/1, counters/1]).
+         submit/2, submit_host/2, collect/1, counters/1]).
 -on_load(init/0).
 
 -type engine() :: reference().
@@ -55,8 +55,6 @@ submit(_Eng, _EventsBin) -> erlang:nif_error(nif_not_loaded).
 submit_host(_Eng, _HostEventsBin) -> erlang:nif_error(nif_not_loaded).
 -spec collect(engine()) -> {binary(), binary()} | {error, integer()}.
 collect(_Eng) -> erlang:nif_error(nif_not_loaded).
--spec fetch_output(engine()) -> {binary(), binary()} | {error, integer()}.
-fetch_output(_Eng) -> erlang:nif_error(nif_not_loaded).
 
 %% ra_engine_counters: the aggregate counters and the reference's per-path ones (ra.hrl:324-343)
 -spec counters(engine()) -> map() | {error, integer()}.

@@ -408,6 +408,9 @@ int  ra_engine_ipc_import(ra_engine* e, uint32_t shard, const ra_ipc_handles* h)
  * words in every peer's HBM, release / acquire at system scope) instead of a collective.  All shards
  * must have the same number of rows; never use it with several shards on ONE stream. */
 int  ra_engine_peer_barrier(ra_engine* e);
+/* on != 0: ra_engine_flood ends every step with that barrier, so a multi-step flood of one shard per process
+ * runs without the host between steps (one process per GPU only: see above) */
+int  ra_engine_set_flood_barrier(ra_engine* e, int on);
 
 /*
  * The same call for batches made only of events the HOST originates (written, command(s), timeouts, tick,

@@ -102,6 +102,9 @@ struct ra_oracle {
     u8 *loc_n;
     u64 step_no;
     u32 note_cap;                    /* notes per row per step (cfg.note_cap or RA_NOTE_CAP) */
+    /* sample view (ra_oracle_set_sample): local group g stands for global group offset + g * stride of a run
+       over total_groups groups; the flood host model is keyed by the GLOBAL group / row ids */
+    u32 s_stride, s_offset, s_total;
 };
 
 /* per-row, per-step output context */
@@ -1741,6 +1744,8 @@ static void host_model(ra_oracle *o, ctx_t *c, u64 step, u32 cmds, u32 permille,
 {
     member_t *m = c->m;
     u32 row = m->row, G = o->cfg.n_groups, g = row % G;
+    u64 gg = g, grow = row;                       /* ids the model hashes */
+    if (o->s_stride) { gg = (u64)o->s_offset + (u64)g * o->s_stride; grow = (u64)m->self_slot * o->s_total + gg; }
     ra_event *loc = o->loc; u8 *ln = &o->loc_n[row];
     u32 k = 0;
     /* the last two WAL_APPEND notes become WRITTEN events */
@@ -1764,9 +1769,9 @@ static void host_model(ra_oracle *o, ctx_t *c, u64 step, u32 cmds, u32 permille,
     if (m->role == RA_LEADER || (c->status & RA_ST_LEADER_MSG)) m->idle = 0;
     else m->idle++;
     if (m->role != RA_LEADER) {
-        u32 h = (u32)(mix64(seed ^ (step * 0x9E3779B97F4A7C15ull) ^ ((u64)g * 0xD1B54A32D192ED03ull)) >> 32);
+        u32 h = (u32)(mix64(seed ^ (step * 0x9E3779B97F4A7C15ull) ^ (gg * 0xD1B54A32D192ED03ull)) >> 32);
         if (permille && (h % 1000u) < permille && ((h / 1000u) % o->cfg.n_members) == m->self_slot) fire = 1;
-        u32 h2 = (u32)(mix64(seed ^ ((u64)row * 0xA24BAED4963EE407ull) ^ step) >> 32);
+        u32 h2 = (u32)(mix64(seed ^ (grow * 0xA24BAED4963EE407ull) ^ step) >> 32);
         if (m->idle >= 8 + (h2 & 7u)) fire = 1;
     }
     if (fire) {
@@ -1776,6 +1781,15 @@ static void host_model(ra_oracle *o, ctx_t *c, u64 step, u32 cmds, u32 permille,
         m->idle = 0;
     }
     *ln = (u8)k;
+}
+
+/* checker for big runs: this oracle's group g plays global group offset + g * stride of a flood over
+   total_groups groups (groups are independent; the host model is the only thing keyed by their ids) */
+int ra_oracle_set_sample(ra_oracle *o, uint32_t stride, uint32_t offset, uint32_t total_groups)
+{
+    if (!o || !stride || (uint64_t)offset + (uint64_t)(o->cfg.n_groups - 1) * stride >= total_groups) return RA_E_INVAL;
+    o->s_stride = stride; o->s_offset = offset; o->s_total = total_groups;
+    return RA_OK;
 }
 
 static void flood_groups(ra_oracle *o, u32 g0, u32 g1, u32 n_steps, u32 cmds, u32 permille,

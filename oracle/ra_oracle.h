@@ -33,6 +33,9 @@ int  ra_oracle_flood(ra_oracle* o, uint32_t n_steps, uint32_t cmds_per_step,
 int  ra_oracle_step_host(ra_oracle* o, const ra_host_event* ev, size_t n_ev, ra_event* msgs, size_t msgs_cap,
                          size_t* n_msgs, ra_note* notes, size_t notes_cap, size_t* n_notes);
 int  ra_oracle_counters(ra_oracle* o, ra_counters* out);
+/* this oracle's group g stands for global group offset + g * stride of a flood over total_groups groups (the
+   flood host model is keyed by global group / row ids): the checker of runs too big to replay in full */
+int  ra_oracle_set_sample(ra_oracle* o, uint32_t stride, uint32_t offset, uint32_t total_groups);
 
 /* in-module KAT of the reference: agreed_commit/1, src/ra_server.erl:3657-3661 */
 uint64_t ra_oracle_agreed_commit(const uint64_t* indexes, size_t n);

@@ -66,6 +66,7 @@ FATAL_LEADER_SAW_HEARTBEAT_SAME_TERM = 6
 FATAL_NOTE_OVERFLOW = 7
 
 RA_OK, RA_E_INVAL, RA_E_NOMEM, RA_E_CUDA, RA_E_UNGROUPED, RA_E_CAPACITY, RA_E_NODEVICE = 0, -1, -2, -3, -4, -5, -6
+RA_E_BUSY = -7
 
 
 class RaEvent(C.Structure):
@@ -359,6 +360,47 @@ class Backend:
         self._check(self._fn("step")(self._h, ev, n, msgs, msgs_cap, C.byref(nm), notes, notes_cap,
                                      C.byref(nn)), "step")
         return list(msgs[: nm.value]), list(notes[: nn.value])
+
+    # -- output capacity: a step whose outputs did not fit lost nothing (include/ra_engine.h "Capacity") --------
+    def fetch_output(self, msgs_cap: int, notes_cap: int):
+        """-> (status, n_msgs, n_notes, msgs, notes): RA_OK, or RA_E_CAPACITY with the sizes needed."""
+        f = self._fn("fetch_output")
+        sz = C.c_size_t
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.POINTER(RaEvent), sz, C.POINTER(sz), C.POINTER(RaNote), sz, C.POINTER(sz)]
+        msgs = (RaEvent * max(msgs_cap, 1))()
+        notes = (RaNote * max(notes_cap, 1))()
+        nm, nn = sz(0), sz(0)
+        st = f(self._h, msgs, msgs_cap, C.byref(nm), notes, notes_cap, C.byref(nn))
+        if st not in (RA_OK, RA_E_CAPACITY):
+            self._check(st, "fetch_output")
+        ok = st == RA_OK
+        return st, nm.value, nn.value, (list(msgs[: nm.value]) if ok else []), (list(notes[: nn.value]) if ok else [])
+
+    # -- split-phase calls (engine only) ---------------------------------------------------------------------
+    def submit(self, events: Sequence[RaEvent], msgs_cap: int, notes_cap: int):
+        """ra_engine_submit: returns the status and a ticket holding the buffers until collect()."""
+        f = self._fn("submit")
+        sz = C.c_size_t
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.POINTER(RaEvent), sz, C.POINTER(RaEvent), sz, C.POINTER(RaNote), sz]
+        n = len(events)
+        ev = (RaEvent * max(n, 1))(*events)
+        msgs = (RaEvent * max(msgs_cap, 1))()
+        notes = (RaNote * max(notes_cap, 1))()
+        st = f(self._h, ev, n, msgs, msgs_cap, notes, notes_cap)
+        return st, (ev, msgs, notes)
+
+    def collect(self, ticket):
+        f = self._fn("collect")
+        sz = C.c_size_t
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.POINTER(sz), C.POINTER(sz)]
+        nm, nn = sz(0), sz(0)
+        st = f(self._h, C.byref(nm), C.byref(nn))
+        _ev, msgs, notes = ticket
+        ok = st == RA_OK
+        return st, nm.value, nn.value, (list(msgs[: nm.value]) if ok else []), (list(notes[: nn.value]) if ok else [])
 
     def counters(self) -> dict:
         c = RaCounters()

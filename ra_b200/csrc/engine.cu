@@ -554,11 +554,12 @@ struct IoSlot {
     void* d_ev; size_t d_ev_bytes;            // device copy of the call's events
     OutHdr* hdr;                              // pinned + mapped
     cudaEvent_t h2d_done, done;
-    // where gather_out_kernel writes: the caller's buffers when they are pinned (ra_engine_alloc_host /
-    // ra_engine_register_host), else the slot's own pinned staging, copied out by ra_engine_collect
+    // gather_out_kernel compacts the outputs into the slot's device staging; the DMA to the caller's buffers is
+    // enqueued right behind it with PREDICTED sizes (what the previous call produced, plus a margin), so the
+    // call still has a single wait; collect tops up with a second copy in the rare step that produced more
     ra_event* user_msgs; ra_note* user_notes; size_t msgs_cap, notes_cap;
-    ra_event* st_msgs; size_t st_msgs_cap; ra_note* st_notes; size_t st_notes_cap;
-    int staged_msgs, staged_notes;
+    ra_event* d_msgs; size_t d_msgs_cap; ra_note* d_notes; size_t d_notes_cap;
+    size_t copied_msgs, copied_notes;
 };
 
 struct ra_engine {
@@ -570,9 +571,11 @@ struct ra_engine {
     int cur;
     u64 step_no, steps;
     u64 bar_epoch;                            // peer transport: barriers passed since the last reset
+    int flood_barrier;                        // peer transport: ra_engine_flood ends every step with the device barrier
     void* allocs[64]; int n_allocs;
     IoSlot io[RA_IO_SLOTS]; u32 io_head, io_tail;   // FIFO: submit fills io[io_head % SLOTS], collect drains io_tail
     int out_pending;                          // the last collect ended in RA_E_CAPACITY: outputs wait in the row slots
+    size_t pred_msgs, pred_notes;             // outputs of the last collected call (sizes the next DMA is enqueued with)
     int loc_dirty;                            // the flood host model may have left host events queued
     u64* d_offs; void* d_scan_tmp; size_t scan_tmp_bytes;
     u32* d_err;                               // [0] sticky ingest error (= Cols::abort), [1] peer barrier timeout
@@ -630,10 +633,8 @@ extern "C" void ra_engine_destroy(ra_engine* e)
     cudaFree(e->d_rows); cudaFree(e->d_scan_tmp);
     for (int i = 0; i < RA_IO_SLOTS; i++) {
         IoSlot& q = e->io[i];
-        cudaFree(q.d_ev);
+        cudaFree(q.d_ev); cudaFree(q.d_msgs); cudaFree(q.d_notes);
         if (q.hdr) cudaFreeHost(q.hdr);
-        if (q.st_msgs) cudaFreeHost(q.st_msgs);
-        if (q.st_notes) cudaFreeHost(q.st_notes);
         if (q.h2d_done) cudaEventDestroy(q.h2d_done);
         if (q.done) cudaEventDestroy(q.done);
     }
@@ -656,7 +657,7 @@ extern "C" int ra_engine_reset_empty(ra_engine* e)
     CK(cudaMemsetAsync(e->d_err, 0, 4 * sizeof(u32), e->stream));
     CK(cudaStreamSynchronize(e->stream));
     for (int i = 0; i < RA_IO_SLOTS; i++) e->io[i].busy = 0;
-    e->io_head = e->io_tail = 0; e->out_pending = 0; e->loc_dirty = 0;
+    e->io_head = e->io_tail = 0; e->out_pending = 0; e->loc_dirty = 0; e->pred_msgs = e->pred_notes = 0;
     return RA_OK;
 }
 
@@ -870,40 +871,28 @@ static bool host_ptr_mapped(const void* p, void** dev)
     return true;
 }
 
-template <typename T>
-static int ensure_pinned(ra_engine* e, T** p, size_t* cap, size_t need)
-{
-    if (*cap >= need && *p) return RA_OK;
-    if (*p) cudaFreeHost(*p);
-    void* q = nullptr;
-    const size_t nc = need < 1024 ? 1024 : need + need / 4;
-    cudaError_t ce = cudaHostAlloc(&q, nc * sizeof(T), cudaHostAllocMapped | cudaHostAllocPortable);
-    if (ce != cudaSuccess) { *p = nullptr; *cap = 0; return fail(e, ce, "cudaHostAlloc staging"); }
-    *p = (T*)q; *cap = nc;
-    return RA_OK;
-}
-
 static int enqueue_gather(ra_engine* e, IoSlot& q)
 {
-    void *dm = nullptr, *dn = nullptr;
     int rc;
-    q.staged_msgs = q.staged_notes = 0;
-    if (q.msgs_cap && !host_ptr_mapped(q.user_msgs, &dm)) {
-        if ((rc = ensure_pinned(e, &q.st_msgs, &q.st_msgs_cap, q.msgs_cap))) return rc;
-        q.staged_msgs = 1; host_ptr_mapped(q.st_msgs, &dm);
-    }
-    if (q.notes_cap && !host_ptr_mapped(q.user_notes, &dn)) {
-        if ((rc = ensure_pinned(e, &q.st_notes, &q.st_notes_cap, q.notes_cap))) return rc;
-        q.staged_notes = 1; host_ptr_mapped(q.st_notes, &dn);
-    }
+    if ((rc = ensure(e, &q.d_msgs, &q.d_msgs_cap, q.msgs_cap ? q.msgs_cap : 1))) return rc;
+    if ((rc = ensure(e, &q.d_notes, &q.d_notes_cap, q.notes_cap ? q.notes_cap : 1))) return rc;
     void* dh = nullptr;
     host_ptr_mapped(q.hdr, &dh);
     const u32 R = e->C.rows;
     CK(cub::DeviceScan::ExclusiveSum(e->d_scan_tmp, e->scan_tmp_bytes, PackedIt(e->C.out_n, PackCounts()), e->d_offs,
                                      (int)(R + 1), e->stream));
     gather_out_kernel<<<nblocks(e->C.tiles, 4), 128, 0, e->stream>>>(
-        e->C, e->d_offs, (ulonglong2*)dm, (u64)q.msgs_cap, (ulonglong2*)dn, (u64)q.notes_cap, (OutHdr*)dh, e->d_err);
+        e->C, e->d_offs, (ulonglong2*)q.d_msgs, (u64)q.msgs_cap, (ulonglong2*)q.d_notes, (u64)q.notes_cap, (OutHdr*)dh, e->d_err);
     CK(cudaGetLastError());
+    // the outputs follow by DMA, sized by what the previous call produced (+ 1/16): steady streams of batches
+    // produce steady amounts of output.  (A pinned destination -- ra_engine_alloc_host / ra_engine_register_host --
+    // makes it a true asynchronous copy; a pageable one is staged by the driver.)
+    q.copied_msgs = e->pred_msgs + e->pred_msgs / 16 + (e->pred_msgs ? 16 : 0);
+    q.copied_notes = e->pred_notes + e->pred_notes / 16 + (e->pred_notes ? 64 : 0);
+    if (q.copied_msgs > q.msgs_cap) q.copied_msgs = q.msgs_cap;
+    if (q.copied_notes > q.notes_cap) q.copied_notes = q.notes_cap;
+    if (q.copied_msgs) CK(cudaMemcpyAsync(q.user_msgs, q.d_msgs, q.copied_msgs * sizeof(ra_event), cudaMemcpyDeviceToHost, e->stream));
+    if (q.copied_notes) CK(cudaMemcpyAsync(q.user_notes, q.d_notes, q.copied_notes * sizeof(ra_note), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaEventRecord(q.done, e->stream));
     return RA_OK;
 }
@@ -971,8 +960,20 @@ static int finish_slot(ra_engine* e, IoSlot& q, size_t* n_msgs, size_t* n_notes,
         return bad == 1 ? RA_E_UNGROUPED : (bad == 2 ? RA_E_CAPACITY : RA_E_INVAL);
     }
     if (h.status & 0x100u) { e->out_pending = 1; return RA_E_CAPACITY; }   // nothing lost: ra_engine_fetch_output
-    if (q.staged_msgs && h.n_msgs) memcpy(q.user_msgs, q.st_msgs, (size_t)h.n_msgs * sizeof(ra_event));
-    if (q.staged_notes && h.n_notes) memcpy(q.user_notes, q.st_notes, (size_t)h.n_notes * sizeof(ra_note));
+    // top up what the predicted-size copies did not cover (first call, a burst)
+    bool more = false;
+    if (h.n_msgs > q.copied_msgs) {
+        CK(cudaMemcpyAsync(q.user_msgs + q.copied_msgs, q.d_msgs + q.copied_msgs, (size_t)(h.n_msgs - q.copied_msgs) * sizeof(ra_event),
+                           cudaMemcpyDeviceToHost, e->copy_stream));
+        more = true;
+    }
+    if (h.n_notes > q.copied_notes) {
+        CK(cudaMemcpyAsync(q.user_notes + q.copied_notes, q.d_notes + q.copied_notes, (size_t)(h.n_notes - q.copied_notes) * sizeof(ra_note),
+                           cudaMemcpyDeviceToHost, e->copy_stream));
+        more = true;
+    }
+    if (more) CK(cudaStreamSynchronize(e->copy_stream));
+    e->pred_msgs = (size_t)h.n_msgs; e->pred_notes = (size_t)h.n_notes;
     return RA_OK;
 }
 
@@ -1064,6 +1065,10 @@ extern "C" int ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per
         F.seed = seed; F.step = e->step_no + t;
         int rc = launch_step(e, F);
         if (rc) return rc;
+        if (e->flood_barrier && e->C.peer_mode) {               // lock step with the other shards, no host in the loop
+            e->bar_epoch++;
+            peer_barrier_kernel<<<1, 32, 0, e->stream>>>(e->C, e->bar_epoch, e->d_err);
+        }
     }
     CK(cudaEventRecord(e->ev1, e->stream));
     e->step_no += n_steps;
@@ -1136,6 +1141,13 @@ extern "C" int ra_engine_peer_barrier(ra_engine* e)
     e->bar_epoch++;
     peer_barrier_kernel<<<1, 32, 0, e->stream>>>(e->C, e->bar_epoch, e->d_err);
     CK(cudaGetLastError());
+    return RA_OK;
+}
+
+extern "C" int ra_engine_set_flood_barrier(ra_engine* e, int on)
+{
+    if (!e) return RA_E_INVAL;
+    e->flood_barrier = on ? 1 : 0;
     return RA_OK;
 }
 

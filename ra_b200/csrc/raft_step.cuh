@@ -1594,6 +1594,13 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
     const u32 type = R_type(e);
     u32 role = m_role(m);
     const bool nonempty = m_nruns(m) != 0;
+#ifdef RA_LEAN_FAST
+    // only the five steady-state shapes stay in the hot kernel (instruction-cache footprint): elections,
+    // votes and enforce-leadership go to the general kernel
+    if (!(type == RA_EV_AER || type == RA_EV_WRITTEN || type == RA_EV_AER_REPLY || type == RA_EV_COMMAND)) return false;
+    if (role != RA_FOLLOWER && role != RA_LEADER) return false;
+#endif
+#ifndef RA_LEAN_FAST
     if (role == RA_PRE_VOTE && type == RA_EV_AER && R_term(e) >= m.term && !m.C->pure) {
         // handle_pre_vote(#append_entries_rpc{}) :1175-1180: back to follower, the rpc is
         // re-queued ({next_event, Msg}) and handled as a follower right away
@@ -1604,6 +1611,7 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
         m.meta &= ~(0xFFFFFFull << 32);                            // become/3 :2166-2175
         role = RA_FOLLOWER;
     }
+#endif
     if (role == RA_FOLLOWER) {
         bool apply = false, reply = false;
         u64 reply_term = 0;
@@ -1636,6 +1644,7 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
             reply = (m.lw_idx != R_b(e) || m.lw_term != m.last_term) && leader != SLOT_NONE;
             reply_term = m.term;
             m.lw_idx = R_b(e); m.lw_term = m.last_term;
+#ifndef RA_LEAN_FAST
         } else if (type == RA_EV_PRE_VOTE) {                           // :1459-1466
             m.c_pack += 1u;
             if (MT_MEMBERSHIP(m.meta) == RA_VOTER) (void)process_pre_vote<MM>(m, RA_FOLLOWER, e);
@@ -1651,6 +1660,7 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
             MT_SET(m.meta, 0, 3, RA_PRE_VOTE);
             m.status |= RA_ST_ROLE_CHANGED;
             MT_SET(m.meta, 15, 4, 1);
+#endif
         } else return false;
         if (apply) evaluate_commit_index_follower(m);
         if (reply) emit_msg<MM>(m, leader, aer_reply(m, reply_term, true));
@@ -1664,12 +1674,15 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
         peers_ensure<MM>(m);              // the ONE place the hot kernel stages the peer columns
         bool quorum = false, chase = false, force = false;
         u32 mode = RP_PIPELINE;
+#ifndef RA_LEAN_FAST
         if (type == RA_EV_PRE_VOTE) {                                  // :952-957 enforce leadership
             // (with a consistent query in flight make_all_rpcs also re-sends heartbeats: general path)
             if (R_term(e) > m.term || ((m.meta >> 32) & 0xFFFFFFull) != 0 || q_index(m) != 0) return false;
             m.c_pack += 1u;
             mode = RP_ALL;
-        } else if (type == RA_EV_COMMAND) {                            // :644-729
+        } else
+#endif
+        if (type == RA_EV_COMMAND) {                            // :644-729
             const u64 n = R_n(e);
             if (n == 0 || !nonempty) return false;
             m.c_pack += 1u;
@@ -1697,7 +1710,12 @@ __device__ __forceinline__ bool fast_event(Member& m, const Rec& e)
         // exact shortcut: nothing evaluate_quorum reads has moved since it last ran in this step
         if (quorum && !(m.cold & 8u)) evaluate_quorum<MM>(m);
         // a chased {next_event, info, pipeline_rpcs}: one pass, the rest is deferred (contract 4)
-        if (rpc_pass<MM>(m, mode, force, false) && chase) { MT_SET(m.meta, 24, 1, 1); m.status |= RA_ST_PIPELINE_PENDING; }
+#ifdef RA_LEAN_FAST
+        if (rpc_pass<MM>(m, RP_PIPELINE, force, false) && chase)
+#else
+        if (rpc_pass<MM>(m, mode, force, false) && chase)
+#endif
+        { MT_SET(m.meta, 24, 1, 1); m.status |= RA_ST_PIPELINE_PENDING; }
         return true;
     }
     return false;

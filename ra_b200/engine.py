@@ -58,7 +58,8 @@ EXPORTS = ["ra_engine_create", "ra_engine_destroy", "ra_engine_load_rows", "ra_e
            "ra_engine_ipc_export", "ra_engine_ipc_import", "ra_engine_peer_barrier",
            "ra_engine_load_query_state", "ra_engine_read_query_state", "ra_engine_step_host",
            "ra_engine_submit", "ra_engine_submit_host", "ra_engine_collect", "ra_engine_pending_output",
-           "ra_engine_fetch_output", "ra_engine_register_host", "ra_engine_unregister_host"]
+           "ra_engine_fetch_output", "ra_engine_register_host", "ra_engine_unregister_host",
+           "ra_engine_set_flood_barrier"]
 HOST_EXPORTS = ["ra_wal_batch_to_events"]            # host-only helpers of the same library
 HOSTSIM_EXPORTS = ["ra_hostsim_create", "ra_hostsim_create_multi", "ra_hostsim_destroy", "ra_hostsim_run",
                    "ra_hostsim_stats", "ra_hostsim_breakdown"]

@@ -203,6 +203,12 @@ class NvlinkPeerTransport:
             if k != shard.shard:
                 shard.ipc_import(k, raw)
         self._tok = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", shard.dev))
+        # with the device barrier a multi-step flood needs no host between steps: ra_engine_flood appends it
+        self.fused = bool(self.device_barrier)
+        l = lib()
+        l.ra_engine_set_flood_barrier.restype = C.c_int
+        l.ra_engine_set_flood_barrier.argtypes = [C.c_void_p, C.c_int]
+        shard.eng._check(l.ra_engine_set_flood_barrier(shard.eng._h, 1 if self.fused else 0), "set_flood_barrier")
         dist.barrier()
 
     def exchange(self) -> None:
@@ -233,6 +239,10 @@ class ShardedFlood:
         self.t.exchange()
 
     def run(self, n_steps: int, cmds: int = 1, permille: int = 0, seed: int = 1) -> None:
+        if getattr(self.t, "fused", False):                  # every step ends with the device-side barrier
+            for s in self.t.shards:
+                s.eng.flood(n_steps, cmds, permille, seed, sync=False)
+            return
         for _ in range(n_steps):
             for s in self.t.shards:
                 s.eng.flood(1, cmds, permille, seed, sync=False)

@@ -29,6 +29,7 @@ struct ra_emu {
     int cur;
     u64 step_no, steps;
     void* allocs[64]; int n_allocs;
+    int out_pending;                                  // a step's outputs did not fit: they wait in the row slots
     int sub_busy, sub_rc; size_t sub_nm, sub_nn;      // the one "submitted" call (ra_engine_submit_host shim)
 };
 
@@ -317,7 +318,8 @@ extern "C" int ra_emu_fetch_output(ra_emu* e, ra_event* msgs, size_t msgs_cap, s
     for (u32 r = 0; r < R; r++) { tm += C.out_n[r] & 0xffffu; tn += C.out_n[r] >> 16; }
     if (n_msgs) *n_msgs = tm;
     if (n_notes) *n_notes = tn;
-    if (tm > msgs_cap || tn > notes_cap) return RA_E_CAPACITY;
+    if (tm > msgs_cap || tn > notes_cap) { e->out_pending = 1; return RA_E_CAPACITY; }
+    e->out_pending = 0;
     size_t om = 0, on = 0;
     for (u32 r = 0; r < R; r++) {
         const u32 v = C.out_n[r];
@@ -335,6 +337,7 @@ extern "C" int ra_emu_step(ra_emu* e, const ra_event* ev, size_t n_ev,
                            ra_note* notes, size_t notes_cap, size_t* n_notes)
 {
     if (!e || (!ev && n_ev) || n_ev > 0x7fffffffull) return RA_E_INVAL;
+    if (e->out_pending) return RA_E_CAPACITY;                    // ra_emu_fetch_output first
     const Cols& C = e->C;
     const u32 R = C.rows;
     for (u32 r = 0; r < R; r++) C.loc_n[r] = 0;                  // clear_loc_kernel

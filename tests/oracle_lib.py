@@ -43,6 +43,14 @@ class Oracle(abi.Backend):
                                           threads), "flood")
 
 
+    def set_sample(self, stride: int, offset: int, total_groups: int) -> None:
+        """group g of this oracle plays global group offset + g * stride of a flood over total_groups groups"""
+        f = lib().ra_oracle_set_sample
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        self._check(f(self._h, stride, offset, total_groups), "set_sample")
+
+
 def agreed_commit(indexes):
     arr = (C.c_uint64 * len(indexes))(*indexes)
     return int(lib().ra_oracle_agreed_commit(arr, len(indexes)))
