@@ -223,13 +223,13 @@ def run_engine(args):
         fl = ShardedFlood(NvlinkPeerTransport(sh) if peer else NcclTransport(sh))
         fl.bootstrap()
         seed = args.seed                                         # one global host model
-        flood = lambda n: fl.run(n, args.cmds, args.permille, seed)
+        flood = lambda n: fl.run(n, args.cmds, args.permille, seed, faults=args.faults)
     else:
         eng = Engine(G, M, device=dev, route_on_device=True)
         eng.reset_empty()
         eng.step([abi.ev_simple(eng.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(G)])
         seed = args.seed + rank
-        flood = lambda n: eng.flood(n, args.cmds, args.permille, seed=seed, sync=False)
+        flood = lambda n: eng.flood(n, args.cmds, args.permille, seed=seed, sync=False, faults=args.faults)
     flood(args.settle)                                           # elect leaders, fill the pipeline
     flood(args.warmup)                                           # W untimed warm-up steps
     torch.cuda.synchronize(dev)
@@ -340,6 +340,21 @@ def run_engine(args):
         hf.close()
         eng2.close()
 
+    latency = None
+    if world == 1 and args.latency:
+        try:
+            latency = latency_probe(dev)
+        except Exception as ex:
+            latency = {"error": repr(ex)[:200]}
+    extras = {}
+    if args.extra_configs and args.config == 3:
+        eng.close()
+        ks = [2, 4, 5] if world == 1 else [4]
+        for k in ks:
+            try:
+                extras["config%d" % k] = extra_config(k, world, rank, local)
+            except Exception as ex:                      # an extra must never take the headline down with it
+                extras["config%d" % k] = {"error": repr(ex)[:200]}
     if rank != 0:
         return
     peak, peak_src = hbm_peak()
@@ -356,16 +371,10 @@ def run_engine(args):
         "metric": METRIC, "value": value, "unit": "commits/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "%d groups x %d members per GPU, steady-state AppendEntries flood, %d command(s) per "
-                               "leader per step, %.1f%% election timeouts per step (BASELINE.json configs[2] shape)"
-                               % (G, M, args.cmds, args.permille / 10.0),
-                   "groups_per_gpu": G, "members": M, "cmds_per_step": args.cmds,
-                   "election_permille": args.permille, "parallelism": par,
-                   "placement": "spread" if spread else "group",
-                   "l2": "working set (SoA %.0f MB + mailboxes) exceeds the 126 MB L2; no explicit flush"
-                         % (G * M * 392 / 1e6),
-                   "events_per_step": events / args.steps, "commits_per_step": commits / args.steps,
-                   "msgs_dropped": dropped},
+        "config": workload_config(args),
+        "run": {"parallelism": par, "placement": "spread" if spread else ("group" if world > 1 else "single GPU"),
+                "events_per_step": events_all / args.steps, "commits_per_step": commits_all / args.steps,
+                "msgs_dropped": dropped},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -378,11 +387,141 @@ def run_engine(args):
     }
     if parity:
         out["parity"] = parity
+    if extras:
+        out["configs"] = extras
+    if latency:
+        out["latency"] = latency
     if e2e:
         out["e2e"] = e2e
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(args, sample_groups=min(G, args.cpu_groups), steps=args.cpu_steps)
     print(json.dumps(out))
+
+
+CONFIGS = {
+    # BASELINE.json configs[1..4] as flood parameters (groups are per GPU unless "total")
+    2: dict(groups=10_000, members=5, cmds=1, permille=0, faults=None,
+            what="configs[1]: 10k groups x 5, steady-state AppendEntries, 1 entry/RPC (20 MB of state: L2-resident)"),
+    3: dict(groups=100_000, members=5, cmds=1, permille=10, faults=None,
+            what="configs[2]: 100k groups x 5, AppendEntries + 1 % election timeouts per step"),
+    4: dict(groups=100_000, members=5, cmds=64, permille=10, faults=None, total=True,
+            what="configs[3]: 100k groups x 5 IN TOTAL over the GPUs (strong scaling), 64-entry pipelined AppendEntries"),
+    5: dict(groups=10_000, members=7, cmds=1, permille=0, faults=(5, 20, 10, 32),
+            what="configs[4]: 10k groups x 7, 0.5 % AppendEntries lost, 2 % lagging fsync, 1 % of groups partitioned "
+                 "per 32-step window (next_index back-off, term-conflict / truncate paths)"),
+}
+
+
+def extra_config(k: int, world: int, rank: int, local: int, steps: int = 100, warmup: int = 10, settle: int = 40) -> dict:
+    """One more configuration on the device-resident flood path, timed like the headline (CUDA events, max over
+    ranks).  Single GPU: one engine; N > 1 (config 4): members spread over the ranks, peer-store transport."""
+    import torch
+    from ra_b200 import abi
+    from ra_b200.engine import Engine
+    c = CONFIGS[k]
+    G, M = c["groups"], c["members"]
+    if world > 1:
+        from ra_b200.sharded import NvlinkPeerTransport, Shard, ShardedFlood
+        gl = G // world if c.get("total") else G
+        sh = Shard(gl, M, world, rank, device=local, buckets=False)
+        eng = sh.eng
+        fl = ShardedFlood(NvlinkPeerTransport(sh))
+        fl.bootstrap()
+        flood = lambda n: fl.run(n, c["cmds"], c["permille"], 0xA00 + k, faults=c["faults"])
+    else:
+        gl = G
+        eng = Engine(G, M, device=local, route_on_device=True)
+        eng.reset_empty()
+        eng.step([abi.ev_simple(eng.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(G)])
+        flood = lambda n: eng.flood(n, c["cmds"], c["permille"], seed=0xA00 + k, sync=False, faults=c["faults"])
+    flood(settle); flood(warmup)
+    torch.cuda.synchronize(local); eng.sync()
+    c0 = eng.counters()
+    barrier_sync(world, local)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        t0.record(); flood(steps); t1.record()
+        torch.cuda.synchronize(local)
+        ms = t0.elapsed_time(t1)
+    else:
+        flood(steps); eng.sync()
+        ms, _ = eng.last_kernel_ms()
+    barrier_sync(world, local)
+    c1 = eng.counters()
+    ms_max, commits, events = reduce_max_sum(world, local, ms, c1["commits"] - c0["commits"], c1["events"] - c0["events"])
+    out = {"what": c["what"], "groups_per_gpu": gl, "members": M, "cmds_per_step": c["cmds"], "election_permille": c["permille"],
+           "faults": c["faults"], "value": commits / (ms_max * 1e-3), "unit": "commits/s", "ms_per_step": ms_max / steps,
+           "steps": steps, "events_per_step": events / steps, "msgs_dropped": c1["msgs_dropped"] - c0["msgs_dropped"],
+           "fatal_rows": c1["fatal_rows"], "scaling": "strong" if c.get("total") and world > 1 else "n/a"}
+    if c["cmds"] == 1:
+        out["roofline_frac"] = out["value"] / world * b_commit(M) / 1e9 / hbm_peak()[0]
+    eng.close()
+    return out
+
+
+def latency_probe(dev: int, groups: int = 100_000, members: int = 5) -> dict:
+    """Round trip of ONE ra_engine_step_host call (what a batching process pays per batch) on a 500k-row engine,
+    for batches of 1 / 1k / 100k command events, host buffers pinned (ra_engine_alloc_host) and pageable.
+    p50 / p99 over repeated calls; every call also evaluates what the previous calls left in the mailboxes."""
+    import ctypes as C
+    from ra_b200 import abi
+    from ra_b200.engine import Engine, lib
+    eng = Engine(groups, members, device=dev, route_on_device=True)
+    eng.reset_empty()
+    eng.step([abi.ev_simple(eng.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(groups)])
+    eng.flood(40, 1, 0, seed=1)                      # leaders = slot 0 of every group (rows 0 .. groups-1)
+    l = lib()
+    f = l.ra_engine_step_host
+    sz = C.c_size_t
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, sz, C.c_void_p, sz, C.POINTER(sz), C.c_void_p, sz, C.POINTER(sz)]
+    l.ra_engine_alloc_host.restype = C.c_void_p
+    l.ra_engine_alloc_host.argtypes = [sz]
+    l.ra_engine_free_host.argtypes = [C.c_void_p]
+    notes_cap, msgs_cap = groups * members * 3, 1024
+    nm, nn = sz(0), sz(0)
+    out = {}
+    for kind in ("pinned", "pageable"):
+        nbytes_ev, nbytes_n, nbytes_m = 100_000 * 32, notes_cap * 32, msgs_cap * 64
+        if kind == "pinned":
+            pev, pn, pm = (l.ra_engine_alloc_host(b) for b in (nbytes_ev, nbytes_n, nbytes_m))
+            keep = None
+        else:
+            keep = [C.create_string_buffer(b) for b in (nbytes_ev, nbytes_n, nbytes_m)]
+            pev, pn, pm = (C.addressof(k) for k in keep)
+        evs = (abi.RaHostEvent * 100_000).from_address(pev)
+        for i in range(100_000):
+            evs[i].row = i; evs[i].type = abi.EV_COMMAND; evs[i].flags = 0; evs[i].n = 1
+        for _ in range(6):                                # drain what the flood left in flight
+            eng._check(f(eng._h, pev, 0, pm, msgs_cap, C.byref(nm), pn, notes_cap, C.byref(nn)), "step_host")
+        for n, reps in ((1, 60), (1000, 60), (100_000, 15)):
+            ts = []
+            for _ in range(reps + 3):
+                t0 = time.perf_counter()
+                eng._check(f(eng._h, pev, n, pm, msgs_cap, C.byref(nm), pn, notes_cap, C.byref(nn)), "step_host")
+                ts.append((time.perf_counter() - t0) * 1e3)
+            ts = sorted(ts[3:])
+            out["%s_%d" % (kind, n)] = {"p50_ms": ts[len(ts) // 2], "p99_ms": ts[min(len(ts) - 1, int(len(ts) * 0.99))],
+                                       "notes_out": int(nn.value)}
+        if kind == "pinned":
+            for q in (pev, pn, pm):
+                l.ra_engine_free_host(q)
+    eng.close()
+    out["how"] = ("one ra_engine_step_host call per sample: n COMMAND events to n leaders of a %d-row engine "
+                  "(route_on_device), wall clock around the call" % (groups * members))
+    return out
+
+
+def workload_config(args) -> dict:
+    """The `config` object of BOTH arms (engine and --impl reference): the workload, nothing measured."""
+    G, M = args.groups, args.members
+    return {"workload": "%d groups x %d members per GPU, steady-state AppendEntries flood, %d command(s) per leader per "
+                        "step, %.1f%% election timeouts per step (BASELINE.json configs[%d])%s"
+                        % (G, M, args.cmds, args.permille / 10.0, args.config - 1,
+                           (", faults %s" % (args.faults,)) if args.faults else ""),
+            "groups_per_gpu": G, "members": M, "cmds_per_step": args.cmds, "election_permille": args.permille,
+            "l2": "working set (SoA %.0f MB + mailboxes) %s the 126 MB L2; no explicit flush"
+                  % (G * M * 392 / 1e6, "exceeds" if G * M * 392 > 126e6 else "fits in")}
 
 
 def parity_sample(args, eng, world: int, rank: int, spread: bool, seed: int, flood_steps: int, stride: int = 97) -> dict:
@@ -398,7 +537,8 @@ def parity_sample(args, eng, world: int, rank: int, spread: bool, seed: int, flo
     o.set_sample(stride, 0, total)
     o.reset_empty()
     o.step([abi.ev_simple(o.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(n)])
-    o.flood(flood_steps, args.cmds, args.permille, seed=seed, threads=max(1, min(8, effective_cpus() // max(1, world))))
+    o.flood(flood_steps, args.cmds, args.permille, seed=seed, threads=max(1, min(8, effective_cpus() // max(1, world))),
+            faults=args.faults)
     want = o.read_rows(range(o.n_rows))
     ids, exp = [], []
     for i in range(n):
@@ -443,8 +583,22 @@ def effective_cpus() -> int:
     return max(1, n)
 
 
-def cpu_baseline(args, sample_groups: int, steps: int, threads: int | None = None) -> dict:
-    """The oracle (CPU port of ra_server's hot path) on a bounded sample of the same workload."""
+def cpu_model() -> str:
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_baseline(args, sample_groups: int, steps: int, threads: int | None = None, min_seconds: float = 2.0) -> dict:
+    """The oracle (CPU port of ra_server's hot path) on the same workload: all host cores, then one core.
+
+    The timed region is whole floods of `chunk` steps repeated until it is at least `min_seconds` long, after a
+    warm-up flood (thread start-up, page faults and the first growth steps of the log arrays happen before it),
+    so the figure does not depend on the step count asked for."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import Oracle
     from ra_b200 import abi
@@ -452,17 +606,32 @@ def cpu_baseline(args, sample_groups: int, steps: int, threads: int | None = Non
     o = Oracle(sample_groups, args.members, route_on_device=True)
     o.reset_empty()
     o.step([abi.ev_simple(o.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(sample_groups)])
-    o.flood(args.settle, args.cmds, args.permille, seed=args.seed, threads=cores)
+    o.flood(args.settle, args.cmds, args.permille, seed=args.seed, threads=cores, faults=args.faults)
+    chunk = max(5, min(20, steps))
+    o.flood(chunk, args.cmds, args.permille, seed=args.seed, threads=cores, faults=args.faults)      # warm-up
     c0 = o.counters()
     t0 = time.perf_counter()
-    o.flood(steps, args.cmds, args.permille, seed=args.seed, threads=cores)
-    dt = time.perf_counter() - t0
+    done = 0
+    while True:
+        o.flood(chunk, args.cmds, args.permille, seed=args.seed, threads=cores, faults=args.faults)
+        done += chunk
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or done >= 2000:
+            break
     c1 = o.counters()
+    # one core, same rows (a few steps are enough: ~10x slower per step)
+    s1 = max(2, min(5, chunk // 4))
+    t1 = time.perf_counter()
+    o.flood(s1, args.cmds, args.permille, seed=args.seed, threads=1, faults=args.faults)
+    dt1 = time.perf_counter() - t1
+    c2 = o.counters()
     o.close()
     return {"value": (c1["commits"] - c0["commits"]) / dt, "unit": "commits/s", "cores": cores, "kind": "port",
-            "sample": "%d groups x %d members, %d steps of the same flood (%.1f s); C restatement of "
-                      "ra_server.erl, not BEAM" % (sample_groups, args.members, steps, dt),
-            "seconds": dt, "ms_per_step": dt * 1e3 / steps}
+            "cpu_model": cpu_model(),
+            "sample": "%d groups x %d members (the full workload), %d steps of the same flood in %.1f s after a "
+                      "warm-up flood; C restatement of ra_server.erl, not BEAM" % (sample_groups, args.members, done, dt),
+            "seconds": dt, "ms_per_step": dt * 1e3 / done, "steps": done,
+            "one_core": {"value": (c2["commits"] - c1["commits"]) / dt1, "unit": "commits/s", "steps": s1, "seconds": dt1}}
 
 
 def run_reference(args):
@@ -470,17 +639,14 @@ def run_reference(args):
     if rank != 0:
         return
     G, M = args.groups, args.members
-    # every step is a bounded sample of the workload: cpu_groups groups instead of G
+    # the full workload (cpu_groups caps it for small hosts); whole floods repeated for >= 2 s, see cpu_baseline
     sg = min(G, args.cpu_groups)
     cb = cpu_baseline(args, sample_groups=sg, steps=args.steps)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "commits/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": {"workload": "%d groups x %d members per GPU, steady-state AppendEntries flood, %d command(s) per "
-                                  "leader per step, %.1f%% election timeouts per step (BASELINE.json configs[2] shape)"
-                                  % (G, M, args.cmds, args.permille / 10.0),
-                      "sample_groups": sg, "members": M, "cmds_per_step": args.cmds,
-                      "election_permille": args.permille},
+           "config": workload_config(args),
+           "run": {"groups": sg, "threads": cb["cores"], "steps_timed": cb["steps"], "seconds": cb["seconds"]},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "commits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -503,7 +669,7 @@ def main():
     ap.add_argument("--e2e-engines", type=int, default=4,
                     help="e2e leg at N=1: partitions (engines holding disjoint groups) one host thread pipelines "
                          "through ra_engine_submit_host / ra_engine_collect")
-    ap.add_argument("--cpu-groups", type=int, default=50_000)
+    ap.add_argument("--cpu-groups", type=int, default=100_000, help="groups of the CPU legs (default: the full workload)")
     ap.add_argument("--cpu-steps", type=int, default=300)
     ap.add_argument("--placement", default="spread", choices=["spread", "group"],
                     help="N>1: spread = members of a group on different GPUs + NCCL all-to-all of RPC records; "
@@ -513,8 +679,19 @@ def main():
                          "a2a = per-destination buckets + NCCL all_to_all_single + deliver kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configs[config-1] as the headline workload (default 3 = configs[2])")
+    ap.add_argument("--no-extra-configs", dest="extra_configs", action="store_false",
+                    help="skip the keyed entries for the other configs (N=1: 2, 4, 5; N>1: 4 strong-scaled)")
+    ap.add_argument("--no-latency", dest="latency", action="store_false", help="skip the per-call latency probe (N=1)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle replay of every 97th group of this run")
     args = ap.parse_args()
+    args.faults = None
+    if args.config != 3:
+        c = CONFIGS[args.config]
+        args.groups, args.members, args.cmds, args.permille, args.faults = c["groups"], c["members"], c["cmds"], c["permille"], c["faults"]
+        if c.get("total"):
+            args.groups = c["groups"] // max(1, int(os.environ.get("WORLD_SIZE", "1")))
     if args.warmup < 3:
         args.warmup = 3
     try:

@@ -366,6 +366,25 @@ int  ra_engine_fetch_output(ra_engine* e, ra_event* msgs, size_t msgs_cap, size_
  */
 int  ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per_step,
                      uint32_t election_permille, uint64_t seed);
+/*
+ * The same flood with fault injection (BASELINE.json configs[4]: follower lag / log-mismatch): all deterministic,
+ * keyed by (seed, step, GLOBAL group / row ids), so the CPU oracle and a sharded run reproduce them exactly.
+ *   drop_permille       an AppendEntries record evaluated at step t by row r from sender s is lost iff
+ *                       hi32(mix64(seed ^ t*K1 ^ r*K2 ^ (s+1)<<56)) mod 1000 < drop_permille  (-> `missing` ->
+ *                       await_condition -> failure reply -> next_index back-off)
+ *   withhold_permille   the WRITTEN events for a row's WAL_APPEND notes of step t are not produced (a lagging
+ *                       fsync: a later notification covers the range) iff hash(seed, t, r) mod 1000 < it
+ *   partition_permille  in every window of partition_steps steps, a group has one member cut off with that
+ *                       probability (chosen by hash(seed, window, group)): it evaluates no mailbox record and
+ *                       nobody evaluates a record from it.  When it is the leader the others elect a new one and
+ *                       the old leader later rejoins with an unreplicated tail (term-conflict / truncate path).
+ * Lost records are counted in msgs_dropped.  All zero = ra_engine_flood.
+ */
+typedef struct ra_flood_faults {
+    uint32_t drop_permille, withhold_permille, partition_permille, partition_steps;
+} ra_flood_faults;
+int  ra_engine_flood_faults(ra_engine* e, uint32_t n_steps, uint32_t cmds_per_step, uint32_t election_permille,
+                            uint64_t seed, const ra_flood_faults* faults);
 int  ra_engine_sync(ra_engine* e);
 int  ra_engine_counters(ra_engine* e, ra_counters* out);     /* syncs */
 /* diagnostics: out[role * 16 + event_type] = events that were not covered by a steady-state fast

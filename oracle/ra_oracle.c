@@ -107,6 +107,9 @@ struct ra_oracle {
     u32 s_stride, s_offset, s_total;
 };
 
+/* flood fault injection (include/ra_engine.h, ra_flood_faults): contract, keyed by global ids */
+struct flood_faults { u32 drop, withhold, part, part_len; };
+
 /* per-row, per-step output context */
 typedef struct {
     ra_oracle *o;
@@ -116,6 +119,8 @@ typedef struct {
     u32 status;                 /* RA_ST_* */
     u32 fatal_code;
     u32 unconsumed;             /* host events refused by the note budget */
+    const struct flood_faults *ff; /* fault injection of the flood in progress (NULL otherwise) */
+    u64 ff_seed, ff_step;
     u8  role_at_start;
     u8  sent_to[RA_MAX_MEMBERS]; /* routed mode: records put in (self -> slot) mailbox */
     ra_counters *cnt;
@@ -347,8 +352,36 @@ static void budget_drop_record(ctx_t *c)
 { c->status |= RA_ST_NOTE_OVERFLOW | RA_ST_MSG_DROPPED; c->cnt->msgs_dropped++; }
 static void budget_refuse_local(ctx_t *c) { c->status |= RA_ST_NOTE_OVERFLOW; c->unconsumed++; }
 static void process_event(ctx_t *c, const ra_event *in);
+static u64 mix64(u64 x);
+static void flood_ids(const ctx_t *c, u64 *gg, u64 *gr)
+{
+    const ra_oracle *o = c->o; const member_t *m = c->m;
+    u32 G = o->cfg.n_groups, g = m->row % G;
+    *gg = g; *gr = m->row;
+    if (o->s_stride) { *gg = (u64)o->s_offset + (u64)g * o->s_stride; *gr = (u64)m->self_slot * o->s_total + *gg; }
+}
+/* contract: is this mailbox record lost before the row evaluates it? */
+static int flood_lost(const ctx_t *c, const ra_event *e)
+{
+    const struct flood_faults *f = c->ff;
+    if (!f || !(f->drop | f->part)) return 0;
+    u64 gg, gr; flood_ids(c, &gg, &gr);
+    if (f->part) {
+        u64 w = c->ff_step / f->part_len;
+        u32 h = (u32)(mix64(c->ff_seed ^ (w * 0xC2B2AE3D27D4EB4Full) ^ (gg * 0x165667B19E3779F9ull)) >> 32);
+        if (h % 1000u < f->part) { u32 p = (h / 1000u) % c->m->n_members; if (p == c->m->self_slot || p == e->from_slot) return 1; }
+    }
+    if (f->drop && e->type == RA_EV_AER) {
+        u32 h = (u32)(mix64(c->ff_seed ^ (c->ff_step * 0x9E3779B97F4A7C15ull) ^ (gr * 0xD6E8FEB86659FD93ull) ^ ((u64)(e->from_slot + 1) << 56)) >> 32);
+        if (h % 1000u < f->drop) return 1;
+    }
+    return 0;
+}
 static void take_record(ctx_t *c, const ra_event *e)
-{ if (!c->m->fatal && !note_budget_ok(c)) budget_drop_record(c); else process_event(c, e); }
+{
+    if (!c->m->fatal && flood_lost(c, e)) { c->cnt->msgs_dropped++; return; }
+    if (!c->m->fatal && !note_budget_ok(c)) budget_drop_record(c); else process_event(c, e);
+}
 static void take_local(ctx_t *c, const ra_event *e)
 { if (!c->m->fatal && !note_budget_ok(c)) budget_refuse_local(c); else process_event(c, e); }
 
@@ -1736,7 +1769,7 @@ static u64 mix64(u64 x)
 
 typedef struct {
     ra_oracle *o; u32 g0, g1; u32 n_steps, cmds, permille; u64 seed; ra_counters cnt;
-    u64 step0;
+    u64 step0; const struct flood_faults *ff;
 } flood_arg_t;
 
 /* host model for one row after its step: notes -> next step's local events */
@@ -1752,6 +1785,9 @@ static void host_model(ra_oracle *o, ctx_t *c, u64 step, u32 cmds, u32 permille,
     int w[2] = { -1, -1 };
     for (u32 i = 0; i < c->n_notes; i++)
         if (c->notes[i].type == RA_NOTE_WAL_APPEND) { w[0] = w[1]; w[1] = (int)i; }
+    if (c->ff && c->ff->withhold && w[1] >= 0 &&           /* a lagging fsync: no notification this step */
+        (u32)(mix64(seed ^ (step * 0xA0761D6478BD642Full) ^ (grow * 0xE7037ED1A0B428DBull)) >> 32) % 1000u < c->ff->withhold)
+        w[0] = w[1] = -1;
     for (int j = 0; j < 2; j++) {
         if (w[j] < 0) continue;
         ra_event e; memset(&e, 0, sizeof e);
@@ -1793,7 +1829,7 @@ int ra_oracle_set_sample(ra_oracle *o, uint32_t stride, uint32_t offset, uint32_
 }
 
 static void flood_groups(ra_oracle *o, u32 g0, u32 g1, u32 n_steps, u32 cmds, u32 permille,
-                         u64 seed, u64 step0, ra_counters *cnt)
+                         u64 seed, u64 step0, ra_counters *cnt, const struct flood_faults *ff)
 {
     u32 M = o->cfg.n_members, G = o->cfg.n_groups;
     /* groups are independent: a shard can run all its steps back to back.  `cur` is
@@ -1808,6 +1844,7 @@ static void flood_groups(ra_oracle *o, u32 g0, u32 g1, u32 n_steps, u32 cmds, u3
                 ctx_t c; ctx_begin(&c, o, m, cnt, 1);
                 /* process_row_prologue/publish use o->cur: emulate with a local copy */
                 ra_oracle view = *o; view.cur = cur; c.o = &view;
+                c.ff = ff; c.ff_seed = seed; c.ff_step = step0 + t;
                 if (!m->fatal) {
                     process_row_prologue(&c);
                     u32 nl = o->loc_n[row];
@@ -1829,14 +1866,22 @@ static void flood_groups(ra_oracle *o, u32 g0, u32 g1, u32 n_steps, u32 cmds, u3
 static void *flood_thread(void *p)
 {
     flood_arg_t *a = (flood_arg_t *)p;
-    flood_groups(a->o, a->g0, a->g1, a->n_steps, a->cmds, a->permille, a->seed, a->step0, &a->cnt);
+    flood_groups(a->o, a->g0, a->g1, a->n_steps, a->cmds, a->permille, a->seed, a->step0, &a->cnt, a->ff);
     return NULL;
 }
 
 int ra_oracle_flood(ra_oracle *o, uint32_t n_steps, uint32_t cmds_per_step,
                     uint32_t election_permille, uint64_t seed, uint32_t threads)
+{ return ra_oracle_flood_faults(o, n_steps, cmds_per_step, election_permille, seed, threads, NULL); }
+
+int ra_oracle_flood_faults(ra_oracle *o, uint32_t n_steps, uint32_t cmds_per_step, uint32_t election_permille,
+                           uint64_t seed, uint32_t threads, const ra_flood_faults *faults)
 {
     if (!o || !o->cfg.route_on_device) return RA_E_INVAL;
+    if (faults && faults->partition_permille && !faults->partition_steps) return RA_E_INVAL;
+    struct flood_faults ffv, *ff = NULL;
+    if (faults) { ffv.drop = faults->drop_permille; ffv.withhold = faults->withhold_permille;
+                  ffv.part = faults->partition_permille; ffv.part_len = faults->partition_steps; ff = &ffv; }
     if (threads < 1) threads = 1;
     if (threads > o->cfg.n_groups) threads = o->cfg.n_groups;
     flood_arg_t *args = (flood_arg_t *)calloc(threads, sizeof *args);
@@ -1845,7 +1890,7 @@ int ra_oracle_flood(ra_oracle *o, uint32_t n_steps, uint32_t cmds_per_step,
     for (u32 i = 0; i < threads; i++) {
         args[i].o = o; args[i].g0 = (u32)((u64)G * i / threads); args[i].g1 = (u32)((u64)G * (i + 1) / threads);
         args[i].n_steps = n_steps; args[i].cmds = cmds_per_step; args[i].permille = election_permille;
-        args[i].seed = seed; args[i].step0 = o->step_no;
+        args[i].seed = seed; args[i].step0 = o->step_no; args[i].ff = ff;
         if (threads == 1) flood_thread(&args[i]);
         else pthread_create(&th[i], NULL, flood_thread, &args[i]);
     }

@@ -30,6 +30,8 @@ int  ra_oracle_step(ra_oracle* o, const ra_event* ev, size_t n_ev,
 /* threads > 1: groups are sharded statically over that many pthreads */
 int  ra_oracle_flood(ra_oracle* o, uint32_t n_steps, uint32_t cmds_per_step,
                      uint32_t election_permille, uint64_t seed, uint32_t threads);
+int  ra_oracle_flood_faults(ra_oracle* o, uint32_t n_steps, uint32_t cmds_per_step, uint32_t election_permille,
+                            uint64_t seed, uint32_t threads, const ra_flood_faults* faults);
 int  ra_oracle_step_host(ra_oracle* o, const ra_host_event* ev, size_t n_ev, ra_event* msgs, size_t msgs_cap,
                          size_t* n_msgs, ra_note* notes, size_t notes_cap, size_t* n_notes);
 int  ra_oracle_counters(ra_oracle* o, ra_counters* out);

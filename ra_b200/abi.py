@@ -153,6 +153,12 @@ class RaQueryState(C.Structure):
         return (self.row, self.query_index, self.agreed_index, tuple(self.peer_query_index[:n_members]))
 
 
+class RaFloodFaults(C.Structure):
+    """ra_flood_faults: (drop_permille, withhold_permille, partition_permille, partition_steps)"""
+    _fields_ = [("drop_permille", C.c_uint32), ("withhold_permille", C.c_uint32),
+                ("partition_permille", C.c_uint32), ("partition_steps", C.c_uint32)]
+
+
 class RaEngineCfg(C.Structure):
     _fields_ = [("n_groups", C.c_uint32), ("n_members", C.c_uint32),
                 ("max_pipeline_count", C.c_uint32), ("max_aer_batch", C.c_uint32),

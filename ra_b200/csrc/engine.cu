@@ -252,6 +252,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             if (rec_has_tail(c0)) { t2 = sp[2 * RT + lane]; t3 = sp[3 * RT + lane]; }
             const Rec e = rec_decode(c0, c1, t2, t3, r);
             if (MT_FATAL(m.meta)) m.c_pack += 1u;
+            else if (p < NPM && flood_lost<MM>(F, C, m, r, e)) m.c_pack += 1u << 20;   // fault injection: lost in transit
             else if (!note_budget_ok(m) || C.pure || !fast_event<MM>(m, e)) {
                 stalled = true;                                 // planes are consumed in bit order:
                 rem = mine & ~(((mask_t)1 << p) - 1);           // p and up are left for the general kernel
@@ -330,6 +331,7 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
                 const u32 p = __ffs(rem_mbox) - 1; rem_mbox &= rem_mbox - 1;
                 const Rec e = ld_rec_plane(C.mbox[cur], C.tiles, p, r);
                 if (MT_FATAL(m.meta)) m.c_pack += 1u;
+                else if (flood_lost<MM>(F, C, m, r, e)) m.c_pack += 1u << 20;
                 else if (!note_budget_ok(m)) budget_drop_record(m);
                 else if (C.pure || !fast_event<MM>(m, e)) { process_event<MM>(m, e); m.cold &= ~8u; }
             }
@@ -1056,12 +1058,19 @@ extern "C" int ra_engine_unregister_host(void* p)
 
 extern "C" int ra_engine_flood(ra_engine* e, uint32_t n_steps, uint32_t cmds_per_step,
                                uint32_t election_permille, uint64_t seed)
+{ return ra_engine_flood_faults(e, n_steps, cmds_per_step, election_permille, seed, nullptr); }
+
+extern "C" int ra_engine_flood_faults(ra_engine* e, uint32_t n_steps, uint32_t cmds_per_step,
+                                      uint32_t election_permille, uint64_t seed, const ra_flood_faults* ff)
 {
     if (!e || !e->C.routed) return RA_E_INVAL;
+    if (ff && ff->partition_permille && !ff->partition_steps) return RA_E_INVAL;
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaEventRecord(e->ev0, e->stream));
     for (u32 t = 0; t < n_steps; t++) {
-        FloodArgs F; F.on = 1; F.cmds = cmds_per_step; F.permille = election_permille; F._p = 0;
+        FloodArgs F; memset(&F, 0, sizeof F);
+        F.on = 1; F.cmds = cmds_per_step; F.permille = election_permille;
+        if (ff) { F.drop = ff->drop_permille; F.withhold = ff->withhold_permille; F.part = ff->partition_permille; F.part_len = ff->partition_steps; }
         F.seed = seed; F.step = e->step_no + t;
         int rc = launch_step(e, F);
         if (rc) return rc;

@@ -46,6 +46,34 @@ __device__ __forceinline__ void member_writeback(const Member& m, const Cols& C,
     lrs_writeback(m);
 }
 
+// ---- flood fault injection (include/ra_engine.h, ra_flood_faults): keyed by GLOBAL ids ---------------------
+__device__ __forceinline__ void flood_ids(const Cols& C, const Member& m, u32 r, u64& gg, u64& gr)
+{
+    gg = m.group; gr = r;
+    if (C.n_shards > 1) {
+        gg = (u64)C.n_shards * m.group + (C.shard + 8u * C.n_shards - m.slot) % C.n_shards;
+        gr = (u64)m.slot * C.groups * C.n_shards + gg;
+    }
+}
+// is the mailbox record `e` lost before row r evaluates it in step F.step?
+template <int MM>
+__device__ __forceinline__ bool flood_lost(const FloodArgs& F, const Cols& C, const Member& m, u32 r, const Rec& e)
+{
+    if (!(F.drop | F.part)) return false;
+    u64 gg, gr; flood_ids(C, m, r, gg, gr);
+    const u32 from = R_from(e);
+    if (F.part) {                                            // one member of the group is cut off in this window
+        const u64 w = F.step / F.part_len;
+        const u32 h = (u32)(mix64(F.seed ^ (w * 0xC2B2AE3D27D4EB4Full) ^ (gg * 0x165667B19E3779F9ull)) >> 32);
+        if (h % 1000u < F.part) { const u32 p = (h / 1000u) % NMEM(C); if (p == m.slot || p == from) return true; }
+    }
+    if (F.drop && R_type(e) == RA_EV_AER) {
+        const u32 h = (u32)(mix64(F.seed ^ (F.step * 0x9E3779B97F4A7C15ull) ^ (gr * 0xD6E8FEB86659FD93ull) ^ ((u64)(from + 1) << 56)) >> 32);
+        if (h % 1000u < F.drop) return true;
+    }
+    return false;
+}
+
 // end of a row's step: publish mailbox counts, STATUS note, output counts, flood host model
 template <int MM>
 __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, int cur, const FloodArgs& F)
@@ -84,6 +112,12 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
     // flood: synthetic host (DESIGN.md "flood host model")
     if (F.on && !MT_FATAL(m.meta)) {
         u32 k = 0;
+        bool held = false;                                  // a lagging fsync: this step's notifications are not produced
+        if (F.withhold && (m.wk & 3u)) {
+            u64 gg0, gr0; flood_ids(C, m, r, gg0, gr0);
+            held = (u32)(mix64(F.seed ^ (F.step * 0xA0761D6478BD642Full) ^ (gr0 * 0xE7037ED1A0B428DBull)) >> 32) % 1000u < F.withhold;
+        }
+        if (held) m.wk = 0;
         // {written, Term, {From, To}} for the (last two) WAL_APPEND notes of this step: read back
         // from the row's own note slots instead of being carried in registers through the step
         if ((m.wk & 3u) == 2) {

@@ -133,7 +133,7 @@ __device__ __forceinline__ size_t rec_word(u32 tiles, u32 plane, u32 row, u32 j)
     return (((size_t)plane * tiles + (row >> 5)) * 4 + j) * RT + (row & (RT - 1));
 }
 
-struct FloodArgs { u32 on; u32 cmds; u32 permille; u32 _p; u64 seed; u64 step; };
+struct FloodArgs { u32 on; u32 cmds; u32 permille; u32 drop; u32 withhold; u32 part; u32 part_len; u32 _p; u64 seed; u64 step; };
 
 __device__ __forceinline__ ulonglong2 ld2(const ulonglong2* p) { return *p; }
 __device__ __forceinline__ void st2(ulonglong2* p, u64 x, u64 y) { *p = make_ulonglong2(x, y); }

@@ -59,7 +59,7 @@ EXPORTS = ["ra_engine_create", "ra_engine_destroy", "ra_engine_load_rows", "ra_e
            "ra_engine_load_query_state", "ra_engine_read_query_state", "ra_engine_step_host",
            "ra_engine_submit", "ra_engine_submit_host", "ra_engine_collect", "ra_engine_pending_output",
            "ra_engine_fetch_output", "ra_engine_register_host", "ra_engine_unregister_host",
-           "ra_engine_set_flood_barrier"]
+           "ra_engine_set_flood_barrier", "ra_engine_flood_faults"]
 HOST_EXPORTS = ["ra_wal_batch_to_events"]            # host-only helpers of the same library
 HOSTSIM_EXPORTS = ["ra_hostsim_create", "ra_hostsim_create_multi", "ra_hostsim_destroy", "ra_hostsim_run",
                    "ra_hostsim_stats", "ra_hostsim_breakdown"]
@@ -87,8 +87,16 @@ class Engine(abi.Backend):
             raise err
 
     def flood(self, n_steps: int, cmds_per_step: int = 1, election_permille: int = 0, seed: int = 1,
-              sync: bool = True) -> None:
-        self._check(lib().ra_engine_flood(self._h, n_steps, cmds_per_step, election_permille, seed), "flood")
+              sync: bool = True, faults=None) -> None:
+        """faults: None or (drop_permille, withhold_permille, partition_permille, partition_steps)"""
+        if faults is None:
+            self._check(lib().ra_engine_flood(self._h, n_steps, cmds_per_step, election_permille, seed), "flood")
+        else:
+            f = lib().ra_engine_flood_faults
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(abi.RaFloodFaults)]
+            ff = abi.RaFloodFaults(*faults)
+            self._check(f(self._h, n_steps, cmds_per_step, election_permille, seed, C.byref(ff)), "flood_faults")
         if sync:
             self.sync()
 

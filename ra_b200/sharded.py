@@ -238,14 +238,14 @@ class ShardedFlood:
             s.eng.step(s.bootstrap_events())
         self.t.exchange()
 
-    def run(self, n_steps: int, cmds: int = 1, permille: int = 0, seed: int = 1) -> None:
+    def run(self, n_steps: int, cmds: int = 1, permille: int = 0, seed: int = 1, faults=None) -> None:
         if getattr(self.t, "fused", False):                  # every step ends with the device-side barrier
             for s in self.t.shards:
-                s.eng.flood(n_steps, cmds, permille, seed, sync=False)
+                s.eng.flood(n_steps, cmds, permille, seed, sync=False, faults=faults)
             return
         for _ in range(n_steps):
             for s in self.t.shards:
-                s.eng.flood(1, cmds, permille, seed, sync=False)
+                s.eng.flood(1, cmds, permille, seed, sync=False, faults=faults)
             self.t.exchange()
 
     def sync(self) -> None:

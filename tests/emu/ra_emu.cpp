@@ -182,6 +182,7 @@ static void general_row(const Cols& C, int cur, const FloodArgs& F, const StallC
         const u32 p = __ffs(rem_mbox) - 1; rem_mbox &= rem_mbox - 1;
         const Rec e = ld_rec_plane(C.mbox[cur], C.tiles, p, r);
         if (MT_FATAL(m.meta)) m.c_pack += 1u;
+        else if (flood_lost<MM>(F, C, m, r, e)) m.c_pack += 1u << 20;
         else if (!note_budget_ok(m)) budget_drop_record(m);
         else if (C.pure || !fast_event<MM>(m, e)) { process_event<MM>(m, e); m.cold &= ~8u; }
     }
@@ -236,6 +237,7 @@ static bool step_row(const Cols& C, int cur, const FloodArgs& F, u32 r, StallCtx
         if (stalled) continue;
         const Rec e = p < NPM ? ld_rec_plane(C.mbox[cur], C.tiles, p, r) : ld_rec_plane(C.loc, C.tiles, p - NPM, r);
         if (MT_FATAL(m.meta)) m.c_pack += 1u;
+        else if (p < NPM && flood_lost<MM>(F, C, m, r, e)) m.c_pack += 1u << 20;
         else if (!note_budget_ok(m) || C.pure || !fast_event<MM>(m, e)) {
             stalled = true;
             rem = mine & ~(((u64)1 << p) - 1);
@@ -385,12 +387,20 @@ extern "C" int ra_emu_step_host(ra_emu* e, const ra_host_event* ev, size_t n_ev,
     return rc;
 }
 
+extern "C" int ra_emu_flood_faults(ra_emu* e, uint32_t n_steps, uint32_t cmds_per_step, uint32_t election_permille,
+                                   uint64_t seed, const ra_flood_faults* ff);
 extern "C" int ra_emu_flood(ra_emu* e, uint32_t n_steps, uint32_t cmds_per_step, uint32_t election_permille,
                             uint64_t seed)
+{ return ra_emu_flood_faults(e, n_steps, cmds_per_step, election_permille, seed, nullptr); }
+extern "C" int ra_emu_flood_faults(ra_emu* e, uint32_t n_steps, uint32_t cmds_per_step, uint32_t election_permille,
+                                   uint64_t seed, const ra_flood_faults* ff)
 {
     if (!e || !e->C.routed) return RA_E_INVAL;
+    if (ff && ff->partition_permille && !ff->partition_steps) return RA_E_INVAL;
     for (u32 t = 0; t < n_steps; t++) {
-        FloodArgs F; F.on = 1; F.cmds = cmds_per_step; F.permille = election_permille; F._p = 0;
+        FloodArgs F; memset(&F, 0, sizeof F);
+        F.on = 1; F.cmds = cmds_per_step; F.permille = election_permille;
+        if (ff) { F.drop = ff->drop_permille; F.withhold = ff->withhold_permille; F.part = ff->partition_permille; F.part_len = ff->partition_steps; }
         F.seed = seed; F.step = e->step_no + t;
         const int rc = run_step(e, F);
         if (rc) return rc;

@@ -40,8 +40,16 @@ class Emu(abi.Backend):
     def __init__(self, n_groups: int, n_members: int, **kw):
         super().__init__(lib(), "ra_emu", n_groups, n_members, **kw)
 
-    def flood(self, n_steps: int, cmds_per_step: int = 1, election_permille: int = 0, seed: int = 1, **_kw) -> None:
-        self._check(lib().ra_emu_flood(self._h, n_steps, cmds_per_step, election_permille, seed), "flood")
+    def flood(self, n_steps: int, cmds_per_step: int = 1, election_permille: int = 0, seed: int = 1, faults=None,
+              **_kw) -> None:
+        if faults is None:
+            self._check(lib().ra_emu_flood(self._h, n_steps, cmds_per_step, election_permille, seed), "flood")
+            return
+        f = lib().ra_emu_flood_faults
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(abi.RaFloodFaults)]
+        ff = abi.RaFloodFaults(*faults)
+        self._check(f(self._h, n_steps, cmds_per_step, election_permille, seed, C.byref(ff)), "flood_faults")
 
     def stall_histogram(self) -> dict:
         arr = (C.c_uint64 * 128)()

@@ -38,9 +38,16 @@ class Oracle(abi.Backend):
         super().__init__(lib(), "ra_oracle", n_groups, n_members, **kw)
 
     def flood(self, n_steps: int, cmds_per_step: int = 1, election_permille: int = 0, seed: int = 1,
-              threads: int = 1) -> None:
-        self._check(lib().ra_oracle_flood(self._h, n_steps, cmds_per_step, election_permille, seed,
-                                          threads), "flood")
+              threads: int = 1, faults=None) -> None:
+        if faults is None:
+            self._check(lib().ra_oracle_flood(self._h, n_steps, cmds_per_step, election_permille, seed,
+                                              threads), "flood")
+            return
+        f = lib().ra_oracle_flood_faults
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(abi.RaFloodFaults)]
+        ff = abi.RaFloodFaults(*faults)
+        self._check(f(self._h, n_steps, cmds_per_step, election_permille, seed, threads, C.byref(ff)), "flood_faults")
 
 
     def set_sample(self, stride: int, offset: int, total_groups: int) -> None:

@@ -51,6 +51,37 @@ def test_sharded_flood_equals_unsharded_oracle(n, m, gl, steps, permille, cmds, 
     assert co["commits"] > 0 and co["msgs_dropped"] == 0
 
 
+def test_config4_at_stated_size():
+    """BASELINE.json configs[3] at its stated size: 100,000 groups x 5 members spread over 8 shards (12,500 local
+    groups per slot and shard), 64-entry commands -> pipelined 64-entry AppendEntries, peer-store transport.
+    Counters equal the unsharded oracle's; every 13th row of every shard is diffed field by field."""
+    from ra_b200.sharded import LocalPeerTransport, Shard, ShardedFlood
+    n, m, gl, steps, permille, cmds = 8, 5, 12_500, 24, 10, 64
+    shards = [Shard(gl, m, n, k, buckets=False) for k in range(n)]
+    fl = ShardedFlood(LocalPeerTransport(shards))
+    fl.bootstrap()
+    fl.run(steps, cmds, permille, seed=0xA04)
+    fl.sync()
+    g = n * gl
+    o = Oracle(g, m, route_on_device=True)
+    o.reset_empty()
+    o.step([abi.ev_simple(o.row_of(i, 0), abi.EV_ELECTION_TIMEOUT) for i in range(g)])
+    o.flood(steps, cmds, permille, seed=0xA04, threads=8)
+    co, ce = o.counters(), fl.counters()
+    for k in ("events", "commits", "applied", "msgs_out", "msgs_dropped", "elections_won", "fatal_rows",
+              "aer_received_follower", "aer_replies_success"):
+        assert ce[k] == co[k], k
+    assert co["commits"] >= g * 64 * (steps - 8) and co["msgs_dropped"] == 0
+    checked = 0
+    for s in shards:
+        ids = list(range(0, s.eng.n_rows, 13))
+        want = {r.row: r.key()[1:] for r in o.read_rows([s.global_row(i, g) for i in ids])}
+        for r in s.eng.read_rows(ids):
+            assert r.key()[1:] == want[s.global_row(r.row, g)], (s.shard, r.row)
+            checked += 1
+    assert checked > 30_000
+
+
 def test_placement_math():
     from ra_b200.sharded import global_group, local_group, shard_of
     for n in (1, 2, 3, 8):
