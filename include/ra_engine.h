@@ -247,7 +247,12 @@ typedef struct ra_engine_cfg {
     int32_t  device;              /* CUDA device ordinal                                  */
     uint32_t route_on_device;     /* 1: RPC records for rows of this engine are delivered
                                      through HBM mailboxes (benchmark transport), never
-                                     shown to the host.  0: every RPC record is returned. */
+                                     shown to the host.  0: every RPC record is returned.
+                                     BENCHMARK / CLOSED-LOOP TESTS ONLY: a row's replies reach their
+                                     destination in the same step that sets RA_ST_TERM_VOTE_CHANGED,
+                                     before the host could persist term / voted_for
+                                     (ra_server.erl:3024-3025); a real integration uses 0, persists,
+                                     then sends.                                                    */
     uint32_t pure;                /* 1: do not chase {next_event,_}; return it as a record
                                      (the shape ra_server_SUITE asserts on)               */
     uint32_t n_shards;            /* 0 or 1: every member of a group lives in this engine.  N > 1 (needs
@@ -307,6 +312,11 @@ int  ra_engine_load_rows(ra_engine* e, const ra_row_state* rows, size_t n);
 static inline int ra_row_state_valid(const ra_row_state* s)
 {
     if (s->n_runs > RA_MAX_RUNS || s->n_members < 1 || s->n_members > RA_MAX_MEMBERS || s->self_slot >= s->n_members) return 0;
+    if (s->role > RA_AWAIT_CONDITION || s->membership > RA_UNKNOWN || s->condition > 2) return 0;
+    /* leader_id / voted_for may name a server outside the cluster map (the reference keeps whatever id it was told):
+       any slot below 15 or RA_NO_SLOT is representable */
+    if ((s->leader_slot != RA_NO_SLOT && s->leader_slot >= 15) || (s->voted_for != RA_NO_SLOT && s->voted_for >= 15)) return 0;
+    for (uint32_t p = 0; p < RA_MAX_MEMBERS; p++) if (s->peers[p].status > RA_PEER_DISCONNECTED) return 0;
     if (s->n_runs == 0) return s->first_index > s->last_index;
     if (s->first_index > s->last_index || s->run_start[0] != s->first_index) return 0;
     for (uint32_t k = 1; k < s->n_runs; k++)

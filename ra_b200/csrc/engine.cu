@@ -396,7 +396,7 @@ __global__ void ingest_kernel(const Cols C, const ra_event* ev, u32 n, u32* err,
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || *sticky) return;
     const u32 row = ev[i].row;
-    if (row >= C.rows) { atomicMax(err, 3u); return; }
+    if (row >= C.rows || ev[i].type > RA_EV_CONSISTENT_QUERY || ev[i].type == RA_EV_NONE) { atomicMax(err, 3u); return; }
     if (i > 0 && ev[i - 1].row == row) return;                 // not the head of its run
     u32 len = 1;
     while (i + len < n && ev[i + len].row == row && len <= RA_LOCAL_CAP) len++;

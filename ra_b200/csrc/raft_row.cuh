@@ -91,7 +91,10 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
                 if (peer) cnt = C.peer_cnt[cur ^ 1][ds];                 // byte store over NVLink
                 else if (ds != C.shard) continue;   // set when the records are delivered (deliver_kernel)
             }
-            reinterpret_cast<u8*>(&cnt[(size_t)s * C.groups + m.group])[m.slot] = (u8)((m.sent_to >> (4 * s)) & 15u);
+            // (a count byte is zero when its buffer comes round again -- the owner clears the word when it consumes
+            // it -- so only senders that sent something have to publish: 1 of a follower's 4 bytes in steady state)
+            const u32 nsent = (m.sent_to >> (4 * s)) & 15u;
+            if (nsent) reinterpret_cast<u8*>(&cnt[(size_t)s * C.groups + m.group])[m.slot] = (u8)nsent;
         }
     }
     // record_leader_msg alone (the steady state of a follower) does not get a STATUS note of its own: the

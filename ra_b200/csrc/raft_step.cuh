@@ -1573,7 +1573,7 @@ __device__ __forceinline__ void process_event(Member& m, const Rec& in)
         u32 front = nq.codes, nf = nq.n;
         if (nr == RA_LEADER && old == RA_CANDIDATE) { front = (front << 4) | NX_TICK; nf++; }
         if (nf) {
-            if (np + nf > 8) nf = 8 - np;
+            if (np + nf > 8) { set_fatal(m, RA_FATAL_ASSERT); return; }   // (cannot happen: <= 3 next events per clause)
             pend = (pend << (4 * nf)) | (front & ((nf >= 8) ? 0xFFFFFFFFu : ((1u << (4 * nf)) - 1u)));
             np += nf;
         }

@@ -347,7 +347,7 @@ extern "C" int ra_emu_step(ra_emu* e, const ra_event* ev, size_t n_ev,
     u32 err = 0;
     for (size_t i = 0; i < n_ev; i++) {
         const u32 row = ev[i].row;
-        if (row >= R) { if (err < 3) err = 3; continue; }
+        if (row >= R || ev[i].type > RA_EV_CONSISTENT_QUERY || ev[i].type == RA_EV_NONE) { if (err < 3) err = 3; continue; }
         if (i > 0 && ev[i - 1].row == row) continue;
         u32 len = 1;
         while (i + len < n_ev && ev[i + len].row == row && len <= RA_LOCAL_CAP) len++;
