@@ -140,7 +140,7 @@ __device__ __forceinline__ void flush_ref_counters(const Cols& C, u32 lane, u64 
     }
 }
 
-template <int MM>
+template <int MM, bool FAULTS>
 __global__ void __launch_bounds__(CTA_T, MINB)
 raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F,
                  StallCtx* __restrict__ stall_list, u32* __restrict__ stall_count, u32* __restrict__ stall_count_next)
@@ -252,7 +252,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
             if (rec_has_tail(c0)) { t2 = sp[2 * RT + lane]; t3 = sp[3 * RT + lane]; }
             const Rec e = rec_decode(c0, c1, t2, t3, r);
             if (MT_FATAL(m.meta)) m.c_pack += 1u;
-            else if (p < NPM && flood_lost<MM>(F, C, m, r, e)) m.c_pack += 1u << 20;   // fault injection: lost in transit
+            else if (FAULTS && p < NPM && flood_lost<MM>(F, C, m, r, e)) m.c_pack += 1u << 20;   // fault injection: lost in transit
             else if (!note_budget_ok(m) || C.pure || !fast_event<MM>(m, e)) {
                 stalled = true;                                 // planes are consumed in bit order:
                 rem = mine & ~(((mask_t)1 << p) - 1);           // p and up are left for the general kernel
@@ -270,7 +270,7 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
         if (nloc) C.loc_n[r] = 0;
         if ((m.pstate & 3u) == 2u) asm volatile("cp.async.wait_all;" ::: "memory");   // prefetch never consumed
         peers_writeback<MM>(m);
-        if (!stalled) k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
+        if (!stalled) k_fatal = row_end_of_step<MM, FAULTS>(m, C, r, cur, F);
         member_writeback(m, C, r);
         k_events = m.c_pack & 0xffu; k_commits = m.c_commits; k_applied = m.c_applied;
         k_msgs = (m.c_pack >> 8) & 0xffu; k_dropped = m.c_pack >> 20; k_elect = (m.c_pack >> 16) & 15u;
@@ -657,6 +657,7 @@ extern "C" int ra_engine_reset_empty(ra_engine* e)
     e->cur = 0; e->step_no = 0; e->steps = 0; e->bar_epoch = 0;
     if (e->C.routed) CK(cudaMemsetAsync(e->C.mbox_cnt[0] + e->C.rows, 0, RA_BAR_WORDS * sizeof(u64), e->stream));
     CK(cudaMemsetAsync(e->d_err, 0, 4 * sizeof(u32), e->stream));
+    CK(cudaMemsetAsync(e->C.q_used, 0, 4 * sizeof(u32), e->stream));
     CK(cudaStreamSynchronize(e->stream));
     for (int i = 0; i < RA_IO_SLOTS; i++) e->io[i].busy = 0;
     e->io_head = e->io_tail = 0; e->out_pending = 0; e->loc_dirty = 0; e->pred_msgs = e->pred_notes = 0;
@@ -705,7 +706,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
 #define DA(p, n) if ((rc = dalloc(e, &(p), (n))) != RA_OK) goto bad
         DA(C.tc, R); DA(C.lg, R); DA(C.lw, R); DA(C.ap, R); DA(C.sn, R); DA(C.tk, R); DA(C.fm, R);
         DA(C.cd, 2 * R); DA(C.pnm, M * R); DA(C.pcs, M * R); DA(C.run, RA_MAX_RUNS * R); DA(C.lrs, R);
-        DA(C.qi, R); DA(C.qa, R); DA(C.pqi, M * R);
+        DA(C.qi, R); DA(C.qa, R); DA(C.pqi, M * R); DA(C.q_used, 4);
         C.tiles = (u32)((R + RT - 1) / RT);
         const size_t PW = (size_t)C.tiles * 4 * RT;             // 16-byte words per tiled plane
         DA(C.loc, (size_t)RA_LOCAL_CAP * PW); DA(C.loc_n, R);
@@ -727,11 +728,12 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp_bytes, PackedIt(C.out_n, PackCounts()), e->d_offs, (int)(R + 1), e->stream);
         if ((ce = cudaMalloc(&e->d_scan_tmp, e->scan_tmp_bytes ? e->scan_tmp_bytes : 16)) != cudaSuccess) { rc = fail(e, ce, "cudaMalloc scan"); goto bad; }
     }
-#define SMEM_ATTR(MEMB, TRN) \
-    if ((ce = cudaFuncSetAttribute(raft_step_kernel<MK_MM(MEMB, TRN)>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+#define SMEM_ATTR(MEMB, TRN, FLT) \
+    if ((ce = cudaFuncSetAttribute(raft_step_kernel<MK_MM(MEMB, TRN), FLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)sizeof(StepSmem<MK_MM(MEMB, TRN)>))) != cudaSuccess) { rc = fail(e, ce, "cudaFuncSetAttribute"); goto bad; }
-    SMEM_ATTR(0, TR_RUNTIME) SMEM_ATTR(5, TR_LOCAL) SMEM_ATTR(5, TR_PEER) SMEM_ATTR(5, TR_BUCKET) SMEM_ATTR(5, TR_HOST)
-    SMEM_ATTR(3, TR_LOCAL) SMEM_ATTR(7, TR_LOCAL)
+    SMEM_ATTR(0, TR_RUNTIME, true) SMEM_ATTR(0, TR_RUNTIME, false)
+    SMEM_ATTR(5, TR_LOCAL, false) SMEM_ATTR(5, TR_PEER, false) SMEM_ATTR(5, TR_BUCKET, false) SMEM_ATTR(5, TR_HOST, false)
+    SMEM_ATTR(3, TR_LOCAL, false) SMEM_ATTR(7, TR_LOCAL, false) SMEM_ATTR(5, TR_LOCAL, true) SMEM_ATTR(7, TR_LOCAL, true)
 #undef SMEM_ATTR
     {
         int sms = 148;
@@ -832,21 +834,26 @@ static int launch_step(ra_engine* e, const FloodArgs& F)
     u32* cnt = e->d_stall_cnt + (e->steps & 1), *cnt_next = e->d_stall_cnt + ((e->steps + 1) & 1);
     // one specialisation of the hot kernel per (member count, transport): see MK_MM
     const int tr = !e->C.routed ? TR_HOST : (e->C.n_shards > 1 ? (e->C.peer_mode ? TR_PEER : TR_BUCKET) : TR_LOCAL);
-#define LAUNCH(MEMB, TRN) raft_step_kernel<MK_MM(MEMB, TRN)><<<grid, CTA_T, sizeof(StepSmem<MK_MM(MEMB, TRN)>), e->stream>>>( \
+#define LAUNCH(MEMB, TRN, FLT) raft_step_kernel<MK_MM(MEMB, TRN), FLT><<<grid, CTA_T, sizeof(StepSmem<MK_MM(MEMB, TRN)>), e->stream>>>( \
         e->C, e->cur, F, e->d_stall, cnt, cnt_next)
-    if (e->C.members == 5) {
+    const bool faults = (F.drop | F.withhold | F.part) != 0;     // fault injection: its own specialisations
+    if (faults) {
+        if (e->C.members == 5 && tr == TR_LOCAL) LAUNCH(5, TR_LOCAL, true);
+        else if (e->C.members == 7 && tr == TR_LOCAL) LAUNCH(7, TR_LOCAL, true);
+        else LAUNCH(0, TR_RUNTIME, true);
+    } else if (e->C.members == 5) {
         switch (tr) {
-        case TR_LOCAL:  LAUNCH(5, TR_LOCAL); break;
-        case TR_PEER:   LAUNCH(5, TR_PEER); break;
-        case TR_BUCKET: LAUNCH(5, TR_BUCKET); break;
-        default:        LAUNCH(5, TR_HOST); break;
+        case TR_LOCAL:  LAUNCH(5, TR_LOCAL, false); break;
+        case TR_PEER:   LAUNCH(5, TR_PEER, false); break;
+        case TR_BUCKET: LAUNCH(5, TR_BUCKET, false); break;
+        default:        LAUNCH(5, TR_HOST, false); break;
         }
     } else if (e->C.members == 3 && tr == TR_LOCAL) {
-        LAUNCH(3, TR_LOCAL);
+        LAUNCH(3, TR_LOCAL, false);
     } else if (e->C.members == 7 && tr == TR_LOCAL) {
-        LAUNCH(7, TR_LOCAL);
+        LAUNCH(7, TR_LOCAL, false);
     } else {
-        LAUNCH(0, TR_RUNTIME);
+        LAUNCH(0, TR_RUNTIME, false);
     }
 #undef LAUNCH
     cudaError_t ce = cudaGetLastError();

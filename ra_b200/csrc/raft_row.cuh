@@ -75,7 +75,8 @@ __device__ __forceinline__ bool flood_lost(const FloodArgs& F, const Cols& C, co
 }
 
 // end of a row's step: publish mailbox counts, STATUS note, output counts, flood host model
-template <int MM>
+// FAULTS = false compiles the fault injection out (the specialisations of the hot kernel that run the plain flood)
+template <int MM, bool FAULTS = true>
 __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, int cur, const FloodArgs& F)
 {
     u32 fatal = 0;
@@ -116,7 +117,7 @@ __device__ __forceinline__ u32 row_end_of_step(Member& m, const Cols& C, u32 r, 
     if (F.on && !MT_FATAL(m.meta)) {
         u32 k = 0;
         bool held = false;                                  // a lagging fsync: this step's notifications are not produced
-        if (F.withhold && (m.wk & 3u)) {
+        if (FAULTS && F.withhold && (m.wk & 3u)) {
             u64 gg0, gr0; flood_ids(C, m, r, gg0, gr0);
             held = (u32)(mix64(F.seed ^ (F.step * 0xA0761D6478BD642Full) ^ (gr0 * 0xE7037ED1A0B428DBull)) >> 32) % 1000u < F.withhold;
         }
@@ -283,6 +284,7 @@ __device__ __forceinline__ void deliver_record(const Cols& C, const int buf, con
 __device__ __forceinline__ void load_query_row(const Cols& C, const ra_query_state& q)
 {
     const u32 r = q.row;
+    *C.q_used = 1u;
     C.qi[r] = q.query_index; C.qa[r] = q.agreed_index;
     for (u32 p = 0; p < C.members; p++) C.pqi[(size_t)p * C.rows + r] = q.peer_query_index[p];
 }

@@ -88,6 +88,7 @@ struct Cols {
     u64*        qi;
     u64*        qa;
     u64*        pqi;
+    u32*        q_used; // != 0 once any consistent-query state may be non-zero in this engine (see update_term_and_voted_for)
     u64*        lrs;    // [rows] start index of the LAST run (copy of run[n_runs-1].x; 0 when the log is
                         // empty): lets the step kernel load it together with the other pairs
     // transport / io.  Input record planes (mailboxes, locals) are TILED: plane p holds, for
@@ -586,7 +587,11 @@ __device__ __forceinline__ void note(Member& m, u32 type, u32 slot, u64 a, u64 b
 // RA_NOTE_RESERVE slots + the STATUS slot are free.  Otherwise it stops for this step: mailbox records it has
 // not reached are dropped and counted like a full transport (Raft tolerates loss, the tick path re-sends),
 // host events are left unconsumed and reported (RA_ST_NOTE_OVERFLOW, STATUS.c bits 8..15).
+#ifdef RA_NO_BUDGET
+__device__ __forceinline__ bool note_budget_ok(const Member&) { return true; }
+#else
 __device__ __forceinline__ bool note_budget_ok(const Member& m) { return m.n_notes + RA_NOTE_RESERVE + 1u <= m.C->note_cap; }
+#endif
 __device__ __forceinline__ void budget_drop_record(Member& m)
 { m.status |= RA_ST_NOTE_OVERFLOW | RA_ST_MSG_DROPPED; m.c_pack += 1u << 20; }
 __device__ __forceinline__ void budget_refuse_local(Member& m)
@@ -659,14 +664,20 @@ __device__ __forceinline__ void nq_push(NextQ& q, u32 code) { q.codes |= code <<
 // shifts of the reference's per-path counters inside Member::c_ref (ra.hrl:324-343)
 enum { CR_AER_RX = 0, CR_AER_RX_EMPTY = 8, CR_REPLY_OK = 16, CR_REPLY_FAIL = 24, CR_ELECTIONS = 32, CR_PRE_VOTE_ELECTIONS = 40,
        CR_TERM_VOTE = 48 };
+#ifdef RA_NO_REF_COUNTERS
+#define CR_INC(m, f) ((void)0)
+#else
 #define CR_INC(m, f) ((m).c_ref += 1ull << (f))
+#endif
 
 // update_term_and_voted_for/3 :3014-3031
 __device__ __forceinline__ void update_term_and_voted_for(Member& m, u64 term, u32 voted)
 {
     if (term == m.term && voted == MT_VOTED(m.meta)) return;
     CR_INC(m, CR_TERM_VOTE);                                            // :3026
-    reset_query_indexes(m.C->pqi, m.C->rows, m.row, m.C->members);      // :3029
+    // reset_query_index/1 :3029.  Every peer query_index of the engine is zero until a heartbeat reply or
+    // ra_engine_load_query_state writes one -- both raise q_used first -- so until then there is nothing to reset
+    if (*m.C->q_used) reset_query_indexes(m.C->pqi, m.C->rows, m.row, m.C->members);
     m.term = term;
     MT_SET(m.meta, 7, 4, voted);
     m.status |= RA_ST_TERM_VOTE_CHANGED;
@@ -1310,7 +1321,7 @@ __device__ __forceinline__ u32 handle_leader(Member& m, const Rec& e, NextQ& nq)
     if (type == RA_EV_HEARTBEAT_REPLY) {                                   // :895-918
         if (R_term(e) == m.term) {                                         // heartbeat_rpc_quorum/3 :3773-3795
             const u32 from = R_from(e);
-            if (from < NMEM(C) && R_a(e) > q_peer(m, from)) q_peer(m, from) = R_a(e);   // update_peer_query_index/3
+            if (from < NMEM(C) && R_a(e) > q_peer(m, from)) { *m.C->q_used = 1u; q_peer(m, from) = R_a(e); }   // update_peer_query_index/3
             query_agreed(m, query_quorum<MM>(m));
             return RA_LEADER;
         }

@@ -55,6 +55,7 @@ extern "C" int ra_emu_reset_empty(ra_emu* e)
     if (!e) return RA_E_INVAL;
     for (u32 r = 0; r < e->C.rows; r++) reset_row(e->C, r);
     memset(e->C.counters, 0, (8 + 8 * 16 + 8) * sizeof(u64));
+    e->C.q_used[0] = 0;
     e->cur = 0; e->step_no = 0; e->steps = 0;
     return RA_OK;
 }
@@ -89,7 +90,7 @@ extern "C" int ra_emu_create(const ra_engine_cfg* cfg, ra_emu** out)
     {
         const size_t PW = (size_t)C.tiles * 4 * RT;
         HA(C.loc, (size_t)RA_LOCAL_CAP * PW); HA(C.loc_n, R);
-        HA(C.onote, (size_t)RA_NOTE_CAP * R); HA(C.out_n, R); HA(C.counters, 8 + 8 * 16 + 8);
+        HA(C.onote, (size_t)RA_NOTE_CAP * R); HA(C.out_n, R); HA(C.counters, 8 + 8 * 16 + 8); HA(C.q_used, 4);
         if (C.routed) {
             for (int b = 0; b < 2; b++) { HA(C.mbox[b], M * RA_MBOX_DEPTH * PW); HA(C.mbox_cnt[b], R); }
             HA(C.omsg, (size_t)RA_MSG_CAP * (C.pure ? R : 1));
