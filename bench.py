@@ -276,27 +276,7 @@ def run_engine(args):
     if not args.no_e2e:
         # host-model threads: the CPUs this job may really use, shared by the ranks of the node
         os.environ.setdefault("RA_HOSTSIM_THREADS", str(max(1, min(16, effective_cpus() // max(1, world)))))
-        if spread:
-            from ra_b200.sharded import NcclTransport, NvlinkPeerTransport, Shard
-            sh2 = Shard(G, M, world, rank, device=dev, buckets=not peer)
-            eng2 = sh2.eng
-            tr2 = NvlinkPeerTransport(sh2) if peer else NcclTransport(sh2)
-            eng2.reset_empty()
-            tr2.exchange_barrier()
-            hf = HostFlood(eng2)
-            hf.run(0, args.cmds, args.permille, seed=args.seed, bootstrap=True)
-            tr2.exchange()
-
-            def host_steps(n):
-                h2d = d2h = 0
-                t_0 = time.perf_counter()
-                for _ in range(n):
-                    st_ = hf.run(1, args.cmds, args.permille, seed=args.seed)
-                    tr2.exchange()
-                    h2d += st_["h2d_bytes"]; d2h += st_["d2h_bytes"]
-                torch.cuda.synchronize(dev)
-                return dict(seconds=time.perf_counter() - t_0, h2d_bytes=h2d, d2h_bytes=d2h)
-        else:
+        if True:
             # K engines (disjoint sets of groups) driven by ONE host thread through the split-phase calls
             # ra_engine_submit_host / ra_engine_collect: while the notes of one partition travel device->host and
             # its host model runs, another partition's batch travels host->device and its kernels run.  Every
@@ -335,8 +315,10 @@ def run_engine(args):
                "steps": args.e2e_steps, "ms_per_step": sec * 1e3 / args.e2e_steps,
                "engine_call_ms_per_step": st.get("step_seconds", 0.0) * 1e3 / args.e2e_steps,
                "host_model_ms_per_step": st.get("model_seconds", 0.0) * 1e3 / args.e2e_steps,
-               "gpu_launches_per_step": (6 + 1) if spread else 6 * max(1, min(args.e2e_engines, G)),
-               "engines": 1 if spread else max(1, min(args.e2e_engines, G))}
+               "gpu_launches_per_step": 6 * max(1, min(args.e2e_engines, G)),
+               "engines": max(1, min(args.e2e_engines, G)),
+               "placement": "every rank drives %d engines holding disjoint groups of its own (all members of a group on "
+                            "one GPU, records routed on that GPU); no cross-rank traffic on this leg" % max(1, min(args.e2e_engines, G))}
         hf.close()
         eng2.close()
 
