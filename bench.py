@@ -34,9 +34,26 @@ sys.path.insert(0, ROOT)
 B_COMMIT = {3: 40 + 104 * 3 + 2 * (169 + 185) + (128 + 8 * 3) + 2 * (145 + 8 * 3),
             5: 2884, 7: 4282}
 METRIC = "committed entries/sec across N Raft groups; HBM GB/s vs roofline"
-# dram__bytes_read.sum + dram__bytes_write.sum of raft_step_kernel per launch, from the last
-# `ncu --set full` capture of this workload (profiles/, see profiles/README.md); None until measured
-TRAFFIC_BYTES = 250_279_424      # profiles/r01_v12_raft_step_ncu_full.txt (136.0 MB read + 114.3 MB written)
+# dram__bytes_read.sum + dram__bytes_write.sum of raft_step_kernel per launch: read from the committed ncu summary
+# of the shipped build (tools/ncu_summary.py output of one `ncu --set full` capture of this workload)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_raft_step_ncu_full.txt")
+
+
+def traffic_bytes():
+    """-> (bytes per launch or None, source)"""
+    try:
+        rd = wr = None
+        for ln in open(TRAFFIC_FILE):
+            f = ln.split()
+            if len(f) >= 3 and f[0] == "dram__bytes_read.sum":
+                rd = float(f[1]) * {"[Mbyte]": 1e6, "[Gbyte]": 1e9, "[Kbyte]": 1e3, "[byte]": 1.0}[f[2]]
+            if len(f) >= 3 and f[0] == "dram__bytes_write.sum":
+                wr = float(f[1]) * {"[Mbyte]": 1e6, "[Gbyte]": 1e9, "[Kbyte]": 1e3, "[byte]": 1.0}[f[2]]
+        if rd is not None and wr is not None:
+            return int(rd + wr), os.path.relpath(TRAFFIC_FILE, ROOT)
+    except (OSError, KeyError, ValueError):
+        pass
+    return None, "no ncu summary found"
 
 
 def b_commit(m: int) -> int:
@@ -340,11 +357,15 @@ def run_engine(args):
     if rank != 0:
         return
     peak, peak_src = hbm_peak()
+    traffic, traffic_src = traffic_bytes()
     bc = b_commit(M)
     achieved = (commits / (ms * 1e-3)) * bc / 1e9               # this rank, GB/s
     par = ("members of a group on different GPUs ((group+slot) mod N); " +
            ("RPC records are stored by the step kernels straight into the destination GPU's mailbox planes "
-            "over NVLink (CUDA IPC peer mappings); one 1-element NCCL all-reduce per step keeps the shards in lock step"
+            "over NVLink (CUDA IPC peer mappings); " +
+            ("a device-side flag barrier over the same mappings closes every step (no collective, no host in the loop)"
+             if os.environ.get("RA_PEER_BARRIER", "device") == "device" else
+             "one 1-element NCCL all-reduce per step keeps the shards in lock step")
             if spread and peer else
             "cross-shard RPC records by NCCL all_to_all_single (bucket counts + equal-size buckets) every step")
            if spread else
@@ -360,10 +381,11 @@ def run_engine(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": TRAFFIC_BYTES, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      # also against the nominal HBM3e figure; and what the kernel really moves
                      "peak_nominal": 8000.0, "frac_nominal": achieved / 8000.0,
-                     "achieved_traffic": (TRAFFIC_BYTES / 1e9) / (ms * 1e-3 / args.steps) if (TRAFFIC_BYTES and world == 1) else None,
+                     "achieved_traffic": (traffic / 1e9) / (ms * 1e-3 / args.steps) if (traffic and world == 1 and args.config == 3) else None,
+                     "frac_traffic": ((traffic / 1e9) / (ms * 1e-3 / args.steps) / peak) if (traffic and world == 1 and args.config == 3) else None,
                      "bytes_per_commit": bc, "algorithmic_bytes_per_launch": bc * commits / args.steps,
                      "kernel": "raft_step_kernel (+ raft_general_kernel for the rows that leave the fast paths)"},
     }

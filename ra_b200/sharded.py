@@ -185,8 +185,9 @@ class LocalPeerTransport:
 class NvlinkPeerTransport:
     """One shard per rank on one NVLink/NVSwitch domain: mailbox buffers are mapped across
     processes with CUDA IPC at start-up, the step kernels store RPC records straight into the
-    destination GPU's HBM, and the only per-step collective is the lock-step barrier (a 1-element
-    NCCL all-reduce on the compute stream)."""
+    destination GPU's HBM.  Lock step between steps: a device-side flag barrier over the same IPC mappings
+    (default; ra_engine_flood appends it to every step, so a multi-step flood runs without the host), or with
+    RA_PEER_BARRIER=nccl a 1-element NCCL all-reduce on the compute stream."""
 
     def __init__(self, shard: Shard, device_barrier: bool | None = None):
         import os
@@ -195,7 +196,7 @@ class NvlinkPeerTransport:
         self.shard = shard
         self.shards = [shard]
         # step barrier: a kernel on the engine's stream (flag words in the peers' HBM) or a 1-element all-reduce
-        self.device_barrier = (os.environ.get("RA_PEER_BARRIER", "nccl") == "device") if device_barrier is None \
+        self.device_barrier = (os.environ.get("RA_PEER_BARRIER", "device") == "device") if device_barrier is None \
             else device_barrier
         handles = [None] * dist.get_world_size()
         dist.all_gather_object(handles, shard.ipc_export())
