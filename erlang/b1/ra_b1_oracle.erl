@@ -79,8 +79,28 @@ event(<<Row:32/little, _/binary>> = Ev, States, Groups) ->
     IdOf = fun(_R, Slot) -> id(G, Slot) end,
     {Row, _From, _Seq, _Flags, Msg0} = ra_engine_codec:decode_record(Ev, IdOf),
     {Role, St} = maps:get(Row, States),
-    Msg = to_ra_msg(Msg0, Ev, St),
+    Msg = token_in(Row, to_ra_msg(Msg0, Ev, St), St),
+    put(cur_row, Row),
     States#{Row => dispatch(Role, [Msg], St)}.
+
+%% Pre-vote tokens: ra_server makes a reference per pre-vote election (call_for_election/3 :2873-2897), the engine
+%% counts them (token = the member's n-th pre-vote election).  The recorded traces carry the engine's integers,
+%% so the harness counts this member's pre-vote elections too and hands ra_server its own current token when a
+%% result names the current election, a foreign reference otherwise.
+token_in(Row, #pre_vote_result{token = I} = R, St) when is_integer(I) ->
+    case get({pv_count, Row}) of
+        I -> R#pre_vote_result{token = maps:get(pre_vote_token, St, make_ref())};
+        _ -> R#pre_vote_result{token = make_ref()}
+    end;
+token_in(_Row, Msg, _St) -> Msg.
+
+count_pre_votes(Effects) ->
+    case [x || {send_vote_requests, [{_, #pre_vote_rpc{}} | _]} <- lists:flatten(Effects)] of
+        [] -> ok;
+        L ->
+            Row = get(cur_row),
+            put({pv_count, Row}, (case get({pv_count, Row}) of undefined -> 0; N -> N end) + length(L))
+    end.
 
 %% what ra_engine_codec hands back -> the ra_msg() ra_server takes
 to_ra_msg({aer, Rpc, {From, To}, {N1, D, E}}, _Ev, _St) ->
@@ -91,15 +111,8 @@ to_ra_msg({command, N, true}, _Ev, _St) when N >= 1 -> {command, {noop, #{from =
 to_ra_msg({command, 1, false}, _Ev, _St) -> {command, usr(cmd)};
 to_ra_msg({command, N, false}, _Ev, _St) -> {commands, [usr(cmd) || _ <- lists:seq(1, N)]};
 to_ra_msg(tick, _Ev, _St) -> {tick, 0};                       %% leader tick -> make_rpcs (ra_server_proc.erl:610-613)
-to_ra_msg(Msg, Ev, _St) ->
-    %% host-origin events the record decoder does not name
-    case Ev of
-        <<_:32, 7, _:24, _:64, Term:64/little, A:64/little, B:64/little, _/binary>> ->
-            {ra_log_event, {written, Term, [{A, B}]}};
-        <<_:32, 9, _/binary>> -> election_timeout;
-        <<_:32, 10, _/binary>> -> await_condition_timeout;
-        _ -> Msg
-    end.
+to_ra_msg({ra_log_event, {written, Term, {A, B}}}, _Ev, _St) -> {ra_log_event, {written, Term, [{A, B}]}};
+to_ra_msg(Msg, _Ev, _St) -> Msg.               %% RPC records, election_timeout, await_condition_timeout, pipeline_rpcs
 
 usr(Data) -> {'$usr', #{from => undefined, ts => 0}, Data, noreply}.
 
@@ -118,6 +131,7 @@ dispatch(Role, [Msg | Q], St0) ->
         try ra_server:Fun(Msg, St0)
         catch throw:{N, S, E} when is_atom(N), is_map(S), is_list(E) -> {N, S, E}
         end,
+    count_pre_votes(Effects),
     St = case Next =/= Role of
              true -> element(1, ra_server:handle_state_enter(Next, Role, St1));   %% become/3 (:2153-2177)
              false -> St1

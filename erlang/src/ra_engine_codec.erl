@@ -164,6 +164,10 @@ decode_record(<<Row:32/little, Type, From, Flags, _Pad, N:16/little, N1:16/littl
                   #heartbeat_rpc{query_index = A, term = Term, leader_id = IdOf(Row, From)};
               ?EV_HEARTBEAT_REPLY ->
                   {IdOf(Row, From), #heartbeat_reply{query_index = A, term = Term}};
+              ?EV_WRITTEN -> {ra_log_event, {written, Term, {A, B}}};
+              ?EV_ELECTION_TIMEOUT -> election_timeout;
+              ?EV_AWAIT_COND_TIMEOUT -> await_condition_timeout;
+              ?EV_CONSISTENT_QUERY -> consistent_query;
               ?EV_PIPELINE_RPCS -> pipeline_rpcs;          %% pure mode: {next_event, info, pipeline_rpcs}
               ?EV_COMMAND -> {command, N, Flags band ?EVF_NOOP =/= 0};
               ?EV_TICK -> tick

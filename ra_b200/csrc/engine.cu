@@ -224,16 +224,17 @@ raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs 
     }
     mask_t toissue = todo;                                      // planes still to request
     u32 n_issued = 0, n_done = 0, st_issue = 0, st = 0, par = 0; // ring positions = counters mod NST, phase parity
-    const size_t plane_words = (size_t)C.tiles * (4 * RT);      // 16-byte words per plane
-    const ulonglong2* const mb_base = C.mbox[cur] + (size_t)wtile * (4 * RT);
-    const ulonglong2* const lc_base = C.loc + (size_t)wtile * (4 * RT) - (size_t)NPM * plane_words;
 #pragma unroll 1
     while (todo) {
         if (lane == 0) {
 #pragma unroll 1
             while (toissue && n_issued < n_done + NST) {
                 const u32 q = mask_ffs(toissue); toissue &= toissue - 1;
-                const ulonglong2* src = (q < NPM ? mb_base : lc_base) + (size_t)q * plane_words;
+                // (the tile address is rebuilt per issue -- a handful of integer ops in one lane -- instead of
+                // holding two 64-bit plane bases in registers through the whole event loop)
+                const size_t plane_words = (size_t)C.tiles * (4 * RT);      // 16-byte words per plane
+                const ulonglong2* src = (q < NPM ? C.mbox[cur] + (size_t)q * plane_words
+                                                 : C.loc + (size_t)(q - NPM) * plane_words) + (size_t)wtile * (4 * RT);
                 const u32 tbit = q < NPM ? q / RA_MBOX_DEPTH : 8u + q - NPM;
                 const u32 bytes = ((w_tail >> tbit) & 1u) ? TILE_BYTES : TILE_BYTES / 2;
                 fence_proxy_async();                            // the slot was read through the generic proxy

@@ -31,7 +31,12 @@ __device__ __forceinline__ void member_init(Member& m, const Cols& C, u32 r, ulo
     m.sent_to = 0; m.pn_type = RA_NOTE_NONE; m.pn_slot = 0; m.pn_a = m.pn_b = m.pn_c = 0;
     m.c_pack = 0; m.c_ref = 0; m.c_commits = m.c_applied = 0;
     m.nb = cur ^ 1;
-    m.sp = sp; m.pstate = 0; m.pipe_clean = 0;
+#ifdef RA_HOST_EMU
+    m.sp = sp;
+#else
+    m.sp = (u32)__cvta_generic_to_shared(sp);
+#endif
+    m.pstate = 0; m.pipe_clean = 0;
 }
 
 // The four hot pairs change on practically every step of an active row (commit_index,

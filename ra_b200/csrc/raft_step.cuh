@@ -284,7 +284,11 @@ struct Member {
     // next_index >= next_log_index and commit_index_sent >= commit_index; stays true while only
     // success replies (next/match can only grow) arrive and neither the log nor commit_index move
     u32 pipe_clean;             // cleared wherever last_index or commit_index move
-    ulonglong2* sp;             // &nm[0][thread] of the per-thread peer columns in shared memory
+#ifdef RA_HOST_EMU
+    ulonglong2* sp;             // &nm[0][thread] of the per-thread peer columns (host emulation: plain memory)
+#else
+    u32 sp;                     // shared-window address of &nm[0][thread]: one register, and every access is an LDS / STS
+#endif
     u32 pstate;                 // bit0 loaded, bits 8..15 {next,match} dirty, bits 16..23 commit_sent dirty
 };
 
@@ -329,10 +333,22 @@ __device__ __forceinline__ void lrs_writeback(const Member& m)
 //   nm[s][thread] 16 B {next_index, match_index},  cs[s][thread] 8 B commit_index_sent.
 // m.sp points at nm[0][thread].
 template <int MM>
+#ifdef RA_HOST_EMU
 __device__ __forceinline__ ulonglong2* peer_nm_p(const Member& m, u32 s) { return m.sp + s * CTA_T; }
+#else
+__device__ __forceinline__ ulonglong2* peer_nm_p(const Member& m, u32 s)
+{ return reinterpret_cast<ulonglong2*>(__cvta_shared_to_generic(m.sp + s * (CTA_T * 16u))); }
+#endif
 template <int MM>
 __device__ __forceinline__ u64* peer_cs_p(const Member& m, u32 s)
-{ return reinterpret_cast<u64*>(m.sp + PSTR * CTA_T) - threadIdx.x + s * CTA_T; }
+{
+#ifdef RA_HOST_EMU
+    return reinterpret_cast<u64*>(m.sp + PSTR * CTA_T) - threadIdx.x + s * CTA_T;
+#else
+    // cs[s][thread] sits directly behind nm[PSTR][CTA_T]: nm base of thread 0 + PSTR * CTA_T * 16, then 8-byte cells
+    return reinterpret_cast<u64*>(__cvta_shared_to_generic(m.sp - threadIdx.x * 16u + PSTR * (CTA_T * 16u) + (s * CTA_T + threadIdx.x) * 8u));
+#endif
+}
 
 // asynchronous global -> shared copies of the row's peer cells (LDGSTS): issued as soon as the
 // role is known, waited for at the first use, so the DRAM latency hides behind the record tiles
