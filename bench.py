@@ -287,6 +287,9 @@ def run_engine(args):
             t = torch.tensor([parity["rows_checked"], parity["rows_bad"]], dtype=torch.int64, device="cuda:%d" % local)
             dist.all_reduce(t)
             parity["rows_checked"], parity["rows_bad"] = int(t[0]), int(t[1])
+        # the oracle replays a LOSSLESS transport: records dropped for capacity (counted, Raft tolerates them) make the
+        # two runs legitimately different
+        parity["msgs_dropped_in_run"] = int(c1["msgs_dropped"])
 
     # e2e: the same flood through ra_engine_step with pinned host buffers (rank-local engine)
     e2e = None

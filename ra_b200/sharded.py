@@ -74,8 +74,10 @@ class Shard:
         self.eng = Engine(groups_local, members, device=device, route_on_device=True, n_shards=n_shards,
                           shard=shard, **kw)
         rows = groups_local * members
-        # per destination and step: ~3.1 records per row on average in a flood, spread over N shards
-        self.cap = cap or max(4096, (rows * 6) // n_shards)
+        # per destination and step: a flood emits ~3.2 records per row (2 AppendEntries per follower -- the entry, then
+        # the commit_index update -- and 2 replies each), spread over the destination shards; with N > M two slot
+        # offsets can share one destination (N = 8, M = 5: +4 and -4), which then takes 0.8 records per row
+        self.cap = cap or max(4096, (rows * 6) // n_shards, rows)
         tdev = torch.device("cuda", device)
         with torch.cuda.device(tdev):
             stream = torch.cuda.current_stream(tdev).cuda_stream
