@@ -41,12 +41,22 @@ struct Part {
     u64 seed_off;                     // partition p runs the model with seed + p (independent groups)
 };
 
-struct ra_hostsim {
-    std::vector<Part> parts;
+// a driver = one host thread that owns some of the partitions (collect, model, submit, round robin) and a team of
+// model threads; with two drivers one's waits overlap the other's model
+struct Driver {
     u32 threads;
     std::vector<std::vector<ra_host_event>> tmp;
     std::vector<size_t> cnt, off;
-    double t_model, t_step;          // seconds spent in the host model / waiting inside engine calls
+    double t_model, t_step;
+    u64 h2d, d2h, calls;
+    int rc;
+};
+
+struct ra_hostsim {
+    std::vector<Part> parts;
+    u32 threads;                     // model threads in total
+    std::vector<Driver> drivers;
+    double t_model, t_step;          // seconds spent in the host model / waiting inside engine calls (max over drivers)
     u64 h2d, d2h, calls; double seconds;
 };
 
@@ -100,8 +110,16 @@ extern "C" int ra_hostsim_create_multi(ra_engine* const* engines, uint32_t n, ra
         const char* env = getenv("RA_HOSTSIM_THREADS");
         s->threads = env ? (u32)atoi(env) : (hc > 16 ? 16u : (hc ? hc : 1u));
         if (s->threads < 1) s->threads = 1;
-        s->tmp.resize(s->threads);
-        s->cnt.assign(s->threads, 0); s->off.assign(s->threads + 1, 0);
+        const char* de = getenv("RA_HOSTSIM_DRIVERS");
+        u32 nd = de ? (u32)atoi(de) : ((n >= 2 && s->threads >= 8) ? 2u : 1u);
+        if (nd < 1) nd = 1;
+        if (nd > n) nd = n;
+        s->drivers.resize(nd);
+        for (Driver& d : s->drivers) {
+            d.threads = s->threads / nd ? s->threads / nd : 1;
+            d.tmp.resize(d.threads);
+            d.cnt.assign(d.threads, 0); d.off.assign(d.threads + 1, 0);
+        }
     }
     s->h2d = s->d2h = s->calls = 0; s->seconds = 0; s->t_model = s->t_step = 0;
     *out = s;
@@ -171,7 +189,7 @@ static size_t model_range(Part* s, const ra_note* notes, size_t n_notes, u32 r0,
 // the model over all rows of a partition on s->threads host threads (OpenMP keeps the team alive between
 // steps): each thread fills a private buffer for its row range, then the pieces are copied, in row order, into
 // the partition's pinned batch
-static void model(ra_hostsim* s, Part* p, size_t n_notes, u32 cmds, u32 permille, u64 seed, bool run_model)
+static void model(Driver* s, Part* p, size_t n_notes, u32 cmds, u32 permille, u64 seed, bool run_model)
 {
     const int T = (int)s->threads;
     if (T <= 1 || p->rows < 4096) {
@@ -198,7 +216,7 @@ static void model(ra_hostsim* s, Part* p, size_t n_notes, u32 cmds, u32 permille
 }
 
 // collect a partition's call; a note buffer that turned out too small is grown and the outputs fetched again
-static int collect_part(ra_hostsim* s, Part* p, size_t* nn)
+static int collect_part(Driver* s, Part* p, size_t* nn)
 {
     size_t nm = 0;
     int rc = ra_engine_collect(p->e, &nm, nn);
@@ -223,55 +241,79 @@ static int collect_part(ra_hostsim* s, Part* p, size_t* nn)
     return RA_OK;
 }
 
+// the partitions i with i % n_drivers == k, driven by one thread
+static void drive(ra_hostsim* s, u32 k, uint32_t n_steps, uint32_t cmds, uint32_t permille, uint64_t seed, int bootstrap)
+{
+    Driver* d = &s->drivers[k];
+    const size_t P = s->parts.size(), D = s->drivers.size();
+    d->h2d = d->d2h = d->calls = 0; d->t_model = d->t_step = 0; d->rc = RA_OK;
+    size_t nn = 0;
+    int rc;
+#define FAIL_IF(x) do { if ((rc = (x))) { d->rc = rc; return; } } while (0)
+    if (bootstrap) {
+        for (size_t i = k; i < P; i += D) {
+            Part& p = s->parts[i];
+            for (u32 g = 0; g < p.groups; g++) put(&p.ev[g], g, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0);
+            FAIL_IF(ra_engine_submit_host(p.e, p.ev, p.groups, p.msgs, p.msgs_cap, p.notes, p.notes_cap));
+            d->h2d += (u64)p.groups * sizeof(ra_host_event); d->calls++;
+        }
+        for (size_t i = k; i < P; i += D) {
+            Part& p = s->parts[i];
+            FAIL_IF(collect_part(d, &p, &nn));
+            model(d, &p, nn, cmds, permille, seed + p.seed_off, false);   // roles only; no model run for this step
+            p.n_ev = 0;
+        }
+    }
+    if (!n_steps) return;
+    // software pipeline over the partitions: every partition always has one call in flight
+    for (size_t i = k; i < P; i += D) {
+        Part& p = s->parts[i];
+        FAIL_IF(ra_engine_submit_host(p.e, p.ev, p.n_ev, p.msgs, p.msgs_cap, p.notes, p.notes_cap));
+        d->h2d += (u64)p.n_ev * sizeof(ra_host_event); d->calls++;
+    }
+    for (u32 t = 0; t < n_steps; t++) {
+        for (size_t i = k; i < P; i += D) {
+            Part& p = s->parts[i];
+            auto a0 = std::chrono::steady_clock::now();
+            FAIL_IF(collect_part(d, &p, &nn));
+            auto a1 = std::chrono::steady_clock::now();
+            model(d, &p, nn, cmds, permille, seed + p.seed_off, true);
+            p.step++;
+            auto a2 = std::chrono::steady_clock::now();
+            if (t + 1 < n_steps) {
+                FAIL_IF(ra_engine_submit_host(p.e, p.ev, p.n_ev, p.msgs, p.msgs_cap, p.notes, p.notes_cap));
+                d->h2d += (u64)p.n_ev * sizeof(ra_host_event); d->calls++;
+            }
+            auto a3 = std::chrono::steady_clock::now();
+            d->t_step += std::chrono::duration<double>(a1 - a0).count() + std::chrono::duration<double>(a3 - a2).count();
+            d->t_model += std::chrono::duration<double>(a2 - a1).count();
+        }
+    }
+#undef FAIL_IF
+}
+
 extern "C" int ra_hostsim_run(ra_hostsim* s, uint32_t n_steps, uint32_t cmds, uint32_t permille,
                               uint64_t seed, int bootstrap)
 {
     if (!s) return RA_E_INVAL;
     auto t0 = std::chrono::steady_clock::now();
-    s->h2d = s->d2h = s->calls = 0;
-    s->t_model = s->t_step = 0;
-    size_t nn = 0;
-    int rc;
-    const size_t P = s->parts.size();
-    if (bootstrap) {
-        for (Part& p : s->parts) {
-            for (u32 g = 0; g < p.groups; g++) put(&p.ev[g], g, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0);
-            if ((rc = ra_engine_submit_host(p.e, p.ev, p.groups, p.msgs, p.msgs_cap, p.notes, p.notes_cap))) return rc;
-            s->h2d += (u64)p.groups * sizeof(ra_host_event); s->calls++;
-        }
-        for (Part& p : s->parts) {
-            if ((rc = collect_part(s, &p, &nn))) return rc;
-            model(s, &p, nn, cmds, permille, seed + p.seed_off, false);   // roles only; no model run for this step
-            p.n_ev = 0;
-        }
+    const u32 D = (u32)s->drivers.size();
+    if (D == 1) drive(s, 0, n_steps, cmds, permille, seed, bootstrap);
+    else {
+        std::vector<std::thread> th;
+        for (u32 k = 0; k < D; k++) th.emplace_back(drive, s, k, n_steps, cmds, permille, seed, bootstrap);
+        for (auto& t : th) t.join();
     }
-    if (n_steps) {
-        // software pipeline over the partitions: every partition always has one call in flight
-        for (Part& p : s->parts) {
-            if ((rc = ra_engine_submit_host(p.e, p.ev, p.n_ev, p.msgs, p.msgs_cap, p.notes, p.notes_cap))) return rc;
-            s->h2d += (u64)p.n_ev * sizeof(ra_host_event); s->calls++;
-        }
-        for (u32 t = 0; t < n_steps; t++) {
-            for (size_t i = 0; i < P; i++) {
-                Part& p = s->parts[i];
-                auto a0 = std::chrono::steady_clock::now();
-                if ((rc = collect_part(s, &p, &nn))) return rc;
-                auto a1 = std::chrono::steady_clock::now();
-                model(s, &p, nn, cmds, permille, seed + p.seed_off, true);
-                p.step++;
-                auto a2 = std::chrono::steady_clock::now();
-                if (t + 1 < n_steps) {
-                    if ((rc = ra_engine_submit_host(p.e, p.ev, p.n_ev, p.msgs, p.msgs_cap, p.notes, p.notes_cap))) return rc;
-                    s->h2d += (u64)p.n_ev * sizeof(ra_host_event); s->calls++;
-                }
-                auto a3 = std::chrono::steady_clock::now();
-                s->t_step += std::chrono::duration<double>(a1 - a0).count() + std::chrono::duration<double>(a3 - a2).count();
-                s->t_model += std::chrono::duration<double>(a2 - a1).count();
-            }
-        }
+    s->h2d = s->d2h = s->calls = 0; s->t_model = s->t_step = 0;
+    int rc = RA_OK;
+    for (Driver& d : s->drivers) {
+        s->h2d += d.h2d; s->d2h += d.d2h; s->calls += d.calls;
+        if (d.t_model > s->t_model) s->t_model = d.t_model;
+        if (d.t_step > s->t_step) s->t_step = d.t_step;
+        if (d.rc && !rc) rc = d.rc;
     }
     s->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    return RA_OK;
+    return rc;
 }
 
 extern "C" int ra_hostsim_stats(ra_hostsim* s, uint64_t* h2d, uint64_t* d2h, double* seconds, uint64_t* calls)
