@@ -42,7 +42,7 @@ struct Part {
 };
 
 // a driver = one host thread that owns some of the partitions (collect, model, submit, round robin) and a team of
-// model threads; with two drivers one's waits overlap the other's model
+// model threads.  One driver is the default; RA_HOSTSIM_DRIVERS=2 lets one's waits overlap the other's model
 struct Driver {
     u32 threads;
     std::vector<std::vector<ra_host_event>> tmp;
@@ -111,7 +111,7 @@ extern "C" int ra_hostsim_create_multi(ra_engine* const* engines, uint32_t n, ra
         s->threads = env ? (u32)atoi(env) : (hc > 16 ? 16u : (hc ? hc : 1u));
         if (s->threads < 1) s->threads = 1;
         const char* de = getenv("RA_HOSTSIM_DRIVERS");
-        u32 nd = de ? (u32)atoi(de) : ((n >= 2 && s->threads >= 8) ? 2u : 1u);
+        u32 nd = de ? (u32)atoi(de) : 1u;      // measured: the flood is PCIe-bound from 4 partitions on, a second driver adds nothing
         if (nd < 1) nd = 1;
         if (nd > n) nd = n;
         s->drivers.resize(nd);
