@@ -39,6 +39,27 @@ def global_group(local_q: int, slot: int, shard: int, n_shards: int) -> int:
     return n_shards * local_q + ((shard - slot) % n_shards)
 
 
+def hashed_group(app_group: int, total_groups: int) -> int:
+    """SURVEY 8e asks for `gpu = (hash32(group) + slot) mod N`.  The engine's placement is
+    `(group + slot) mod N` on the group ids IT is given, so a hash placement is a relabelling on the host: hand the
+    engine `hashed_group(g, G)` -- a bijection of [0, G) (multiplicative hash with a multiplier coprime to G) --
+    instead of g.  Neighbouring application groups then land on unrelated shards and rows, and routing still
+    needs no table (the inverse is `unhashed_group`)."""
+    return (app_group * _multiplier(total_groups)) % total_groups
+
+
+def unhashed_group(engine_group: int, total_groups: int) -> int:
+    return (engine_group * pow(_multiplier(total_groups), -1, total_groups)) % total_groups
+
+
+def _multiplier(total: int) -> int:
+    import math
+    a = 2654435761 % total or 1                 # Knuth's multiplicative constant, made coprime to `total`
+    while math.gcd(a, total) != 1:
+        a += 1
+    return a
+
+
 def _declare(l):
     l.ra_engine_set_stream.restype = C.c_int
     l.ra_engine_set_stream.argtypes = [C.c_void_p, C.c_void_p]

@@ -121,3 +121,16 @@ def test_group_sharding_over_gloo_world_size_2(tmp_path):
     o.step([abi.ev_simple(o.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(200)])
     o.flood(50, 1, 10, seed=101)
     assert r["commits"] == r["mine"] + o.counters()["commits"]
+
+
+def test_hashed_group_is_a_bijection():
+    """hash placement = a host-side relabelling of group ids (ra_b200/sharded.py)"""
+    from ra_b200.sharded import hashed_group, shard_of, unhashed_group
+    for total in (1, 7, 64, 1000, 100_000):
+        seen = {hashed_group(g, total) for g in range(min(total, 5000))}
+        assert len(seen) == min(total, 5000)
+        for g in {0, 1 % total, total // 2, total - 1}:
+            assert unhashed_group(hashed_group(g, total), total) == g
+    # neighbours spread over the shards
+    shards = [shard_of(hashed_group(g, 100_000), 0, 8) for g in range(64)]
+    assert len(set(shards)) == 8
