@@ -337,6 +337,9 @@ def run_engine(args):
                "host_model_ms_per_step": st.get("model_seconds", 0.0) * 1e3 / args.e2e_steps,
                "gpu_launches_per_step": 6 * max(1, min(args.e2e_engines, G)),
                "engines": max(1, min(args.e2e_engines, G)),
+               "notes_format": ("16-byte units (ra_note16: one per note, extension entries for the rare note that does "
+                                "not fit; decoded by the host model)" if os.environ.get("RA_HOSTSIM_COMPACT", "1") != "0"
+                                else "32-byte ra_note records"),
                "placement": "every rank drives %d engines holding disjoint groups of its own (all members of a group on "
                             "one GPU, records routed on that GPU); no cross-rank traffic on this leg" % max(1, min(args.e2e_engines, G))}
         hf.close()

@@ -474,6 +474,36 @@ int  ra_engine_submit(ra_engine* e, const ra_event* ev, size_t n_ev,
 int  ra_engine_submit_host(ra_engine* e, const ra_host_event* ev, size_t n_ev,
                            ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap);
 int  ra_engine_collect(ra_engine* e, size_t* n_msgs, size_t* n_notes);
+/*
+ * Compact note stream.  With ra_engine_set_note_format(e, 1) the `notes` buffer of step / submit / fetch_output
+ * receives 16-byte units instead of 32-byte ra_note records (notes_cap and *n_notes then count units / notes):
+ *
+ *   units[0 .. n_notes)                 one ra_note16 per note, ordered by (row, seq) like the notes
+ *   units[n_notes .. n_notes + 2*n_ext) the extension area: n_ext entries of {a, b}, {c, 0}  (ra_engine_last_ext_count)
+ *
+ * A note {row, type, slot, aux, a, b, c} is ONE unit {row, type, n, aux, a} when slot = 0, 0 <= b - a < 256 (n = b - a)
+ * and c is derivable: 0, or -- WAL_APPEND only, flagged RA_N16_SAME_TERM -- the c of this row's previous WAL_APPEND
+ * note (the decoder keeps that per row, starting from 0 at reset / load / format switch; every WAL_APPEND note,
+ * compact or not, updates it).  Any other note has RA_N16_EXT set: `n` is its slot, `a` the index of its extension
+ * entry.  In the steady-state flood every note is compact: half the device->host bytes.  ra_notes16_expand is the
+ * decoder (host code): it rebuilds the ra_note records.
+ */
+typedef struct ra_note16 {
+    uint32_t row;
+    uint8_t  type;       /* enum ra_note_type | RA_N16_EXT | RA_N16_SAME_TERM */
+    uint8_t  n;          /* b - a, or the slot of an extended note            */
+    uint16_t aux;
+    uint64_t a;          /* a, or the extension index of an extended note     */
+} ra_note16;
+#define RA_N16_EXT        0x80u
+#define RA_N16_SAME_TERM  0x40u
+int    ra_engine_set_note_format(ra_engine* e, int compact);   /* only while no call is in flight */
+size_t ra_engine_last_ext_count(ra_engine* e);                 /* n_ext of the call collected last */
+/* units + extension area -> ra_note records; last_wal_c = the caller's per-row array (n_rows entries, zeroed at
+   reset / load / format switch).  Returns the number of notes written (n_notes), or 0 if cap < n_notes. */
+size_t ra_notes16_expand(const ra_note16* units, size_t n_notes, size_t n_ext, uint64_t* last_wal_c,
+                         ra_note* out, size_t cap);
+
 /* pin + map caller-owned host memory once (cudaHostRegister), e.g. a NIF's resource buffers */
 int  ra_engine_register_host(void* p, size_t bytes);
 int  ra_engine_unregister_host(void* p);

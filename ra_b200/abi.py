@@ -135,6 +135,14 @@ class RaRowState(C.Structure):
                       for p in list(self.peers)[: self.n_members]))
 
 
+class RaNote16(C.Structure):
+    """ra_note16: one 16-byte unit of the compact note stream (include/ra_engine.h)"""
+    _fields_ = [("row", C.c_uint32), ("type", C.c_uint8), ("n", C.c_uint8), ("aux", C.c_uint16), ("a", C.c_uint64)]
+
+
+N16_EXT, N16_SAME_TERM = 0x80, 0x40
+
+
 class RaHostEvent(C.Structure):
     """ra_host_event: 32-byte record for batches of host-origin events (ra_engine_step_host)."""
     _fields_ = [("row", C.c_uint32), ("type", C.c_uint8), ("flags", C.c_uint8), ("n", C.c_uint16),

@@ -465,7 +465,7 @@ typedef cub::TransformInputIterator<u64, PackCounts, const u32*> PackedIt;
 
 // What the host reads when a call completes (pinned, mapped: written by gather_out_kernel itself, so a
 // call needs no device->host copy whose size the host would first have to learn).
-struct OutHdr { u64 n_msgs, n_notes; u32 status, _pad; };     // status: ingest error 1..3 | 0x100 = outputs do not fit
+struct OutHdr { u64 n_msgs, n_notes; u32 status, n_ext; };    // status: ingest error 1..3 | 0x100 = outputs do not fit
 
 // One warp per tile of 32 rows.  The warp's notes (and records) occupy one contiguous range of the output;
 // a small table in shared memory maps every output position to (lane, k), then the range is written in
@@ -485,7 +485,7 @@ gather_out_kernel(const Cols C, const u64* __restrict__ offs, ulonglong2* __rest
     const u32 bad = *err;
     const bool fits = tm <= msgs_cap && tn <= notes_cap;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        hdr->n_msgs = tm; hdr->n_notes = tn; hdr->status = bad | (fits ? 0u : 0x100u);
+        hdr->n_msgs = tm; hdr->n_notes = tn; hdr->n_ext = 0; hdr->status = bad | (fits ? 0u : 0x100u);
     }
     if (bad || !fits) return;
     const u32 r = tile * 32 + lane;
@@ -510,6 +510,123 @@ gather_out_kernel(const Cols C, const u64* __restrict__ offs, ulonglong2* __rest
         __syncwarp();
     }
     {   // RPC records: 4 chunks each
+        const u32 nm = v & 0xffffu;
+        const u64 om = off & 0xffffffffull;
+        const u64 base = __shfl_sync(0xffffffffu, om, 0);
+        const u32 cnt = (u32)(__shfl_sync(0xffffffffu, om + nm, 31) - base);
+        if (cnt == 0) return;
+        for (u32 k = 0; k < nm; k++) t[(u32)(om - base) + k] = (unsigned short)((lane << 4) | k);
+        __syncwarp();
+        for (u32 c = lane; c < 4 * cnt; c += 32) {
+            const u32 ent = t[c >> 2];
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(&C.omsg[(size_t)(ent & 15u) * C.rows + tile * 32 + (ent >> 4)]);
+            msgs[(base << 2) + c] = src[c & 3u];
+        }
+    }
+}
+
+// ---- compact note stream (ra_engine_set_note_format, include/ra_engine.h): one 16-byte unit per note ------------
+// A note {row, type, slot, aux, a, b, c} becomes {row, type', n, aux, a} when slot = 0, 0 <= b - a < 256 and c is
+// derivable: 0, or -- for WAL_APPEND -- the c of the row's previous WAL_APPEND note (bit 6 of type'), which the
+// decoder remembers per row exactly as the engine does in Cols::wc.  Everything else gets bit 7, carries an index
+// instead of a, and its {a, b, c} goes to the extension area behind the units.  In the steady-state flood every
+// note is compact: half the device->host bytes.
+__device__ __forceinline__ u32 note16_classify(const Cols& C, u32 r, u32 nn, u64& wc, u32& cmask)
+{
+    u32 extmask = 0;
+    cmask = 0;
+    for (u32 k = 0; k < nn; k++) {
+        const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&C.onote[(size_t)k * C.rows + r]);
+        const ulonglong2 h = q[0], t = q[1];
+        const u32 type = (u32)(h.x >> 32) & 0xffu, slot = (u32)(h.x >> 40) & 0xffu;
+        const bool small = slot == 0 && t.x >= h.y && t.x - h.y < 256;
+        bool cf = false;
+        if (type == RA_NOTE_WAL_APPEND) { cf = t.y == wc; wc = t.y; }
+        const bool compact = small && (type == RA_NOTE_WAL_APPEND ? cf : t.y == 0);
+        if (!compact) extmask |= 1u << k;
+        else if (cf) cmask |= 1u << k;
+    }
+    return extmask;
+}
+
+__global__ void note_ext_count_kernel(const Cols C, u32* __restrict__ next)
+{
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > C.rows) return;
+    if (r == C.rows) { next[r] = 0; return; }
+    const u32 nn = C.out_n[r] >> 16;
+    u32 cm; u64 wc = nn ? C.wc[r] : 0;
+    next[r] = nn ? (u32)__popc(note16_classify(C, r, nn, wc, cm)) : 0u;
+}
+
+__global__ void __launch_bounds__(128)
+gather_out16_kernel(const Cols C, const u64* __restrict__ offs, const u32* __restrict__ xoffs,
+                    ulonglong2* __restrict__ msgs, const u64 msgs_cap, ulonglong2* __restrict__ units, const u64 units_cap,
+                    OutHdr* hdr, const u32* err)
+{
+    __shared__ unsigned short tab[4][32 * (RA_NOTE_CAP > RA_MSG_CAP ? RA_NOTE_CAP : RA_MSG_CAP)];
+    __shared__ u32 s_mask[4][32], s_xb[4][32];
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u32 tile = blockIdx.x * 4 + warp;
+    const u64 total = offs[C.rows];
+    const u64 tm = total & 0xffffffffull, tn = total >> 32;
+    const u64 tx = xoffs[C.rows];
+    const u32 bad = *err;
+    const bool fits = tm <= msgs_cap && tn + 2 * tx <= units_cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        hdr->n_msgs = tm; hdr->n_notes = tn; hdr->n_ext = (u32)tx; hdr->status = bad | (fits ? 0u : 0x100u);
+    }
+    if (bad || !fits) return;
+    const u32 r = tile * 32 + lane;
+    const bool valid = r < C.rows;
+    const u32 v = valid ? C.out_n[r] : 0u;
+    if (!__any_sync(0xffffffffu, v != 0)) return;
+    const u64 off = offs[valid ? r : C.rows];
+    if (v) C.out_n[r] = 0;
+    unsigned short* t = tab[warp];
+    {
+        const u32 nn = v >> 16;
+        const u64 on = off >> 32;
+        const u64 base = __shfl_sync(0xffffffffu, on, 0);
+        const u32 cnt = (u32)(__shfl_sync(0xffffffffu, on + nn, 31) - base);
+        // the owner walks its row's notes in order (the WAL_APPEND rule depends on the one before)
+        u32 extmask = 0, cmask = 0;
+        const u32 xb = valid ? xoffs[r] : 0u;
+        if (nn) {
+            u64 wc = C.wc[r];
+            extmask = note16_classify(C, r, nn, wc, cmask);
+            C.wc[r] = wc;
+            for (u32 k = 0; k < nn; k++) {
+                t[(u32)(on - base) + k] = (unsigned short)((lane << 4) | k);
+                if ((extmask >> k) & 1u) {                           // {a, b}, {c, 0} into the extension area
+                    const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&C.onote[(size_t)k * C.rows + r]);
+                    const u64 idx = xb + (u32)__popc(extmask & ((1u << k) - 1u));
+                    units[tn + 2 * idx] = make_ulonglong2(q[0].y, q[1].x);
+                    units[tn + 2 * idx + 1] = make_ulonglong2(q[1].y, 0);
+                }
+            }
+        }
+        s_mask[warp][lane] = extmask | (cmask << 16);
+        s_xb[warp][lane] = xb;
+        __syncwarp();
+        for (u32 j = lane; j < cnt; j += 32) {                       // one 16-byte unit per note, lane-consecutive
+            const u32 ent = t[j], src_lane = ent >> 4, k = ent & 15u;
+            const ulonglong2* q = reinterpret_cast<const ulonglong2*>(&C.onote[(size_t)k * C.rows + tile * 32 + src_lane]);
+            const ulonglong2 h = q[0];
+            const u32 m = s_mask[warp][src_lane];
+            u64 w0 = h.x, w1 = h.y;
+            if ((m >> k) & 1u) {
+                w0 |= 0x80ull << 32;                                  // type' bit 7: extension; slot stays in place
+                w1 = s_xb[warp][src_lane] + (u32)__popc(m & 0xffffu & ((1u << k) - 1u));
+            } else {
+                const u64 n = q[1].x - h.y;                           // b - a < 256 goes where the (zero) slot was
+                w0 |= (n << 40) | (((m >> (16 + k)) & 1u) ? (0x40ull << 32) : 0ull);
+            }
+            units[base + j] = make_ulonglong2(w0, w1);
+        }
+        __syncwarp();
+    }
+    {   // RPC records: 4 chunks each (unchanged)
         const u32 nm = v & 0xffffu;
         const u64 om = off & 0xffffffffull;
         const u64 base = __shfl_sync(0xffffffffu, om, 0);
@@ -562,7 +679,7 @@ struct IoSlot {
     // call still has a single wait; collect tops up with a second copy in the rare step that produced more
     ra_event* user_msgs; ra_note* user_notes; size_t msgs_cap, notes_cap;
     ra_event* d_msgs; size_t d_msgs_cap; ra_note* d_notes; size_t d_notes_cap;
-    size_t copied_msgs, copied_notes;
+    size_t copied_msgs, copied_notes;         // (copied_notes counts 16-byte units in compact mode)
 };
 
 struct ra_engine {
@@ -578,7 +695,10 @@ struct ra_engine {
     void* allocs[64]; int n_allocs;
     IoSlot io[RA_IO_SLOTS]; u32 io_head, io_tail;   // FIFO: submit fills io[io_head % SLOTS], collect drains io_tail
     int out_pending;                          // the last collect ended in RA_E_CAPACITY: outputs wait in the row slots
-    size_t pred_msgs, pred_notes;             // outputs of the last collected call (sizes the next DMA is enqueued with)
+    size_t pred_msgs, pred_notes, pred_ext;   // outputs of the last collected call (sizes the next DMA is enqueued with)
+    int compact;                              // notes leave as 16-byte units (ra_engine_set_note_format)
+    u32 *d_next, *d_xoffs; void* d_scan_tmp2; size_t scan_tmp2_bytes;   // compact stream: per-row extension counts + scan
+    size_t last_ext;                          // extension entries of the last collected call
     int loc_dirty;                            // the flood host model may have left host events queued
     u64* d_offs; void* d_scan_tmp; size_t scan_tmp_bytes;
     u32* d_err;                               // [0] sticky ingest error (= Cols::abort), [1] peer barrier timeout
@@ -633,7 +753,7 @@ extern "C" void ra_engine_destroy(ra_engine* e)
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     for (int i = 0; i < e->n_allocs; i++) cudaFree(e->allocs[i]);
-    cudaFree(e->d_rows); cudaFree(e->d_scan_tmp);
+    cudaFree(e->d_rows); cudaFree(e->d_scan_tmp); cudaFree(e->d_scan_tmp2);
     for (int i = 0; i < RA_IO_SLOTS; i++) {
         IoSlot& q = e->io[i];
         cudaFree(q.d_ev); cudaFree(q.d_msgs); cudaFree(q.d_notes);
@@ -661,7 +781,9 @@ extern "C" int ra_engine_reset_empty(ra_engine* e)
     CK(cudaMemsetAsync(e->C.q_used, 0, 4 * sizeof(u32), e->stream));
     CK(cudaStreamSynchronize(e->stream));
     for (int i = 0; i < RA_IO_SLOTS; i++) e->io[i].busy = 0;
-    e->io_head = e->io_tail = 0; e->out_pending = 0; e->loc_dirty = 0; e->pred_msgs = e->pred_notes = 0;
+    e->io_head = e->io_tail = 0; e->out_pending = 0; e->loc_dirty = 0; e->pred_msgs = e->pred_notes = e->pred_ext = 0; e->last_ext = 0;
+    CK(cudaMemsetAsync(e->C.wc, 0, (size_t)e->C.rows * sizeof(u64), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     return RA_OK;
 }
 
@@ -707,7 +829,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
 #define DA(p, n) if ((rc = dalloc(e, &(p), (n))) != RA_OK) goto bad
         DA(C.tc, R); DA(C.lg, R); DA(C.lw, R); DA(C.ap, R); DA(C.sn, R); DA(C.tk, R); DA(C.fm, R);
         DA(C.cd, 2 * R); DA(C.pnm, M * R); DA(C.pcs, M * R); DA(C.run, RA_MAX_RUNS * R); DA(C.lrs, R);
-        DA(C.qi, R); DA(C.qa, R); DA(C.pqi, M * R); DA(C.q_used, 4);
+        DA(C.qi, R); DA(C.qa, R); DA(C.pqi, M * R); DA(C.q_used, 4); DA(C.wc, R);
         C.tiles = (u32)((R + RT - 1) / RT);
         const size_t PW = (size_t)C.tiles * 4 * RT;             // 16-byte words per tiled plane
         DA(C.loc, (size_t)RA_LOCAL_CAP * PW); DA(C.loc_n, R);
@@ -721,13 +843,16 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
             C.mbox[0] = C.mbox[1] = nullptr; C.mbox_cnt[0] = C.mbox_cnt[1] = nullptr;
             DA(C.omsg, (size_t)RA_MSG_CAP * R);
         }
-        DA(e->d_offs, R + 1); DA(e->d_err, 4);
+        DA(e->d_offs, R + 1); DA(e->d_err, 4); DA(e->d_next, R + 1); DA(e->d_xoffs, R + 1);
         DA(e->d_stall, R); DA(e->d_stall_cnt, 4);
 #undef DA
         C.abort = e->d_err;
         e->scan_tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp_bytes, PackedIt(C.out_n, PackCounts()), e->d_offs, (int)(R + 1), e->stream);
         if ((ce = cudaMalloc(&e->d_scan_tmp, e->scan_tmp_bytes ? e->scan_tmp_bytes : 16)) != cudaSuccess) { rc = fail(e, ce, "cudaMalloc scan"); goto bad; }
+        e->scan_tmp2_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp2_bytes, e->d_next, e->d_xoffs, (int)(R + 1), e->stream);
+        if ((ce = cudaMalloc(&e->d_scan_tmp2, e->scan_tmp2_bytes ? e->scan_tmp2_bytes : 16)) != cudaSuccess) { rc = fail(e, ce, "cudaMalloc scan"); goto bad; }
     }
 #define SMEM_ATTR(MEMB, TRN, FLT) \
     if ((ce = cudaFuncSetAttribute(raft_step_kernel<MK_MM(MEMB, TRN), FLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -891,18 +1016,27 @@ static int enqueue_gather(ra_engine* e, IoSlot& q)
     const u32 R = e->C.rows;
     CK(cub::DeviceScan::ExclusiveSum(e->d_scan_tmp, e->scan_tmp_bytes, PackedIt(e->C.out_n, PackCounts()), e->d_offs,
                                      (int)(R + 1), e->stream));
+    if (e->compact) {
+        note_ext_count_kernel<<<nblocks((u64)R + 1, 256), 256, 0, e->stream>>>(e->C, e->d_next);
+        CK(cub::DeviceScan::ExclusiveSum(e->d_scan_tmp2, e->scan_tmp2_bytes, e->d_next, e->d_xoffs, (int)(R + 1), e->stream));
+        gather_out16_kernel<<<nblocks(e->C.tiles, 4), 128, 0, e->stream>>>(
+            e->C, e->d_offs, e->d_xoffs, (ulonglong2*)q.d_msgs, (u64)q.msgs_cap, (ulonglong2*)q.d_notes, (u64)q.notes_cap,
+            (OutHdr*)dh, e->d_err);
+    } else
     gather_out_kernel<<<nblocks(e->C.tiles, 4), 128, 0, e->stream>>>(
         e->C, e->d_offs, (ulonglong2*)q.d_msgs, (u64)q.msgs_cap, (ulonglong2*)q.d_notes, (u64)q.notes_cap, (OutHdr*)dh, e->d_err);
     CK(cudaGetLastError());
     // the outputs follow by DMA, sized by what the previous call produced (+ 1/16): steady streams of batches
     // produce steady amounts of output.  (A pinned destination -- ra_engine_alloc_host / ra_engine_register_host --
     // makes it a true asynchronous copy; a pageable one is staged by the driver.)
+    const size_t unit = e->compact ? 16 : sizeof(ra_note);
+    const size_t pn = e->compact ? e->pred_notes + 2 * e->pred_ext : e->pred_notes;   // compact: units, extensions behind
     q.copied_msgs = e->pred_msgs + e->pred_msgs / 16 + (e->pred_msgs ? 16 : 0);
-    q.copied_notes = e->pred_notes + e->pred_notes / 16 + (e->pred_notes ? 64 : 0);
+    q.copied_notes = pn + pn / 16 + (pn ? 64 : 0);
     if (q.copied_msgs > q.msgs_cap) q.copied_msgs = q.msgs_cap;
     if (q.copied_notes > q.notes_cap) q.copied_notes = q.notes_cap;
     if (q.copied_msgs) CK(cudaMemcpyAsync(q.user_msgs, q.d_msgs, q.copied_msgs * sizeof(ra_event), cudaMemcpyDeviceToHost, e->stream));
-    if (q.copied_notes) CK(cudaMemcpyAsync(q.user_notes, q.d_notes, q.copied_notes * sizeof(ra_note), cudaMemcpyDeviceToHost, e->stream));
+    if (q.copied_notes) CK(cudaMemcpyAsync(q.user_notes, q.d_notes, q.copied_notes * unit, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaEventRecord(q.done, e->stream));
     return RA_OK;
 }
@@ -977,13 +1111,17 @@ static int finish_slot(ra_engine* e, IoSlot& q, size_t* n_msgs, size_t* n_notes,
                            cudaMemcpyDeviceToHost, e->copy_stream));
         more = true;
     }
-    if (h.n_notes > q.copied_notes) {
-        CK(cudaMemcpyAsync(q.user_notes + q.copied_notes, q.d_notes + q.copied_notes, (size_t)(h.n_notes - q.copied_notes) * sizeof(ra_note),
-                           cudaMemcpyDeviceToHost, e->copy_stream));
-        more = true;
+    {
+        const size_t unit = e->compact ? 16 : sizeof(ra_note);
+        const size_t have = e->compact ? (size_t)h.n_notes + 2 * (size_t)h.n_ext : (size_t)h.n_notes;
+        if (have > q.copied_notes) {
+            CK(cudaMemcpyAsync((char*)q.user_notes + q.copied_notes * unit, (const char*)q.d_notes + q.copied_notes * unit,
+                               (have - q.copied_notes) * unit, cudaMemcpyDeviceToHost, e->copy_stream));
+            more = true;
+        }
     }
     if (more) CK(cudaStreamSynchronize(e->copy_stream));
-    e->pred_msgs = (size_t)h.n_msgs; e->pred_notes = (size_t)h.n_notes;
+    e->pred_msgs = (size_t)h.n_msgs; e->pred_notes = (size_t)h.n_notes; e->pred_ext = (size_t)h.n_ext; e->last_ext = (size_t)h.n_ext;
     return RA_OK;
 }
 
@@ -1050,6 +1188,20 @@ extern "C" int ra_engine_step_host(ra_engine* e, const ra_host_event* ev, size_t
                                    ra_event* msgs, size_t msgs_cap, size_t* n_msgs,
                                    ra_note* notes, size_t notes_cap, size_t* n_notes)
 { return step_impl(e, ev, n_ev, true, msgs, msgs_cap, n_msgs, notes, notes_cap, n_notes); }
+
+// notes as 16-byte units (include/ra_engine.h: ra_note16); switch only while no call is in flight
+extern "C" int ra_engine_set_note_format(ra_engine* e, int compact)
+{
+    if (!e) return RA_E_INVAL;
+    if (e->io_head != e->io_tail || e->out_pending) return RA_E_BUSY;
+    CK(cudaSetDevice(e->cfg.device));
+    e->compact = compact ? 1 : 0;
+    e->pred_notes = e->pred_ext = 0;
+    CK(cudaMemsetAsync(e->C.wc, 0, (size_t)e->C.rows * sizeof(u64), e->stream));   // the decoder starts from zero too
+    CK(cudaStreamSynchronize(e->stream));
+    return RA_OK;
+}
+extern "C" size_t ra_engine_last_ext_count(ra_engine* e) { return e ? e->last_ext : 0; }
 
 // caller-owned host buffers (a NIF's resource binaries ...) pinned and mapped once, so that batches built in
 // them are copied by DMA and outputs are written into them directly

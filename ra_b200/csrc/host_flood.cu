@@ -39,6 +39,8 @@ struct Part {
     size_t n_ev;
     u64 step;
     u64 seed_off;                     // partition p runs the model with seed + p (independent groups)
+    std::vector<uint64_t> last_c;     // compact note stream: the decoder's per-row state
+    size_t n_ext;                     // extension entries of the call collected last
 };
 
 // a driver = one host thread that owns some of the partitions (collect, model, submit, round robin) and a team of
@@ -55,6 +57,7 @@ struct Driver {
 struct ra_hostsim {
     std::vector<Part> parts;
     u32 threads;                     // model threads in total
+    int compact;                     // notes travel as 16-byte units (RA_HOSTSIM_COMPACT, default on)
     std::vector<Driver> drivers;
     double t_model, t_step;          // seconds spent in the host model / waiting inside engine calls (max over drivers)
     u64 h2d, d2h, calls; double seconds;
@@ -102,7 +105,7 @@ extern "C" int ra_hostsim_create_multi(ra_engine* const* engines, uint32_t n, ra
         p.msgs = (ra_event*)ra_engine_alloc_host(p.msgs_cap * sizeof(ra_event));
         p.notes = (ra_note*)ra_engine_alloc_host(p.notes_cap * sizeof(ra_note));
         if (!p.ev || !p.msgs || !p.notes) { ra_hostsim_destroy(s); return RA_E_NOMEM; }
-        p.n_ev = 0; p.step = 0; p.seed_off = i;
+        p.n_ev = 0; p.step = 0; p.seed_off = i; p.n_ext = 0;
         if (p.rows > max_rows) max_rows = p.rows;
     }
     {
@@ -120,6 +123,20 @@ extern "C" int ra_hostsim_create_multi(ra_engine* const* engines, uint32_t n, ra
             d.tmp.resize(d.threads);
             d.cnt.assign(d.threads, 0); d.off.assign(d.threads + 1, 0);
         }
+    }
+    {   // notes as 16-byte units (half the device->host bytes of a step) unless RA_HOSTSIM_COMPACT=0
+        const char* ce = getenv("RA_HOSTSIM_COMPACT");
+        s->compact = !(ce && ce[0] == '0');
+#ifdef RA_NO_CUDA
+        s->compact = 0;                              // (the host emulation of tests/emu/ has the plain format only)
+#else
+        if (s->compact)
+            for (Part& p : s->parts) {
+                if (ra_engine_set_note_format(p.e, 1) != RA_OK) { s->compact = 0; break; }
+                p.last_c.assign(p.rows, 0);
+            }
+        if (!s->compact) for (Part& p : s->parts) { ra_engine_set_note_format(p.e, 0); p.last_c.clear(); }
+#endif
     }
     s->h2d = s->d2h = s->calls = 0; s->seconds = 0; s->t_model = s->t_step = 0;
     *out = s;
@@ -140,21 +157,32 @@ static inline void put(ra_event* e, u32 row, u32 type, u32 n, u64 term, u64 a, u
 }
 
 // notes of one step -> events of the next (the flood host model), rows [r0, r1) of one partition
+// note16_decode is defined below (compact note stream)
+static inline void note16_decode(const ra_note16* units, size_t n_notes, size_t i, uint64_t* last_wal_c, ra_note* o);
+
+template <bool COMPACT>
 static size_t model_range(Part* s, const ra_note* notes, size_t n_notes, u32 r0, u32 r1, ra_host_event* out,
                           u32 cmds, u32 permille, u64 seed, bool run_model)
 {
+    const ra_note16* units = reinterpret_cast<const ra_note16*>(notes);      // COMPACT: 16-byte units, extensions behind
+    auto row_at = [&](size_t k) -> u32 { return COMPACT ? units[k].row : notes[k].row; };
     // first note of row r0 (notes are ordered by row)
     size_t lo = 0, hi = n_notes;
-    while (lo < hi) { size_t mid = (lo + hi) / 2; if (notes[mid].row < r0) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (row_at(mid) < r0) lo = mid + 1; else hi = mid; }
     size_t ne = 0, i = lo;
     for (u32 row = r0; row < r1; row++) {
+        ra_note wa, wb, cur;                                 // the row's last two WAL_APPEND notes, the note at hand
         const ra_note* w0 = nullptr; const ra_note* w1 = nullptr;
         u32 status = 0; bool fatal = false;
         const ra_note* last = nullptr;
-        for (; i < n_notes && notes[i].row == row; i++) {
-            const ra_note& n = notes[i];
+        for (; i < n_notes && row_at(i) == row; i++) {
+            if (COMPACT) note16_decode(units, n_notes, i, s->last_c.data(), &cur);
+            const ra_note& n = COMPACT ? cur : notes[i];
             last = &n;
-            if (n.type == RA_NOTE_WAL_APPEND) { w0 = w1; w1 = &n; }
+            if (n.type == RA_NOTE_WAL_APPEND) {
+                if (w1) { wa = *w1; w0 = &wa; }
+                wb = n; w1 = &wb;
+            }
             else if (n.type == RA_NOTE_STATUS) {
                 status = n.aux;
                 s->role[row] = (unsigned char)((n.b >> 24) & 0xff);
@@ -192,8 +220,10 @@ static size_t model_range(Part* s, const ra_note* notes, size_t n_notes, u32 r0,
 static void model(Driver* s, Part* p, size_t n_notes, u32 cmds, u32 permille, u64 seed, bool run_model)
 {
     const int T = (int)s->threads;
+    const bool compact = !p->last_c.empty();
     if (T <= 1 || p->rows < 4096) {
-        p->n_ev = model_range(p, p->notes, n_notes, 0, p->rows, p->ev, cmds, permille, seed, run_model);
+        p->n_ev = compact ? model_range<true>(p, p->notes, n_notes, 0, p->rows, p->ev, cmds, permille, seed, run_model)
+                          : model_range<false>(p, p->notes, n_notes, 0, p->rows, p->ev, cmds, permille, seed, run_model);
         return;
     }
     std::vector<size_t>& cnt = s->cnt;
@@ -203,7 +233,8 @@ static void model(Driver* s, Part* p, size_t n_notes, u32 cmds, u32 permille, u6
         const int t = omp_get_thread_num();
         const u32 r0 = (u32)((u64)p->rows * t / T), r1 = (u32)((u64)p->rows * (t + 1) / T);
         if (s->tmp[t].size() < (size_t)(r1 - r0) * RA_LOCAL_CAP) s->tmp[t].resize((size_t)(r1 - r0) * RA_LOCAL_CAP);
-        cnt[t] = model_range(p, p->notes, n_notes, r0, r1, s->tmp[t].data(), cmds, permille, seed, run_model);
+        cnt[t] = compact ? model_range<true>(p, p->notes, n_notes, r0, r1, s->tmp[t].data(), cmds, permille, seed, run_model)
+                         : model_range<false>(p, p->notes, n_notes, r0, r1, s->tmp[t].data(), cmds, permille, seed, run_model);
 #pragma omp barrier
 #pragma omp single
         {
@@ -215,16 +246,19 @@ static void model(Driver* s, Part* p, size_t n_notes, u32 cmds, u32 permille, u6
     p->n_ev = off[T];
 }
 
+// capacity of a partition's note buffer in the units of its note format (a 32-byte slot holds two 16-byte units)
+static inline size_t note_cap_of(const Part& p) { return p.last_c.empty() ? p.notes_cap : 2 * p.notes_cap; }
+
 // collect a partition's call; a note buffer that turned out too small is grown and the outputs fetched again
 static int collect_part(Driver* s, Part* p, size_t* nn)
 {
     size_t nm = 0;
     int rc = ra_engine_collect(p->e, &nm, nn);
 #ifndef RA_NO_CUDA
-    if (rc == RA_E_CAPACITY && (*nn > p->notes_cap || nm > p->msgs_cap)) {
-        if (*nn > p->notes_cap) {
+    if (rc == RA_E_CAPACITY) {
+        if (*nn + *nn / 8 > p->notes_cap || !p->last_c.empty()) {   // (compact: the extension count is not known here)
             ra_engine_free_host(p->notes);
-            p->notes_cap = *nn + *nn / 4;
+            p->notes_cap = *nn * 2 + 1024;
             p->notes = (ra_note*)ra_engine_alloc_host(p->notes_cap * sizeof(ra_note));
         }
         if (nm > p->msgs_cap) {
@@ -233,10 +267,17 @@ static int collect_part(Driver* s, Part* p, size_t* nn)
             p->msgs = (ra_event*)ra_engine_alloc_host(p->msgs_cap * sizeof(ra_event));
         }
         if (!p->notes || !p->msgs) return RA_E_NOMEM;
-        rc = ra_engine_fetch_output(p->e, p->msgs, p->msgs_cap, &nm, p->notes, p->notes_cap, nn);
+        rc = ra_engine_fetch_output(p->e, p->msgs, p->msgs_cap, &nm, p->notes, note_cap_of(*p), nn);
     }
 #endif
     if (rc) return rc;
+#ifndef RA_NO_CUDA
+    if (!p->last_c.empty()) {
+        p->n_ext = ra_engine_last_ext_count(p->e);
+        s->d2h += (*nn + 2 * p->n_ext) * sizeof(ra_note16) + nm * sizeof(ra_event);
+        return RA_OK;
+    }
+#endif
     s->d2h += *nn * sizeof(ra_note) + nm * sizeof(ra_event);
     return RA_OK;
 }
@@ -254,7 +295,7 @@ static void drive(ra_hostsim* s, u32 k, uint32_t n_steps, uint32_t cmds, uint32_
         for (size_t i = k; i < P; i += D) {
             Part& p = s->parts[i];
             for (u32 g = 0; g < p.groups; g++) put(&p.ev[g], g, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0);
-            FAIL_IF(ra_engine_submit_host(p.e, p.ev, p.groups, p.msgs, p.msgs_cap, p.notes, p.notes_cap));
+            FAIL_IF(ra_engine_submit_host(p.e, p.ev, p.groups, p.msgs, p.msgs_cap, p.notes, note_cap_of(p)));
             d->h2d += (u64)p.groups * sizeof(ra_host_event); d->calls++;
         }
         for (size_t i = k; i < P; i += D) {
@@ -268,7 +309,7 @@ static void drive(ra_hostsim* s, u32 k, uint32_t n_steps, uint32_t cmds, uint32_
     // software pipeline over the partitions: every partition always has one call in flight
     for (size_t i = k; i < P; i += D) {
         Part& p = s->parts[i];
-        FAIL_IF(ra_engine_submit_host(p.e, p.ev, p.n_ev, p.msgs, p.msgs_cap, p.notes, p.notes_cap));
+        FAIL_IF(ra_engine_submit_host(p.e, p.ev, p.n_ev, p.msgs, p.msgs_cap, p.notes, note_cap_of(p)));
         d->h2d += (u64)p.n_ev * sizeof(ra_host_event); d->calls++;
     }
     for (u32 t = 0; t < n_steps; t++) {
@@ -281,7 +322,7 @@ static void drive(ra_hostsim* s, u32 k, uint32_t n_steps, uint32_t cmds, uint32_
             p.step++;
             auto a2 = std::chrono::steady_clock::now();
             if (t + 1 < n_steps) {
-                FAIL_IF(ra_engine_submit_host(p.e, p.ev, p.n_ev, p.msgs, p.msgs_cap, p.notes, p.notes_cap));
+                FAIL_IF(ra_engine_submit_host(p.e, p.ev, p.n_ev, p.msgs, p.msgs_cap, p.notes, note_cap_of(p)));
                 d->h2d += (u64)p.n_ev * sizeof(ra_host_event); d->calls++;
             }
             auto a3 = std::chrono::steady_clock::now();
@@ -331,6 +372,30 @@ extern "C" int ra_hostsim_breakdown(ra_hostsim* s, double* step_seconds, double*
     return RA_OK;
 }
 
+
+// ---- compact note stream: the decoder (include/ra_engine.h, ra_note16) ------------------------------------
+static inline void note16_decode(const ra_note16* units, size_t n_notes, size_t i, uint64_t* last_wal_c, ra_note* o)
+{
+    const ra_note16& u = units[i];
+    o->row = u.row; o->type = (uint8_t)(u.type & 0x3fu); o->aux = u.aux;
+    if (u.type & RA_N16_EXT) {
+        const uint64_t* x = reinterpret_cast<const uint64_t*>(units + n_notes + 2 * (size_t)u.a);
+        o->slot = u.n; o->a = x[0]; o->b = x[1]; o->c = x[2];
+    } else {
+        o->slot = 0; o->a = u.a; o->b = u.a + u.n;
+        o->c = (u.type & RA_N16_SAME_TERM) ? last_wal_c[u.row] : 0;
+    }
+    if (o->type == RA_NOTE_WAL_APPEND) last_wal_c[u.row] = o->c;
+}
+
+extern "C" size_t ra_notes16_expand(const ra_note16* units, size_t n_notes, size_t n_ext, uint64_t* last_wal_c,
+                                    ra_note* out, size_t cap)
+{
+    (void)n_ext;
+    if (!units || !out || !last_wal_c || cap < n_notes) return 0;
+    for (size_t i = 0; i < n_notes; i++) note16_decode(units, n_notes, i, last_wal_c, &out[i]);
+    return n_notes;
+}
 
 // ---- written-event source: one WAL batch -> one grouped event array (include/ra_engine.h) -----------
 // Within one call a row gets at most max_per_row records and every row's records are adjacent; a writer

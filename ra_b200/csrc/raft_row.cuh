@@ -183,7 +183,7 @@ __device__ __forceinline__ void reset_row(const Cols& C, const u32 r)
     for (u32 s = 0; s < C.members; s++) { st2(&C.pnm[(size_t)s * C.rows + r], 1, 0); C.pcs[(size_t)s * C.rows + r] = 0; }
     for (u32 k = 0; k < RA_MAX_RUNS; k++) st2(&C.run[(size_t)k * C.rows + r], 0, 0);
     C.lrs[r] = 0;
-    C.qi[r] = 0; C.qa[r] = 0;
+    C.qi[r] = 0; C.qa[r] = 0; C.wc[r] = 0;
     for (u32 s = 0; s < C.members; s++) C.pqi[(size_t)s * C.rows + r] = 0;
     C.loc_n[r] = 0; C.out_n[r] = 0;
     if (C.routed) { C.mbox_cnt[0][r] = 0; C.mbox_cnt[1][r] = 0; }
@@ -224,7 +224,7 @@ __device__ __forceinline__ void load_row(const Cols& C, const ra_row_state& s)
     for (u32 k = 0; k < RA_MAX_RUNS; k++)
         st2(&C.run[(size_t)k * C.rows + r], k < s.n_runs ? s.run_start[k] : 0, k < s.n_runs ? s.run_term[k] : 0);
     C.lrs[r] = s.n_runs ? s.run_start[s.n_runs - 1] : 0;
-    C.qi[r] = 0; C.qa[r] = 0;
+    C.qi[r] = 0; C.qa[r] = 0; C.wc[r] = 0;
     for (u32 p = 0; p < C.members; p++) C.pqi[(size_t)p * C.rows + r] = 0;
     C.loc_n[r] = 0;
 }

@@ -88,6 +88,7 @@ struct Cols {
     u64*        qi;
     u64*        qa;
     u64*        pqi;
+    u64*        wc;     // [rows] compact note stream: term of the last WAL_APPEND note the host was told for this row
     u32*        q_used; // != 0 once any consistent-query state may be non-zero in this engine (see update_term_and_voted_for)
     u64*        lrs;    // [rows] start index of the LAST run (copy of run[n_runs-1].x; 0 when the log is
                         // empty): lets the step kernel load it together with the other pairs

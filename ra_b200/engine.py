@@ -59,8 +59,9 @@ EXPORTS = ["ra_engine_create", "ra_engine_destroy", "ra_engine_load_rows", "ra_e
            "ra_engine_load_query_state", "ra_engine_read_query_state", "ra_engine_step_host",
            "ra_engine_submit", "ra_engine_submit_host", "ra_engine_collect", "ra_engine_pending_output",
            "ra_engine_fetch_output", "ra_engine_register_host", "ra_engine_unregister_host",
-           "ra_engine_set_flood_barrier", "ra_engine_flood_faults"]
-HOST_EXPORTS = ["ra_wal_batch_to_events"]            # host-only helpers of the same library
+           "ra_engine_set_flood_barrier", "ra_engine_flood_faults", "ra_engine_set_note_format",
+           "ra_engine_last_ext_count"]
+HOST_EXPORTS = ["ra_wal_batch_to_events", "ra_notes16_expand"]            # host-only helpers of the same library
 HOSTSIM_EXPORTS = ["ra_hostsim_create", "ra_hostsim_create_multi", "ra_hostsim_destroy", "ra_hostsim_run",
                    "ra_hostsim_stats", "ra_hostsim_breakdown"]
 
@@ -102,6 +103,39 @@ class Engine(abi.Backend):
 
     def sync(self) -> None:
         self._check(lib().ra_engine_sync(self._h), "sync")
+
+    # -- compact note stream (16-byte units; include/ra_engine.h ra_note16) ------------------------------------
+    def set_note_format(self, compact: bool) -> None:
+        f = lib().ra_engine_set_note_format
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int]
+        self._check(f(self._h, 1 if compact else 0), "set_note_format")
+        self._last_c = (C.c_uint64 * self.n_rows)() if compact else None
+
+    def step_compact(self, events, msgs_cap: int = 4096, units_cap: int | None = None):
+        """ra_engine_step in compact mode -> (msgs, notes as expanded by ra_notes16_expand, raw units, n_ext)"""
+        l = lib()
+        sz = C.c_size_t
+        n = len(events)
+        ev = (abi.RaEvent * max(n, 1))(*events)
+        units_cap = units_cap or max(256, self.n_rows * abi.RA_NOTE_CAP)
+        msgs = (abi.RaEvent * msgs_cap)()
+        units = (abi.RaNote16 * units_cap)()
+        nm, nn = sz(0), sz(0)
+        f = l.ra_engine_step
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, sz, C.c_void_p, sz, C.POINTER(sz), C.c_void_p, sz, C.POINTER(sz)]
+        self._check(f(self._h, ev, n, msgs, msgs_cap, C.byref(nm), units, units_cap, C.byref(nn)), "step")
+        l.ra_engine_last_ext_count.restype = sz
+        l.ra_engine_last_ext_count.argtypes = [C.c_void_p]
+        n_ext = l.ra_engine_last_ext_count(self._h)
+        out = (abi.RaNote * max(nn.value, 1))()
+        x = l.ra_notes16_expand
+        x.restype = sz
+        x.argtypes = [C.c_void_p, sz, sz, C.c_void_p, C.c_void_p, sz]
+        got = x(units, nn.value, n_ext, self._last_c, out, max(nn.value, 1))
+        assert got == nn.value
+        return list(msgs[: nm.value]), list(out[: nn.value]), list(units[: nn.value + 2 * n_ext]), n_ext
 
     def stall_histogram(self) -> dict:
         """{(role, event_type): count} of events that took the general kernel."""

@@ -90,7 +90,7 @@ extern "C" int ra_emu_create(const ra_engine_cfg* cfg, ra_emu** out)
     {
         const size_t PW = (size_t)C.tiles * 4 * RT;
         HA(C.loc, (size_t)RA_LOCAL_CAP * PW); HA(C.loc_n, R);
-        HA(C.onote, (size_t)RA_NOTE_CAP * R); HA(C.out_n, R); HA(C.counters, 8 + 8 * 16 + 8); HA(C.q_used, 4);
+        HA(C.onote, (size_t)RA_NOTE_CAP * R); HA(C.out_n, R); HA(C.counters, 8 + 8 * 16 + 8); HA(C.q_used, 4); HA(C.wc, R);
         if (C.routed) {
             for (int b = 0; b < 2; b++) { HA(C.mbox[b], M * RA_MBOX_DEPTH * PW); HA(C.mbox_cnt[b], R); }
             HA(C.omsg, (size_t)RA_MSG_CAP * (C.pure ? R : 1));

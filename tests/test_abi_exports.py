@@ -29,7 +29,7 @@ def test_header_symbols_exported():
     assert sim == sorted(engine.HOSTSIM_EXPORTS)
     for n in sim + engine.HOST_EXPORTS:
         assert hasattr(lib, n), n
-    assert sorted(set(re.findall(r"\b(ra_wal_[a-z_]+)\s*\(", src))) == sorted(engine.HOST_EXPORTS)
+    assert sorted(set(re.findall(r"\b(ra_wal_[a-z_]+|ra_notes16_[a-z_]+)\s*\(", src))) == sorted(engine.HOST_EXPORTS)
 
 
 def test_record_sizes_match_header():
