@@ -473,6 +473,12 @@ int  ra_engine_submit(ra_engine* e, const ra_event* ev, size_t n_ev,
                       ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap);
 int  ra_engine_submit_host(ra_engine* e, const ra_host_event* ev, size_t n_ev,
                            ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap);
+/* the same batch handed over in pieces -- one per producer thread, each in its own (pinned) buffer -- which the engine
+ * copies back to back: no host-side concatenation.  The grouping contract holds for the concatenation; a row's
+ * events must not be split between two pieces.  At most 256 pieces. */
+typedef struct ra_host_event_seg { const ra_host_event* ev; size_t n; } ra_host_event_seg;
+int  ra_engine_submit_host_segs(ra_engine* e, const ra_host_event_seg* segs, size_t n_segs,
+                                ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap);
 int  ra_engine_collect(ra_engine* e, size_t* n_msgs, size_t* n_notes);
 /*
  * Compact note stream.  With ra_engine_set_note_format(e, 1) the `notes` buffer of step / submit / fetch_output

@@ -1041,16 +1041,23 @@ static int enqueue_gather(ra_engine* e, IoSlot& q)
     return RA_OK;
 }
 
-static int submit_impl(ra_engine* e, const void* ev, size_t n_ev, bool host32,
+// a batch handed over in pieces (one per producer thread): copied back to back into one device array
+struct EvSeg { const void* p; size_t n; };
+
+static int submit_impl(ra_engine* e, const EvSeg* segs, size_t n_segs, bool host32,
                        ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap)
 {
-    if (!e || (!ev && n_ev) || n_ev > 0x7fffffffull || (!msgs && msgs_cap) || (!notes && notes_cap)) return RA_E_INVAL;
+    if (!e || (!segs && n_segs) || (!msgs && msgs_cap) || (!notes && notes_cap)) return RA_E_INVAL;
+    size_t n_ev = 0;
+    for (size_t k = 0; k < n_segs; k++) { if (!segs[k].p && segs[k].n) return RA_E_INVAL; n_ev += segs[k].n; }
+    if (n_ev > 0x7fffffffull) return RA_E_INVAL;
     if (e->out_pending) return RA_E_CAPACITY;                     // ra_engine_fetch_output first
     IoSlot& q = e->io[e->io_head % RA_IO_SLOTS];
     if (e->io_head - e->io_tail >= RA_IO_SLOTS || q.busy) return RA_E_BUSY;
     CK(cudaSetDevice(e->cfg.device));
     const u32 R = e->C.rows;
-    const size_t bytes = n_ev * (host32 ? sizeof(ra_host_event) : sizeof(ra_event));
+    const size_t rec = host32 ? sizeof(ra_host_event) : sizeof(ra_event);
+    const size_t bytes = n_ev * rec;
     if (n_ev) {
         if (q.d_ev_bytes < bytes) {
             cudaFree(q.d_ev); q.d_ev = nullptr; q.d_ev_bytes = 0;
@@ -1059,7 +1066,12 @@ static int submit_impl(ra_engine* e, const void* ev, size_t n_ev, bool host32,
             q.d_ev_bytes = nb;
         }
         // a pinned source makes this a true asynchronous DMA; a pageable one is staged by the driver
-        CK(cudaMemcpyAsync(q.d_ev, ev, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        size_t off = 0;
+        for (size_t k = 0; k < n_segs; k++) {
+            if (!segs[k].n) continue;
+            CK(cudaMemcpyAsync((char*)q.d_ev + off, segs[k].p, segs[k].n * rec, cudaMemcpyHostToDevice, e->copy_stream));
+            off += segs[k].n * rec;
+        }
         CK(cudaEventRecord(q.h2d_done, e->copy_stream));
         CK(cudaStreamWaitEvent(e->stream, q.h2d_done, 0));
     }
@@ -1138,11 +1150,20 @@ extern "C" int ra_engine_collect(ra_engine* e, size_t* n_msgs, size_t* n_notes)
 
 extern "C" int ra_engine_submit(ra_engine* e, const ra_event* ev, size_t n_ev,
                                 ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap)
-{ return submit_impl(e, ev, n_ev, false, msgs, msgs_cap, notes, notes_cap); }
+{ if (!ev && n_ev) return RA_E_INVAL; EvSeg s = { ev, n_ev }; return submit_impl(e, &s, 1, false, msgs, msgs_cap, notes, notes_cap); }
 
 extern "C" int ra_engine_submit_host(ra_engine* e, const ra_host_event* ev, size_t n_ev,
                                      ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap)
-{ return submit_impl(e, ev, n_ev, true, msgs, msgs_cap, notes, notes_cap); }
+{ if (!ev && n_ev) return RA_E_INVAL; EvSeg s = { ev, n_ev }; return submit_impl(e, &s, 1, true, msgs, msgs_cap, notes, notes_cap); }
+
+extern "C" int ra_engine_submit_host_segs(ra_engine* e, const ra_host_event_seg* segs, size_t n_segs,
+                                          ra_event* msgs, size_t msgs_cap, ra_note* notes, size_t notes_cap)
+{
+    if (n_segs > 256 || (!segs && n_segs)) return RA_E_INVAL;
+    EvSeg s[256];
+    for (size_t k = 0; k < n_segs; k++) { s[k].p = segs[k].ev; s[k].n = segs[k].n; }
+    return submit_impl(e, s, n_segs, true, msgs, msgs_cap, notes, notes_cap);
+}
 
 // outputs that did not fit the buffers of the call that produced them (RA_E_CAPACITY): how many, and again
 extern "C" int ra_engine_pending_output(ra_engine* e, size_t* n_msgs, size_t* n_notes)
@@ -1174,7 +1195,9 @@ static int step_impl(ra_engine* e, const void* ev, size_t n_ev, bool host32,
                      ra_note* notes, size_t notes_cap, size_t* n_notes)
 {
     if (e && e->io_head != e->io_tail) return RA_E_BUSY;          // collect what was submitted first
-    int rc = submit_impl(e, ev, n_ev, host32, msgs, msgs_cap, notes, notes_cap);
+    if (!ev && n_ev) return RA_E_INVAL;
+    EvSeg sg = { ev, n_ev };
+    int rc = submit_impl(e, &sg, 1, host32, msgs, msgs_cap, notes, notes_cap);
     if (rc) return rc;
     return ra_engine_collect(e, n_msgs, n_notes);
 }

@@ -60,7 +60,7 @@ EXPORTS = ["ra_engine_create", "ra_engine_destroy", "ra_engine_load_rows", "ra_e
            "ra_engine_submit", "ra_engine_submit_host", "ra_engine_collect", "ra_engine_pending_output",
            "ra_engine_fetch_output", "ra_engine_register_host", "ra_engine_unregister_host",
            "ra_engine_set_flood_barrier", "ra_engine_flood_faults", "ra_engine_set_note_format",
-           "ra_engine_last_ext_count"]
+           "ra_engine_last_ext_count", "ra_engine_submit_host_segs"]
 HOST_EXPORTS = ["ra_wal_batch_to_events", "ra_notes16_expand"]            # host-only helpers of the same library
 HOSTSIM_EXPORTS = ["ra_hostsim_create", "ra_hostsim_create_multi", "ra_hostsim_destroy", "ra_hostsim_run",
                    "ra_hostsim_stats", "ra_hostsim_breakdown"]

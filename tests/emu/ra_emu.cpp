@@ -462,6 +462,19 @@ extern "C" int ra_engine_submit_host(ra_engine* e, const ra_host_event* ev, size
     m->sub_busy = 1;
     return RA_OK;
 }
+extern "C" int ra_engine_submit_host_segs(ra_engine* e, const ra_host_event_seg* segs, size_t n_segs, ra_event* msgs,
+                                          size_t msgs_cap, ra_note* notes, size_t notes_cap)
+{
+    size_t n = 0;
+    for (size_t k = 0; k < n_segs; k++) n += segs[k].n;
+    ra_host_event* all = (ra_host_event*)malloc((n ? n : 1) * sizeof(ra_host_event));
+    if (!all) return RA_E_NOMEM;
+    size_t off = 0;
+    for (size_t k = 0; k < n_segs; k++) { if (segs[k].n) memcpy(all + off, segs[k].ev, segs[k].n * sizeof(ra_host_event)); off += segs[k].n; }
+    const int rc = ra_engine_submit_host(e, all, n, msgs, msgs_cap, notes, notes_cap);
+    free(all);
+    return rc;
+}
 extern "C" int ra_engine_collect(ra_engine* e, size_t* n_msgs, size_t* n_notes)
 {
     ra_emu* m = (ra_emu*)e;
