@@ -41,7 +41,6 @@ struct Part {
     u64 seed_off;                     // partition p runs the model with seed + p (independent groups)
     std::vector<uint64_t> last_c;     // compact note stream: the decoder's per-row state
     size_t n_ext;                     // extension entries of the call collected last
-    std::vector<ra_host_event_seg> segs;   // the next batch as the model's threads left it: one piece per thread, in row order
 };
 
 // a driver = one host thread that owns some of the partitions (collect, model, submit, round robin) and a team of
@@ -225,25 +224,26 @@ static void model(Driver* s, Part* p, size_t n_notes, u32 cmds, u32 permille, u6
     if (T <= 1 || p->rows < 4096) {
         p->n_ev = compact ? model_range<true>(p, p->notes, n_notes, 0, p->rows, p->ev, cmds, permille, seed, run_model)
                           : model_range<false>(p, p->notes, n_notes, 0, p->rows, p->ev, cmds, permille, seed, run_model);
-        p->segs.assign(1, ra_host_event_seg{p->ev, p->n_ev});
         return;
     }
-    // every thread writes its row range's events straight into its own region of the pinned batch (a row yields at
-    // most RA_LOCAL_CAP events, so region t starts at r0 * RA_LOCAL_CAP); the pieces go to the engine as they are
-    // (ra_engine_submit_host_segs): nothing is concatenated on the host
-    p->segs.resize(T);
     std::vector<size_t>& cnt = s->cnt;
+    std::vector<size_t>& off = s->off;
 #pragma omp parallel num_threads(T)
     {
         const int t = omp_get_thread_num();
         const u32 r0 = (u32)((u64)p->rows * t / T), r1 = (u32)((u64)p->rows * (t + 1) / T);
-        ra_host_event* dst = p->ev + (size_t)r0 * RA_LOCAL_CAP;
-        cnt[t] = compact ? model_range<true>(p, p->notes, n_notes, r0, r1, dst, cmds, permille, seed, run_model)
-                         : model_range<false>(p, p->notes, n_notes, r0, r1, dst, cmds, permille, seed, run_model);
-        p->segs[t].ev = dst; p->segs[t].n = cnt[t];
+        if (s->tmp[t].size() < (size_t)(r1 - r0) * RA_LOCAL_CAP) s->tmp[t].resize((size_t)(r1 - r0) * RA_LOCAL_CAP);
+        cnt[t] = compact ? model_range<true>(p, p->notes, n_notes, r0, r1, s->tmp[t].data(), cmds, permille, seed, run_model)
+                         : model_range<false>(p, p->notes, n_notes, r0, r1, s->tmp[t].data(), cmds, permille, seed, run_model);
+#pragma omp barrier
+#pragma omp single
+        {
+            off[0] = 0;
+            for (int k = 0; k < T; k++) off[k + 1] = off[k] + cnt[k];
+        }
+        if (cnt[t]) memcpy(p->ev + off[t], s->tmp[t].data(), cnt[t] * sizeof(ra_host_event));
     }
-    p->n_ev = 0;
-    for (int t = 0; t < T; t++) p->n_ev += cnt[t];
+    p->n_ev = off[T];
 }
 
 // capacity of a partition's note buffer in the units of its note format (a 32-byte slot holds two 16-byte units)
@@ -295,23 +295,21 @@ static void drive(ra_hostsim* s, u32 k, uint32_t n_steps, uint32_t cmds, uint32_
         for (size_t i = k; i < P; i += D) {
             Part& p = s->parts[i];
             for (u32 g = 0; g < p.groups; g++) put(&p.ev[g], g, RA_EV_ELECTION_TIMEOUT, 0, 0, 0, 0);
-            p.segs.assign(1, ra_host_event_seg{p.ev, p.groups});
-            FAIL_IF(ra_engine_submit_host_segs(p.e, p.segs.data(), p.segs.size(), p.msgs, p.msgs_cap, p.notes, note_cap_of(p)));
+            FAIL_IF(ra_engine_submit_host(p.e, p.ev, p.groups, p.msgs, p.msgs_cap, p.notes, note_cap_of(p)));
             d->h2d += (u64)p.groups * sizeof(ra_host_event); d->calls++;
         }
         for (size_t i = k; i < P; i += D) {
             Part& p = s->parts[i];
             FAIL_IF(collect_part(d, &p, &nn));
             model(d, &p, nn, cmds, permille, seed + p.seed_off, false);   // roles only; no model run for this step
-            p.n_ev = 0; p.segs.assign(1, ra_host_event_seg{p.ev, 0});
+            p.n_ev = 0;
         }
     }
     if (!n_steps) return;
     // software pipeline over the partitions: every partition always has one call in flight
     for (size_t i = k; i < P; i += D) {
         Part& p = s->parts[i];
-        if (p.segs.empty()) p.segs.assign(1, ra_host_event_seg{p.ev, p.n_ev});
-        FAIL_IF(ra_engine_submit_host_segs(p.e, p.segs.data(), p.segs.size(), p.msgs, p.msgs_cap, p.notes, note_cap_of(p)));
+        FAIL_IF(ra_engine_submit_host(p.e, p.ev, p.n_ev, p.msgs, p.msgs_cap, p.notes, note_cap_of(p)));
         d->h2d += (u64)p.n_ev * sizeof(ra_host_event); d->calls++;
     }
     for (u32 t = 0; t < n_steps; t++) {
@@ -324,8 +322,7 @@ static void drive(ra_hostsim* s, u32 k, uint32_t n_steps, uint32_t cmds, uint32_
             p.step++;
             auto a2 = std::chrono::steady_clock::now();
             if (t + 1 < n_steps) {
-                if (p.segs.empty()) p.segs.assign(1, ra_host_event_seg{p.ev, p.n_ev});
-        FAIL_IF(ra_engine_submit_host_segs(p.e, p.segs.data(), p.segs.size(), p.msgs, p.msgs_cap, p.notes, note_cap_of(p)));
+                FAIL_IF(ra_engine_submit_host(p.e, p.ev, p.n_ev, p.msgs, p.msgs_cap, p.notes, note_cap_of(p)));
                 d->h2d += (u64)p.n_ev * sizeof(ra_host_event); d->calls++;
             }
             auto a3 = std::chrono::steady_clock::now();
