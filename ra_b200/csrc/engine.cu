@@ -29,6 +29,9 @@
 #define MINB 5                              // CTAs per SM the register allocation is held to: 20 warps,
                                             // <= 96 registers (no spills), 5 x 39 KB of shared memory
 #endif
+#ifndef MINB_NARROW
+#define MINB_NARROW 6                       // the narrow pass (32-bit index arithmetic) needs fewer registers
+#endif
 #define TILE_BYTES (RT * 64)
 #define RA_BAR_WORDS 64                       // barrier flag words behind mbox_cnt[b] (one per source shard)
 #define WARPS (CTA_T / 32)
@@ -73,11 +76,12 @@ __device__ __forceinline__ void tma_load_tile(void* dst_smem, const void* src_gm
 //   stage[warp][NST][4][32] x 16 B   record tiles staged by TMA, chunk-major (conflict-free LDS.128)
 //   bars[warp][NST]                  one mbarrier per stage
 //   peers[3][8][128] x 8 B           per-thread peer columns (next, match, commit_index_sent), lazy
-template <int MM>
+// (narrow pass, NARROW = true: the peer cells are 8 + 4 bytes instead of 16 + 8)
+template <int MM, bool NARROW = false>
 struct StepSmem {
     ulonglong2 stage[WARPS][NST][4 * RT];
-    ulonglong2 peers_nm[PSTR * CTA_T];       // [s][thread] {next_index, match_index}
-    u64 peers_cs[PSTR * CTA_T];              // [s][thread] commit_index_sent (directly behind peers_nm)
+    ulonglong2 peers_nm[PSTR * CTA_T / (NARROW ? 2 : 1)];   // [s][thread] {next_index, match_index}
+    u64 peers_cs[PSTR * CTA_T / (NARROW ? 2 : 1)];          // [s][thread] commit_index_sent (directly behind peers_nm)
     u64 bars[WARPS][NST];
 };
 
@@ -140,161 +144,19 @@ __device__ __forceinline__ void flush_ref_counters(const Cols& C, u32 lane, u64 
     }
 }
 
-template <int MM, bool FAULTS>
-__global__ void __launch_bounds__(CTA_T, MINB)
-raft_step_kernel(const __grid_constant__ Cols C, const int cur, const FloodArgs F,
-                 StallCtx* __restrict__ stall_list, u32* __restrict__ stall_count, u32* __restrict__ stall_count_next)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    StepSmem<MM>& S = *reinterpret_cast<StepSmem<MM>*>(smem_raw);
-    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-#ifdef RA_INTERLEAVE
-    // CTAs are handed their tiles slot-interleaved: consecutive CTAs work on different slots' row ranges, so that
-    // the long-running warps of one kind of row (a slot full of leaders) are spread over the whole launch
-    // instead of filling its first wave.  (grid = per * members CTAs, see launch_step)
-    u32 wtile;
-    {
-        const u32 k = C.members, per = gridDim.x / k;
-        wtile = ((blockIdx.x % k) * per + blockIdx.x / k) * WARPS + warp;
-    }
-#else
-    const u32 wtile = blockIdx.x * WARPS + warp;                 // this warp's record tile
-#endif
-    const u32 r = wtile * RT + lane;
-    const bool valid = r < C.rows;
-    u32 k_events = 0, k_commits = 0, k_applied = 0, k_msgs = 0, k_dropped = 0, k_elect = 0, k_fatal = 0;
-    u64 k_ref = 0;
-    if (blockIdx.x == 0 && tid == 0) *stall_count_next = 0;    // the list of the step after this one
-
-    // ---- what does this row have to do? ---------------------------------------------------
-    // every per-row input of the step is requested up front, in one round trip to HBM
-    const ulonglong2 z2 = make_ulonglong2(0, 0);
-    ulonglong2 ap = z2, tc = z2, lg = z2, lw = z2;
-    u64 cntw = 0, lrs = 0; u32 nloc = 0;
-    if (valid) {
-        ap = C.ap[r];
-        nloc = C.loc_n[r];
-        if (C.routed) cntw = C.mbox_cnt[cur][r];
-        tc = C.tc[r]; lg = C.lg[r]; lw = C.lw[r]; lrs = C.lrs[r];
-    }
-    if (*C.abort) return;                                       // a host batch was rejected: nothing may change
-    const bool fatal0 = MT_FATAL(ap.y) != 0;
-    const bool pending = valid && MT_PIPE_PEND(ap.y) != 0;
-    // planes of this row: mailbox plane (sender s, depth k) = bit s * DEPTH + k, host slot k = bit NPM + k
-    constexpr u32 NPM = (MMEM ? MMEM : RA_MAX_MEMBERS) * RA_MBOX_DEPTH;
-    typedef typename PlaneMask<(NPM + RA_LOCAL_CAP <= 32)>::type mask_t;
-    mask_t mine = 0;
-    u32 my_tail = 0;                                            // senders (bits 0..7) / host slots (8..)
-    if (valid && !fatal0) {                                     // whose records carry a 32-byte tail
-        u32 mb = 0;
-        for (u32 s = 0; s < NMEM(C); s++) {
-            const u32 c = (u32)(cntw >> (8 * s)) & 0xffu;
-            mb |= ((1u << (c & 7u)) - 1u) << (RA_MBOX_DEPTH * s);
-            my_tail |= ((c >> 3) & 1u) << s;
-        }
-        mine = (mask_t)mb | ((mask_t)((1u << (nloc & 7u)) - 1u) << NPM);
-        my_tail |= nloc & 0xff00u;
-    }
-    const bool work = valid && (F.on || nloc || cntw || pending);
-    // everything below is per warp: no CTA-wide barrier anywhere in this kernel
-    mask_t todo = mask_or_warp(mine);                           // planes still to consume
-    const u32 w_tail = __reduce_or_sync(0xffffffffu, my_tail);
-    if (!__any_sync(0xffffffffu, work)) return;                 // whole warp idle
-    u64* bars = &S.bars[warp][0];
-    if (lane == 0) {
-        for (int i = 0; i < NST; i++) mbar_init(&bars[i], 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-
-    Member m;
-    member_init(m, C, valid ? r : 0, tc, lg, lw, ap, lrs, cur, &S.peers_nm[tid]);
-    m.row = r;
-    if (work && !fatal0 && MT_ROLE(ap.y) == RA_LEADER) peers_prefetch<MM>(m);
-
-    bool stalled = false;
-    u32 stall_flags = 0;
-
-    // ---- inputs: TMA stages this warp's record tiles through a ring of NST 2 KB slots, in ------
-    // evaluation order: deferred pipeline pass, mailbox planes by sender slot then depth, then
-    // the host-event planes.  A slot is refilled as soon as the warp has consumed it.
-    mask_t rem = 0;                                             // a stalled row's planes not yet evaluated
-    if (work && !fatal0 && pending) {                           // pipeline_rpcs is not a fast path
-        stalled = true; stall_flags = STALL_PENDING; rem = mine;
-    }
-    mask_t toissue = todo;                                      // planes still to request
-    u32 n_issued = 0, n_done = 0, st_issue = 0, st = 0, par = 0; // ring positions = counters mod NST, phase parity
-#pragma unroll 1
-    while (todo) {
-        if (lane == 0) {
-#pragma unroll 1
-            while (toissue && n_issued < n_done + NST) {
-                const u32 q = mask_ffs(toissue); toissue &= toissue - 1;
-                // (the tile address is rebuilt per issue -- a handful of integer ops in one lane -- instead of
-                // holding two 64-bit plane bases in registers through the whole event loop)
-                const size_t plane_words = (size_t)C.tiles * (4 * RT);      // 16-byte words per plane
-                const ulonglong2* src = (q < NPM ? C.mbox[cur] + (size_t)q * plane_words
-                                                 : C.loc + (size_t)(q - NPM) * plane_words) + (size_t)wtile * (4 * RT);
-                const u32 tbit = q < NPM ? q / RA_MBOX_DEPTH : 8u + q - NPM;
-                const u32 bytes = ((w_tail >> tbit) & 1u) ? TILE_BYTES : TILE_BYTES / 2;
-                fence_proxy_async();                            // the slot was read through the generic proxy
-                mbar_expect_tx(&bars[st_issue], bytes);
-                tma_load_tile(&S.stage[warp][st_issue][0], src, bytes, &bars[st_issue]);
-                n_issued++; st_issue = st_issue + 1 == NST ? 0 : st_issue + 1;
-            }
-        }
-        const u32 p = mask_ffs(todo); todo &= todo - 1;
-        const bool my = !stalled && ((mine >> p) & 1u);
-        mbar_wait(&bars[st], par);
-        if (my) {
-            const ulonglong2* sp = &S.stage[warp][st][0];
-            const ulonglong2 c0 = sp[lane], c1 = sp[RT + lane];
-            ulonglong2 t2 = make_ulonglong2(0, 0), t3 = t2;
-            if (rec_has_tail(c0)) { t2 = sp[2 * RT + lane]; t3 = sp[3 * RT + lane]; }
-            const Rec e = rec_decode(c0, c1, t2, t3, r);
-            if (MT_FATAL(m.meta)) m.c_pack += 1u;
-            else if (FAULTS && p < NPM && flood_lost<MM>(F, C, m, r, e)) m.c_pack += 1u << 20;   // fault injection: lost in transit
-            else if (!note_budget_ok(m) || C.pure || !fast_event<MM>(m, e)) {
-                stalled = true;                                 // planes are consumed in bit order:
-                rem = mine & ~(((mask_t)1 << p) - 1);           // p and up are left for the general kernel
-                atomicAdd(&C.counters[8 + (m_role(m) & 7u) * 16 + (R_type(e) & 15u)], 1ull);   // diagnostics
-            }
-        }
-        n_done++;
-        if (++st == NST) { st = 0; par ^= 1u; }
-        __syncwarp();                                           // every lane is done with the slot
-    }
-    const u32 rem_mbox = (u32)(rem & (((mask_t)1 << (NPM - 1) << 1) - 1)), rem_loc = (u32)(rem >> (NPM - 1) >> 1);
-
-    if (work) {
-        if (cntw && !fatal0) C.mbox_cnt[cur][r] = 0;
-        if (nloc) C.loc_n[r] = 0;
-        if ((m.pstate & 3u) == 2u) asm volatile("cp.async.wait_all;" ::: "memory");   // prefetch never consumed
-        peers_writeback<MM>(m);
-        if (!stalled) k_fatal = row_end_of_step<MM, FAULTS>(m, C, r, cur, F);
-        member_writeback(m, C, r);
-        k_events = m.c_pack & 0xffu; k_commits = m.c_commits; k_applied = m.c_applied;
-        k_msgs = (m.c_pack >> 8) & 0xffu; k_dropped = m.c_pack >> 20; k_elect = (m.c_pack >> 16) & 15u;
-        k_ref = m.c_ref;
-    }
-    // stalled rows: hand the rest of the step to raft_general_kernel
-    const u32 sm = __ballot_sync(0xffffffffu, stalled);
-    if (sm) {
-        u32 base = 0;
-        if (lane == 0) base = atomicAdd(stall_count, (u32)__popc(sm));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (stalled) {
-            ulonglong2* q = reinterpret_cast<ulonglong2*>(&stall_list[base + __popc(sm & ((1u << lane) - 1u))]);
-            q[0] = make_ulonglong2((u64)r | ((u64)stall_flags << 32), (u64)rem_mbox | ((u64)rem_loc << 32));
-            q[1] = make_ulonglong2((u64)(m.n_msgs | (m.n_notes << 16)) | ((u64)m.status << 32),
-                                   (u64)m.sent_to | ((u64)(m.pn_type | (m.pn_slot << 8) | (m.wk << 16)) << 32));
-            q[2] = make_ulonglong2(m.pn_a, m.pn_b);
-            q[3] = make_ulonglong2(m.pn_c, 0);
-        }
-    }
-    flush_counters(C, lane, k_events, k_commits, k_applied, k_msgs, k_dropped, k_elect, k_fatal);
-    flush_ref_counters(C, lane, k_ref);
+// the hot kernel, once per index width (raft_step.cuh): ra_wide::raft_step_kernel, ra_narrow::raft_step_kernel
+namespace ra_wide {
+#define RA_NARROW_PASS 0
+#include "raft_step_kernel.cuh"
+#undef RA_NARROW_PASS
 }
+#ifndef RA_NO_NARROW
+namespace ra_narrow {
+#define RA_NARROW_PASS 1
+#include "raft_step_kernel.cuh"
+#undef RA_NARROW_PASS
+}
+#endif
 
 // general path for the stalled rows of this step (one thread per list entry)
 __global__ void __launch_bounds__(CTA_T)
@@ -322,6 +184,7 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
             m.sent_to = (u32)q1.y;
             { const u32 w = (u32)(q1.y >> 32); m.pn_type = w & 0xffu; m.pn_slot = (w >> 8) & 0xffu; m.wk = w >> 16; }
             m.pn_a = q2.x; m.pn_b = q2.y; m.pn_c = q3.x;
+            u64 big = 0;                                        // see row_mark_wide
             if (flags & STALL_PENDING) {
                 MT_SET(m.meta, 24, 1, 0);
                 process_event<MM>(m, mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
@@ -331,6 +194,7 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
             while (rem_mbox) {
                 const u32 p = __ffs(rem_mbox) - 1; rem_mbox &= rem_mbox - 1;
                 const Rec e = ld_rec_plane(C.mbox[cur], C.tiles, p, r);
+                big |= rec_magnitude(e);
                 if (MT_FATAL(m.meta)) m.c_pack += 1u;
                 else if (flood_lost<MM>(F, C, m, r, e)) m.c_pack += 1u << 20;
                 else if (!note_budget_ok(m)) budget_drop_record(m);
@@ -340,6 +204,7 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
             while (rem_loc) {
                 const u32 p = __ffs(rem_loc) - 1; rem_loc &= rem_loc - 1;
                 const Rec e = ld_rec_plane(C.loc, C.tiles, p, r);
+                big |= rec_magnitude(e);
                 if (MT_FATAL(m.meta)) m.c_pack += 1u;
                 else if (!note_budget_ok(m)) budget_refuse_local(m);
                 else if (C.pure || !fast_event<MM>(m, e)) { process_event<MM>(m, e); m.cold &= ~8u; }
@@ -347,6 +212,7 @@ raft_general_kernel(const __grid_constant__ Cols C, const int cur, const FloodAr
             peers_writeback<MM>(m);
             k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
             member_writeback(m, C, r);
+            row_mark_wide(C, r, m, big);
             k_events = m.c_pack & 0xffu; k_commits = m.c_commits; k_applied = m.c_applied;
             k_msgs = (m.c_pack >> 8) & 0xffu; k_dropped = m.c_pack >> 20; k_elect = (m.c_pack >> 16) & 15u;
             k_ref = m.c_ref;
@@ -692,8 +558,9 @@ struct ra_engine {
     u64 step_no, steps;
     u64 bar_epoch;                            // peer transport: barriers passed since the last reset
     int flood_barrier;                        // peer transport: ra_engine_flood ends every step with the device barrier
-    void* allocs[64]; int n_allocs;
+    void* allocs[96]; int n_allocs;
     IoSlot io[RA_IO_SLOTS]; u32 io_head, io_tail;   // FIFO: submit fills io[io_head % SLOTS], collect drains io_tail
+    int narrow;                               // the hot kernel computes on 32-bit indexes where it can (default; RA_STEP_WIDE=1: never)
     int out_pending;                          // the last collect ended in RA_E_CAPACITY: outputs wait in the row slots
     size_t pred_msgs, pred_notes, pred_ext;   // outputs of the last collected call (sizes the next DMA is enqueued with)
     int compact;                              // notes leave as 16-byte units (ra_engine_set_note_format)
@@ -798,6 +665,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
     ra_engine* e = (ra_engine*)calloc(1, sizeof(ra_engine));
     if (!e) return RA_E_NOMEM;
     e->cfg = *cfg;
+    { const char* w = getenv("RA_STEP_WIDE"); e->narrow = !(w && *w && *w != '0'); }
     if (e->cfg.max_pipeline_count == 0) e->cfg.max_pipeline_count = 4096;
     if (e->cfg.max_aer_batch == 0) e->cfg.max_aer_batch = 128;
     int rc = RA_OK;
@@ -829,7 +697,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
 #define DA(p, n) if ((rc = dalloc(e, &(p), (n))) != RA_OK) goto bad
         DA(C.tc, R); DA(C.lg, R); DA(C.lw, R); DA(C.ap, R); DA(C.sn, R); DA(C.tk, R); DA(C.fm, R);
         DA(C.cd, 2 * R); DA(C.pnm, M * R); DA(C.pcs, M * R); DA(C.run, RA_MAX_RUNS * R); DA(C.lrs, R);
-        DA(C.qi, R); DA(C.qa, R); DA(C.pqi, M * R); DA(C.q_used, 4); DA(C.wc, R);
+        DA(C.qi, R); DA(C.qa, R); DA(C.pqi, M * R); DA(C.q_used, 4); DA(C.wc, R); DA(C.wf, R);
         C.tiles = (u32)((R + RT - 1) / RT);
         const size_t PW = (size_t)C.tiles * 4 * RT;             // 16-byte words per tiled plane
         DA(C.loc, (size_t)RA_LOCAL_CAP * PW); DA(C.loc_n, R);
@@ -854,13 +722,19 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
         cub::DeviceScan::ExclusiveSum(nullptr, e->scan_tmp2_bytes, e->d_next, e->d_xoffs, (int)(R + 1), e->stream);
         if ((ce = cudaMalloc(&e->d_scan_tmp2, e->scan_tmp2_bytes ? e->scan_tmp2_bytes : 16)) != cudaSuccess) { rc = fail(e, ce, "cudaMalloc scan"); goto bad; }
     }
-#define SMEM_ATTR(MEMB, TRN, FLT) \
-    if ((ce = cudaFuncSetAttribute(raft_step_kernel<MK_MM(MEMB, TRN), FLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                   (int)sizeof(StepSmem<MK_MM(MEMB, TRN)>))) != cudaSuccess) { rc = fail(e, ce, "cudaFuncSetAttribute"); goto bad; }
+#define SMEM_ATTR_NS(NS, NARROW, MEMB, TRN, FLT) \
+    if ((ce = cudaFuncSetAttribute(NS::raft_step_kernel<MK_MM(MEMB, TRN), FLT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   (int)sizeof(StepSmem<MK_MM(MEMB, TRN), NARROW>))) != cudaSuccess) { rc = fail(e, ce, "cudaFuncSetAttribute"); goto bad; }
+#define SMEM_ATTR(MEMB, TRN, FLT) SMEM_ATTR_NS(ra_wide, false, MEMB, TRN, FLT)
+#ifndef RA_NO_NARROW
+    SMEM_ATTR_NS(ra_narrow, true, 5, TR_LOCAL, false) SMEM_ATTR_NS(ra_narrow, true, 5, TR_PEER, false) SMEM_ATTR_NS(ra_narrow, true, 5, TR_HOST, false)
+    SMEM_ATTR_NS(ra_narrow, true, 3, TR_LOCAL, false) SMEM_ATTR_NS(ra_narrow, true, 7, TR_LOCAL, false)
+#endif
     SMEM_ATTR(0, TR_RUNTIME, true) SMEM_ATTR(0, TR_RUNTIME, false)
     SMEM_ATTR(5, TR_LOCAL, false) SMEM_ATTR(5, TR_PEER, false) SMEM_ATTR(5, TR_BUCKET, false) SMEM_ATTR(5, TR_HOST, false)
     SMEM_ATTR(3, TR_LOCAL, false) SMEM_ATTR(7, TR_LOCAL, false) SMEM_ATTR(5, TR_LOCAL, true) SMEM_ATTR(7, TR_LOCAL, true)
 #undef SMEM_ATTR
+#undef SMEM_ATTR_NS
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -960,8 +834,16 @@ static int launch_step(ra_engine* e, const FloodArgs& F)
     u32* cnt = e->d_stall_cnt + (e->steps & 1), *cnt_next = e->d_stall_cnt + ((e->steps + 1) & 1);
     // one specialisation of the hot kernel per (member count, transport): see MK_MM
     const int tr = !e->C.routed ? TR_HOST : (e->C.n_shards > 1 ? (e->C.peer_mode ? TR_PEER : TR_BUCKET) : TR_LOCAL);
-#define LAUNCH(MEMB, TRN, FLT) raft_step_kernel<MK_MM(MEMB, TRN), FLT><<<grid, CTA_T, sizeof(StepSmem<MK_MM(MEMB, TRN)>), e->stream>>>( \
+#define LAUNCH_NS(NS, NARROW, MEMB, TRN, FLT) NS::raft_step_kernel<MK_MM(MEMB, TRN), FLT><<<grid, CTA_T, sizeof(StepSmem<MK_MM(MEMB, TRN), NARROW>), e->stream>>>( \
         e->C, e->cur, F, e->d_stall, cnt, cnt_next)
+#define LAUNCH(MEMB, TRN, FLT) LAUNCH_NS(ra_wide, false, MEMB, TRN, FLT)
+#ifndef RA_NO_NARROW
+    // 32-bit index arithmetic for the specialisations that carry the load (exact: rows or records that do not fit
+    // stall to the 64-bit general kernel); RA_STEP_WIDE=1 in the environment keeps the 64-bit hot kernel
+#define LAUNCH_N(MEMB, TRN, FLT) do { if (e->narrow) LAUNCH_NS(ra_narrow, true, MEMB, TRN, FLT); else LAUNCH_NS(ra_wide, false, MEMB, TRN, FLT); } while (0)
+#else
+#define LAUNCH_N(MEMB, TRN, FLT) LAUNCH_NS(ra_wide, false, MEMB, TRN, FLT)
+#endif
     const bool faults = (F.drop | F.withhold | F.part) != 0;     // fault injection: its own specialisations
     if (faults) {
         if (e->C.members == 5 && tr == TR_LOCAL) LAUNCH(5, TR_LOCAL, true);
@@ -969,19 +851,21 @@ static int launch_step(ra_engine* e, const FloodArgs& F)
         else LAUNCH(0, TR_RUNTIME, true);
     } else if (e->C.members == 5) {
         switch (tr) {
-        case TR_LOCAL:  LAUNCH(5, TR_LOCAL, false); break;
-        case TR_PEER:   LAUNCH(5, TR_PEER, false); break;
+        case TR_LOCAL:  LAUNCH_N(5, TR_LOCAL, false); break;
+        case TR_PEER:   LAUNCH_N(5, TR_PEER, false); break;
         case TR_BUCKET: LAUNCH(5, TR_BUCKET, false); break;
-        default:        LAUNCH(5, TR_HOST, false); break;
+        default:        LAUNCH_N(5, TR_HOST, false); break;
         }
     } else if (e->C.members == 3 && tr == TR_LOCAL) {
-        LAUNCH(3, TR_LOCAL, false);
+        LAUNCH_N(3, TR_LOCAL, false);
     } else if (e->C.members == 7 && tr == TR_LOCAL) {
-        LAUNCH(7, TR_LOCAL, false);
+        LAUNCH_N(7, TR_LOCAL, false);
     } else {
         LAUNCH(0, TR_RUNTIME, false);
     }
 #undef LAUNCH
+#undef LAUNCH_N
+#undef LAUNCH_NS
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(e, ce, "raft_step_kernel");
     raft_general_kernel<<<e->general_grid, CTA_T, 0, e->stream>>>(e->C, e->cur, F, e->d_stall, cnt);

@@ -16,6 +16,8 @@
 
 struct ulonglong2 { unsigned long long x, y; };
 static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { ulonglong2 r; r.x = x; r.y = y; return r; }
+struct uint2 { unsigned int x, y; };
+static inline uint2 make_uint2(unsigned int x, unsigned int y) { uint2 r; r.x = x; r.y = y; return r; }
 
 struct ra_emu_dim3 { unsigned x, y, z; };
 static const ra_emu_dim3 threadIdx = {0, 0, 0};

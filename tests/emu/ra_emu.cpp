@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #include <new>
 #include "cuda_shim.h"
@@ -28,7 +29,8 @@ struct ra_emu {
     Cols C;
     int cur;
     u64 step_no, steps;
-    void* allocs[64]; int n_allocs;
+    void* allocs[96]; int n_allocs;
+    int narrow;                                       // RA_STEP_WIDE=1 in the environment: 64-bit pass only (as engine.cu)
     int out_pending;                                  // a step's outputs did not fit: they wait in the row slots
     int sub_busy, sub_rc; size_t sub_nm, sub_nn;      // the one "submitted" call (ra_engine_submit_host shim)
 };
@@ -68,6 +70,7 @@ extern "C" int ra_emu_create(const ra_engine_cfg* cfg, ra_emu** out)
     ra_emu* e = (ra_emu*)calloc(1, sizeof(ra_emu));
     if (!e) return RA_E_NOMEM;
     e->cfg = *cfg;
+    { const char* w = getenv("RA_STEP_WIDE"); e->narrow = !(w && *w && *w != '0'); }
     if (e->cfg.max_pipeline_count == 0) e->cfg.max_pipeline_count = 4096;
     if (e->cfg.max_aer_batch == 0) e->cfg.max_aer_batch = 128;
     int rc = RA_OK;
@@ -90,7 +93,7 @@ extern "C" int ra_emu_create(const ra_engine_cfg* cfg, ra_emu** out)
     {
         const size_t PW = (size_t)C.tiles * 4 * RT;
         HA(C.loc, (size_t)RA_LOCAL_CAP * PW); HA(C.loc_n, R);
-        HA(C.onote, (size_t)RA_NOTE_CAP * R); HA(C.out_n, R); HA(C.counters, 8 + 8 * 16 + 8); HA(C.q_used, 4); HA(C.wc, R);
+        HA(C.onote, (size_t)RA_NOTE_CAP * R); HA(C.out_n, R); HA(C.counters, 8 + 8 * 16 + 8); HA(C.q_used, 4); HA(C.wc, R); HA(C.wf, R);
         if (C.routed) {
             for (int b = 0; b < 2; b++) { HA(C.mbox[b], M * RA_MBOX_DEPTH * PW); HA(C.mbox_cnt[b], R); }
             HA(C.omsg, (size_t)RA_MSG_CAP * (C.pure ? R : 1));
@@ -152,12 +155,27 @@ extern "C" int ra_emu_read_query_state(ra_emu* e, ra_query_state* q, size_t n)
 
 struct Scratch { ulonglong2 nm[RA_MAX_MEMBERS]; u64 cs[RA_MAX_MEMBERS]; };   // the per-thread shared-memory columns
 
-static void add_counters(const Cols& C, const Member& m, u32 k_fatal)
+// test observability: rows stepped by the narrow pass, records it refused (a field >= 2^30), rows it left to the
+// general kernel because their sticky `wide` byte is set
+static unsigned long long g_narrow_stats[3];
+extern "C" void ra_emu_narrow_stats(unsigned long long* out, int reset)
+{ for (int i = 0; i < 3; i++) { out[i] = g_narrow_stats[i]; if (reset) g_narrow_stats[i] = 0; } }
+
+namespace ra_wide {
+#define RA_NARROW_PASS 0
+#include "step_row.inc"
+#undef RA_NARROW_PASS
+}
+namespace ra_narrow {
+#define RA_NARROW_PASS 1
+#include "step_row.inc"
+#undef RA_NARROW_PASS
+}
+// a value left or entered the 32-bit pass out of range: the guards (Cols::wf, rec_decode) have a hole
+extern "C" void ra_emu_narrow_violation(const char* what, unsigned long long v)
 {
-    C.counters[0] += m.c_pack & 0xffu; C.counters[1] += m.c_commits; C.counters[2] += m.c_applied;
-    C.counters[3] += (m.c_pack >> 8) & 0xffu; C.counters[4] += m.c_pack >> 20; C.counters[5] += (m.c_pack >> 16) & 15u;
-    C.counters[6] += k_fatal;
-    for (int f = 0; f < 7; f++) C.counters[136 + f] += (m.c_ref >> (8 * f)) & 0xffu;   // the reference's counters
+    fprintf(stderr, "ra_emu: narrow pass violation in %s(): value %llu\n", what, v);
+    abort();
 }
 
 // the general kernel's body for one stall context (engine.cu: raft_general_kernel)
@@ -174,6 +192,7 @@ static void general_row(const Cols& C, int cur, const FloodArgs& F, const StallC
     m.sent_to = ctx.sent_to;
     { const u32 w = ctx.pn_type_slot_wk; m.pn_type = w & 0xffu; m.pn_slot = (w >> 8) & 0xffu; m.wk = w >> 16; }
     m.pn_a = ctx.pn_a; m.pn_b = ctx.pn_b; m.pn_c = ctx.pn_c;
+    u64 big = 0;
     if (flags & STALL_PENDING) {
         MT_SET(m.meta, 24, 1, 0);
         process_event<MM>(m, mk_rec(r, RA_EV_PIPELINE_RPCS, RA_NO_SLOT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
@@ -182,6 +201,7 @@ static void general_row(const Cols& C, int cur, const FloodArgs& F, const StallC
     while (rem_mbox) {
         const u32 p = __ffs(rem_mbox) - 1; rem_mbox &= rem_mbox - 1;
         const Rec e = ld_rec_plane(C.mbox[cur], C.tiles, p, r);
+        big |= rec_magnitude(e);
         if (MT_FATAL(m.meta)) m.c_pack += 1u;
         else if (flood_lost<MM>(F, C, m, r, e)) m.c_pack += 1u << 20;
         else if (!note_budget_ok(m)) budget_drop_record(m);
@@ -190,6 +210,7 @@ static void general_row(const Cols& C, int cur, const FloodArgs& F, const StallC
     while (rem_loc) {
         const u32 p = __ffs(rem_loc) - 1; rem_loc &= rem_loc - 1;
         const Rec e = ld_rec_plane(C.loc, C.tiles, p, r);
+        big |= rec_magnitude(e);
         if (MT_FATAL(m.meta)) m.c_pack += 1u;
         else if (!note_budget_ok(m)) budget_refuse_local(m);
         else if (C.pure || !fast_event<MM>(m, e)) { process_event<MM>(m, e); m.cold &= ~8u; }
@@ -197,69 +218,8 @@ static void general_row(const Cols& C, int cur, const FloodArgs& F, const StallC
     peers_writeback<MM>(m);
     const u32 k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
     member_writeback(m, C, r);
-    add_counters(C, m, k_fatal);
-}
-
-// the step kernel's body for one row (engine.cu: raft_step_kernel<MM>); true = the row stalled
-template <int MM>
-static bool step_row(const Cols& C, int cur, const FloodArgs& F, u32 r, StallCtx& ctx)
-{
-    constexpr u32 NPM = (MMEM ? MMEM : RA_MAX_MEMBERS) * RA_MBOX_DEPTH;
-    Scratch sc;
-    const ulonglong2 ap = C.ap[r];
-    const u32 nloc = C.loc_n[r];
-    const u64 cntw = C.routed ? C.mbox_cnt[cur][r] : 0;
-    const ulonglong2 tc = C.tc[r], lg = C.lg[r], lw = C.lw[r];
-    const u64 lrs = C.lrs[r];
-    const bool fatal0 = MT_FATAL(ap.y) != 0;
-    const bool pending = MT_PIPE_PEND(ap.y) != 0;
-    u64 mine = 0;
-    if (!fatal0) {
-        u32 mb = 0;
-        for (u32 s = 0; s < NMEM(C); s++) {
-            const u32 c = (u32)(cntw >> (8 * s)) & 0xffu;
-            mb |= ((1u << (c & 7u)) - 1u) << (RA_MBOX_DEPTH * s);
-        }
-        mine = (u64)mb | ((u64)((1u << (nloc & 7u)) - 1u) << NPM);
-    }
-    const bool work = F.on || nloc || cntw || pending;
-    if (!work) return false;
-    Member m;
-    member_init(m, C, r, tc, lg, lw, ap, lrs, cur, sc.nm);
-    m.row = r;
-    if (!fatal0 && MT_ROLE(ap.y) == RA_LEADER) peers_prefetch<MM>(m);
-    bool stalled = false;
-    u32 stall_flags = 0;
-    u64 rem = 0;
-    if (!fatal0 && pending) { stalled = true; stall_flags = STALL_PENDING; rem = mine; }
-    u64 todo = mine;
-    while (todo) {
-        const u32 p = (u32)__ffsll((long long)todo) - 1u; todo &= todo - 1;
-        if (stalled) continue;
-        const Rec e = p < NPM ? ld_rec_plane(C.mbox[cur], C.tiles, p, r) : ld_rec_plane(C.loc, C.tiles, p - NPM, r);
-        if (MT_FATAL(m.meta)) m.c_pack += 1u;
-        else if (p < NPM && flood_lost<MM>(F, C, m, r, e)) m.c_pack += 1u << 20;
-        else if (!note_budget_ok(m) || C.pure || !fast_event<MM>(m, e)) {
-            stalled = true;
-            rem = mine & ~(((u64)1 << p) - 1);
-            atomicAdd(&C.counters[8 + (m_role(m) & 7u) * 16 + (R_type(e) & 15u)], 1ull);
-        }
-    }
-    if (cntw && !fatal0) C.mbox_cnt[cur][r] = 0;
-    if (nloc) C.loc_n[r] = 0;
-    peers_writeback<MM>(m);
-    u32 k_fatal = 0;
-    if (!stalled) k_fatal = row_end_of_step<MM>(m, C, r, cur, F);
-    member_writeback(m, C, r);
-    add_counters(C, m, k_fatal);
-    if (stalled) {
-        ctx.row = r; ctx.flags = stall_flags;
-        ctx.rem_mbox = (u32)(rem & (((u64)1 << NPM) - 1)); ctx.rem_loc = (u32)(rem >> NPM);
-        ctx.n_msgs_notes = m.n_msgs | (m.n_notes << 16); ctx.status = m.status; ctx.sent_to = m.sent_to;
-        ctx.pn_type_slot_wk = m.pn_type | (m.pn_slot << 8) | (m.wk << 16);
-        ctx.pn_a = m.pn_a; ctx.pn_b = m.pn_b; ctx.pn_c = m.pn_c; ctx._pad = 0;
-    }
-    return stalled;
+    row_mark_wide(C, r, m, big);
+    ra_wide::add_counters(C, m, k_fatal);
 }
 
 static int run_step(ra_emu* e, const FloodArgs& F)
@@ -276,11 +236,14 @@ static int run_step(ra_emu* e, const FloodArgs& F)
         bool stalled;
         if (C.members == 5) {
             switch (tr) {
-            case TR_LOCAL:  stalled = step_row<MK_MM(5, TR_LOCAL)>(C, e->cur, F, r, ctx); break;
-            case TR_BUCKET: stalled = step_row<MK_MM(5, TR_BUCKET)>(C, e->cur, F, r, ctx); break;
-            default:        stalled = step_row<MK_MM(5, TR_HOST)>(C, e->cur, F, r, ctx); break;
+            // (narrow pass for the same specialisations as launch_step(); RA_STEP_WIDE=1 keeps the 64-bit pass)
+            case TR_LOCAL:  stalled = e->narrow ? ra_narrow::step_row<MK_MM(5, TR_LOCAL)>(C, e->cur, F, r, ctx)
+                                                : ra_wide::step_row<MK_MM(5, TR_LOCAL)>(C, e->cur, F, r, ctx); break;
+            case TR_BUCKET: stalled = ra_wide::step_row<MK_MM(5, TR_BUCKET)>(C, e->cur, F, r, ctx); break;
+            default:        stalled = e->narrow ? ra_narrow::step_row<MK_MM(5, TR_HOST)>(C, e->cur, F, r, ctx)
+                                                : ra_wide::step_row<MK_MM(5, TR_HOST)>(C, e->cur, F, r, ctx); break;
             }
-        } else stalled = step_row<MK_MM(0, TR_RUNTIME)>(C, e->cur, F, r, ctx);
+        } else stalled = ra_wide::step_row<MK_MM(0, TR_RUNTIME)>(C, e->cur, F, r, ctx);
         // the general kernel runs after the step kernel; rows only ever write to OTHER rows' mailboxes of
         // the NEXT step, so handling a stalled row right away is the same thing
         if (stalled) general_row(C, e->cur, F, ctx);

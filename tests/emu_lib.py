@@ -20,9 +20,9 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        srcs = [os.path.join(_DIR, "ra_emu.cpp"), os.path.join(_DIR, "cuda_shim.h"),
-                os.path.join(_ROOT, "ra_b200", "csrc", "raft_step.cuh"),
-                os.path.join(_ROOT, "ra_b200", "csrc", "raft_row.cuh"),
+        srcs = [os.path.join(_DIR, "ra_emu.cpp"), os.path.join(_DIR, "step_row.inc"), os.path.join(_DIR, "cuda_shim.h"),
+                *[os.path.join(_ROOT, "ra_b200", "csrc", f) for f in
+                  ("raft_step.cuh", "raft_common.cuh", "raft_logic.cuh", "raft_row_logic.cuh", "raft_row.cuh")],
                 os.path.join(_ROOT, "include", "ra_engine.h")]
         if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
             subprocess.check_call(["make", "-C", _DIR], stdout=subprocess.DEVNULL)
@@ -50,6 +50,14 @@ class Emu(abi.Backend):
         f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(abi.RaFloodFaults)]
         ff = abi.RaFloodFaults(*faults)
         self._check(f(self._h, n_steps, cmds_per_step, election_permille, seed, C.byref(ff)), "flood_faults")
+
+    @staticmethod
+    def narrow_stats(reset: bool = True) -> dict:
+        """Process-wide: rows stepped by the 32-bit pass of the hot kernel's logic, records it refused (a field
+        >= 2^30), rows it left to the 64-bit general path because their sticky `wide` byte is set."""
+        arr = (C.c_ulonglong * 3)()
+        lib().ra_emu_narrow_stats(arr, 1 if reset else 0)
+        return dict(rows_narrow=arr[0], records_refused=arr[1], rows_wide=arr[2])
 
     def stall_histogram(self) -> dict:
         arr = (C.c_uint64 * 128)()

@@ -23,9 +23,9 @@ samp = sum(f(r[ix['# Samples']]) for r in data)
 print(blk["name"][:90], "SASS lines", len(data), "warp instructions", tot)
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-m = re.search(r"raft_(\w+)_kernel<\(int\)(\d+)(?:, \(int\)(\d+))?>", blk["name"])
-kind, mm, roles = m.group(1), m.group(2), m.group(3)
-want = "raft_%s_kernelILi%sE" % (kind, mm) + (("Li%sE" % roles) if roles else "")
+m = re.search(r"raft_(\w+)_kernel<\(int\)(\d+)(?:, \((int|bool)\)(\d+))?>", blk["name"])
+kind, mm, ty, roles = m.group(1), m.group(2), m.group(3), m.group(4)
+want = "raft_%s_kernelILi%sE" % (kind, mm) + ((("Lb%sE" if ty == "bool" else "Li%sE") % roles) if roles else "")
 a2l = {}
 for fn in os.listdir(tmp):
     if not (fn.endswith(".cubin") and fn.startswith("engine.")): continue
