@@ -30,8 +30,8 @@
                                             // <= 96 registers (no spills), 5 x 39 KB of shared memory
 #endif
 #ifndef MINB_NARROW
-#define MINB_NARROW 6                       // the narrow pass (32-bit index arithmetic) needs fewer registers
-#endif
+#define MINB_NARROW 5                       // the narrow pass (32-bit index arithmetic) needs ~84 registers: measured
+#endif                                      // 0.0796 ms at 5 CTAs/SM (no spill), 0.0816 at 6 (80 regs, 24 B), 0.0865 at 7 (72, 68 B)
 #define TILE_BYTES (RT * 64)
 #define RA_BAR_WORDS 64                       // barrier flag words behind mbox_cnt[b] (one per source shard)
 #define WARPS (CTA_T / 32)
@@ -81,7 +81,8 @@ template <int MM, bool NARROW = false>
 struct StepSmem {
     ulonglong2 stage[WARPS][NST][4 * RT];
     ulonglong2 peers_nm[PSTR * CTA_T / (NARROW ? 2 : 1)];   // [s][thread] {next_index, match_index}
-    u64 peers_cs[PSTR * CTA_T / (NARROW ? 2 : 1)];          // [s][thread] commit_index_sent (directly behind peers_nm)
+    // [s][thread] commit_index_sent, directly behind peers_nm (narrow: 4-byte cells, no column for the own slot)
+    u64 peers_cs[NARROW ? (PSTR > 1 ? PSTR - 1 : 1) * CTA_T / 2 : PSTR * CTA_T];
     u64 bars[WARPS][NST];
 };
 

@@ -379,18 +379,19 @@ __device__ __forceinline__ void peers_writeback(Member& m)
 
 #else
 // Narrow pass: the same per-thread columns hold 32-bit values -- nm[s][thread] 8 B {next_index, match_index},
-// cs[s][thread] 4 B commit_index_sent (half the shared memory: one more CTA per SM) -- filled from the low words of
+// cs[c][thread] 4 B commit_index_sent, c = s without the member's own slot (a member is not its own peer; the 512 bytes
+// are what lets a seventh CTA fit an SM) -- less than half the shared memory of the 64-bit columns -- filled from the low words of
 // the 64-bit cells in HBM (the high words are zero for a row this pass may touch) and written back zero-extended.
 // m.sp = shared-window address of nm[0][thread] (host emulation: pointer to this thread's scratch, same layout).
 #ifdef RA_HOST_EMU
 template <int MM> __device__ __forceinline__ u32* peer_nm_q(const Member& m, u32 s)
 { return reinterpret_cast<u32*>(m.sp) + 2 * (s * CTA_T); }
 template <int MM> __device__ __forceinline__ u32* peer_cs_q(const Member& m, u32 s)
-{ return reinterpret_cast<u32*>(m.sp) + 2 * (PSTR * CTA_T) + s * CTA_T; }
+{ return reinterpret_cast<u32*>(m.sp) + 2 * (PSTR * CTA_T) + (s - (s > m.slot ? 1u : 0u)) * CTA_T; }
 #else
 template <int MM> __device__ __forceinline__ u32 peer_nm_a(const Member& m, u32 s) { return m.sp + s * (CTA_T * 8u); }
 template <int MM> __device__ __forceinline__ u32 peer_cs_a(const Member& m, u32 s)
-{ return m.sp - threadIdx.x * 8u + PSTR * (CTA_T * 8u) + (s * CTA_T + threadIdx.x) * 4u; }
+{ return m.sp - threadIdx.x * 8u + PSTR * (CTA_T * 8u) + ((s - (s > m.slot ? 1u : 0u)) * CTA_T + threadIdx.x) * 4u; }
 template <int MM> __device__ __forceinline__ u32* peer_nm_q(const Member& m, u32 s)
 { return reinterpret_cast<u32*>(__cvta_shared_to_generic(peer_nm_a<MM>(m, s))); }
 template <int MM> __device__ __forceinline__ u32* peer_cs_q(const Member& m, u32 s)
@@ -413,7 +414,8 @@ __device__ __forceinline__ void peers_prefetch(Member& m)
         const u32 a = peer_nm_a<MM>(m, s);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(a), "l"(&g->x) : "memory");
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(a + 4u), "l"(&g->y) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(peer_cs_a<MM>(m, s)), "l"(&C.pcs[(size_t)s * C.rows + m.row]) : "memory");
+        if (s != m.slot)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(peer_cs_a<MM>(m, s)), "l"(&C.pcs[(size_t)s * C.rows + m.row]) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     m.pstate |= 2u;
@@ -436,7 +438,7 @@ __device__ __forceinline__ void peers_ensure(Member& m)
     for (u32 s = 0; s < NMEM(C); s++) {
         const ulonglong2 v = C.pnm[(size_t)s * C.rows + m.row];
         peer_nm_put<MM>(m, s, N(v.x), N(v.y));
-        peer_cs_put<MM>(m, s, N(C.pcs[(size_t)s * C.rows + m.row]));
+        if (s != m.slot) peer_cs_put<MM>(m, s, N(C.pcs[(size_t)s * C.rows + m.row]));
     }
     m.pstate |= 1u;
 }
@@ -445,7 +447,7 @@ __device__ __forceinline__ void peer_nm_set(Member& m, u32 s, ix_t next, ix_t ma
 { peer_nm_put<MM>(m, s, next, match); m.pstate |= 1u << (8 + s); }
 template <int MM>
 __device__ __forceinline__ void peer_cs_set(Member& m, u32 s, ix_t v)
-{ peer_cs_put<MM>(m, s, v); m.pstate |= 1u << (16 + s); }
+{ if (s == m.slot) return; peer_cs_put<MM>(m, s, v); m.pstate |= 1u << (16 + s); }    // (no column for the own slot)
 template <int MM>
 __device__ __forceinline__ void peers_writeback(Member& m)
 {
@@ -1034,7 +1036,8 @@ __device__ __forceinline__ bool make_pipelined_rpcs(Member& m, bool force) { ret
 template <int MM>
 __device__ __forceinline__ void make_rpcs(Member& m, bool all) { (void)rpc_pass<MM>(m, all ? RP_ALL : RP_STALE, false); }
 
-// initialise_peers/1 :3207-3215
+#if !RA_NARROW_PASS
+// initialise_peers/1 :3207-3215 (becoming leader: general path)
 template <int MM>
 __device__ __forceinline__ void initialise_peers(Member& m)
 {
@@ -1048,6 +1051,8 @@ __device__ __forceinline__ void initialise_peers(Member& m)
         MT_SET(m.meta, 32 + 3 * s, 3, RA_PEER_NORMAL);
     }
 }
+
+#endif
 
 // ---- elections --------------------------------------------------------------------------
 
