@@ -323,13 +323,20 @@ def run_engine(args):
             eng2 = _Multi()
         host_steps(args.settle)
         host_steps(min(args.warmup, 10))
-        d0 = eng2.counters()
-        barrier_sync(world, local)
-        st = host_steps(args.e2e_steps)
-        barrier_sync(world, local)
-        d1 = eng2.counters()
-        sec, ec, _ = reduce_max_sum(world, local, st["seconds"], d1["commits"] - d0["commits"], 0)
+        # three timed blocks of e2e_steps steps, the MEDIAN block is reported (a block is ~20 ms of wall time on 16
+        # shared host cores: one scheduling hiccup would otherwise decide the number); all three are listed
+        blocks = []
+        for _b in range(3):
+            d0 = eng2.counters()
+            barrier_sync(world, local)
+            st_b = host_steps(args.e2e_steps)
+            barrier_sync(world, local)
+            d1 = eng2.counters()
+            sec_b, ec_b, _ = reduce_max_sum(world, local, st_b["seconds"], d1["commits"] - d0["commits"], 0)
+            blocks.append((ec_b / sec_b, sec_b, ec_b, st_b))
+        _, sec, ec, st = sorted(blocks, key=lambda b: b[0])[1]
         e2e = {"value": ec / sec, "unit": "commits/s",
+               "blocks_commits_per_s": [round(b[0], 1) for b in blocks], "reported": "median of 3 blocks",
                "h2d_bytes_per_step": st["h2d_bytes"] // args.e2e_steps,
                "d2h_bytes_per_step": st["d2h_bytes"] // args.e2e_steps,
                "steps": args.e2e_steps, "ms_per_step": sec * 1e3 / args.e2e_steps,
