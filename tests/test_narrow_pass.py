@@ -151,3 +151,45 @@ def test_record_with_a_wide_field_goes_to_the_general_path_gpu():
     from ra_b200.engine import Engine
     outs = [_wide_record_script(b, 600) for b in (Oracle(600, 5), Engine(600, 5))]
     assert outs[0] == outs[1]
+
+
+# ---- closed-loop traces (loss, delay, duplicates, lagging fsync, elections, adversarial records) across the limit ----
+def _restarted(b, base, term):
+    rows = []
+    for r in range(b.n_rows):
+        s = abi.empty_row(r, b.n_groups, b.n_members)
+        abi.set_log(s, [], last_written=(base, term), snapshot=(base, term))
+        s.current_term = term
+        s.commit_index = s.last_applied = base
+        for p in range(b.n_members):
+            s.peers[p].next_index = base + 1
+        rows.append(s)
+    b.load_rows(rows)
+    return b
+
+
+TRACE_CROSSINGS = [
+    # groups, members, steps, seed, base index, term, knobs
+    (10, 5, 260, 5, LIM - 60, 3, dict(p_cmd=0.9, max_cmd=3)),                         # indexes cross in mid-run
+    (10, 5, 260, 9, 40, LIM - 3, dict(p_timeout=0.06)),                               # terms cross, many elections
+    (8, 5, 220, 13, LIM - 400, LIM - 2, dict(p_cmd=0.9, max_cmd=60, p_timeout=0.04, p_adversarial=0.05)),
+    (8, 5, 200, 21, (1 << 32) - 200, (1 << 32) - 2, dict(p_cmd=0.9, max_cmd=40, p_timeout=0.04)),   # 32-bit wrap territory
+    (6, 3, 200, 31, LIM - 50, LIM - 2, dict(p_drop=0.05, p_withhold_written=0.1)),    # runtime-M specialisation (64-bit pass)
+]
+
+
+@pytest.mark.parametrize("g,m,steps,seed,base,term,knobs", TRACE_CROSSINGS)
+def test_trace_parity_across_the_narrow_limit_emu(g, m, steps, seed, base, term, knobs):
+    import trace_gen
+    batches = trace_gen.generate(lambda gg, mm: _restarted(Oracle(gg, mm), base, term), g, m, steps, seed, **knobs)
+    Emu.narrow_stats()
+    want, want_rows, want_cnt = trace_gen.replay(_restarted(Oracle(g, m), base, term), batches)
+    got, got_rows, got_cnt = trace_gen.replay(_restarted(Emu(g, m), base, term), batches)
+    for t, (w, x) in enumerate(zip(want, got)):
+        assert x[0] == w[0], "RPC records differ at step %d" % t
+        assert x[1] == w[1], "host notes differ at step %d" % t
+    assert got_rows == want_rows
+    assert got_cnt == want_cnt
+    st = Emu.narrow_stats()
+    if m == 5 and base < LIM and term < LIM:
+        assert st["rows_narrow"] > 0 and st["rows_wide"] > 0      # the run started narrow and crossed

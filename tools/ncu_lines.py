@@ -26,6 +26,8 @@ subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capt
 m = re.search(r"raft_(\w+)_kernel<\(int\)(\d+)(?:, \((int|bool)\)(\d+))?>", blk["name"])
 kind, mm, ty, roles = m.group(1), m.group(2), m.group(3), m.group(4)
 want = "raft_%s_kernelILi%sE" % (kind, mm) + ((("Lb%sE" if ty == "bool" else "Li%sE") % roles) if roles else "")
+ns = re.search(r"(ra_narrow|ra_wide)::", blk["name"])          # the hot kernel exists once per index width
+if ns: want = "%d%s%d%s" % (len(ns.group(1)), ns.group(1), len("raft_%s_kernel" % kind), want)
 a2l = {}
 for fn in os.listdir(tmp):
     if not (fn.endswith(".cubin") and fn.startswith("engine.")): continue
