@@ -991,7 +991,14 @@ __device__ __forceinline__ bool rpc_pass(Member& m, u32 mode, bool force, const 
     const Cols& C = *m.C;
     if (mode == RP_PIPELINE && m.pipe_clean && !force) return false;
     ix_t next_log_idx = m.last_idx + 1;
+#if RA_NARROW_PASS
+    // (the configured limits are 32-bit unsigned; every quantity they are compared with or cut to is below 2^31 in
+    // this pass -- in_flight, the distance to last_index -- so clamping them to 2^31 - 1 changes no outcome)
+    sx_t max_pipe = (sx_t)(C.max_pipeline < 0x7fffffffu ? C.max_pipeline : 0x7fffffffu);
+    sx_t max_batch = (sx_t)(C.max_batch < 0x7fffffffu ? C.max_batch : 0x7fffffffu);
+#else
     sx_t max_pipe = C.max_pipeline, max_batch = C.max_batch;
+#endif
     bool more = false, clean = true;
     if (heartbeats && mode == RP_ALL)          // make_all_rpcs/1: CancelEffects ++ EffectsAER ++ EffectsHR
         for (u32 s = 0; s < NMEM(C); s++)
@@ -1003,12 +1010,12 @@ __device__ __forceinline__ bool rpc_pass(Member& m, u32 mode, bool force, const 
             !(heartbeats && mode == RP_ALL && MT_PSTATUS(m.meta, s) == RA_PEER_SNAPSHOT_BACKOFF)) continue;
         ixpair nm = peer_nm<MM>(m, s);
         ix_t cs = peer_cs<MM>(m, s);
-        sx_t bs = 1;
+        i64 bs = 1;                            // (64-bit in both passes: max_pipe - in_flight may pass 2^31)
         if (mode == RP_PIPELINE) {
             if (!(nm.x < next_log_idx || cs < m.commit)) continue;
             sx_t in_flight = (sx_t)nm.x - (sx_t)nm.y - 1;
             if (!(in_flight < max_pipe || force)) { clean = false; continue; }
-            bs = max_pipe - in_flight; if (max_batch < bs) bs = max_batch; if (bs < 1) bs = 1;
+            bs = (i64)max_pipe - (i64)in_flight; if ((i64)max_batch < bs) bs = max_batch; if (bs < 1) bs = 1;
         } else if (mode == RP_STALE) {
             bool stale = ((sx_t)nm.y < (sx_t)nm.x - 1) || (cs < m.commit);
             if (!stale) continue;

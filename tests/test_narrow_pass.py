@@ -193,3 +193,24 @@ def test_trace_parity_across_the_narrow_limit_emu(g, m, steps, seed, base, term,
     st = Emu.narrow_stats()
     if m == 5 and base < LIM and term < LIM:
         assert st["rows_narrow"] > 0 and st["rows_wide"] > 0      # the run started narrow and crossed
+
+
+LIMITS = [dict(max_pipeline_count=0xFFFFFFFF), dict(max_pipeline_count=0x80000000, max_aer_batch=0xFFFFFFFF),
+          dict(max_aer_batch=0x90000000), dict(max_pipeline_count=3, max_aer_batch=2)]
+
+
+@pytest.mark.parametrize("kw", LIMITS)
+def test_pipeline_limits_beyond_31_bits_emu(kw):
+    """max_pipeline_count / max_aer_batch are 32-bit unsigned configuration values; the 32-bit pass compares them with
+    signed differences of indexes (found by review: 'unlimited' = 0xFFFFFFFF read as -1 stopped every pipeline pass)."""
+    import trace_gen
+    o, e = Oracle(50, 5, route_on_device=True, **kw), Emu(50, 5, route_on_device=True, **kw)
+    for b in (o, e):
+        b.reset_empty()
+        b.step([abi.ev_simple(b.row_of(g, 0), abi.EV_ELECTION_TIMEOUT) for g in range(50)])
+    o.flood(60, 3, 20, seed=5, threads=1)
+    e.flood(60, 3, 20, seed=5)
+    assert e.counters() == o.counters() and _rows_bytes(e) == _rows_bytes(o) and o.counters()["commits"] > 0
+    # and a lossy closed-loop trace (failure replies move next_index below match_index + 1: in_flight < 0)
+    batches = trace_gen.generate(lambda gg, mm: Oracle(gg, mm, **kw), 8, 5, 200, 3, p_drop=0.08, p_cmd=0.9, max_cmd=9)
+    assert trace_gen.replay(Emu(8, 5, **kw), batches) == trace_gen.replay(Oracle(8, 5, **kw), batches)
