@@ -323,7 +323,7 @@ def run_engine(args):
             eng2 = _Multi()
         host_steps(args.settle)
         host_steps(min(args.warmup, 10))
-        # three timed blocks of e2e_steps steps, the MEDIAN block is reported (a block is ~20 ms of wall time on 16
+        # three timed blocks of e2e_steps steps, the MEDIAN block is reported (a block is ~70 ms of wall time on 16
         # shared host cores: one scheduling hiccup would otherwise decide the number); all three are listed
         blocks = []
         for _b in range(3):
@@ -682,7 +682,7 @@ def main():
     ap.add_argument("--permille", type=int, default=10, help="election timeouts per step per 1000 groups")
     ap.add_argument("--settle", type=int, default=40, help="untimed steps to elect leaders and fill the pipeline")
     ap.add_argument("--seed", type=int, default=0xA00)
-    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--e2e-engines", type=int, default=4,
                     help="e2e leg at N=1: partitions (engines holding disjoint groups) one host thread pipelines "
                          "through ra_engine_submit_host / ra_engine_collect")
