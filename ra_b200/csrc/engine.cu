@@ -561,7 +561,11 @@ struct ra_engine {
     int flood_barrier;                        // peer transport: ra_engine_flood ends every step with the device barrier
     void* allocs[96]; int n_allocs;
     IoSlot io[RA_IO_SLOTS]; u32 io_head, io_tail;   // FIFO: submit fills io[io_head % SLOTS], collect drains io_tail
-    int narrow;                               // the hot kernel computes on 32-bit indexes where it can (default; RA_STEP_WIDE=1: never)
+    // The hot kernel computes on 32-bit indexes where it can (ra_narrow::raft_step_kernel, exact for any input: rows
+    // that do not fit stall to the 64-bit general kernel) -- unless most rows do not fit, where the 64-bit hot kernel
+    // is the faster choice.  narrow_mode: 0 auto (bulk loads decide: ra_engine_load_rows), 1 always narrow
+    // (RA_STEP_WIDE=0), 2 never (RA_STEP_WIDE=1).  A performance choice only; results do not depend on it.
+    int narrow, narrow_mode;
     int out_pending;                          // the last collect ended in RA_E_CAPACITY: outputs wait in the row slots
     size_t pred_msgs, pred_notes, pred_ext;   // outputs of the last collected call (sizes the next DMA is enqueued with)
     int compact;                              // notes leave as 16-byte units (ra_engine_set_note_format)
@@ -644,6 +648,7 @@ extern "C" int ra_engine_reset_empty(ra_engine* e)
     CK(cudaMemsetAsync(e->C.counters, 0, RA_N_COUNTERS * sizeof(u64), e->stream));
     CK(cudaMemsetAsync(e->d_stall_cnt, 0, 4 * sizeof(u32), e->stream));
     e->cur = 0; e->step_no = 0; e->steps = 0; e->bar_epoch = 0;
+    e->narrow = e->narrow_mode != 2;
     if (e->C.routed) CK(cudaMemsetAsync(e->C.mbox_cnt[0] + e->C.rows, 0, RA_BAR_WORDS * sizeof(u64), e->stream));
     CK(cudaMemsetAsync(e->d_err, 0, 4 * sizeof(u32), e->stream));
     CK(cudaMemsetAsync(e->C.q_used, 0, 4 * sizeof(u32), e->stream));
@@ -666,7 +671,7 @@ extern "C" int ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out)
     ra_engine* e = (ra_engine*)calloc(1, sizeof(ra_engine));
     if (!e) return RA_E_NOMEM;
     e->cfg = *cfg;
-    { const char* w = getenv("RA_STEP_WIDE"); e->narrow = !(w && *w && *w != '0'); }
+    { const char* w = getenv("RA_STEP_WIDE"); e->narrow_mode = !(w && *w) ? 0 : (*w == '0' ? 1 : 2); e->narrow = e->narrow_mode != 2; }
     if (e->cfg.max_pipeline_count == 0) e->cfg.max_pipeline_count = 4096;
     if (e->cfg.max_aer_batch == 0) e->cfg.max_aer_batch = 128;
     int rc = RA_OK;
@@ -768,6 +773,11 @@ extern "C" int ra_engine_load_rows(ra_engine* e, const ra_row_state* rows, size_
     if (n == 0) return RA_OK;
     for (size_t i = 0; i < n; i++)
         if (rows[i].row >= e->C.rows || rows[i].n_members != e->C.members || !ra_row_state_valid(&rows[i])) return RA_E_INVAL;
+    if (e->narrow_mode == 0 && n * 2 >= e->C.rows) {            // a bulk load: which hot kernel suits this engine?
+        size_t wide = 0;
+        for (size_t i = 0; i < n; i++) wide += row_state_is_wide(rows[i], e->C.members) ? 1 : 0;
+        e->narrow = wide * 2 < n;
+    }
     CK(cudaSetDevice(e->cfg.device));
     int rc = ensure(e, &e->d_rows, &e->d_rows_cap, n); if (rc) return rc;
     CK(cudaMemcpyAsync(e->d_rows, rows, n * sizeof(ra_row_state), cudaMemcpyHostToDevice, e->stream));

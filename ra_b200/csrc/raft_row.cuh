@@ -23,6 +23,19 @@ __device__ __forceinline__ void reset_row(const Cols& C, const u32 r)
     if (C.routed) { C.mbox_cnt[0][r] = 0; C.mbox_cnt[1][r] = 0; }
 }
 
+// does any index / term of a row state reach 2^30 (RA_NARROW_LIMIT)?  (device: load_row; host: ra_engine_load_rows
+// counts them to choose the hot kernel)
+__host__ __device__ __forceinline__ bool row_state_is_wide(const ra_row_state& s, u32 members)
+{
+    u64 big = s.current_term | s.commit_index | s.last_index | s.last_term | s.last_written_index | s.last_written_term |
+              s.last_applied | s.snapshot_index | s.snapshot_term | s.pre_vote_token | s.token_counter | s.first_index |
+              s.cond_reply_term | s.cond_reply_next_index | s.cond_reply_last_index | s.cond_reply_last_term;
+    for (u32 p = 0; p < members && p < RA_MAX_MEMBERS; p++)
+        big |= s.peers[p].next_index | s.peers[p].match_index | s.peers[p].commit_index_sent;
+    for (u32 k = 0; k < s.n_runs && k < RA_MAX_RUNS; k++) big |= s.run_start[k] | s.run_term[k];
+    return big >= 0x40000000ull;
+}
+
 __device__ __forceinline__ void load_row(const Cols& C, const ra_row_state& s)
 {
     const u32 r = s.row;
@@ -58,14 +71,8 @@ __device__ __forceinline__ void load_row(const Cols& C, const ra_row_state& s)
     for (u32 k = 0; k < RA_MAX_RUNS; k++)
         st2(&C.run[(size_t)k * C.rows + r], k < s.n_runs ? s.run_start[k] : 0, k < s.n_runs ? s.run_term[k] : 0);
     C.lrs[r] = s.n_runs ? s.run_start[s.n_runs - 1] : 0;
-    {   // the sticky `wide` byte (raft_logic.cuh, narrow pass): does every index / term of the row fit below 2^30?
-        u64 big = s.current_term | s.commit_index | s.last_index | s.last_term | s.last_written_index | s.last_written_term |
-                  s.last_applied | s.snapshot_index | s.snapshot_term | s.pre_vote_token | s.token_counter | s.first_index |
-                  s.cond_reply_term | s.cond_reply_next_index | s.cond_reply_last_index | s.cond_reply_last_term;
-        for (u32 p = 0; p < C.members; p++) big |= s.peers[p].next_index | s.peers[p].match_index | s.peers[p].commit_index_sent;
-        for (u32 k = 0; k < s.n_runs && k < RA_MAX_RUNS; k++) big |= s.run_start[k] | s.run_term[k];
-        C.wf[r] = big >= RA_NARROW_LIMIT ? 1 : 0;
-    }
+    // the sticky `wide` byte (raft_logic.cuh, narrow pass): does every index / term of the row fit below 2^30?
+    C.wf[r] = row_state_is_wide(s, C.members) ? 1 : 0;
     C.qi[r] = 0; C.qa[r] = 0; C.wc[r] = 0;
     for (u32 p = 0; p < C.members; p++) C.pqi[(size_t)p * C.rows + r] = 0;
     C.loc_n[r] = 0;

@@ -30,7 +30,7 @@ struct ra_emu {
     int cur;
     u64 step_no, steps;
     void* allocs[96]; int n_allocs;
-    int narrow;                                       // RA_STEP_WIDE=1 in the environment: 64-bit pass only (as engine.cu)
+    int narrow, narrow_mode;                          // as engine.cu: RA_STEP_WIDE unset = auto, 0 = always narrow, 1 = never
     int out_pending;                                  // a step's outputs did not fit: they wait in the row slots
     int sub_busy, sub_rc; size_t sub_nm, sub_nn;      // the one "submitted" call (ra_engine_submit_host shim)
 };
@@ -59,6 +59,7 @@ extern "C" int ra_emu_reset_empty(ra_emu* e)
     memset(e->C.counters, 0, (8 + 8 * 16 + 8) * sizeof(u64));
     e->C.q_used[0] = 0;
     e->cur = 0; e->step_no = 0; e->steps = 0;
+    e->narrow = e->narrow_mode != 2;
     return RA_OK;
 }
 
@@ -70,7 +71,7 @@ extern "C" int ra_emu_create(const ra_engine_cfg* cfg, ra_emu** out)
     ra_emu* e = (ra_emu*)calloc(1, sizeof(ra_emu));
     if (!e) return RA_E_NOMEM;
     e->cfg = *cfg;
-    { const char* w = getenv("RA_STEP_WIDE"); e->narrow = !(w && *w && *w != '0'); }
+    { const char* w = getenv("RA_STEP_WIDE"); e->narrow_mode = !(w && *w) ? 0 : (*w == '0' ? 1 : 2); e->narrow = e->narrow_mode != 2; }
     if (e->cfg.max_pipeline_count == 0) e->cfg.max_pipeline_count = 4096;
     if (e->cfg.max_aer_batch == 0) e->cfg.max_aer_batch = 128;
     int rc = RA_OK;
@@ -123,6 +124,11 @@ extern "C" int ra_emu_load_rows(ra_emu* e, const ra_row_state* rows, size_t n)
     if (!e || (!rows && n)) return RA_E_INVAL;
     for (size_t i = 0; i < n; i++)
         if (rows[i].row >= e->C.rows || rows[i].n_members != e->C.members || !ra_row_state_valid(&rows[i])) return RA_E_INVAL;
+    if (e->narrow_mode == 0 && n * 2 >= e->C.rows) {
+        size_t wide = 0;
+        for (size_t i = 0; i < n; i++) wide += row_state_is_wide(rows[i], e->C.members) ? 1 : 0;
+        e->narrow = wide * 2 < n;
+    }
     for (size_t i = 0; i < n; i++) load_row(e->C, rows[i]);
     return RA_OK;
 }

@@ -72,8 +72,15 @@ CROSSINGS = [
 ]
 
 
+@pytest.mark.parametrize("force_narrow", [False, True])
 @pytest.mark.parametrize("base,term,steps,cmds,permille", CROSSINGS)
-def test_flood_across_the_narrow_limit_emu(base, term, steps, cmds, permille):
+def test_flood_across_the_narrow_limit_emu(base, term, steps, cmds, permille, force_narrow, monkeypatch):
+    """force_narrow: RA_STEP_WIDE=0, the 32-bit hot kernel whatever was loaded (every wide row goes through the general
+    path); otherwise the engine picks the 64-bit hot kernel for a bulk load most of whose rows are wide."""
+    if force_narrow:
+        monkeypatch.setenv("RA_STEP_WIDE", "0")
+    else:
+        monkeypatch.delenv("RA_STEP_WIDE", raising=False)
     Emu.narrow_stats()
     rows = _flood_pair(Oracle(120, 5, route_on_device=True), Emu(120, 5, route_on_device=True), base, term, steps, cmds, permille)
     st = Emu.narrow_stats()
@@ -81,7 +88,7 @@ def test_flood_across_the_narrow_limit_emu(base, term, steps, cmds, permille):
     if base < LIM - 1000 and term < LIM - 1000:
         assert st["rows_narrow"] > 0 and st["rows_wide"] == 0 and top < LIM
     elif base >= LIM or term >= LIM:
-        assert st["rows_narrow"] == 0 and st["rows_wide"] > 0
+        assert st["rows_narrow"] == 0 and (st["rows_wide"] > 0) == force_narrow     # auto: the 64-bit hot kernel
     else:
         assert st["rows_narrow"] > 0 and st["rows_wide"] > 0 and top >= LIM      # the run did cross
 
@@ -89,7 +96,7 @@ def test_flood_across_the_narrow_limit_emu(base, term, steps, cmds, permille):
 def test_narrow_and_wide_pass_agree_emu(monkeypatch):
     """RA_STEP_WIDE=1 (64-bit hot kernel only) and the default produce the same rows, records and notes."""
     outs = []
-    for wide in ("0", "1"):
+    for wide in ("0", "1"):                                 # always the 32-bit hot kernel / never
         monkeypatch.setenv("RA_STEP_WIDE", wide)
         Emu.narrow_stats()
         e = Emu(40, 5)
