@@ -299,7 +299,12 @@ enum ra_status {
 
 /* Lifecycle.  The engine owns the HBM Struct-of-Arrays; callers own all host buffers and
    the engine never keeps a host pointer past a call.  One engine per GPU; calls on one
-   engine must be serialised (as gen_statem serialises one member's mailbox).          */
+   engine must be serialised (as gen_statem serialises one member's mailbox).
+   Index width: every index and term of this ABI is 64 bits wide and is evaluated as such.  Internally the hot
+   kernel keeps a member's values in 32-bit registers while ALL of them are below 2^30 and hands a member (or a
+   record) that has outgrown that to the 64-bit kernels -- results are bit-identical either way.  Environment, read
+   at create time, performance only: RA_STEP_WIDE=1 never uses the 32-bit hot kernel, RA_STEP_WIDE=0 always does,
+   unset = a bulk ra_engine_load_rows (>= half the rows) decides by what it loads.               */
 int  ra_engine_create(const ra_engine_cfg* cfg, ra_engine** out);
 void ra_engine_destroy(ra_engine* e);
 int  ra_engine_get_cfg(ra_engine* e, ra_engine_cfg* out);
