@@ -1,3 +1,9 @@
+// raft_logic.cuh -- the member-level Raft logic (records, the per-thread member view, the log view, notes, emit_msg,
+// quorum, the leader's RPC passes, elections, the general clauses of ra_server:handle_<state>/2 and the steady-state
+// fast paths; reference lines are cited at each function, the map is at the top of raft_common.cuh).
+// NO include guard: raft_step.cuh includes this file once per index width, inside namespace ra_wide (RA_NARROW_PASS 0)
+// and inside namespace ra_narrow (RA_NARROW_PASS 1; the general clauses are left out there).
+//
 // ---- index width of this pass (raft_step.cuh) ---------------------------------------------------------
 // narrow pass: every index / term lives in ONE 32-bit register.  It is exact because the hot kernel runs a row's
 // events through it only while (a) the row's sticky `wide` byte (Cols::wf) is clear -- which, by induction over
