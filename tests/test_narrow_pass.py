@@ -17,6 +17,12 @@ from ra_b200 import abi
 LIM = 1 << 30
 
 
+@pytest.fixture(autouse=True)
+def _auto_mode(monkeypatch):
+    """These tests assert which pass ran: start from the default (RA_STEP_WIDE unset), whatever the ambient environment."""
+    monkeypatch.delenv("RA_STEP_WIDE", raising=False)
+
+
 def _rows_bytes(b):
     arr = (abi.RaRowState * b.n_rows)()
     for i in range(b.n_rows):
